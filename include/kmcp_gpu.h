@@ -1,0 +1,204 @@
+/*
+ * kmcp_gpu.h — C ABI of libkmcp_gpu.so, the B200 (sm_100a) implementation of the `kmcp search` hot path.
+ *
+ * The reference (shenwei356/kmcp v0.9.5) is pure Go and has no FFI; the seam this library occupies is the
+ * search-engine object used by kmcp/cmd/search.go.  Every entry point below names the
+ * reference interface it replaces (paths relative to /root/reference/kmcp/cmd/):
+ *   U: = util-db-search.go   S: = search.go   X: = index/serialization.go   H: = util-hash.go   F: = util-fpr.go
+ * INTEGRATION.md shows the cgo binding a kmcp maintainer would add on top of these symbols.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative KMCPG_E*
+ * code and never aborts; kmcpg_last_error() gives the message.  Inputs are caller-owned and not retained
+ * after the call returns (cgo pointer rule); outputs are library-owned until the matching free call.
+ * There is NO CPU fallback anywhere: without a CUDA device kmcpg_create fails with KMCPG_ECUDA.
+ */
+#ifndef KMCP_GPU_H
+#define KMCP_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMCPG_ABI_VERSION 1
+
+enum {
+    KMCPG_OK = 0,
+    KMCPG_EINVAL = -1,      /* bad argument */
+    KMCPG_EIO = -2,         /* file missing / truncated */
+    KMCPG_EFORMAT = -3,     /* X:38-56 ErrInvalidIndexFileFormat / ErrVersionMismatch / incompatible blocks (U:689-695) */
+    KMCPG_ECUDA = -4,       /* CUDA runtime error, or no device */
+    KMCPG_ENOMEM = -5,      /* HBM or host allocation failed */
+    KMCPG_EUNSUPPORTED = -6
+};
+
+typedef struct kmcpg_ctx kmcpg_ctx;
+
+/* ---- lifecycle: replaces NewUnikIndexDBSearchEngine / sg.Close (U:222, U:591) ------------------------- */
+/* One context drives ONE device (one process per GPU, or several contexts in one process). */
+int kmcpg_create(int device, kmcpg_ctx **out);
+int kmcpg_close(kmcpg_ctx *ctx);
+const char *kmcpg_last_error(const kmcpg_ctx *ctx); /* ctx may be NULL: error of the failed kmcpg_create */
+int kmcpg_abi_version(void);
+/* run all work of this context on the caller's CUDA stream (e.g. torch's current stream) so the caller's
+ * events bracket it; NULL restores the context's own stream */
+int kmcpg_set_stream(kmcpg_ctx *ctx, void *cuda_stream);
+
+/* ---- database: replaces NewUnikIndexDB + NewUnikIndex + index.NewReader (U:648-760, U:1196-1280, X:372-593) */
+typedef struct {
+    int32_t shard_rank;   /* this context keeps the blocks assigned to shard_rank of shard_world (greedy by bytes, */
+    int32_t shard_world;  /* largest first); 0/1 = keep everything.  Target numbering stays global in every shard. */
+    int64_t max_resident_bytes; /* 0 = no limit; otherwise fail with KMCPG_ENOMEM instead of oversubscribing HBM */
+} kmcpg_db_opts;
+
+typedef struct {
+    int32_t n_ks; int32_t ks[8];        /* descending, U:752-759 */
+    int32_t canonical, num_hashes;
+    int32_t scaled; uint32_t scale;
+    int32_t minimizer; uint32_t minimizer_w;
+    int32_t syncmer; uint32_t syncmer_s;
+    double fpr;                          /* __db.yml fpr: p of one k-mer (F:140) */
+    int32_t n_blocks;                    /* all blocks of the DB */
+    int32_t n_resident_blocks;           /* blocks in this context's HBM */
+    int64_t n_targets;                   /* all targets of the DB */
+    int64_t sum_row_bytes;               /* Σ numRowBytes over RESIDENT blocks: algorithmic bytes per probed row set */
+    int64_t resident_bytes;              /* HBM bytes of the re-pitched resident rows */
+    int64_t disk_bytes;                  /* Σ numSigs·numRowBytes over resident blocks */
+} kmcpg_db_info_t;
+
+typedef struct {
+    const char *name;        /* library-owned, valid until kmcpg_close */
+    uint32_t index;          /* chunkIdx | nChunks<<16 (I:1096, S:532-533) */
+    uint64_t genome_size;
+    uint64_t n_kmers;        /* Sizes[t] */
+    int32_t block, col;
+    int32_t resident;        /* 1 if the target's block is in this context */
+} kmcpg_target_t;
+
+/* dir = the directory holding __db.yml (normally <db>/R001, S:299-324) */
+int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts);
+int kmcpg_db_info(const kmcpg_ctx *ctx, kmcpg_db_info_t *out);
+int kmcpg_target(const kmcpg_ctx *ctx, int64_t global_target, kmcpg_target_t *out);
+
+/* ---- the hot path: replaces UnikIndexDB.handleQuery k-mer generation + every UnikIndex worker `fn`
+ *      (U:763-941 and U:6613-7741) for a whole batch of queries ------------------------------------------- */
+typedef struct {
+    int32_t min_query_len;    /* -m, SearchOptions.MinQLen (U:778) */
+    int32_t min_matched;      /* -c, MinMatched (U:854, U:7466) */
+    int32_t dedup_threshold;  /* -u, DeduplicateThreshold (U:874) */
+    int32_t paired;           /* 1: sequences 2q and 2q+1 are Seq / Seq2 of query q (U:797-805) */
+    double min_query_cov;     /* -t, MinQueryCov: count must be > n*t in float64 (U:6625, U:7469) */
+    int32_t k;                /* 0 = largest k of the DB; multi-k DBs are driven by the host engine (U:763) */
+    int32_t mate_select;      /* 0 both mates, 1 Seq only, 2 Seq2 only (--try-se retries, U:826-842) */
+} kmcpg_search_params;
+
+typedef struct {
+    uint32_t query;   /* index within the batch */
+    uint32_t target;  /* global target index */
+    uint32_t count;   /* matched k-mers (Match.NumKmers) */
+} kmcpg_hit;
+
+typedef struct {
+    uint32_t n_queries;
+    uint64_t n_hits;
+    int32_t *n_kmers;      /* per query: k-mers probed after dedup (QueryResult.NumKmers); 0 = skipped (U:778-786, 854-869) */
+    int32_t *query_len;    /* per query (QueryResult.QueryLen) */
+    kmcpg_hit *hits;       /* every (query,target) with count >= min_matched and count > n*min_query_cov, sorted by (query,target) */
+    /* device-side timing of this call (CUDA events on the library's streams), milliseconds */
+    float ms_hash;    /* slot scan + hash (+ sort/unique) + per-query verdict */
+    float ms_locs;    /* code → row index kernels */
+    float ms_probe;   /* Σ durations of the probe kernel launches ONLY (events bracketing each launch) */
+    float ms_total;   /* host wall clock of the call */
+    uint32_t probe_launches;
+    uint64_t probe_row_bytes;   /* algorithmic bytes the probe kernels had to fetch: Σ_q n_q · h · Σ_b numRowBytes_b */
+    uint32_t kernel_launches;   /* kernels of this library launched for the call */
+    void *_priv;
+} kmcpg_hits;
+
+void kmcpg_default_params(kmcpg_search_params *p);
+/* host buffers: seq = concatenated ASCII, off = n_seqs+1 offsets into seq */
+int kmcpg_search_batch(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *seq, const uint64_t *off,
+                       uint32_t n_seqs, kmcpg_hits *out);
+/* same with seq/off already in this device's HBM (e.g. a batch that arrived by ncclBroadcast) */
+int kmcpg_search_batch_device(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *d_seq,
+                              const uint64_t *d_off, uint32_t n_seqs, uint64_t seq_bytes, kmcpg_hits *out);
+void kmcpg_free_hits(kmcpg_hits *h);
+
+/* pinned host memory for batch buffers (so the H2D copy of kmcpg_search_batch runs at full PCIe speed) */
+int kmcpg_host_alloc(void **p, size_t bytes);
+int kmcpg_host_free(void *p);
+/* device memory helpers for callers without a CUDA binding (tests, bench, NCCL staging) */
+int kmcpg_device_alloc(kmcpg_ctx *ctx, void **p, size_t bytes);
+int kmcpg_device_free(kmcpg_ctx *ctx, void *p);
+int kmcpg_memcpy_h2d(kmcpg_ctx *ctx, void *d, const void *h, size_t bytes);
+int kmcpg_memcpy_d2h(kmcpg_ctx *ctx, void *h, const void *d, size_t bytes);
+
+/* ---- stage-level entry points (each replaces one reference function; used by the parity tests) --------- */
+/* UnikIndexDB.generateKmers (U:1037-1107) for a batch: codes of sequence i are out_codes[out_off[i] .. out_off[i+1]) */
+typedef struct {
+    int32_t k, canonical, scaled; uint32_t scale;
+    int32_t minimizer; uint32_t minimizer_w;
+    int32_t syncmer; uint32_t syncmer_s;
+} kmcpg_sketch_params;
+int kmcpg_generate_kmers(kmcpg_ctx *ctx, const kmcpg_sketch_params *sp, const uint8_t *seq, const uint64_t *off,
+                         uint32_t n_seqs, uint64_t **out_codes, uint64_t **out_off);
+/* one UnikIndex worker pass without thresholds (U:6613-7408): dense counts[n_targets] of one code list
+ * against all resident blocks (non-resident targets get 0); dedup is NOT applied */
+int kmcpg_count_codes(kmcpg_ctx *ctx, const uint64_t *codes, uint64_t n, uint32_t *counts);
+void kmcpg_free(void *p);
+
+/* ---- host engine: C++ mirror of UnikIndexDBSearchEngine result handling (U:260-345, U:7466-7491) -------- */
+typedef struct {
+    int32_t min_query_len, min_matched, dedup_threshold;
+    double min_query_cov, min_target_cov, max_fpr;
+    int32_t sort_by;        /* 0 qcov, 1 tcov, 2 jacc (S:1093) */
+    int32_t do_not_sort;    /* -S */
+    int32_t top_n_scores;   /* -n */
+    int32_t try_se;         /* --try-se */
+    int32_t paired;
+    int32_t threads;        /* host threads for the post-filter; <=0: all */
+} kmcpg_engine_opts;
+
+typedef struct {
+    uint32_t query, target, count, _pad;
+    double fpr, qcov, tcov, jacc;      /* Match.FPR/QCov/TCov/JaccardIndex (U:83-93) */
+} kmcpg_match;
+
+typedef struct {
+    uint32_t n_queries;
+    uint64_t n_matches;
+    int32_t *query_len, *n_kmers, *k_used;   /* per query */
+    uint64_t *match_off;                     /* n_queries+1 */
+    kmcpg_match *matches;                    /* per query in output order (sorted / truncated as U:273-311) */
+    float ms_gpu_total;
+    uint64_t probe_row_bytes;
+    uint32_t kernel_launches;
+    void *_priv;
+} kmcpg_results;
+
+void kmcpg_default_engine_opts(kmcpg_engine_opts *o);
+int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off,
+                        uint32_t n_seqs, kmcpg_results *out);
+void kmcpg_free_results(kmcpg_results *r);
+/* QueryFPRWithCacheWithConstantFPR's underlying function (F:32-50, F:140-193), bit-exact with Go */
+double kmcpg_query_fpr(int n, int c, double p);
+
+/* ---- synthetic workloads (bench/test tooling; seeded pure functions, mirrored in oracle/oracle.py) ------ */
+/* d_out[i*read_len .. ) = read (first+i) of the seeded read set; returns device pointers */
+int kmcpg_synth_reads(kmcpg_ctx *ctx, uint64_t seed, uint64_t first, uint32_t n_reads, uint32_t read_len,
+                      uint64_t genome_seed, uint32_t n_genomes, uint32_t genome_len, uint8_t *d_out);
+/* build an in-HBM DB from seeded random genomes exactly as `kmcp compute`+`kmcp index` would (C:577-826,
+ * I:667-1309, non-circular split mode), without touching disk; replaces any open DB of ctx */
+typedef struct {
+    uint64_t genome_seed; uint32_t n_genomes; uint32_t genome_len;
+    int32_t k; int32_t n_chunks; int32_t overlap;
+    int32_t num_hashes; double fpr; int32_t block_size; /* targets per block */
+} kmcpg_synth_db;
+int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec);
+/* dump resident block b in .uniki format (X:153-304), for parity checks of the device builder */
+int kmcpg_write_block(kmcpg_ctx *ctx, int resident_block, const char *path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

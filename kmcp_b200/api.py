@@ -1,0 +1,373 @@
+"""ctypes binding of libkmcp_gpu.so (the C ABI in include/kmcp_gpu.h).
+
+This module is plumbing for tests and bench.py: the product is the shared library.  There is no Python or
+CPU implementation of the search path here — if the library is missing, or no CUDA device is present,
+every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkmcp_gpu.so")
+
+KMCPG_OK, KMCPG_EINVAL, KMCPG_EIO, KMCPG_EFORMAT, KMCPG_ECUDA, KMCPG_ENOMEM, KMCPG_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+
+class KmcpGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libkmcp_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class DbOpts(C.Structure):
+    _fields_ = [("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("max_resident_bytes", C.c_int64)]
+
+
+class DbInfo(C.Structure):
+    _fields_ = [("n_ks", C.c_int32), ("ks", C.c_int32 * 8), ("canonical", C.c_int32), ("num_hashes", C.c_int32),
+                ("scaled", C.c_int32), ("scale", C.c_uint32), ("minimizer", C.c_int32), ("minimizer_w", C.c_uint32),
+                ("syncmer", C.c_int32), ("syncmer_s", C.c_uint32), ("fpr", C.c_double), ("n_blocks", C.c_int32),
+                ("n_resident_blocks", C.c_int32), ("n_targets", C.c_int64), ("sum_row_bytes", C.c_int64),
+                ("resident_bytes", C.c_int64), ("disk_bytes", C.c_int64)]
+
+
+class TargetInfo(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("index", C.c_uint32), ("genome_size", C.c_uint64), ("n_kmers", C.c_uint64),
+                ("block", C.c_int32), ("col", C.c_int32), ("resident", C.c_int32)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("min_query_len", C.c_int32), ("min_matched", C.c_int32), ("dedup_threshold", C.c_int32),
+                ("paired", C.c_int32), ("min_query_cov", C.c_double), ("k", C.c_int32), ("mate_select", C.c_int32)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("target", C.c_uint32), ("count", C.c_uint32)]
+
+
+HIT_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("count", "<u4")])
+
+
+class Hits(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("n_hits", C.c_uint64), ("n_kmers", C.POINTER(C.c_int32)),
+                ("query_len", C.POINTER(C.c_int32)), ("hits", C.POINTER(Hit)), ("ms_hash", C.c_float), ("ms_locs", C.c_float),
+                ("ms_probe", C.c_float), ("ms_total", C.c_float), ("probe_launches", C.c_uint32), ("probe_row_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint32), ("_priv", C.c_void_p)]
+
+
+class SketchParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("canonical", C.c_int32), ("scaled", C.c_int32), ("scale", C.c_uint32),
+                ("minimizer", C.c_int32), ("minimizer_w", C.c_uint32), ("syncmer", C.c_int32), ("syncmer_s", C.c_uint32)]
+
+
+class EngineOpts(C.Structure):
+    _fields_ = [("min_query_len", C.c_int32), ("min_matched", C.c_int32), ("dedup_threshold", C.c_int32),
+                ("min_query_cov", C.c_double), ("min_target_cov", C.c_double), ("max_fpr", C.c_double),
+                ("sort_by", C.c_int32), ("do_not_sort", C.c_int32), ("top_n_scores", C.c_int32), ("try_se", C.c_int32),
+                ("paired", C.c_int32), ("threads", C.c_int32)]
+
+
+class Match(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("target", C.c_uint32), ("count", C.c_uint32), ("_pad", C.c_uint32),
+                ("fpr", C.c_double), ("qcov", C.c_double), ("tcov", C.c_double), ("jacc", C.c_double)]
+
+
+MATCH_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("count", "<u4"), ("_pad", "<u4"),
+                        ("fpr", "<f8"), ("qcov", "<f8"), ("tcov", "<f8"), ("jacc", "<f8")])
+
+
+class Results(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("n_matches", C.c_uint64), ("query_len", C.POINTER(C.c_int32)),
+                ("n_kmers", C.POINTER(C.c_int32)), ("k_used", C.POINTER(C.c_int32)), ("match_off", C.POINTER(C.c_uint64)),
+                ("matches", C.POINTER(Match)), ("ms_gpu_total", C.c_float), ("probe_row_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint32), ("_priv", C.c_void_p)]
+
+
+class SynthDb(C.Structure):
+    _fields_ = [("genome_seed", C.c_uint64), ("n_genomes", C.c_uint32), ("genome_len", C.c_uint32), ("k", C.c_int32),
+                ("n_chunks", C.c_int32), ("overlap", C.c_int32), ("num_hashes", C.c_int32), ("fpr", C.c_double),
+                ("block_size", C.c_int32)]
+
+
+# every symbol include/kmcp_gpu.h declares (checked by tests/test_abi.py without a GPU)
+ABI_SYMBOLS = [
+    "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
+    "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_free_hits", "kmcpg_host_alloc",
+    "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
+    "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search",
+    "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_synth_reads", "kmcpg_build_synth_db", "kmcpg_write_block",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libkmcp_gpu.so; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("kmcp_b200/libkmcp_gpu.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C kmcp_b200/csrc). The search path has no CPU or Python fallback.")
+    L = C.CDLL(LIB_PATH)
+    u8p, u64p, vp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_void_p
+    L.kmcpg_abi_version.restype = C.c_int
+    L.kmcpg_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.kmcpg_close.argtypes = [vp]
+    L.kmcpg_set_stream.argtypes = [vp, vp]
+    L.kmcpg_last_error.restype = C.c_char_p
+    L.kmcpg_last_error.argtypes = [vp]
+    L.kmcpg_open_db.argtypes = [vp, C.c_char_p, C.POINTER(DbOpts)]
+    L.kmcpg_db_info.argtypes = [vp, C.POINTER(DbInfo)]
+    L.kmcpg_target.argtypes = [vp, C.c_int64, C.POINTER(TargetInfo)]
+    L.kmcpg_default_params.argtypes = [C.POINTER(SearchParams)]
+    L.kmcpg_default_params.restype = None
+    L.kmcpg_search_batch.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, C.POINTER(Hits)]
+    L.kmcpg_search_batch_device.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, C.c_uint64, C.POINTER(Hits)]
+    L.kmcpg_free_hits.argtypes = [C.POINTER(Hits)]
+    L.kmcpg_free_hits.restype = None
+    L.kmcpg_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.kmcpg_host_free.argtypes = [vp]
+    L.kmcpg_device_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
+    L.kmcpg_device_free.argtypes = [vp, vp]
+    L.kmcpg_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.kmcpg_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.kmcpg_generate_kmers.argtypes = [vp, C.POINTER(SketchParams), vp, vp, C.c_uint32, C.POINTER(u64p), C.POINTER(u64p)]
+    L.kmcpg_count_codes.argtypes = [vp, vp, C.c_uint64, vp]
+    L.kmcpg_free.argtypes = [vp]
+    L.kmcpg_free.restype = None
+    L.kmcpg_default_engine_opts.argtypes = [C.POINTER(EngineOpts)]
+    L.kmcpg_default_engine_opts.restype = None
+    L.kmcpg_engine_search.argtypes = [vp, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
+    L.kmcpg_free_results.argtypes = [C.POINTER(Results)]
+    L.kmcpg_free_results.restype = None
+    L.kmcpg_query_fpr.restype = C.c_double
+    L.kmcpg_query_fpr.argtypes = [C.c_int, C.c_int, C.c_double]
+    L.kmcpg_synth_reads.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, vp]
+    L.kmcpg_build_synth_db.argtypes = [vp, C.POINTER(SynthDb)]
+    L.kmcpg_write_block.argtypes = [vp, C.c_int, C.c_char_p]
+    _lib = L
+    return L
+
+
+def pack_seqs(seqs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    joined = b"".join(seqs)
+    buf = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(1, np.uint8)
+    return buf, off
+
+
+@dataclass
+class BatchHits:
+    n_kmers: np.ndarray
+    query_len: np.ndarray
+    hits: np.ndarray            # HIT_DTYPE sorted by (query, target)
+    ms_hash: float
+    ms_locs: float
+    ms_probe: float
+    ms_total: float
+    probe_launches: int
+    probe_row_bytes: int
+    kernel_launches: int
+
+
+@dataclass
+class EngineResults:
+    query_len: np.ndarray
+    n_kmers: np.ndarray
+    k_used: np.ndarray
+    match_off: np.ndarray
+    matches: np.ndarray         # MATCH_DTYPE
+    ms_gpu_total: float
+    probe_row_bytes: int
+    kernel_launches: int
+
+
+def _np_from(ptr, n, ctype_size, dtype):
+    if not n:
+        return np.zeros(0, dtype)
+    return np.frombuffer(C.string_at(ptr, int(n) * ctype_size), dtype=dtype).copy()
+
+
+class Context:
+    """One GPU context == one kmcpg_ctx (one device)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load()
+        h = C.c_void_p()
+        rc = self._L.kmcpg_create(device, C.byref(h))
+        if rc:
+            raise KmcpGpuError(rc, self._L.kmcpg_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def _check(self, rc: int):
+        if rc:
+            raise KmcpGpuError(rc, self._L.kmcpg_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kmcpg_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int = 0):
+        self._check(self._L.kmcpg_set_stream(self._h, cuda_stream or None))
+
+    # ---- database ----
+    def open_db(self, r001_dir: str, shard_rank: int = 0, shard_world: int = 1, max_resident_bytes: int = 0):
+        o = DbOpts(shard_rank, shard_world, max_resident_bytes)
+        self._check(self._L.kmcpg_open_db(self._h, r001_dir.encode(), C.byref(o)))
+
+    def build_synth_db(self, genome_seed: int, n_genomes: int, genome_len: int, k: int = 21, n_chunks: int = 10,
+                       overlap: int = 150, num_hashes: int = 1, fpr: float = 0.3, block_size: int = 0):
+        s = SynthDb(genome_seed, n_genomes, genome_len, k, n_chunks, overlap, num_hashes, fpr, block_size)
+        self._check(self._L.kmcpg_build_synth_db(self._h, C.byref(s)))
+
+    def write_block(self, resident_block: int, path: str):
+        self._check(self._L.kmcpg_write_block(self._h, resident_block, path.encode()))
+
+    def db_info(self) -> DbInfo:
+        i = DbInfo()
+        self._check(self._L.kmcpg_db_info(self._h, C.byref(i)))
+        return i
+
+    def target(self, g: int) -> TargetInfo:
+        t = TargetInfo()
+        self._check(self._L.kmcpg_target(self._h, g, C.byref(t)))
+        return t
+
+    # ---- hot path ----
+    def default_params(self, **kw) -> SearchParams:
+        p = SearchParams()
+        self._L.kmcpg_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def _take_hits(self, h: Hits) -> BatchHits:
+        out = BatchHits(_np_from(h.n_kmers, h.n_queries, 4, np.int32), _np_from(h.query_len, h.n_queries, 4, np.int32),
+                        _np_from(h.hits, h.n_hits, C.sizeof(Hit), HIT_DTYPE), h.ms_hash, h.ms_locs, h.ms_probe, h.ms_total,
+                        int(h.probe_launches), int(h.probe_row_bytes), int(h.kernel_launches))
+        self._L.kmcpg_free_hits(C.byref(h))
+        return out
+
+    def search_batch(self, buf: np.ndarray, off: np.ndarray, params: Optional[SearchParams] = None) -> BatchHits:
+        p = params or self.default_params()
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        h = Hits()
+        self._check(self._L.kmcpg_search_batch(self._h, C.byref(p), buf.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(h)))
+        return self._take_hits(h)
+
+    def search_batch_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, params: SearchParams, device: bool, seq_bytes: int = 0) -> BatchHits:
+        """raw-pointer form (pinned host buffers or device buffers owned by the caller)"""
+        h = Hits()
+        if device:
+            self._check(self._L.kmcpg_search_batch_device(self._h, C.byref(params), seq_ptr, off_ptr, n_seqs, seq_bytes, C.byref(h)))
+        else:
+            self._check(self._L.kmcpg_search_batch(self._h, C.byref(params), seq_ptr, off_ptr, n_seqs, C.byref(h)))
+        return self._take_hits(h)
+
+    def generate_kmers(self, buf: np.ndarray, off: np.ndarray, sp: SketchParams) -> Tuple[np.ndarray, np.ndarray]:
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = len(off) - 1
+        pc, po = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+        self._check(self._L.kmcpg_generate_kmers(self._h, C.byref(sp), buf.ctypes.data, off.ctypes.data, n, C.byref(pc), C.byref(po)))
+        oo = _np_from(po, n + 1, 8, np.uint64)
+        cc = _np_from(pc, int(oo[-1]) if n else 0, 8, np.uint64)
+        self._L.kmcpg_free(pc)
+        self._L.kmcpg_free(po)
+        return cc, oo
+
+    def count_codes(self, codes: np.ndarray) -> np.ndarray:
+        c = np.ascontiguousarray(codes, dtype=np.uint64)
+        out = np.zeros(self.db_info().n_targets, dtype=np.uint32)
+        self._check(self._L.kmcpg_count_codes(self._h, c.ctypes.data if c.size else None, c.size, out.ctypes.data))
+        return out
+
+    # ---- engine ----
+    def default_engine_opts(self, **kw) -> EngineOpts:
+        o = EngineOpts()
+        self._L.kmcpg_default_engine_opts(C.byref(o))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def engine_search(self, buf: np.ndarray, off: np.ndarray, opts: Optional[EngineOpts] = None) -> EngineResults:
+        o = opts or self.default_engine_opts()
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o)
+
+    def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts) -> EngineResults:
+        r = Results()
+        self._check(self._L.kmcpg_engine_search(self._h, C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r)))
+        nq = r.n_queries
+        out = EngineResults(_np_from(r.query_len, nq, 4, np.int32), _np_from(r.n_kmers, nq, 4, np.int32),
+                            _np_from(r.k_used, nq, 4, np.int32), _np_from(r.match_off, nq + 1, 8, np.uint64),
+                            _np_from(r.matches, r.n_matches, C.sizeof(Match), MATCH_DTYPE), r.ms_gpu_total,
+                            int(r.probe_row_bytes), int(r.kernel_launches))
+        self._L.kmcpg_free_results(C.byref(r))
+        return out
+
+    # ---- memory helpers ----
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._L.kmcpg_device_alloc(self._h, C.byref(p), nbytes))
+        return p.value
+
+    def device_free(self, ptr: int):
+        self._check(self._L.kmcpg_device_free(self._h, ptr))
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        a = np.ascontiguousarray(arr)
+        self._check(self._L.kmcpg_memcpy_h2d(self._h, dptr, a.ctypes.data, a.nbytes))
+
+    def d2h(self, dptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        self._check(self._L.kmcpg_memcpy_d2h(self._h, out.ctypes.data, dptr, nbytes))
+        return out
+
+    def synth_reads(self, seed: int, first: int, n_reads: int, read_len: int, genome_seed: int, n_genomes: int,
+                    genome_len: int, dptr: int):
+        self._check(self._L.kmcpg_synth_reads(self._h, seed, first, n_reads, read_len, genome_seed, n_genomes, genome_len, dptr))
+
+
+def host_alloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    rc = load().kmcpg_host_alloc(C.byref(p), nbytes)
+    if rc:
+        raise KmcpGpuError(rc, "pinned allocation failed")
+    return p.value
+
+
+def host_free(ptr: int):
+    load().kmcpg_host_free(ptr)
+
+
+def pinned_array(nbytes: int, dtype=np.uint8) -> Tuple[np.ndarray, int]:
+    """numpy view over pinned host memory (caller keeps ptr and frees it with host_free)"""
+    ptr = host_alloc(nbytes)
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype), ptr

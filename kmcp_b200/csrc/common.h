@@ -1,0 +1,60 @@
+// common.h — shared host-side declarations of libkmcp_gpu (no CUDA types here).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/kmcp_gpu.h"
+
+namespace kmcpg {
+
+// One `.uniki` block header (reference: kmcp/cmd/index/serialization.go:60-80 Header, read by X:383-593).
+struct BlockMeta {
+    std::string path;
+    int k = 0;
+    bool canonical = false, compact = false;
+    int num_hashes = 0;
+    uint64_t num_sigs = 0;
+    int n_names = 0;
+    int row_bytes = 0;           // (n_names+7)/8  (X:379)
+    uint64_t data_offset = 0;    // file position of row 0 (U:1207)
+    std::vector<std::string> names;     // Target[0] of every column
+    std::vector<uint32_t> indices;      // chunkIdx | nChunks<<16
+    std::vector<uint64_t> gsizes, sizes;
+    int64_t target_base = 0;     // global index of column 0
+};
+
+// `__db.yml` (reference: kmcp/cmd/util-db-info.go:46-79) + every block header.
+struct DbMeta {
+    std::string dir;
+    int version = 0, index_version = 0;
+    std::vector<int> ks;         // descending
+    bool canonical = false, scaled = false, minimizer = false, syncmer = false;
+    uint32_t scale = 0, minimizer_w = 0, syncmer_s = 0;
+    int num_hashes = 0;
+    double fpr = 0;
+    std::vector<std::string> files;
+    std::vector<BlockMeta> blocks;
+    int64_t n_targets = 0;
+};
+
+// returns 0 or a KMCPG_E* code, message in err
+int read_block_header(const std::string &path, BlockMeta &out, std::string &err);
+int read_db_meta(const std::string &dir, DbMeta &out, std::string &err);
+// X:153-304 writer (used by kmcpg_write_block and the device index builder)
+int write_block_file(const std::string &path, const BlockMeta &m, const uint8_t *rows_unpadded, std::string &err);
+
+// H:46-50 CalcSignatureSize
+uint64_t calc_signature_size(uint64_t n_elements, int num_hashes, double fpr);
+// F:32-50 QueryFPR, bit-exact with Go (math.Pow loop, big.Float prec-53 binomials)
+double query_fpr(int n, int c, double p);
+double go_pow(double x, double y);
+
+// 128-bit reciprocal for exact x % d (replaces bmkessler/fastdiv Uint64.Mod; U:6611, U:6811)
+struct FastMod {
+    uint64_t d = 1, m_hi = 0, m_lo = 0;
+};
+FastMod make_fastmod(uint64_t d);
+uint64_t fastmod_host(uint64_t a, const FastMod &f);
+
+}  // namespace kmcpg

@@ -1,0 +1,542 @@
+// kernels.cu — hand-written sm_100a kernels of the kmcp search hot path.
+//
+//   hash_kernel   : ASCII reads → canonical ntHash1 codes (+ FracMinHash cut, code>0), one warp per query.
+//                   Replaces sketches.Iterator/nthash.NTHi driven by UnikIndexDB.generateKmers (U:1037-1107).
+//   locs_kernel   : code → Bloom row index of one block: hashValues (H:125-141) + exact 64-bit modulo
+//                   (fastdiv.Mod, U:6811) by a 128-bit reciprocal.
+//   probe_kernel  : the COBS probe (U:6613-7741).  A task = (query, 16·G-byte column chunk of the block);
+//                   G lanes own one 16-byte column slab each and keep the per-target match counters
+//                   BIT-SLICED in registers (plane p = bit p of 128 targets' counts).  Rows are fetched with
+//                   independent, coalesced 16-byte loads (8 rows in flight per lane), h rows are AND-ed in
+//                   registers (pand), and 8 rows at a time go through a carry-save adder tree (Harley–Seal),
+//                   which replaces the reference's byte transpose + pospop.Count8.  Thresholding
+//                   (count >= min_matched, float64(count) > n·t) is evaluated bit-serially on the planes;
+//                   only surviving targets are unpacked and appended to the hit list.
+//
+// Integer/bitset work, HBM-bandwidth bound: no tensor cores by design.
+#include <cub/cub.cuh>
+
+#include "kernels.cuh"
+
+namespace kmcpg {
+
+// ------------------------------------------------------------------------------------------------------
+// ntHash1 seeds (will-rowe/nthash v0.4.0 == bcgsc ntHash 1.x)
+// ------------------------------------------------------------------------------------------------------
+#define SEED_A 0x3c8bfbb395c60474ULL
+#define SEED_C 0x3193c18562a02b4cULL
+#define SEED_G 0x20323ed082572324ULL
+#define SEED_T 0x295549f54be24456ULL
+
+__device__ __forceinline__ uint64_t rol1(uint64_t x) { return (x << 1) | (x >> 63); }
+__device__ __forceinline__ uint64_t ror1(uint64_t x) { return (x >> 1) | (x << 63); }
+__device__ __forceinline__ uint64_t rolv(uint64_t x, unsigned r) {
+    r &= 63;
+    return r ? (x << r) | (x >> (64 - r)) : x;
+}
+
+__device__ __forceinline__ uint64_t seed_fwd(uint8_t b) {
+    // forward table: A/a C/c G/g T/t U/u, everything else 0
+    switch (b | 0x20) {
+        case 'a': return SEED_A;
+        case 'c': return SEED_C;
+        case 'g': return SEED_G;
+        case 't': return SEED_T;
+        case 'u': return SEED_T;
+        default: return 0;
+    }
+}
+
+__global__ void slot_bounds_kernel(const uint64_t *__restrict__ seq_off, uint32_t n_seqs, int k, uint64_t *__restrict__ cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_seqs) {
+        uint64_t len = seq_off[i + 1] - seq_off[i];
+        cnt[i] = len >= (uint64_t)k ? len - k + 1 : 0;
+    }
+    if (i == n_seqs) cnt[i] = 0;
+}
+
+cudaError_t launch_slot_bounds(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *slot_cnt, cudaStream_t st) {
+    uint32_t n = n_seqs + 1;
+    slot_bounds_kernel<<<(n + 255) / 256, 256, 0, st>>>(seq_off, n_seqs, k, slot_cnt);
+    return cudaGetLastError();
+}
+
+// shared seed tables: F[256], Fk[256] = rol(F,k); R[8], R1[8] = ror(R,1), Rk1[8] = rol(R,k-1)
+struct SeedTables {
+    uint64_t F[256], Fk[256], R[8], R1[8], Rk1[8];
+};
+
+constexpr int HASH_WARPS = 8;
+constexpr int HASH_RUN = 8;   // max consecutive positions rolled by one lane
+
+__global__ void __launch_bounds__(HASH_WARPS * 32) hash_kernel(HashArgs a) {
+    __shared__ SeedTables T;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint64_t f = seed_fwd((uint8_t)i);
+        // entries 0..7 double as the reverse-strand table seedTab[b & 7] = {N,T,N,G,A,A,N,C}
+        if (i < 8) {
+            const uint64_t r8[8] = {0, SEED_T, 0, SEED_G, SEED_A, SEED_A, 0, SEED_C};
+            f = r8[i];
+            T.R[i] = f;
+            T.R1[i] = ror1(f);
+            T.Rk1[i] = rolv(f, (unsigned)(a.k - 1));
+        }
+        T.F[i] = f;
+        T.Fk[i] = rolv(f, (unsigned)a.k);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int k = a.k;
+
+    for (uint32_t q = warp; q < a.n_queries; q += n_warps) {
+        const uint32_t s0 = a.paired ? 2 * q : q;
+        const int n_mates = a.paired ? 2 : 1;
+        const uint64_t len0 = a.seq_off[s0 + 1] - a.seq_off[s0];
+        const uint64_t len1 = a.paired ? a.seq_off[s0 + 2] - a.seq_off[s0 + 1] : 0;
+        uint64_t *out = a.codes + a.slot_off[s0];
+        uint32_t written = 0;
+        // U:778-786: skip when Seq is shorter than min-query-len unless Seq2 is long enough
+        bool skip = (int64_t)len0 < a.min_query_len && !(a.paired && (int64_t)len1 >= a.min_query_len);
+        int32_t qlen = (int32_t)(len0 + len1);
+        if (a.mate_select == 1) qlen = (int32_t)len0;
+        if (a.mate_select == 2) qlen = (int32_t)len1;
+        if (!skip) {
+            for (int m = 0; m < n_mates; m++) {
+                if (a.mate_select == 1 && m == 1) continue;
+                if (a.mate_select == 2 && m == 0) continue;
+                const uint8_t *s = a.seq + a.seq_off[s0 + m];
+                const uint64_t len = m == 0 ? len0 : len1;
+                if (len < (uint64_t)k) continue;                       // sketches.ErrShortSeq (U:1059-1062)
+                const uint64_t nk = len - k + 1;
+                uint64_t run = (nk + 31) / 32;
+                if (run > HASH_RUN) run = HASH_RUN;
+                for (uint64_t base = 0; base < nk; base += 32 * run) {
+                    const uint64_t p0 = base + (uint64_t)lane * run;
+                    int cnt = 0;
+                    if (p0 < nk) cnt = (int)((nk - p0) < run ? (nk - p0) : run);
+                    uint64_t c[HASH_RUN];
+                    uint32_t valid = 0;
+                    if (cnt > 0) {
+                        // Horner initialisation: fwd = XOR_j rol(F[s_j], k-1-j), rev = XOR_j rol(R[s_j&7], j)
+                        uint64_t fh = 0, rh = 0;
+                        for (int j = 0; j < k; j++) {
+                            fh = rol1(fh) ^ T.F[s[p0 + j]];
+                            rh = rol1(rh) ^ T.R[s[p0 + k - 1 - j] & 7];
+                        }
+#pragma unroll
+                        for (int r = 0; r < HASH_RUN; r++) {
+                            if (r < cnt) {
+                                uint64_t code = a.canonical ? (fh < rh ? fh : rh) : fh;
+                                bool ok = code != 0 && !(a.scaled && code > a.max_hash);       // U:1097-1102
+                                c[r] = code;
+                                if (ok) valid |= 1u << r;
+                                if (r + 1 < cnt) {
+                                    uint8_t bo = s[p0 + r], bi = s[p0 + r + k];
+                                    fh = rol1(fh) ^ T.Fk[bo] ^ T.F[bi];
+                                    rh = ror1(rh) ^ T.R1[bo & 7] ^ T.Rk1[bi & 7];
+                                }
+                            }
+                        }
+                    }
+                    // in-order compaction inside the query's code region
+                    int mine = __popc(valid);
+                    int incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    int total = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t w = written + (uint32_t)(incl - mine);
+#pragma unroll
+                    for (int r = 0; r < HASH_RUN; r++)
+                        if (valid & (1u << r)) out[w++] = c[r];
+                    written += (uint32_t)total;
+                }
+            }
+        }
+        if (lane == 0) {
+            a.n_codes[q] = skip ? 0xFFFFFFFFu : written;    // 0xFFFFFFFF marks "skipped by length" (NumKmers = 0)
+            a.query_len[q] = qlen;
+        }
+    }
+}
+
+cudaError_t launch_hash(const HashArgs &a, cudaStream_t st) {
+    if (a.n_queries == 0) return cudaSuccess;
+    uint32_t blocks = (a.n_queries + HASH_WARPS - 1) / HASH_WARPS;
+    if (blocks > 148u * 64u) blocks = 148u * 64u;
+    hash_kernel<<<blocks, HASH_WARPS * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// dedup + per-query verdict
+// ------------------------------------------------------------------------------------------------------
+__global__ void sort_segments_kernel(const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ n_codes, uint32_t nq,
+                                     int paired, int thr, int *__restrict__ seg_begin, int *__restrict__ seg_end) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint64_t b = slot_off[paired ? 2 * q : q];
+    uint32_t n = n_codes[q];
+    if (n == 0xFFFFFFFFu) n = 0;
+    seg_begin[q] = (int)b;
+    seg_end[q] = (int)((n > (uint32_t)thr) ? b + n : b);      // strict > (U:874)
+}
+
+cudaError_t launch_sort_segments(const uint64_t *slot_off, const uint32_t *n_codes, uint32_t nq, int paired, int thr,
+                                 int *seg_begin, int *seg_end, cudaStream_t st) {
+    if (!nq) return cudaSuccess;
+    sort_segments_kernel<<<(nq + 255) / 256, 256, 0, st>>>(slot_off, n_codes, nq, paired, thr, seg_begin, seg_end);
+    return cudaGetLastError();
+}
+
+// one warp per query: unique of an ascending region in place (U:878-908), then n_eff / threshold
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = warp; q < a.n_queries; q += n_warps) {
+        uint32_t n = a.n_codes[q];
+        bool skipped = n == 0xFFFFFFFFu;
+        if (skipped) n = 0;
+        // U:854-869: fewer k-mers than min-matched → unmatched, checked BEFORE dedup
+        bool too_few = (int64_t)n < (int64_t)a.min_matched;
+        if (!skipped && !too_few && a.do_unique && n > (uint32_t)a.dedup_threshold) {
+            uint64_t *c = a.codes + a.slot_off[a.paired ? 2 * q : q];
+            uint32_t w = 0;
+            for (uint32_t base = 0; base < n; base += 32) {
+                uint32_t i = base + lane;
+                uint64_t v = 0, prev = 0;
+                bool keep = false;
+                if (i < n) {
+                    v = c[i];
+                    keep = (i == 0);
+                    if (i > 0) { prev = c[i - 1]; keep = v != prev; }
+                }
+                __syncwarp();                                  // all reads of this round before any write
+                uint32_t m = __ballot_sync(0xffffffffu, keep);
+                if (keep) c[w + __popc(m & ((1u << lane) - 1))] = v;
+                w += __popc(m);
+                __syncwarp();
+            }
+            n = w;
+        }
+        if (lane == 0) {
+            uint32_t eff = (skipped || too_few) ? 0 : n;
+            a.n_codes[q] = n;
+            a.n_eff[q] = eff;
+            a.n_kmers_out[q] = (int32_t)eff;
+            // smallest integer count with float64(count) > float64(n)*t (U:6625, U:7469), and >= min_matched (U:7466)
+            double x = (double)n * a.min_query_cov;
+            double fl = floor(x);
+            uint32_t t = fl >= 4294967294.0 ? 0xFFFFFFFFu : (uint32_t)fl + 1;
+            if ((int64_t)t < (int64_t)a.min_matched) t = (uint32_t)a.min_matched;
+            if (t == 0) t = 1;
+            a.thresh[q] = t;
+        }
+    }
+}
+
+cudaError_t launch_finalize(const FinalizeArgs &a, cudaStream_t st) {
+    if (!a.n_queries) return cudaSuccess;
+    uint32_t blocks = (a.n_queries + 7) / 8;
+    if (blocks > 148u * 32u) blocks = 148u * 32u;
+    finalize_kernel<<<blocks, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// locs: hashValues + exact modulo
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t fastmod_dev(uint64_t a, uint64_t m_hi, uint64_t m_lo, uint64_t d) {
+    // lowbits = M*a mod 2^128 ; result = (lowbits*d) >> 128
+    uint64_t lo = m_lo * a;
+    uint64_t hi = __umul64hi(m_lo, a) + m_hi * a;
+    uint64_t bottom = __umul64hi(lo, d);
+    uint64_t top_lo = hi * d;
+    uint64_t top_hi = __umul64hi(hi, d);
+    uint64_t sum = bottom + top_lo;
+    return top_hi + (sum < bottom ? 1 : 0);
+}
+
+template <int H>
+__global__ void __launch_bounds__(256) locs_kernel(const uint64_t *__restrict__ codes, uint64_t n, FastMod fm, uint32_t *__restrict__ locs) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint64_t code = codes[i];
+        if (H == 1) {
+            locs[i] = (uint32_t)fastmod_dev(code, fm.m_hi, fm.m_lo, fm.d);
+        } else {
+            uint32_t x = (uint32_t)(code >> 32), y = (uint32_t)code;      // baseHashes (H:61-63)
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)H; j++) {
+                uint64_t v = (uint64_t)(uint32_t)(x + y * j);             // uint32 wrap-around (H:137-139)
+                locs[i * H + j] = (uint32_t)fastmod_dev(v, fm.m_hi, fm.m_lo, fm.d);
+            }
+        }
+    }
+}
+
+cudaError_t launch_locs(const uint64_t *codes, uint64_t n, int h, FastMod fm, uint32_t *locs, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    uint64_t blocks64 = (n + 255) / 256;
+    uint32_t blocks = blocks64 > 148u * 64u ? 148u * 64u : (uint32_t)blocks64;
+    switch (h) {
+        case 1: locs_kernel<1><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        case 2: locs_kernel<2><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        case 3: locs_kernel<3><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        case 4: locs_kernel<4><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// probe
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint4 ld_row16(const uint8_t *p) {
+    // streaming 16-byte load of a bit-matrix row slab: read-only path, do not keep in L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+constexpr int PROBE_THREADS = 256;
+constexpr int PROBE_ROWS = 8;   // rows in flight per lane = inputs of one carry-save tree
+
+template <int H, int P>
+__global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(ProbeArgs a) {
+    const uint32_t G = a.lanes_per_task;
+    const uint32_t gl = threadIdx.x & (G - 1);                          // lane inside the task group
+    const uint64_t groups_per_grid = ((uint64_t)gridDim.x * blockDim.x) / G;
+    const uint64_t total = (uint64_t)a.n_queries * a.chunks;
+    const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint64_t iters = (total + groups_per_grid - 1) / groups_per_grid;
+    const int lane = threadIdx.x & 31;
+
+    for (uint64_t it = 0; it < iters; it++) {
+        const uint64_t g = first + it * groups_per_grid;
+        uint32_t q = 0, chunk = 0, n = 0;
+        if (g < total) {
+            q = (uint32_t)(g / a.chunks);
+            chunk = (uint32_t)(g - (uint64_t)q * a.chunks);             // chunk fastest: neighbouring groups share rows
+            n = a.n_eff[q];
+        }
+        const uint32_t col16 = chunk * G + gl;                          // this lane's 16-byte slab of the row
+        const bool active = n > 0 && col16 < a.row16;
+        uint32_t c[P][4];
+#pragma unroll
+        for (int p = 0; p < P; p++) c[p][0] = c[p][1] = c[p][2] = c[p][3] = 0;
+
+        if (active) {
+            const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
+            const uint8_t *colbase = a.rows + (uint64_t)col16 * 16;
+            for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
+                uint4 r[PROBE_ROWS];
+#pragma unroll
+                for (int u = 0; u < PROBE_ROWS; u++) {
+                    if (i + u < n) {
+                        uint32_t loc = __ldg(lp + (uint64_t)(i + u) * H);
+                        r[u] = ld_row16(colbase + (uint64_t)loc * a.pitch);
+#pragma unroll
+                        for (int h = 1; h < H; h++) {                    // row AND for h>1 (pand, U:6639-6645)
+                            uint32_t loc2 = __ldg(lp + (uint64_t)(i + u) * H + h);
+                            uint4 t = ld_row16(colbase + (uint64_t)loc2 * a.pitch);
+                            r[u].x &= t.x; r[u].y &= t.y; r[u].z &= t.z; r[u].w &= t.w;
+                        }
+                    } else {
+                        r[u] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+                // Harley–Seal: 8 one-bit inputs + planes 0..2 → planes 0..2 and one weight-8 carry
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t x0 = (&r[0].x)[w], x1 = (&r[1].x)[w], x2 = (&r[2].x)[w], x3 = (&r[3].x)[w];
+                    const uint32_t x4 = (&r[4].x)[w], x5 = (&r[5].x)[w], x6 = (&r[6].x)[w], x7 = (&r[7].x)[w];
+                    uint32_t ones = c[0][w], twos = c[1][w], fours = c[2][w];
+                    uint32_t t1a = maj3(ones, x0, x1); ones = xor3(ones, x0, x1);
+                    uint32_t t1b = maj3(ones, x2, x3); ones = xor3(ones, x2, x3);
+                    uint32_t t2a = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
+                    t1a = maj3(ones, x4, x5); ones = xor3(ones, x4, x5);
+                    t1b = maj3(ones, x6, x7); ones = xor3(ones, x6, x7);
+                    uint32_t t2b = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
+                    uint32_t carry = maj3(fours, t2a, t2b); fours = xor3(fours, t2a, t2b);
+                    c[0][w] = ones; c[1][w] = twos; c[2][w] = fours;
+#pragma unroll
+                    for (int p = 3; p < P; p++) {                        // ripple the weight-8 carry upwards
+                        uint32_t t = c[p][w] & carry;
+                        c[p][w] ^= carry;
+                        carry = t;
+                    }
+                }
+            }
+        }
+
+        // ---- thresholds on the bit-sliced counters: ge = (count >= T) per target bit ----
+        uint32_t ge[4] = {0, 0, 0, 0};
+        int nhit = 0;
+        if (active) {
+            const uint32_t T = a.thresh[q];
+            uint32_t high = (P < 32) ? (T >> P) : 0;                     // T does not fit in P bits → nothing passes
+            if (!high) {
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int p = P - 1; p >= 0; p--) {
+                        if ((T >> p) & 1) { eq &= c[p][w]; }
+                        else { gt |= eq & c[p][w]; eq &= ~c[p][w]; }
+                    }
+                    ge[w] = gt | eq;
+                    nhit += __popc(ge[w]);
+                }
+            }
+            if (a.dense_counts) {                                        // test hook: dump every count of this slab
+#pragma unroll
+                for (int w = 0; w < 4; w++)
+                    for (int bit = 0; bit < 32; bit++) {
+                        uint32_t t = (col16 * 16 + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                        if (t < a.n_names) {
+                            uint32_t cnt = 0;
+#pragma unroll
+                            for (int p = 0; p < P; p++) cnt |= ((c[p][w] >> bit) & 1u) << p;
+                            a.dense_counts[(uint64_t)q * 0 + a.target_base + t] = cnt;
+                        }
+                    }
+            }
+        }
+        // ---- append hits: one atomic per warp ----
+        __syncwarp();
+        int incl = nhit;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot > 0) {
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(a.hit_count, (unsigned long long)tot);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            unsigned long long slot = base + (unsigned long long)(incl - nhit);
+            if (nhit > 0) {
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    uint32_t m = ge[w];
+                    while (m) {
+                        int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        // byte (col16*16 + w*4 + bit/8), bit 7-j ↔ target 8*byte + j  (I:1157, U:7415)
+                        uint32_t t = (col16 * 16 + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                        uint32_t cnt = 0;
+#pragma unroll
+                        for (int p = 0; p < P; p++) cnt |= ((c[p][w] >> bit) & 1u) << p;
+                        if (slot < a.hit_cap) {
+                            a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
+                            a.hit_vals[slot] = cnt;
+                        }
+                        slot++;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int H>
+static cudaError_t launch_probe_h(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
+    switch (a.planes) {
+        case 8: probe_kernel<H, 8><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
+        case 16: probe_kernel<H, 16><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
+        case 24: probe_kernel<H, 24><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
+        case 32: probe_kernel<H, 32><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st) {
+    if (!a.n_queries) return cudaSuccess;
+    const uint64_t total_groups = (uint64_t)a.n_queries * a.chunks;
+    const uint64_t threads = total_groups * a.lanes_per_task;
+    uint64_t blocks64 = (threads + PROBE_THREADS - 1) / PROBE_THREADS;
+    // persistent-style grid: a multiple of the SM count, several CTAs per SM, each thread loops over tasks
+    const uint64_t cap = (uint64_t)sm_count * 16;
+    uint32_t blocks = (uint32_t)(blocks64 < cap ? blocks64 : cap);
+    switch (a.num_hashes) {
+        case 1: return launch_probe_h<1>(a, blocks, st);
+        case 2: return launch_probe_h<2>(a, blocks, st);
+        case 3: return launch_probe_h<3>(a, blocks, st);
+        case 4: return launch_probe_h<4>(a, blocks, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// re-pitch rows on upload
+// ------------------------------------------------------------------------------------------------------
+__global__ void repitch_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch) {
+    const uint64_t total = n_rows * pitch;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        uint64_t r = i / pitch;
+        uint32_t x = (uint32_t)(i - r * pitch);
+        dst[i] = x < row_bytes ? src[r * row_bytes + x] : 0;
+    }
+}
+__global__ void unpitch_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch) {
+    const uint64_t total = n_rows * row_bytes;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        uint64_t r = i / row_bytes;
+        uint32_t x = (uint32_t)(i - r * row_bytes);
+        dst[i] = src[r * pitch + x];
+    }
+}
+
+__global__ void pack_hits_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t qbase, kmcpg_hit *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = keys[i];
+    kmcpg_hit h;
+    h.query = (uint32_t)(k >> 32) + qbase; h.target = (uint32_t)k; h.count = vals[i];
+    out[i] = h;
+}
+cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint32_t qbase, kmcpg_hit *out, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    pack_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, vals, n, qbase, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_repitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch, cudaStream_t st) {
+    if (!n_rows) return cudaSuccess;
+    repitch_kernel<<<148 * 16, 256, 0, st>>>(src, dst, n_rows, row_bytes, pitch);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch, cudaStream_t st) {
+    if (!n_rows) return cudaSuccess;
+    unpitch_kernel<<<148 * 16, 256, 0, st>>>(src, dst, n_rows, row_bytes, pitch);
+    return cudaGetLastError();
+}
+
+}  // namespace kmcpg

@@ -1,0 +1,101 @@
+// kernels.cuh — launch interface of the sm_100a kernels of the kmcp search path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.h"
+
+namespace kmcpg {
+
+// ---- kernel 1: sequences → k-mer codes (UnikIndexDB.generateKmers, U:1037-1107) -------------------------
+struct HashArgs {
+    const uint8_t *seq;         // concatenated ASCII
+    const uint64_t *seq_off;    // n_seqs+1
+    const uint64_t *slot_off;   // n_seqs+1: start of the code region of every sequence (upper bound layout)
+    uint64_t *codes;            // [slot_off[n_seqs]]
+    uint32_t *n_codes;          // per QUERY: codes written (mates concatenated)
+    int32_t *query_len;         // per QUERY: len(Seq)+len(Seq2)
+    uint32_t n_queries;
+    int paired;                 // 1: query q = sequences 2q, 2q+1
+    int mate_select;            // 0 both, 1 first, 2 second
+    int k;
+    int canonical;
+    int scaled;
+    uint64_t max_hash;
+    int minimizer; uint32_t minimizer_w;
+    int syncmer; uint32_t syncmer_s;
+    int min_query_len;
+};
+cudaError_t launch_slot_bounds(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *slot_cnt, cudaStream_t st);
+cudaError_t launch_hash(const HashArgs &a, cudaStream_t st);
+
+// in-place unique of sorted regions longer than the dedup threshold (U:874-908), and the per-query verdict
+struct FinalizeArgs {
+    uint64_t *codes;
+    const uint64_t *slot_off;   // per sequence
+    uint32_t *n_codes;          // in: codes per query; out: after dedup
+    int32_t *n_kmers_out;       // reported NumKmers (0 when skipped)
+    uint32_t *n_eff;            // codes to probe (0 = skip)
+    uint32_t *thresh;           // smallest count that passes min_matched and count > n*min_query_cov
+    uint32_t n_queries;
+    int paired;
+    int dedup_threshold;
+    int do_unique;              // regions with n > dedup_threshold are already sorted: unique them
+    int min_matched;
+    double min_query_cov;
+};
+cudaError_t launch_finalize(const FinalizeArgs &a, cudaStream_t st);
+// segment descriptors for cub::DeviceSegmentedSort: begin/end of regions with n > dedup_threshold (else empty)
+cudaError_t launch_sort_segments(const uint64_t *slot_off, const uint32_t *n_codes, uint32_t n_queries, int paired,
+                                 int dedup_threshold, int *seg_begin, int *seg_end, cudaStream_t st);
+
+// ---- kernel 2a: code → row index of one block (hashValues + fastdiv.Mod; H:125-141, U:6811) ------------
+cudaError_t launch_locs(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint32_t *locs,
+                        cudaStream_t st);
+
+// ---- kernel 2b: the COBS probe of one block (U:6613-7741) ----------------------------------------------
+struct ProbeArgs {
+    const uint8_t *rows;        // re-pitched bit matrix of the block in HBM
+    uint32_t pitch;             // bytes between rows
+    uint32_t row16;             // 16-byte units per row that carry data: ceil(row_bytes/16)
+    uint32_t lanes_per_task;    // G: 1,2,4,8,16,32 lanes × 16 B = one task's column chunk
+    uint32_t chunks;            // tasks per query = ceil(row16 / G)
+    uint32_t n_names;
+    uint32_t target_base;
+    int num_hashes;
+    const uint32_t *locs;       // [slot][h]
+    const uint64_t *slot_off;   // per sequence
+    const uint32_t *n_eff;      // per query
+    const uint32_t *thresh;     // per query
+    uint32_t n_queries;
+    int paired;
+    uint64_t *hit_keys;         // query<<32 | global target
+    uint32_t *hit_vals;         // matched k-mers
+    unsigned long long *hit_count;
+    uint64_t hit_cap;
+    uint32_t *dense_counts;     // optional [n_queries=1][n_targets] dump of all counts (kmcpg_count_codes)
+    int planes;                 // counter bits: 8, 16, 24, 32
+};
+cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st);
+
+// ---- small utilities ------------------------------------------------------------------------------------
+// rows (unpadded, row_bytes each) → dst with `pitch` bytes per row, zero padded
+cudaError_t launch_repitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch,
+                           cudaStream_t st);
+cudaError_t launch_unpitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch,
+                           cudaStream_t st);
+// sorted (key,val) pairs → kmcpg_hit records, query index rebased by query_base
+cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint32_t query_base, kmcpg_hit *out,
+                             cudaStream_t st);
+
+// ---- synthetic data + device index builder (synth.cu) ---------------------------------------------------
+cudaError_t launch_synth_reads(uint64_t seed, uint64_t first, uint32_t n_reads, uint32_t read_len, uint64_t genome_seed,
+                               uint32_t n_genomes, uint32_t genome_len, uint8_t *out, cudaStream_t st);
+cudaError_t launch_synth_genome(uint64_t genome_seed, uint32_t genome, uint64_t start, uint64_t len, uint8_t *out,
+                                cudaStream_t st);
+// sets bit (7-(col&7)) of byte col>>3 in row loc for every code (I:1157 / I:1188)
+cudaError_t launch_set_bits(const uint64_t *codes, uint64_t n, int num_hashes, FastMod fm, uint8_t *rows, uint32_t pitch,
+                            uint32_t col, cudaStream_t st);
+
+}  // namespace kmcpg

@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact everywhere: codes, per-target counts, hit sets, float columns of the engine output.
+None of these read /root/reference (it does not exist on the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+GSEED, RSEED = 11, 23
+
+
+@pytest.fixture(scope="module")
+def small_db(oracle, tmp_path_factory):
+    """40 genomes x 30 kb, 5 chunks -> 200 targets; h=1; blocks of 64 (8-byte rows, G=1) → 4 blocks"""
+    O = oracle
+    sp = O.sketch_params(21)
+    targets = helpers.make_synth_targets(O, sp, GSEED, 40, 30000, 5, 150)
+    out = str(tmp_path_factory.mktemp("db_small"))
+    r001 = O.build_db(targets, out, sp, num_hashes=1, fpr=0.3, block_size=64)
+    return r001
+
+
+@pytest.fixture(scope="module")
+def wide_db(oracle, tmp_path_factory):
+    """150 genomes x 12 kb, 10 chunks -> 1500 targets in ONE block: 188-byte rows → two 128-byte task chunks; h=3"""
+    O = oracle
+    sp = O.sketch_params(21)
+    targets = helpers.make_synth_targets(O, sp, GSEED + 1, 150, 12000, 10, 100)
+    out = str(tmp_path_factory.mktemp("db_wide"))
+    r001 = O.build_db(targets, out, sp, num_hashes=3, fpr=0.1, block_size=1500)
+    return r001
+
+
+def _oracle_opts(O, **kw):
+    o = O.default_opts()
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+# ---------------------------------------------------------------------------------------------------- kernel 1
+@pytest.mark.parametrize("k", [21, 31, 11, 64])
+def test_generate_kmers_matches_oracle(gpu_ctx, oracle, k):
+    from kmcp_b200 import api
+    O = oracle
+    reads = helpers.edge_reads(k) + helpers.make_reads(O, RSEED, 300, 40, 30000, GSEED)
+    buf, off = api.pack_seqs(reads)
+    for scaled, scale in ((0, 1), (1, 8)):
+        sp = api.SketchParams(k, 1, scaled, scale, 0, 0, 0, 0)
+        codes, coff = gpu_ctx.generate_kmers(buf, off, sp)
+        osp = O.sketch_params(k, scaled=bool(scaled), scale=scale)
+        for i, r in enumerate(reads):
+            exp = O.generate_kmers(r, osp)
+            got = codes[int(coff[i]):int(coff[i + 1])]
+            assert np.array_equal(got, exp), (k, scaled, i, len(r))
+
+
+def test_generate_kmers_long_sequence(gpu_ctx, oracle):
+    from kmcp_b200 import api
+    O = oracle
+    seq = O.synth_genome(5, 0, 200000)
+    seq = seq[:70000] + b"N" * 500 + seq[70000:]
+    buf, off = api.pack_seqs([seq, seq[:5000]])
+    for scaled, scale in ((0, 1), (1, 100)):
+        sp = api.SketchParams(31, 1, scaled, scale, 0, 0, 0, 0)
+        codes, coff = gpu_ctx.generate_kmers(buf, off, sp)
+        osp = O.sketch_params(31, scaled=bool(scaled), scale=scale)
+        assert np.array_equal(codes[:int(coff[1])], O.generate_kmers(seq, osp))
+        assert np.array_equal(codes[int(coff[1]):], O.generate_kmers(seq[:5000], osp))
+
+
+# ---------------------------------------------------------------------------------------------------- kernel 2
+@pytest.mark.parametrize("dbname", ["small_db", "wide_db"])
+def test_count_codes_matches_oracle(gpu_ctx, oracle, request, dbname):
+    O = oracle
+    r001 = request.getfixturevalue(dbname)
+    odb = O.DB(r001)
+    gpu_ctx.open_db(r001)
+    info = gpu_ctx.db_info()
+    assert info.n_targets == odb.info.n_targets and info.n_blocks == odb.info.n_blocks
+    assert info.sum_row_bytes == odb.info.sum_row_bytes and info.disk_bytes == odb.info.total_bytes
+    sp = odb.sketch_params()
+    ng, gl = (40, 30000) if dbname == "small_db" else (150, 12000)
+    gs = GSEED if dbname == "small_db" else GSEED + 1
+    for n_reads in (1, 7):
+        reads = helpers.make_reads(O, RSEED + n_reads, n_reads, ng, gl, gs)
+        codes = np.concatenate([O.generate_kmers(r, sp) for r in reads])
+        exp = odb.count_codes(codes)
+        got = gpu_ctx.count_codes(codes)
+        assert np.array_equal(got, exp)
+        assert exp.max() > 50
+    # > 255 and > 65535 codes exercise the 16- and 24-plane counters
+    long_codes = O.generate_kmers(O.synth_genome(gs, 3, gl), sp)
+    for codes in (long_codes[:300], long_codes[:5000], np.tile(long_codes[:7000], 10)):
+        assert np.array_equal(gpu_ctx.count_codes(codes), odb.count_codes(codes))
+    assert np.array_equal(gpu_ctx.count_codes(np.zeros(0, np.uint64)), np.zeros(info.n_targets, np.uint32))
+
+
+def test_targets_metadata(gpu_ctx, oracle, small_db):
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    for g in range(odb.info.n_targets):
+        a, b = odb.target(g), gpu_ctx.target(g)
+        assert (a.name, a.index, a.genome_size, a.n_kmers, a.block, a.col) == (b.name, b.index, b.genome_size, b.n_kmers, b.block, b.col)
+        assert b.resident == 1
+
+
+# ---------------------------------------------------------------------------------------------------- whole path
+def _compare_engine(O, odb, ctx, reads, paired=False, **opts):
+    from kmcp_b200 import api
+    buf, off = api.pack_seqs(reads)
+    oo = _oracle_opts(O, **opts)
+    exp = odb.search(reads, paired=paired, opts=oo)
+    eo = ctx.default_engine_opts(paired=int(paired), **opts)
+    got = ctx.engine_search(buf, off, eo)
+    assert np.array_equal(got.query_len, exp.query_len)
+    assert np.array_equal(got.n_kmers, exp.n_kmers)
+    assert np.array_equal(got.match_off, exp.hit_off)
+    for f in ("query", "target", "count", "fpr", "qcov", "tcov", "jacc"):
+        assert np.array_equal(got.matches[f], exp.hits[f]), f      # floats compared bit for bit
+    return got
+
+
+@pytest.mark.parametrize("dbname,ng,gl,gs", [("small_db", 40, 30000, GSEED), ("wide_db", 150, 12000, GSEED + 1)])
+def test_search_batch_hits_match_oracle(gpu_ctx, oracle, request, dbname, ng, gl, gs):
+    from kmcp_b200 import api
+    O = oracle
+    r001 = request.getfixturevalue(dbname)
+    odb = O.DB(r001)
+    gpu_ctx.open_db(r001)
+    reads = helpers.make_reads(O, RSEED, 2000, ng, gl, gs) + helpers.edge_reads(odb.k)
+    buf, off = api.pack_seqs(reads)
+    got = gpu_ctx.search_batch(buf, off)
+    # oracle with the post filters disabled = exactly the device-side contract
+    exp = odb.search(reads, opts=_oracle_opts(O, max_fpr=1.0, min_target_cov=0.0))
+    assert np.array_equal(got.n_kmers, exp.n_kmers)
+    assert np.array_equal(got.query_len, exp.query_len)
+    assert helpers.hits_to_set(got.hits) == helpers.hits_to_set(exp.hits)
+    assert len(got.hits) == len(exp.hits) > 1000
+    # canonical order
+    key = got.hits["query"].astype(np.uint64) << np.uint64(32) | got.hits["target"].astype(np.uint64)
+    assert np.all(key[1:] > key[:-1])
+    assert got.kernel_launches > 0
+    n_sum = int(got.n_kmers.astype(np.int64).sum())
+    assert got.probe_row_bytes == n_sum * odb.info.num_hashes * odb.info.sum_row_bytes
+
+
+@pytest.mark.parametrize("dbname,ng,gl,gs", [("small_db", 40, 30000, GSEED), ("wide_db", 150, 12000, GSEED + 1)])
+def test_engine_matches_oracle_defaults(gpu_ctx, oracle, request, dbname, ng, gl, gs):
+    O = oracle
+    r001 = request.getfixturevalue(dbname)
+    odb = O.DB(r001)
+    gpu_ctx.open_db(r001)
+    reads = helpers.make_reads(O, RSEED + 5, 3000, ng, gl, gs) + helpers.edge_reads(odb.k)
+    got = _compare_engine(O, odb, gpu_ctx, reads)
+    assert len(got.matches) > 1500
+
+
+def test_engine_option_variants(gpu_ctx, oracle, small_db):
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    reads = helpers.make_reads(O, RSEED + 9, 800, 40, 30000, GSEED) + helpers.edge_reads(odb.k)
+    _compare_engine(O, odb, gpu_ctx, reads, min_query_cov=0.3, sort_by=1)
+    _compare_engine(O, odb, gpu_ctx, reads, min_query_cov=0.7, sort_by=2, top_n_scores=1)
+    _compare_engine(O, odb, gpu_ctx, reads, min_query_cov=0.2, min_matched=3, min_target_cov=0.002, max_fpr=1e-6)
+    _compare_engine(O, odb, gpu_ctx, reads, do_not_sort=1, min_query_len=100)
+    _compare_engine(O, odb, gpu_ctx, reads, dedup_threshold=50)       # 150 bp reads now take the sort+unique path
+    _compare_engine(O, odb, gpu_ctx, reads, min_query_cov=0.0)
+    _compare_engine(O, odb, gpu_ctx, reads, min_query_cov=1.0)
+
+
+def test_engine_paired_and_try_se(gpu_ctx, oracle, small_db):
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    r1 = helpers.make_reads(O, RSEED + 1, 600, 40, 30000, GSEED)
+    r2 = helpers.make_reads(O, RSEED + 2, 600, 40, 30000, GSEED)
+    r2[5] = b"ACGT"            # short mate
+    r1[6] = b"ACGTACGT"        # short Seq, long Seq2
+    r1[7] = b""; r2[7] = b""
+    reads = [x for p in zip(r1, r2) for x in p]
+    _compare_engine(O, odb, gpu_ctx, reads, paired=True)
+    _compare_engine(O, odb, gpu_ctx, reads, paired=True, try_se=1, min_query_cov=0.6)
+    _compare_engine(O, odb, gpu_ctx, reads, paired=True, dedup_threshold=200)
+
+
+def test_long_reads_dedup(gpu_ctx, oracle, small_db):
+    """HiFi-like queries: n >> 256 → device sort+unique (U:874-908), 16-plane counters"""
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    rng = np.random.default_rng(3)
+    reads = []
+    for i in range(40):
+        g = int(rng.integers(0, 40)); L = int(rng.integers(300, 12000)); p = int(rng.integers(0, 30000 - L))
+        s = O.synth_genome(GSEED, g, 30000)[p:p + L]
+        if i % 3 == 0:
+            s = s + s[:L // 2]                     # duplicated k-mers
+        reads.append(s)
+    reads += helpers.make_reads(O, RSEED, 50, 40, 30000, GSEED)     # mixed with short reads in one batch
+    got = _compare_engine(O, odb, gpu_ctx, reads)
+    assert got.n_kmers.max() > 5000
+
+
+def test_device_resident_batch(gpu_ctx, oracle, small_db):
+    from kmcp_b200 import api
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    reads = helpers.make_reads(O, RSEED + 3, 500, 40, 30000, GSEED)
+    buf, off = api.pack_seqs(reads)
+    host = gpu_ctx.search_batch(buf, off)
+    dseq = gpu_ctx.device_alloc(buf.nbytes); doff = gpu_ctx.device_alloc(off.nbytes)
+    gpu_ctx.h2d(dseq, buf); gpu_ctx.h2d(doff, off)
+    dev = gpu_ctx.search_batch_ptr(dseq, doff, len(reads), gpu_ctx.default_params(), device=True, seq_bytes=buf.nbytes)
+    gpu_ctx.device_free(dseq); gpu_ctx.device_free(doff)
+    assert np.array_equal(host.hits, dev.hits) and np.array_equal(host.n_kmers, dev.n_kmers)
+
+
+def test_sharded_blocks_union_equals_whole(oracle, small_db):
+    """blocks → shards: per-shard hit lists are disjoint by target and their union is the 1-GPU result (§8e)"""
+    from kmcp_b200 import api
+    O = oracle
+    reads = helpers.make_reads(O, RSEED + 4, 1500, 40, 30000, GSEED)
+    buf, off = api.pack_seqs(reads)
+    with api.Context(0) as whole:
+        whole.open_db(small_db)
+        ref = whole.search_batch(buf, off)
+    parts = []
+    for world in (2, 3):
+        parts = []
+        nres = 0
+        for rank in range(world):
+            with api.Context(0) as c:
+                c.open_db(small_db, shard_rank=rank, shard_world=world)
+                nres += c.db_info().n_resident_blocks
+                parts.append(c.search_batch(buf, off).hits)
+        assert nres == 4
+        allh = np.concatenate(parts)
+        allh = allh[np.lexsort((allh["target"], allh["query"]))]
+        assert np.array_equal(allh, ref.hits)
+
+
+# ---------------------------------------------------------------------------------------------------- synthetic tooling
+def test_synth_reads_match_oracle_generator(gpu_ctx, oracle):
+    O = oracle
+    n, L = 500, 150
+    d = gpu_ctx.device_alloc(n * L)
+    gpu_ctx.synth_reads(RSEED, 100, n, L, GSEED, 40, 30000, d)
+    got = gpu_ctx.d2h(d, n * L).reshape(n, L)
+    gpu_ctx.device_free(d)
+    for r in range(n):
+        assert got[r].tobytes() == O.synth_read(RSEED, 100 + r, 40, 30000, L, GSEED), r
+
+
+@pytest.mark.parametrize("h,fpr,bs", [(1, 0.3, 16), (3, 0.05, 40)])
+def test_device_index_builder_matches_oracle_builder(gpu_ctx, oracle, tmp_path, h, fpr, bs):
+    """kmcpg_build_synth_db (GPU compute+index) writes byte-identical .uniki blocks to the oracle's builder"""
+    O = oracle
+    sp = O.sketch_params(21)
+    ng, gl, nc, ov = 12, 20000, 5, 150
+    targets = helpers.make_synth_targets(O, sp, 77, ng, gl, nc, ov)
+    r001 = O.build_db(targets, str(tmp_path / "o"), sp, num_hashes=h, fpr=fpr, block_size=bs)
+    gpu_ctx.build_synth_db(77, ng, gl, k=21, n_chunks=nc, overlap=ov, num_hashes=h, fpr=fpr, block_size=bs)
+    info = gpu_ctx.db_info()
+    assert info.n_targets == len(targets)
+    for b in range(info.n_blocks):
+        p = str(tmp_path / ("g%d.uniki" % b))
+        gpu_ctx.write_block(b, p)
+        with open(p, "rb") as f1, open(os.path.join(r001, "_block%03d.uniki" % (b + 1)), "rb") as f2:
+            assert f1.read() == f2.read(), b
+    # and the freshly built in-HBM DB answers queries like the oracle's copy
+    odb = O.DB(r001)
+    reads = helpers.make_reads(O, RSEED, 400, ng, gl, 77)
+    _compare_engine(O, odb, gpu_ctx, reads)
+
+
+def test_errors_are_reported_not_fatal(gpu_ctx, tmp_path):
+    from kmcp_b200 import api
+    with pytest.raises(api.KmcpGpuError) as e:
+        gpu_ctx.open_db(str(tmp_path / "missing"))
+    assert e.value.code == api.KMCPG_EIO
+    d = tmp_path / "bad"; d.mkdir()
+    (d / "__db.yml").write_text("version: 3\nfiles:\n- x.uniki\n")
+    with pytest.raises(api.KmcpGpuError) as e:
+        gpu_ctx.open_db(str(d))
+    assert e.value.code == api.KMCPG_EFORMAT
