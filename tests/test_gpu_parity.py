@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests import helpers
+import parity_helpers as helpers
 
 pytestmark = pytest.mark.gpu
 
