@@ -79,8 +79,9 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
     memset(out, 0, sizeof(*out));
     const uint32_t step = o->paired ? 2 : 1;
     const uint32_t nq = n_seqs / step;
-    static thread_local FprCache cache;
-    cache.reset(info.fpr);
+    static thread_local FprCache tl_cache;
+    tl_cache.reset(info.fpr);
+    FprCache *cache = &tl_cache;          // worker threads must share THIS instance, not their own thread_local
 
     // per-target Sizes (k-mers of the target) once
     std::vector<double> tsize((size_t)info.n_targets);
@@ -151,7 +152,7 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                         const double c = (double)h.count, sz = tsize[h.target];
                         const double tcov = c / sz;
                         if (!(tcov >= o->min_target_cov)) continue;              // U:7473-7474
-                        const double fpr = cache.get(n, (int)h.count);
+                        const double fpr = cache->get(n, (int)h.count);
                         if (!(fpr <= o->max_fpr)) continue;                      // U:7477-7478
                         kmcpg_match m;
                         m.query = q; m.target = h.target; m.count = h.count; m._pad = 0;

@@ -161,6 +161,16 @@ def test_engine_matches_oracle_defaults(gpu_ctx, oracle, request, dbname, ng, gl
     assert len(got.matches) > 1500
 
 
+def test_engine_large_batch_threaded_postfilter(gpu_ctx, oracle, small_db):
+    """> 4096 queries: the host post-filter runs on several threads"""
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    reads = helpers.make_reads(O, RSEED + 11, 12000, 40, 30000, GSEED)
+    got = _compare_engine(O, odb, gpu_ctx, reads)
+    assert len(got.matches) > 8000
+
+
 def test_engine_option_variants(gpu_ctx, oracle, small_db):
     O = oracle
     odb = O.DB(small_db)
