@@ -259,7 +259,7 @@ def main():
 
     # ---------------- value: device-resident inputs ----------------
     def dev_step(s):
-        return ctx.search_batch_ptr(d_reads.data_ptr() + s * step_bytes, d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes)
+        return ctx.search_batch_ptr(d_reads.data_ptr() + s * step_bytes, d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes, copy=False)
 
     with torch.cuda.stream(stream):
         for s in range(args.warmup):
@@ -279,7 +279,7 @@ def main():
     probe_launches = sum(o.probe_launches for o in outs)
     probe_bytes = sum(o.probe_row_bytes for o in outs)
     launches = sum(o.kernel_launches for o in outs)
-    n_hits = sum(len(o.hits) for o in outs)
+    n_hits = sum(o.n_hits for o in outs)
     value = world * READS_PER_STEP * args.steps / (ms_total / 1e3)       # units all ranks processed ÷ time (§5: read×shard probes)
 
     # ---------------- e2e: pinned host buffers through the engine ----------------
@@ -296,8 +296,8 @@ def main():
             barrier()
             t0 = time.perf_counter()
             for s in range(args.steps):
-                r = ctx.engine_search_ptr(h_ptr + s * step_bytes, h_off_ptr, READS_PER_STEP, eopts)
-                e2e_matches += len(r.matches)
+                r = ctx.engine_search_ptr(h_ptr + s * step_bytes, h_off_ptr, READS_PER_STEP, eopts, copy=False)
+                e2e_matches += r.n_matches
             torch.cuda.synchronize()
             e2e_s = time.perf_counter() - t0
             d2h_bytes = int(12 * n_hits / args.steps + 8 * READS_PER_STEP)
@@ -378,7 +378,7 @@ def main():
                             "rank0 H2D → ncclBroadcast → kmcpg_search_batch_device on every rank → host concat on rank 0 (gloo)"},
             "gpu_launches": int(launches), "clocks": clocks,
             "stage_ms_per_step": {"hash": sum(o.ms_hash for o in outs) / args.steps, "locs": sum(o.ms_locs for o in outs) / args.steps,
-                                  "probe": probe_ms / args.steps},
+                                  "probe": probe_ms / args.steps, "call_wall": sum(o.ms_total for o in outs) / args.steps},
         }
         print(json.dumps(line))
     ctx.close()

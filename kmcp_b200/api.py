@@ -177,6 +177,7 @@ class BatchHits:
     probe_launches: int
     probe_row_bytes: int
     kernel_launches: int
+    n_hits: int = 0
 
 
 @dataclass
@@ -189,6 +190,7 @@ class EngineResults:
     ms_gpu_total: float
     probe_row_bytes: int
     kernel_launches: int
+    n_matches: int = 0
 
 
 def _np_from(ptr, n, ctype_size, dtype):
@@ -264,10 +266,17 @@ class Context:
             setattr(p, k, v)
         return p
 
-    def _take_hits(self, h: Hits) -> BatchHits:
+    def _take_hits(self, h: Hits, copy: bool = True) -> BatchHits:
+        if not copy:       # timing harness: only the summary, no Python-side copies of the result arrays
+            out = BatchHits(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(int(h.n_hits), np.uint8)[:0], h.ms_hash, h.ms_locs, h.ms_probe,
+                            h.ms_total, int(h.probe_launches), int(h.probe_row_bytes), int(h.kernel_launches))
+            out.n_hits = int(h.n_hits)
+            self._L.kmcpg_free_hits(C.byref(h))
+            return out
         out = BatchHits(_np_from(h.n_kmers, h.n_queries, 4, np.int32), _np_from(h.query_len, h.n_queries, 4, np.int32),
                         _np_from(h.hits, h.n_hits, C.sizeof(Hit), HIT_DTYPE), h.ms_hash, h.ms_locs, h.ms_probe, h.ms_total,
                         int(h.probe_launches), int(h.probe_row_bytes), int(h.kernel_launches))
+        out.n_hits = int(h.n_hits)
         self._L.kmcpg_free_hits(C.byref(h))
         return out
 
@@ -279,14 +288,15 @@ class Context:
         self._check(self._L.kmcpg_search_batch(self._h, C.byref(p), buf.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(h)))
         return self._take_hits(h)
 
-    def search_batch_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, params: SearchParams, device: bool, seq_bytes: int = 0) -> BatchHits:
+    def search_batch_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, params: SearchParams, device: bool, seq_bytes: int = 0,
+                         copy: bool = True) -> BatchHits:
         """raw-pointer form (pinned host buffers or device buffers owned by the caller)"""
         h = Hits()
         if device:
             self._check(self._L.kmcpg_search_batch_device(self._h, C.byref(params), seq_ptr, off_ptr, n_seqs, seq_bytes, C.byref(h)))
         else:
             self._check(self._L.kmcpg_search_batch(self._h, C.byref(params), seq_ptr, off_ptr, n_seqs, C.byref(h)))
-        return self._take_hits(h)
+        return self._take_hits(h, copy)
 
     def generate_kmers(self, buf: np.ndarray, off: np.ndarray, sp: SketchParams) -> Tuple[np.ndarray, np.ndarray]:
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
@@ -320,14 +330,21 @@ class Context:
         off = np.ascontiguousarray(off, dtype=np.uint64)
         return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o)
 
-    def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts) -> EngineResults:
+    def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts, copy: bool = True) -> EngineResults:
         r = Results()
         self._check(self._L.kmcpg_engine_search(self._h, C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r)))
         nq = r.n_queries
+        if not copy:
+            out = EngineResults(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint64), np.zeros(0, MATCH_DTYPE),
+                                r.ms_gpu_total, int(r.probe_row_bytes), int(r.kernel_launches))
+            out.n_matches = int(r.n_matches)
+            self._L.kmcpg_free_results(C.byref(r))
+            return out
         out = EngineResults(_np_from(r.query_len, nq, 4, np.int32), _np_from(r.n_kmers, nq, 4, np.int32),
                             _np_from(r.k_used, nq, 4, np.int32), _np_from(r.match_off, nq + 1, 8, np.uint64),
                             _np_from(r.matches, r.n_matches, C.sizeof(Match), MATCH_DTYPE), r.ms_gpu_total,
                             int(r.probe_row_bytes), int(r.kernel_launches))
+        out.n_matches = int(r.n_matches)
         self._L.kmcpg_free_results(C.byref(r))
         return out
 

@@ -1,22 +1,28 @@
-// ctx.cu — context, database residency in HBM, the batch pipeline, and the C ABI of include/kmcp_gpu.h.
+// ctx.cu — context, database residency in HBM, the batch executor, and the C ABI of include/kmcp_gpu.h.
 //
 // Data layout in HBM (per resident block): the on-disk row-major bit matrix numSigs × numRowBytes
 // (X:307-349; row r byte i bit 7-j ⇔ Bloom bit r of target 8i+j) is re-pitched on upload so that every
 // row starts 16-byte aligned (128-byte aligned for rows wider than 256 B) and is zero padded; the disk
-// format is untouched.  One batch flows  H2D → hash → (sort+unique of long queries) → per block
-// {locs, probe} → radix sort of the hit list → D2H,  all on the context's stream.
+// format is untouched.
+//
+// Batch executor: a call is cut into parts (≤ 32 M k-mer slots each).  ALL kernels run in order on one
+// compute stream, so every launch can be timed exactly with events; transfers run on a copy stream.
+// Part i goes  [H2D] → slot scan → hash → (sort+unique of long queries) → verdict → per block {locs, probe}
+// and, once the host has read its hit count, → radix sort of the hit list → pack → [D2H into pinned results].
+// Two work sets alternate, and the kernels of part i+1 are enqueued BEFORE the host waits for part i's hit
+// count, so the round trip and the result copies hide behind the next part's probe kernel.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
-
-#include <chrono>
 
 #include "ctx_internal.h"
 
@@ -31,8 +37,6 @@ int fail(kmcpg_ctx *c, int code, const std::string &msg) {
     return code;
 }
 
-
-
 uint32_t pitch_for(uint32_t row_bytes) {
     if (row_bytes > 256) return (row_bytes + 127) / 128 * 128;
     return (row_bytes + 15) / 16 * 16;
@@ -41,8 +45,10 @@ uint32_t pitch_for(uint32_t row_bytes) {
 void layout_block(DeviceBlock &b, const BlockMeta &m) {
     b.pitch = pitch_for((uint32_t)m.row_bytes);
     b.row16 = ((uint32_t)m.row_bytes + 15) / 16;
+    uint32_t gmax = 8;                          // a task covers up to 128 B of a row
+    if (const char *e = getenv("KMCPG_PROBE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) gmax = (uint32_t)v; }
     uint32_t g = 1;
-    while (g < b.row16 && g < 8) g <<= 1;       // a task covers up to 128 B of a row
+    while (g < b.row16 && g < gmax) g <<= 1;
     b.G = g;
     b.chunks = (b.row16 + g - 1) / g;
     b.fm = make_fastmod(m.num_sigs);
@@ -52,11 +58,56 @@ void free_db(kmcpg_ctx *ctx) {
     for (auto &b : ctx->blocks) if (b.d_rows) cudaFree(b.d_rows);
     ctx->blocks.clear();
     ctx->resident_of.clear();
+    ctx->target_sizes.clear();
     ctx->has_db = false;
     ctx->sum_row_bytes = ctx->resident_bytes = ctx->disk_bytes = 0;
 }
 
-int planes_for(uint64_t max_n) {
+void WorkSet::release() {
+    for (DevBuf *b : {&seq, &off, &slot_cnt, &slot_off, &codes, &codes2, &locs, &ncodes, &qlen, &nk, &neff, &thresh, &hkeys, &hvals, &hkeys2, &hvals2,
+                      &hits, &counters, &tmp, &segb, &sege})
+        b->release();
+    h_off.release(); h_cnt.release();
+    for (cudaEvent_t *e : {&ev_in, &ev_a0, &ev_hash, &ev_a, &ev_cnt, &ev_sorted, &ev_b}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (auto e : probe_ev) cudaEventDestroy(e);
+    probe_ev.clear();
+}
+
+int pin_acquire(kmcpg_ctx *ctx, size_t bytes, PinBuf &out) {
+    if (bytes == 0) bytes = 8;
+    {
+        std::lock_guard<std::mutex> lk(ctx->pin_mu);
+        int best = -1;
+        for (size_t i = 0; i < ctx->pin_pool.size(); i++)
+            if (ctx->pin_pool[i].cap >= bytes && (best < 0 || ctx->pin_pool[i].cap < ctx->pin_pool[best].cap)) best = (int)i;
+        if (best >= 0 && ctx->pin_pool[best].cap <= bytes * 4 + (1u << 20)) {
+            out = ctx->pin_pool[best];
+            ctx->pin_pool.erase(ctx->pin_pool.begin() + best);
+            return KMCPG_OK;
+        }
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, KMCPG_ENOMEM, std::string("pinned allocation failed: ") + cudaGetErrorString(e)); }
+    out.p = p; out.cap = want;
+    return KMCPG_OK;
+}
+
+void pin_release(kmcpg_ctx *ctx, PinBuf &b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> lk(ctx->pin_mu);
+    ctx->pin_pool.push_back(b);
+    b = PinBuf();
+    while (ctx->pin_pool.size() > 12) {      // keep the pool small: drop the smallest buffer
+        size_t m = 0;
+        for (size_t i = 1; i < ctx->pin_pool.size(); i++) if (ctx->pin_pool[i].cap < ctx->pin_pool[m].cap) m = i;
+        cudaFreeHost(ctx->pin_pool[m].p);
+        ctx->pin_pool.erase(ctx->pin_pool.begin() + m);
+    }
+}
+
+static int planes_for(uint64_t max_n) {
     if (max_n <= 255) return 8;
     if (max_n <= 65535) return 16;
     if (max_n < (1ull << 24)) return 24;
@@ -65,28 +116,40 @@ int planes_for(uint64_t max_n) {
 
 struct Timing { float ms_hash = 0, ms_locs = 0, ms_probe = 0; uint64_t probe_bytes = 0; uint32_t probe_launches = 0; };
 
-int run_hash_stage(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out) {
+static int ensure_events(kmcpg_ctx *ctx, WorkSet &w) {
+    for (cudaEvent_t *e : {&w.ev_in, &w.ev_a0, &w.ev_hash, &w.ev_a, &w.ev_cnt, &w.ev_sorted, &w.ev_b})
+        if (!*e) CU(cudaEventCreate(e));
+    while (w.probe_ev.size() < ctx->blocks.size() * 3 + 3) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        w.probe_ev.push_back(e);
+    }
+    CU(w.h_cnt.ensure(64));
+    CU(w.counters.ensure(64));
+    return KMCPG_OK;
+}
+
+// slot scan → hash → (sort+unique) → verdict, all on the compute stream; sb.d_seq/d_off must already be valid there
+int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out) {
     const DbMeta &m = ctx->meta;
     cudaStream_t st = ctx->st;
-    CU(ctx->d_slot_cnt.ensure((sb.n_seqs + 1) * 8ull));
-    CU(ctx->d_slot_off.ensure((sb.n_seqs + 1) * 8ull));
-    CU(launch_slot_bounds(sb.d_off, sb.n_seqs, k, ctx->d_slot_cnt.as<uint64_t>(), st)); ctx->launches++;
+    int rc = ensure_events(ctx, w);
+    if (rc) return rc;
+    CU(w.slot_cnt.ensure((sb.n_seqs + 1) * 8ull));
+    CU(w.slot_off.ensure((sb.n_seqs + 1) * 8ull));
+    CU(launch_slot_bounds(sb.d_off, sb.n_seqs, k, w.slot_cnt.as<uint64_t>(), st)); ctx->launches++;
     size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_slot_cnt.as<uint64_t>(), ctx->d_slot_off.as<uint64_t>(), (int)(sb.n_seqs + 1), st);
-    CU(ctx->d_tmp.ensure(tmp));
-    CU(cub::DeviceScan::ExclusiveSum(ctx->d_tmp.p, tmp, ctx->d_slot_cnt.as<uint64_t>(), ctx->d_slot_off.as<uint64_t>(), (int)(sb.n_seqs + 1), st));
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, w.slot_cnt.as<uint64_t>(), w.slot_off.as<uint64_t>(), (int)(sb.n_seqs + 1), st);
+    CU(w.tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(w.tmp.p, tmp, w.slot_cnt.as<uint64_t>(), w.slot_off.as<uint64_t>(), (int)(sb.n_seqs + 1), st));
     ctx->launches += 2;
-    CU(ctx->d_codes.ensure(std::max<uint64_t>(sb.total_slots, 1) * 8));
-    CU(ctx->d_ncodes.ensure(std::max<uint32_t>(nq, 1) * 4ull));
-    CU(ctx->d_qlen.ensure(std::max<uint32_t>(nq, 1) * 4ull));
-    CU(ctx->d_nk.ensure(std::max<uint32_t>(nq, 1) * 4ull));
-    CU(ctx->d_neff.ensure(std::max<uint32_t>(nq, 1) * 4ull));
-    CU(ctx->d_thresh.ensure(std::max<uint32_t>(nq, 1) * 4ull));
+    CU(w.codes.ensure(std::max<uint64_t>(sb.total_slots, 1) * 8));
+    for (DevBuf *b : {&w.ncodes, &w.qlen, &w.nk, &w.neff, &w.thresh}) CU(b->ensure(std::max<uint32_t>(nq, 1) * 4ull));
 
     HashArgs ha;
     memset(&ha, 0, sizeof(ha));
-    ha.seq = sb.d_seq; ha.seq_off = sb.d_off; ha.slot_off = ctx->d_slot_off.as<uint64_t>();
-    ha.codes = ctx->d_codes.as<uint64_t>(); ha.n_codes = ctx->d_ncodes.as<uint32_t>(); ha.query_len = ctx->d_qlen.as<int32_t>();
+    ha.seq = sb.d_seq; ha.seq_off = sb.d_off; ha.slot_off = w.slot_off.as<uint64_t>();
+    ha.codes = w.codes.as<uint64_t>(); ha.n_codes = w.ncodes.as<uint32_t>(); ha.query_len = w.qlen.as<int32_t>();
     ha.n_queries = nq; ha.paired = p.paired; ha.mate_select = p.mate_select; ha.k = k; ha.canonical = m.canonical;
     ha.scaled = m.scaled;
     ha.max_hash = ~0ull;
@@ -98,29 +161,30 @@ int run_hash_stage(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const Su
     ha.min_query_len = p.min_query_len;
     CU(launch_hash(ha, st)); ctx->launches++;
 
-    uint64_t *codes = ctx->d_codes.as<uint64_t>();
+    uint64_t *codes = w.codes.as<uint64_t>();
     int do_unique = 0;
     if (sb.max_query_slots > (uint64_t)p.dedup_threshold && sb.total_slots > 0) {
         // U:874-908: sort + unique of queries with more than dedup_threshold k-mers
         if (sb.total_slots >= (1ull << 31)) return fail(ctx, KMCPG_EUNSUPPORTED, "sub-batch too large for the dedup sort");
-        CU(ctx->d_segb.ensure(nq * 4ull)); CU(ctx->d_sege.ensure(nq * 4ull));
-        CU(ctx->d_codes2.ensure(sb.total_slots * 8));
-        CU(launch_sort_segments(ctx->d_slot_off.as<uint64_t>(), ctx->d_ncodes.as<uint32_t>(), nq, p.paired, p.dedup_threshold,
-                                ctx->d_segb.as<int>(), ctx->d_sege.as<int>(), st));
-        CU(cudaMemcpyAsync(ctx->d_codes2.p, ctx->d_codes.p, sb.total_slots * 8, cudaMemcpyDeviceToDevice, st));
+        CU(w.segb.ensure(nq * 4ull)); CU(w.sege.ensure(nq * 4ull));
+        CU(w.codes2.ensure(sb.total_slots * 8));
+        CU(launch_sort_segments(w.slot_off.as<uint64_t>(), w.ncodes.as<uint32_t>(), nq, p.paired, p.dedup_threshold, w.segb.as<int>(), w.sege.as<int>(), st));
+        CU(cudaMemcpyAsync(w.codes2.p, w.codes.p, sb.total_slots * 8, cudaMemcpyDeviceToDevice, st));
         size_t t2 = 0;
-        cub::DeviceSegmentedSort::SortKeys(nullptr, t2, ctx->d_codes.as<uint64_t>(), ctx->d_codes2.as<uint64_t>(), (int)sb.total_slots,
-                                           (int)nq, ctx->d_segb.as<int>(), ctx->d_sege.as<int>(), st);
-        CU(ctx->d_tmp.ensure(t2));
-        CU(cub::DeviceSegmentedSort::SortKeys(ctx->d_tmp.p, t2, ctx->d_codes.as<uint64_t>(), ctx->d_codes2.as<uint64_t>(),
-                                              (int)sb.total_slots, (int)nq, ctx->d_segb.as<int>(), ctx->d_sege.as<int>(), st));
+        cub::DeviceSegmentedSort::SortKeys(nullptr, t2, w.codes.as<uint64_t>(), w.codes2.as<uint64_t>(), (int)sb.total_slots, (int)nq,
+                                           w.segb.as<int>(), w.sege.as<int>(), st);
+        CU(w.tmp.ensure(t2));
+        CU(cub::DeviceSegmentedSort::SortKeys(w.tmp.p, t2, w.codes.as<uint64_t>(), w.codes2.as<uint64_t>(), (int)sb.total_slots, (int)nq,
+                                              w.segb.as<int>(), w.sege.as<int>(), st));
         ctx->launches += 4;
-        codes = ctx->d_codes2.as<uint64_t>();
+        codes = w.codes2.as<uint64_t>();
         do_unique = 1;
     }
+    CU(cudaMemsetAsync(w.counters.p, 0, 16, st));     // [0] hit count, [1] Σ n_kmers
     FinalizeArgs fa;
-    fa.codes = codes; fa.slot_off = ctx->d_slot_off.as<uint64_t>(); fa.n_codes = ctx->d_ncodes.as<uint32_t>();
-    fa.n_kmers_out = ctx->d_nk.as<int32_t>(); fa.n_eff = ctx->d_neff.as<uint32_t>(); fa.thresh = ctx->d_thresh.as<uint32_t>();
+    fa.codes = codes; fa.slot_off = w.slot_off.as<uint64_t>(); fa.n_codes = w.ncodes.as<uint32_t>();
+    fa.n_kmers_out = w.nk.as<int32_t>(); fa.n_eff = w.neff.as<uint32_t>(); fa.thresh = w.thresh.as<uint32_t>();
+    fa.n_sum = w.counters.as<unsigned long long>() + 1;
     fa.n_queries = nq; fa.paired = p.paired; fa.dedup_threshold = p.dedup_threshold; fa.do_unique = do_unique;
     fa.min_matched = p.min_matched; fa.min_query_cov = p.min_query_cov;
     CU(launch_finalize(fa, st)); ctx->launches++;
@@ -128,99 +192,151 @@ int run_hash_stage(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const Su
     return KMCPG_OK;
 }
 
-int run_subbatch(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const SubBatch &sb, HitsPriv &res, Timing &tm) {
+// per block {locs, probe} on the compute stream, then the counters travel to the host on the copy stream
+static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p) {
     cudaStream_t st = ctx->st;
-    const uint32_t nq = p.paired ? sb.n_seqs / 2 : sb.n_seqs;
-    if (nq == 0) return KMCPG_OK;
-    CU(cudaEventRecord(ctx->ev[0], st));
-    uint64_t *codes = nullptr;
-    int rc = run_hash_stage(ctx, p, k, sb, nq, &codes);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev[1], st));
-
     const int H = ctx->meta.num_hashes;
-    CU(ctx->d_locs.ensure(std::max<uint64_t>(sb.total_slots, 1) * 4ull * H));
-    CU(ctx->d_hitcount.ensure(8));
-    uint64_t cap = std::max<uint64_t>(1u << 20, 4ull * nq);
-    if (ctx->d_hkeys.cap / 8 > cap) cap = ctx->d_hkeys.cap / 8;
-    uint64_t n_hits = 0;
-    const int planes = planes_for(sb.max_query_slots);
-    for (int attempt = 0; attempt < 3; attempt++) {
-        CU(ctx->d_hkeys.ensure(cap * 8)); CU(ctx->d_hvals.ensure(cap * 4));
-        CU(cudaMemsetAsync(ctx->d_hitcount.p, 0, 8, st));
-        while (ctx->probe_ev.size() < ctx->blocks.size() * 3) {
-            cudaEvent_t e;
-            CU(cudaEventCreate(&e));
-            ctx->probe_ev.push_back(e);
-        }
-        size_t bi = 0;
-        for (auto &b : ctx->blocks) {
-            const BlockMeta &bm = ctx->meta.blocks[b.meta_idx];
-            CU(cudaEventRecord(ctx->probe_ev[bi * 3], st));
-            CU(launch_locs(codes, sb.total_slots, H, b.fm, ctx->d_locs.as<uint32_t>(), st)); ctx->launches++;
-            CU(cudaEventRecord(ctx->probe_ev[bi * 3 + 1], st));
-            ProbeArgs pa;
-            memset(&pa, 0, sizeof(pa));
-            pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row16 = b.row16; pa.lanes_per_task = b.G; pa.chunks = b.chunks;
-            pa.n_names = (uint32_t)bm.n_names; pa.target_base = (uint32_t)bm.target_base; pa.num_hashes = H;
-            pa.locs = ctx->d_locs.as<uint32_t>(); pa.slot_off = ctx->d_slot_off.as<uint64_t>();
-            pa.n_eff = ctx->d_neff.as<uint32_t>(); pa.thresh = ctx->d_thresh.as<uint32_t>(); pa.n_queries = nq; pa.paired = p.paired;
-            pa.hit_keys = ctx->d_hkeys.as<uint64_t>(); pa.hit_vals = ctx->d_hvals.as<uint32_t>();
-            pa.hit_count = ctx->d_hitcount.as<unsigned long long>(); pa.hit_cap = cap; pa.dense_counts = nullptr; pa.planes = planes;
-            CU(launch_probe(pa, ctx->sm_count, st)); ctx->launches++;
-            CU(cudaEventRecord(ctx->probe_ev[bi * 3 + 2], st));
-            bi++;
-        }
-        CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_hitcount.p, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        n_hits = *ctx->h_small.as<uint64_t>();
-        for (size_t i = 0; i < ctx->blocks.size(); i++) {
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, ctx->probe_ev[i * 3], ctx->probe_ev[i * 3 + 1]);
-            cudaEventElapsedTime(&b, ctx->probe_ev[i * 3 + 1], ctx->probe_ev[i * 3 + 2]);
-            tm.ms_locs += a; tm.ms_probe += b; tm.probe_launches++;
-        }
-        if (n_hits <= cap) break;
-        cap = n_hits + n_hits / 4 + 1024;            // hit list overflowed: grow and redo the probe phase
-        if (attempt == 2) return fail(ctx, KMCPG_ENOMEM, "hit list keeps overflowing");
+    CU(w.locs.ensure(std::max<uint64_t>(w.sb.total_slots, 1) * 4ull * H));
+    CU(w.hkeys.ensure(w.cap * 8)); CU(w.hvals.ensure(w.cap * 4));
+    CU(cudaMemsetAsync(w.counters.p, 0, 8, st));
+    size_t bi = 0;
+    for (auto &b : ctx->blocks) {
+        const BlockMeta &bm = ctx->meta.blocks[b.meta_idx];
+        CU(cudaEventRecord(w.probe_ev[bi * 3], st));
+        CU(launch_locs(w.codes_ptr, w.sb.total_slots, H, b.fm, w.locs.as<uint32_t>(), st)); ctx->launches++;
+        CU(cudaEventRecord(w.probe_ev[bi * 3 + 1], st));
+        ProbeArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row16 = b.row16; pa.lanes_per_task = b.G; pa.chunks = b.chunks;
+        pa.n_names = (uint32_t)bm.n_names; pa.target_base = (uint32_t)bm.target_base; pa.num_hashes = H;
+        pa.locs = w.locs.as<uint32_t>(); pa.slot_off = w.slot_off.as<uint64_t>();
+        pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = w.nq; pa.paired = p.paired;
+        pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
+        pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = w.cap; pa.dense_counts = nullptr; pa.planes = w.planes;
+        CU(launch_probe(pa, ctx->sm_count, st)); ctx->launches++;
+        CU(cudaEventRecord(w.probe_ev[bi * 3 + 2], st));
+        bi++;
     }
-    CU(cudaEventRecord(ctx->ev[2], st));
-
-    // canonical order: sort by (query, target)
-    const size_t old_hits = res.hits.size(), old_q = res.n_kmers.size();
-    res.n_kmers.resize(old_q + nq); res.query_len.resize(old_q + nq);
-    if (n_hits) {
-        CU(ctx->d_hkeys2.ensure(n_hits * 8)); CU(ctx->d_hvals2.ensure(n_hits * 4)); CU(ctx->d_hits.ensure(n_hits * sizeof(kmcpg_hit)));
-        int qbits = 1; while ((1ull << qbits) < nq) qbits++;
-        size_t t3 = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, t3, ctx->d_hkeys.as<uint64_t>(), ctx->d_hkeys2.as<uint64_t>(), ctx->d_hvals.as<uint32_t>(),
-                                        ctx->d_hvals2.as<uint32_t>(), (int64_t)n_hits, 0, 32 + qbits, st);
-        CU(ctx->d_tmp.ensure(t3));
-        CU(cub::DeviceRadixSort::SortPairs(ctx->d_tmp.p, t3, ctx->d_hkeys.as<uint64_t>(), ctx->d_hkeys2.as<uint64_t>(),
-                                           ctx->d_hvals.as<uint32_t>(), ctx->d_hvals2.as<uint32_t>(), (int64_t)n_hits, 0, 32 + qbits, st));
-        CU(launch_pack_hits(ctx->d_hkeys2.as<uint64_t>(), ctx->d_hvals2.as<uint32_t>(), n_hits, sb.query_base, ctx->d_hits.as<kmcpg_hit>(), st));
-        ctx->launches += 4;
-        res.hits.resize(old_hits + n_hits);
-        CU(cudaMemcpyAsync(res.hits.data() + old_hits, ctx->d_hits.p, n_hits * sizeof(kmcpg_hit), cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaMemcpyAsync(res.n_kmers.data() + old_q, ctx->d_nk.p, nq * 4ull, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(res.query_len.data() + old_q, ctx->d_qlen.p, nq * 4ull, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    float a = 0;
-    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-    tm.ms_hash += a;
-    uint64_t nsum = 0;
-    for (uint32_t i = 0; i < nq; i++) nsum += (uint64_t)res.n_kmers[old_q + i];
-    tm.probe_bytes += nsum * (uint64_t)H * (uint64_t)ctx->sum_row_bytes;
+    CU(cudaEventRecord(w.ev_a, st));
+    CU(cudaStreamWaitEvent(ctx->copy_st, w.ev_a, 0));
+    CU(cudaMemcpyAsync(w.h_cnt.p, w.counters.p, 16, cudaMemcpyDeviceToHost, ctx->copy_st));
+    CU(cudaEventRecord(w.ev_cnt, ctx->copy_st));
     return KMCPG_OK;
 }
 
-void fill_out(kmcpg_hits *out, HitsPriv *priv, const Timing &tm, float ms_total, uint32_t launches) {
-    out->n_queries = (uint32_t)priv->n_kmers.size();
-    out->n_hits = priv->hits.size();
-    out->n_kmers = priv->n_kmers.data();
-    out->query_len = priv->query_len.data();
-    out->hits = priv->hits.data();
+// stage A of a part: everything up to the probes.  host_seq != nullptr → stage the inputs through the copy stream.
+static int enqueue_part(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb_in, const uint8_t *host_seq,
+                        const uint64_t *host_off, uint64_t host_bytes) {
+    cudaStream_t st = ctx->st;
+    int rc = ensure_events(ctx, w);
+    if (rc) return rc;
+    w.sb = sb_in;
+    w.nq = p.paired ? sb_in.n_seqs / 2 : sb_in.n_seqs;
+    if (host_seq) {
+        CU(w.h_off.ensure((sb_in.n_seqs + 1) * 8ull));
+        CU(w.off.ensure((sb_in.n_seqs + 1) * 8ull));
+        CU(w.seq.ensure(std::max<uint64_t>(host_bytes, 1) + 64));
+        uint64_t *ho = w.h_off.as<uint64_t>();
+        const uint64_t base = host_off[0];
+        for (uint32_t i = 0; i <= sb_in.n_seqs; i++) ho[i] = host_off[i] - base;
+        CU(cudaMemcpyAsync(w.off.p, ho, (sb_in.n_seqs + 1) * 8ull, cudaMemcpyHostToDevice, ctx->copy_st));
+        if (host_bytes) CU(cudaMemcpyAsync(w.seq.p, host_seq + base, host_bytes, cudaMemcpyHostToDevice, ctx->copy_st));
+        CU(cudaEventRecord(w.ev_in, ctx->copy_st));
+        CU(cudaStreamWaitEvent(st, w.ev_in, 0));
+        w.sb.d_seq = w.seq.as<uint8_t>();
+        w.sb.d_off = w.off.as<uint64_t>();
+    }
+    CU(cudaEventRecord(w.ev_a0, st));
+    rc = run_hash_stage(ctx, w, p, k, w.sb, w.nq, &w.codes_ptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(w.ev_hash, st));
+    w.planes = planes_for(w.sb.max_query_slots);
+    w.cap = std::max<uint64_t>(1u << 20, 4ull * w.nq);
+    if (w.hkeys.cap / 8 > w.cap) w.cap = w.hkeys.cap / 8;
+    rc = enqueue_probes(ctx, w, p);
+    if (rc) return rc;
+    w.busy = true;
+    return KMCPG_OK;
+}
+
+static int grow_hits(kmcpg_ctx *ctx, HitsPriv &res, uint64_t need) {
+    if (res.hits.cap >= need * sizeof(kmcpg_hit)) return KMCPG_OK;
+    // results already copied (or in flight on the copy stream) must land before they are moved
+    CU(cudaStreamSynchronize(ctx->copy_st));
+    PinBuf nb;
+    int rc = pin_acquire(ctx, std::max<uint64_t>(need * 2, 1u << 16) * sizeof(kmcpg_hit), nb);
+    if (rc) return rc;
+    if (res.nh) memcpy(nb.p, res.hits.p, res.nh * sizeof(kmcpg_hit));
+    pin_release(ctx, res.hits);
+    res.hits = nb;
+    return KMCPG_OK;
+}
+
+// stage B: hit count known → sort, pack, results to the host (asynchronously, on the copy stream)
+static int finish_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, HitsPriv &res, Timing &tm) {
+    cudaStream_t st = ctx->st;
+    for (int attempt = 0;; attempt++) {
+        CU(cudaEventSynchronize(w.ev_cnt));
+        w.n_hits = w.h_cnt.as<uint64_t>()[0];
+        for (size_t i = 0; i < ctx->blocks.size(); i++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, w.probe_ev[i * 3], w.probe_ev[i * 3 + 1]);
+            cudaEventElapsedTime(&b, w.probe_ev[i * 3 + 1], w.probe_ev[i * 3 + 2]);
+            tm.ms_locs += a; tm.ms_probe += b; tm.probe_launches++;
+        }
+        if (w.n_hits <= w.cap) break;
+        if (attempt == 2) return fail(ctx, KMCPG_ENOMEM, "hit list keeps overflowing");
+        // rare: the hit list overflowed.  Drain, grow, redo the probe phase of this part.
+        CU(cudaStreamSynchronize(st));
+        CU(cudaStreamSynchronize(ctx->copy_st));
+        w.cap = w.n_hits + w.n_hits / 4 + 1024;
+        int rc = enqueue_probes(ctx, w, p);
+        if (rc) return rc;
+    }
+    float a = 0;
+    cudaEventElapsedTime(&a, w.ev_a0, w.ev_hash);
+    tm.ms_hash += a;
+    tm.probe_bytes += w.h_cnt.as<uint64_t>()[1] * (uint64_t)ctx->meta.num_hashes * (uint64_t)ctx->sum_row_bytes;
+
+    const uint64_t n_hits = w.n_hits;
+    w.hit_dst = res.nh;
+    if (n_hits) {
+        int rc = grow_hits(ctx, res, res.nh + n_hits);
+        if (rc) return rc;
+        CU(w.hkeys2.ensure(n_hits * 8)); CU(w.hvals2.ensure(n_hits * 4)); CU(w.hits.ensure(n_hits * sizeof(kmcpg_hit)));
+        int qbits = 1; while ((1ull << qbits) < w.nq) qbits++;
+        size_t t3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
+                                        (int64_t)n_hits, 0, 32 + qbits, st);
+        CU(w.tmp.ensure(t3));
+        CU(cub::DeviceRadixSort::SortPairs(w.tmp.p, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
+                                           (int64_t)n_hits, 0, 32 + qbits, st));
+        CU(launch_pack_hits(w.hkeys2.as<uint64_t>(), w.hvals2.as<uint32_t>(), n_hits, w.sb.query_base, w.hits.as<kmcpg_hit>(), st));
+        ctx->launches += 4;
+    }
+    CU(cudaEventRecord(w.ev_sorted, st));
+    CU(cudaStreamWaitEvent(ctx->copy_st, w.ev_sorted, 0));
+    if (n_hits) CU(cudaMemcpyAsync((kmcpg_hit *)res.hits.p + res.nh, w.hits.p, n_hits * sizeof(kmcpg_hit), cudaMemcpyDeviceToHost, ctx->copy_st));
+    CU(cudaMemcpyAsync((int32_t *)res.nk.p + w.sb.query_base, w.nk.p, w.nq * 4ull, cudaMemcpyDeviceToHost, ctx->copy_st));
+    CU(cudaMemcpyAsync((int32_t *)res.ql.p + w.sb.query_base, w.qlen.p, w.nq * 4ull, cudaMemcpyDeviceToHost, ctx->copy_st));
+    CU(cudaEventRecord(w.ev_b, ctx->copy_st));
+    res.nh += n_hits;
+    return KMCPG_OK;
+}
+
+static int wait_part(kmcpg_ctx *ctx, WorkSet &w) {
+    if (!w.busy) return KMCPG_OK;
+    CU(cudaEventSynchronize(w.ev_b));
+    w.busy = false;
+    return KMCPG_OK;
+}
+
+static void fill_out(kmcpg_hits *out, HitsPriv *priv, const Timing &tm, float ms_total, uint32_t launches) {
+    out->n_queries = priv->nq;
+    out->n_hits = priv->nh;
+    out->n_kmers = (int32_t *)priv->nk.p;
+    out->query_len = (int32_t *)priv->ql.p;
+    out->hits = (kmcpg_hit *)priv->hits.p;
     out->ms_hash = tm.ms_hash; out->ms_locs = tm.ms_locs; out->ms_probe = tm.ms_probe; out->ms_total = ms_total;
     out->probe_launches = tm.probe_launches;
     out->probe_row_bytes = tm.probe_bytes;
@@ -228,7 +344,13 @@ void fill_out(kmcpg_hits *out, HitsPriv *priv, const Timing &tm, float ms_total,
     out->_priv = priv;
 }
 
-int check_search_args(kmcpg_ctx *ctx, const kmcpg_search_params *p, const void *seq, const void *off, uint32_t n_seqs, kmcpg_hits *out, int *k) {
+static void drop_priv(HitsPriv *priv) {
+    if (!priv) return;
+    if (priv->ctx) { pin_release(priv->ctx, priv->nk); pin_release(priv->ctx, priv->ql); pin_release(priv->ctx, priv->hits); }
+    delete priv;
+}
+
+static int check_search_args(kmcpg_ctx *ctx, const kmcpg_search_params *p, const void *seq, const void *off, uint32_t n_seqs, kmcpg_hits *out, int *k) {
     if (!ctx) return KMCPG_EINVAL;
     if (!p || !out || (n_seqs && (!seq || !off))) return fail(ctx, KMCPG_EINVAL, "null argument");
     if (!ctx->has_db) return fail(ctx, KMCPG_EINVAL, "no database open");
@@ -239,6 +361,85 @@ int check_search_args(kmcpg_ctx *ctx, const kmcpg_search_params *p, const void *
     if (ctx->meta.minimizer || ctx->meta.syncmer) return fail(ctx, KMCPG_EUNSUPPORTED, "minimizer/syncmer sketches are not on the device path yet");
     if (p->min_matched < 1) return fail(ctx, KMCPG_EINVAL, "min_matched must be >= 1");
     if (!(p->min_query_cov >= 0 && p->min_query_cov <= 1)) return fail(ctx, KMCPG_EINVAL, "min_query_cov must be in [0,1]");
+    return KMCPG_OK;
+}
+
+struct Part { uint32_t a, b; uint64_t slots, maxq; };
+
+static const uint64_t PART_SLOTS = 32ull << 20;   // k-mer slots per part (≈ 250 k reads of 150 bp)
+static const uint32_t PART_SEQS = 2u << 20;
+
+// greedy parts [a, b) from host-visible offsets
+static int cut_parts(kmcpg_ctx *ctx, const uint64_t *off, uint32_t n_seqs, uint32_t step, int k, std::vector<Part> &parts) {
+    for (uint32_t a = 0; a < n_seqs;) {
+        uint64_t slots = 0, maxq = 0;
+        uint32_t b = a;
+        while (b < n_seqs && (b - a) < PART_SEQS) {
+            uint64_t qs = 0;
+            for (uint32_t m = 0; m < step; m++) {
+                if (off[b + m + 1] < off[b + m]) return fail(ctx, KMCPG_EINVAL, "offsets must be non-decreasing");
+                uint64_t len = off[b + m + 1] - off[b + m];
+                qs += len >= (uint64_t)k ? len - k + 1 : 0;
+            }
+            if (b > a && slots + qs > PART_SLOTS) break;
+            slots += qs; maxq = std::max(maxq, qs);
+            b += step;
+        }
+        parts.push_back({a, b, slots, maxq});
+        a = b;
+    }
+    return KMCPG_OK;
+}
+
+// runs the two-deep pipeline over the parts
+static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const std::vector<Part> &parts, const uint8_t *host_seq, const uint64_t *host_off,
+                     const uint8_t *d_seq, const uint64_t *d_off, HitsPriv &res, Timing &tm) {
+    const uint32_t step = p.paired ? 2 : 1;
+    int rc = KMCPG_OK;
+    for (size_t i = 0; i <= parts.size(); i++) {
+        if (i < parts.size()) {
+            WorkSet &w = ctx->ws[i & 1];
+            rc = wait_part(ctx, w);                       // results of part i-2 have left this work set
+            if (rc) return rc;
+            const Part &pt = parts[i];
+            SubBatch sb{d_seq, d_off ? d_off + pt.a : nullptr, pt.b - pt.a, pt.slots, pt.maxq, pt.a / step};
+            if (host_seq) rc = enqueue_part(ctx, w, p, k, sb, host_seq, host_off + pt.a, host_off[pt.b] - host_off[pt.a]);
+            else rc = enqueue_part(ctx, w, p, k, sb, nullptr, nullptr, 0);
+            if (rc) return rc;
+        }
+        if (i >= 1) {
+            rc = finish_probes(ctx, ctx->ws[(i - 1) & 1], p, res, tm);
+            if (rc) return rc;
+        }
+    }
+    for (auto &w : ctx->ws) { rc = wait_part(ctx, w); if (rc) return rc; }
+    return KMCPG_OK;
+}
+
+static void abort_parts(kmcpg_ctx *ctx) {
+    cudaStreamSynchronize(ctx->st);
+    cudaStreamSynchronize(ctx->copy_st);
+    for (auto &w : ctx->ws) w.busy = false;
+}
+
+static int search_common(kmcpg_ctx *ctx, const kmcpg_search_params *p, int k, const uint64_t *host_off, uint32_t n_seqs, const uint8_t *host_seq,
+                         const uint8_t *d_seq, const uint64_t *d_off, kmcpg_hits *out) {
+    auto t0 = std::chrono::steady_clock::now();
+    const uint32_t launches0 = ctx->launches;
+    const uint32_t step = p->paired ? 2 : 1;
+    std::vector<Part> parts;
+    int rc = cut_parts(ctx, host_off, n_seqs, step, k, parts);
+    if (rc) return rc;
+    HitsPriv *priv = new HitsPriv();
+    priv->ctx = ctx; priv->nq = n_seqs / step;
+    rc = pin_acquire(ctx, std::max<uint32_t>(priv->nq, 1) * 4ull, priv->nk);
+    if (!rc) rc = pin_acquire(ctx, std::max<uint32_t>(priv->nq, 1) * 4ull, priv->ql);
+    if (!rc) rc = pin_acquire(ctx, std::max<uint64_t>(1u << 16, 2ull * priv->nq) * sizeof(kmcpg_hit), priv->hits);
+    Timing tm;
+    if (!rc) rc = run_parts(ctx, *p, k, parts, host_seq, host_off, d_seq, d_off, *priv, tm);
+    if (rc) { abort_parts(ctx); drop_priv(priv); return rc; }
+    float ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fill_out(out, priv, tm, ms_total, ctx->launches - launches0);
     return KMCPG_OK;
 }
 
@@ -276,8 +477,8 @@ int kmcpg_create(int device, kmcpg_ctx **out) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     ctx->st = ctx->own_st;
-    for (auto &ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = ctx->h_small.ensure(256)) != cudaSuccess) return bail(e, "cudaMallocHost");
     *out = ctx;
     return KMCPG_OK;
@@ -296,15 +497,15 @@ int kmcpg_close(kmcpg_ctx *ctx) {
     if (!ctx) return KMCPG_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
+    cudaStreamSynchronize(ctx->copy_st);
     free_db(ctx);
-    for (DevBuf *b : {&ctx->d_seq, &ctx->d_off, &ctx->d_slot_cnt, &ctx->d_slot_off, &ctx->d_codes, &ctx->d_codes2, &ctx->d_locs, &ctx->d_ncodes,
-                      &ctx->d_qlen, &ctx->d_nk, &ctx->d_neff, &ctx->d_thresh, &ctx->d_hkeys, &ctx->d_hvals, &ctx->d_hkeys2, &ctx->d_hvals2,
-                      &ctx->d_hits, &ctx->d_hitcount, &ctx->d_tmp, &ctx->d_segb, &ctx->d_sege, &ctx->d_dense, &ctx->d_scal})
-        b->release();
-    ctx->h_stage.release(); ctx->h_off.release(); ctx->h_small.release();
-    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    for (auto &ev : ctx->probe_ev) cudaEventDestroy(ev);
+    for (auto &w : ctx->ws) w.release();
+    for (DevBuf *b : {&ctx->d_tmp, &ctx->d_dense, &ctx->d_scal, &ctx->d_genome}) b->release();
+    ctx->h_stage.release(); ctx->h_small.release();
+    for (auto &b : ctx->pin_pool) cudaFreeHost(b.p);
+    ctx->pin_pool.clear();
     if (ctx->own_st) cudaStreamDestroy(ctx->own_st);
+    if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     delete ctx;
     return KMCPG_OK;
 }
@@ -342,7 +543,7 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
     for (size_t i = 0; i < m.blocks.size(); i++) {
         if (owner[i] != rank) continue;
         const BlockMeta &bm = m.blocks[i];
-        if (bm.num_sigs >= (1ull << 32)) return fail(ctx, KMCPG_EUNSUPPORTED, "blocks with >= 2^32 signatures are not supported");
+        if (bm.num_sigs >= (1ull << 32) - 1) return fail(ctx, KMCPG_EUNSUPPORTED, "blocks with >= 2^32-1 signatures are not supported");
         DeviceBlock b;
         b.meta_idx = (int)i;
         layout_block(b, bm);
@@ -370,6 +571,9 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
         ctx->resident_bytes += (int64_t)b.bytes;
         ctx->disk_bytes += (int64_t)(bm.num_sigs * (uint64_t)bm.row_bytes);
     }
+    ctx->target_sizes.resize((size_t)m.n_targets);
+    for (auto &bm : m.blocks)
+        for (int c = 0; c < bm.n_names; c++) ctx->target_sizes[(size_t)bm.target_base + c] = (double)bm.sizes[c];
     ctx->has_db = true;
     return KMCPG_OK;
 }
@@ -390,7 +594,6 @@ int kmcpg_db_info(const kmcpg_ctx *ctx, kmcpg_db_info_t *o) {
 int kmcpg_target(const kmcpg_ctx *ctx, int64_t g, kmcpg_target_t *o) {
     if (!ctx || !o || !ctx->has_db) return KMCPG_EINVAL;
     const auto &bl = ctx->meta.blocks;
-    // blocks are few: binary search over target_base
     size_t lo = 0, hi = bl.size();
     while (lo + 1 < hi) { size_t mid = (lo + hi) / 2; if (bl[mid].target_base <= g) lo = mid; else hi = mid; }
     if (bl.empty() || g < bl[lo].target_base || g >= bl[lo].target_base + bl[lo].n_names) return KMCPG_EINVAL;
@@ -399,6 +602,9 @@ int kmcpg_target(const kmcpg_ctx *ctx, int64_t g, kmcpg_target_t *o) {
     o->block = (int32_t)lo; o->col = c; o->resident = ctx->resident_of[lo] >= 0;
     return KMCPG_OK;
 }
+
+// internal (engine.cpp): Sizes[t] of every target as float64, valid while the DB is open
+const double *kmcpg_internal_target_sizes(const kmcpg_ctx *ctx) { return ctx && ctx->has_db ? ctx->target_sizes.data() : nullptr; }
 
 void kmcpg_default_params(kmcpg_search_params *p) {
     if (!p) return;
@@ -413,49 +619,7 @@ int kmcpg_search_batch(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     memset(out, 0, sizeof(*out));
-    HitsPriv *priv = new HitsPriv();
-    Timing tm;
-    const uint32_t launches0 = ctx->launches;
-    auto t0 = std::chrono::steady_clock::now();
-    const uint64_t MAX_SLOTS = 64ull << 20;
-    const uint32_t MAX_SEQS = 4u << 20;
-    const uint32_t step = p->paired ? 2 : 1;
-    uint32_t a = 0;
-    while (a < n_seqs) {
-        // greedy sub-batch [a, b)
-        uint64_t slots = 0, maxq = 0;
-        uint32_t b = a;
-        while (b < n_seqs && (b - a) < MAX_SEQS) {
-            uint64_t qs = 0;
-            for (uint32_t m = 0; m < step; m++) {
-                uint64_t len = off[b + m + 1] - off[b + m];
-                if (off[b + m + 1] < off[b + m]) { delete priv; return fail(ctx, KMCPG_EINVAL, "offsets must be non-decreasing"); }
-                qs += len >= (uint64_t)k ? len - k + 1 : 0;
-            }
-            if (b > a && slots + qs > MAX_SLOTS) break;
-            slots += qs; maxq = std::max(maxq, qs);
-            b += step;
-        }
-        const uint32_t ns = b - a;
-        const uint64_t nbytes = off[b] - off[a];
-        // stage offsets (rebased) + bytes, H2D
-        cudaError_t e = ctx->h_off.ensure((ns + 1) * 8ull);
-        if (e == cudaSuccess) e = ctx->d_off.ensure((ns + 1) * 8ull);
-        if (e == cudaSuccess) e = ctx->d_seq.ensure(std::max<uint64_t>(nbytes, 1) + 64);
-        if (e != cudaSuccess) { delete priv; CU(e); }
-        uint64_t *ho = ctx->h_off.as<uint64_t>();
-        for (uint32_t i = 0; i <= ns; i++) ho[i] = off[a + i] - off[a];
-        e = cudaMemcpyAsync(ctx->d_off.p, ho, (ns + 1) * 8ull, cudaMemcpyHostToDevice, ctx->st);
-        if (e == cudaSuccess && nbytes) e = cudaMemcpyAsync(ctx->d_seq.p, seq + off[a], nbytes, cudaMemcpyHostToDevice, ctx->st);
-        if (e != cudaSuccess) { delete priv; CU(e); }
-        SubBatch sb{ctx->d_seq.as<uint8_t>(), ctx->d_off.as<uint64_t>(), ns, slots, maxq, a / step};
-        rc = run_subbatch(ctx, *p, k, sb, *priv, tm);
-        if (rc) { delete priv; return rc; }
-        a = b;
-    }
-    float ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    fill_out(out, priv, tm, ms_total, ctx->launches - launches0);
-    return KMCPG_OK;
+    return search_common(ctx, p, k, off, n_seqs, seq ? seq : (const uint8_t *)"", nullptr, nullptr, out);
 }
 
 int kmcpg_search_batch_device(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *d_seq, const uint64_t *d_off, uint32_t n_seqs,
@@ -467,36 +631,25 @@ int kmcpg_search_batch_device(kmcpg_ctx *ctx, const kmcpg_search_params *p, cons
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     memset(out, 0, sizeof(*out));
-    auto t0 = std::chrono::steady_clock::now();
-    const uint32_t launches0 = ctx->launches;
-    // slot totals are needed on the host to size buffers: Σ and max of the per-sequence bounds
-    CU(ctx->d_slot_cnt.ensure((n_seqs + 1) * 8ull));
-    CU(ctx->d_scal.ensure(16));
-    CU(launch_slot_bounds(d_off, n_seqs, k, ctx->d_slot_cnt.as<uint64_t>(), ctx->st));
-    size_t t1 = 0, t2 = 0;
-    cub::DeviceReduce::Sum(nullptr, t1, ctx->d_slot_cnt.as<uint64_t>(), ctx->d_scal.as<uint64_t>(), (int)n_seqs, ctx->st);
-    cub::DeviceReduce::Max(nullptr, t2, ctx->d_slot_cnt.as<uint64_t>(), ctx->d_scal.as<uint64_t>() + 1, (int)n_seqs, ctx->st);
-    CU(ctx->d_tmp.ensure(std::max(t1, t2)));
-    CU(cub::DeviceReduce::Sum(ctx->d_tmp.p, t1, ctx->d_slot_cnt.as<uint64_t>(), ctx->d_scal.as<uint64_t>(), (int)n_seqs, ctx->st));
-    CU(cub::DeviceReduce::Max(ctx->d_tmp.p, t2, ctx->d_slot_cnt.as<uint64_t>(), ctx->d_scal.as<uint64_t>() + 1, (int)n_seqs, ctx->st));
-    ctx->launches += 3;
-    CU(cudaMemcpyAsync(ctx->h_small.p, ctx->d_scal.p, 16, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    uint64_t total = ctx->h_small.as<uint64_t>()[0], mx = ctx->h_small.as<uint64_t>()[1];
-    if (p->paired) mx *= 2;
-    HitsPriv *priv = new HitsPriv();
-    Timing tm;
-    SubBatch sb{d_seq, d_off, n_seqs, total, mx, 0};
-    rc = run_subbatch(ctx, *p, k, sb, *priv, tm);
-    if (rc) { delete priv; return rc; }
-    float ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    fill_out(out, priv, tm, ms_total, ctx->launches - launches0);
-    return KMCPG_OK;
+    // the lengths live on the device: fetch the offsets once (8 B per sequence) to cut the batch into parts
+    PinBuf hb;
+    rc = pin_acquire(ctx, ((size_t)n_seqs + 1) * 8, hb);
+    if (rc) return rc;
+    uint64_t *hoff = (uint64_t *)hb.p;
+    hoff[0] = 0;
+    if (n_seqs) {
+        cudaError_t e = cudaMemcpyAsync(hoff, d_off, (n_seqs + 1) * 8ull, cudaMemcpyDeviceToHost, ctx->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+        if (e != cudaSuccess) { pin_release(ctx, hb); CU(e); }
+    }
+    rc = search_common(ctx, p, k, hoff, n_seqs, nullptr, d_seq, d_off, out);
+    pin_release(ctx, hb);
+    return rc;
 }
 
 void kmcpg_free_hits(kmcpg_hits *h) {
     if (!h) return;
-    delete (HitsPriv *)h->_priv;
+    drop_priv((HitsPriv *)h->_priv);
     memset(h, 0, sizeof(*h));
 }
 
@@ -563,21 +716,25 @@ int kmcpg_generate_kmers(kmcpg_ctx *ctx, const kmcpg_sketch_params *sp, const ui
     uint64_t *codes = nullptr;
     std::vector<uint64_t> ho(n_seqs + 1);
     for (uint32_t i = 0; i <= n_seqs; i++) ho[i] = n_seqs ? off[i] - off[0] : 0;
+    WorkSet &w = ctx->ws[0];
     auto body = [&]() -> int {
-        CU(ctx->d_off.ensure((n_seqs + 1) * 8ull));
-        CU(ctx->d_seq.ensure(nbytes + 64));
-        CU(cudaMemcpyAsync(ctx->d_off.p, ho.data(), (n_seqs + 1) * 8ull, cudaMemcpyHostToDevice, ctx->st));
-        if (nbytes) CU(cudaMemcpyAsync(ctx->d_seq.p, seq + off[0], nbytes, cudaMemcpyHostToDevice, ctx->st));
-        SubBatch sb{ctx->d_seq.as<uint8_t>(), ctx->d_off.as<uint64_t>(), n_seqs, total, mx, 0};
-        int r = run_hash_stage(ctx, p, sp->k, sb, n_seqs, &codes);
+        CU(w.off.ensure((n_seqs + 1) * 8ull));
+        CU(w.seq.ensure(nbytes + 64));
+        CU(cudaMemcpyAsync(w.off.p, ho.data(), (n_seqs + 1) * 8ull, cudaMemcpyHostToDevice, ctx->st));
+        if (nbytes) CU(cudaMemcpyAsync(w.seq.p, seq + off[0], nbytes, cudaMemcpyHostToDevice, ctx->st));
+        SubBatch sb{w.seq.as<uint8_t>(), w.off.as<uint64_t>(), n_seqs, total, mx, 0};
+        int r = run_hash_stage(ctx, w, p, sp->k, sb, n_seqs, &codes);
         if (r) return r;
         std::vector<uint32_t> nc(n_seqs);
         std::vector<uint64_t> so(n_seqs + 1);
-        CU(cudaMemcpyAsync(nc.data(), ctx->d_ncodes.p, n_seqs * 4ull, cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaMemcpyAsync(so.data(), ctx->d_slot_off.p, (n_seqs + 1) * 8ull, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(nc.data(), w.ncodes.p, n_seqs * 4ull, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(so.data(), w.slot_off.p, (n_seqs + 1) * 8ull, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
         std::vector<uint64_t> all(total ? total : 1);
-        if (total) CU(cudaMemcpy(all.data(), codes, total * 8, cudaMemcpyDeviceToHost));
+        if (total) {
+            CU(cudaMemcpyAsync(all.data(), codes, total * 8, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+        }
         uint64_t *oo = (uint64_t *)malloc((n_seqs + 1) * 8ull);
         uint64_t sum = 0;
         for (uint32_t i = 0; i < n_seqs; i++) { oo[i] = sum; sum += nc[i] == 0xFFFFFFFFu ? 0 : nc[i]; }
@@ -603,32 +760,33 @@ int kmcpg_count_codes(kmcpg_ctx *ctx, const uint64_t *codes, uint64_t n, uint32_
     const int H = ctx->meta.num_hashes;
     const uint64_t nt = (uint64_t)ctx->meta.n_targets;
     cudaStream_t st = ctx->st;
+    WorkSet &w = ctx->ws[0];
     CU(ctx->d_dense.ensure(std::max<uint64_t>(nt, 1) * 4));
     CU(cudaMemsetAsync(ctx->d_dense.p, 0, std::max<uint64_t>(nt, 1) * 4, st));
     if (n > 0) {
         if (n >= (1ull << 32) - 1) return fail(ctx, KMCPG_EUNSUPPORTED, "too many codes");
-        CU(ctx->d_codes.ensure(n * 8)); CU(ctx->d_locs.ensure(n * 4 * H)); CU(ctx->d_slot_off.ensure(16));
-        CU(ctx->d_neff.ensure(4)); CU(ctx->d_thresh.ensure(4)); CU(ctx->d_hitcount.ensure(8));
-        CU(ctx->d_hkeys.ensure(8)); CU(ctx->d_hvals.ensure(4));
+        CU(w.codes.ensure(n * 8)); CU(w.locs.ensure(n * 4 * H)); CU(w.slot_off.ensure(16));
+        CU(w.neff.ensure(4)); CU(w.thresh.ensure(4)); CU(w.counters.ensure(64));
+        CU(w.hkeys.ensure(8)); CU(w.hvals.ensure(4));
         uint64_t so[2] = {0, n};
         uint32_t neff = (uint32_t)n, th = 0xFFFFFFFFu;
-        CU(cudaMemcpyAsync(ctx->d_codes.p, codes, n * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_slot_off.p, so, 16, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_neff.p, &neff, 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->d_thresh.p, &th, 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemsetAsync(ctx->d_hitcount.p, 0, 8, st));
+        CU(cudaMemcpyAsync(w.codes.p, codes, n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(w.slot_off.p, so, 16, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(w.neff.p, &neff, 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(w.thresh.p, &th, 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(w.counters.p, 0, 8, st));
         CU(cudaStreamSynchronize(st));
         for (auto &b : ctx->blocks) {
             const BlockMeta &bm = ctx->meta.blocks[b.meta_idx];
-            CU(launch_locs(ctx->d_codes.as<uint64_t>(), n, H, b.fm, ctx->d_locs.as<uint32_t>(), st));
+            CU(launch_locs(w.codes.as<uint64_t>(), n, H, b.fm, w.locs.as<uint32_t>(), st));
             ProbeArgs pa;
             memset(&pa, 0, sizeof(pa));
             pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row16 = b.row16; pa.lanes_per_task = b.G; pa.chunks = b.chunks;
             pa.n_names = (uint32_t)bm.n_names; pa.target_base = (uint32_t)bm.target_base; pa.num_hashes = H;
-            pa.locs = ctx->d_locs.as<uint32_t>(); pa.slot_off = ctx->d_slot_off.as<uint64_t>();
-            pa.n_eff = ctx->d_neff.as<uint32_t>(); pa.thresh = ctx->d_thresh.as<uint32_t>(); pa.n_queries = 1; pa.paired = 0;
-            pa.hit_keys = ctx->d_hkeys.as<uint64_t>(); pa.hit_vals = ctx->d_hvals.as<uint32_t>();
-            pa.hit_count = ctx->d_hitcount.as<unsigned long long>(); pa.hit_cap = 0; pa.dense_counts = ctx->d_dense.as<uint32_t>();
+            pa.locs = w.locs.as<uint32_t>(); pa.slot_off = w.slot_off.as<uint64_t>();
+            pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = 1; pa.paired = 0;
+            pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
+            pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = 0; pa.dense_counts = ctx->d_dense.as<uint32_t>();
             pa.planes = planes_for(n);
             CU(launch_probe(pa, ctx->sm_count, st));
         }

@@ -9,6 +9,8 @@
 #include "common.h"
 #include "kernels.cuh"
 
+struct kmcpg_ctx;
+
 namespace kmcpg {
 
 struct DevBuf {
@@ -51,9 +53,17 @@ struct DeviceBlock {
     FastMod fm;
 };
 
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+// results of one search call live in pinned host memory borrowed from the context's pool
 struct HitsPriv {
-    std::vector<int32_t> n_kmers, query_len;
-    std::vector<kmcpg_hit> hits;
+    kmcpg_ctx *ctx = nullptr;
+    PinBuf nk, ql, hits;
+    uint32_t nq = 0;
+    uint64_t nh = 0;
 };
 
 // one sub-batch, inputs already on the device
@@ -66,23 +76,43 @@ struct SubBatch {
     uint32_t query_base;       // index of the first query inside the caller's batch
 };
 
+// device + pinned buffers of one in-flight sub-batch; two sets let the host-side work of part i
+// (hit count round trip, result copies) hide behind the kernels of part i+1
+struct WorkSet {
+    DevBuf seq, off, slot_cnt, slot_off, codes, codes2, locs, ncodes, qlen, nk, neff, thresh;
+    DevBuf hkeys, hvals, hkeys2, hvals2, hits, counters, tmp, segb, sege;
+    HostBuf h_off, h_cnt;
+    cudaEvent_t ev_in = nullptr, ev_a0 = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_cnt = nullptr, ev_sorted = nullptr, ev_b = nullptr;
+    std::vector<cudaEvent_t> probe_ev;   // 3 per resident block: before locs, before probe, after probe
+    // state of the part currently in flight
+    bool busy = false;
+    SubBatch sb{};
+    uint32_t nq = 0;
+    uint64_t cap = 0, n_hits = 0, hit_dst = 0;
+    int planes = 8;
+    uint64_t *codes_ptr = nullptr;
+    void release();
+};
+
 }  // namespace kmcpg
 
 struct kmcpg_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;        // compute stream (own_st or the caller's)
     cudaStream_t own_st = nullptr;
-    std::vector<cudaEvent_t> probe_ev;   // 2 per probe launch of a sub-batch (+2 around the locs kernels)
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_st = nullptr;   // transfers that overlap the kernels
     bool has_db = false;
     kmcpg::DbMeta meta;
     std::vector<kmcpg::DeviceBlock> blocks;
     std::vector<int> resident_of;     // meta block index -> index in `blocks` or -1
+    std::vector<double> target_sizes; // Sizes[t] of every target as float64 (U:1393-1396 sizesFloat)
     int64_t sum_row_bytes = 0, resident_bytes = 0, disk_bytes = 0;
-    kmcpg::DevBuf d_seq, d_off, d_slot_cnt, d_slot_off, d_codes, d_codes2, d_locs, d_ncodes, d_qlen, d_nk, d_neff, d_thresh;
-    kmcpg::DevBuf d_hkeys, d_hvals, d_hkeys2, d_hvals2, d_hits, d_hitcount, d_tmp, d_segb, d_sege, d_dense, d_scal, d_genome;
-    kmcpg::HostBuf h_stage, h_off, h_small;
+    kmcpg::WorkSet ws[2];
+    kmcpg::DevBuf d_tmp, d_dense, d_scal, d_genome;
+    kmcpg::HostBuf h_stage, h_small;
+    std::vector<kmcpg::PinBuf> pin_pool;
+    std::mutex pin_mu;
     std::string err;
     std::mutex mu;
     uint32_t launches = 0;
@@ -94,7 +124,9 @@ int fail(kmcpg_ctx *c, int code, const std::string &msg);
 uint32_t pitch_for(uint32_t row_bytes);
 void layout_block(DeviceBlock &b, const BlockMeta &m);
 void free_db(kmcpg_ctx *ctx);
-int run_hash_stage(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out);
+int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out);
+int pin_acquire(kmcpg_ctx *ctx, size_t bytes, PinBuf &out);
+void pin_release(kmcpg_ctx *ctx, PinBuf &b);
 
 #define CU(call)                                                                                      \
     do {                                                                                              \

@@ -3,14 +3,18 @@
 // (reference kmcp/cmd/util-db-search.go: multi-k loop U:763-1025, --try-se U:808-842 + 995-1011,
 //  Match fields and filters U:7466-7491, sort U:273-282 with Less functions U:105-145, top-N scores U:285-311).
 // The counts themselves always come from the GPU (kmcpg_search_batch); nothing here probes an index.
+//
+// A "round" = one device search of the still-undecided queries with one k and one mate selection; its hit
+// list (sorted by query) is filtered and sorted per query by a few host threads into one flat array.
 #include <algorithm>
-#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <thread>
 #include <vector>
 
 #include "common.h"
+
+extern "C" const double *kmcpg_internal_target_sizes(const kmcpg_ctx *ctx);
 
 namespace {
 
@@ -58,6 +62,51 @@ struct ResPriv {
     std::vector<kmcpg_match> matches;
 };
 
+// matches of one round, flat, in local-query order
+struct Round {
+    std::vector<uint32_t> queries;        // local index → global query
+    std::vector<uint64_t> off;            // local index → range in `matches`
+    std::vector<kmcpg_match> matches;
+};
+
+// filters + sorts the hits of local queries [lo, hi) (U:7466-7491, U:273-311)
+void post_filter(const kmcpg_engine_opts *o, const kmcpg_hits &hits, const std::vector<uint64_t> &hoff, const std::vector<uint32_t> &cur,
+                 const double *tsize, FprCache *cache, uint32_t lo, uint32_t hi, std::vector<kmcpg_match> &out, std::vector<uint32_t> &count) {
+    const Less less{o->sort_by};
+    for (uint32_t l = lo; l < hi; l++) {
+        const int n = hits.n_kmers[l];
+        count[l] = 0;
+        if (n == 0 || hoff[l] == hoff[l + 1]) continue;
+        const uint32_t q = cur[l];
+        const double nh = (double)n;
+        const size_t start = out.size();
+        for (uint64_t i = hoff[l]; i < hoff[l + 1]; i++) {
+            const kmcpg_hit &h = hits.hits[i];
+            const double c = (double)h.count, sz = tsize[h.target];
+            const double tcov = c / sz;
+            if (!(tcov >= o->min_target_cov)) continue;              // U:7473-7474
+            const double fpr = cache->get(n, (int)h.count);
+            if (!(fpr <= o->max_fpr)) continue;                      // U:7477-7478
+            kmcpg_match m;
+            m.query = q; m.target = h.target; m.count = h.count; m._pad = 0;
+            m.fpr = fpr; m.qcov = c / nh; m.tcov = tcov; m.jacc = c / (nh + sz - c);   // U:7470-7488
+            out.push_back(m);
+        }
+        size_t cnt = out.size() - start;
+        if (cnt > 1 && !o->do_not_sort) std::sort(out.begin() + start, out.end(), less);   // U:273-282
+        if (cnt > 0 && o->top_n_scores > 0 && !o->do_not_sort) {     // U:285-311 (kept verbatim, including [:i+1])
+            int nsc = 0; double pscore = 1024; size_t i = 0; bool broke = false;
+            for (i = 0; i < cnt; i++) {
+                const kmcpg_match &m = out[start + i];
+                double score = o->sort_by == 0 ? m.qcov : (o->sort_by == 1 ? m.tcov : m.jacc);
+                if (score < pscore) { nsc++; if (nsc > o->top_n_scores) { broke = true; break; } pscore = score; }
+            }
+            if (broke) { out.resize(start + i + 1); cnt = i + 1; }
+        }
+        count[l] = (uint32_t)cnt;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -82,24 +131,20 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
     static thread_local FprCache tl_cache;
     tl_cache.reset(info.fpr);
     FprCache *cache = &tl_cache;          // worker threads must share THIS instance, not their own thread_local
-
-    // per-target Sizes (k-mers of the target) once
-    std::vector<double> tsize((size_t)info.n_targets);
-    for (int64_t t = 0; t < info.n_targets; t++) {
-        kmcpg_target_t tt;
-        kmcpg_target(ctx, t, &tt);
-        tsize[(size_t)t] = (double)tt.n_kmers;
-    }
+    const double *tsize = kmcpg_internal_target_sizes(ctx);
 
     ResPriv *priv = new ResPriv();
     priv->query_len.assign(nq, 0); priv->n_kmers.assign(nq, 0); priv->k_used.assign(nq, info.ks[0]);
-    std::vector<std::vector<kmcpg_match>> per(nq);
     std::vector<uint32_t> pending(nq);
     for (uint32_t q = 0; q < nq; q++) pending[q] = q;
     const int tries_max = (o->try_se && o->paired) ? 3 : 1;
     int threads = o->threads > 0 ? o->threads : (int)std::thread::hardware_concurrency();
-    if (threads < 1) threads = 1;
+    threads = std::max(1, std::min(threads, 32));
 
+    std::vector<Round> rounds;
+    // where the final matches of query q live: (round, local index); round -1 = unmatched
+    std::vector<int32_t> q_round(nq, -1);
+    std::vector<uint32_t> q_local(nq, 0);
     std::vector<uint8_t> sub_seq;
     std::vector<uint64_t> sub_off;
     for (int ik = 0; ik < info.n_ks && !pending.empty(); ik++) {
@@ -109,8 +154,7 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
         for (int tries = 0; tries < tries_max && !cur.empty(); tries++) {
             // pack the pending subset (the first pass uses the caller's buffers untouched)
             const uint8_t *bs = seq; const uint64_t *bo = off; uint32_t bn = n_seqs;
-            const bool all = cur.size() == nq;
-            if (!all) {
+            if (cur.size() != nq) {
                 sub_off.assign(1, 0); sub_seq.clear();
                 for (uint32_t q : cur)
                     for (uint32_t m = 0; m < step; m++) {
@@ -130,63 +174,61 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
             if (rc) { delete priv; return rc; }
             out->ms_gpu_total += hits.ms_total; out->probe_row_bytes += hits.probe_row_bytes; out->kernel_launches += hits.kernel_launches;
 
-            // hit ranges per local query (hits are sorted by query)
             const uint32_t ln = (uint32_t)cur.size();
-            std::vector<uint64_t> hoff(ln + 1, 0);
+            // hit ranges per local query (hits are sorted by query)
+            std::vector<uint64_t> hoff((size_t)ln + 1, 0);
             for (uint64_t i = 0; i < hits.n_hits; i++) hoff[hits.hits[i].query + 1]++;
             for (uint32_t i = 0; i < ln; i++) hoff[i + 1] += hoff[i];
 
-            std::vector<uint8_t> found(ln, 0), gave_up(ln, 0);
-            auto work = [&](uint32_t lo, uint32_t hi) {
-                for (uint32_t l = lo; l < hi; l++) {
-                    const uint32_t q = cur[l];
-                    const int n = hits.n_kmers[l];
-                    priv->query_len[q] = hits.query_len[l];
-                    priv->k_used[q] = k;
-                    if (n == 0) { gave_up[l] = 1; if (tries == 0) priv->n_kmers[q] = 0; continue; }   // U:778-786, U:854-869: final
-                    priv->n_kmers[q] = n;
-                    const double nh = (double)n;
-                    std::vector<kmcpg_match> &ms = per[q];
-                    for (uint64_t i = hoff[l]; i < hoff[l + 1]; i++) {
-                        const kmcpg_hit &h = hits.hits[i];
-                        const double c = (double)h.count, sz = tsize[h.target];
-                        const double tcov = c / sz;
-                        if (!(tcov >= o->min_target_cov)) continue;              // U:7473-7474
-                        const double fpr = cache->get(n, (int)h.count);
-                        if (!(fpr <= o->max_fpr)) continue;                      // U:7477-7478
-                        kmcpg_match m;
-                        m.query = q; m.target = h.target; m.count = h.count; m._pad = 0;
-                        m.fpr = fpr; m.qcov = c / nh; m.tcov = tcov; m.jacc = c / (nh + sz - c);   // U:7470-7488
-                        ms.push_back(m);
-                    }
-                    if (ms.empty()) continue;
-                    found[l] = 1;
-                    if (ms.size() > 1 && !o->do_not_sort) std::sort(ms.begin(), ms.end(), Less{o->sort_by});   // U:273-282
-                    if (o->top_n_scores > 0 && !o->do_not_sort) {                // U:285-311 (kept verbatim, including [:i+1])
-                        int nsc = 0; double pscore = 1024; size_t i = 0; bool broke = false;
-                        for (i = 0; i < ms.size(); i++) {
-                            double score = o->sort_by == 0 ? ms[i].qcov : (o->sort_by == 1 ? ms[i].tcov : ms[i].jacc);
-                            if (score < pscore) { nsc++; if (nsc > o->top_n_scores) { broke = true; break; } pscore = score; }
-                        }
-                        if (broke) ms.resize(i + 1);
-                    }
-                }
-            };
-            if (threads > 1 && ln > 4096) {
-                std::vector<std::thread> th;
-                uint32_t per_t = (ln + threads - 1) / threads;
-                for (int t = 0; t < threads; t++) {
-                    uint32_t lo = std::min<uint32_t>(ln, t * per_t), hi = std::min<uint32_t>(ln, lo + per_t);
-                    if (lo < hi) th.emplace_back(work, lo, hi);
-                }
-                for (auto &t : th) t.join();
-            } else {
-                work(0, ln);
+            rounds.emplace_back();
+            Round &R = rounds.back();
+            const int ridx = (int)rounds.size() - 1;
+            std::vector<uint32_t> count(ln, 0);
+            int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 16384 + 1));
+            std::vector<std::vector<kmcpg_match>> parts(T);
+            std::vector<uint32_t> bounds(T + 1, ln);
+            bounds[0] = 0;
+            for (int t = 1; t < T; t++) {            // split by hits so the threads get equal work
+                uint64_t want = hits.n_hits * (uint64_t)t / T;
+                bounds[t] = (uint32_t)(std::lower_bound(hoff.begin(), hoff.end(), want) - hoff.begin());
+                if (bounds[t] > ln) bounds[t] = ln;
+                if (bounds[t] < bounds[t - 1]) bounds[t] = bounds[t - 1];
             }
-            kmcpg_free_hits(&hits);
+            if (T == 1) {
+                post_filter(o, hits, hoff, cur, tsize, cache, 0, ln, parts[0], count);
+            } else {
+                std::vector<std::thread> th;
+                for (int t = 0; t < T; t++)
+                    th.emplace_back([&, t] {
+                        parts[t].reserve((size_t)(hoff[bounds[t + 1]] - hoff[bounds[t]]));
+                        post_filter(o, hits, hoff, cur, tsize, cache, bounds[t], bounds[t + 1], parts[t], count);
+                    });
+                for (auto &t : th) t.join();
+            }
+            size_t total = 0;
+            for (auto &v : parts) total += v.size();
+            if (T == 1) R.matches.swap(parts[0]);
+            else {
+                R.matches.resize(total);
+                size_t w = 0;
+                for (auto &v : parts) { if (!v.empty()) memcpy(R.matches.data() + w, v.data(), v.size() * sizeof(kmcpg_match)); w += v.size(); }
+            }
+            R.off.resize((size_t)ln + 1);
+            R.off[0] = 0;
             std::vector<uint32_t> retry;
-            for (uint32_t l = 0; l < ln; l++)
-                if (!found[l] && !gave_up[l]) retry.push_back(cur[l]);
+            for (uint32_t l = 0; l < ln; l++) {
+                const uint32_t q = cur[l];
+                const int n = hits.n_kmers[l];
+                R.off[l + 1] = R.off[l] + count[l];
+                priv->query_len[q] = hits.query_len[l];
+                priv->k_used[q] = k;
+                if (n == 0) { if (tries == 0) priv->n_kmers[q] = 0; continue; }     // U:778-786, U:854-869: final, unmatched
+                priv->n_kmers[q] = n;
+                if (count[l]) { q_round[q] = ridx; q_local[q] = l; }
+                else retry.push_back(q);
+            }
+            R.queries.swap(cur);
+            kmcpg_free_hits(&hits);
             if (tries + 1 < tries_max) cur.swap(retry);          // --try-se: read1 only, then read2 only
             else { next_k.insert(next_k.end(), retry.begin(), retry.end()); cur.clear(); }
         }
@@ -194,11 +236,25 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
         pending.swap(next_k);                                    // U:1018-1023: try the next smaller k
     }
 
-    priv->match_off.assign(nq + 1, 0);
-    for (uint32_t q = 0; q < nq; q++) priv->match_off[q + 1] = priv->match_off[q] + per[q].size();
-    priv->matches.resize(priv->match_off[nq]);
-    for (uint32_t q = 0; q < nq; q++)
-        if (!per[q].empty()) memcpy(priv->matches.data() + priv->match_off[q], per[q].data(), per[q].size() * sizeof(kmcpg_match));
+    priv->match_off.assign((size_t)nq + 1, 0);
+    if (rounds.size() == 1 && rounds[0].queries.size() == nq) {
+        // the common case: one round over all queries — its flat array already is the answer
+        priv->matches.swap(rounds[0].matches);
+        for (uint32_t q = 0; q < nq; q++) priv->match_off[q + 1] = rounds[0].off[q + 1];
+    } else {
+        for (uint32_t q = 0; q < nq; q++) {
+            uint64_t c = 0;
+            if (q_round[q] >= 0) { const Round &R = rounds[q_round[q]]; c = R.off[q_local[q] + 1] - R.off[q_local[q]]; }
+            priv->match_off[q + 1] = priv->match_off[q] + c;
+        }
+        priv->matches.resize(priv->match_off[nq]);
+        for (uint32_t q = 0; q < nq; q++)
+            if (q_round[q] >= 0) {
+                const Round &R = rounds[q_round[q]];
+                memcpy(priv->matches.data() + priv->match_off[q], R.matches.data() + R.off[q_local[q]],
+                       (priv->match_off[q + 1] - priv->match_off[q]) * sizeof(kmcpg_match));
+            }
+    }
     out->n_queries = nq; out->n_matches = priv->matches.size();
     out->query_len = priv->query_len.data(); out->n_kmers = priv->n_kmers.data(); out->k_used = priv->k_used.data();
     out->match_off = priv->match_off.data(); out->matches = priv->matches.data();

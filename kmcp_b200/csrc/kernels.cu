@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long local_sum = 0;
     for (uint32_t q = warp; q < a.n_queries; q += n_warps) {
         uint32_t n = a.n_codes[q];
         bool skipped = n == 0xFFFFFFFFu;
@@ -238,8 +239,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
             if ((int64_t)t < (int64_t)a.min_matched) t = (uint32_t)a.min_matched;
             if (t == 0) t = 1;
             a.thresh[q] = t;
+            local_sum += eff;
         }
     }
+    if (lane == 0 && local_sum && a.n_sum) atomicAdd(a.n_sum, local_sum);
 }
 
 cudaError_t launch_finalize(const FinalizeArgs &a, cudaStream_t st) {
@@ -320,10 +323,66 @@ __device__ __forceinline__ uint4 ld_row16(const uint8_t *p) {
 }
 
 constexpr int PROBE_THREADS = 256;
-constexpr int PROBE_ROWS = 8;   // rows in flight per lane = inputs of one carry-save tree
+constexpr int PROBE_ROWS = 8;   // rows per carry-save tree
+constexpr uint32_t LOC_NONE = 0xFFFFFFFFu;
 
-template <int H, int P>
-__global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(ProbeArgs a) {
+// row indices of 8 consecutive k-mers (H each); LOC_NONE past the end of the query
+template <int H>
+__device__ __forceinline__ void load_locs(uint32_t (&L)[PROBE_ROWS * H], const uint32_t *__restrict__ lp, uint32_t i, uint32_t n) {
+#pragma unroll
+    for (int u = 0; u < PROBE_ROWS; u++)
+#pragma unroll
+        for (int h = 0; h < H; h++) L[u * H + h] = (i + u < n) ? __ldg(lp + (uint64_t)(i + u) * H + h) : LOC_NONE;
+}
+
+// 16-byte slabs of the 8 rows (h rows AND-ed: pand, U:6639-6645); zero for LOC_NONE
+template <int H>
+__device__ __forceinline__ void load_rows(uint4 (&r)[PROBE_ROWS], const uint32_t (&L)[PROBE_ROWS * H], const uint8_t *__restrict__ colbase, uint32_t pitch) {
+#pragma unroll
+    for (int u = 0; u < PROBE_ROWS; u++) {
+        if (L[u * H] != LOC_NONE) {
+            r[u] = ld_row16(colbase + (uint64_t)L[u * H] * pitch);
+#pragma unroll
+            for (int h = 1; h < H; h++) {
+                uint4 t = ld_row16(colbase + (uint64_t)L[u * H + h] * pitch);
+                r[u].x &= t.x; r[u].y &= t.y; r[u].z &= t.z; r[u].w &= t.w;
+            }
+        } else {
+            r[u] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// Harley–Seal: 8 one-bit inputs + planes 0..2 → planes 0..2 and one weight-8 carry rippled into planes 3..P-1
+template <int P>
+__device__ __forceinline__ void csa8(uint32_t (&c)[P][4], const uint4 (&r)[PROBE_ROWS]) {
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t x0 = (&r[0].x)[w], x1 = (&r[1].x)[w], x2 = (&r[2].x)[w], x3 = (&r[3].x)[w];
+        const uint32_t x4 = (&r[4].x)[w], x5 = (&r[5].x)[w], x6 = (&r[6].x)[w], x7 = (&r[7].x)[w];
+        uint32_t ones = c[0][w], twos = c[1][w], fours = c[2][w];
+        uint32_t t1a = maj3(ones, x0, x1); ones = xor3(ones, x0, x1);
+        uint32_t t1b = maj3(ones, x2, x3); ones = xor3(ones, x2, x3);
+        uint32_t t2a = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
+        t1a = maj3(ones, x4, x5); ones = xor3(ones, x4, x5);
+        t1b = maj3(ones, x6, x7); ones = xor3(ones, x6, x7);
+        uint32_t t2b = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
+        uint32_t carry = maj3(fours, t2a, t2b); fours = xor3(fours, t2a, t2b);
+        c[0][w] = ones; c[1][w] = twos; c[2][w] = fours;
+#pragma unroll
+        for (int p = 3; p < P; p++) {
+            uint32_t t = c[p][w] & carry;
+            c[p][w] ^= carry;
+            carry = t;
+        }
+    }
+}
+
+// VAR 0: load locs, load rows, add (simple).  VAR 1: row indices of the next 8 k-mers are prefetched while the
+// current rows are in flight.  VAR 2: additionally the rows are double-buffered in registers, so 8..16 rows per
+// lane are always in flight while the carry-save tree of the previous 8 runs.
+template <int H, int P, int VAR, int MINB>
+__global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a) {
     const uint32_t G = a.lanes_per_task;
     const uint32_t gl = threadIdx.x & (G - 1);                          // lane inside the task group
     const uint64_t groups_per_grid = ((uint64_t)gridDim.x * blockDim.x) / G;
@@ -349,43 +408,34 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(ProbeArgs a) {
         if (active) {
             const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
             const uint8_t *colbase = a.rows + (uint64_t)col16 * 16;
-            for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
-                uint4 r[PROBE_ROWS];
-#pragma unroll
-                for (int u = 0; u < PROBE_ROWS; u++) {
-                    if (i + u < n) {
-                        uint32_t loc = __ldg(lp + (uint64_t)(i + u) * H);
-                        r[u] = ld_row16(colbase + (uint64_t)loc * a.pitch);
-#pragma unroll
-                        for (int h = 1; h < H; h++) {                    // row AND for h>1 (pand, U:6639-6645)
-                            uint32_t loc2 = __ldg(lp + (uint64_t)(i + u) * H + h);
-                            uint4 t = ld_row16(colbase + (uint64_t)loc2 * a.pitch);
-                            r[u].x &= t.x; r[u].y &= t.y; r[u].z &= t.z; r[u].w &= t.w;
-                        }
-                    } else {
-                        r[u] = make_uint4(0, 0, 0, 0);
-                    }
+            uint32_t L[PROBE_ROWS * H];
+            if (VAR == 0) {
+                for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
+                    uint4 r[PROBE_ROWS];
+                    load_locs<H>(L, lp, i, n);
+                    load_rows<H>(r, L, colbase, a.pitch);
+                    csa8<P>(c, r);
                 }
-                // Harley–Seal: 8 one-bit inputs + planes 0..2 → planes 0..2 and one weight-8 carry
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const uint32_t x0 = (&r[0].x)[w], x1 = (&r[1].x)[w], x2 = (&r[2].x)[w], x3 = (&r[3].x)[w];
-                    const uint32_t x4 = (&r[4].x)[w], x5 = (&r[5].x)[w], x6 = (&r[6].x)[w], x7 = (&r[7].x)[w];
-                    uint32_t ones = c[0][w], twos = c[1][w], fours = c[2][w];
-                    uint32_t t1a = maj3(ones, x0, x1); ones = xor3(ones, x0, x1);
-                    uint32_t t1b = maj3(ones, x2, x3); ones = xor3(ones, x2, x3);
-                    uint32_t t2a = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
-                    t1a = maj3(ones, x4, x5); ones = xor3(ones, x4, x5);
-                    t1b = maj3(ones, x6, x7); ones = xor3(ones, x6, x7);
-                    uint32_t t2b = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
-                    uint32_t carry = maj3(fours, t2a, t2b); fours = xor3(fours, t2a, t2b);
-                    c[0][w] = ones; c[1][w] = twos; c[2][w] = fours;
-#pragma unroll
-                    for (int p = 3; p < P; p++) {                        // ripple the weight-8 carry upwards
-                        uint32_t t = c[p][w] & carry;
-                        c[p][w] ^= carry;
-                        carry = t;
-                    }
+            } else if (VAR == 1) {
+                load_locs<H>(L, lp, 0, n);
+                for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
+                    uint4 r[PROBE_ROWS];
+                    load_rows<H>(r, L, colbase, a.pitch);
+                    load_locs<H>(L, lp, i + PROBE_ROWS, n);
+                    csa8<P>(c, r);
+                }
+            } else {
+                uint4 r0[PROBE_ROWS], r1[PROBE_ROWS];
+                load_locs<H>(L, lp, 0, n);
+                load_rows<H>(r0, L, colbase, a.pitch);
+                load_locs<H>(L, lp, PROBE_ROWS, n);
+                for (uint32_t i = 0; i < n; i += 2 * PROBE_ROWS) {
+                    load_rows<H>(r1, L, colbase, a.pitch);
+                    load_locs<H>(L, lp, i + 2 * PROBE_ROWS, n);
+                    csa8<P>(c, r0);
+                    load_rows<H>(r0, L, colbase, a.pitch);
+                    load_locs<H>(L, lp, i + 3 * PROBE_ROWS, n);
+                    if (i + PROBE_ROWS < n) csa8<P>(c, r1);
                 }
             }
         }
@@ -461,16 +511,43 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(ProbeArgs a) {
     }
 }
 
+struct ProbeTune { int var = 2, minb = 2, cap = 16; };
+static ProbeTune probe_tune() {
+    // development knobs (tools/probe_sweep.py): KMCPG_PROBE_VAR, KMCPG_PROBE_MINB, KMCPG_PROBE_CAP
+    static ProbeTune t = [] {
+        ProbeTune x;
+        if (const char *e = getenv("KMCPG_PROBE_VAR")) x.var = atoi(e);
+        if (const char *e = getenv("KMCPG_PROBE_MINB")) x.minb = atoi(e);
+        if (const char *e = getenv("KMCPG_PROBE_CAP")) x.cap = atoi(e);
+        return x;
+    }();
+    return t;
+}
+
+template <int H, int P>
+static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
+    const ProbeTune t = probe_tune();
+    if (P == 8) {       // the short-read case gets the tuned variants
+        if (t.var == 0) probe_kernel<H, P, 0, 2><<<blocks, PROBE_THREADS, 0, st>>>(a);
+        else if (t.var == 1 && t.minb >= 3) probe_kernel<H, P, 1, 3><<<blocks, PROBE_THREADS, 0, st>>>(a);
+        else if (t.var == 1) probe_kernel<H, P, 1, 2><<<blocks, PROBE_THREADS, 0, st>>>(a);
+        else if (t.minb >= 3) probe_kernel<H, P, 2, 3><<<blocks, PROBE_THREADS, 0, st>>>(a);
+        else probe_kernel<H, P, 2, 2><<<blocks, PROBE_THREADS, 0, st>>>(a);
+    } else {
+        probe_kernel<H, P, 1, 1><<<blocks, PROBE_THREADS, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
 template <int H>
 static cudaError_t launch_probe_h(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     switch (a.planes) {
-        case 8: probe_kernel<H, 8><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
-        case 16: probe_kernel<H, 16><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
-        case 24: probe_kernel<H, 24><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
-        case 32: probe_kernel<H, 32><<<blocks, PROBE_THREADS, 0, st>>>(a); break;
+        case 8: return launch_probe_hp<H, 8>(a, blocks, st);
+        case 16: return launch_probe_hp<H, 16>(a, blocks, st);
+        case 24: return launch_probe_hp<H, 24>(a, blocks, st);
+        case 32: return launch_probe_hp<H, 32>(a, blocks, st);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st) {
@@ -479,7 +556,7 @@ cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st) {
     const uint64_t threads = total_groups * a.lanes_per_task;
     uint64_t blocks64 = (threads + PROBE_THREADS - 1) / PROBE_THREADS;
     // persistent-style grid: a multiple of the SM count, several CTAs per SM, each thread loops over tasks
-    const uint64_t cap = (uint64_t)sm_count * 16;
+    const uint64_t cap = (uint64_t)sm_count * probe_tune().cap;
     uint32_t blocks = (uint32_t)(blocks64 < cap ? blocks64 : cap);
     switch (a.num_hashes) {
         case 1: return launch_probe_h<1>(a, blocks, st);

@@ -38,6 +38,7 @@ struct FinalizeArgs {
     int32_t *n_kmers_out;       // reported NumKmers (0 when skipped)
     uint32_t *n_eff;            // codes to probe (0 = skip)
     uint32_t *thresh;           // smallest count that passes min_matched and count > n*min_query_cov
+    unsigned long long *n_sum;  // += Σ n_eff (algorithmic probe volume of the sub-batch)
     uint32_t n_queries;
     int paired;
     int dedup_threshold;

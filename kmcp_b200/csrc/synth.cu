@@ -186,8 +186,8 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
     std::vector<uint64_t> sizes(n_targets, 0);
     std::vector<uint64_t> h_off((size_t)gpp * nw + 1);
     std::vector<uint32_t> h_nc((size_t)gpp * nw);
-    CU(ctx->d_genome.ensure((uint64_t)gpp * (L + 16) + 64));
-    CU(ctx->d_off.ensure(((uint64_t)gpp * nw + 1) * 8));
+    WorkSet &w = ctx->ws[0];
+    CU(w.off.ensure(((uint64_t)gpp * nw + 1) * 8));
 
     // target order / block composition are known only after pass 1
     std::vector<uint32_t> order;          // sorted position → target id (genome*nw + window)
@@ -235,6 +235,9 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
                 ctx->disk_bytes += (int64_t)(bm.num_sigs * (uint64_t)bm.row_bytes);
             }
             m.n_targets = (int64_t)n_targets;
+            ctx->target_sizes.resize(n_targets);
+            for (auto &bm : m.blocks)
+                for (int c = 0; c < bm.n_names; c++) ctx->target_sizes[(size_t)bm.target_base + c] = (double)bm.sizes[c];
             ctx->resident_of.resize(nb);
             std::iota(ctx->resident_of.begin(), ctx->resident_of.end(), 0);
         }
@@ -246,19 +249,19 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
             const uint32_t ns = ng * nw;
             for (uint32_t s = 0; s < ns; s++) { h_off[s] = bytes; bytes += wins[s % nw].len; }
             h_off[ns] = bytes;
-            CU(ctx->d_seq.ensure(bytes + 64));
+            CU(w.seq.ensure(bytes + 64));
             for (uint32_t s = 0; s < ns; s++)
-                CU(launch_synth_genome(spec->genome_seed, g0 + s / nw, wins[s % nw].start, wins[s % nw].len, ctx->d_seq.as<uint8_t>() + h_off[s], st));
-            CU(cudaMemcpyAsync(ctx->d_off.p, h_off.data(), (ns + 1) * 8ull, cudaMemcpyHostToDevice, st));
+                CU(launch_synth_genome(spec->genome_seed, g0 + s / nw, wins[s % nw].start, wins[s % nw].len, w.seq.as<uint8_t>() + h_off[s], st));
+            CU(cudaMemcpyAsync(w.off.p, h_off.data(), (ns + 1) * 8ull, cudaMemcpyHostToDevice, st));
             uint64_t total = 0, mx = 0;
             for (uint32_t s = 0; s < ns; s++) { uint64_t c = wins[s % nw].len - spec->k + 1; total += c; mx = std::max(mx, c); }
-            SubBatch sb{ctx->d_seq.as<uint8_t>(), ctx->d_off.as<uint64_t>(), ns, total, mx, 0};
+            SubBatch sb{w.seq.as<uint8_t>(), w.off.as<uint64_t>(), ns, total, mx, 0};
             uint64_t *codes = nullptr;
-            int rc = run_hash_stage(ctx, hp, spec->k, sb, ns, &codes);
+            int rc = run_hash_stage(ctx, w, hp, spec->k, sb, ns, &codes);
             if (rc) return rc;
-            CU(cudaMemcpyAsync(h_nc.data(), ctx->d_ncodes.p, ns * 4ull, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_nc.data(), w.ncodes.p, ns * 4ull, cudaMemcpyDeviceToHost, st));
             std::vector<uint64_t> h_slot(ns + 1);
-            CU(cudaMemcpyAsync(h_slot.data(), ctx->d_slot_off.p, (ns + 1) * 8ull, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_slot.data(), w.slot_off.p, (ns + 1) * 8ull, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             for (uint32_t s = 0; s < ns; s++) {
                 const uint64_t id = (uint64_t)(g0 + s / nw) * nw + (s % nw);
