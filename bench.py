@@ -290,6 +290,7 @@ def main():
     eopts = ctx.default_engine_opts()
     d2h_bytes = 0
     e2e_matches = 0
+    e2e_break = {"search_call_ms": 0.0, "post_filter_ms": 0.0, "engine_call_ms": 0.0}
     with torch.cuda.stream(stream):
         if world == 1:
             ctx.engine_search_ptr(h_ptr, h_off_ptr, READS_PER_STEP, eopts)          # warm the host-side caches once
@@ -298,6 +299,8 @@ def main():
             for s in range(args.steps):
                 r = ctx.engine_search_ptr(h_ptr + s * step_bytes, h_off_ptr, READS_PER_STEP, eopts, copy=False)
                 e2e_matches += r.n_matches
+                e2e_break["search_call_ms"] += r.ms_gpu_total / args.steps; e2e_break["post_filter_ms"] += r.ms_post / args.steps
+                e2e_break["engine_call_ms"] += r.ms_total / args.steps
             torch.cuda.synchronize()
             e2e_s = time.perf_counter() - t0
             d2h_bytes = int(12 * n_hits / args.steps + 8 * READS_PER_STEP)
@@ -373,7 +376,7 @@ def main():
                          "traffic_note": traffic.get("note") if traffic else "no ncu --set full capture committed yet"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": step_bytes + off_np.nbytes, "d2h_bytes_per_step": d2h_bytes,
-                    "matches_per_step": int(e2e_matches / args.steps),
+                    "matches_per_step": int(e2e_matches / args.steps), "ms_per_step": e2e_s / args.steps * 1e3, "breakdown_ms_per_step": e2e_break,
                     "path": "kmcpg_engine_search (pinned host reads → H2D → kernels → D2H hits → host tCov/FPR/sort)" if world == 1 else
                             "rank0 H2D → ncclBroadcast → kmcpg_search_batch_device on every rank → host concat on rank 0 (gloo)"},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -170,7 +170,9 @@ typedef struct {
     int32_t *query_len, *n_kmers, *k_used;   /* per query */
     uint64_t *match_off;                     /* n_queries+1 */
     kmcpg_match *matches;                    /* per query in output order (sorted / truncated as U:273-311) */
-    float ms_gpu_total;
+    float ms_gpu_total;                      /* Σ wall time of the kmcpg_search_batch calls */
+    float ms_post;                           /* host post-filter (tCov, FPR, sort, top-N) */
+    float ms_total;                          /* wall time of the whole engine call */
     uint64_t probe_row_bytes;
     uint32_t kernel_launches;
     void *_priv;

@@ -85,7 +85,7 @@ MATCH_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("count", "<u4"), (
 class Results(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("n_matches", C.c_uint64), ("query_len", C.POINTER(C.c_int32)),
                 ("n_kmers", C.POINTER(C.c_int32)), ("k_used", C.POINTER(C.c_int32)), ("match_off", C.POINTER(C.c_uint64)),
-                ("matches", C.POINTER(Match)), ("ms_gpu_total", C.c_float), ("probe_row_bytes", C.c_uint64),
+                ("matches", C.POINTER(Match)), ("ms_gpu_total", C.c_float), ("ms_post", C.c_float), ("ms_total", C.c_float), ("probe_row_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("_priv", C.c_void_p)]
 
 
@@ -191,6 +191,8 @@ class EngineResults:
     probe_row_bytes: int
     kernel_launches: int
     n_matches: int = 0
+    ms_post: float = 0.0
+    ms_total: float = 0.0
 
 
 def _np_from(ptr, n, ctype_size, dtype):
@@ -337,14 +339,14 @@ class Context:
         if not copy:
             out = EngineResults(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint64), np.zeros(0, MATCH_DTYPE),
                                 r.ms_gpu_total, int(r.probe_row_bytes), int(r.kernel_launches))
-            out.n_matches = int(r.n_matches)
+            out.n_matches = int(r.n_matches); out.ms_post = r.ms_post; out.ms_total = r.ms_total
             self._L.kmcpg_free_results(C.byref(r))
             return out
         out = EngineResults(_np_from(r.query_len, nq, 4, np.int32), _np_from(r.n_kmers, nq, 4, np.int32),
                             _np_from(r.k_used, nq, 4, np.int32), _np_from(r.match_off, nq + 1, 8, np.uint64),
                             _np_from(r.matches, r.n_matches, C.sizeof(Match), MATCH_DTYPE), r.ms_gpu_total,
                             int(r.probe_row_bytes), int(r.kernel_launches))
-        out.n_matches = int(r.n_matches)
+        out.n_matches = int(r.n_matches); out.ms_post = r.ms_post; out.ms_total = r.ms_total
         self._L.kmcpg_free_results(C.byref(r))
         return out
 

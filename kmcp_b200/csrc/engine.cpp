@@ -7,8 +7,11 @@
 // A "round" = one device search of the still-undecided queries with one k and one mate selection; its hit
 // list (sorted by query) is filtered and sorted per query by a few host threads into one flat array.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -56,30 +59,69 @@ struct Less {
     }
 };
 
+// Big result arrays are recycled through a small process-wide pool: a fresh 40 MB allocation per call costs
+// more in page faults than the whole post-filter.
+struct BigBuf { void *p = nullptr; size_t cap = 0; };
+std::mutex g_pool_mu;
+std::vector<BigBuf> g_pool;
+
+BigBuf big_acquire(size_t bytes) {
+    if (bytes < 64) bytes = 64;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (g_pool[i].cap >= bytes && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = (int)i;
+        if (best >= 0 && g_pool[best].cap <= bytes * 4 + (1u << 20)) {
+            BigBuf b = g_pool[best];
+            g_pool.erase(g_pool.begin() + best);
+            return b;
+        }
+    }
+    BigBuf b;
+    b.cap = bytes + bytes / 4;
+    b.p = malloc(b.cap);
+    return b;
+}
+void big_release(BigBuf &b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(b);
+    b = BigBuf();
+    while (g_pool.size() > 16) {
+        size_t m = 0;
+        for (size_t i = 1; i < g_pool.size(); i++) if (g_pool[i].cap < g_pool[m].cap) m = i;
+        free(g_pool[m].p);
+        g_pool.erase(g_pool.begin() + m);
+    }
+}
+
 struct ResPriv {
-    std::vector<int32_t> query_len, n_kmers, k_used;
-    std::vector<uint64_t> match_off;
-    std::vector<kmcpg_match> matches;
+    BigBuf query_len, n_kmers, k_used, match_off, matches;
+    ~ResPriv() { big_release(query_len); big_release(n_kmers); big_release(k_used); big_release(match_off); big_release(matches); }
 };
 
 // matches of one round, flat, in local-query order
 struct Round {
     std::vector<uint32_t> queries;        // local index → global query
     std::vector<uint64_t> off;            // local index → range in `matches`
-    std::vector<kmcpg_match> matches;
+    BigBuf buf;                           // kmcpg_match[n]
+    size_t n = 0;
+    kmcpg_match *matches() const { return (kmcpg_match *)buf.p; }
 };
 
-// filters + sorts the hits of local queries [lo, hi) (U:7466-7491, U:273-311)
-void post_filter(const kmcpg_engine_opts *o, const kmcpg_hits &hits, const std::vector<uint64_t> &hoff, const std::vector<uint32_t> &cur,
-                 const double *tsize, FprCache *cache, uint32_t lo, uint32_t hi, std::vector<kmcpg_match> &out, std::vector<uint32_t> &count) {
+// filters + sorts the hits of local queries [lo, hi) (U:7466-7491, U:273-311); matches are written densely from dst
+size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_hits &hits, const uint64_t *hoff, const uint32_t *cur, const double *tsize, FprCache *cache,
+                   uint32_t lo, uint32_t hi, kmcpg_match *dst, uint32_t *count) {
     const Less less{o->sort_by};
+    size_t w = 0;
     for (uint32_t l = lo; l < hi; l++) {
         const int n = hits.n_kmers[l];
         count[l] = 0;
         if (n == 0 || hoff[l] == hoff[l + 1]) continue;
-        const uint32_t q = cur[l];
+        const uint32_t q = cur ? cur[l] : l;
         const double nh = (double)n;
-        const size_t start = out.size();
+        const size_t start = w;
         for (uint64_t i = hoff[l]; i < hoff[l + 1]; i++) {
             const kmcpg_hit &h = hits.hits[i];
             const double c = (double)h.count, sz = tsize[h.target];
@@ -87,24 +129,24 @@ void post_filter(const kmcpg_engine_opts *o, const kmcpg_hits &hits, const std::
             if (!(tcov >= o->min_target_cov)) continue;              // U:7473-7474
             const double fpr = cache->get(n, (int)h.count);
             if (!(fpr <= o->max_fpr)) continue;                      // U:7477-7478
-            kmcpg_match m;
+            kmcpg_match &m = dst[w++];
             m.query = q; m.target = h.target; m.count = h.count; m._pad = 0;
             m.fpr = fpr; m.qcov = c / nh; m.tcov = tcov; m.jacc = c / (nh + sz - c);   // U:7470-7488
-            out.push_back(m);
         }
-        size_t cnt = out.size() - start;
-        if (cnt > 1 && !o->do_not_sort) std::sort(out.begin() + start, out.end(), less);   // U:273-282
+        size_t cnt = w - start;
+        if (cnt > 1 && !o->do_not_sort) std::sort(dst + start, dst + w, less);     // U:273-282
         if (cnt > 0 && o->top_n_scores > 0 && !o->do_not_sort) {     // U:285-311 (kept verbatim, including [:i+1])
             int nsc = 0; double pscore = 1024; size_t i = 0; bool broke = false;
             for (i = 0; i < cnt; i++) {
-                const kmcpg_match &m = out[start + i];
+                const kmcpg_match &m = dst[start + i];
                 double score = o->sort_by == 0 ? m.qcov : (o->sort_by == 1 ? m.tcov : m.jacc);
                 if (score < pscore) { nsc++; if (nsc > o->top_n_scores) { broke = true; break; } pscore = score; }
             }
-            if (broke) { out.resize(start + i + 1); cnt = i + 1; }
+            if (broke) { cnt = i + 1; w = start + cnt; }
         }
         count[l] = (uint32_t)cnt;
     }
+    return w;
 }
 
 }  // namespace
@@ -126,6 +168,8 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
     int rc = kmcpg_db_info(ctx, &info);
     if (rc) return rc;
     memset(out, 0, sizeof(*out));
+    auto T0 = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     const uint32_t step = o->paired ? 2 : 1;
     const uint32_t nq = n_seqs / step;
     static thread_local FprCache tl_cache;
@@ -134,27 +178,33 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
     const double *tsize = kmcpg_internal_target_sizes(ctx);
 
     ResPriv *priv = new ResPriv();
-    priv->query_len.assign(nq, 0); priv->n_kmers.assign(nq, 0); priv->k_used.assign(nq, info.ks[0]);
-    std::vector<uint32_t> pending(nq);
-    for (uint32_t q = 0; q < nq; q++) pending[q] = q;
+    priv->query_len = big_acquire((size_t)nq * 4); priv->n_kmers = big_acquire((size_t)nq * 4); priv->k_used = big_acquire((size_t)nq * 4);
+    priv->match_off = big_acquire(((size_t)nq + 1) * 8);
+    int32_t *r_qlen = (int32_t *)priv->query_len.p, *r_nk = (int32_t *)priv->n_kmers.p, *r_k = (int32_t *)priv->k_used.p;
+    uint64_t *r_off = (uint64_t *)priv->match_off.p;
     const int tries_max = (o->try_se && o->paired) ? 3 : 1;
     int threads = o->threads > 0 ? o->threads : (int)std::thread::hardware_concurrency();
-    threads = std::max(1, std::min(threads, 32));
+    threads = std::max(1, std::min(threads, 16));
 
+    // scratch that survives between calls of this thread (no page faults after the first batch)
+    static thread_local std::vector<uint64_t> hoff;
+    static thread_local std::vector<uint32_t> count;
     std::vector<Round> rounds;
-    // where the final matches of query q live: (round, local index); round -1 = unmatched
-    std::vector<int32_t> q_round(nq, -1);
-    std::vector<uint32_t> q_local(nq, 0);
+    std::vector<uint32_t> pending;                // empty + all_pending = every query
+    bool all_pending = true;
+    std::vector<int32_t> q_round;                 // only materialised when more than one round happens
+    std::vector<uint32_t> q_local;
     std::vector<uint8_t> sub_seq;
     std::vector<uint64_t> sub_off;
-    for (int ik = 0; ik < info.n_ks && !pending.empty(); ik++) {
+    for (int ik = 0; ik < info.n_ks && (all_pending || !pending.empty()); ik++) {
         const int k = info.ks[ik];
         std::vector<uint32_t> next_k;                 // queries that found nothing with this k
         std::vector<uint32_t> cur = pending;
-        for (int tries = 0; tries < tries_max && !cur.empty(); tries++) {
+        bool cur_all = all_pending;
+        for (int tries = 0; tries < tries_max && (cur_all || !cur.empty()); tries++) {
             // pack the pending subset (the first pass uses the caller's buffers untouched)
             const uint8_t *bs = seq; const uint64_t *bo = off; uint32_t bn = n_seqs;
-            if (cur.size() != nq) {
+            if (!cur_all) {
                 sub_off.assign(1, 0); sub_seq.clear();
                 for (uint32_t q : cur)
                     for (uint32_t m = 0; m < step; m++) {
@@ -174,19 +224,23 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
             if (rc) { delete priv; return rc; }
             out->ms_gpu_total += hits.ms_total; out->probe_row_bytes += hits.probe_row_bytes; out->kernel_launches += hits.kernel_launches;
 
-            const uint32_t ln = (uint32_t)cur.size();
+            auto Tp = std::chrono::steady_clock::now();
+            const uint32_t ln = cur_all ? nq : (uint32_t)cur.size();
+            const uint32_t *curp = cur_all ? nullptr : cur.data();
             // hit ranges per local query (hits are sorted by query)
-            std::vector<uint64_t> hoff((size_t)ln + 1, 0);
+            hoff.assign((size_t)ln + 1, 0);
             for (uint64_t i = 0; i < hits.n_hits; i++) hoff[hits.hits[i].query + 1]++;
             for (uint32_t i = 0; i < ln; i++) hoff[i + 1] += hoff[i];
+            count.resize(ln);
 
             rounds.emplace_back();
             Round &R = rounds.back();
             const int ridx = (int)rounds.size() - 1;
-            std::vector<uint32_t> count(ln, 0);
-            int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 16384 + 1));
-            std::vector<std::vector<kmcpg_match>> parts(T);
+            R.buf = big_acquire(std::max<uint64_t>(hits.n_hits, 1) * sizeof(kmcpg_match));
+            kmcpg_match *M = R.matches();
+            int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 32768 + 1));
             std::vector<uint32_t> bounds(T + 1, ln);
+            std::vector<size_t> produced(T, 0);
             bounds[0] = 0;
             for (int t = 1; t < T; t++) {            // split by hits so the threads get equal work
                 uint64_t want = hits.n_hits * (uint64_t)t / T;
@@ -194,71 +248,83 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                 if (bounds[t] > ln) bounds[t] = ln;
                 if (bounds[t] < bounds[t - 1]) bounds[t] = bounds[t - 1];
             }
-            if (T == 1) {
-                post_filter(o, hits, hoff, cur, tsize, cache, 0, ln, parts[0], count);
-            } else {
+            // every thread writes at the hit offset of its first query: no overlap, compaction only if a filter dropped hits
+            const uint64_t *hp = hoff.data();
+            uint32_t *cp = count.data();
+            auto work = [&](int t) { produced[t] = post_filter(o, hits, hp, curp, tsize, cache, bounds[t], bounds[t + 1], M + hp[bounds[t]], cp); };
+            if (T == 1) work(0);
+            else {
                 std::vector<std::thread> th;
-                for (int t = 0; t < T; t++)
-                    th.emplace_back([&, t] {
-                        parts[t].reserve((size_t)(hoff[bounds[t + 1]] - hoff[bounds[t]]));
-                        post_filter(o, hits, hoff, cur, tsize, cache, bounds[t], bounds[t + 1], parts[t], count);
-                    });
+                for (int t = 1; t < T; t++) th.emplace_back(work, t);
+                work(0);
                 for (auto &t : th) t.join();
             }
-            size_t total = 0;
-            for (auto &v : parts) total += v.size();
-            if (T == 1) R.matches.swap(parts[0]);
-            else {
-                R.matches.resize(total);
-                size_t w = 0;
-                for (auto &v : parts) { if (!v.empty()) memcpy(R.matches.data() + w, v.data(), v.size() * sizeof(kmcpg_match)); w += v.size(); }
+            size_t w = produced[0];
+            for (int t = 1; t < T; t++) {
+                if (produced[t] && w != hp[bounds[t]]) memmove(M + w, M + hp[bounds[t]], produced[t] * sizeof(kmcpg_match));
+                w += produced[t];
             }
+            R.n = w;
             R.off.resize((size_t)ln + 1);
             R.off[0] = 0;
+            const bool single = (ik == 0 && tries == 0 && cur_all);
+            if (!single && q_round.empty()) { q_round.assign(nq, -1); q_local.assign(nq, 0); }
             std::vector<uint32_t> retry;
             for (uint32_t l = 0; l < ln; l++) {
-                const uint32_t q = cur[l];
+                const uint32_t q = curp ? curp[l] : l;
                 const int n = hits.n_kmers[l];
-                R.off[l + 1] = R.off[l] + count[l];
-                priv->query_len[q] = hits.query_len[l];
-                priv->k_used[q] = k;
-                if (n == 0) { if (tries == 0) priv->n_kmers[q] = 0; continue; }     // U:778-786, U:854-869: final, unmatched
-                priv->n_kmers[q] = n;
-                if (count[l]) { q_round[q] = ridx; q_local[q] = l; }
+                R.off[l + 1] = R.off[l] + cp[l];
+                r_qlen[q] = hits.query_len[l];
+                r_k[q] = k;
+                if (n == 0) { if (tries == 0) r_nk[q] = 0; continue; }             // U:778-786, U:854-869: final, unmatched
+                r_nk[q] = n;
+                if (cp[l]) { if (!q_round.empty()) { q_round[q] = ridx; q_local[q] = l; } }
                 else retry.push_back(q);
             }
-            R.queries.swap(cur);
+            if (single && (tries_max > 1 || info.n_ks > 1) && !retry.empty()) {
+                // more rounds will follow: remember where round 0 put every matched query
+                q_round.assign(nq, -1); q_local.assign(nq, 0);
+                for (uint32_t l = 0; l < ln; l++) if (cp[l]) { q_round[l] = 0; q_local[l] = l; }
+            }
+            if (!cur_all) R.queries.swap(cur);
             kmcpg_free_hits(&hits);
+            out->ms_post += ms_since(Tp);
+            cur_all = false;
             if (tries + 1 < tries_max) cur.swap(retry);          // --try-se: read1 only, then read2 only
             else { next_k.insert(next_k.end(), retry.begin(), retry.end()); cur.clear(); }
         }
         std::sort(next_k.begin(), next_k.end());
         pending.swap(next_k);                                    // U:1018-1023: try the next smaller k
+        all_pending = false;
     }
 
-    priv->match_off.assign((size_t)nq + 1, 0);
-    if (rounds.size() == 1 && rounds[0].queries.size() == nq) {
+    if (rounds.size() == 1) {
         // the common case: one round over all queries — its flat array already is the answer
-        priv->matches.swap(rounds[0].matches);
-        for (uint32_t q = 0; q < nq; q++) priv->match_off[q + 1] = rounds[0].off[q + 1];
+        priv->matches = rounds[0].buf; rounds[0].buf = BigBuf();
+        memcpy(r_off, rounds[0].off.data(), ((size_t)nq + 1) * 8);
+        out->n_matches = rounds[0].n;
     } else {
+        r_off[0] = 0;
         for (uint32_t q = 0; q < nq; q++) {
             uint64_t c = 0;
-            if (q_round[q] >= 0) { const Round &R = rounds[q_round[q]]; c = R.off[q_local[q] + 1] - R.off[q_local[q]]; }
-            priv->match_off[q + 1] = priv->match_off[q] + c;
+            if (!q_round.empty() && q_round[q] >= 0) { const Round &R = rounds[q_round[q]]; c = R.off[q_local[q] + 1] - R.off[q_local[q]]; }
+            r_off[q + 1] = r_off[q] + c;
         }
-        priv->matches.resize(priv->match_off[nq]);
+        priv->matches = big_acquire(std::max<uint64_t>(r_off[nq], 1) * sizeof(kmcpg_match));
+        kmcpg_match *dst = (kmcpg_match *)priv->matches.p;
         for (uint32_t q = 0; q < nq; q++)
-            if (q_round[q] >= 0) {
+            if (!q_round.empty() && q_round[q] >= 0) {
                 const Round &R = rounds[q_round[q]];
-                memcpy(priv->matches.data() + priv->match_off[q], R.matches.data() + R.off[q_local[q]],
-                       (priv->match_off[q + 1] - priv->match_off[q]) * sizeof(kmcpg_match));
+                memcpy(dst + r_off[q], R.matches() + R.off[q_local[q]], (r_off[q + 1] - r_off[q]) * sizeof(kmcpg_match));
             }
+        out->n_matches = r_off[nq];
+        for (auto &R : rounds) big_release(R.buf);
     }
-    out->n_queries = nq; out->n_matches = priv->matches.size();
-    out->query_len = priv->query_len.data(); out->n_kmers = priv->n_kmers.data(); out->k_used = priv->k_used.data();
-    out->match_off = priv->match_off.data(); out->matches = priv->matches.data();
+    out->n_queries = nq;
+    out->query_len = r_qlen; out->n_kmers = r_nk; out->k_used = r_k;
+    out->match_off = r_off; out->matches = (kmcpg_match *)priv->matches.p;
     out->_priv = priv;
+    out->ms_total = ms_since(T0);
     return KMCPG_OK;
 }
 
