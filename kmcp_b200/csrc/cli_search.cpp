@@ -1,0 +1,428 @@
+// kmcp-gpu — drop-in for `kmcp search` on B200: same flags, same input formats, same 15-column TSV.
+// Mirrors kmcp/cmd/search.go of the reference: flag set S:1031-1107 (names, shorthands, defaults), DB discovery
+// S:299-324, query construction S:793-1000 (single-end, paired-end -1/-2, whole-file -g), ordered output and
+// the 15 columns S:437 + S:460-575, trailer S:1023-1025, log lines S:1011-1017.
+// All searching goes through libkmcp_gpu (include/kmcp_gpu.h); there is no CPU search path in this program.
+#include <dirent.h>
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/kmcp_gpu.h"
+
+namespace {
+
+bool g_quiet = false;
+FILE *g_log = nullptr;
+
+void logf(const char *level, const char *fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    auto now = std::chrono::system_clock::now();
+    time_t t = std::chrono::system_clock::to_time_t(now);
+    int ms = (int)(std::chrono::duration_cast<std::chrono::milliseconds>(now.time_since_epoch()).count() % 1000);
+    struct tm tmv;
+    localtime_r(&t, &tmv);
+    char ts[32];
+    strftime(ts, sizeof(ts), "%H:%M:%S", &tmv);
+    bool err = !strcmp(level, "ERRO");
+    if (!g_quiet || err) fprintf(stderr, "%s.%03d [%s] %s\n", ts, ms, level, buf);
+    if (g_log) fprintf(g_log, "%s.%03d [%s] %s\n", ts, ms, level, buf);
+}
+
+[[noreturn]] void die(const char *fmt, ...) {     // checkError → log + os.Exit(-1) (util-cli.go:35-40)
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    logf("ERRO", "%s", buf);
+    exit(255);
+}
+
+struct Opts {
+    std::string db_dir, out_file = "-", read1, read2, sort_by = "qcov", query_id, log_file;
+    std::vector<std::string> files, name_maps;
+    int dedup = 256, min_kmers = 10, min_qlen = 30, top_scores = 0, threads = 0, device = 0;
+    double qcov = 0.55, tcov = 0, max_fpr = 0.01;
+    bool try_se = false, whole_file = false, use_filename = false, default_name_map = false, keep_unmatched = false, no_header = false,
+         do_not_sort = false;
+    size_t batch_reads = 1u << 20, batch_bytes = 512u << 20;
+};
+
+void usage() {
+    fputs(
+        "Search sequences against a kmcp database on a B200 GPU (drop-in for `kmcp search`)\n\n"
+        "Usage:\n  kmcp-gpu search [flags] [-w] -d <kmcp db> [-t <min-query-cov>] [read1.fq.gz] [read2.fq.gz] [unpaired.fq.gz] [-o read.tsv.gz]\n\n"
+        "Flags (same names, shorthands and defaults as kmcp search):\n"
+        "  -d, --db-dir string              database directory created by \"kmcp index\"\n"
+        "  -1, --read1 string / -2, --read2 string   paired-end read files\n"
+        "      --try-se                     if paired-end reads have no hits, re-search with read1, then read2\n"
+        "  -u, --kmer-dedup-threshold int   remove duplicated kmers for a query with >= X k-mers (default 256)\n"
+        "  -g, --query-whole-file           use the whole file as a query\n"
+        "  -G, --use-filename               use file name as query ID with -g\n"
+        "      --query-id string            custom query ID with -g\n"
+        "  -c, --min-kmers int              minimum number of matched k-mers (default 10)\n"
+        "  -m, --min-query-len int          minimum query length (default 30)\n"
+        "  -t, --min-query-cov float        minimum query coverage (default 0.55)\n"
+        "  -T, --min-target-cov float       minimum target coverage (default 0)\n"
+        "  -f, --max-fpr float              maximum false positive rate of a query (default 0.01)\n"
+        "  -o, --out-file string            out file, \".gz\" suffix supported (default \"-\")\n"
+        "  -N, --name-map strings           two-column file(s) mapping reference IDs to user-defined values\n"
+        "  -D, --default-name-map           load ${db}/__name_mapping.tsv first\n"
+        "  -K, --keep-unmatched             keep unmatched query sequence information\n"
+        "  -n, --keep-top-scores int        keep matches with the top N scores, 0 for all\n"
+        "  -H, --no-header-row              do not print header row\n"
+        "  -s, --sort-by string             qcov, tcov or jacc (default \"qcov\")\n"
+        "  -S, --do-not-sort                do not sort matches of a query\n"
+        "  -w, --load-whole-db / --low-mem  accepted for compatibility (the index always lives in HBM)\n"
+        "  -j, --threads int                host threads for the post-filter (default all)\n"
+        "  -q, --quiet / --log string       logging\n"
+        "      --gpu int                    CUDA device ordinal (default 0)\n",
+        stderr);
+}
+
+struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default reader: ID = header up to first blank)
+    gzFile f = nullptr;
+    std::string path, line, pending;
+    bool have_pending = false, eof = false;
+    bool open(const std::string &p) {
+        path = p;
+        f = p == "-" ? gzdopen(0, "rb") : gzopen(p.c_str(), "rb");
+        if (f) gzbuffer(f, 1 << 20);
+        return f != nullptr;
+    }
+    void close() { if (f) gzclose(f); f = nullptr; }
+    bool getline(std::string &out) {
+        if (have_pending) { out.swap(pending); have_pending = false; return true; }
+        out.clear();
+        char buf[1 << 16];
+        for (;;) {
+            if (!gzgets(f, buf, sizeof(buf))) return !out.empty();
+            size_t n = strlen(buf);
+            out.append(buf, n);
+            if (n && buf[n - 1] == '\n') break;
+        }
+        while (!out.empty() && (out.back() == '\n' || out.back() == '\r')) out.pop_back();
+        return true;
+    }
+    // returns false at EOF
+    bool next(std::string &id, std::string &seq) {
+        std::string l;
+        do { if (!getline(l)) return false; } while (l.empty());
+        if (l[0] != '>' && l[0] != '@') die("invalid FASTA/Q record in %s", path.c_str());
+        bool fq = l[0] == '@';
+        size_t e = 1;
+        while (e < l.size() && l[e] != ' ' && l[e] != '\t') e++;
+        id.assign(l, 1, e - 1);
+        seq.clear();
+        if (fq) {
+            if (!getline(l)) return true;
+            seq = l;
+            std::string plus, qual;
+            if (!getline(plus)) return true;
+            while (plus.empty() || plus[0] != '+') { seq += plus; if (!getline(plus)) return true; }   // multi-line FASTQ
+            size_t got = 0;
+            while (got < seq.size() && getline(qual)) got += qual.size();
+        } else {
+            while (getline(l)) {
+                if (!l.empty() && l[0] == '>') { pending.swap(l); have_pending = true; break; }
+                seq += l;
+            }
+        }
+        return true;
+    }
+};
+
+struct Writer {
+    FILE *fp = nullptr;
+    gzFile gz = nullptr;
+    std::string buf;
+    void open(const std::string &p) {
+        if (p == "-") fp = stdout;
+        else if (p.size() > 3 && p.compare(p.size() - 3, 3, ".gz") == 0) { gz = gzopen(p.c_str(), "wb6"); if (!gz) die("fail to write %s", p.c_str()); gzbuffer(gz, 1 << 20); }
+        else { fp = fopen(p.c_str(), "wb"); if (!fp) die("fail to write %s", p.c_str()); }
+        buf.reserve(8 << 20);
+    }
+    void flush() {
+        if (buf.empty()) return;
+        if (gz) gzwrite(gz, buf.data(), (unsigned)buf.size()); else fwrite(buf.data(), 1, buf.size(), fp);
+        buf.clear();
+    }
+    void write(const char *s, size_t n) { buf.append(s, n); if (buf.size() > (4u << 20)) flush(); }
+    void close() { flush(); if (gz) gzclose(gz); else if (fp && fp != stdout) fclose(fp); else if (fp) fflush(fp); }
+};
+
+bool is_dir(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+bool is_file(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
+
+std::string trim_ext(const std::string &file) {     // filepathTrimExtension: strip dir, .gz/.xz/.zst/.bz2, then one extension
+    std::string b = file.substr(file.find_last_of('/') == std::string::npos ? 0 : file.find_last_of('/') + 1);
+    for (const char *z : {".gz", ".xz", ".zst", ".bz2"}) {
+        size_t n = strlen(z);
+        if (b.size() > n && b.compare(b.size() - n, n, z) == 0) { b.resize(b.size() - n); break; }
+    }
+    size_t dot = b.find_last_of('.');
+    if (dot != std::string::npos && dot > 0) b.resize(dot);
+    return b;
+}
+
+void load_kv(const std::string &path, std::map<std::string, std::string> &m) {
+    Reader r;
+    if (!r.open(path)) die("fail to read name mapping file: %s", path.c_str());
+    std::string l;
+    while (r.getline(l)) {
+        size_t t = l.find('\t');
+        if (l.empty() || t == std::string::npos) continue;
+        m[l.substr(0, t)] = l.substr(t + 1);
+    }
+    r.close();
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Opts o;
+    int ai = 1;
+    if (ai < argc && !strcmp(argv[ai], "search")) ai++;
+    else if (ai < argc && (!strcmp(argv[ai], "-h") || !strcmp(argv[ai], "--help"))) { usage(); return 0; }
+    auto need = [&](int &i) -> const char * { if (i + 1 >= argc) die("flag needs an argument: %s", argv[i]); return argv[++i]; };
+    for (int i = ai; i < argc; i++) {
+        std::string a = argv[i], val;
+        bool has_eq = false;
+        if (a.rfind("--", 0) == 0) { size_t eq = a.find('='); if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_eq = true; } }
+        auto sval = [&]() -> std::string { return has_eq ? val : std::string(need(i)); };
+        if (a == "-h" || a == "--help") { usage(); return 0; }
+        else if (a == "-d" || a == "--db-dir") o.db_dir = sval();
+        else if (a == "-o" || a == "--out-file") o.out_file = sval();
+        else if (a == "-1" || a == "--read1") o.read1 = sval();
+        else if (a == "-2" || a == "--read2") o.read2 = sval();
+        else if (a == "--try-se") o.try_se = true;
+        else if (a == "-u" || a == "--kmer-dedup-threshold") o.dedup = atoi(sval().c_str());
+        else if (a == "-g" || a == "--query-whole-file") o.whole_file = true;
+        else if (a == "-G" || a == "--use-filename") o.use_filename = true;
+        else if (a == "--query-id") o.query_id = sval();
+        else if (a == "-c" || a == "--min-kmers") o.min_kmers = atoi(sval().c_str());
+        else if (a == "-m" || a == "--min-query-len") o.min_qlen = atoi(sval().c_str());
+        else if (a == "-t" || a == "--min-query-cov") o.qcov = atof(sval().c_str());
+        else if (a == "-T" || a == "--min-target-cov") o.tcov = atof(sval().c_str());
+        else if (a == "-f" || a == "--max-fpr") o.max_fpr = atof(sval().c_str());
+        else if (a == "-N" || a == "--name-map") o.name_maps.push_back(sval());
+        else if (a == "-D" || a == "--default-name-map") o.default_name_map = true;
+        else if (a == "-K" || a == "--keep-unmatched") o.keep_unmatched = true;
+        else if (a == "-n" || a == "--keep-top-scores") o.top_scores = atoi(sval().c_str());
+        else if (a == "-H" || a == "--no-header-row") o.no_header = true;
+        else if (a == "-s" || a == "--sort-by") o.sort_by = sval();
+        else if (a == "-S" || a == "--do-not-sort") o.do_not_sort = true;
+        else if (a == "-w" || a == "--load-whole-db" || a == "--low-mem") {}
+        else if (a == "-j" || a == "--threads") o.threads = atoi(sval().c_str());
+        else if (a == "-q" || a == "--quiet") g_quiet = true;
+        else if (a == "--log") o.log_file = sval();
+        else if (a == "--gpu") o.device = atoi(sval().c_str());
+        else if (a == "-i" || a == "--infile-list") { Reader r; std::string f = sval(), l; if (!r.open(f)) die("fail to read %s", f.c_str()); while (r.getline(l)) if (!l.empty()) o.files.push_back(l); r.close(); }
+        else if (a.size() > 1 && a[0] == '-' && a != "-") die("unknown flag: %s", a.c_str());
+        else o.files.push_back(a);
+    }
+    if (!o.log_file.empty()) g_log = fopen(o.log_file.c_str(), "w");
+    auto t_start = std::chrono::steady_clock::now();
+
+    // ---- flag checks (S:157-205) ----
+    if (o.db_dir.empty()) die("flag -d/--db-dir needed");
+    if (o.min_qlen < 0) die("value of flag --min-query-len should be greater than or equal to 0");
+    if (o.min_kmers <= 0) die("value of flag --min-kmers should be greater than 0");
+    if (!(o.max_fpr > 0)) die("value of flag --max-fpr should be greater than 0");
+    if (o.dedup <= 0) die("value of flag --kmer-dedup-threshold should be greater than 0");
+    if (o.top_scores < 0) die("value of flag --keep-top-scores should be greater than or equal to 0");
+    int sort_by = o.sort_by == "qcov" ? 0 : o.sort_by == "tcov" ? 1 : o.sort_by == "jacc" ? 2 : -1;
+    if (sort_by < 0) die("invalid value for flag -s/--sort-by: %s. Available: qcov/tsov/jacc", o.sort_by.c_str());
+    if (o.qcov < 0 || o.qcov > 1) die("value of -t/--min-query-cov should be in range [0, 1]");
+    if (o.tcov < 0 || o.tcov > 1) die("value of -T/-target-cov should be in range [0, 1]");
+    if (o.do_not_sort && o.top_scores > 0) logf("WARN", "flag -n/--keep-top-scores ignored when -S/--do-not-sort given");
+
+    logf("INFO", "kmcp-gpu (B200 search path of kmcp v0.9.5)");
+    logf("INFO", "checking input files ...");
+    bool paired = false;
+    std::vector<std::string> files;
+    if (o.read1.empty()) { if (!o.read2.empty()) files.push_back(o.read2); }
+    else if (o.read2.empty()) files.push_back(o.read1);
+    else { paired = true; logf("INFO", "paired end files given: %s, %s", o.read1.c_str(), o.read2.c_str()); }
+    if (o.try_se && !paired) { logf("WARN", "flag --try-se ignored for single-end input(s)"); o.try_se = false; }
+    if (!paired) {
+        for (auto &f : o.files) files.push_back(f);
+        if (files.empty()) files.push_back("-");
+        logf("INFO", "  %zu input file(s) given", files.size());
+        for (auto &f : files) if (f != "-" && f == o.out_file) die("out file should not be one of the input file");
+    }
+
+    // ---- database (S:299-324): every child directory holding __db.yml ----
+    logf("INFO", "checking the database: %s", o.db_dir.c_str());
+    std::vector<std::string> dbs;
+    DIR *d = opendir(o.db_dir.c_str());
+    if (!d) die("read database error: open %s: no such file or directory", o.db_dir.c_str());
+    while (dirent *e = readdir(d)) {
+        if (e->d_name[0] == '.') continue;
+        std::string p = o.db_dir + "/" + e->d_name;
+        if (is_dir(p) && is_file(p + "/__db.yml")) dbs.push_back(p);
+    }
+    closedir(d);
+    std::sort(dbs.begin(), dbs.end());
+    if (dbs.empty()) die("invalid kmcp database: %s", o.db_dir.c_str());
+    if (dbs.size() > 1) die("databases with several repeats (R001, R002, ...) are not supported by kmcp-gpu yet");
+
+    kmcpg_ctx *ctx = nullptr;
+    if (kmcpg_create(o.device, &ctx)) die("%s", kmcpg_last_error(nullptr));
+    logf("INFO", "loading database into HBM ...");
+    auto t_db = std::chrono::steady_clock::now();
+    if (kmcpg_open_db(ctx, dbs[0].c_str(), nullptr)) die("open kmcp db: %s: %s", dbs[0].c_str(), kmcpg_last_error(ctx));
+    kmcpg_db_info_t info;
+    kmcpg_db_info(ctx, &info);
+    logf("INFO", "database loaded: %s (%d blocks, %lld targets, %.2f GB in HBM, %.1f s)", o.db_dir.c_str(), info.n_blocks, (long long)info.n_targets,
+         info.resident_bytes / 1e9, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_db).count());
+    if (o.qcov <= info.fpr)      // S:405-409
+        logf("WARN", "the value of -t/--min-query-cov (%f) is <= FPR (%f) of the database, you may get many false positives", o.qcov, info.fpr);
+    logf("INFO", "-------------------- [main parameters] --------------------");
+    logf("INFO", "  minimum    query length: %d", o.min_qlen);
+    logf("INFO", "  minimum  matched k-mers: %d", o.min_kmers);
+    logf("INFO", "  minimum  query coverage: %f", o.qcov);
+    logf("INFO", "  minimum target coverage: %f", o.tcov);
+    logf("INFO", "-------------------- [main parameters] --------------------");
+
+    std::map<std::string, std::string> name_map;
+    if (o.default_name_map && is_file(dbs[0] + "/__name_mapping.tsv")) load_kv(dbs[0] + "/__name_mapping.tsv", name_map);
+    for (auto &f : o.name_maps) load_kv(f, name_map);       // user maps override the default one (U:322-330)
+    std::vector<const std::string *> mapped((size_t)info.n_targets, nullptr);
+    std::vector<kmcpg_target_t> targets((size_t)info.n_targets);
+    for (int64_t t = 0; t < info.n_targets; t++) {
+        kmcpg_target(ctx, t, &targets[(size_t)t]);
+        auto it = name_map.find(targets[(size_t)t].name);
+        if (it != name_map.end()) mapped[(size_t)t] = &it->second;
+    }
+
+    Writer w;
+    w.open(o.out_file);
+    if (!o.no_header) {
+        const char *h = "#query\tqLen\tqKmers\tFPR\thits\ttarget\tchunkIdx\tchunks\ttLen\tkSize\tmKmers\tqCov\ttCov\tjacc\tqueryIdx\n";   // S:437
+        w.write(h, strlen(h));
+    }
+
+    kmcpg_engine_opts eo;
+    kmcpg_default_engine_opts(&eo);
+    eo.min_query_len = o.min_qlen; eo.min_matched = o.min_kmers; eo.dedup_threshold = o.dedup; eo.min_query_cov = o.qcov; eo.min_target_cov = o.tcov;
+    eo.max_fpr = o.max_fpr; eo.sort_by = sort_by; eo.do_not_sort = o.do_not_sort; eo.top_n_scores = o.top_scores; eo.try_se = o.try_se;
+    eo.paired = paired; eo.threads = o.threads;
+
+    // ---- batches: ids + packed sequences → engine → TSV in input order ----
+    std::vector<std::string> ids;
+    std::vector<uint8_t> seqbuf;
+    std::vector<uint64_t> offs(1, 0);
+    uint64_t total = 0, matched = 0, query_base = 0;
+    char line[512];
+    auto flush_batch = [&]() {
+        if (ids.empty()) return;
+        if (seqbuf.empty()) seqbuf.push_back(0);
+        kmcpg_results r;
+        if (kmcpg_engine_search(ctx, &eo, seqbuf.data(), offs.data(), (uint32_t)(offs.size() - 1), &r)) die("%s", kmcpg_last_error(ctx));
+        for (uint32_t q = 0; q < r.n_queries; q++) {
+            const uint64_t a = r.match_off[q], b = r.match_off[q + 1];
+            const std::string &id = ids[q];
+            if (a == b) {
+                if (!o.keep_unmatched) continue;
+                int n = snprintf(line, sizeof(line), "\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%llu\n", r.query_len[q], r.n_kmers[q], r.k_used[q],     // S:460-511
+                                 (unsigned long long)(query_base + q));
+                w.write(id.data(), id.size()); w.write(line, (size_t)n);
+                continue;
+            }
+            matched++;
+            for (uint64_t i = a; i < b; i++) {
+                const kmcpg_match &m = r.matches[i];
+                const kmcpg_target_t &t = targets[m.target];
+                const std::string *mp = mapped[m.target];
+                int n1 = snprintf(line, sizeof(line), "\t%d\t%d\t%.4e\t%llu\t", r.query_len[q], r.n_kmers[q], m.fpr, (unsigned long long)(b - a));
+                w.write(id.data(), id.size()); w.write(line, (size_t)n1);
+                if (mp) w.write(mp->data(), mp->size()); else w.write(t.name, strlen(t.name));
+                int n2 = snprintf(line, sizeof(line), "\t%u\t%u\t%llu\t%d\t%u\t%.4f\t%.4f\t%.4f\t%llu\n", t.index & 0xFFFFu, t.index >> 16,          // S:532-539
+                                  (unsigned long long)t.genome_size, r.k_used[q], m.count, m.qcov, m.tcov, m.jacc, (unsigned long long)(query_base + q));
+                w.write(line, (size_t)n2);
+            }
+        }
+        total += r.n_queries;
+        query_base += r.n_queries;
+        kmcpg_free_results(&r);
+        ids.clear(); seqbuf.clear(); offs.assign(1, 0);
+        if (!g_quiet) fprintf(stderr, "processed queries: %llu\r", (unsigned long long)total);
+    };
+    auto add_seq = [&](const std::string &s) { seqbuf.insert(seqbuf.end(), s.begin(), s.end()); offs.push_back(seqbuf.size()); };
+
+    logf("INFO", "searching ...");
+    auto t_search = std::chrono::steady_clock::now();
+    std::string id, seq, id2, seq2;
+    if (paired) {
+        Reader r1, r2;
+        if (!r1.open(o.read1)) die("%s: no such file", o.read1.c_str());
+        if (!r2.open(o.read2)) die("%s: no such file", o.read2.c_str());
+        logf("INFO", "reading from paired-end files: %s, %s", o.read1.c_str(), o.read2.c_str());
+        while (r1.next(id, seq) && r2.next(id2, seq2)) {          // S:806-867: ID of read1
+            ids.push_back(id); add_seq(seq); add_seq(seq2);
+            if (ids.size() >= o.batch_reads || seqbuf.size() >= o.batch_bytes) flush_batch();
+        }
+        r1.close(); r2.close();
+    } else {
+        const int kmax = info.ks[0];
+        for (auto &file : files) {
+            logf("INFO", "reading sequence file: %s", file.c_str());
+            Reader r;
+            if (!r.open(file)) die("%s: no such file", file.c_str());
+            if (o.whole_file) {                                   // S:885-937 (the N-run follows every record after the second)
+                std::string qid, whole;
+                bool first = true;
+                while (r.next(id, seq)) {
+                    if (first) { qid = o.use_filename ? trim_ext(file) : (!o.query_id.empty() ? o.query_id : id); whole = seq; first = false; }
+                    else { whole += seq; whole.append((size_t)(kmax - 1), 'N'); }
+                }
+                if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); r.close(); continue; }
+                ids.push_back(qid); add_seq(whole);
+                if (seqbuf.size() >= o.batch_bytes) flush_batch();
+            } else {
+                uint64_t n0 = ids.size() + total;
+                while (r.next(id, seq)) {
+                    ids.push_back(id); add_seq(seq);
+                    if (ids.size() >= o.batch_reads || seqbuf.size() >= o.batch_bytes) flush_batch();
+                }
+                if (ids.size() + total == n0) logf("WARN", "no valid sequences in file: %s", file.c_str());
+            }
+            r.close();
+        }
+    }
+    flush_batch();
+
+    double minutes = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_search).count() / 60.0;
+    if (!g_quiet) fprintf(stderr, "\n");
+    logf("INFO", "");
+    logf("INFO", "processed queries: %llu, speed: %.3f million queries per minute", (unsigned long long)total, total / 1e6 / (minutes > 0 ? minutes : 1e-9));
+    logf("INFO", "%.4f%% (%llu/%llu) queries matched", total ? (double)matched / (double)total * 100 : 0.0, (unsigned long long)matched, (unsigned long long)total);
+    logf("INFO", "done searching");
+    if (o.out_file != "-") logf("INFO", "search results saved to: %s", o.out_file.c_str());
+    int n = snprintf(line, sizeof(line), "# input queries: %llu\n# matched queries: %llu\n# matched percentage: %.4f%%\n", (unsigned long long)total,    // S:1023-1025
+                     (unsigned long long)matched, total ? (double)matched / (double)total * 100 : NAN);
+    w.write(line, (size_t)n);
+    w.close();
+    kmcpg_close(ctx);
+    logf("INFO", "");
+    logf("INFO", "elapsed time: %.3fs", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    if (g_log) fclose(g_log);
+    return 0;
+}

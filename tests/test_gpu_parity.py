@@ -301,3 +301,66 @@ def test_errors_are_reported_not_fatal(gpu_ctx, tmp_path):
     with pytest.raises(api.KmcpGpuError) as e:
         gpu_ctx.open_db(str(d))
     assert e.value.code == api.KMCPG_EFORMAT
+
+
+# ---------------------------------------------------------------------------------------------------- CLI
+def _write_fastq(path, ids, seqs, gz=True):
+    import gzip
+    op = gzip.open if gz else open
+    with op(path, "wb") as f:
+        for i, s in zip(ids, seqs):
+            f.write(b"@" + i + b" some description\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+
+def _run_cli(args):
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmcp_b200", "kmcp-gpu")
+    p = subprocess.run([exe, "search", "-q"] + args, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    return p
+
+
+def test_cli_tsv_is_byte_identical_to_the_oracle_formatter(oracle, small_db, tmp_path):
+    """kmcp-gpu search: same flags as `kmcp search`, 15-column TSV + trailer identical to the oracle's S:437-575 restatement"""
+    import gzip
+    O = oracle
+    odb = O.DB(small_db)
+    dbdir = os.path.dirname(small_db)
+    reads = helpers.make_reads(O, RSEED + 20, 1500, 40, 30000, GSEED) + [r for r in helpers.edge_reads(21) if len(r) > 0]
+    ids = [b"read_%d/1" % i for i in range(len(reads))]
+    fq = str(tmp_path / "q.fq.gz")
+    _write_fastq(fq, ids, reads)
+    # single-end, defaults, gz output
+    out = str(tmp_path / "o.tsv.gz")
+    _run_cli(["-d", dbdir, fq, "-o", out])
+    exp = O.format_tsv(odb, ids, odb.search(reads))
+    assert gzip.open(out, "rb").read().decode() == exp
+    # -K keeps unmatched rows; other thresholds; sort by jacc; top score
+    out2 = str(tmp_path / "o2.tsv")
+    _run_cli(["-d", dbdir, fq, "-o", out2, "-K", "-t", "0.4", "-c", "5", "-s", "jacc", "-n", "1", "-f", "0.05"])
+    oo = O.default_opts(); oo.min_query_cov = 0.4; oo.min_matched = 5; oo.sort_by = 2; oo.top_n_scores = 1; oo.max_fpr = 0.05
+    exp2 = O.format_tsv(odb, ids, odb.search(reads, opts=oo), keep_unmatched=True)
+    assert open(out2).read() == exp2
+    # paired-end (-1/-2): IDs of read1, mates concatenated
+    r2 = helpers.make_reads(O, RSEED + 21, len(reads), 40, 30000, GSEED)
+    fq2 = str(tmp_path / "q2.fq")
+    _write_fastq(fq2, [b"read_%d/2" % i for i in range(len(r2))], r2, gz=False)
+    out3 = str(tmp_path / "o3.tsv")
+    _run_cli(["-d", dbdir, "-1", fq, "-2", fq2, "-o", out3, "-H"])
+    inter = [x for p in zip(reads, r2) for x in p]
+    exp3 = O.format_tsv(odb, ids, odb.search(inter, paired=True), header=False)
+    assert open(out3).read() == exp3
+    # whole-file query (-g) from a multi-record FASTA, custom ID
+    fa = str(tmp_path / "g.fa")
+    recs = [O.synth_genome(GSEED, 7, 30000)[:9000], O.synth_genome(GSEED, 7, 30000)[9000:15000], O.synth_genome(GSEED, 8, 30000)[:5000]]
+    with open(fa, "wb") as f:
+        for i, s in enumerate(recs):
+            f.write(b">rec%d desc\n" % i)
+            for j in range(0, len(s), 70):
+                f.write(s[j:j + 70] + b"\n")
+    out4 = str(tmp_path / "o4.tsv")
+    _run_cli(["-d", dbdir, "-g", "--query-id", "myquery", fa, "-o", out4, "-t", "0.1"])
+    whole = recs[0] + recs[1] + b"N" * 20 + recs[2] + b"N" * 20          # S:905-913
+    o4 = O.default_opts(); o4.min_query_cov = 0.1
+    exp4 = O.format_tsv(odb, [b"myquery"], odb.search([whole], opts=o4))
+    assert open(out4).read() == exp4
