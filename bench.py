@@ -218,7 +218,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from kmcp_b200 import api
+    from kmcp_b200 import api, multigpu
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -316,20 +316,9 @@ def main():
                 o = ctx.search_batch_ptr(stage.data_ptr(), d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes)
                 hits = o.hits.copy()
                 hits["target"] += np.uint32(rank * BLOCK_SIZE)                         # global target numbering across shards
-                cnt = torch.tensor([len(hits)], dtype=torch.int64)
-                counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)] if rank == 0 else None
-                dist.gather(cnt, counts, dst=0, group=gloo)
+                merged = multigpu.gather_hits(hits, rank, world, group=gloo)            # host concat on rank 0
                 if rank == 0:
-                    bufs = [torch.empty(int(c.item()) * 12, dtype=torch.uint8) for c in counts]
-                    dist.gather(torch.from_numpy(hits.view(np.uint8)), None, dst=0, group=gloo) if False else None
-                    # variable-size concat on the host of rank 0
-                    recv = [torch.from_numpy(hits.view(np.uint8).copy())]
-                    for src in range(1, world):
-                        dist.recv(bufs[src], src=src, group=gloo)
-                        recv.append(bufs[src])
-                    e2e_matches += sum(len(b) // 12 for b in recv)
-                else:
-                    dist.send(torch.from_numpy(hits.view(np.uint8).copy()), dst=0, group=gloo)
+                    e2e_matches += len(merged)
             barrier()
             e2e_s = time.perf_counter() - t0
             t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

@@ -75,6 +75,9 @@ typedef struct {
     int32_t resident;        /* 1 if the target's block is in this context */
 } kmcpg_target_t;
 
+/* the block → shard assignment kmcpg_open_db uses (host only, no device needed): blocks sorted by re-pitched
+ * bytes, largest first onto the least loaded shard; owner[i] = shard of block i in __db.yml order */
+int kmcpg_shard_plan(const char *dir, int shard_world, int32_t *owner, int32_t n_owner);
 /* dir = the directory holding __db.yml (normally <db>/R001, S:299-324) */
 int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts);
 int kmcpg_db_info(const kmcpg_ctx *ctx, kmcpg_db_info_t *out);

@@ -97,7 +97,7 @@ class SynthDb(C.Structure):
 
 # every symbol include/kmcp_gpu.h declares (checked by tests/test_abi.py without a GPU)
 ABI_SYMBOLS = [
-    "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
+    "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
     "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_free_hits", "kmcpg_host_alloc",
     "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
     "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search",
@@ -124,6 +124,7 @@ def load() -> C.CDLL:
     L.kmcpg_last_error.restype = C.c_char_p
     L.kmcpg_last_error.argtypes = [vp]
     L.kmcpg_open_db.argtypes = [vp, C.c_char_p, C.POINTER(DbOpts)]
+    L.kmcpg_shard_plan.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.c_int32]
     L.kmcpg_db_info.argtypes = [vp, C.POINTER(DbInfo)]
     L.kmcpg_target.argtypes = [vp, C.c_int64, C.POINTER(TargetInfo)]
     L.kmcpg_default_params.argtypes = [C.POINTER(SearchParams)]
@@ -371,6 +372,16 @@ class Context:
     def synth_reads(self, seed: int, first: int, n_reads: int, read_len: int, genome_seed: int, n_genomes: int,
                     genome_len: int, dptr: int):
         self._check(self._L.kmcpg_synth_reads(self._h, seed, first, n_reads, read_len, genome_seed, n_genomes, genome_len, dptr))
+
+
+def shard_plan(r001_dir: str, world: int):
+    """owner shard of every block of the DB (host only; the plan kmcpg_open_db follows)"""
+    L = load()
+    buf = (C.c_int32 * 65536)()
+    n = L.kmcpg_shard_plan(r001_dir.encode(), world, buf, 65536)
+    if n < 0:
+        raise KmcpGpuError(n, L.kmcpg_last_error(None).decode())
+    return [int(buf[i]) for i in range(n)]
 
 
 def host_alloc(nbytes: int) -> int:

@@ -107,6 +107,21 @@ void pin_release(kmcpg_ctx *ctx, PinBuf &b) {
     }
 }
 
+// blocks → shards: largest first onto the least loaded shard (deterministic in every rank)
+static void plan_shards(const DbMeta &m, int world, std::vector<int> &owner, std::vector<uint64_t> &load) {
+    std::vector<int> order(m.blocks.size());
+    std::iota(order.begin(), order.end(), 0);
+    auto bytes_of = [&](int i) { return (uint64_t)m.blocks[i].num_sigs * pitch_for((uint32_t)m.blocks[i].row_bytes); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bytes_of(a) > bytes_of(b); });
+    load.assign(world, 0);
+    owner.assign(m.blocks.size(), 0);
+    for (int i : order) {
+        int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        owner[i] = best;
+        load[best] += bytes_of(i);
+    }
+}
+
 static int planes_for(uint64_t max_n) {
     if (max_n <= 255) return 8;
     if (max_n <= 65535) return 16;
@@ -523,18 +538,9 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
     int world = opts && opts->shard_world > 1 ? opts->shard_world : 1;
     int rank = opts && world > 1 ? opts->shard_rank : 0;
     if (rank < 0 || rank >= world) return fail(ctx, KMCPG_EINVAL, "shard_rank out of range");
-    // blocks → shards: largest first onto the least loaded shard (deterministic in every rank)
-    std::vector<int> order(m.blocks.size());
-    std::iota(order.begin(), order.end(), 0);
-    auto bytes_of = [&](int i) { return (uint64_t)m.blocks[i].num_sigs * pitch_for((uint32_t)m.blocks[i].row_bytes); };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bytes_of(a) > bytes_of(b); });
-    std::vector<uint64_t> load(world, 0);
-    std::vector<int> owner(m.blocks.size(), 0);
-    for (int i : order) {
-        int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        owner[i] = best;
-        load[best] += bytes_of(i);
-    }
+    std::vector<int> owner;
+    std::vector<uint64_t> load;
+    plan_shards(m, world, owner, load);
     if (opts && opts->max_resident_bytes > 0 && (int64_t)load[rank] > opts->max_resident_bytes)
         return fail(ctx, KMCPG_ENOMEM, "resident blocks exceed max_resident_bytes");
     ctx->resident_of.assign(m.blocks.size(), -1);
@@ -576,6 +582,20 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
         for (int c = 0; c < bm.n_names; c++) ctx->target_sizes[(size_t)bm.target_base + c] = (double)bm.sizes[c];
     ctx->has_db = true;
     return KMCPG_OK;
+}
+
+int kmcpg_shard_plan(const char *dir, int shard_world, int32_t *owner_out, int32_t n_owner) {
+    if (!dir || !owner_out || shard_world < 1) return KMCPG_EINVAL;
+    DbMeta m;
+    std::string err;
+    int rc = read_db_meta(dir, m, err);
+    if (rc) return fail(nullptr, rc, err);
+    if ((size_t)n_owner < m.blocks.size()) return fail(nullptr, KMCPG_EINVAL, "owner array too small");
+    std::vector<int> owner;
+    std::vector<uint64_t> load;
+    plan_shards(m, shard_world, owner, load);
+    for (size_t i = 0; i < owner.size(); i++) owner_out[i] = owner[i];
+    return (int)owner.size();
 }
 
 int kmcpg_db_info(const kmcpg_ctx *ctx, kmcpg_db_info_t *o) {
