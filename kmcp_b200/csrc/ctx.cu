@@ -65,7 +65,7 @@ void free_db(kmcpg_ctx *ctx) {
 
 void WorkSet::release() {
     for (DevBuf *b : {&seq, &off, &slot_cnt, &slot_off, &codes, &codes2, &locs, &ncodes, &qlen, &nk, &neff, &thresh, &hkeys, &hvals, &hkeys2, &hvals2,
-                      &hits, &counters, &tmp, &segb, &sege})
+                      &hits, &counters, &tmp, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off})
         b->release();
     h_off.release(); h_cnt.release();
     for (cudaEvent_t *e : {&ev_in, &ev_a0, &ev_hash, &ev_a, &ev_cnt, &ev_sorted, &ev_b}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
@@ -174,7 +174,39 @@ int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int
     }
     ha.minimizer = m.minimizer; ha.minimizer_w = m.minimizer_w; ha.syncmer = m.syncmer; ha.syncmer_s = m.syncmer_s;
     ha.min_query_len = p.min_query_len;
-    CU(launch_hash(ha, st)); ctx->launches++;
+    if (!m.minimizer && !m.syncmer) {
+        CU(launch_hash(ha, st)); ctx->launches++;
+    } else {
+        // sketch databases: hash every position (k-mers, and s-mers for syncmers), then select per window
+        CU(w.ck.ensure(std::max<uint64_t>(sb.total_slots, 1) * 8));
+        HashArgs hr = ha;
+        hr.raw = 1; hr.n_queries = sb.n_seqs; hr.codes = w.ck.as<uint64_t>();
+        CU(launch_hash(hr, st)); ctx->launches++;
+        SelectArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.seq_off = sb.d_off; sa.ck = w.ck.as<uint64_t>(); sa.slot_off = w.slot_off.as<uint64_t>();
+        if (m.syncmer) {
+            const int s = (int)m.syncmer_s;
+            if (s < 1 || s >= k) return fail(ctx, KMCPG_EFORMAT, "syncmer-s must be in 1..k-1");
+            CU(w.cs_cnt.ensure((sb.n_seqs + 1) * 8ull)); CU(w.cs_off.ensure((sb.n_seqs + 1) * 8ull));
+            CU(launch_slot_bounds(sb.d_off, sb.n_seqs, s, w.cs_cnt.as<uint64_t>(), st));
+            size_t t1 = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, t1, w.cs_cnt.as<uint64_t>(), w.cs_off.as<uint64_t>(), (int)(sb.n_seqs + 1), st);
+            CU(w.tmp.ensure(t1));
+            CU(cub::DeviceScan::ExclusiveSum(w.tmp.p, t1, w.cs_cnt.as<uint64_t>(), w.cs_off.as<uint64_t>(), (int)(sb.n_seqs + 1), st));
+            // every sequence has at most k-s more s-mers than k-mers (plus the ones shorter than k)
+            CU(w.cs.ensure((sb.total_slots + (uint64_t)sb.n_seqs * (uint64_t)(k - s + 1) + 1) * 8));
+            HashArgs hs = hr;
+            hs.k = s; hs.slot_off = w.cs_off.as<uint64_t>(); hs.codes = w.cs.as<uint64_t>();
+            CU(launch_hash(hs, st));
+            ctx->launches += 4;
+            sa.cs = w.cs.as<uint64_t>(); sa.cs_off = w.cs_off.as<uint64_t>(); sa.syncmer_s = s;
+        }
+        sa.codes = w.codes.as<uint64_t>(); sa.n_codes = w.ncodes.as<uint32_t>(); sa.query_len = w.qlen.as<int32_t>();
+        sa.n_queries = nq; sa.paired = p.paired; sa.mate_select = p.mate_select; sa.k = k; sa.minimizer_w = m.minimizer_w;
+        sa.scaled = m.scaled; sa.max_hash = ha.max_hash; sa.min_query_len = p.min_query_len;
+        CU(launch_select(sa, st)); ctx->launches++;
+    }
 
     uint64_t *codes = w.codes.as<uint64_t>();
     int do_unique = 0;
@@ -373,7 +405,6 @@ static int check_search_args(kmcpg_ctx *ctx, const kmcpg_search_params *p, const
     *k = p->k > 0 ? p->k : ctx->meta.ks.front();
     if (std::find(ctx->meta.ks.begin(), ctx->meta.ks.end(), *k) == ctx->meta.ks.end()) return fail(ctx, KMCPG_EINVAL, "k is not one of the database's k values");
     if (*k > 64 || *k < 1) return fail(ctx, KMCPG_EUNSUPPORTED, "k must be in 1..64");
-    if (ctx->meta.minimizer || ctx->meta.syncmer) return fail(ctx, KMCPG_EUNSUPPORTED, "minimizer/syncmer sketches are not on the device path yet");
     if (p->min_matched < 1) return fail(ctx, KMCPG_EINVAL, "min_matched must be >= 1");
     if (!(p->min_query_cov >= 0 && p->min_query_cov <= 1)) return fail(ctx, KMCPG_EINVAL, "min_query_cov must be in [0,1]");
     return KMCPG_OK;
@@ -714,7 +745,7 @@ int kmcpg_generate_kmers(kmcpg_ctx *ctx, const kmcpg_sketch_params *sp, const ui
                          uint64_t **out_codes, uint64_t **out_off) {
     if (!ctx || !sp || !out_codes || !out_off || (n_seqs && (!seq || !off))) return KMCPG_EINVAL;
     if (sp->k < 1 || sp->k > 64) return fail(ctx, KMCPG_EUNSUPPORTED, "k must be in 1..64");
-    if (sp->minimizer || sp->syncmer) return fail(ctx, KMCPG_EUNSUPPORTED, "minimizer/syncmer sketches are not on the device path yet");
+    if (sp->syncmer && (sp->syncmer_s < 1 || (int)sp->syncmer_s >= sp->k)) return fail(ctx, KMCPG_EINVAL, "syncmer_s must be in 1..k-1");
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     // borrow the pipeline's hash stage with a throw-away DbMeta view

@@ -93,14 +93,14 @@ __global__ void __launch_bounds__(HASH_WARPS * 32) hash_kernel(HashArgs a) {
     const int k = a.k;
 
     for (uint32_t q = warp; q < a.n_queries; q += n_warps) {
-        const uint32_t s0 = a.paired ? 2 * q : q;
-        const int n_mates = a.paired ? 2 : 1;
+        const uint32_t s0 = (a.paired && !a.raw) ? 2 * q : q;
+        const int n_mates = (a.paired && !a.raw) ? 2 : 1;
         const uint64_t len0 = a.seq_off[s0 + 1] - a.seq_off[s0];
-        const uint64_t len1 = a.paired ? a.seq_off[s0 + 2] - a.seq_off[s0 + 1] : 0;
+        const uint64_t len1 = (a.paired && !a.raw) ? a.seq_off[s0 + 2] - a.seq_off[s0 + 1] : 0;
         uint64_t *out = a.codes + a.slot_off[s0];
         uint32_t written = 0;
         // U:778-786: skip when Seq is shorter than min-query-len unless Seq2 is long enough
-        bool skip = (int64_t)len0 < a.min_query_len && !(a.paired && (int64_t)len1 >= a.min_query_len);
+        bool skip = !a.raw && (int64_t)len0 < a.min_query_len && !(a.paired && (int64_t)len1 >= a.min_query_len);
         int32_t qlen = (int32_t)(len0 + len1);
         if (a.mate_select == 1) qlen = (int32_t)len0;
         if (a.mate_select == 2) qlen = (int32_t)len1;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(HASH_WARPS * 32) hash_kernel(HashArgs a) {
                         for (int r = 0; r < HASH_RUN; r++) {
                             if (r < cnt) {
                                 uint64_t code = a.canonical ? (fh < rh ? fh : rh) : fh;
-                                bool ok = code != 0 && !(a.scaled && code > a.max_hash);       // U:1097-1102
+                                bool ok = a.raw || (code != 0 && !(a.scaled && code > a.max_hash));       // U:1097-1102
                                 c[r] = code;
                                 if (ok) valid |= 1u << r;
                                 if (r + 1 < cnt) {
@@ -141,6 +141,12 @@ __global__ void __launch_bounds__(HASH_WARPS * 32) hash_kernel(HashArgs a) {
                                 }
                             }
                         }
+                    }
+                    if (a.raw) {                                    // position-indexed output for the sketch selection
+#pragma unroll
+                        for (int r = 0; r < HASH_RUN; r++)
+                            if (valid & (1u << r)) out[p0 + r] = c[r];
+                        continue;
                     }
                     // in-order compaction inside the query's code region
                     int mine = __popc(valid);
@@ -159,11 +165,97 @@ __global__ void __launch_bounds__(HASH_WARPS * 32) hash_kernel(HashArgs a) {
                 }
             }
         }
-        if (lane == 0) {
+        if (lane == 0 && !a.raw) {
             a.n_codes[q] = skip ? 0xFFFFFFFFu : written;    // 0xFFFFFFFF marks "skipped by length" (NumKmers = 0)
             a.query_len[q] = qlen;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// minimizer / closed syncmer selection: one warp per query, 32 windows per round, every lane scans its window
+// for the LEFTMOST minimum (bio/sketches keeps a sorted buffer whose ties stay in arrival order)
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) select_kernel(SelectArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int k = a.k, s = a.syncmer_s;
+    for (uint32_t q = warp; q < a.n_queries; q += n_warps) {
+        const uint32_t s0 = a.paired ? 2 * q : q;
+        const int n_mates = a.paired ? 2 : 1;
+        const uint64_t len0 = a.seq_off[s0 + 1] - a.seq_off[s0];
+        const uint64_t len1 = a.paired ? a.seq_off[s0 + 2] - a.seq_off[s0 + 1] : 0;
+        uint64_t *out = a.codes + a.slot_off[s0];
+        uint32_t written = 0;
+        bool skip = (int64_t)len0 < a.min_query_len && !(a.paired && (int64_t)len1 >= a.min_query_len);   // U:778-786
+        int32_t qlen = (int32_t)(len0 + len1);
+        if (a.mate_select == 1) qlen = (int32_t)len0;
+        if (a.mate_select == 2) qlen = (int32_t)len1;
+        if (!skip) {
+            for (int m = 0; m < n_mates; m++) {
+                if (a.mate_select == 1 && m == 1) continue;
+                if (a.mate_select == 2 && m == 0) continue;
+                const uint64_t len = m == 0 ? len0 : len1;
+                if (len < (uint64_t)k) continue;
+                const uint64_t *ck = a.ck + a.slot_off[s0 + m];
+                uint64_t n_win, W;
+                int64_t kms = 0;
+                const uint64_t *src;
+                if (s > 0) {                       // windows of L = 2k-s-1 bases holding W = 2(k-s) s-mers (A.4)
+                    const uint64_t L = 2ull * k - s - 1;
+                    if (len < L) continue;
+                    n_win = len - L + 1; W = 2ull * (k - s); kms = k - s;
+                    src = a.cs + a.cs_off[s0 + m];
+                } else {                           // windows of w consecutive k-mers (A.5)
+                    const uint64_t nk = len - k + 1;
+                    W = a.minimizer_w < 1 ? 1 : a.minimizer_w;
+                    if (nk < W) continue;
+                    n_win = nk - W + 1;
+                    src = ck;
+                }
+                uint64_t prev_last = ~0ull;        // selected position of the window before this round
+                for (uint64_t base = 0; base < n_win; base += 32) {
+                    const uint64_t idx = base + lane;
+                    uint64_t pos = ~0ull;
+                    if (idx < n_win) {
+                        uint64_t best = src[idx], bi = 0;
+                        for (uint64_t t = 1; t < W; t++) {
+                            uint64_t v = src[idx + t];
+                            if (v < best) { best = v; bi = t; }     // strict <: leftmost minimum
+                        }
+                        pos = s > 0 ? ((int64_t)bi < kms ? idx + bi : idx + bi - (uint64_t)kms) : idx + bi;
+                    }
+                    uint64_t before = __shfl_up_sync(0xffffffffu, pos, 1);
+                    if (lane == 0) before = prev_last;
+                    bool emit = idx < n_win && pos != before;         // runs of equal positions are contiguous
+                    uint64_t code = 0;
+                    if (emit) {
+                        code = ck[pos];
+                        if (code == 0 || (a.scaled && code > a.max_hash)) emit = false;     // U:1071-1076 / 1084-1089
+                    }
+                    const int last_active = (int)((n_win - base) < 32 ? (n_win - base - 1) : 31);
+                    prev_last = __shfl_sync(0xffffffffu, pos, last_active);
+                    __syncwarp();
+                    uint32_t mask = __ballot_sync(0xffffffffu, emit);
+                    if (emit) out[written + __popc(mask & ((1u << lane) - 1))] = code;
+                    written += __popc(mask);
+                }
+            }
+        }
+        if (lane == 0) {
+            a.n_codes[q] = skip ? 0xFFFFFFFFu : written;
+            a.query_len[q] = qlen;
+        }
+    }
+}
+
+cudaError_t launch_select(const SelectArgs &a, cudaStream_t st) {
+    if (a.n_queries == 0) return cudaSuccess;
+    uint32_t blocks = (a.n_queries + 7) / 8;
+    if (blocks > 148u * 32u) blocks = 148u * 32u;
+    select_kernel<<<blocks, 256, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_hash(const HashArgs &a, cudaStream_t st) {

@@ -26,7 +26,29 @@ struct HashArgs {
     int minimizer; uint32_t minimizer_w;
     int syncmer; uint32_t syncmer_s;
     int min_query_len;
+    int raw;                    // 1: every sequence on its own, hash of position p written to codes[slot_off[s]+p],
+                                //    no filter, no compaction, n_codes/query_len untouched (input of the sketch selection)
 };
+// minimizer / closed-syncmer selection (bio/sketches NextMinimizer / NextSyncmer)
+struct SelectArgs {
+    const uint64_t *seq_off;    // n_seqs+1 (lengths)
+    const uint64_t *ck;         // canonical k-mer hash of every position, region slot_off[s]
+    const uint64_t *slot_off;   // n_seqs+1
+    const uint64_t *cs;         // syncmer: canonical s-mer hash of every position, region cs_off[s]
+    const uint64_t *cs_off;     // n_seqs+1
+    uint64_t *codes;            // out: selected codes, compacted at slot_off[first sequence of the query]
+    uint32_t *n_codes;          // per query
+    int32_t *query_len;         // per query
+    uint32_t n_queries;
+    int paired, mate_select;
+    int k;
+    int syncmer_s;              // > 0: closed syncmer with this s; 0: minimizer
+    uint32_t minimizer_w;
+    int scaled;
+    uint64_t max_hash;
+    int min_query_len;
+};
+cudaError_t launch_select(const SelectArgs &a, cudaStream_t st);
 cudaError_t launch_slot_bounds(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *slot_cnt, cudaStream_t st);
 cudaError_t launch_hash(const HashArgs &a, cudaStream_t st);
 

@@ -364,3 +364,73 @@ def test_cli_tsv_is_byte_identical_to_the_oracle_formatter(oracle, small_db, tmp
     o4 = O.default_opts(); o4.min_query_cov = 0.1
     exp4 = O.format_tsv(odb, [b"myquery"], odb.search([whole], opts=o4))
     assert open(out4).read() == exp4
+
+
+# ---------------------------------------------------------------------------------------------------- sketches
+@pytest.mark.parametrize("k,kw", [(31, dict(syncmer_s=15)), (31, dict(syncmer_s=15, scaled=True, scale=4)), (21, dict(syncmer_s=11)),
+                                  (21, dict(syncmer_s=20)), (21, dict(syncmer_s=1)), (21, dict(minimizer_w=5)),
+                                  (31, dict(minimizer_w=20, scaled=True, scale=3)), (21, dict(minimizer_w=1)), (15, dict(minimizer_w=100))])
+def test_sketch_selection_matches_oracle(gpu_ctx, oracle, k, kw):
+    """closed syncmer (windowed) and minimizer (A.5) selection kernels vs the oracle"""
+    from kmcp_b200 import api
+    O = oracle
+    osp = O.sketch_params(k, **kw)
+    reads = helpers.edge_reads(k) + helpers.make_reads(O, RSEED, 100, 40, 30000, GSEED) + [O.synth_genome(3, 1, 40000), b"ACGT" * 300, b"A" * 500]
+    reads.append(O.synth_genome(3, 2, 3000)[:1500] + b"N" * 100 + O.synth_genome(3, 2, 3000)[1500:])
+    buf, off = api.pack_seqs(reads)
+    sp = api.SketchParams(k, 1, osp.scaled, osp.scale, osp.minimizer, osp.minimizer_w, osp.syncmer, osp.syncmer_s)
+    codes, coff = gpu_ctx.generate_kmers(buf, off, sp)
+    for i, r in enumerate(reads):
+        exp = O.generate_kmers(r, osp)
+        got = codes[int(coff[i]):int(coff[i + 1])]
+        assert np.array_equal(got, exp), (k, kw, i, len(r), len(got), len(exp))
+
+
+def test_golden_vectors_from_reference_data(gpu_ctx, oracle):
+    """tests/golden/*.json were generated from the reference's demo files by the oracle after it reproduced G1-G5"""
+    import json
+    from kmcp_b200 import api
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = json.load(open(os.path.join(gold, "reads_k21.json")))
+    reads = [r["seq"].encode() for r in d["reads"]]
+    buf, off = api.pack_seqs(reads)
+    codes, coff = gpu_ctx.generate_kmers(buf, off, api.SketchParams(21, 1, 0, 1, 0, 0, 0, 0))
+    for i, r in enumerate(d["reads"]):
+        assert [int(c) for c in codes[int(coff[i]):int(coff[i + 1])]] == r["codes"]
+    sk = json.load(open(os.path.join(gold, "sketch_k31.json")))
+    buf, off = api.pack_seqs([sk["seq"].encode()])
+    for name, sp in (("scaled1000", api.SketchParams(31, 1, 1, 1000, 0, 0, 0, 0)), ("scaled50", api.SketchParams(31, 1, 1, 50, 0, 0, 0, 0)),
+                     ("syncmer15_scaled62", api.SketchParams(31, 1, 1, 62, 0, 0, 1, 15)), ("syncmer15", api.SketchParams(31, 1, 0, 1, 0, 0, 1, 15)),
+                     ("minimizer10", api.SketchParams(31, 1, 0, 1, 1, 10, 0, 0))):
+        codes, _ = gpu_ctx.generate_kmers(buf, off, sp)
+        assert [int(c) for c in codes] == sk["lists"][name], name
+    L = api.load()
+    for c in json.load(open(os.path.join(gold, "fpr.json"))):
+        assert float(L.kmcpg_query_fpr(c["n"], c["c"], c["p"])).hex() == c["fpr_hex"]
+
+
+@pytest.mark.parametrize("kw,h,fpr", [(dict(syncmer_s=15, scaled=True, scale=8), 3, 0.01), (dict(minimizer_w=8), 1, 0.3),
+                                      (dict(scaled=True, scale=20), 3, 0.01)])
+def test_sketch_database_search_end_to_end(gpu_ctx, oracle, tmp_path, kw, h, fpr):
+    """genome-vs-genome search on sketch DBs (the demo-searching shape: -g queries, sort by jacc, -t 0.1)"""
+    O = oracle
+    k = 31
+    sp = O.sketch_params(k, **kw)
+    # related genomes: mutated copies of a common ancestor so containment varies
+    base = O.synth_genome(21, 0, 60000)
+    rng = np.random.default_rng(5)
+    genomes = []
+    for g in range(12):
+        b = bytearray(base)
+        for pos in rng.integers(0, len(b), int(len(b) * 0.004 * g)):
+            b[pos] = b"ACGT"[int(rng.integers(0, 4))]
+        genomes.append(bytes(b))
+    targets = []
+    for g, s in enumerate(genomes):
+        targets += O.compute_targets([(b"g", b"g", s)], "genome_%02d" % g, sp)
+    r001 = O.build_db(targets, str(tmp_path / "db"), sp, num_hashes=h, fpr=fpr, block_size=8)
+    odb = O.DB(r001)
+    gpu_ctx.open_db(r001)
+    queries = [genomes[0], genomes[5], genomes[11], O.synth_genome(22, 3, 50000), genomes[3][:200]]
+    got = _compare_engine(O, odb, gpu_ctx, queries, min_query_cov=0.1, sort_by=2)
+    assert len(got.matches) >= 12 and got.n_kmers.max() > 256
