@@ -361,8 +361,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "probe_kernel<1,8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "launches": probe_launches, "avg_launch_ms": probe_ms / max(1, probe_launches),
                          "algorithmic_bytes_per_launch": probe_bytes / max(1, probe_launches),
-                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                         "traffic_note": traffic.get("note") if traffic else "no ncu --set full capture committed yet"},
+                         "traffic": (traffic["dram_over_algorithmic"] * probe_bytes / max(1, probe_launches)) if traffic else None,
+                         "traffic_note": ("average launch of this run x the DRAM/algorithmic ratio of the committed ncu --set full capture: " + traffic["source"])
+                         if traffic else "no ncu --set full capture committed yet"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": step_bytes + off_np.nbytes, "d2h_bytes_per_step": d2h_bytes,
                     "matches_per_step": int(e2e_matches / args.steps), "ms_per_step": e2e_s / args.steps * 1e3, "breakdown_ms_per_step": e2e_break,

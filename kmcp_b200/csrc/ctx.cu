@@ -283,12 +283,13 @@ static int enqueue_part(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p
         CU(w.h_off.ensure((sb_in.n_seqs + 1) * 8ull));
         CU(w.off.ensure((sb_in.n_seqs + 1) * 8ull));
         CU(w.seq.ensure(std::max<uint64_t>(host_bytes, 1) + 64));
+        if (w.busy) CU(cudaStreamWaitEvent(ctx->in_st, w.ev_b, 0));     // the previous part of this work set is completely done
         uint64_t *ho = w.h_off.as<uint64_t>();
         const uint64_t base = host_off[0];
         for (uint32_t i = 0; i <= sb_in.n_seqs; i++) ho[i] = host_off[i] - base;
-        CU(cudaMemcpyAsync(w.off.p, ho, (sb_in.n_seqs + 1) * 8ull, cudaMemcpyHostToDevice, ctx->copy_st));
-        if (host_bytes) CU(cudaMemcpyAsync(w.seq.p, host_seq + base, host_bytes, cudaMemcpyHostToDevice, ctx->copy_st));
-        CU(cudaEventRecord(w.ev_in, ctx->copy_st));
+        CU(cudaMemcpyAsync(w.off.p, ho, (sb_in.n_seqs + 1) * 8ull, cudaMemcpyHostToDevice, ctx->in_st));
+        if (host_bytes) CU(cudaMemcpyAsync(w.seq.p, host_seq + base, host_bytes, cudaMemcpyHostToDevice, ctx->in_st));
+        CU(cudaEventRecord(w.ev_in, ctx->in_st));
         CU(cudaStreamWaitEvent(st, w.ev_in, 0));
         w.sb.d_seq = w.seq.as<uint8_t>();
         w.sb.d_off = w.off.as<uint64_t>();
@@ -427,7 +428,8 @@ static int cut_parts(kmcpg_ctx *ctx, const uint64_t *off, uint32_t n_seqs, uint3
                 uint64_t len = off[b + m + 1] - off[b + m];
                 qs += len >= (uint64_t)k ? len - k + 1 : 0;
             }
-            if (b > a && slots + qs > PART_SLOTS) break;
+            // a short first part fills the pipeline quickly (its input copy and hash are not hidden behind a probe)
+            if (b > a && slots + qs > (a == 0 ? PART_SLOTS / 4 : PART_SLOTS)) break;
             slots += qs; maxq = std::max(maxq, qs);
             b += step;
         }
@@ -445,8 +447,9 @@ static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const 
     for (size_t i = 0; i <= parts.size(); i++) {
         if (i < parts.size()) {
             WorkSet &w = ctx->ws[i & 1];
-            rc = wait_part(ctx, w);                       // results of part i-2 have left this work set
-            if (rc) return rc;
+            // part i-2 used this work set: its result copies (copy stream) must finish before these buffers are
+            // rewritten — a stream dependency, not a host wait, so the host keeps enqueueing ahead of the GPU
+            if (w.busy) CU(cudaStreamWaitEvent(ctx->st, w.ev_b, 0));
             const Part &pt = parts[i];
             SubBatch sb{d_seq, d_off ? d_off + pt.a : nullptr, pt.b - pt.a, pt.slots, pt.maxq, pt.a / step};
             if (host_seq) rc = enqueue_part(ctx, w, p, k, sb, host_seq, host_off + pt.a, host_off[pt.b] - host_off[pt.a]);
@@ -465,6 +468,7 @@ static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const 
 static void abort_parts(kmcpg_ctx *ctx) {
     cudaStreamSynchronize(ctx->st);
     cudaStreamSynchronize(ctx->copy_st);
+    cudaStreamSynchronize(ctx->in_st);
     for (auto &w : ctx->ws) w.busy = false;
 }
 
@@ -524,6 +528,7 @@ int kmcpg_create(int device, kmcpg_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->in_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     ctx->st = ctx->own_st;
     if ((e = ctx->h_small.ensure(256)) != cudaSuccess) return bail(e, "cudaMallocHost");
     *out = ctx;
@@ -552,6 +557,7 @@ int kmcpg_close(kmcpg_ctx *ctx) {
     ctx->pin_pool.clear();
     if (ctx->own_st) cudaStreamDestroy(ctx->own_st);
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
+    if (ctx->in_st) cudaStreamDestroy(ctx->in_st);
     delete ctx;
     return KMCPG_OK;
 }

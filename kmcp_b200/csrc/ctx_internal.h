@@ -102,7 +102,8 @@ struct kmcpg_ctx {
     int sm_count = 148;
     cudaStream_t st = nullptr;        // compute stream (own_st or the caller's)
     cudaStream_t own_st = nullptr;
-    cudaStream_t copy_st = nullptr;   // transfers that overlap the kernels
+    cudaStream_t copy_st = nullptr;   // device→host transfers that overlap the kernels
+    cudaStream_t in_st = nullptr;     // host→device input staging (its own queue, so it never waits behind result copies)
     bool has_db = false;
     kmcpg::DbMeta meta;
     std::vector<kmcpg::DeviceBlock> blocks;

@@ -121,11 +121,14 @@ __global__ void __launch_bounds__(HASH_WARPS * 32) hash_kernel(HashArgs a) {
                     uint64_t c[HASH_RUN];
                     uint32_t valid = 0;
                     if (cnt > 0) {
-                        // Horner initialisation: fwd = XOR_j rol(F[s_j], k-1-j), rev = XOR_j rol(R[s_j&7], j)
+                        // one pass over the k bases: fwd = XOR_j rol(F[s_j], k-1-j) by Horner (rotate left),
+                        // rev = XOR_j rol(R[s_j&7], j) by rotating the accumulator right and adding rol(R, k-1)
                         uint64_t fh = 0, rh = 0;
+#pragma unroll 4
                         for (int j = 0; j < k; j++) {
-                            fh = rol1(fh) ^ T.F[s[p0 + j]];
-                            rh = rol1(rh) ^ T.R[s[p0 + k - 1 - j] & 7];
+                            const uint8_t b = s[p0 + j];
+                            fh = rol1(fh) ^ T.F[b];
+                            rh = ror1(rh) ^ T.Rk1[b & 7];
                         }
 #pragma unroll
                         for (int r = 0; r < HASH_RUN; r++) {
