@@ -416,26 +416,42 @@ struct Part { uint32_t a, b; uint64_t slots, maxq; };
 static const uint64_t PART_SLOTS = 32ull << 20;   // k-mer slots per part (≈ 250 k reads of 150 bp)
 static const uint32_t PART_SEQS = 2u << 20;
 
-// greedy parts [a, b) from host-visible offsets
+// greedy parts [a, b) from host-visible offsets.  Sequences are taken in blocks of 4096 whose slot sum / max are
+// computed by a branch-free (vectorisable) loop; only blocks that are large by themselves are walked one by one.
 static int cut_parts(kmcpg_ctx *ctx, const uint64_t *off, uint32_t n_seqs, uint32_t step, int k, std::vector<Part> &parts) {
-    for (uint32_t a = 0; a < n_seqs;) {
-        uint64_t slots = 0, maxq = 0;
-        uint32_t b = a;
-        while (b < n_seqs && (b - a) < PART_SEQS) {
-            uint64_t qs = 0;
-            for (uint32_t m = 0; m < step; m++) {
-                if (off[b + m + 1] < off[b + m]) return fail(ctx, KMCPG_EINVAL, "offsets must be non-decreasing");
-                uint64_t len = off[b + m + 1] - off[b + m];
-                qs += len >= (uint64_t)k ? len - k + 1 : 0;
-            }
-            // a short first part fills the pipeline quickly (its input copy and hash are not hidden behind a probe)
-            if (b > a && slots + qs > (a == 0 ? PART_SLOTS / 4 : PART_SLOTS)) break;
-            slots += qs; maxq = std::max(maxq, qs);
-            b += step;
+    const uint64_t kk = (uint64_t)k;
+    const uint32_t BLK = 4096;
+    uint32_t a = 0, b = 0;
+    uint64_t slots = 0, maxq = 0;
+    auto limit = [&]() { return a == 0 ? PART_SLOTS / 4 : PART_SLOTS; };   // a short first part fills the pipeline quickly
+    auto close = [&]() { parts.push_back({a, b, slots, maxq}); a = b; slots = 0; maxq = 0; };
+    while (b < n_seqs) {
+        const uint32_t e = std::min<uint32_t>(n_seqs, b + BLK);
+        uint64_t bsum = 0, bmax = 0, bad = 0;
+        for (uint32_t i = b; i < e; i++) {
+            const uint64_t lo = off[i], hi = off[i + 1];
+            bad |= (uint64_t)(hi < lo);
+            const uint64_t len = hi - lo;
+            const uint64_t qs = len >= kk ? len - kk + 1 : 0;
+            bsum += qs;
+            bmax = bmax > qs ? bmax : qs;
         }
-        parts.push_back({a, b, slots, maxq});
-        a = b;
+        if (bad) return fail(ctx, KMCPG_EINVAL, "offsets must be non-decreasing");
+        if (step == 2) bmax *= 2;                                   // upper bound of a query's two mates
+        if (bsum <= PART_SLOTS / 16) {                              // a small block moves as one unit
+            if (b > a && (slots + bsum > limit() || (b - a) + (e - b) > PART_SEQS)) close();
+            slots += bsum; maxq = std::max(maxq, bmax); b = e;
+        } else {                                                    // long sequences: query by query
+            for (uint32_t i = b; i < e; i += step) {
+                uint64_t qs = 0;
+                for (uint32_t m = 0; m < step; m++) { const uint64_t len = off[i + m + 1] - off[i + m]; qs += len >= kk ? len - kk + 1 : 0; }
+                if (i > a && (slots + qs > limit() || (i - a) >= PART_SEQS)) { b = i; close(); }
+                slots += qs; maxq = std::max(maxq, qs);
+            }
+            b = e;
+        }
     }
+    if (b > a) close();
     return KMCPG_OK;
 }
 
