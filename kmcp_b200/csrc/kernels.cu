@@ -473,11 +473,41 @@ __device__ __forceinline__ void csa8(uint32_t (&c)[P][4], const uint4 (&r)[PROBE
     }
 }
 
+// Counters: 8 bit-sliced planes in registers count up to 255 rows.  Queries with more k-mers (long reads, -g genomes)
+// keep the full P = 8+PH planes per thread in shared memory and fold the register planes into them every 248 rows
+// (one ripple add), so every query length runs the same register-lean inner loop.
+template <int PH>
+__device__ __forceinline__ void fold_planes(uint32_t (&c)[8][4], uint32_t *T) {
+    // T[(p*4+w)*blockDim + tid] += c (bit-sliced add), c = 0
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t carry = 0;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            uint32_t *t = T + (p * 4 + w) * PROBE_THREADS;
+            const uint32_t tv = *t, x = c[p][w];
+            *t = xor3(tv, x, carry);
+            carry = maj3(tv, x, carry);
+            c[p][w] = 0;
+        }
+#pragma unroll
+        for (int p = 8; p < 8 + PH; p++) {
+            uint32_t *t = T + (p * 4 + w) * PROBE_THREADS;
+            const uint32_t tv = *t;
+            *t = tv ^ carry;
+            carry &= tv;
+        }
+    }
+}
+
 // VAR 0: load locs, load rows, add (simple).  VAR 1: row indices of the next 8 k-mers are prefetched while the
 // current rows are in flight.  VAR 2: additionally the rows are double-buffered in registers, so 8..16 rows per
 // lane are always in flight while the carry-save tree of the previous 8 runs.
-template <int H, int P, int VAR, int MINB>
+template <int H, int PH, int VAR, int MINB>
 __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a) {
+    constexpr int P = 8 + PH;
+    extern __shared__ uint32_t smem_planes[];                          // PH > 0: P*4*PROBE_THREADS words
+    uint32_t *T = smem_planes + threadIdx.x;
     const uint32_t G = a.lanes_per_task;
     const uint32_t gl = threadIdx.x & (G - 1);                          // lane inside the task group
     const uint64_t groups_per_grid = ((uint64_t)gridDim.x * blockDim.x) / G;
@@ -496,20 +526,32 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
         }
         const uint32_t col16 = chunk * G + gl;                          // this lane's 16-byte slab of the row
         const bool active = n > 0 && col16 < a.row16;
-        uint32_t c[P][4];
+        uint32_t c[8][4];
 #pragma unroll
-        for (int p = 0; p < P; p++) c[p][0] = c[p][1] = c[p][2] = c[p][3] = 0;
+        for (int p = 0; p < 8; p++) c[p][0] = c[p][1] = c[p][2] = c[p][3] = 0;
 
         if (active) {
+            if (PH > 0) {
+#pragma unroll
+                for (int i = 0; i < P * 4; i++) T[i * PROBE_THREADS] = 0;
+            }
             const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
             const uint8_t *colbase = a.rows + (uint64_t)col16 * 16;
             uint32_t L[PROBE_ROWS * H];
+            uint32_t acc = 0;                                           // rows added to the register planes since the last fold
+            auto add8 = [&](const uint4 (&r)[PROBE_ROWS]) {
+                if (PH > 0) {
+                    if (acc + PROBE_ROWS > 255) { fold_planes<PH>(c, T); acc = 0; }
+                    acc += PROBE_ROWS;
+                }
+                csa8<8>(c, r);
+            };
             if (VAR == 0) {
                 for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
                     uint4 r[PROBE_ROWS];
                     load_locs<H>(L, lp, i, n);
                     load_rows<H>(r, L, colbase, a.pitch);
-                    csa8<P>(c, r);
+                    add8(r);
                 }
             } else if (VAR == 1) {
                 load_locs<H>(L, lp, 0, n);
@@ -517,7 +559,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
                     uint4 r[PROBE_ROWS];
                     load_rows<H>(r, L, colbase, a.pitch);
                     load_locs<H>(L, lp, i + PROBE_ROWS, n);
-                    csa8<P>(c, r);
+                    add8(r);
                 }
             } else {
                 uint4 r0[PROBE_ROWS], r1[PROBE_ROWS];
@@ -527,28 +569,32 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
                 for (uint32_t i = 0; i < n; i += 2 * PROBE_ROWS) {
                     load_rows<H>(r1, L, colbase, a.pitch);
                     load_locs<H>(L, lp, i + 2 * PROBE_ROWS, n);
-                    csa8<P>(c, r0);
+                    add8(r0);
                     load_rows<H>(r0, L, colbase, a.pitch);
                     load_locs<H>(L, lp, i + 3 * PROBE_ROWS, n);
-                    if (i + PROBE_ROWS < n) csa8<P>(c, r1);
+                    if (i + PROBE_ROWS < n) add8(r1);
                 }
             }
+            if (PH > 0) fold_planes<PH>(c, T);
         }
+        // plane p, word w of this thread's final counters
+        auto plane = [&](int p, int w) -> uint32_t { return PH > 0 ? T[(p * 4 + w) * PROBE_THREADS] : c[p < 8 ? p : 0][w]; };
 
         // ---- thresholds on the bit-sliced counters: ge = (count >= T) per target bit ----
         uint32_t ge[4] = {0, 0, 0, 0};
         int nhit = 0;
         if (active) {
-            const uint32_t T = a.thresh[q];
-            uint32_t high = (P < 32) ? (T >> P) : 0;                     // T does not fit in P bits → nothing passes
+            const uint32_t Tq = a.thresh[q];
+            uint32_t high = (P < 32) ? (Tq >> P) : 0;                    // threshold does not fit in P bits → nothing passes
             if (!high) {
 #pragma unroll
                 for (int w = 0; w < 4; w++) {
                     uint32_t gt = 0, eq = 0xFFFFFFFFu;
 #pragma unroll
                     for (int p = P - 1; p >= 0; p--) {
-                        if ((T >> p) & 1) { eq &= c[p][w]; }
-                        else { gt |= eq & c[p][w]; eq &= ~c[p][w]; }
+                        const uint32_t v = plane(p, w);
+                        if ((Tq >> p) & 1) { eq &= v; }
+                        else { gt |= eq & v; eq &= ~v; }
                     }
                     ge[w] = gt | eq;
                     nhit += __popc(ge[w]);
@@ -562,8 +608,8 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
                         if (t < a.n_names) {
                             uint32_t cnt = 0;
 #pragma unroll
-                            for (int p = 0; p < P; p++) cnt |= ((c[p][w] >> bit) & 1u) << p;
-                            a.dense_counts[(uint64_t)q * 0 + a.target_base + t] = cnt;
+                            for (int p = 0; p < P; p++) cnt |= ((plane(p, w) >> bit) & 1u) << p;
+                            a.dense_counts[a.target_base + t] = cnt;
                         }
                     }
             }
@@ -593,7 +639,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
                         uint32_t t = (col16 * 16 + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
                         uint32_t cnt = 0;
 #pragma unroll
-                        for (int p = 0; p < P; p++) cnt |= ((c[p][w] >> bit) & 1u) << p;
+                        for (int p = 0; p < P; p++) cnt |= ((plane(p, w) >> bit) & 1u) << p;
                         if (slot < a.hit_cap) {
                             a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
                             a.hit_vals[slot] = cnt;
@@ -606,41 +652,54 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
     }
 }
 
-struct ProbeTune { int var = 2, minb = 2, cap = 16; };
+struct ProbeTune { int var = 2, minb = 2, cap = 16, var_h = 2, minb_h = 1; };
 static ProbeTune probe_tune() {
-    // development knobs (tools/probe_sweep.py): KMCPG_PROBE_VAR, KMCPG_PROBE_MINB, KMCPG_PROBE_CAP
+    // development knobs (tools/probe_sweep.sh): KMCPG_PROBE_VAR / _MINB (h=1), KMCPG_PROBE_VARH / _MINBH (h>1), KMCPG_PROBE_CAP
     static ProbeTune t = [] {
         ProbeTune x;
         if (const char *e = getenv("KMCPG_PROBE_VAR")) x.var = atoi(e);
         if (const char *e = getenv("KMCPG_PROBE_MINB")) x.minb = atoi(e);
+        if (const char *e = getenv("KMCPG_PROBE_VARH")) x.var_h = atoi(e);
+        if (const char *e = getenv("KMCPG_PROBE_MINBH")) x.minb_h = atoi(e);
         if (const char *e = getenv("KMCPG_PROBE_CAP")) x.cap = atoi(e);
         return x;
     }();
     return t;
 }
 
-template <int H, int P>
+template <int H, int PH, int VAR, int MINB>
+static cudaError_t launch_probe_k(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
+    const size_t smem = PH > 0 ? (size_t)(8 + PH) * 4 * PROBE_THREADS * sizeof(uint32_t) : 0;
+    if (smem > 48 * 1024) {
+        static bool done = false;       // per instantiation
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(probe_kernel<H, PH, VAR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            done = true;
+        }
+    }
+    probe_kernel<H, PH, VAR, MINB><<<blocks, PROBE_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int H, int PH>
 static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     const ProbeTune t = probe_tune();
-    if (P == 8) {       // the short-read case gets the tuned variants
-        if (t.var == 0) probe_kernel<H, P, 0, 2><<<blocks, PROBE_THREADS, 0, st>>>(a);
-        else if (t.var == 1 && t.minb >= 3) probe_kernel<H, P, 1, 3><<<blocks, PROBE_THREADS, 0, st>>>(a);
-        else if (t.var == 1) probe_kernel<H, P, 1, 2><<<blocks, PROBE_THREADS, 0, st>>>(a);
-        else if (t.minb >= 3) probe_kernel<H, P, 2, 3><<<blocks, PROBE_THREADS, 0, st>>>(a);
-        else probe_kernel<H, P, 2, 2><<<blocks, PROBE_THREADS, 0, st>>>(a);
-    } else {
-        probe_kernel<H, P, 1, 1><<<blocks, PROBE_THREADS, 0, st>>>(a);
-    }
-    return cudaGetLastError();
+    const int var = H == 1 ? t.var : t.var_h;
+    int minb = H == 1 ? t.minb : t.minb_h;
+    if (PH >= 24) minb = 1;                                  // 128 KB of counter planes per CTA
+    if (var == 0) return launch_probe_k<H, PH, 0, 2>(a, blocks, st);
+    if (var == 1) return minb >= 2 ? launch_probe_k<H, PH, 1, 2>(a, blocks, st) : launch_probe_k<H, PH, 1, 1>(a, blocks, st);
+    return minb >= 2 ? launch_probe_k<H, PH, 2, 2>(a, blocks, st) : launch_probe_k<H, PH, 2, 1>(a, blocks, st);
 }
 
 template <int H>
 static cudaError_t launch_probe_h(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     switch (a.planes) {
-        case 8: return launch_probe_hp<H, 8>(a, blocks, st);
-        case 16: return launch_probe_hp<H, 16>(a, blocks, st);
-        case 24: return launch_probe_hp<H, 24>(a, blocks, st);
-        case 32: return launch_probe_hp<H, 32>(a, blocks, st);
+        case 8: return launch_probe_hp<H, 0>(a, blocks, st);
+        case 16: return launch_probe_hp<H, 8>(a, blocks, st);
+        case 24: return launch_probe_hp<H, 16>(a, blocks, st);
+        case 32: return launch_probe_hp<H, 24>(a, blocks, st);
         default: return cudaErrorInvalidValue;
     }
 }
