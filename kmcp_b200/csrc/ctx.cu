@@ -211,20 +211,27 @@ int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int
     uint64_t *codes = w.codes.as<uint64_t>();
     int do_unique = 0;
     if (sb.max_query_slots > (uint64_t)p.dedup_threshold && sb.total_slots > 0) {
-        // U:874-908: sort + unique of queries with more than dedup_threshold k-mers
-        if (sb.total_slots >= (1ull << 31)) return fail(ctx, KMCPG_EUNSUPPORTED, "sub-batch too large for the dedup sort");
-        CU(w.segb.ensure(nq * 4ull)); CU(w.sege.ensure(nq * 4ull));
-        CU(w.codes2.ensure(sb.total_slots * 8));
-        CU(launch_sort_segments(w.slot_off.as<uint64_t>(), w.ncodes.as<uint32_t>(), nq, p.paired, p.dedup_threshold, w.segb.as<int>(), w.sege.as<int>(), st));
-        CU(cudaMemcpyAsync(w.codes2.p, w.codes.p, sb.total_slots * 8, cudaMemcpyDeviceToDevice, st));
-        size_t t2 = 0;
-        cub::DeviceSegmentedSort::SortKeys(nullptr, t2, w.codes.as<uint64_t>(), w.codes2.as<uint64_t>(), (int)sb.total_slots, (int)nq,
-                                           w.segb.as<int>(), w.sege.as<int>(), st);
-        CU(w.tmp.ensure(t2));
-        CU(cub::DeviceSegmentedSort::SortKeys(w.tmp.p, t2, w.codes.as<uint64_t>(), w.codes2.as<uint64_t>(), (int)sb.total_slots, (int)nq,
-                                              w.segb.as<int>(), w.sege.as<int>(), st));
-        ctx->launches += 4;
-        codes = w.codes2.as<uint64_t>();
+        // U:874-908: sort + unique of queries with more than dedup_threshold k-mers.
+        // up to SMALL_DEDUP_MAX k-mers: inside one warp, in place; longer queries: CUB segmented sort
+        CU(launch_small_dedup(w.codes.as<uint64_t>(), w.slot_off.as<uint64_t>(), w.ncodes.as<uint32_t>(), nq, p.paired, p.dedup_threshold,
+                              p.min_matched, sb.max_query_slots, st));
+        ctx->launches++;
+        if (sb.max_query_slots > (uint64_t)SMALL_DEDUP_MAX) {
+            if (sb.total_slots >= (1ull << 31)) return fail(ctx, KMCPG_EUNSUPPORTED, "sub-batch too large for the dedup sort");
+            CU(w.segb.ensure(nq * 4ull)); CU(w.sege.ensure(nq * 4ull));
+            CU(w.codes2.ensure(sb.total_slots * 8));
+            CU(launch_sort_segments(w.slot_off.as<uint64_t>(), w.ncodes.as<uint32_t>(), nq, p.paired, std::max(p.dedup_threshold, SMALL_DEDUP_MAX),
+                                    w.segb.as<int>(), w.sege.as<int>(), st));
+            CU(cudaMemcpyAsync(w.codes2.p, w.codes.p, sb.total_slots * 8, cudaMemcpyDeviceToDevice, st));
+            size_t t2 = 0;
+            cub::DeviceSegmentedSort::SortKeys(nullptr, t2, w.codes.as<uint64_t>(), w.codes2.as<uint64_t>(), (int)sb.total_slots, (int)nq,
+                                               w.segb.as<int>(), w.sege.as<int>(), st);
+            CU(w.tmp.ensure(t2));
+            CU(cub::DeviceSegmentedSort::SortKeys(w.tmp.p, t2, w.codes.as<uint64_t>(), w.codes2.as<uint64_t>(), (int)sb.total_slots, (int)nq,
+                                                  w.segb.as<int>(), w.sege.as<int>(), st));
+            ctx->launches += 4;
+            codes = w.codes2.as<uint64_t>();
+        }
         do_unique = 1;
     }
     CU(cudaMemsetAsync(w.counters.p, 0, 16, st));     // [0] hit count, [1] Σ n_kmers

@@ -278,7 +278,7 @@ __global__ void sort_segments_kernel(const uint64_t *__restrict__ slot_off, cons
     if (q >= nq) return;
     uint64_t b = slot_off[paired ? 2 * q : q];
     uint32_t n = n_codes[q];
-    if (n == 0xFFFFFFFFu) n = 0;
+    if (n == 0xFFFFFFFFu || (n & 0x80000000u)) n = 0;                  // skipped, or already handled by small_dedup_kernel
     seg_begin[q] = (int)b;
     seg_end[q] = (int)((n > (uint32_t)thr) ? b + n : b);      // strict > (U:874)
 }
@@ -287,6 +287,88 @@ cudaError_t launch_sort_segments(const uint64_t *slot_off, const uint32_t *n_cod
                                  int *seg_begin, int *seg_end, cudaStream_t st) {
     if (!nq) return cudaSuccess;
     sort_segments_kernel<<<(nq + 255) / 256, 256, 0, st>>>(slot_off, n_codes, nq, paired, thr, seg_begin, seg_end);
+    return cudaGetLastError();
+}
+
+// ---- warp-level sort + unique for mid-sized queries (U:874-908) ----
+// element i of the N = 32*ITEMS keys lives in register i/32 of lane i%32; compare-exchange partners at distance
+// j < 32 sit in another lane (shuffle), at distance j >= 32 in another register of the same lane.
+template <int ITEMS>
+__device__ __forceinline__ uint32_t warp_sort_unique(uint64_t *c, uint32_t n, int lane) {
+    uint64_t v[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) { const uint32_t i = r * 32 + lane; v[r] = i < n ? c[i] : ~0ull; }
+    constexpr int N = ITEMS * 32;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < ITEMS; r++) {
+                    if ((r & rr) == 0) {
+                        const bool asc = (((r * 32) & k) == 0);            // k >= 64 here: depends on the register index only
+                        const uint64_t a = v[r], b = v[r | rr];
+                        const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+                        v[r] = asc ? lo : hi; v[r | rr] = asc ? hi : lo;
+                    }
+                }
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < ITEMS; r++) {
+                    const uint32_t i = r * 32 + lane;
+                    const bool asc = ((i & k) == 0);
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const uint64_t mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+                    v[r] = (asc == lower) ? mn : mx;
+                }
+            }
+        }
+    }
+    // unique, written back in ascending order
+    __syncwarp();
+    uint32_t w = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        const uint32_t i = r * 32 + lane;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, v[r], 1);
+        if (r > 0) { const uint64_t pl = __shfl_sync(0xffffffffu, v[r - 1], 31); if (lane == 0) prev = pl; }
+        const bool keep = i < n && (i == 0 || v[r] != prev);
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) c[w + __popc(m & ((1u << lane) - 1))] = v[r];
+        w += __popc(m);
+    }
+    return w;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(128) small_dedup_kernel(uint64_t *__restrict__ codes, const uint64_t *__restrict__ slot_off, uint32_t *__restrict__ n_codes,
+                                                          uint32_t nq, int paired, uint32_t lo, uint32_t hi, uint32_t min_matched) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = warp; q < nq; q += n_warps) {
+        const uint32_t n = n_codes[q];
+        if (n == 0xFFFFFFFFu || n <= lo || n > hi) continue;              // this launch handles lo < n <= hi
+        if (n < min_matched) continue;                                    // unmatched by U:854-869, which looks at the count BEFORE dedup
+        uint64_t *c = codes + slot_off[paired ? 2 * q : q];
+        const uint32_t m = warp_sort_unique<ITEMS>(c, n, lane);
+        if (lane == 0) n_codes[q] = m | 0x80000000u;                      // flag: already deduplicated, and it passed the min-kmers gate
+    }
+}
+
+cudaError_t launch_small_dedup(uint64_t *codes, const uint64_t *slot_off, uint32_t *n_codes, uint32_t nq, int paired, int thr, int min_matched,
+                               uint64_t max_n, cudaStream_t st) {
+    if (!nq) return cudaSuccess;
+    uint32_t blocks = (nq + 3) / 4;
+    if (blocks > 148u * 32u) blocks = 148u * 32u;
+    const uint32_t t = (uint32_t)thr;                                      // strict > (U:874)
+    // one launch per size class that can occur in this part (register budget differs by class)
+    if (t < 512 && max_n > t) small_dedup_kernel<16><<<blocks, 128, 0, st>>>(codes, slot_off, n_codes, nq, paired, t, 512, (uint32_t)min_matched);
+    if (t < 1024 && max_n > 512) small_dedup_kernel<32><<<blocks, 128, 0, st>>>(codes, slot_off, n_codes, nq, paired, t > 512 ? t : 512, 1024, (uint32_t)min_matched);
+    if (t < 2048 && max_n > 1024) small_dedup_kernel<64><<<blocks, 128, 0, st>>>(codes, slot_off, n_codes, nq, paired, t > 1024 ? t : 1024, 2048, (uint32_t)min_matched);
     return cudaGetLastError();
 }
 
@@ -300,9 +382,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
         uint32_t n = a.n_codes[q];
         bool skipped = n == 0xFFFFFFFFu;
         if (skipped) n = 0;
+        const bool deduped = !skipped && (n & 0x80000000u);                // small_dedup_kernel already sorted + uniqued this query
+        n &= 0x7FFFFFFFu;
         // U:854-869: fewer k-mers than min-matched → unmatched, checked BEFORE dedup
-        bool too_few = (int64_t)n < (int64_t)a.min_matched;
-        if (!skipped && !too_few && a.do_unique && n > (uint32_t)a.dedup_threshold) {
+        bool too_few = !deduped && (int64_t)n < (int64_t)a.min_matched;
+        if (!skipped && !too_few && !deduped && a.do_unique && n > (uint32_t)a.dedup_threshold) {
             uint64_t *c = a.codes + a.slot_off[a.paired ? 2 * q : q];
             uint32_t w = 0;
             for (uint32_t base = 0; base < n; base += 32) {
@@ -652,7 +736,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
     }
 }
 
-struct ProbeTune { int var = 2, minb = 2, cap = 16, var_h = 2, minb_h = 1; };
+struct ProbeTune { int var = 2, minb = 2, cap = 16, var_h = 1, minb_h = 3; };
 static ProbeTune probe_tune() {
     // development knobs (tools/probe_sweep.sh): KMCPG_PROBE_VAR / _MINB (h=1), KMCPG_PROBE_VARH / _MINBH (h>1), KMCPG_PROBE_CAP
     static ProbeTune t = [] {
@@ -688,8 +772,8 @@ static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStre
     const int var = H == 1 ? t.var : t.var_h;
     int minb = H == 1 ? t.minb : t.minb_h;
     if (PH >= 24) minb = 1;                                  // 128 KB of counter planes per CTA
-    if (var == 0) return launch_probe_k<H, PH, 0, 2>(a, blocks, st);
-    if (var == 1) return minb >= 2 ? launch_probe_k<H, PH, 1, 2>(a, blocks, st) : launch_probe_k<H, PH, 1, 1>(a, blocks, st);
+    if (var == 0) return minb >= 3 ? launch_probe_k<H, PH, 0, 3>(a, blocks, st) : launch_probe_k<H, PH, 0, 2>(a, blocks, st);
+    if (var == 1) return minb >= 3 ? launch_probe_k<H, PH, 1, 3>(a, blocks, st) : (minb >= 2 ? launch_probe_k<H, PH, 1, 2>(a, blocks, st) : launch_probe_k<H, PH, 1, 1>(a, blocks, st));
     return minb >= 2 ? launch_probe_k<H, PH, 2, 2>(a, blocks, st) : launch_probe_k<H, PH, 2, 1>(a, blocks, st);
 }
 

@@ -69,9 +69,14 @@ struct FinalizeArgs {
     double min_query_cov;
 };
 cudaError_t launch_finalize(const FinalizeArgs &a, cudaStream_t st);
-// segment descriptors for cub::DeviceSegmentedSort: begin/end of regions with n > dedup_threshold (else empty)
+// segment descriptors for cub::DeviceSegmentedSort: begin/end of regions with n > min_n (else empty)
 cudaError_t launch_sort_segments(const uint64_t *slot_off, const uint32_t *n_codes, uint32_t n_queries, int paired,
-                                 int dedup_threshold, int *seg_begin, int *seg_end, cudaStream_t st);
+                                 int min_n, int *seg_begin, int *seg_end, cudaStream_t st);
+// queries with dedup_threshold < n <= SMALL_DEDUP_MAX k-mers: sort + unique inside one warp (bitonic network in
+// registers), in place; n_codes updated.  Covers paired-end 2x150 bp (n = 260) and reads up to ~2 kb.
+constexpr int SMALL_DEDUP_MAX = 2048;
+cudaError_t launch_small_dedup(uint64_t *codes, const uint64_t *slot_off, uint32_t *n_codes, uint32_t n_queries, int paired,
+                               int dedup_threshold, int min_matched, uint64_t max_query_slots, cudaStream_t st);
 
 // ---- kernel 2a: code → row index of one block (hashValues + fastdiv.Mod; H:125-141, U:6811) ------------
 cudaError_t launch_locs(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint32_t *locs,
