@@ -316,7 +316,7 @@ def main():
                 o = ctx.search_batch_ptr(stage.data_ptr(), d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes)
                 hits = o.hits.copy()
                 hits["target"] += np.uint32(rank * BLOCK_SIZE)                         # global target numbering across shards
-                merged = multigpu.gather_hits(hits, rank, world, group=gloo)            # host concat on rank 0
+                merged = multigpu.gather_hits(hits, rank, world, group=gloo, order="none")   # host concat on rank 0
                 if rank == 0:
                     e2e_matches += len(merged)
             barrier()

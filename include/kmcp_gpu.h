@@ -188,6 +188,28 @@ void kmcpg_free_results(kmcpg_results *r);
 /* QueryFPRWithCacheWithConstantFPR's underlying function (F:32-50, F:140-193), bit-exact with Go */
 double kmcpg_query_fpr(int n, int c, double p);
 
+/* ---- database build on the GPU: `kmcp compute` + `kmcp index` fused (compute.go C:577-1033, index.go I:117-1400;
+ *      SURVEY.md §8 f1).  FASTA/Q(.gz) files → <out_dir>/R001/{_blockNNN.uniki, __db.yml, __name_mapping.tsv}; the
+ *      database is left open in this context.  One file = one reference genome. ----------------------------------- */
+typedef struct {
+    int32_t k;                    /* compute -k */
+    int32_t num_hashes;           /* index -n/--num-hash (1..4) */
+    double fpr;                   /* index -f/--false-positive-rate */
+    int32_t split_number;         /* compute -n/--split-number (<=1: no splitting) */
+    int32_t split_overlap;        /* compute -l/--split-overlap (<0: k-1, C:268-270) */
+    int32_t split_min_ref;        /* compute -m/--split-min-ref */
+    uint32_t scale;               /* compute -D/--scale (>1: FracMinHash) */
+    uint32_t minimizer_w;         /* compute -W */
+    uint32_t syncmer_s;           /* compute -S */
+    int32_t block_size;           /* index -b/--block-size; 0: (nFiles/threads+7)/8*8 clamped to [8,nFiles] (I:670-682) */
+    int32_t threads;              /* the -j the block-size rule divides by */
+    const char *ref_name_regexp;  /* compute -N (first capture group of the file name); NULL: file name without extension */
+    const char *const *seq_name_filters; /* compute -B regexps (case-insensitive), matched against the whole header */
+    int32_t n_seq_name_filters;
+} kmcpg_index_params;
+void kmcpg_default_index_params(kmcpg_index_params *p);
+int kmcpg_index_fasta(kmcpg_ctx *ctx, const kmcpg_index_params *p, const char *const *files, int n_files, const char *out_dir);
+
 /* ---- synthetic workloads (bench/test tooling; seeded pure functions, mirrored in oracle/oracle.py) ------ */
 /* d_out[i*read_len .. ) = read (first+i) of the seeded read set; returns device pointers */
 int kmcpg_synth_reads(kmcpg_ctx *ctx, uint64_t seed, uint64_t first, uint32_t n_reads, uint32_t read_len,

@@ -89,6 +89,12 @@ class Results(C.Structure):
                 ("kernel_launches", C.c_uint32), ("_priv", C.c_void_p)]
 
 
+class IndexParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("num_hashes", C.c_int32), ("fpr", C.c_double), ("split_number", C.c_int32), ("split_overlap", C.c_int32),
+                ("split_min_ref", C.c_int32), ("scale", C.c_uint32), ("minimizer_w", C.c_uint32), ("syncmer_s", C.c_uint32), ("block_size", C.c_int32),
+                ("threads", C.c_int32), ("ref_name_regexp", C.c_char_p), ("seq_name_filters", C.POINTER(C.c_char_p)), ("n_seq_name_filters", C.c_int32)]
+
+
 class SynthDb(C.Structure):
     _fields_ = [("genome_seed", C.c_uint64), ("n_genomes", C.c_uint32), ("genome_len", C.c_uint32), ("k", C.c_int32),
                 ("n_chunks", C.c_int32), ("overlap", C.c_int32), ("num_hashes", C.c_int32), ("fpr", C.c_double),
@@ -101,7 +107,7 @@ ABI_SYMBOLS = [
     "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_free_hits", "kmcpg_host_alloc",
     "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
     "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search",
-    "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_synth_reads", "kmcpg_build_synth_db", "kmcpg_write_block",
+    "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_build_synth_db", "kmcpg_write_block",
 ]
 
 _lib = None
@@ -150,6 +156,9 @@ def load() -> C.CDLL:
     L.kmcpg_free_results.restype = None
     L.kmcpg_query_fpr.restype = C.c_double
     L.kmcpg_query_fpr.argtypes = [C.c_int, C.c_int, C.c_double]
+    L.kmcpg_default_index_params.argtypes = [C.POINTER(IndexParams)]
+    L.kmcpg_default_index_params.restype = None
+    L.kmcpg_index_fasta.argtypes = [vp, C.POINTER(IndexParams), C.POINTER(C.c_char_p), C.c_int, C.c_char_p]
     L.kmcpg_synth_reads.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, vp]
     L.kmcpg_build_synth_db.argtypes = [vp, C.POINTER(SynthDb)]
     L.kmcpg_write_block.argtypes = [vp, C.c_int, C.c_char_p]
@@ -247,6 +256,20 @@ class Context:
                        overlap: int = 150, num_hashes: int = 1, fpr: float = 0.3, block_size: int = 0):
         s = SynthDb(genome_seed, n_genomes, genome_len, k, n_chunks, overlap, num_hashes, fpr, block_size)
         self._check(self._L.kmcpg_build_synth_db(self._h, C.byref(s)))
+
+    def index_fasta(self, files, out_dir: str, k: int = 21, num_hashes: int = 1, fpr: float = 0.3, split_number: int = 1, split_overlap: int = -1,
+                    split_min_ref: int = 1000, scale: int = 1, minimizer_w: int = 0, syncmer_s: int = 0, block_size: int = 0, threads: int = 16,
+                    ref_name_regexp: Optional[str] = None, seq_name_filters: Sequence[str] = ()):
+        """kmcp compute + kmcp index on the GPU; the new database stays open in this context"""
+        p = IndexParams()
+        self._L.kmcpg_default_index_params(C.byref(p))
+        p.k, p.num_hashes, p.fpr, p.split_number, p.split_overlap, p.split_min_ref = k, num_hashes, fpr, split_number, split_overlap, split_min_ref
+        p.scale, p.minimizer_w, p.syncmer_s, p.block_size, p.threads = scale, minimizer_w, syncmer_s, block_size, threads
+        p.ref_name_regexp = ref_name_regexp.encode() if ref_name_regexp else None
+        flt = (C.c_char_p * max(1, len(seq_name_filters)))(*[f.encode() for f in seq_name_filters])
+        p.seq_name_filters = C.cast(flt, C.POINTER(C.c_char_p)); p.n_seq_name_filters = len(seq_name_filters)
+        arr = (C.c_char_p * len(files))(*[f.encode() for f in files])
+        self._check(self._L.kmcpg_index_fasta(self._h, C.byref(p), arr, len(files), out_dir.encode() if out_dir else None))
 
     def write_block(self, resident_block: int, path: str):
         self._check(self._L.kmcpg_write_block(self._h, resident_block, path.encode()))

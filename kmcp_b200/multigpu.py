@@ -18,9 +18,10 @@ def broadcast_batch(dev_buf: torch.Tensor, src: int = 0) -> torch.Tensor:
     return dev_buf
 
 
-def gather_hits(hits: np.ndarray, rank: int, world: int, group=None, dst: int = 0):
-    """variable-size gather of 12-byte hit records on a CPU (gloo) group; rank `dst` gets all records sorted
-    by (query, target), the others get None"""
+def gather_hits(hits: np.ndarray, rank: int, world: int, group=None, dst: int = 0, order: str = "query_target"):
+    """variable-size gather of 12-byte hit records on a CPU (gloo) group; rank `dst` gets all records, the others
+    get None.  order: "query_target" = canonical (query, target) order; "query" = stable by query only (each
+    shard's list is already sorted, shards are disjoint by target); "none" = plain concatenation"""
     raw = torch.from_numpy(np.ascontiguousarray(hits).view(np.uint8).copy())
     cnt = torch.tensor([raw.numel()], dtype=torch.int64)
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
@@ -36,6 +37,10 @@ def gather_hits(hits: np.ndarray, rank: int, world: int, group=None, dst: int = 
             parts.append(buf)
         allb = torch.cat(parts).numpy()
         out = allb.view(hits.dtype)
+        if order == "none":
+            return out
+        if order == "query":
+            return out[np.argsort(out["query"], kind="stable")]
         return out[np.lexsort((out["target"], out["query"]))]
     if raw.numel():
         dist.send(raw, dst=dst, group=group)

@@ -434,3 +434,77 @@ def test_sketch_database_search_end_to_end(gpu_ctx, oracle, tmp_path, kw, h, fpr
     queries = [genomes[0], genomes[5], genomes[11], O.synth_genome(22, 3, 50000), genomes[3][:200]]
     got = _compare_engine(O, odb, gpu_ctx, queries, min_query_cov=0.1, sort_by=2)
     assert len(got.matches) >= 12 and got.n_kmers.max() > 256
+
+
+# ---------------------------------------------------------------------------------------------------- GPU compute+index
+def _write_fasta(path, records, gz=False):
+    import gzip
+    op = gzip.open if gz else open
+    with op(path, "wb") as f:
+        for hdr, s in records:
+            f.write(b">" + hdr + b"\n")
+            for j in range(0, len(s), 60):
+                f.write(s[j:j + 60] + b"\n")
+
+
+def _make_genome_files(O, tmp_path, n=10):
+    rng = np.random.default_rng(11)
+    files = []
+    for g in range(n):
+        L = int(rng.integers(15000, 40000))
+        chrom = O.synth_genome(41, g, L)
+        recs = [(b"chr1 Genome %d chromosome" % g, chrom[:L // 2].lower() if g % 3 == 0 else chrom[:L // 2]),
+                (b"chr2 second contig", chrom[L // 2:]),
+                (b"p1 Genome %d Plasmid pX" % g, O.synth_genome(42, g, 3000))]
+        if g == 4:
+            recs.append((b"tiny", b"ACGTACGTAC"))
+        path = str(tmp_path / ("GCF_%06d.%d.fa%s" % (g, 1 + g % 2, ".gz" if g % 2 else "")))
+        _write_fasta(path, recs, gz=bool(g % 2))
+        files.append(path)
+    return files
+
+
+@pytest.mark.parametrize("mode", ["split_k21_h1", "nosplit_syncmer_h3", "nosplit_scaled_h2"])
+def test_gpu_compute_index_matches_oracle_builder(gpu_ctx, oracle, tmp_path, mode):
+    """kmcpg_index_fasta (GPU `kmcp compute` + `kmcp index`) writes the same database, byte for byte, as the oracle's
+    restatement of compute/index on the same FASTA files, and answers queries identically"""
+    import re
+    O = oracle
+    files = _make_genome_files(O, tmp_path)
+    name_re = r"^([\w\.\_]+\.\d+)"
+    if mode == "split_k21_h1":
+        kw = dict(k=21, num_hashes=1, fpr=0.3, split_number=5, split_overlap=100, block_size=16)
+        sp = O.sketch_params(21)
+    elif mode == "nosplit_syncmer_h3":
+        kw = dict(k=31, num_hashes=3, fpr=0.01, syncmer_s=15, scale=4, threads=2)
+        sp = O.sketch_params(31, scaled=True, scale=4, syncmer_s=15)
+    else:
+        kw = dict(k=31, num_hashes=2, fpr=0.05, scale=10, block_size=8)
+        sp = O.sketch_params(31, scaled=True, scale=10)
+    # oracle side
+    targets = []
+    for f in files:
+        name = re.match(name_re, os.path.basename(f)).group(1)
+        targets += O.compute_targets(list(O.read_fastx(f)), name, sp, split_number=kw.get("split_number", 1), split_overlap=kw.get("split_overlap", 0),
+                                     name_filters=["plasmid"])
+    r001 = O.build_db(targets, str(tmp_path / "odb"), sp, num_hashes=kw["num_hashes"], fpr=kw["fpr"], block_size=kw.get("block_size", 0),
+                      threads=kw.get("threads", 16))
+    # device side
+    out = str(tmp_path / "gdb")
+    gpu_ctx.index_fasta(files, out, ref_name_regexp=name_re, seq_name_filters=["plasmid"], **kw)
+    gfiles = sorted(f for f in os.listdir(os.path.join(out, "R001")) if f.endswith(".uniki"))
+    ofiles = sorted(f for f in os.listdir(r001) if f.endswith(".uniki"))
+    assert gfiles == ofiles and len(gfiles) >= 2
+    for fn in gfiles:
+        assert open(os.path.join(out, "R001", fn), "rb").read() == open(os.path.join(r001, fn), "rb").read(), fn
+    # the written DB opens in the oracle and reports the same parameters
+    odb_g = O.DB(os.path.join(out, "R001"))
+    odb = O.DB(r001)
+    for f in ("n_targets", "n_blocks", "num_hashes", "scaled", "scale", "syncmer", "syncmer_s", "fpr", "total_bytes"):
+        assert getattr(odb_g.info, f) == getattr(odb.info, f), f
+    # the context holds the new DB: search it straight away
+    qs = [O.synth_genome(41, 2, 9000)[1000:8000], O.synth_genome(41, 7, 9000)[:3000]] + helpers.make_reads(O, 3, 50, 10, 15000, 41)
+    _compare_engine(O, odb, gpu_ctx, qs, min_query_cov=0.2)
+    # and it can be re-opened from disk
+    gpu_ctx.open_db(os.path.join(out, "R001"))
+    _compare_engine(O, odb, gpu_ctx, qs, min_query_cov=0.2)
