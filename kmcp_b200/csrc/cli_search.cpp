@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <regex>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,9 @@ void logf(const char *level, const char *fmt, ...) {
     logf("ERRO", "%s", buf);
     exit(255);
 }
+
+bool is_dir(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+bool is_file(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
 
 struct Opts {
     std::string db_dir, out_file = "-", read1, read2, sort_by = "qcov", query_id, log_file;
@@ -167,8 +171,6 @@ struct Writer {
     void close() { flush(); if (gz) gzclose(gz); else if (fp && fp != stdout) fclose(fp); else if (fp) fflush(fp); }
 };
 
-bool is_dir(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
-bool is_file(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
 
 std::string trim_ext(const std::string &file) {     // filepathTrimExtension: strip dir, .gz/.xz/.zst/.bz2, then one extension
     std::string b = file.substr(file.find_last_of('/') == std::string::npos ? 0 : file.find_last_of('/') + 1);
@@ -195,7 +197,76 @@ void load_kv(const std::string &path, std::map<std::string, std::string> &m) {
 
 }  // namespace
 
+// kmcp-gpu index: `kmcp compute` + `kmcp index` in one step on the GPU (flags keep the reference's names; -n is
+// compute's --split-number, index's -n/--num-hash is spelled --num-hash here)
+int index_main(int argc, char **argv) {
+    kmcpg_index_params p;
+    kmcpg_default_index_params(&p);
+    std::string in_dir, out_dir, file_re = "\\.(f[aq](st[aq])?|fna)(.gz)?$", name_re = "(?i)(.+)\\.(f[aq](st[aq])?|fna)(.gz)?$";
+    std::vector<std::string> files, filters;
+    bool force = false;
+    int device = 0;
+    auto need = [&](int &i) -> const char * { if (i + 1 >= argc) die("flag needs an argument: %s", argv[i]); return argv[++i]; };
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "-I" || a == "--in-dir") in_dir = need(i);
+        else if (a == "-r" || a == "--file-regexp") file_re = need(i);
+        else if (a == "-O" || a == "--out-dir") out_dir = need(i);
+        else if (a == "-k" || a == "--kmer") p.k = atoi(need(i));
+        else if (a == "-n" || a == "--split-number") p.split_number = atoi(need(i));
+        else if (a == "-l" || a == "--split-overlap") p.split_overlap = atoi(need(i));
+        else if (a == "-m" || a == "--split-min-ref") p.split_min_ref = atoi(need(i));
+        else if (a == "-B" || a == "--seq-name-filter") filters.push_back(need(i));
+        else if (a == "-N" || a == "--ref-name-regexp") name_re = need(i);
+        else if (a == "-D" || a == "--scale") p.scale = (uint32_t)atoi(need(i));
+        else if (a == "-W" || a == "--minimizer-w") p.minimizer_w = (uint32_t)atoi(need(i));
+        else if (a == "-S" || a == "--syncmer-s") p.syncmer_s = (uint32_t)atoi(need(i));
+        else if (a == "-f" || a == "--false-positive-rate") p.fpr = atof(need(i));
+        else if (a == "--num-hash") p.num_hashes = atoi(need(i));
+        else if (a == "-b" || a == "--block-size") p.block_size = atoi(need(i));
+        else if (a == "-j" || a == "--threads") p.threads = atoi(need(i));
+        else if (a == "--force") force = true;
+        else if (a == "-q" || a == "--quiet") g_quiet = true;
+        else if (a == "--gpu") device = atoi(need(i));
+        else if (a == "-h" || a == "--help") {
+            fputs("kmcp-gpu index [-I <dir> | files...] -O <out.kmcp> [-k 21] [-n split-number] [-l split-overlap] [-B regexp]... [-N regexp]\n"
+                  "               [-D scale] [-W minimizer-w] [-S syncmer-s] [-f fpr] [--num-hash n] [-b block-size] [-j threads] [--force]\n", stderr);
+            return 0;
+        } else if (a.size() > 1 && a[0] == '-') die("unknown flag: %s", a.c_str());
+        else files.push_back(a);
+    }
+    if (out_dir.empty()) die("flag -O/--out-dir needed");
+    if (is_dir(out_dir) && !force) die("out-dir not empty: %s, use --force to overwrite", out_dir.c_str());
+    if (!in_dir.empty()) {
+        std::regex re(file_re, std::regex::ECMAScript | std::regex::icase);
+        DIR *d = opendir(in_dir.c_str());
+        if (!d) die("fail to read directory: %s", in_dir.c_str());
+        while (dirent *e = readdir(d)) { std::string n = e->d_name; if (std::regex_search(n, re) && is_file(in_dir + "/" + n)) files.push_back(in_dir + "/" + n); }
+        closedir(d);
+    }
+    std::sort(files.begin(), files.end());
+    if (files.empty()) die("no files given");
+    logf("INFO", "kmcp-gpu index: %zu input file(s)", files.size());
+    kmcpg_ctx *ctx = nullptr;
+    if (kmcpg_create(device, &ctx)) die("%s", kmcpg_last_error(nullptr));
+    std::vector<const char *> fp, flt;
+    for (auto &f : files) fp.push_back(f.c_str());
+    for (auto &f : filters) flt.push_back(f.c_str());
+    p.ref_name_regexp = name_re.c_str();
+    p.seq_name_filters = flt.empty() ? nullptr : flt.data();
+    p.n_seq_name_filters = (int)flt.size();
+    auto t0 = std::chrono::steady_clock::now();
+    if (kmcpg_index_fasta(ctx, &p, fp.data(), (int)fp.size(), out_dir.c_str())) die("%s", kmcpg_last_error(ctx));
+    kmcpg_db_info_t info;
+    kmcpg_db_info(ctx, &info);
+    logf("INFO", "kmcp database with %lld targets in %d block(s) saved to: %s (%.1f s)", (long long)info.n_targets, info.n_blocks, out_dir.c_str(),
+         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    kmcpg_close(ctx);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && !strcmp(argv[1], "index")) return index_main(argc, argv);
     Opts o;
     int ai = 1;
     if (ai < argc && !strcmp(argv[ai], "search")) ai++;

@@ -508,3 +508,33 @@ def test_gpu_compute_index_matches_oracle_builder(gpu_ctx, oracle, tmp_path, mod
     # and it can be re-opened from disk
     gpu_ctx.open_db(os.path.join(out, "R001"))
     _compare_engine(O, odb, gpu_ctx, qs, min_query_cov=0.2)
+
+
+def test_cli_index_then_search_roundtrip(oracle, tmp_path):
+    """kmcp-gpu index (GPU compute+index) → kmcp-gpu search, against the oracle's compute/index/search/TSV on the same files"""
+    import re
+    import subprocess
+    O = oracle
+    files = _make_genome_files(O, tmp_path, n=8)
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmcp_b200", "kmcp-gpu")
+    out = str(tmp_path / "cli.kmcp")
+    name_re = r"^([\w\.\_]+\.\d+)"
+    p = subprocess.run([exe, "index", "-q", "-O", out, "-k", "21", "-n", "4", "-l", "150", "-B", "plasmid", "-N", name_re, "-f", "0.3", "-b", "8"] + files,
+                       capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    sp = O.sketch_params(21)
+    targets = []
+    for f in files:
+        targets += O.compute_targets(list(O.read_fastx(f)), re.match(name_re, os.path.basename(f)).group(1), sp, split_number=4, split_overlap=150,
+                                     name_filters=["plasmid"])
+    r001 = O.build_db(targets, str(tmp_path / "odb"), sp, num_hashes=1, fpr=0.3, block_size=8)
+    for fn in sorted(f for f in os.listdir(r001) if f.endswith(".uniki")):
+        assert open(os.path.join(out, "R001", fn), "rb").read() == open(os.path.join(r001, fn), "rb").read(), fn
+    reads = helpers.make_reads(O, 13, 600, 8, 15000, 41)
+    ids = [b"r%d" % i for i in range(len(reads))]
+    fq = str(tmp_path / "q.fq.gz")
+    _write_fastq(fq, ids, reads)
+    tsv = str(tmp_path / "o.tsv")
+    _run_cli(["-d", out, fq, "-o", tsv])
+    odb = O.DB(r001)
+    assert open(tsv).read() == O.format_tsv(odb, ids, odb.search(reads))
