@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -111,15 +112,15 @@ struct Round {
 };
 
 // filters + sorts the hits of local queries [lo, hi) (U:7466-7491, U:273-311); matches are written densely from dst
-size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_hits &hits, const uint64_t *hoff, const uint32_t *cur, const double *tsize, FprCache *cache,
-                   uint32_t lo, uint32_t hi, kmcpg_match *dst, uint32_t *count) {
+size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_hits &hits, const uint64_t *hoff, const uint32_t *cur, uint32_t q0, const double *tsize,
+                   FprCache *cache, uint32_t lo, uint32_t hi, kmcpg_match *dst, uint32_t *count) {
     const Less less{o->sort_by};
     size_t w = 0;
     for (uint32_t l = lo; l < hi; l++) {
         const int n = hits.n_kmers[l];
         count[l] = 0;
         if (n == 0 || hoff[l] == hoff[l + 1]) continue;
-        const uint32_t q = cur ? cur[l] : l;
+        const uint32_t q = cur ? cur[l] : q0 + l;
         const double nh = (double)n;
         const size_t start = w;
         for (uint64_t i = hoff[l]; i < hoff[l + 1]; i++) {
@@ -203,7 +204,7 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
         bool cur_all = all_pending;
         for (int tries = 0; tries < tries_max && (cur_all || !cur.empty()); tries++) {
             // pack the pending subset (the first pass uses the caller's buffers untouched)
-            const uint8_t *bs = seq; const uint64_t *bo = off; uint32_t bn = n_seqs;
+            const uint8_t *bs = seq; const uint64_t *bo = off;
             if (!cur_all) {
                 sub_off.assign(1, 0); sub_seq.clear();
                 for (uint32_t q : cur)
@@ -213,82 +214,109 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                         sub_off.push_back(sub_seq.size());
                     }
                 if (sub_seq.empty()) sub_seq.push_back(0);
-                bs = sub_seq.data(); bo = sub_off.data(); bn = (uint32_t)cur.size() * step;
+                bs = sub_seq.data(); bo = sub_off.data();
             }
             kmcpg_search_params p;
             kmcpg_default_params(&p);
             p.min_query_len = o->min_query_len; p.min_matched = o->min_matched; p.dedup_threshold = o->dedup_threshold;
             p.paired = o->paired; p.min_query_cov = o->min_query_cov; p.k = k; p.mate_select = tries;
-            kmcpg_hits hits;
-            rc = kmcpg_search_batch(ctx, &p, bs, bo, bn, &hits);
-            if (rc) { delete priv; return rc; }
-            out->ms_gpu_total += hits.ms_total; out->probe_row_bytes += hits.probe_row_bytes; out->kernel_launches += hits.kernel_launches;
 
-            auto Tp = std::chrono::steady_clock::now();
-            const uint32_t ln = cur_all ? nq : (uint32_t)cur.size();
+            const uint32_t ln_total = cur_all ? nq : (uint32_t)cur.size();
             const uint32_t *curp = cur_all ? nullptr : cur.data();
-            // hit ranges per local query (hits are sorted by query)
-            hoff.assign((size_t)ln + 1, 0);
-            for (uint64_t i = 0; i < hits.n_hits; i++) hoff[hits.hits[i].query + 1]++;
-            for (uint32_t i = 0; i < ln; i++) hoff[i + 1] += hoff[i];
-            count.resize(ln);
-
             rounds.emplace_back();
             Round &R = rounds.back();
             const int ridx = (int)rounds.size() - 1;
-            R.buf = big_acquire(std::max<uint64_t>(hits.n_hits, 1) * sizeof(kmcpg_match));
-            kmcpg_match *M = R.matches();
-            int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 32768 + 1));
-            std::vector<uint32_t> bounds(T + 1, ln);
-            std::vector<size_t> produced(T, 0);
-            bounds[0] = 0;
-            for (int t = 1; t < T; t++) {            // split by hits so the threads get equal work
-                uint64_t want = hits.n_hits * (uint64_t)t / T;
-                bounds[t] = (uint32_t)(std::lower_bound(hoff.begin(), hoff.end(), want) - hoff.begin());
-                if (bounds[t] > ln) bounds[t] = ln;
-                if (bounds[t] < bounds[t - 1]) bounds[t] = bounds[t - 1];
-            }
-            // every thread writes at the hit offset of its first query: no overlap, compaction only if a filter dropped hits
-            const uint64_t *hp = hoff.data();
-            uint32_t *cp = count.data();
-            auto work = [&](int t) { produced[t] = post_filter(o, hits, hp, curp, tsize, cache, bounds[t], bounds[t + 1], M + hp[bounds[t]], cp); };
-            if (T == 1) work(0);
-            else {
-                std::vector<std::thread> th;
-                for (int t = 1; t < T; t++) th.emplace_back(work, t);
-                work(0);
-                for (auto &t : th) t.join();
-            }
-            size_t w = produced[0];
-            for (int t = 1; t < T; t++) {
-                if (produced[t] && w != hp[bounds[t]]) memmove(M + w, M + hp[bounds[t]], produced[t] * sizeof(kmcpg_match));
-                w += produced[t];
-            }
-            R.n = w;
-            R.off.resize((size_t)ln + 1);
-            R.off[0] = 0;
+            R.off.assign((size_t)ln_total + 1, 0);
             const bool single = (ik == 0 && tries == 0 && cur_all);
             if (!single && q_round.empty()) { q_round.assign(nq, -1); q_local.assign(nq, 0); }
             std::vector<uint32_t> retry;
-            for (uint32_t l = 0; l < ln; l++) {
-                const uint32_t q = curp ? curp[l] : l;
-                const int n = hits.n_kmers[l];
-                R.off[l + 1] = R.off[l] + cp[l];
-                r_qlen[q] = hits.query_len[l];
-                r_k[q] = k;
-                if (n == 0) { if (tries == 0) r_nk[q] = 0; continue; }             // U:778-786, U:854-869: final, unmatched
-                r_nk[q] = n;
-                if (cp[l]) { if (!q_round.empty()) { q_round[q] = ridx; q_local[q] = l; } }
-                else retry.push_back(q);
+
+            // filters the hits of local queries [q0, q0+ln) of this round and appends the matches to R
+            auto absorb = [&](const kmcpg_hits &hits, uint32_t q0, uint32_t ln) {
+                auto Tp = std::chrono::steady_clock::now();
+                hoff.assign((size_t)ln + 1, 0);
+                for (uint64_t i = 0; i < hits.n_hits; i++) hoff[hits.hits[i].query + 1]++;      // hits are sorted by query
+                for (uint32_t i = 0; i < ln; i++) hoff[i + 1] += hoff[i];
+                count.resize(ln);
+                const size_t need = (R.n + std::max<uint64_t>(hits.n_hits, 1)) * sizeof(kmcpg_match);
+                if (R.buf.cap < need) {
+                    BigBuf nb = big_acquire(need + need / 2);
+                    if (R.n) memcpy(nb.p, R.buf.p, R.n * sizeof(kmcpg_match));
+                    big_release(R.buf);
+                    R.buf = nb;
+                }
+                kmcpg_match *M = R.matches() + R.n;
+                int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 32768 + 1));
+                std::vector<uint32_t> bounds(T + 1, ln);
+                std::vector<size_t> produced(T, 0);
+                bounds[0] = 0;
+                for (int t = 1; t < T; t++) {            // split by hits so the threads get equal work
+                    uint64_t want = hits.n_hits * (uint64_t)t / T;
+                    bounds[t] = (uint32_t)(std::lower_bound(hoff.begin(), hoff.end(), want) - hoff.begin());
+                    if (bounds[t] > ln) bounds[t] = ln;
+                    if (bounds[t] < bounds[t - 1]) bounds[t] = bounds[t - 1];
+                }
+                // every thread writes at the hit offset of its first query: no overlap, compaction only if a filter dropped hits
+                const uint64_t *hp = hoff.data();
+                uint32_t *cp = count.data();
+                const uint32_t *lcur = curp ? curp + q0 : nullptr;
+                auto work = [&](int t) {
+                    produced[t] = post_filter(o, hits, hp, lcur, q0, tsize, cache, bounds[t], bounds[t + 1], M + hp[bounds[t]], cp);
+                };
+                if (T == 1) work(0);
+                else {
+                    std::vector<std::thread> th;
+                    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+                    work(0);
+                    for (auto &t : th) t.join();
+                }
+                size_t w = produced[0];
+                for (int t = 1; t < T; t++) {
+                    if (produced[t] && w != hp[bounds[t]]) memmove(M + w, M + hp[bounds[t]], produced[t] * sizeof(kmcpg_match));
+                    w += produced[t];
+                }
+                R.n += w;
+                for (uint32_t l = 0; l < ln; l++) {
+                    const uint32_t gl = q0 + l;                                    // index inside the round
+                    const uint32_t q = curp ? curp[gl] : gl;
+                    const int n = hits.n_kmers[l];
+                    R.off[gl + 1] = R.off[gl] + cp[l];
+                    r_qlen[q] = hits.query_len[l];
+                    r_k[q] = k;
+                    if (n == 0) { if (tries == 0) r_nk[q] = 0; continue; }         // U:778-786, U:854-869: final, unmatched
+                    r_nk[q] = n;
+                    if (cp[l]) { if (!q_round.empty()) { q_round[q] = ridx; q_local[q] = gl; } }
+                    else retry.push_back(q);
+                }
+                out->ms_gpu_total += hits.ms_total; out->probe_row_bytes += hits.probe_row_bytes; out->kernel_launches += hits.kernel_launches;
+                out->ms_post += ms_since(Tp);
+            };
+
+            // big rounds are cut into chunks: the device searches chunk c+1 (second thread) while this thread filters chunk c
+            const uint32_t CHUNK_Q = 384u << 10;
+            const uint32_t n_chunks = ln_total > 2 * CHUNK_Q ? (ln_total + CHUNK_Q - 1) / CHUNK_Q : 1;
+            auto run_search = [&](uint32_t c, kmcpg_hits *h) -> int {
+                const uint32_t a = (uint32_t)((uint64_t)ln_total * c / n_chunks), b = (uint32_t)((uint64_t)ln_total * (c + 1) / n_chunks);
+                return kmcpg_search_batch(ctx, &p, bs, bo + (size_t)a * step, (b - a) * step, h);
+            };
+            {
+                kmcpg_hits hits[2];
+                std::future<int> fut = std::async(std::launch::async, run_search, 0u, &hits[0]);
+                for (uint32_t c = 0; c < n_chunks; c++) {
+                    rc = fut.get();
+                    if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
+                    if (c + 1 < n_chunks) fut = std::async(std::launch::async, run_search, c + 1, &hits[(c + 1) & 1]);
+                    const uint32_t a = (uint32_t)((uint64_t)ln_total * c / n_chunks), b = (uint32_t)((uint64_t)ln_total * (c + 1) / n_chunks);
+                    absorb(hits[c & 1], a, b - a);
+                    kmcpg_free_hits(&hits[c & 1]);
+                }
             }
             if (single && (tries_max > 1 || info.n_ks > 1) && !retry.empty()) {
                 // more rounds will follow: remember where round 0 put every matched query
                 q_round.assign(nq, -1); q_local.assign(nq, 0);
-                for (uint32_t l = 0; l < ln; l++) if (cp[l]) { q_round[l] = 0; q_local[l] = l; }
+                for (uint32_t l = 0; l < ln_total; l++) if (R.off[l + 1] > R.off[l]) { q_round[l] = 0; q_local[l] = l; }
             }
             if (!cur_all) R.queries.swap(cur);
-            kmcpg_free_hits(&hits);
-            out->ms_post += ms_since(Tp);
             cur_all = false;
             if (tries + 1 < tries_max) cur.swap(retry);          // --try-se: read1 only, then read2 only
             else { next_k.insert(next_k.end(), retry.begin(), retry.end()); cur.clear(); }

@@ -538,3 +538,14 @@ def test_cli_index_then_search_roundtrip(oracle, tmp_path):
     _run_cli(["-d", out, fq, "-o", tsv])
     odb = O.DB(r001)
     assert open(tsv).read() == O.format_tsv(odb, ids, odb.search(reads))
+
+
+def test_engine_chunked_round_overlaps_search_and_postfilter(gpu_ctx, oracle, small_db):
+    """> 768 k queries: the engine cuts the round into chunks searched by a second thread while the first filters"""
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    base = helpers.make_reads(O, RSEED + 30, 4000, 40, 30000, GSEED) + helpers.edge_reads(21)
+    reads = (base * 200)[:800000]
+    got = _compare_engine(O, odb, gpu_ctx, reads)
+    assert len(got.matches) > 400000
