@@ -127,6 +127,21 @@ int kmcpg_search_batch_device(kmcpg_ctx *ctx, const kmcpg_search_params *p, cons
                               const uint64_t *d_off, uint32_t n_seqs, uint64_t seq_bytes, kmcpg_hits *out);
 void kmcpg_free_hits(kmcpg_hits *h);
 
+/* streaming form: the batch is processed in parts (≈ 250 k reads); `cb` is called on the calling thread, in query
+ * order, as soon as a part's hits are in host memory — while the GPU is already probing the next parts — so a host
+ * can post-process (tCov/FPR/sort, TSV formatting) in the shadow of the device work.  The pointers are valid until
+ * the call returns; `hits[i].query` is the index inside the batch.  The callback must not call back into this ctx. */
+typedef struct {
+    uint32_t first_query, n_queries;
+    const int32_t *n_kmers;      /* [n_queries], of first_query.. */
+    const int32_t *query_len;    /* [n_queries] */
+    const kmcpg_hit *hits;       /* sorted by (query, target) */
+    uint64_t n_hits;
+} kmcpg_part;
+typedef void (*kmcpg_part_cb)(void *user, const kmcpg_part *part);
+int kmcpg_search_batch_cb(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *seq, const uint64_t *off,
+                          uint32_t n_seqs, kmcpg_part_cb cb, void *user, kmcpg_hits *summary /* timings and totals; arrays stay valid until freed */);
+
 /* pinned host memory for batch buffers (so the H2D copy of kmcpg_search_batch runs at full PCIe speed) */
 int kmcpg_host_alloc(void **p, size_t bytes);
 int kmcpg_host_free(void *p);

@@ -61,6 +61,14 @@ class Hits(C.Structure):
                 ("kernel_launches", C.c_uint32), ("_priv", C.c_void_p)]
 
 
+class Part(C.Structure):
+    _fields_ = [("first_query", C.c_uint32), ("n_queries", C.c_uint32), ("n_kmers", C.POINTER(C.c_int32)), ("query_len", C.POINTER(C.c_int32)),
+                ("hits", C.POINTER(Hit)), ("n_hits", C.c_uint64)]
+
+
+PART_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Part))
+
+
 class SketchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("canonical", C.c_int32), ("scaled", C.c_int32), ("scale", C.c_uint32),
                 ("minimizer", C.c_int32), ("minimizer_w", C.c_uint32), ("syncmer", C.c_int32), ("syncmer_s", C.c_uint32)]
@@ -104,7 +112,7 @@ class SynthDb(C.Structure):
 # every symbol include/kmcp_gpu.h declares (checked by tests/test_abi.py without a GPU)
 ABI_SYMBOLS = [
     "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
-    "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_free_hits", "kmcpg_host_alloc",
+    "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_free_hits", "kmcpg_host_alloc",
     "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
     "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search",
     "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_build_synth_db", "kmcpg_write_block",
@@ -137,6 +145,7 @@ def load() -> C.CDLL:
     L.kmcpg_default_params.restype = None
     L.kmcpg_search_batch.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, C.POINTER(Hits)]
     L.kmcpg_search_batch_device.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, C.c_uint64, C.POINTER(Hits)]
+    L.kmcpg_search_batch_cb.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, PART_CB, vp, C.POINTER(Hits)]
     L.kmcpg_free_hits.argtypes = [C.POINTER(Hits)]
     L.kmcpg_free_hits.restype = None
     L.kmcpg_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -323,6 +332,22 @@ class Context:
         else:
             self._check(self._L.kmcpg_search_batch(self._h, C.byref(params), seq_ptr, off_ptr, n_seqs, C.byref(h)))
         return self._take_hits(h, copy)
+
+    def search_batch_streaming(self, buf: np.ndarray, off: np.ndarray, params: Optional[SearchParams] = None):
+        """kmcpg_search_batch_cb: returns (list of per-part (first_query, n_queries, n_kmers, hits) copies, summary)"""
+        p = params or self.default_params()
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        parts = []
+
+        def cb(_user, part):
+            pt = part.contents
+            parts.append((pt.first_query, pt.n_queries, _np_from(pt.n_kmers, pt.n_queries, 4, np.int32),
+                          _np_from(pt.hits, pt.n_hits, C.sizeof(Hit), HIT_DTYPE)))
+
+        h = Hits()
+        self._check(self._L.kmcpg_search_batch_cb(self._h, C.byref(p), buf.ctypes.data, off.ctypes.data, len(off) - 1, PART_CB(cb), None, C.byref(h)))
+        return parts, self._take_hits(h)
 
     def generate_kmers(self, buf: np.ndarray, off: np.ndarray, sp: SketchParams) -> Tuple[np.ndarray, np.ndarray]:
         buf = np.ascontiguousarray(buf, dtype=np.uint8)

@@ -463,10 +463,27 @@ static int cut_parts(kmcpg_ctx *ctx, const uint64_t *off, uint32_t n_seqs, uint3
 }
 
 // runs the two-deep pipeline over the parts
+struct PartDone { uint32_t first_query, nq; uint64_t hit_dst, n_hits; cudaEvent_t ev; };
+
 static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const std::vector<Part> &parts, const uint8_t *host_seq, const uint64_t *host_off,
-                     const uint8_t *d_seq, const uint64_t *d_off, HitsPriv &res, Timing &tm) {
+                     const uint8_t *d_seq, const uint64_t *d_off, HitsPriv &res, Timing &tm, kmcpg_part_cb cb, void *user) {
     const uint32_t step = p.paired ? 2 : 1;
     int rc = KMCPG_OK;
+    std::vector<PartDone> done;
+    size_t delivered = 0;
+    // hands every part whose results have reached the host to the caller, in order (up to and including `upto`)
+    auto deliver = [&](size_t upto) -> int {
+        for (; cb && delivered < done.size() && delivered <= upto; delivered++) {
+            const PartDone &d = done[delivered];
+            CU(cudaEventSynchronize(d.ev));
+            kmcpg_part pt;
+            pt.first_query = d.first_query; pt.n_queries = d.nq;
+            pt.n_kmers = (const int32_t *)res.nk.p + d.first_query; pt.query_len = (const int32_t *)res.ql.p + d.first_query;
+            pt.hits = (const kmcpg_hit *)res.hits.p + d.hit_dst; pt.n_hits = d.n_hits;
+            cb(user, &pt);
+        }
+        return KMCPG_OK;
+    };
     for (size_t i = 0; i <= parts.size(); i++) {
         if (i < parts.size()) {
             WorkSet &w = ctx->ws[i & 1];
@@ -480,12 +497,17 @@ static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const 
             if (rc) return rc;
         }
         if (i >= 1) {
-            rc = finish_probes(ctx, ctx->ws[(i - 1) & 1], p, res, tm);
+            WorkSet &w = ctx->ws[(i - 1) & 1];
+            rc = finish_probes(ctx, w, p, res, tm);
             if (rc) return rc;
+            done.push_back({w.sb.query_base, w.nq, w.hit_dst, w.n_hits, w.ev_b});
+            // part i-2 has certainly landed by now (its copies were queued a whole probe kernel ago): give it to the caller
+            // while the GPU works on part i
+            if (i >= 2) { rc = deliver(i - 2); if (rc) return rc; }
         }
     }
     for (auto &w : ctx->ws) { rc = wait_part(ctx, w); if (rc) return rc; }
-    return KMCPG_OK;
+    return deliver(parts.size());
 }
 
 static void abort_parts(kmcpg_ctx *ctx) {
@@ -496,7 +518,7 @@ static void abort_parts(kmcpg_ctx *ctx) {
 }
 
 static int search_common(kmcpg_ctx *ctx, const kmcpg_search_params *p, int k, const uint64_t *host_off, uint32_t n_seqs, const uint8_t *host_seq,
-                         const uint8_t *d_seq, const uint64_t *d_off, kmcpg_hits *out) {
+                         const uint8_t *d_seq, const uint64_t *d_off, kmcpg_hits *out, kmcpg_part_cb cb = nullptr, void *user = nullptr) {
     auto t0 = std::chrono::steady_clock::now();
     const uint32_t launches0 = ctx->launches;
     const uint32_t step = p->paired ? 2 : 1;
@@ -509,7 +531,7 @@ static int search_common(kmcpg_ctx *ctx, const kmcpg_search_params *p, int k, co
     if (!rc) rc = pin_acquire(ctx, std::max<uint32_t>(priv->nq, 1) * 4ull, priv->ql);
     if (!rc) rc = pin_acquire(ctx, std::max<uint64_t>(1u << 16, 2ull * priv->nq) * sizeof(kmcpg_hit), priv->hits);
     Timing tm;
-    if (!rc) rc = run_parts(ctx, *p, k, parts, host_seq, host_off, d_seq, d_off, *priv, tm);
+    if (!rc) rc = run_parts(ctx, *p, k, parts, host_seq, host_off, d_seq, d_off, *priv, tm, cb, user);
     if (rc) { abort_parts(ctx); drop_priv(priv); return rc; }
     float ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     fill_out(out, priv, tm, ms_total, ctx->launches - launches0);
@@ -700,6 +722,18 @@ int kmcpg_search_batch(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8
     CU(cudaSetDevice(ctx->device));
     memset(out, 0, sizeof(*out));
     return search_common(ctx, p, k, off, n_seqs, seq ? seq : (const uint8_t *)"", nullptr, nullptr, out);
+}
+
+int kmcpg_search_batch_cb(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs, kmcpg_part_cb cb, void *user,
+                          kmcpg_hits *out) {
+    int k = 0;
+    int rc = check_search_args(ctx, p, seq, off, n_seqs, out, &k);
+    if (rc) return rc;
+    if (!cb) return fail(ctx, KMCPG_EINVAL, "callback is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    return search_common(ctx, p, k, off, n_seqs, seq ? seq : (const uint8_t *)"", nullptr, nullptr, out, cb, user);
 }
 
 int kmcpg_search_batch_device(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *d_seq, const uint64_t *d_off, uint32_t n_seqs,

@@ -11,7 +11,6 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <future>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -112,7 +111,7 @@ struct Round {
 };
 
 // filters + sorts the hits of local queries [lo, hi) (U:7466-7491, U:273-311); matches are written densely from dst
-size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_hits &hits, const uint64_t *hoff, const uint32_t *cur, uint32_t q0, const double *tsize,
+size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_part &hits, const uint64_t *hoff, const uint32_t *cur, uint32_t q0, const double *tsize,
                    FprCache *cache, uint32_t lo, uint32_t hi, kmcpg_match *dst, uint32_t *count) {
     const Less less{o->sort_by};
     size_t w = 0;
@@ -231,11 +230,12 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
             if (!single && q_round.empty()) { q_round.assign(nq, -1); q_local.assign(nq, 0); }
             std::vector<uint32_t> retry;
 
-            // filters the hits of local queries [q0, q0+ln) of this round and appends the matches to R
-            auto absorb = [&](const kmcpg_hits &hits, uint32_t q0, uint32_t ln) {
+            // filters the hits of one delivered part (local queries [q0, q0+ln) of this round) and appends the matches to R
+            auto absorb = [&](const kmcpg_part &hits) {
                 auto Tp = std::chrono::steady_clock::now();
+                const uint32_t q0 = hits.first_query, ln = hits.n_queries;
                 hoff.assign((size_t)ln + 1, 0);
-                for (uint64_t i = 0; i < hits.n_hits; i++) hoff[hits.hits[i].query + 1]++;      // hits are sorted by query
+                for (uint64_t i = 0; i < hits.n_hits; i++) hoff[hits.hits[i].query - q0 + 1]++;  // hits are sorted by query
                 for (uint32_t i = 0; i < ln; i++) hoff[i + 1] += hoff[i];
                 count.resize(ln);
                 const size_t need = (R.n + std::max<uint64_t>(hits.n_hits, 1)) * sizeof(kmcpg_match);
@@ -288,28 +288,18 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                     if (cp[l]) { if (!q_round.empty()) { q_round[q] = ridx; q_local[q] = gl; } }
                     else retry.push_back(q);
                 }
-                out->ms_gpu_total += hits.ms_total; out->probe_row_bytes += hits.probe_row_bytes; out->kernel_launches += hits.kernel_launches;
                 out->ms_post += ms_since(Tp);
             };
 
-            // big rounds are cut into chunks: the device searches chunk c+1 (second thread) while this thread filters chunk c
-            const uint32_t CHUNK_Q = 384u << 10;
-            const uint32_t n_chunks = ln_total > 2 * CHUNK_Q ? (ln_total + CHUNK_Q - 1) / CHUNK_Q : 1;
-            auto run_search = [&](uint32_t c, kmcpg_hits *h) -> int {
-                const uint32_t a = (uint32_t)((uint64_t)ln_total * c / n_chunks), b = (uint32_t)((uint64_t)ln_total * (c + 1) / n_chunks);
-                return kmcpg_search_batch(ctx, &p, bs, bo + (size_t)a * step, (b - a) * step, h);
-            };
+            // one streaming device call per round: every part is filtered here while the GPU already probes the next ones
             {
-                kmcpg_hits hits[2];
-                std::future<int> fut = std::async(std::launch::async, run_search, 0u, &hits[0]);
-                for (uint32_t c = 0; c < n_chunks; c++) {
-                    rc = fut.get();
-                    if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
-                    if (c + 1 < n_chunks) fut = std::async(std::launch::async, run_search, c + 1, &hits[(c + 1) & 1]);
-                    const uint32_t a = (uint32_t)((uint64_t)ln_total * c / n_chunks), b = (uint32_t)((uint64_t)ln_total * (c + 1) / n_chunks);
-                    absorb(hits[c & 1], a, b - a);
-                    kmcpg_free_hits(&hits[c & 1]);
-                }
+                struct CbCtx { decltype(absorb) *fn; } cbctx{&absorb};
+                kmcpg_hits summary;
+                rc = kmcpg_search_batch_cb(ctx, &p, bs, bo, ln_total * step,
+                                           [](void *u, const kmcpg_part *part) { (*((CbCtx *)u)->fn)(*part); }, &cbctx, &summary);
+                if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
+                out->ms_gpu_total += summary.ms_total; out->probe_row_bytes += summary.probe_row_bytes; out->kernel_launches += summary.kernel_launches;
+                kmcpg_free_hits(&summary);
             }
             if (single && (tries_max > 1 || info.n_ks > 1) && !retry.empty()) {
                 // more rounds will follow: remember where round 0 put every matched query

@@ -549,3 +549,19 @@ def test_engine_chunked_round_overlaps_search_and_postfilter(gpu_ctx, oracle, sm
     reads = (base * 200)[:800000]
     got = _compare_engine(O, odb, gpu_ctx, reads)
     assert len(got.matches) > 400000
+
+
+def test_streaming_parts_equal_the_batch_result(gpu_ctx, oracle, small_db):
+    """kmcpg_search_batch_cb delivers the same hits, part by part and in query order"""
+    from kmcp_b200 import api
+    O = oracle
+    gpu_ctx.open_db(small_db)
+    reads = (helpers.make_reads(O, RSEED + 40, 3000, 40, 30000, GSEED) * 120)[:330000]      # several parts
+    buf, off = api.pack_seqs(reads)
+    whole = gpu_ctx.search_batch(buf, off)
+    parts, summary = gpu_ctx.search_batch_streaming(buf, off)
+    assert len(parts) >= 2 and parts[0][0] == 0
+    assert sum(p[1] for p in parts) == len(reads) and all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(len(parts) - 1))
+    assert np.array_equal(np.concatenate([p[3] for p in parts]), whole.hits)
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), whole.n_kmers)
+    assert np.array_equal(summary.hits, whole.hits)
