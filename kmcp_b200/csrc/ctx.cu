@@ -65,7 +65,7 @@ void free_db(kmcpg_ctx *ctx) {
 
 void WorkSet::release() {
     for (DevBuf *b : {&seq, &off, &slot_cnt, &slot_off, &codes, &codes2, &locs, &ncodes, &qlen, &nk, &neff, &thresh, &hkeys, &hvals, &hkeys2, &hvals2,
-                      &hits, &counters, &tmp, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off})
+                      &hits, &counters, &tmp, &tmp2, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off})
         b->release();
     h_off.release(); h_cnt.release();
     for (cudaEvent_t *e : {&ev_in, &ev_a0, &ev_hash, &ev_a, &ev_cnt, &ev_sorted, &ev_b}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
@@ -355,6 +355,10 @@ static int finish_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &
 
     const uint64_t n_hits = w.n_hits;
     w.hit_dst = res.nh;
+    // the part's probes are done (the host has just read their counters): sort + pack on the post stream, so the results
+    // reach the host while the compute stream is already busy with the next part's probe kernel
+    cudaStream_t ps = ctx->post_st;
+    CU(cudaStreamWaitEvent(ps, w.ev_a, 0));
     if (n_hits) {
         int rc = grow_hits(ctx, res, res.nh + n_hits);
         if (rc) return rc;
@@ -362,14 +366,14 @@ static int finish_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &
         int qbits = 1; while ((1ull << qbits) < w.nq) qbits++;
         size_t t3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
-                                        (int64_t)n_hits, 0, 32 + qbits, st);
-        CU(w.tmp.ensure(t3));
-        CU(cub::DeviceRadixSort::SortPairs(w.tmp.p, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
-                                           (int64_t)n_hits, 0, 32 + qbits, st));
-        CU(launch_pack_hits(w.hkeys2.as<uint64_t>(), w.hvals2.as<uint32_t>(), n_hits, w.sb.query_base, w.hits.as<kmcpg_hit>(), st));
+                                        (int64_t)n_hits, 0, 32 + qbits, ps);
+        CU(w.tmp2.ensure(t3));
+        CU(cub::DeviceRadixSort::SortPairs(w.tmp2.p, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
+                                           (int64_t)n_hits, 0, 32 + qbits, ps));
+        CU(launch_pack_hits(w.hkeys2.as<uint64_t>(), w.hvals2.as<uint32_t>(), n_hits, w.sb.query_base, w.hits.as<kmcpg_hit>(), ps));
         ctx->launches += 4;
     }
-    CU(cudaEventRecord(w.ev_sorted, st));
+    CU(cudaEventRecord(w.ev_sorted, ps));
     CU(cudaStreamWaitEvent(ctx->copy_st, w.ev_sorted, 0));
     if (n_hits) CU(cudaMemcpyAsync((kmcpg_hit *)res.hits.p + res.nh, w.hits.p, n_hits * sizeof(kmcpg_hit), cudaMemcpyDeviceToHost, ctx->copy_st));
     CU(cudaMemcpyAsync((int32_t *)res.nk.p + w.sb.query_base, w.nk.p, w.nq * 4ull, cudaMemcpyDeviceToHost, ctx->copy_st));
@@ -501,9 +505,10 @@ static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const 
             rc = finish_probes(ctx, w, p, res, tm);
             if (rc) return rc;
             done.push_back({w.sb.query_base, w.nq, w.hit_dst, w.n_hits, w.ev_b});
-            // part i-2 has certainly landed by now (its copies were queued a whole probe kernel ago): give it to the caller
-            // while the GPU works on part i
-            if (i >= 2) { rc = deliver(i - 2); if (rc) return rc; }
+            // its sort + copies run beside the probe of part i: hand part i-1 to the caller as soon as it has landed, while
+            // the GPU keeps working
+            rc = deliver(i - 1);
+            if (rc) return rc;
         }
     }
     for (auto &w : ctx->ws) { rc = wait_part(ctx, w); if (rc) return rc; }
@@ -514,6 +519,7 @@ static void abort_parts(kmcpg_ctx *ctx) {
     cudaStreamSynchronize(ctx->st);
     cudaStreamSynchronize(ctx->copy_st);
     cudaStreamSynchronize(ctx->in_st);
+    cudaStreamSynchronize(ctx->post_st);
     for (auto &w : ctx->ws) w.busy = false;
 }
 
@@ -574,6 +580,7 @@ int kmcpg_create(int device, kmcpg_ctx **out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->own_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->in_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->post_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     ctx->st = ctx->own_st;
     if ((e = ctx->h_small.ensure(256)) != cudaSuccess) return bail(e, "cudaMallocHost");
     *out = ctx;
@@ -594,6 +601,8 @@ int kmcpg_close(kmcpg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     cudaStreamSynchronize(ctx->copy_st);
+    cudaStreamSynchronize(ctx->in_st);
+    cudaStreamSynchronize(ctx->post_st);
     free_db(ctx);
     for (auto &w : ctx->ws) w.release();
     for (DevBuf *b : {&ctx->d_tmp, &ctx->d_dense, &ctx->d_scal, &ctx->d_genome}) b->release();
@@ -603,6 +612,7 @@ int kmcpg_close(kmcpg_ctx *ctx) {
     if (ctx->own_st) cudaStreamDestroy(ctx->own_st);
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     if (ctx->in_st) cudaStreamDestroy(ctx->in_st);
+    if (ctx->post_st) cudaStreamDestroy(ctx->post_st);
     delete ctx;
     return KMCPG_OK;
 }

@@ -80,7 +80,7 @@ struct SubBatch {
 // (hit count round trip, result copies) hide behind the kernels of part i+1
 struct WorkSet {
     DevBuf seq, off, slot_cnt, slot_off, codes, codes2, locs, ncodes, qlen, nk, neff, thresh;
-    DevBuf hkeys, hvals, hkeys2, hvals2, hits, counters, tmp, segb, sege;
+    DevBuf hkeys, hvals, hkeys2, hvals2, hits, counters, tmp, tmp2, segb, sege;
     DevBuf ck, cs, cs_cnt, cs_off;      // sketch selection: per-position k-mer / s-mer hashes
     HostBuf h_off, h_cnt;
     cudaEvent_t ev_in = nullptr, ev_a0 = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_cnt = nullptr, ev_sorted = nullptr, ev_b = nullptr;
@@ -103,6 +103,7 @@ struct kmcpg_ctx {
     cudaStream_t st = nullptr;        // compute stream (own_st or the caller's)
     cudaStream_t own_st = nullptr;
     cudaStream_t copy_st = nullptr;   // device→host transfers that overlap the kernels
+    cudaStream_t post_st = nullptr;   // hit-list sort + pack of a finished part (tiny kernels, concurrent with the next probe)
     cudaStream_t in_st = nullptr;     // host→device input staging (its own queue, so it never waits behind result copies)
     bool has_db = false;
     kmcpg::DbMeta meta;

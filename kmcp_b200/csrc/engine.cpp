@@ -246,7 +246,7 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                     R.buf = nb;
                 }
                 kmcpg_match *M = R.matches() + R.n;
-                int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 32768 + 1));
+                int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 12288 + 1));
                 std::vector<uint32_t> bounds(T + 1, ln);
                 std::vector<size_t> produced(T, 0);
                 bounds[0] = 0;
