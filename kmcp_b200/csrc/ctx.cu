@@ -580,7 +580,11 @@ int kmcpg_create(int device, kmcpg_ctx **out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->own_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->in_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-    if ((e = cudaStreamCreateWithFlags(&ctx->post_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    {   // the post stream gets the highest priority: its tiny sort/pack kernels slip in as soon as probe CTAs retire
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&ctx->post_st, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    }
     ctx->st = ctx->own_st;
     if ((e = ctx->h_small.ensure(256)) != cudaSuccess) return bail(e, "cudaMallocHost");
     *out = ctx;

@@ -10,7 +10,10 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <future>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -96,6 +99,66 @@ void big_release(BigBuf &b) {
     }
 }
 
+// A few persistent workers: spawning threads per part costs more than filtering a part's hits.
+class WorkerPool {
+  public:
+    explicit WorkerPool(int n) {
+        for (int i = 0; i < n; i++) th_.emplace_back([this, i] { run(i); });
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return (int)th_.size(); }
+    // runs fn(0..n-1); the caller executes task 0, workers the rest (n-1 <= size())
+    void parallel(int n, const std::function<void(int)> &fn) {
+        if (n <= 1) { if (n == 1) fn(0); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; pending_ = n - 1; gen_++;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void run(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn = nullptr;
+            int task = -1;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                if (fn_ && id + 1 < n_) { fn = fn_; task = id + 1; }
+            }
+            if (fn) {
+                (*fn)(task);
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+WorkerPool &pool() {
+    static WorkerPool p(std::max(1, std::min((int)std::thread::hardware_concurrency() - 1, 15)));
+    return p;
+}
+
 struct ResPriv {
     BigBuf query_len, n_kmers, k_used, match_off, matches;
     ~ResPriv() { big_release(query_len); big_release(n_kmers); big_release(k_used); big_release(match_off); big_release(matches); }
@@ -110,19 +173,22 @@ struct Round {
     kmcpg_match *matches() const { return (kmcpg_match *)buf.p; }
 };
 
-// filters + sorts the hits of local queries [lo, hi) (U:7466-7491, U:273-311); matches are written densely from dst
-size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_part &hits, const uint64_t *hoff, const uint32_t *cur, uint32_t q0, const double *tsize,
-                   FprCache *cache, uint32_t lo, uint32_t hi, kmcpg_match *dst, uint32_t *count) {
+// filters + sorts the hits [h0, h1) of a part (U:7466-7491, U:273-311).  The range starts and ends on query boundaries;
+// hits are sorted by query, so the groups are found on the fly.  Matches are written densely from dst; count[] (zeroed by
+// the caller) receives the number of matches of every query that has any.
+size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_part &hits, uint64_t h0, uint64_t h1, const uint32_t *cur, uint32_t round_q0,
+                   const double *tsize, FprCache *cache, kmcpg_match *dst, uint32_t *count) {
     const Less less{o->sort_by};
+    const uint32_t q0 = hits.first_query;                              // base of hits[].query inside this device call
     size_t w = 0;
-    for (uint32_t l = lo; l < hi; l++) {
-        const int n = hits.n_kmers[l];
-        count[l] = 0;
-        if (n == 0 || hoff[l] == hoff[l + 1]) continue;
-        const uint32_t q = cur ? cur[l] : q0 + l;
+    uint64_t i = h0;
+    while (i < h1) {
+        const uint32_t lq = hits.hits[i].query - q0;                  // index inside the part
+        const int n = hits.n_kmers[lq];
+        const uint32_t q = cur ? cur[lq] : round_q0 + lq;
         const double nh = (double)n;
         const size_t start = w;
-        for (uint64_t i = hoff[l]; i < hoff[l + 1]; i++) {
+        for (; i < h1 && hits.hits[i].query - q0 == lq; i++) {
             const kmcpg_hit &h = hits.hits[i];
             const double c = (double)h.count, sz = tsize[h.target];
             const double tcov = c / sz;
@@ -136,15 +202,15 @@ size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_part &hits, const uin
         size_t cnt = w - start;
         if (cnt > 1 && !o->do_not_sort) std::sort(dst + start, dst + w, less);     // U:273-282
         if (cnt > 0 && o->top_n_scores > 0 && !o->do_not_sort) {     // U:285-311 (kept verbatim, including [:i+1])
-            int nsc = 0; double pscore = 1024; size_t i = 0; bool broke = false;
-            for (i = 0; i < cnt; i++) {
-                const kmcpg_match &m = dst[start + i];
+            int nsc = 0; double pscore = 1024; size_t j = 0; bool broke = false;
+            for (j = 0; j < cnt; j++) {
+                const kmcpg_match &m = dst[start + j];
                 double score = o->sort_by == 0 ? m.qcov : (o->sort_by == 1 ? m.tcov : m.jacc);
                 if (score < pscore) { nsc++; if (nsc > o->top_n_scores) { broke = true; break; } pscore = score; }
             }
-            if (broke) { cnt = i + 1; w = start + cnt; }
+            if (broke) { cnt = j + 1; w = start + cnt; }
         }
-        count[l] = (uint32_t)cnt;
+        count[lq] = (uint32_t)cnt;
     }
     return w;
 }
@@ -184,11 +250,11 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
     uint64_t *r_off = (uint64_t *)priv->match_off.p;
     const int tries_max = (o->try_se && o->paired) ? 3 : 1;
     int threads = o->threads > 0 ? o->threads : (int)std::thread::hardware_concurrency();
-    threads = std::max(1, std::min(threads, 16));
+    threads = std::max(1, std::min(threads, pool().size() + 1));
 
     // scratch that survives between calls of this thread (no page faults after the first batch)
-    static thread_local std::vector<uint64_t> hoff;
-    static thread_local std::vector<uint32_t> count;
+    static thread_local std::vector<uint32_t> tl_count;
+    std::vector<uint32_t> &count = tl_count;      // a plain reference: the filter thread must use THIS thread's scratch
     std::vector<Round> rounds;
     std::vector<uint32_t> pending;                // empty + all_pending = every query
     bool all_pending = true;
@@ -231,13 +297,10 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
             std::vector<uint32_t> retry;
 
             // filters the hits of one delivered part (local queries [q0, q0+ln) of this round) and appends the matches to R
-            auto absorb = [&](const kmcpg_part &hits) {
+            auto absorb = [&](const kmcpg_part &hits, uint32_t q0 /* position of the part's first query inside the round */) {
                 auto Tp = std::chrono::steady_clock::now();
-                const uint32_t q0 = hits.first_query, ln = hits.n_queries;
-                hoff.assign((size_t)ln + 1, 0);
-                for (uint64_t i = 0; i < hits.n_hits; i++) hoff[hits.hits[i].query - q0 + 1]++;  // hits are sorted by query
-                for (uint32_t i = 0; i < ln; i++) hoff[i + 1] += hoff[i];
-                count.resize(ln);
+                const uint32_t ln = hits.n_queries;
+                count.assign(ln, 0);
                 const size_t need = (R.n + std::max<uint64_t>(hits.n_hits, 1)) * sizeof(kmcpg_match);
                 if (R.buf.cap < need) {
                     BigBuf nb = big_acquire(need + need / 2);
@@ -246,60 +309,76 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                     R.buf = nb;
                 }
                 kmcpg_match *M = R.matches() + R.n;
-                int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, (hits.n_hits + ln / 8) / 12288 + 1));
-                std::vector<uint32_t> bounds(T + 1, ln);
+                int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)threads, hits.n_hits / 8192 + 1));
+                // split the hit list evenly, moving every cut forward to the next query boundary
+                std::vector<uint64_t> cut(T + 1, hits.n_hits);
                 std::vector<size_t> produced(T, 0);
-                bounds[0] = 0;
-                for (int t = 1; t < T; t++) {            // split by hits so the threads get equal work
-                    uint64_t want = hits.n_hits * (uint64_t)t / T;
-                    bounds[t] = (uint32_t)(std::lower_bound(hoff.begin(), hoff.end(), want) - hoff.begin());
-                    if (bounds[t] > ln) bounds[t] = ln;
-                    if (bounds[t] < bounds[t - 1]) bounds[t] = bounds[t - 1];
+                cut[0] = 0;
+                for (int t = 1; t < T; t++) {
+                    uint64_t c = std::max<uint64_t>(cut[t - 1], hits.n_hits * (uint64_t)t / T);
+                    while (c > 0 && c < hits.n_hits && hits.hits[c].query == hits.hits[c - 1].query) c++;
+                    cut[t] = c;
                 }
-                // every thread writes at the hit offset of its first query: no overlap, compaction only if a filter dropped hits
-                const uint64_t *hp = hoff.data();
+                // every thread writes at the index of its first hit: no overlap, compaction only if a filter dropped hits
                 uint32_t *cp = count.data();
                 const uint32_t *lcur = curp ? curp + q0 : nullptr;
-                auto work = [&](int t) {
-                    produced[t] = post_filter(o, hits, hp, lcur, q0, tsize, cache, bounds[t], bounds[t + 1], M + hp[bounds[t]], cp);
-                };
-                if (T == 1) work(0);
-                else {
-                    std::vector<std::thread> th;
-                    for (int t = 1; t < T; t++) th.emplace_back(work, t);
-                    work(0);
-                    for (auto &t : th) t.join();
-                }
+                auto work = [&](int t) { produced[t] = post_filter(o, hits, cut[t], cut[t + 1], lcur, q0, tsize, cache, M + cut[t], cp); };
+                pool().parallel(T, work);
                 size_t w = produced[0];
                 for (int t = 1; t < T; t++) {
-                    if (produced[t] && w != hp[bounds[t]]) memmove(M + w, M + hp[bounds[t]], produced[t] * sizeof(kmcpg_match));
+                    if (produced[t] && w != cut[t]) memmove(M + w, M + cut[t], produced[t] * sizeof(kmcpg_match));
                     w += produced[t];
                 }
                 R.n += w;
-                for (uint32_t l = 0; l < ln; l++) {
-                    const uint32_t gl = q0 + l;                                    // index inside the round
-                    const uint32_t q = curp ? curp[gl] : gl;
-                    const int n = hits.n_kmers[l];
-                    R.off[gl + 1] = R.off[gl] + cp[l];
-                    r_qlen[q] = hits.query_len[l];
-                    r_k[q] = k;
-                    if (n == 0) { if (tries == 0) r_nk[q] = 0; continue; }         // U:778-786, U:854-869: final, unmatched
-                    r_nk[q] = n;
-                    if (cp[l]) { if (!q_round.empty()) { q_round[q] = ridx; q_local[q] = gl; } }
-                    else retry.push_back(q);
+                const bool more_rounds_possible = tries + 1 < tries_max || ik + 1 < info.n_ks;
+                if (!curp && !more_rounds_possible && q_round.empty()) {
+                    // the common case (one k, no --try-se, every query in the round): bulk copies, no per-query bookkeeping
+                    memcpy(r_qlen + q0, hits.query_len, (size_t)ln * 4);
+                    memcpy(r_nk + q0, hits.n_kmers, (size_t)ln * 4);
+                    std::fill(r_k + q0, r_k + q0 + ln, (int32_t)k);
+                    uint64_t acc = R.off[q0];
+                    for (uint32_t l = 0; l < ln; l++) { acc += cp[l]; R.off[q0 + l + 1] = acc; }
+                } else {
+                    for (uint32_t l = 0; l < ln; l++) {
+                        const uint32_t gl = q0 + l;                                    // index inside the round
+                        const uint32_t q = curp ? curp[gl] : gl;
+                        const int n = hits.n_kmers[l];
+                        R.off[gl + 1] = R.off[gl] + cp[l];
+                        r_qlen[q] = hits.query_len[l];
+                        r_k[q] = k;
+                        if (n == 0) { if (tries == 0) r_nk[q] = 0; continue; }         // U:778-786, U:854-869: final, unmatched
+                        r_nk[q] = n;
+                        if (cp[l]) { if (!q_round.empty()) { q_round[q] = ridx; q_local[q] = gl; } }
+                        else retry.push_back(q);
+                    }
                 }
                 out->ms_post += ms_since(Tp);
             };
 
-            // one streaming device call per round: every part is filtered here while the GPU already probes the next ones
+            // big rounds are cut into chunks: a second thread drives the device through chunk c+1 while this thread filters
+            // chunk c (kmcpg_search_batch_cb offers the same overlap at part granularity to hosts that prefer a callback)
+            const uint32_t CHUNK_Q = 320u << 10;
+            const uint32_t n_chunks = ln_total > 2 * CHUNK_Q ? (ln_total + CHUNK_Q - 1) / CHUNK_Q : 1;
+            auto chunk_lo = [&](uint32_t c) { return (uint32_t)((uint64_t)ln_total * c / n_chunks); };
+            auto run_search = [&](uint32_t c, kmcpg_hits *h) -> int {
+                const uint32_t a = chunk_lo(c), b = chunk_lo(c + 1);
+                return kmcpg_search_batch(ctx, &p, bs, bo + (size_t)a * step, (b - a) * step, h);
+            };
             {
-                struct CbCtx { decltype(absorb) *fn; } cbctx{&absorb};
-                kmcpg_hits summary;
-                rc = kmcpg_search_batch_cb(ctx, &p, bs, bo, ln_total * step,
-                                           [](void *u, const kmcpg_part *part) { (*((CbCtx *)u)->fn)(*part); }, &cbctx, &summary);
-                if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
-                out->ms_gpu_total += summary.ms_total; out->probe_row_bytes += summary.probe_row_bytes; out->kernel_launches += summary.kernel_launches;
-                kmcpg_free_hits(&summary);
+                kmcpg_hits hits[2];
+                std::future<int> fut = std::async(std::launch::async, run_search, 0u, &hits[0]);
+                for (uint32_t c = 0; c < n_chunks; c++) {
+                    rc = fut.get();
+                    if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
+                    if (c + 1 < n_chunks) fut = std::async(std::launch::async, run_search, c + 1, &hits[(c + 1) & 1]);
+                    const kmcpg_hits &h = hits[c & 1];
+                    kmcpg_part part;
+                    part.first_query = 0; part.n_queries = h.n_queries; part.n_kmers = h.n_kmers; part.query_len = h.query_len;
+                    part.hits = h.hits; part.n_hits = h.n_hits;
+                    absorb(part, chunk_lo(c));
+                    out->ms_gpu_total += h.ms_total; out->probe_row_bytes += h.probe_row_bytes; out->kernel_launches += h.kernel_launches;
+                    kmcpg_free_hits(&hits[c & 1]);
+                }
             }
             if (single && (tries_max > 1 || info.n_ks > 1) && !retry.empty()) {
                 // more rounds will follow: remember where round 0 put every matched query
