@@ -64,3 +64,37 @@ def test_default_params_are_the_reference_defaults():
     o = api.EngineOpts()
     L.kmcpg_default_engine_opts(C.byref(o))
     assert (o.min_query_cov, o.min_target_cov, o.max_fpr, o.top_n_scores, o.sort_by) == (0.55, 0.0, 0.01, 0, 0)          # S:1066-1093
+
+
+def test_shard_plan_reads_headers_and_reports_format_errors(oracle, tmp_path):
+    """host-only part of kmcpg_open_db: __db.yml + .uniki header parsing, error codes of X:38-56 / util-db-info.go:118"""
+    import parity_helpers as helpers
+    from kmcp_b200 import api
+    O = oracle
+    sp = O.sketch_params(21)
+    targets = helpers.make_synth_targets(O, sp, 5, 6, 6000, 2, 50)
+    r001 = O.build_db(targets, str(tmp_path / "db"), sp, num_hashes=1, fpr=0.3, block_size=8)       # 12 targets → 2 blocks
+    assert sorted(api.shard_plan(r001, 2)) == [0, 1]
+    blk = os.path.join(r001, "_block001.uniki")
+    raw = open(blk, "rb").read()
+    cases = {"bad magic": (b"XXXXXXXX" + raw[8:], api.KMCPG_EFORMAT), "version": (raw[:8] + bytes([3]) + raw[9:], api.KMCPG_EFORMAT),
+             "truncated rows": (raw[:-100], api.KMCPG_EIO), "truncated header": (raw[:30], api.KMCPG_EIO)}
+    for name, (data, code) in cases.items():
+        open(blk, "wb").write(data)
+        with pytest.raises(api.KmcpGpuError) as e:
+            api.shard_plan(r001, 2)
+        assert e.value.code == code, name
+    open(blk, "wb").write(raw)
+    yml = os.path.join(r001, "__db.yml")
+    txt = open(yml).read()
+    open(yml, "w").write(txt.replace("version: 4", "version: 3", 1))
+    with pytest.raises(api.KmcpGpuError) as e:
+        api.shard_plan(r001, 2)
+    assert e.value.code == api.KMCPG_EFORMAT
+    open(yml, "w").write(txt.replace("hashes: 1", "hashes: 2"))          # blocks say 1 hash: incompatible (U:689-695)
+    with pytest.raises(api.KmcpGpuError) as e:
+        api.shard_plan(r001, 2)
+    assert e.value.code == api.KMCPG_EFORMAT
+    with pytest.raises(api.KmcpGpuError) as e:
+        api.shard_plan(str(tmp_path / "nope"), 2)
+    assert e.value.code == api.KMCPG_EIO
