@@ -45,10 +45,8 @@ uint32_t pitch_for(uint32_t row_bytes) {
 void layout_block(DeviceBlock &b, const BlockMeta &m) {
     b.pitch = pitch_for((uint32_t)m.row_bytes);
     b.row16 = ((uint32_t)m.row_bytes + 15) / 16;
-    uint32_t gmax = 8;                          // a task covers up to 128 B of a row
-    if (const char *e = getenv("KMCPG_PROBE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) gmax = (uint32_t)v; }
     uint32_t g = 1;
-    while (g < b.row16 && g < gmax) g <<= 1;
+    while (g < b.row16 && g < 8) g <<= 1;       // informational: the probe kernel derives its task geometry from row_bytes
     b.G = g;
     b.chunks = (b.row16 + g - 1) / g;
     b.fm = make_fastmod(m.num_sigs);
@@ -261,7 +259,7 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
         CU(cudaEventRecord(w.probe_ev[bi * 3 + 1], st));
         ProbeArgs pa;
         memset(&pa, 0, sizeof(pa));
-        pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row16 = b.row16; pa.lanes_per_task = b.G; pa.chunks = b.chunks;
+        pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = (uint32_t)bm.row_bytes;
         pa.n_names = (uint32_t)bm.n_names; pa.target_base = (uint32_t)bm.target_base; pa.num_hashes = H;
         pa.locs = w.locs.as<uint32_t>(); pa.slot_off = w.slot_off.as<uint64_t>();
         pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = w.nq; pa.paired = p.paired;
@@ -909,7 +907,7 @@ int kmcpg_count_codes(kmcpg_ctx *ctx, const uint64_t *codes, uint64_t n, uint32_
             CU(launch_locs(w.codes.as<uint64_t>(), n, H, b.fm, w.locs.as<uint32_t>(), st));
             ProbeArgs pa;
             memset(&pa, 0, sizeof(pa));
-            pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row16 = b.row16; pa.lanes_per_task = b.G; pa.chunks = b.chunks;
+            pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = (uint32_t)bm.row_bytes;
             pa.n_names = (uint32_t)bm.n_names; pa.target_base = (uint32_t)bm.target_base; pa.num_hashes = H;
             pa.locs = w.locs.as<uint32_t>(); pa.slot_off = w.slot_off.as<uint64_t>();
             pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = 1; pa.paired = 0;

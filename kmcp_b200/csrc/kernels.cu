@@ -492,13 +492,19 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-__device__ __forceinline__ uint4 ld_row16(const uint8_t *p) {
-    // streaming 16-byte load of a bit-matrix row slab: read-only path, do not keep in L1
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
-    return v;
+// W 32-bit words of a bit-matrix row owned by one lane (W = 4: 16-byte slab, W = 2: 8-byte slab)
+template <int W> struct Slab { uint32_t v[W]; };
+
+template <int W>
+__device__ __forceinline__ Slab<W> ld_slab(const uint8_t *p) {
+    // streaming load of a row slab: read-only path, do not keep in L1
+    Slab<W> s;
+    if (W == 4) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[W > 2 ? 2 : 0]), "=r"(s.v[W > 3 ? 3 : 0]) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(s.v[0]), "=r"(s.v[1]) : "l"(p));
+    }
+    return s;
 }
 
 constexpr int PROBE_THREADS = 256;
@@ -514,31 +520,33 @@ __device__ __forceinline__ void load_locs(uint32_t (&L)[PROBE_ROWS * H], const u
         for (int h = 0; h < H; h++) L[u * H + h] = (i + u < n) ? __ldg(lp + (uint64_t)(i + u) * H + h) : LOC_NONE;
 }
 
-// 16-byte slabs of the 8 rows (h rows AND-ed: pand, U:6639-6645); zero for LOC_NONE
-template <int H>
-__device__ __forceinline__ void load_rows(uint4 (&r)[PROBE_ROWS], const uint32_t (&L)[PROBE_ROWS * H], const uint8_t *__restrict__ colbase, uint32_t pitch) {
+// slabs of the 8 rows (h rows AND-ed: pand, U:6639-6645); zero for LOC_NONE
+template <int H, int W>
+__device__ __forceinline__ void load_rows(Slab<W> (&r)[PROBE_ROWS], const uint32_t (&L)[PROBE_ROWS * H], const uint8_t *__restrict__ colbase, uint32_t pitch) {
 #pragma unroll
     for (int u = 0; u < PROBE_ROWS; u++) {
         if (L[u * H] != LOC_NONE) {
-            r[u] = ld_row16(colbase + (uint64_t)L[u * H] * pitch);
+            r[u] = ld_slab<W>(colbase + (uint64_t)L[u * H] * pitch);
 #pragma unroll
             for (int h = 1; h < H; h++) {
-                uint4 t = ld_row16(colbase + (uint64_t)L[u * H + h] * pitch);
-                r[u].x &= t.x; r[u].y &= t.y; r[u].z &= t.z; r[u].w &= t.w;
+                const Slab<W> t = ld_slab<W>(colbase + (uint64_t)L[u * H + h] * pitch);
+#pragma unroll
+                for (int w = 0; w < W; w++) r[u].v[w] &= t.v[w];
             }
         } else {
-            r[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int w = 0; w < W; w++) r[u].v[w] = 0;
         }
     }
 }
 
-// Harley–Seal: 8 one-bit inputs + planes 0..2 → planes 0..2 and one weight-8 carry rippled into planes 3..P-1
-template <int P>
-__device__ __forceinline__ void csa8(uint32_t (&c)[P][4], const uint4 (&r)[PROBE_ROWS]) {
+// Harley–Seal: 8 one-bit inputs + planes 0..2 → planes 0..2 and one weight-8 carry rippled into planes 3..7
+template <int W>
+__device__ __forceinline__ void csa8(uint32_t (&c)[8][W], const Slab<W> (&r)[PROBE_ROWS]) {
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
-        const uint32_t x0 = (&r[0].x)[w], x1 = (&r[1].x)[w], x2 = (&r[2].x)[w], x3 = (&r[3].x)[w];
-        const uint32_t x4 = (&r[4].x)[w], x5 = (&r[5].x)[w], x6 = (&r[6].x)[w], x7 = (&r[7].x)[w];
+    for (int w = 0; w < W; w++) {
+        const uint32_t x0 = r[0].v[w], x1 = r[1].v[w], x2 = r[2].v[w], x3 = r[3].v[w];
+        const uint32_t x4 = r[4].v[w], x5 = r[5].v[w], x6 = r[6].v[w], x7 = r[7].v[w];
         uint32_t ones = c[0][w], twos = c[1][w], fours = c[2][w];
         uint32_t t1a = maj3(ones, x0, x1); ones = xor3(ones, x0, x1);
         uint32_t t1b = maj3(ones, x2, x3); ones = xor3(ones, x2, x3);
@@ -549,7 +557,7 @@ __device__ __forceinline__ void csa8(uint32_t (&c)[P][4], const uint4 (&r)[PROBE
         uint32_t carry = maj3(fours, t2a, t2b); fours = xor3(fours, t2a, t2b);
         c[0][w] = ones; c[1][w] = twos; c[2][w] = fours;
 #pragma unroll
-        for (int p = 3; p < P; p++) {
+        for (int p = 3; p < 8; p++) {
             uint32_t t = c[p][w] & carry;
             c[p][w] ^= carry;
             carry = t;
@@ -560,15 +568,15 @@ __device__ __forceinline__ void csa8(uint32_t (&c)[P][4], const uint4 (&r)[PROBE
 // Counters: 8 bit-sliced planes in registers count up to 255 rows.  Queries with more k-mers (long reads, -g genomes)
 // keep the full P = 8+PH planes per thread in shared memory and fold the register planes into them every 248 rows
 // (one ripple add), so every query length runs the same register-lean inner loop.
-template <int PH>
-__device__ __forceinline__ void fold_planes(uint32_t (&c)[8][4], uint32_t *T) {
-    // T[(p*4+w)*blockDim + tid] += c (bit-sliced add), c = 0
+template <int PH, int W>
+__device__ __forceinline__ void fold_planes(uint32_t (&c)[8][W], uint32_t *T) {
+    // T[(p*W+w)*blockDim + tid] += c (bit-sliced add), c = 0
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
+    for (int w = 0; w < W; w++) {
         uint32_t carry = 0;
 #pragma unroll
         for (int p = 0; p < 8; p++) {
-            uint32_t *t = T + (p * 4 + w) * PROBE_THREADS;
+            uint32_t *t = T + (p * W + w) * PROBE_THREADS;
             const uint32_t tv = *t, x = c[p][w];
             *t = xor3(tv, x, carry);
             carry = maj3(tv, x, carry);
@@ -576,7 +584,7 @@ __device__ __forceinline__ void fold_planes(uint32_t (&c)[8][4], uint32_t *T) {
         }
 #pragma unroll
         for (int p = 8; p < 8 + PH; p++) {
-            uint32_t *t = T + (p * 4 + w) * PROBE_THREADS;
+            uint32_t *t = T + (p * W + w) * PROBE_THREADS;
             const uint32_t tv = *t;
             *t = tv ^ carry;
             carry &= tv;
@@ -587,15 +595,23 @@ __device__ __forceinline__ void fold_planes(uint32_t (&c)[8][4], uint32_t *T) {
 // VAR 0: load locs, load rows, add (simple).  VAR 1: row indices of the next 8 k-mers are prefetched while the
 // current rows are in flight.  VAR 2: additionally the rows are double-buffered in registers, so 8..16 rows per
 // lane are always in flight while the carry-save tree of the previous 8 runs.
-template <int H, int PH, int VAR, int MINB>
+// W = words per lane: 4 (16-byte slabs, 8 lanes per 128-byte task) or 2 (8-byte slabs, 16 lanes per task — half the
+// registers per row in flight, which is what the h>1 AND of several rows per k-mer needs).
+template <int H, int PH, int VAR, int MINB, int W>
 __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a) {
     constexpr int P = 8 + PH;
-    extern __shared__ uint32_t smem_planes[];                          // PH > 0: P*4*PROBE_THREADS words
+    constexpr uint32_t SLAB = 4 * W;                                    // bytes per lane
+    extern __shared__ uint32_t smem_planes[];                          // PH > 0: P*W*PROBE_THREADS words
     uint32_t *T = smem_planes + threadIdx.x;
-    const uint32_t G = a.lanes_per_task;
+    // task geometry for this slab width: a task covers up to 128 bytes of a row
+    const uint32_t row_units = (a.row_bytes + SLAB - 1) / SLAB;
+    uint32_t G = 1;
+    while (G < row_units && G < 128 / SLAB) G <<= 1;
+    if (a.lanes_per_task_override) G = a.lanes_per_task_override;
+    const uint32_t chunks = (row_units + G - 1) / G;
     const uint32_t gl = threadIdx.x & (G - 1);                          // lane inside the task group
     const uint64_t groups_per_grid = ((uint64_t)gridDim.x * blockDim.x) / G;
-    const uint64_t total = (uint64_t)a.n_queries * a.chunks;
+    const uint64_t total = (uint64_t)a.n_queries * chunks;
     const uint64_t first = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const uint64_t iters = (total + groups_per_grid - 1) / groups_per_grid;
     const int lane = threadIdx.x & 31;
@@ -604,75 +620,79 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
         const uint64_t g = first + it * groups_per_grid;
         uint32_t q = 0, chunk = 0, n = 0;
         if (g < total) {
-            q = (uint32_t)(g / a.chunks);
-            chunk = (uint32_t)(g - (uint64_t)q * a.chunks);             // chunk fastest: neighbouring groups share rows
+            q = (uint32_t)(g / chunks);
+            chunk = (uint32_t)(g - (uint64_t)q * chunks);               // chunk fastest: neighbouring groups share rows
             n = a.n_eff[q];
         }
-        const uint32_t col16 = chunk * G + gl;                          // this lane's 16-byte slab of the row
-        const bool active = n > 0 && col16 < a.row16;
-        uint32_t c[8][4];
+        const uint32_t colu = chunk * G + gl;                           // this lane's slab of the row
+        const bool active = n > 0 && colu < row_units;
+        uint32_t c[8][W];
 #pragma unroll
-        for (int p = 0; p < 8; p++) c[p][0] = c[p][1] = c[p][2] = c[p][3] = 0;
+        for (int p = 0; p < 8; p++)
+#pragma unroll
+            for (int w = 0; w < W; w++) c[p][w] = 0;
 
         if (active) {
             if (PH > 0) {
 #pragma unroll
-                for (int i = 0; i < P * 4; i++) T[i * PROBE_THREADS] = 0;
+                for (int i = 0; i < P * W; i++) T[i * PROBE_THREADS] = 0;
             }
             const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
-            const uint8_t *colbase = a.rows + (uint64_t)col16 * 16;
+            const uint8_t *colbase = a.rows + (uint64_t)colu * SLAB;
             uint32_t L[PROBE_ROWS * H];
             uint32_t acc = 0;                                           // rows added to the register planes since the last fold
-            auto add8 = [&](const uint4 (&r)[PROBE_ROWS]) {
+            auto add8 = [&](const Slab<W> (&r)[PROBE_ROWS]) {
                 if (PH > 0) {
-                    if (acc + PROBE_ROWS > 255) { fold_planes<PH>(c, T); acc = 0; }
+                    if (acc + PROBE_ROWS > 255) { fold_planes<PH, W>(c, T); acc = 0; }
                     acc += PROBE_ROWS;
                 }
-                csa8<8>(c, r);
+                csa8<W>(c, r);
             };
             if (VAR == 0) {
                 for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
-                    uint4 r[PROBE_ROWS];
+                    Slab<W> r[PROBE_ROWS];
                     load_locs<H>(L, lp, i, n);
-                    load_rows<H>(r, L, colbase, a.pitch);
+                    load_rows<H, W>(r, L, colbase, a.pitch);
                     add8(r);
                 }
             } else if (VAR == 1) {
                 load_locs<H>(L, lp, 0, n);
                 for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
-                    uint4 r[PROBE_ROWS];
-                    load_rows<H>(r, L, colbase, a.pitch);
+                    Slab<W> r[PROBE_ROWS];
+                    load_rows<H, W>(r, L, colbase, a.pitch);
                     load_locs<H>(L, lp, i + PROBE_ROWS, n);
                     add8(r);
                 }
             } else {
-                uint4 r0[PROBE_ROWS], r1[PROBE_ROWS];
+                Slab<W> r0[PROBE_ROWS], r1[PROBE_ROWS];
                 load_locs<H>(L, lp, 0, n);
-                load_rows<H>(r0, L, colbase, a.pitch);
+                load_rows<H, W>(r0, L, colbase, a.pitch);
                 load_locs<H>(L, lp, PROBE_ROWS, n);
                 for (uint32_t i = 0; i < n; i += 2 * PROBE_ROWS) {
-                    load_rows<H>(r1, L, colbase, a.pitch);
+                    load_rows<H, W>(r1, L, colbase, a.pitch);
                     load_locs<H>(L, lp, i + 2 * PROBE_ROWS, n);
                     add8(r0);
-                    load_rows<H>(r0, L, colbase, a.pitch);
+                    load_rows<H, W>(r0, L, colbase, a.pitch);
                     load_locs<H>(L, lp, i + 3 * PROBE_ROWS, n);
                     if (i + PROBE_ROWS < n) add8(r1);
                 }
             }
-            if (PH > 0) fold_planes<PH>(c, T);
+            if (PH > 0) fold_planes<PH, W>(c, T);
         }
         // plane p, word w of this thread's final counters
-        auto plane = [&](int p, int w) -> uint32_t { return PH > 0 ? T[(p * 4 + w) * PROBE_THREADS] : c[p < 8 ? p : 0][w]; };
+        auto plane = [&](int p, int w) -> uint32_t { return PH > 0 ? T[(p * W + w) * PROBE_THREADS] : c[p < 8 ? p : 0][w]; };
 
         // ---- thresholds on the bit-sliced counters: ge = (count >= T) per target bit ----
-        uint32_t ge[4] = {0, 0, 0, 0};
+        uint32_t ge[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) ge[w] = 0;
         int nhit = 0;
         if (active) {
             const uint32_t Tq = a.thresh[q];
             uint32_t high = (P < 32) ? (Tq >> P) : 0;                    // threshold does not fit in P bits → nothing passes
             if (!high) {
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
+                for (int w = 0; w < W; w++) {
                     uint32_t gt = 0, eq = 0xFFFFFFFFu;
 #pragma unroll
                     for (int p = P - 1; p >= 0; p--) {
@@ -686,9 +706,9 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
             }
             if (a.dense_counts) {                                        // test hook: dump every count of this slab
 #pragma unroll
-                for (int w = 0; w < 4; w++)
+                for (int w = 0; w < W; w++)
                     for (int bit = 0; bit < 32; bit++) {
-                        uint32_t t = (col16 * 16 + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                        uint32_t t = (colu * SLAB + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
                         if (t < a.n_names) {
                             uint32_t cnt = 0;
 #pragma unroll
@@ -714,13 +734,13 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
             unsigned long long slot = base + (unsigned long long)(incl - nhit);
             if (nhit > 0) {
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
+                for (int w = 0; w < W; w++) {
                     uint32_t m = ge[w];
                     while (m) {
                         int bit = __ffs(m) - 1;
                         m &= m - 1;
-                        // byte (col16*16 + w*4 + bit/8), bit 7-j ↔ target 8*byte + j  (I:1157, U:7415)
-                        uint32_t t = (col16 * 16 + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                        // byte (colu*SLAB + w*4 + bit/8), bit 7-j ↔ target 8*byte + j  (I:1157, U:7415)
+                        uint32_t t = (colu * SLAB + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
                         uint32_t cnt = 0;
 #pragma unroll
                         for (int p = 0; p < P; p++) cnt |= ((plane(p, w) >> bit) & 1u) << p;
@@ -736,45 +756,59 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
     }
 }
 
-struct ProbeTune { int var = 2, minb = 2, cap = 16, var_h = 1, minb_h = 3; };
+struct ProbeTune { int var = 2, minb = 2, cap = 16, var_h = 1, minb_h = 2, w_h = 2, g = 0; };
 static ProbeTune probe_tune() {
-    // development knobs (tools/probe_sweep.sh): KMCPG_PROBE_VAR / _MINB (h=1), KMCPG_PROBE_VARH / _MINBH (h>1), KMCPG_PROBE_CAP
+    // development knobs (tools/*.sh): KMCPG_PROBE_VAR / _MINB (h=1), KMCPG_PROBE_VARH / _MINBH / _WH (h>1), KMCPG_PROBE_CAP, KMCPG_PROBE_G
     static ProbeTune t = [] {
         ProbeTune x;
         if (const char *e = getenv("KMCPG_PROBE_VAR")) x.var = atoi(e);
         if (const char *e = getenv("KMCPG_PROBE_MINB")) x.minb = atoi(e);
         if (const char *e = getenv("KMCPG_PROBE_VARH")) x.var_h = atoi(e);
         if (const char *e = getenv("KMCPG_PROBE_MINBH")) x.minb_h = atoi(e);
+        if (const char *e = getenv("KMCPG_PROBE_WH")) x.w_h = atoi(e) == 2 ? 2 : 4;
         if (const char *e = getenv("KMCPG_PROBE_CAP")) x.cap = atoi(e);
+        if (const char *e = getenv("KMCPG_PROBE_G")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) x.g = v; }
         return x;
     }();
     return t;
 }
 
-template <int H, int PH, int VAR, int MINB>
+template <int H, int PH, int VAR, int MINB, int W>
 static cudaError_t launch_probe_k(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
-    const size_t smem = PH > 0 ? (size_t)(8 + PH) * 4 * PROBE_THREADS * sizeof(uint32_t) : 0;
+    const size_t smem = PH > 0 ? (size_t)(8 + PH) * W * PROBE_THREADS * sizeof(uint32_t) : 0;
     if (smem > 48 * 1024) {
         static bool done = false;       // per instantiation
         if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(probe_kernel<H, PH, VAR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(probe_kernel<H, PH, VAR, MINB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             done = true;
         }
     }
-    probe_kernel<H, PH, VAR, MINB><<<blocks, PROBE_THREADS, smem, st>>>(a);
+    probe_kernel<H, PH, VAR, MINB, W><<<blocks, PROBE_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int H, int PH>
 static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     const ProbeTune t = probe_tune();
-    const int var = H == 1 ? t.var : t.var_h;
-    int minb = H == 1 ? t.minb : t.minb_h;
-    if (PH >= 24) minb = 1;                                  // 128 KB of counter planes per CTA
-    if (var == 0) return minb >= 3 ? launch_probe_k<H, PH, 0, 3>(a, blocks, st) : launch_probe_k<H, PH, 0, 2>(a, blocks, st);
-    if (var == 1) return minb >= 3 ? launch_probe_k<H, PH, 1, 3>(a, blocks, st) : (minb >= 2 ? launch_probe_k<H, PH, 1, 2>(a, blocks, st) : launch_probe_k<H, PH, 1, 1>(a, blocks, st));
-    return minb >= 2 ? launch_probe_k<H, PH, 2, 2>(a, blocks, st) : launch_probe_k<H, PH, 2, 1>(a, blocks, st);
+    if (H == 1) {
+        int minb = t.minb;
+        if (PH >= 24) minb = 1;                              // 128 KB of counter planes per CTA
+        if (t.var == 0) return launch_probe_k<H, PH, 0, 2, 4>(a, blocks, st);
+        if (t.var == 1) return minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st);
+        return minb >= 2 ? launch_probe_k<H, PH, 2, 2, 4>(a, blocks, st) : launch_probe_k<H, PH, 2, 1, 4>(a, blocks, st);
+    }
+    // h > 1
+    int minb = t.minb_h;
+    if (t.w_h == 2) {
+        if (PH >= 24 && minb > 2) minb = 2;                  // 64 KB of planes per CTA at W = 2
+        if (t.var_h == 2) return minb >= 3 ? launch_probe_k<H, PH, 2, 3, 2>(a, blocks, st) : launch_probe_k<H, PH, 2, 2, 2>(a, blocks, st);
+        return minb >= 3 ? launch_probe_k<H, PH, 1, 3, 2>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 2>(a, blocks, st);
+    }
+    if (PH >= 24) minb = 1;
+    else if (PH >= 16 && minb > 2) minb = 2;                 // 96 KB per CTA
+    if (minb >= 3) return launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st);
+    return minb >= 2 ? launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 1, 4>(a, blocks, st);
 }
 
 template <int H>
@@ -788,13 +822,16 @@ static cudaError_t launch_probe_h(const ProbeArgs &a, uint32_t blocks, cudaStrea
     }
 }
 
-cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st) {
-    if (!a.n_queries) return cudaSuccess;
-    const uint64_t total_groups = (uint64_t)a.n_queries * a.chunks;
-    const uint64_t threads = total_groups * a.lanes_per_task;
+cudaError_t launch_probe(const ProbeArgs &a_in, int sm_count, cudaStream_t st) {
+    if (!a_in.n_queries) return cudaSuccess;
+    ProbeArgs a = a_in;
+    const ProbeTune t = probe_tune();
+    a.lanes_per_task_override = (uint32_t)t.g;
+    // upper bound of the thread demand (8-byte slabs need the most lanes); the grid is persistent-style anyway:
+    // a multiple of the SM count, several CTAs per SM, each thread loops over tasks
+    const uint64_t threads = (uint64_t)a.n_queries * ((a.row_bytes + 7) / 8 + 15);
     uint64_t blocks64 = (threads + PROBE_THREADS - 1) / PROBE_THREADS;
-    // persistent-style grid: a multiple of the SM count, several CTAs per SM, each thread loops over tasks
-    const uint64_t cap = (uint64_t)sm_count * probe_tune().cap;
+    const uint64_t cap = (uint64_t)sm_count * t.cap;
     uint32_t blocks = (uint32_t)(blocks64 < cap ? blocks64 : cap);
     switch (a.num_hashes) {
         case 1: return launch_probe_h<1>(a, blocks, st);

@@ -86,9 +86,8 @@ cudaError_t launch_locs(const uint64_t *codes, uint64_t n_slots, int num_hashes,
 struct ProbeArgs {
     const uint8_t *rows;        // re-pitched bit matrix of the block in HBM
     uint32_t pitch;             // bytes between rows
-    uint32_t row16;             // 16-byte units per row that carry data: ceil(row_bytes/16)
-    uint32_t lanes_per_task;    // G: 1,2,4,8,16,32 lanes × 16 B = one task's column chunk
-    uint32_t chunks;            // tasks per query = ceil(row16 / G)
+    uint32_t row_bytes;         // bytes per row that carry data (un-padded numRowBytes)
+    uint32_t lanes_per_task_override;   // 0: a task = up to 128 bytes of a row (8 lanes × 16 B or 16 lanes × 8 B); dev knob otherwise
     uint32_t n_names;
     uint32_t target_base;
     int num_hashes;
