@@ -235,8 +235,11 @@ typedef struct {
     uint64_t genome_seed; uint32_t n_genomes; uint32_t genome_len;
     int32_t k; int32_t n_chunks; int32_t overlap;
     int32_t num_hashes; double fpr; int32_t block_size; /* targets per block */
+    uint32_t scale;                                      /* > 1: FracMinHash sketch database (compute -D) */
 } kmcpg_synth_db;
 int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec);
+/* d_out[i*genome_len ..) = seeded genome (first+i), ASCII */
+int kmcpg_synth_genomes(kmcpg_ctx *ctx, uint64_t genome_seed, uint32_t first, uint32_t n_genomes, uint32_t genome_len, uint8_t *d_out);
 /* dump resident block b in .uniki format (X:153-304), for parity checks of the device builder */
 int kmcpg_write_block(kmcpg_ctx *ctx, int resident_block, const char *path);
 

@@ -106,7 +106,7 @@ class IndexParams(C.Structure):
 class SynthDb(C.Structure):
     _fields_ = [("genome_seed", C.c_uint64), ("n_genomes", C.c_uint32), ("genome_len", C.c_uint32), ("k", C.c_int32),
                 ("n_chunks", C.c_int32), ("overlap", C.c_int32), ("num_hashes", C.c_int32), ("fpr", C.c_double),
-                ("block_size", C.c_int32)]
+                ("block_size", C.c_int32), ("scale", C.c_uint32)]
 
 
 # every symbol include/kmcp_gpu.h declares (checked by tests/test_abi.py without a GPU)
@@ -115,7 +115,7 @@ ABI_SYMBOLS = [
     "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_free_hits", "kmcpg_host_alloc",
     "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
     "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search",
-    "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_build_synth_db", "kmcpg_write_block",
+    "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_synth_genomes", "kmcpg_build_synth_db", "kmcpg_write_block",
 ]
 
 _lib = None
@@ -170,6 +170,7 @@ def load() -> C.CDLL:
     L.kmcpg_index_fasta.argtypes = [vp, C.POINTER(IndexParams), C.POINTER(C.c_char_p), C.c_int, C.c_char_p]
     L.kmcpg_synth_reads.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, vp]
     L.kmcpg_build_synth_db.argtypes = [vp, C.POINTER(SynthDb)]
+    L.kmcpg_synth_genomes.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.kmcpg_write_block.argtypes = [vp, C.c_int, C.c_char_p]
     _lib = L
     return L
@@ -262,8 +263,8 @@ class Context:
         self._check(self._L.kmcpg_open_db(self._h, r001_dir.encode(), C.byref(o)))
 
     def build_synth_db(self, genome_seed: int, n_genomes: int, genome_len: int, k: int = 21, n_chunks: int = 10,
-                       overlap: int = 150, num_hashes: int = 1, fpr: float = 0.3, block_size: int = 0):
-        s = SynthDb(genome_seed, n_genomes, genome_len, k, n_chunks, overlap, num_hashes, fpr, block_size)
+                       overlap: int = 150, num_hashes: int = 1, fpr: float = 0.3, block_size: int = 0, scale: int = 1):
+        s = SynthDb(genome_seed, n_genomes, genome_len, k, n_chunks, overlap, num_hashes, fpr, block_size, scale)
         self._check(self._L.kmcpg_build_synth_db(self._h, C.byref(s)))
 
     def index_fasta(self, files, out_dir: str, k: int = 21, num_hashes: int = 1, fpr: float = 0.3, split_number: int = 1, split_overlap: int = -1,
@@ -416,6 +417,9 @@ class Context:
         out = np.empty(nbytes, dtype=np.uint8)
         self._check(self._L.kmcpg_memcpy_d2h(self._h, out.ctypes.data, dptr, nbytes))
         return out
+
+    def synth_genomes(self, genome_seed: int, first: int, n_genomes: int, genome_len: int, dptr: int):
+        self._check(self._L.kmcpg_synth_genomes(self._h, genome_seed, first, n_genomes, genome_len, dptr))
 
     def synth_reads(self, seed: int, first: int, n_reads: int, read_len: int, genome_seed: int, n_genomes: int,
                     genome_len: int, dptr: int):

@@ -791,24 +791,22 @@ static cudaError_t launch_probe_k(const ProbeArgs &a, uint32_t blocks, cudaStrea
 template <int H, int PH>
 static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     const ProbeTune t = probe_tune();
+    // the development variants (documented in profiles/config_sweeps_r01.md) exist only for the 8-plane kernels
+    if constexpr (PH == 0) {
+        if (H == 1) {
+            if (t.var == 0) return launch_probe_k<H, PH, 0, 2, 4>(a, blocks, st);
+            if (t.var == 1) return t.minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st);
+        } else {
+            if (t.w_h == 4) return t.minb_h >= 3 ? launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st);
+            if (t.var_h == 2) return launch_probe_k<H, PH, 2, 2, 2>(a, blocks, st);
+            if (t.minb_h >= 3) return launch_probe_k<H, PH, 1, 3, 2>(a, blocks, st);
+        }
+    }
     if (H == 1) {
-        int minb = t.minb;
-        if (PH >= 24) minb = 1;                              // 128 KB of counter planes per CTA
-        if (t.var == 0) return launch_probe_k<H, PH, 0, 2, 4>(a, blocks, st);
-        if (t.var == 1) return minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st);
-        return minb >= 2 ? launch_probe_k<H, PH, 2, 2, 4>(a, blocks, st) : launch_probe_k<H, PH, 2, 1, 4>(a, blocks, st);
+        if (PH >= 24) return launch_probe_k<H, PH, 2, 1, 4>(a, blocks, st);      // 128 KB of counter planes per CTA
+        return launch_probe_k<H, PH, 2, 2, 4>(a, blocks, st);                    // shipped: double-buffered 16-byte slabs, 2 CTAs/SM
     }
-    // h > 1
-    int minb = t.minb_h;
-    if (t.w_h == 2) {
-        if (PH >= 24 && minb > 2) minb = 2;                  // 64 KB of planes per CTA at W = 2
-        if (t.var_h == 2) return minb >= 3 ? launch_probe_k<H, PH, 2, 3, 2>(a, blocks, st) : launch_probe_k<H, PH, 2, 2, 2>(a, blocks, st);
-        return minb >= 3 ? launch_probe_k<H, PH, 1, 3, 2>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 2>(a, blocks, st);
-    }
-    if (PH >= 24) minb = 1;
-    else if (PH >= 16 && minb > 2) minb = 2;                 // 96 KB per CTA
-    if (minb >= 3) return launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st);
-    return minb >= 2 ? launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 1, 4>(a, blocks, st);
+    return launch_probe_k<H, PH, 1, 2, 2>(a, blocks, st);                        // shipped for h>1: 8-byte slabs, index prefetch, 2 CTAs/SM
 }
 
 template <int H>

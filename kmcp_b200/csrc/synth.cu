@@ -153,6 +153,16 @@ int kmcpg_synth_reads(kmcpg_ctx *ctx, uint64_t seed, uint64_t first, uint32_t n_
     return KMCPG_OK;
 }
 
+int kmcpg_synth_genomes(kmcpg_ctx *ctx, uint64_t genome_seed, uint32_t first, uint32_t n_genomes, uint32_t genome_len, uint8_t *d_out) {
+    if (!ctx || !d_out) return KMCPG_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    for (uint32_t g = 0; g < n_genomes; g++)
+        CU(launch_synth_genome(genome_seed, first + g, 0, genome_len, d_out + (uint64_t)g * genome_len, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return KMCPG_OK;
+}
+
 int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
     if (!ctx || !spec) return KMCPG_EINVAL;
     if (spec->k < 1 || spec->k > 64 || spec->n_genomes < 1 || spec->genome_len < (uint32_t)spec->k || spec->num_hashes < 1 || spec->num_hashes > 4 ||
@@ -167,6 +177,7 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
     m = DbMeta();
     m.dir = "<synthetic>";
     m.version = 4; m.index_version = 4; m.ks = {spec->k}; m.canonical = true; m.num_hashes = spec->num_hashes; m.fpr = spec->fpr;
+    m.scaled = spec->scale > 1; m.scale = m.scaled ? spec->scale : 0;
 
     const uint64_t L = spec->genome_len;
     const std::vector<Window> wins = split_windows(L, spec->n_chunks, spec->overlap, spec->k);
