@@ -63,7 +63,7 @@ void free_db(kmcpg_ctx *ctx) {
 
 void WorkSet::release() {
     for (DevBuf *b : {&seq, &off, &slot_cnt, &slot_off, &codes, &codes2, &locs, &ncodes, &qlen, &nk, &neff, &thresh, &hkeys, &hvals, &hkeys2, &hvals2,
-                      &hits, &counters, &tmp, &tmp2, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off})
+                      &hits, &counters, &tmp, &tmp2, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off, &tile_n, &tile_off, &tile_cnt, &tile_pre})
         b->release();
     h_off.release(); h_cnt.release();
     for (cudaEvent_t *e : {&ev_in, &ev_a0, &ev_hash, &ev_a, &ev_cnt, &ev_sorted, &ev_b}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
@@ -142,6 +142,43 @@ static int ensure_events(kmcpg_ctx *ctx, WorkSet &w) {
     return KMCPG_OK;
 }
 
+// widens a u32 count to u64 while scanning
+struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; } };
+
+// hashing of one HashArgs job: warp per query for short sequences, warp per 4096-position tile (+ gather) when a query is long
+static int hash_any(kmcpg_ctx *ctx, WorkSet &w, const HashArgs &ha, uint32_t n_seqs, uint64_t total_slots, uint64_t max_query_slots) {
+    cudaStream_t st = ctx->st;
+    if (max_query_slots <= 2ull * HASH_TILE_POS) {
+        CU(launch_hash(ha, st)); ctx->launches++;
+        return KMCPG_OK;
+    }
+    const uint64_t max_tiles = total_slots / HASH_TILE_POS + n_seqs;
+    CU(w.tile_n.ensure((n_seqs + 1) * 8ull)); CU(w.tile_off.ensure((n_seqs + 1) * 8ull));
+    CU(launch_tiles_per_seq(ha.seq_off, n_seqs, ha.k, w.tile_n.as<uint64_t>(), st));
+    size_t t1 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t1, w.tile_n.as<uint64_t>(), w.tile_off.as<uint64_t>(), (int)(n_seqs + 1), st);
+    CU(w.tmp.ensure(t1));
+    CU(cub::DeviceScan::ExclusiveSum(w.tmp.p, t1, w.tile_n.as<uint64_t>(), w.tile_off.as<uint64_t>(), (int)(n_seqs + 1), st));
+    ctx->launches += 3;
+    if (ha.raw) {                                    // position-indexed output: the tiles write straight to their place
+        CU(launch_hash_tiles(ha, n_seqs, w.tile_off.as<uint64_t>(), max_tiles, nullptr, nullptr, st)); ctx->launches++;
+        return KMCPG_OK;
+    }
+    if (max_tiles >= (1ull << 31)) return fail(ctx, KMCPG_EUNSUPPORTED, "too many tiles in one part");
+    CU(w.tile_cnt.ensure((max_tiles + 1) * 4)); CU(w.tile_pre.ensure((max_tiles + 1) * 8));
+    CU(w.codes2.ensure(std::max<uint64_t>(total_slots, 1) * 8));
+    CU(cudaMemsetAsync(w.tile_cnt.p, 0, (max_tiles + 1) * 4, st));
+    CU(launch_hash_tiles(ha, n_seqs, w.tile_off.as<uint64_t>(), max_tiles, w.codes2.as<uint64_t>(), w.tile_cnt.as<uint32_t>(), st));
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(w.tile_cnt.as<uint32_t>(), U32ToU64());
+    size_t t2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, it, w.tile_pre.as<uint64_t>(), (int)(max_tiles + 1), st);
+    CU(w.tmp.ensure(t2));
+    CU(cub::DeviceScan::ExclusiveSum(w.tmp.p, t2, it, w.tile_pre.as<uint64_t>(), (int)(max_tiles + 1), st));
+    CU(launch_gather_tiles(ha, n_seqs, w.tile_off.as<uint64_t>(), w.tile_pre.as<uint64_t>(), w.tile_cnt.as<uint32_t>(), w.codes2.as<uint64_t>(), max_tiles, st));
+    ctx->launches += 4;
+    return KMCPG_OK;
+}
+
 // slot scan → hash → (sort+unique) → verdict, all on the compute stream; sb.d_seq/d_off must already be valid there
 int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out) {
     const DbMeta &m = ctx->meta;
@@ -173,13 +210,15 @@ int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int
     ha.minimizer = m.minimizer; ha.minimizer_w = m.minimizer_w; ha.syncmer = m.syncmer; ha.syncmer_s = m.syncmer_s;
     ha.min_query_len = p.min_query_len;
     if (!m.minimizer && !m.syncmer) {
-        CU(launch_hash(ha, st)); ctx->launches++;
+        rc = hash_any(ctx, w, ha, sb.n_seqs, sb.total_slots, sb.max_query_slots);
+        if (rc) return rc;
     } else {
         // sketch databases: hash every position (k-mers, and s-mers for syncmers), then select per window
         CU(w.ck.ensure(std::max<uint64_t>(sb.total_slots, 1) * 8));
         HashArgs hr = ha;
         hr.raw = 1; hr.n_queries = sb.n_seqs; hr.codes = w.ck.as<uint64_t>();
-        CU(launch_hash(hr, st)); ctx->launches++;
+        rc = hash_any(ctx, w, hr, sb.n_seqs, sb.total_slots, sb.max_query_slots);
+        if (rc) return rc;
         SelectArgs sa;
         memset(&sa, 0, sizeof(sa));
         sa.seq_off = sb.d_off; sa.ck = w.ck.as<uint64_t>(); sa.slot_off = w.slot_off.as<uint64_t>();
@@ -196,8 +235,9 @@ int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int
             CU(w.cs.ensure((sb.total_slots + (uint64_t)sb.n_seqs * (uint64_t)(k - s + 1) + 1) * 8));
             HashArgs hs = hr;
             hs.k = s; hs.slot_off = w.cs_off.as<uint64_t>(); hs.codes = w.cs.as<uint64_t>();
-            CU(launch_hash(hs, st));
-            ctx->launches += 4;
+            rc = hash_any(ctx, w, hs, sb.n_seqs, sb.total_slots + (uint64_t)sb.n_seqs * (uint64_t)(k - s + 1), sb.max_query_slots + 2ull * (k - s));
+            if (rc) return rc;
+            ctx->launches += 3;
             sa.cs = w.cs.as<uint64_t>(); sa.cs_off = w.cs_off.as<uint64_t>(); sa.syncmer_s = s;
         }
         sa.codes = w.codes.as<uint64_t>(); sa.n_codes = w.ncodes.as<uint32_t>(); sa.query_len = w.qlen.as<int32_t>();

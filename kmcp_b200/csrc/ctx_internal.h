@@ -82,6 +82,7 @@ struct WorkSet {
     DevBuf seq, off, slot_cnt, slot_off, codes, codes2, locs, ncodes, qlen, nk, neff, thresh;
     DevBuf hkeys, hvals, hkeys2, hvals2, hits, counters, tmp, tmp2, segb, sege;
     DevBuf ck, cs, cs_cnt, cs_off;      // sketch selection: per-position k-mer / s-mer hashes
+    DevBuf tile_n, tile_off, tile_cnt, tile_pre;   // long sequences: tiles per sequence, their scan, codes per tile, their scan
     HostBuf h_off, h_cnt;
     cudaEvent_t ev_in = nullptr, ev_a0 = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_cnt = nullptr, ev_sorted = nullptr, ev_b = nullptr;
     std::vector<cudaEvent_t> probe_ev;   // 3 per resident block: before locs, before probe, after probe

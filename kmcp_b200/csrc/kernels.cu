@@ -261,6 +261,174 @@ cudaError_t launch_select(const SelectArgs &a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ---- long sequences: one warp per TILE of positions instead of one warp per query --------------------------------
+// tile t of sequence s covers k-mer positions [j*TILE_POS, (j+1)*TILE_POS); its codes are compacted at the start of the tile's
+// own slot range of a scratch array, then gathered per query in tile order (= position order) after a scan of the tile counts.
+constexpr uint32_t TILE_POS = 4096;
+
+__global__ void tiles_per_seq_kernel(const uint64_t *__restrict__ seq_off, uint32_t n_seqs, int k, uint64_t *__restrict__ cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_seqs) {
+        uint64_t len = seq_off[i + 1] - seq_off[i];
+        uint64_t nk = len >= (uint64_t)k ? len - k + 1 : 0;
+        cnt[i] = (nk + TILE_POS - 1) / TILE_POS;
+    }
+    if (i == n_seqs) cnt[i] = 0;
+}
+
+__device__ __forceinline__ uint32_t seq_of_tile(const uint64_t *__restrict__ tile_off, uint32_t n_seqs, uint64_t t) {
+    uint32_t lo = 0, hi = n_seqs;                      // largest s with tile_off[s] <= t
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (tile_off[mid] <= t) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(HASH_WARPS * 32) hash_tile_kernel(HashArgs a, uint32_t n_seqs, const uint64_t *__restrict__ tile_off, uint64_t *__restrict__ tmp,
+                                                                    uint32_t *__restrict__ tile_cnt) {
+    __shared__ SeedTables T;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint64_t f = seed_fwd((uint8_t)i);
+        if (i < 8) {
+            const uint64_t r8[8] = {0, SEED_T, 0, SEED_G, SEED_A, SEED_A, 0, SEED_C};
+            f = r8[i];
+            T.R[i] = f; T.R1[i] = ror1(f); T.Rk1[i] = rolv(f, (unsigned)(a.k - 1));
+        }
+        T.F[i] = f;
+        T.Fk[i] = rolv(f, (unsigned)a.k);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int k = a.k;
+    const uint64_t n_tiles = tile_off[n_seqs];
+    for (uint64_t t = warp; t < n_tiles; t += n_warps) {
+        const uint32_t sq = seq_of_tile(tile_off, n_seqs, t);
+        const uint64_t j = t - tile_off[sq];
+        const uint8_t *s = a.seq + a.seq_off[sq];
+        const uint64_t len = a.seq_off[sq + 1] - a.seq_off[sq];
+        const uint64_t nk = len - k + 1;                                // a sequence with tiles has len >= k
+        const uint64_t p_begin = j * TILE_POS, p_end = (p_begin + TILE_POS < nk) ? p_begin + TILE_POS : nk;
+        // query-level rules (U:778-786, mate selection of --try-se)
+        bool drop = false;
+        if (!a.raw) {
+            const uint32_t s0 = a.paired ? (sq & ~1u) : sq;
+            const uint64_t len0 = a.seq_off[s0 + 1] - a.seq_off[s0];
+            const uint64_t len1 = a.paired ? a.seq_off[s0 + 2] - a.seq_off[s0 + 1] : 0;
+            drop = (int64_t)len0 < a.min_query_len && !(a.paired && (int64_t)len1 >= a.min_query_len);
+            if (a.paired && a.mate_select == 1 && (sq & 1)) drop = true;
+            if (a.paired && a.mate_select == 2 && !(sq & 1)) drop = true;
+        }
+        uint64_t *out = (a.raw ? a.codes : tmp) + a.slot_off[sq] + p_begin;
+        uint32_t written = 0;
+        if (!drop) {
+            for (uint64_t base = p_begin; base < p_end; base += 32 * HASH_RUN) {
+                const uint64_t p0 = base + (uint64_t)lane * HASH_RUN;
+                int cnt = 0;
+                if (p0 < p_end) cnt = (int)((p_end - p0) < HASH_RUN ? (p_end - p0) : HASH_RUN);
+                uint64_t c[HASH_RUN];
+                uint32_t valid = 0;
+                if (cnt > 0) {
+                    uint64_t fh = 0, rh = 0;
+#pragma unroll 4
+                    for (int jj = 0; jj < k; jj++) {
+                        const uint8_t b = s[p0 + jj];
+                        fh = rol1(fh) ^ T.F[b];
+                        rh = ror1(rh) ^ T.Rk1[b & 7];
+                    }
+#pragma unroll
+                    for (int r = 0; r < HASH_RUN; r++) {
+                        if (r < cnt) {
+                            uint64_t code = a.canonical ? (fh < rh ? fh : rh) : fh;
+                            bool ok = a.raw || (code != 0 && !(a.scaled && code > a.max_hash));
+                            c[r] = code;
+                            if (ok) valid |= 1u << r;
+                            if (r + 1 < cnt) {
+                                uint8_t bo = s[p0 + r], bi = s[p0 + r + k];
+                                fh = rol1(fh) ^ T.Fk[bo] ^ T.F[bi];
+                                rh = ror1(rh) ^ T.R1[bo & 7] ^ T.Rk1[bi & 7];
+                            }
+                        }
+                    }
+                }
+                if (a.raw) {
+#pragma unroll
+                    for (int r = 0; r < HASH_RUN; r++)
+                        if (valid & (1u << r)) out[(p0 - p_begin) + r] = c[r];
+                    continue;
+                }
+                int mine = __popc(valid);
+                int incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int tt = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += tt;
+                }
+                int total = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t w = written + (uint32_t)(incl - mine);
+#pragma unroll
+                for (int r = 0; r < HASH_RUN; r++)
+                    if (valid & (1u << r)) out[w++] = c[r];
+                written += (uint32_t)total;
+            }
+        }
+        if (lane == 0 && !a.raw) tile_cnt[t] = written;
+    }
+}
+
+// tile-compacted codes → contiguous per query, in position order; n_codes / query_len of every query
+__global__ void __launch_bounds__(256) gather_tiles_kernel(HashArgs a, uint32_t n_seqs, const uint64_t *__restrict__ tile_off, const uint64_t *__restrict__ tile_pre,
+                                                           const uint32_t *__restrict__ tile_cnt, const uint64_t *__restrict__ tmp) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_tiles = tile_off[n_seqs];
+    for (uint64_t t = warp; t < n_tiles; t += n_warps) {
+        const uint32_t sq = seq_of_tile(tile_off, n_seqs, t);
+        const uint32_t s0 = a.paired ? (sq & ~1u) : sq;
+        const uint64_t j = t - tile_off[sq];
+        const uint64_t *src = tmp + a.slot_off[sq] + j * TILE_POS;
+        uint64_t *dst = a.codes + a.slot_off[s0] + (tile_pre[t] - tile_pre[tile_off[s0]]);
+        const uint32_t n = tile_cnt[t];
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+    // per query bookkeeping
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < a.n_queries; q += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s0 = a.paired ? 2 * (uint32_t)q : (uint32_t)q;
+        const uint32_t s1 = s0 + (a.paired ? 2 : 1);
+        const uint64_t len0 = a.seq_off[s0 + 1] - a.seq_off[s0];
+        const uint64_t len1 = a.paired ? a.seq_off[s0 + 2] - a.seq_off[s0 + 1] : 0;
+        const bool skip = (int64_t)len0 < a.min_query_len && !(a.paired && (int64_t)len1 >= a.min_query_len);
+        int32_t qlen = (int32_t)(len0 + len1);
+        if (a.mate_select == 1) qlen = (int32_t)len0;
+        if (a.mate_select == 2) qlen = (int32_t)len1;
+        a.n_codes[q] = skip ? 0xFFFFFFFFu : (uint32_t)(tile_pre[tile_off[s1]] - tile_pre[tile_off[s0]]);
+        a.query_len[q] = qlen;
+    }
+}
+
+cudaError_t launch_tiles_per_seq(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *cnt, cudaStream_t st) {
+    uint32_t n = n_seqs + 1;
+    tiles_per_seq_kernel<<<(n + 255) / 256, 256, 0, st>>>(seq_off, n_seqs, k, cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hash_tiles(const HashArgs &a, uint32_t n_seqs, const uint64_t *tile_off, uint64_t max_tiles, uint64_t *tmp, uint32_t *tile_cnt, cudaStream_t st) {
+    if (!n_seqs || !max_tiles) return cudaSuccess;
+    uint64_t blocks64 = (max_tiles + HASH_WARPS - 1) / HASH_WARPS;
+    uint32_t blocks = blocks64 > 148u * 32u ? 148u * 32u : (uint32_t)blocks64;
+    hash_tile_kernel<<<blocks, HASH_WARPS * 32, 0, st>>>(a, n_seqs, tile_off, tmp, tile_cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_tiles(const HashArgs &a, uint32_t n_seqs, const uint64_t *tile_off, const uint64_t *tile_pre, const uint32_t *tile_cnt,
+                                const uint64_t *tmp, uint64_t max_tiles, cudaStream_t st) {
+    if (!n_seqs) return cudaSuccess;
+    uint64_t blocks64 = (std::max<uint64_t>(max_tiles, a.n_queries / 8 + 1) + 7) / 8;
+    uint32_t blocks = blocks64 > 148u * 32u ? 148u * 32u : (uint32_t)blocks64;
+    gather_tiles_kernel<<<blocks, 256, 0, st>>>(a, n_seqs, tile_off, tile_pre, tile_cnt, tmp);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_hash(const HashArgs &a, cudaStream_t st) {
     if (a.n_queries == 0) return cudaSuccess;
     uint32_t blocks = (a.n_queries + HASH_WARPS - 1) / HASH_WARPS;
@@ -756,6 +924,165 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
     }
 }
 
+// Few, long queries (genome-sized -g queries against sketch DBs, a handful of HiFi reads): a task = (query, chunk) is given
+// to a WHOLE CTA.  Its 256/G lane groups each take every (256/G)-th group of 8 k-mers, count them exactly like the kernel
+// above (8 register planes folded into P-plane totals in shared memory), then the per-group totals are added pairwise in
+// shared memory (bit-sliced ripple adders, log2(256/G) levels) and group 0 applies the threshold and emits the hits.
+template <int H, int PH, int W>
+__global__ void __launch_bounds__(PROBE_THREADS, 1) probe_long_kernel(ProbeArgs a) {
+    static_assert(PH > 0, "long queries always carry full-width totals in shared memory");
+    constexpr int P = 8 + PH;
+    constexpr uint32_t SLAB = 4 * W;
+    extern __shared__ uint32_t smem_planes[];                          // P*W*PROBE_THREADS words
+    uint32_t *T = smem_planes + threadIdx.x;
+    const uint32_t row_units = (a.row_bytes + SLAB - 1) / SLAB;
+    uint32_t G = 1;
+    while (G < row_units && G < 128 / SLAB) G <<= 1;
+    const uint32_t chunks = (row_units + G - 1) / G;
+    const uint32_t gl = threadIdx.x & (G - 1);
+    const uint32_t seg = threadIdx.x / G, nseg = PROBE_THREADS / G;     // k-mer segment of this lane group
+    const uint64_t total = (uint64_t)a.n_queries * chunks;
+    const int lane = threadIdx.x & 31;
+
+    for (uint64_t g = blockIdx.x; g < total; g += gridDim.x) {
+        const uint32_t q = (uint32_t)(g / chunks);
+        const uint32_t chunk = (uint32_t)(g - (uint64_t)q * chunks);
+        const uint32_t n = a.n_eff[q];
+        const uint32_t colu = chunk * G + gl;
+        const bool active = n > 0 && colu < row_units;
+        uint32_t c[8][W];
+#pragma unroll
+        for (int p = 0; p < 8; p++)
+#pragma unroll
+            for (int w = 0; w < W; w++) c[p][w] = 0;
+#pragma unroll
+        for (int i = 0; i < P * W; i++) T[i * PROBE_THREADS] = 0;
+        if (active) {
+            const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
+            const uint8_t *colbase = a.rows + (uint64_t)colu * SLAB;
+            uint32_t L[PROBE_ROWS * H];
+            uint32_t acc = 0;
+            const uint32_t stride = nseg * PROBE_ROWS;
+            uint32_t i = seg * PROBE_ROWS;
+            if (i < n) load_locs<H>(L, lp, i, n);
+            for (; i < n; i += stride) {
+                Slab<W> r[PROBE_ROWS];
+                load_rows<H, W>(r, L, colbase, a.pitch);
+                if (i + stride < n) load_locs<H>(L, lp, i + stride, n);
+                if (acc + PROBE_ROWS > 255) { fold_planes<PH, W>(c, T); acc = 0; }
+                acc += PROBE_ROWS;
+                csa8<W>(c, r);
+            }
+            fold_planes<PH, W>(c, T);
+        }
+        __syncthreads();
+        // pairwise addition of the segments' totals: thread t += thread t + s*G
+        for (uint32_t s2 = nseg >> 1; s2 >= 1; s2 >>= 1) {
+            if (seg < s2) {
+                const uint32_t *O = T + s2 * G;
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    uint32_t carry = 0;
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        const uint32_t x = T[(p * W + w) * PROBE_THREADS], y = O[(p * W + w) * PROBE_THREADS];
+                        T[(p * W + w) * PROBE_THREADS] = xor3(x, y, carry);
+                        carry = maj3(x, y, carry);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- thresholds + hits: lane group 0 holds the totals ----
+        uint32_t ge[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) ge[w] = 0;
+        int nhit = 0;
+        const bool owner = active && seg == 0;
+        if (owner) {
+            const uint32_t Tq = a.thresh[q];
+            uint32_t high = (P < 32) ? (Tq >> P) : 0;
+            if (!high) {
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int p = P - 1; p >= 0; p--) {
+                        const uint32_t v = T[(p * W + w) * PROBE_THREADS];
+                        if ((Tq >> p) & 1) { eq &= v; }
+                        else { gt |= eq & v; eq &= ~v; }
+                    }
+                    ge[w] = gt | eq;
+                    nhit += __popc(ge[w]);
+                }
+            }
+            if (a.dense_counts) {
+#pragma unroll
+                for (int w = 0; w < W; w++)
+                    for (int bit = 0; bit < 32; bit++) {
+                        uint32_t t = (colu * SLAB + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                        if (t < a.n_names) {
+                            uint32_t cnt = 0;
+#pragma unroll
+                            for (int p = 0; p < P; p++) cnt |= ((T[(p * W + w) * PROBE_THREADS] >> bit) & 1u) << p;
+                            a.dense_counts[a.target_base + t] = cnt;
+                        }
+                    }
+            }
+        }
+        if (threadIdx.x < 32) {                                          // lane group 0 lives in warp 0 (G <= 32)
+            int incl = nhit;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (tot > 0) {
+                unsigned long long base = 0;
+                if (lane == 31) base = atomicAdd(a.hit_count, (unsigned long long)tot);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                unsigned long long slot = base + (unsigned long long)(incl - nhit);
+                if (nhit > 0) {
+#pragma unroll
+                    for (int w = 0; w < W; w++) {
+                        uint32_t m = ge[w];
+                        while (m) {
+                            int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            uint32_t t = (colu * SLAB + w * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                            uint32_t cnt = 0;
+#pragma unroll
+                            for (int p = 0; p < P; p++) cnt |= ((T[(p * W + w) * PROBE_THREADS] >> bit) & 1u) << p;
+                            if (slot < a.hit_cap) {
+                                a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
+                                a.hit_vals[slot] = cnt;
+                            }
+                            slot++;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                                 // the totals are reused by the next task
+    }
+}
+
+template <int H, int PH, int W>
+static cudaError_t launch_probe_long_k(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
+    const size_t smem = (size_t)(8 + PH) * W * PROBE_THREADS * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        static bool done = false;
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(probe_long_kernel<H, PH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            done = true;
+        }
+    }
+    probe_long_kernel<H, PH, W><<<blocks, PROBE_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 struct ProbeTune { int var = 2, minb = 2, cap = 16, var_h = 1, minb_h = 2, w_h = 2, g = 0; };
 static ProbeTune probe_tune() {
     // development knobs (tools/*.sh): KMCPG_PROBE_VAR / _MINB (h=1), KMCPG_PROBE_VARH / _MINBH / _WH (h>1), KMCPG_PROBE_CAP, KMCPG_PROBE_G
@@ -791,6 +1118,12 @@ static cudaError_t launch_probe_k(const ProbeArgs &a, uint32_t blocks, cudaStrea
 template <int H, int PH>
 static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     const ProbeTune t = probe_tune();
+    if constexpr (PH > 0) {
+        if (a.long_mode) {                                   // few long queries: one CTA per (query, chunk)
+            if constexpr (H == 1) return launch_probe_long_k<H, PH, 4>(a, blocks, st);
+            else return launch_probe_long_k<H, PH, 2>(a, blocks, st);
+        }
+    }
     // the development variants (documented in profiles/config_sweeps_r01.md) exist only for the 8-plane kernels
     if constexpr (PH == 0) {
         if (H == 1) {
@@ -825,6 +1158,25 @@ cudaError_t launch_probe(const ProbeArgs &a_in, int sm_count, cudaStream_t st) {
     ProbeArgs a = a_in;
     const ProbeTune t = probe_tune();
     a.lanes_per_task_override = (uint32_t)t.g;
+    {   // few long queries leave the lane-per-slab mapping without parallelism: give every (query, chunk) a whole CTA
+        const uint32_t slab = a.num_hashes == 1 ? 16 : 8;
+        const uint32_t row_units = (a.row_bytes + slab - 1) / slab;
+        uint32_t G = 1;
+        while (G < row_units && G < 128 / slab) G <<= 1;
+        const uint64_t tasks = (uint64_t)a.n_queries * ((row_units + G - 1) / G);
+        a.long_mode = a.planes > 8 && tasks * G < (uint64_t)sm_count * 512 && !getenv("KMCPG_PROBE_NOLONG");
+        if (a.long_mode) {
+            const uint64_t cap2 = (uint64_t)sm_count * (a.planes >= 32 ? 1 : 2);
+            uint32_t blocks = (uint32_t)(tasks < cap2 ? tasks : cap2);
+            switch (a.num_hashes) {
+                case 1: return launch_probe_h<1>(a, blocks, st);
+                case 2: return launch_probe_h<2>(a, blocks, st);
+                case 3: return launch_probe_h<3>(a, blocks, st);
+                case 4: return launch_probe_h<4>(a, blocks, st);
+                default: return cudaErrorInvalidValue;
+            }
+        }
+    }
     // upper bound of the thread demand (8-byte slabs need the most lanes); the grid is persistent-style anyway:
     // a multiple of the SM count, several CTAs per SM, each thread loops over tasks
     const uint64_t threads = (uint64_t)a.n_queries * ((a.row_bytes + 7) / 8 + 15);

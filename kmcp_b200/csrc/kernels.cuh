@@ -51,6 +51,13 @@ struct SelectArgs {
 cudaError_t launch_select(const SelectArgs &a, cudaStream_t st);
 cudaError_t launch_slot_bounds(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *slot_cnt, cudaStream_t st);
 cudaError_t launch_hash(const HashArgs &a, cudaStream_t st);
+// long sequences (genomes, long reads): warp per 4096-position tile + gather, same results in the same order
+constexpr uint32_t HASH_TILE_POS = 4096;
+cudaError_t launch_tiles_per_seq(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *cnt, cudaStream_t st);
+cudaError_t launch_hash_tiles(const HashArgs &a, uint32_t n_seqs, const uint64_t *tile_off, uint64_t max_tiles, uint64_t *tmp, uint32_t *tile_cnt,
+                              cudaStream_t st);
+cudaError_t launch_gather_tiles(const HashArgs &a, uint32_t n_seqs, const uint64_t *tile_off, const uint64_t *tile_pre, const uint32_t *tile_cnt,
+                                const uint64_t *tmp, uint64_t max_tiles, cudaStream_t st);
 
 // in-place unique of sorted regions longer than the dedup threshold (U:874-908), and the per-query verdict
 struct FinalizeArgs {
@@ -103,6 +110,7 @@ struct ProbeArgs {
     uint64_t hit_cap;
     uint32_t *dense_counts;     // optional [n_queries=1][n_targets] dump of all counts (kmcpg_count_codes)
     int planes;                 // counter bits: 8, 16, 24, 32
+    int long_mode;              // set by launch_probe: one CTA per (query, chunk) for few long queries
 };
 cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st);
 
