@@ -295,7 +295,11 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
     for (auto &b : ctx->blocks) {
         const BlockMeta &bm = ctx->meta.blocks[b.meta_idx];
         CU(cudaEventRecord(w.probe_ev[bi * 3], st));
-        CU(launch_locs(w.codes_ptr, w.sb.total_slots, H, b.fm, w.locs.as<uint32_t>(), st)); ctx->launches++;
+        if (ctx->meta.scaled || ctx->meta.minimizer || ctx->meta.syncmer)
+            CU(launch_locs_by_query(w.codes_ptr, w.slot_off.as<uint64_t>(), w.neff.as<uint32_t>(), w.nq, p.paired, H, b.fm, w.locs.as<uint32_t>(), st));
+        else
+            CU(launch_locs(w.codes_ptr, w.sb.total_slots, H, b.fm, w.locs.as<uint32_t>(), st));
+        ctx->launches++;
         CU(cudaEventRecord(w.probe_ev[bi * 3 + 1], st));
         ProbeArgs pa;
         memset(&pa, 0, sizeof(pa));

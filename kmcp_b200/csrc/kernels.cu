@@ -633,6 +633,46 @@ __global__ void __launch_bounds__(256) locs_kernel(const uint64_t *__restrict__ 
     }
 }
 
+// sketch databases: the code regions are mostly empty (FracMinHash keeps ~2/scale of the positions), so walk the
+// queries instead of the slots: one warp per query, only its n_eff codes
+template <int H>
+__global__ void __launch_bounds__(256) locs_query_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ n_eff,
+                                                         uint32_t nq, int paired, FastMod fm, uint32_t *__restrict__ locs) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = warp; q < nq; q += n_warps) {
+        const uint32_t n = n_eff[q];
+        const uint64_t base = slot_off[paired ? 2 * q : q];
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint64_t code = codes[base + i];
+            if (H == 1) {
+                locs[base + i] = (uint32_t)fastmod_dev(code, fm.m_hi, fm.m_lo, fm.d);
+            } else {
+                const uint32_t x = (uint32_t)(code >> 32), y = (uint32_t)code;
+#pragma unroll
+                for (uint32_t j = 0; j < (uint32_t)H; j++)
+                    locs[(base + i) * H + j] = (uint32_t)fastmod_dev((uint64_t)(uint32_t)(x + y * j), fm.m_hi, fm.m_lo, fm.d);
+            }
+        }
+    }
+}
+
+cudaError_t launch_locs_by_query(const uint64_t *codes, const uint64_t *slot_off, const uint32_t *n_eff, uint32_t nq, int paired, int h, FastMod fm,
+                                 uint32_t *locs, cudaStream_t st) {
+    if (!nq) return cudaSuccess;
+    uint32_t blocks = (nq + 7) / 8;
+    if (blocks > 148u * 32u) blocks = 148u * 32u;
+    switch (h) {
+        case 1: locs_query_kernel<1><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        case 2: locs_query_kernel<2><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        case 3: locs_query_kernel<3><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        case 4: locs_query_kernel<4><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_locs(const uint64_t *codes, uint64_t n, int h, FastMod fm, uint32_t *locs, cudaStream_t st) {
     if (!n) return cudaSuccess;
     uint64_t blocks64 = (n + 255) / 256;

@@ -88,6 +88,9 @@ cudaError_t launch_small_dedup(uint64_t *codes, const uint64_t *slot_off, uint32
 // ---- kernel 2a: code → row index of one block (hashValues + fastdiv.Mod; H:125-141, U:6811) ------------
 cudaError_t launch_locs(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint32_t *locs,
                         cudaStream_t st);
+// same, walking the queries (sketch databases leave most slots empty)
+cudaError_t launch_locs_by_query(const uint64_t *codes, const uint64_t *slot_off, const uint32_t *n_eff, uint32_t n_queries, int paired,
+                                 int num_hashes, FastMod fm, uint32_t *locs, cudaStream_t st);
 
 // ---- kernel 2b: the COBS probe of one block (U:6613-7741) ----------------------------------------------
 struct ProbeArgs {
