@@ -142,11 +142,11 @@ def time_cpu_port(r001, reads_u8, n_reads, target_seconds=12.0):
     off_all = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN)
     n0 = min(CPU_SAMPLE0, n_reads)
     t0 = time.perf_counter()
-    odb.search(packed=(reads_u8[: n0 * READ_LEN], off_all[: n0 + 1]), threads=0, algo=1)
+    odb.search(packed=(reads_u8[: n0 * READ_LEN], off_all[: n0 + 1]), threads=cores, algo=1)
     dt0 = time.perf_counter() - t0
     n1 = int(min(n_reads, max(n0, n0 * target_seconds / max(dt0, 1e-6))))
     t0 = time.perf_counter()
-    odb.search(packed=(reads_u8[: n1 * READ_LEN], off_all[: n1 + 1]), threads=0, algo=1)
+    odb.search(packed=(reads_u8[: n1 * READ_LEN], off_all[: n1 + 1]), threads=cores, algo=1)
     dt = time.perf_counter() - t0
     odb.close()
     return n1 / dt, cores, n1
@@ -181,7 +181,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     off = np.arange(step_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN)
     def step(i):
-        odb.search(packed=(reads[i * step_reads * READ_LEN:(i + 1) * step_reads * READ_LEN], off), threads=0, algo=1)
+        odb.search(packed=(reads[i * step_reads * READ_LEN:(i + 1) * step_reads * READ_LEN], off), threads=cores, algo=1)   # explicit: torchrun sets OMP_NUM_THREADS=1
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()

@@ -565,3 +565,17 @@ def test_streaming_parts_equal_the_batch_result(gpu_ctx, oracle, small_db):
     assert np.array_equal(np.concatenate([p[3] for p in parts]), whole.hits)
     assert np.array_equal(np.concatenate([p[2] for p in parts]), whole.n_kmers)
     assert np.array_equal(summary.hits, whole.hits)
+
+
+def test_degenerate_batches(gpu_ctx, oracle, small_db):
+    """empty batch, batch of empty / too-short sequences only, a single read"""
+    from kmcp_b200 import api
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    r = gpu_ctx.search_batch(np.zeros(1, np.uint8), np.zeros(1, np.uint64))
+    assert len(r.hits) == 0 and len(r.n_kmers) == 0
+    e = gpu_ctx.engine_search(np.zeros(1, np.uint8), np.zeros(1, np.uint64))
+    assert len(e.matches) == 0 and len(e.match_off) == 1
+    _compare_engine(O, odb, gpu_ctx, [b"", b"ACGT", b""])
+    _compare_engine(O, odb, gpu_ctx, helpers.make_reads(O, 77, 1, 40, 30000, GSEED))
