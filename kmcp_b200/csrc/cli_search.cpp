@@ -15,9 +15,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <future>
 #include <map>
+#include <mutex>
 #include <regex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kmcp_gpu.h"
@@ -58,9 +63,19 @@ void logf(const char *level, const char *fmt, ...) {
 bool is_dir(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
 bool is_file(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
 
+struct Less {                       // the engine's match order (U:105-145), used again when several databases are merged
+    int sort_by;
+    int score(const kmcpg_match &a, const kmcpg_match &b) const {      // <0: a first
+        if (sort_by == 0) { if (a.qcov != b.qcov) return a.qcov > b.qcov ? -1 : 1; if (a.tcov != b.tcov) return a.tcov > b.tcov ? -1 : 1; }
+        else if (sort_by == 1) { if (a.tcov != b.tcov) return a.tcov > b.tcov ? -1 : 1; if (a.count != b.count) return a.count > b.count ? -1 : 1; }
+        else { if (a.jacc != b.jacc) return a.jacc > b.jacc ? -1 : 1; if (a.count != b.count) return a.count > b.count ? -1 : 1; }
+        return 0;
+    }
+};
+
 struct Opts {
-    std::string db_dir, out_file = "-", read1, read2, sort_by = "qcov", query_id, log_file;
-    std::vector<std::string> files, name_maps;
+    std::string out_file = "-", read1, read2, sort_by = "qcov", query_id, log_file;
+    std::vector<std::string> db_dirs, files, name_maps;   // several -d: every database is searched, results merged as `kmcp merge` does
     int dedup = 256, min_kmers = 10, min_qlen = 30, top_scores = 0, threads = 0, device = 0;
     double qcov = 0.55, tcov = 0, max_fpr = 0.01;
     bool try_se = false, whole_file = false, use_filename = false, default_name_map = false, keep_unmatched = false, no_header = false,
@@ -152,23 +167,44 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     }
 };
 
+// one complete gzip member for a block of text (concatenated members are a valid .gz stream, as pgzip writes them)
+std::string gz_member(const char *data, size_t n) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (deflateInit2(&zs, 6, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib init failed");
+    std::string out(deflateBound(&zs, (uLong)n) + 64, '\0');
+    zs.next_in = (Bytef *)data; zs.avail_in = (uInt)n;
+    zs.next_out = (Bytef *)&out[0]; zs.avail_out = (uInt)out.size();
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die("zlib deflate failed");
+    out.resize(zs.total_out);
+    deflateEnd(&zs);
+    return out;
+}
+
 struct Writer {
     FILE *fp = nullptr;
-    gzFile gz = nullptr;
-    std::string buf;
+    bool gz = false;
+    int threads = 8;
     void open(const std::string &p) {
         if (p == "-") fp = stdout;
-        else if (p.size() > 3 && p.compare(p.size() - 3, 3, ".gz") == 0) { gz = gzopen(p.c_str(), "wb6"); if (!gz) die("fail to write %s", p.c_str()); gzbuffer(gz, 1 << 20); }
         else { fp = fopen(p.c_str(), "wb"); if (!fp) die("fail to write %s", p.c_str()); }
-        buf.reserve(8 << 20);
+        gz = p.size() > 3 && p.compare(p.size() - 3, 3, ".gz") == 0;
     }
-    void flush() {
-        if (buf.empty()) return;
-        if (gz) gzwrite(gz, buf.data(), (unsigned)buf.size()); else fwrite(buf.data(), 1, buf.size(), fp);
-        buf.clear();
+    // text → file; .gz output is compressed in 8 MB blocks by several threads (independent gzip members, in order)
+    void write(const char *s, size_t n) {
+        if (!n) return;
+        if (!gz) { fwrite(s, 1, n, fp); return; }
+        const size_t BLK = 8u << 20;
+        std::deque<std::future<std::string>> inflight;
+        for (size_t o = 0; o < n; o += BLK) {
+            const size_t len = std::min(BLK, n - o);
+            inflight.push_back(std::async(std::launch::async, gz_member, s + o, len));
+            if ((int)inflight.size() >= threads) { std::string z = inflight.front().get(); inflight.pop_front(); fwrite(z.data(), 1, z.size(), fp); }
+        }
+        while (!inflight.empty()) { std::string z = inflight.front().get(); inflight.pop_front(); fwrite(z.data(), 1, z.size(), fp); }
     }
-    void write(const char *s, size_t n) { buf.append(s, n); if (buf.size() > (4u << 20)) flush(); }
-    void close() { flush(); if (gz) gzclose(gz); else if (fp && fp != stdout) fclose(fp); else if (fp) fflush(fp); }
+    void write(const std::string &t) { write(t.data(), t.size()); }
+    void close() { if (fp && fp != stdout) fclose(fp); else if (fp) fflush(fp); }
 };
 
 
@@ -278,7 +314,7 @@ int main(int argc, char **argv) {
         if (a.rfind("--", 0) == 0) { size_t eq = a.find('='); if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_eq = true; } }
         auto sval = [&]() -> std::string { return has_eq ? val : std::string(need(i)); };
         if (a == "-h" || a == "--help") { usage(); return 0; }
-        else if (a == "-d" || a == "--db-dir") o.db_dir = sval();
+        else if (a == "-d" || a == "--db-dir") o.db_dirs.push_back(sval());
         else if (a == "-o" || a == "--out-file") o.out_file = sval();
         else if (a == "-1" || a == "--read1") o.read1 = sval();
         else if (a == "-2" || a == "--read2") o.read2 = sval();
@@ -312,7 +348,7 @@ int main(int argc, char **argv) {
     auto t_start = std::chrono::steady_clock::now();
 
     // ---- flag checks (S:157-205) ----
-    if (o.db_dir.empty()) die("flag -d/--db-dir needed");
+    if (o.db_dirs.empty()) die("flag -d/--db-dir needed");
     if (o.min_qlen < 0) die("value of flag --min-query-len should be greater than or equal to 0");
     if (o.min_kmers <= 0) die("value of flag --min-kmers should be greater than 0");
     if (!(o.max_fpr > 0)) die("value of flag --max-fpr should be greater than 0");
@@ -339,49 +375,60 @@ int main(int argc, char **argv) {
         for (auto &f : files) if (f != "-" && f == o.out_file) die("out file should not be one of the input file");
     }
 
-    // ---- database (S:299-324): every child directory holding __db.yml ----
-    logf("INFO", "checking the database: %s", o.db_dir.c_str());
-    std::vector<std::string> dbs;
-    DIR *d = opendir(o.db_dir.c_str());
-    if (!d) die("read database error: open %s: no such file or directory", o.db_dir.c_str());
-    while (dirent *e = readdir(d)) {
-        if (e->d_name[0] == '.') continue;
-        std::string p = o.db_dir + "/" + e->d_name;
-        if (is_dir(p) && is_file(p + "/__db.yml")) dbs.push_back(p);
+    // ---- databases (S:299-324): every child directory of a -d holding __db.yml; several -d = several databases ----
+    struct Db {
+        std::string dir;
+        kmcpg_ctx *ctx = nullptr;
+        kmcpg_db_info_t info;
+        std::vector<kmcpg_target_t> targets;
+        std::vector<const std::string *> mapped;
+        std::map<std::string, std::string> name_map;
+    };
+    std::vector<Db> dbs;
+    for (auto &dd : o.db_dirs) {
+        logf("INFO", "checking the database: %s", dd.c_str());
+        std::vector<std::string> subs;
+        DIR *d = opendir(dd.c_str());
+        if (!d) die("read database error: open %s: no such file or directory", dd.c_str());
+        while (dirent *e = readdir(d)) {
+            if (e->d_name[0] == '.') continue;
+            std::string p = dd + "/" + e->d_name;
+            if (is_dir(p) && is_file(p + "/__db.yml")) subs.push_back(p);
+        }
+        closedir(d);
+        std::sort(subs.begin(), subs.end());
+        if (subs.empty()) die("invalid kmcp database: %s", dd.c_str());
+        if (subs.size() > 1) die("databases with several repeats (R001, R002, ...) are not supported by kmcp-gpu yet: %s", dd.c_str());
+        dbs.emplace_back();
+        dbs.back().dir = subs[0];
     }
-    closedir(d);
-    std::sort(dbs.begin(), dbs.end());
-    if (dbs.empty()) die("invalid kmcp database: %s", o.db_dir.c_str());
-    if (dbs.size() > 1) die("databases with several repeats (R001, R002, ...) are not supported by kmcp-gpu yet");
-
-    kmcpg_ctx *ctx = nullptr;
-    if (kmcpg_create(o.device, &ctx)) die("%s", kmcpg_last_error(nullptr));
-    logf("INFO", "loading database into HBM ...");
-    auto t_db = std::chrono::steady_clock::now();
-    if (kmcpg_open_db(ctx, dbs[0].c_str(), nullptr)) die("open kmcp db: %s: %s", dbs[0].c_str(), kmcpg_last_error(ctx));
-    kmcpg_db_info_t info;
-    kmcpg_db_info(ctx, &info);
-    logf("INFO", "database loaded: %s (%d blocks, %lld targets, %.2f GB in HBM, %.1f s)", o.db_dir.c_str(), info.n_blocks, (long long)info.n_targets,
-         info.resident_bytes / 1e9, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_db).count());
-    if (o.qcov <= info.fpr)      // S:405-409
-        logf("WARN", "the value of -t/--min-query-cov (%f) is <= FPR (%f) of the database, you may get many false positives", o.qcov, info.fpr);
+    for (auto &db : dbs) {
+        if (kmcpg_create(o.device, &db.ctx)) die("%s", kmcpg_last_error(nullptr));
+        logf("INFO", "loading database into HBM: %s", db.dir.c_str());
+        auto t_db = std::chrono::steady_clock::now();
+        if (kmcpg_open_db(db.ctx, db.dir.c_str(), nullptr)) die("open kmcp db: %s: %s", db.dir.c_str(), kmcpg_last_error(db.ctx));
+        kmcpg_db_info(db.ctx, &db.info);
+        logf("INFO", "database loaded: %s (%d blocks, %lld targets, %.2f GB in HBM, %.1f s)", db.dir.c_str(), db.info.n_blocks, (long long)db.info.n_targets,
+             db.info.resident_bytes / 1e9, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_db).count());
+        if (o.qcov <= db.info.fpr)      // S:405-409
+            logf("WARN", "the value of -t/--min-query-cov (%f) is <= FPR (%f) of the database, you may get many false positives", o.qcov, db.info.fpr);
+        if (db.info.ks[0] != dbs[0].info.ks[0]) die("databases with different k cannot be searched together");
+        if (o.default_name_map && is_file(db.dir + "/__name_mapping.tsv")) load_kv(db.dir + "/__name_mapping.tsv", db.name_map);
+        for (auto &f : o.name_maps) load_kv(f, db.name_map);       // user maps override the default one (U:322-330)
+        db.targets.resize((size_t)db.info.n_targets);
+        db.mapped.assign((size_t)db.info.n_targets, nullptr);
+        for (int64_t t = 0; t < db.info.n_targets; t++) {
+            kmcpg_target(db.ctx, t, &db.targets[(size_t)t]);
+            auto it = db.name_map.find(db.targets[(size_t)t].name);
+            if (it != db.name_map.end()) db.mapped[(size_t)t] = &it->second;
+        }
+    }
     logf("INFO", "-------------------- [main parameters] --------------------");
     logf("INFO", "  minimum    query length: %d", o.min_qlen);
     logf("INFO", "  minimum  matched k-mers: %d", o.min_kmers);
     logf("INFO", "  minimum  query coverage: %f", o.qcov);
     logf("INFO", "  minimum target coverage: %f", o.tcov);
     logf("INFO", "-------------------- [main parameters] --------------------");
-
-    std::map<std::string, std::string> name_map;
-    if (o.default_name_map && is_file(dbs[0] + "/__name_mapping.tsv")) load_kv(dbs[0] + "/__name_mapping.tsv", name_map);
-    for (auto &f : o.name_maps) load_kv(f, name_map);       // user maps override the default one (U:322-330)
-    std::vector<const std::string *> mapped((size_t)info.n_targets, nullptr);
-    std::vector<kmcpg_target_t> targets((size_t)info.n_targets);
-    for (int64_t t = 0; t < info.n_targets; t++) {
-        kmcpg_target(ctx, t, &targets[(size_t)t]);
-        auto it = name_map.find(targets[(size_t)t].name);
-        if (it != name_map.end()) mapped[(size_t)t] = &it->second;
-    }
 
     Writer w;
     w.open(o.out_file);
@@ -396,89 +443,184 @@ int main(int argc, char **argv) {
     eo.max_fpr = o.max_fpr; eo.sort_by = sort_by; eo.do_not_sort = o.do_not_sort; eo.top_n_scores = o.top_scores; eo.try_se = o.try_se;
     eo.paired = paired; eo.threads = o.threads;
 
-    // ---- batches: ids + packed sequences → engine → TSV in input order ----
-    std::vector<std::string> ids;
-    std::vector<uint8_t> seqbuf;
-    std::vector<uint64_t> offs(1, 0);
-    uint64_t total = 0, matched = 0, query_base = 0;
-    char line[512];
-    auto flush_batch = [&]() {
-        if (ids.empty()) return;
-        if (seqbuf.empty()) seqbuf.push_back(0);
-        kmcpg_results r;
-        if (kmcpg_engine_search(ctx, &eo, seqbuf.data(), offs.data(), (uint32_t)(offs.size() - 1), &r)) die("%s", kmcpg_last_error(ctx));
-        for (uint32_t q = 0; q < r.n_queries; q++) {
-            const uint64_t a = r.match_off[q], b = r.match_off[q + 1];
-            const std::string &id = ids[q];
-            if (a == b) {
-                if (!o.keep_unmatched) continue;
-                int n = snprintf(line, sizeof(line), "\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%llu\n", r.query_len[q], r.n_kmers[q], r.k_used[q],     // S:460-511
-                                 (unsigned long long)(query_base + q));
-                w.write(id.data(), id.size()); w.write(line, (size_t)n);
-                continue;
+    // ---- three-stage pipeline: reader thread (inflate + parse + pack) → this thread (GPU engine, every database) →
+    //      writer thread (merge across databases, TSV formatting on several threads, parallel gzip), all in input order ----
+    struct Batch { std::vector<std::string> ids; std::vector<uint8_t> seq; std::vector<uint64_t> off{0}; uint64_t base = 0; };
+    struct Job { Batch *batch = nullptr; std::vector<kmcpg_results> res; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Batch *> in_q;
+    std::deque<Job *> out_q;
+    bool in_done = false, out_done = false;
+    uint64_t total = 0, matched = 0;
+    const int kmax = dbs[0].info.ks[0];
+
+    std::thread reader([&] {
+        Batch *cur = new Batch();
+        uint64_t next_base = 0;
+        auto emit = [&]() {
+            if (cur->ids.empty()) return;
+            if (cur->seq.empty()) cur->seq.push_back(0);
+            cur->base = next_base;
+            next_base += cur->ids.size();
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return in_q.size() < 2; });
+            in_q.push_back(cur);
+            cv.notify_all();
+            cur = new Batch();
+        };
+        auto add_seq = [&](const std::string &sq) { cur->seq.insert(cur->seq.end(), sq.begin(), sq.end()); cur->off.push_back(cur->seq.size()); };
+        std::string id, seq, id2, seq2;
+        if (paired) {
+            Reader r1, r2;
+            if (!r1.open(o.read1)) die("%s: no such file", o.read1.c_str());
+            if (!r2.open(o.read2)) die("%s: no such file", o.read2.c_str());
+            logf("INFO", "reading from paired-end files: %s, %s", o.read1.c_str(), o.read2.c_str());
+            while (r1.next(id, seq) && r2.next(id2, seq2)) {          // S:806-867: ID of read1
+                cur->ids.push_back(id); add_seq(seq); add_seq(seq2);
+                if (cur->ids.size() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
             }
-            matched++;
-            for (uint64_t i = a; i < b; i++) {
-                const kmcpg_match &m = r.matches[i];
-                const kmcpg_target_t &t = targets[m.target];
-                const std::string *mp = mapped[m.target];
-                int n1 = snprintf(line, sizeof(line), "\t%d\t%d\t%.4e\t%llu\t", r.query_len[q], r.n_kmers[q], m.fpr, (unsigned long long)(b - a));
-                w.write(id.data(), id.size()); w.write(line, (size_t)n1);
-                if (mp) w.write(mp->data(), mp->size()); else w.write(t.name, strlen(t.name));
-                int n2 = snprintf(line, sizeof(line), "\t%u\t%u\t%llu\t%d\t%u\t%.4f\t%.4f\t%.4f\t%llu\n", t.index & 0xFFFFu, t.index >> 16,          // S:532-539
-                                  (unsigned long long)t.genome_size, r.k_used[q], m.count, m.qcov, m.tcov, m.jacc, (unsigned long long)(query_base + q));
-                w.write(line, (size_t)n2);
+            r1.close(); r2.close();
+        } else {
+            for (auto &file : files) {
+                logf("INFO", "reading sequence file: %s", file.c_str());
+                Reader r;
+                if (!r.open(file)) die("%s: no such file", file.c_str());
+                if (o.whole_file) {                                   // S:885-937 (the N-run follows every record after the second)
+                    std::string qid, whole;
+                    bool first = true;
+                    while (r.next(id, seq)) {
+                        if (first) { qid = o.use_filename ? trim_ext(file) : (!o.query_id.empty() ? o.query_id : id); whole = seq; first = false; }
+                        else { whole += seq; whole.append((size_t)(kmax - 1), 'N'); }
+                    }
+                    if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); r.close(); continue; }
+                    cur->ids.push_back(qid); add_seq(whole);
+                    if (cur->seq.size() >= o.batch_bytes) emit();
+                } else {
+                    bool any = false;
+                    while (r.next(id, seq)) {
+                        any = true;
+                        cur->ids.push_back(id); add_seq(seq);
+                        if (cur->ids.size() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
+                    }
+                    if (!any) logf("WARN", "no valid sequences in file: %s", file.c_str());
+                }
+                r.close();
             }
         }
-        total += r.n_queries;
-        query_base += r.n_queries;
-        kmcpg_free_results(&r);
-        ids.clear(); seqbuf.clear(); offs.assign(1, 0);
-        if (!g_quiet) fprintf(stderr, "processed queries: %llu\r", (unsigned long long)total);
-    };
-    auto add_seq = [&](const std::string &s) { seqbuf.insert(seqbuf.end(), s.begin(), s.end()); offs.push_back(seqbuf.size()); };
+        emit();
+        delete cur;
+        std::lock_guard<std::mutex> lk(mu);
+        in_done = true;
+        cv.notify_all();
+    });
+
+    const Less less{sort_by};
+    std::thread writer([&] {
+        const int FT = 16;                                            // formatting threads per batch
+        for (;;) {
+            Job *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !out_q.empty() || out_done; });
+                if (out_q.empty()) return;
+                job = out_q.front(); out_q.pop_front();
+                cv.notify_all();
+            }
+            const Batch &bt = *job->batch;
+            const uint32_t nq = (uint32_t)bt.ids.size();
+            std::vector<std::string> text(FT);
+            std::vector<uint64_t> nmatched(FT, 0);
+            auto fmt = [&](int t) {
+                char line[512];
+                std::string &out = text[t];
+                const uint32_t lo = (uint32_t)((uint64_t)nq * t / FT), hi = (uint32_t)((uint64_t)nq * (t + 1) / FT);
+                out.reserve((size_t)(hi - lo) * 96);
+                std::vector<std::pair<kmcpg_match, int>> merged;      // (match, database) of one query when several databases are searched
+                for (uint32_t q = lo; q < hi; q++) {
+                    const std::string &id = bt.ids[q];
+                    const kmcpg_results &r0 = job->res[0];
+                    uint64_t hits = 0;
+                    for (auto &r : job->res) hits += r.match_off[q + 1] - r.match_off[q];
+                    if (hits == 0) {
+                        if (!o.keep_unmatched) continue;
+                        int n = snprintf(line, sizeof(line), "\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%llu\n", r0.query_len[q], r0.n_kmers[q], r0.k_used[q],     // S:460-511
+                                         (unsigned long long)(bt.base + q));
+                        out.append(id); out.append(line, (size_t)n);
+                        continue;
+                    }
+                    nmatched[t]++;
+                    auto put = [&](const kmcpg_results &r, const Db &db, const kmcpg_match &m) {
+                        const kmcpg_target_t &tg = db.targets[m.target];
+                        const std::string *mp = db.mapped[m.target];
+                        int n1 = snprintf(line, sizeof(line), "\t%d\t%d\t%.4e\t%llu\t", r.query_len[q], r.n_kmers[q], m.fpr, (unsigned long long)hits);
+                        out.append(id); out.append(line, (size_t)n1);
+                        if (mp) out.append(*mp); else out.append(tg.name);
+                        int n2 = snprintf(line, sizeof(line), "\t%u\t%u\t%llu\t%d\t%u\t%.4f\t%.4f\t%.4f\t%llu\n", tg.index & 0xFFFFu, tg.index >> 16,          // S:532-539
+                                          (unsigned long long)tg.genome_size, r.k_used[q], m.count, m.qcov, m.tcov, m.jacc, (unsigned long long)(bt.base + q));
+                        out.append(line, (size_t)n2);
+                    };
+                    if (job->res.size() == 1) {
+                        for (uint64_t i = r0.match_off[q]; i < r0.match_off[q + 1]; i++) put(r0, dbs[0], r0.matches[i]);
+                    } else {                                          // union of the databases' hits, re-sorted (merge.go:190-256)
+                        merged.clear();
+                        for (size_t d = 0; d < job->res.size(); d++)
+                            for (uint64_t i = job->res[d].match_off[q]; i < job->res[d].match_off[q + 1]; i++) merged.push_back({job->res[d].matches[i], (int)d});
+                        if (!o.do_not_sort)
+                            std::stable_sort(merged.begin(), merged.end(), [&](const std::pair<kmcpg_match, int> &a, const std::pair<kmcpg_match, int> &b) {
+                                const int c = less.score(a.first, b.first);           // ties: database order, then target index
+                                if (c) return c < 0;
+                                if (a.second != b.second) return a.second < b.second;
+                                return a.first.target < b.first.target;
+                            });
+                        for (auto &mm : merged) put(job->res[mm.second], dbs[mm.second], mm.first);
+                    }
+                }
+            };
+            std::vector<std::future<void>> fs;
+            for (int t = 1; t < FT; t++) fs.push_back(std::async(std::launch::async, fmt, t));
+            fmt(0);
+            for (auto &f : fs) f.get();
+            std::string all;
+            size_t sz = 0;
+            for (auto &t : text) sz += t.size();
+            all.reserve(sz);
+            for (auto &t : text) all += t;
+            w.write(all);
+            for (auto v : nmatched) matched += v;
+            total += nq;
+            for (auto &r : job->res) kmcpg_free_results(&r);
+            delete job->batch;
+            delete job;
+            if (!g_quiet) fprintf(stderr, "processed queries: %llu\r", (unsigned long long)total);
+        }
+    });
 
     logf("INFO", "searching ...");
     auto t_search = std::chrono::steady_clock::now();
-    std::string id, seq, id2, seq2;
-    if (paired) {
-        Reader r1, r2;
-        if (!r1.open(o.read1)) die("%s: no such file", o.read1.c_str());
-        if (!r2.open(o.read2)) die("%s: no such file", o.read2.c_str());
-        logf("INFO", "reading from paired-end files: %s, %s", o.read1.c_str(), o.read2.c_str());
-        while (r1.next(id, seq) && r2.next(id2, seq2)) {          // S:806-867: ID of read1
-            ids.push_back(id); add_seq(seq); add_seq(seq2);
-            if (ids.size() >= o.batch_reads || seqbuf.size() >= o.batch_bytes) flush_batch();
+    for (;;) {
+        Batch *bt = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !in_q.empty() || in_done; });
+            if (in_q.empty()) break;
+            bt = in_q.front(); in_q.pop_front();
+            cv.notify_all();
         }
-        r1.close(); r2.close();
-    } else {
-        const int kmax = info.ks[0];
-        for (auto &file : files) {
-            logf("INFO", "reading sequence file: %s", file.c_str());
-            Reader r;
-            if (!r.open(file)) die("%s: no such file", file.c_str());
-            if (o.whole_file) {                                   // S:885-937 (the N-run follows every record after the second)
-                std::string qid, whole;
-                bool first = true;
-                while (r.next(id, seq)) {
-                    if (first) { qid = o.use_filename ? trim_ext(file) : (!o.query_id.empty() ? o.query_id : id); whole = seq; first = false; }
-                    else { whole += seq; whole.append((size_t)(kmax - 1), 'N'); }
-                }
-                if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); r.close(); continue; }
-                ids.push_back(qid); add_seq(whole);
-                if (seqbuf.size() >= o.batch_bytes) flush_batch();
-            } else {
-                uint64_t n0 = ids.size() + total;
-                while (r.next(id, seq)) {
-                    ids.push_back(id); add_seq(seq);
-                    if (ids.size() >= o.batch_reads || seqbuf.size() >= o.batch_bytes) flush_batch();
-                }
-                if (ids.size() + total == n0) logf("WARN", "no valid sequences in file: %s", file.c_str());
-            }
-            r.close();
-        }
+        Job *job = new Job();
+        job->batch = bt;
+        job->res.resize(dbs.size());
+        for (size_t d = 0; d < dbs.size(); d++)
+            if (kmcpg_engine_search(dbs[d].ctx, &eo, bt->seq.data(), bt->off.data(), (uint32_t)(bt->off.size() - 1), &job->res[d])) die("%s", kmcpg_last_error(dbs[d].ctx));
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return out_q.size() < 2; });
+        out_q.push_back(job);
+        cv.notify_all();
     }
-    flush_batch();
+    reader.join();
+    { std::lock_guard<std::mutex> lk(mu); out_done = true; cv.notify_all(); }
+    writer.join();
+    char line[512];
 
     double minutes = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_search).count() / 60.0;
     if (!g_quiet) fprintf(stderr, "\n");
@@ -491,7 +633,7 @@ int main(int argc, char **argv) {
                      (unsigned long long)matched, total ? (double)matched / (double)total * 100 : NAN);
     w.write(line, (size_t)n);
     w.close();
-    kmcpg_close(ctx);
+    for (auto &db : dbs) kmcpg_close(db.ctx);
     logf("INFO", "");
     logf("INFO", "elapsed time: %.3fs", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
     if (g_log) fclose(g_log);

@@ -366,6 +366,46 @@ def test_cli_tsv_is_byte_identical_to_the_oracle_formatter(oracle, small_db, tmp
     assert open(out4).read() == exp4
 
 
+def test_cli_several_databases_are_merged_like_kmcp_merge(oracle, small_db, tmp_path):
+    """`-d A -d B`: every database searched, rows of a query united, re-sorted by score, `hits` rewritten (merge.go:190-256)"""
+    O = oracle
+    sp = O.sketch_params(21)
+    targets = helpers.make_synth_targets(O, sp, GSEED, 40, 30000, 5, 150)
+    # second database: other genomes plus ten genomes shared with the first (so queries hit both)
+    t2 = helpers.make_synth_targets(O, sp, GSEED + 5, 20, 30000, 5, 150) + targets[150:]
+    r2 = O.build_db(t2, str(tmp_path / "db2"), sp, num_hashes=1, fpr=0.3, block_size=64)
+    dbs = [O.DB(small_db), O.DB(r2)]
+    reads = helpers.make_reads(O, RSEED + 50, 1200, 40, 30000, GSEED) + helpers.make_reads(O, RSEED + 51, 500, 20, 30000, GSEED + 5)
+    ids = [b"q%d" % i for i in range(len(reads))]
+    fq = str(tmp_path / "q.fq")
+    _write_fastq(fq, ids, reads, gz=False)
+    out = str(tmp_path / "m.tsv")
+    _run_cli(["-d", os.path.dirname(small_db), "-d", os.path.dirname(r2), fq, "-o", out, "-K"])
+    res = [d.search(reads) for d in dbs]
+    exp = [O.TSV_HEADER]
+    matched = 0
+    for q in range(len(ids)):
+        rows = []
+        for di, (d, r) in enumerate(zip(dbs, res)):
+            for h in r.hits[int(r.hit_off[q]):int(r.hit_off[q + 1])]:
+                rows.append((-float(h["qcov"]), -float(h["tcov"]), di, int(h["target"]), h, d, r))
+        if not rows:
+            r = res[0]
+            exp.append("%s\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%d\n" % (ids[q].decode(), r.query_len[q], r.n_kmers[q], r.k_used[q], q))
+            continue
+        matched += 1
+        rows.sort(key=lambda x: x[:4])
+        for _, _, _, _, h, d, r in rows:
+            t = d.target(int(h["target"]))
+            exp.append("%s\t%d\t%d\t%s\t%d\t%s\t%d\t%d\t%d\t%d\t%d\t%.4f\t%.4f\t%.4f\t%d\n" % (
+                ids[q].decode(), r.query_len[q], r.n_kmers[q], O.go_fmt_e4(float(h["fpr"])), len(rows), t.name.decode(), t.index & 0xFFFF, t.index >> 16,
+                t.genome_size, r.k_used[q], int(h["count"]), float(h["qcov"]), float(h["tcov"]), float(h["jacc"]), q))
+    exp.append("# input queries: %d\n# matched queries: %d\n# matched percentage: %.4f%%\n" % (len(ids), matched, matched / len(ids) * 100))
+    got = open(out).read()
+    assert got == "".join(exp)
+    assert sum(1 for l in got.splitlines() if l.split("\t")[4:5] not in ([], ["0"], ["1"], ["hits"])) > 100      # queries with hits in both databases
+
+
 # ---------------------------------------------------------------------------------------------------- sketches
 @pytest.mark.parametrize("k,kw", [(31, dict(syncmer_s=15)), (31, dict(syncmer_s=15, scaled=True, scale=4)), (21, dict(syncmer_s=11)),
                                   (21, dict(syncmer_s=20)), (21, dict(syncmer_s=1)), (21, dict(minimizer_w=5)),
