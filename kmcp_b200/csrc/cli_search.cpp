@@ -80,7 +80,7 @@ struct Opts {
     double qcov = 0.55, tcov = 0, max_fpr = 0.01;
     bool try_se = false, whole_file = false, use_filename = false, default_name_map = false, keep_unmatched = false, no_header = false,
          do_not_sort = false;
-    size_t batch_reads = 1u << 20, batch_bytes = 512u << 20;
+    size_t batch_reads = 1u << 18, batch_bytes = 256u << 20;
 };
 
 void usage() {
@@ -117,50 +117,79 @@ void usage() {
 
 struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default reader: ID = header up to first blank)
     gzFile f = nullptr;
-    std::string path, line, pending;
-    bool have_pending = false, eof = false;
+    std::string path;
+    std::vector<char> buf;   // block buffer: lines are found with memchr, no per-line allocation
+    size_t pos = 0, end = 0;
+    bool eof = false;
     bool open(const std::string &p) {
         path = p;
         f = p == "-" ? gzdopen(0, "rb") : gzopen(p.c_str(), "rb");
         if (f) gzbuffer(f, 1 << 20);
+        buf.resize(16u << 20);
+        pos = end = 0; eof = false;
         return f != nullptr;
     }
     void close() { if (f) gzclose(f); f = nullptr; }
-    bool getline(std::string &out) {
-        if (have_pending) { out.swap(pending); have_pending = false; return true; }
-        out.clear();
-        char buf[1 << 16];
-        for (;;) {
-            if (!gzgets(f, buf, sizeof(buf))) return !out.empty();
-            size_t n = strlen(buf);
-            out.append(buf, n);
-            if (n && buf[n - 1] == '\n') break;
-        }
-        while (!out.empty() && (out.back() == '\n' || out.back() == '\r')) out.pop_back();
+    bool fill() {            // keeps [pos, end), reads more behind it; false at end of file
+        if (eof) return false;
+        if (pos) { memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
+        if (end == buf.size()) buf.resize(buf.size() * 2);
+        int r = gzread(f, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
+        if (r < 0) die("read error in %s", path.c_str());
+        if (r == 0) { eof = true; return false; }
+        end += (size_t)r;
         return true;
     }
-    // returns false at EOF
-    bool next(std::string &id, std::string &seq) {
-        std::string l;
-        do { if (!getline(l)) return false; } while (l.empty());
+    // next line without its end-of-line bytes; the pointer is valid until the next call
+    bool line(const char *&sp, size_t &n) {
+        size_t scanned = pos;
+        for (;;) {
+            const char *nl = (const char *)memchr(buf.data() + scanned, '\n', end - scanned);
+            if (nl) { sp = buf.data() + pos; n = (size_t)(nl - sp); pos = (size_t)(nl - buf.data()) + 1; break; }
+            const size_t had = end - pos;
+            if (!fill()) { if (pos == end) return false; sp = buf.data() + pos; n = end - pos; pos = end; break; }
+            scanned = pos + had;
+        }
+        while (n && (sp[n - 1] == '\r' || sp[n - 1] == '\n')) n--;
+        return true;
+    }
+    int peek() {             // first byte of the next line, -1 at end of file
+        if (pos == end && !fill()) return -1;
+        return (unsigned char)buf[pos];
+    }
+    bool getline(std::string &out) {
+        const char *sp; size_t n;
+        if (!line(sp, n)) return false;
+        out.assign(sp, n);
+        return true;
+    }
+    // one record: ID into `id`, sequence bytes APPENDED to `dst`; false at end of file
+    template <class V>
+    bool next(std::string &id, V &dst) {
+        const char *l; size_t n;
+        do { if (!line(l, n)) return false; } while (n == 0);
         if (l[0] != '>' && l[0] != '@') die("invalid FASTA/Q record in %s", path.c_str());
-        bool fq = l[0] == '@';
+        const bool fq = l[0] == '@';
         size_t e = 1;
-        while (e < l.size() && l[e] != ' ' && l[e] != '\t') e++;
-        id.assign(l, 1, e - 1);
-        seq.clear();
+        while (e < n && l[e] != ' ' && l[e] != '\t') e++;
+        id.assign(l + 1, e - 1);
         if (fq) {
-            if (!getline(l)) return true;
-            seq = l;
-            std::string plus, qual;
-            if (!getline(plus)) return true;
-            while (plus.empty() || plus[0] != '+') { seq += plus; if (!getline(plus)) return true; }   // multi-line FASTQ
+            if (!line(l, n)) return true;                // first line after the header is sequence
+            dst.insert(dst.end(), l, l + n);
+            size_t slen = n;
+            for (;;) {                                   // more sequence lines up to the '+' line (multi-line FASTQ)
+                if (!line(l, n)) return true;
+                if (n && l[0] == '+') break;
+                dst.insert(dst.end(), l, l + n); slen += n;
+            }
             size_t got = 0;
-            while (got < seq.size() && getline(qual)) got += qual.size();
+            while (got < slen && line(l, n)) got += n;
         } else {
-            while (getline(l)) {
-                if (!l.empty() && l[0] == '>') { pending.swap(l); have_pending = true; break; }
-                seq += l;
+            for (;;) {
+                const int c = peek();
+                if (c < 0 || c == '>') break;
+                if (!line(l, n)) break;
+                dst.insert(dst.end(), l, l + n);
             }
         }
         return true;
@@ -184,17 +213,17 @@ std::string gz_member(const char *data, size_t n) {
 struct Writer {
     FILE *fp = nullptr;
     bool gz = false;
-    int threads = 8;
+    int threads = 32;
     void open(const std::string &p) {
         if (p == "-") fp = stdout;
         else { fp = fopen(p.c_str(), "wb"); if (!fp) die("fail to write %s", p.c_str()); }
         gz = p.size() > 3 && p.compare(p.size() - 3, 3, ".gz") == 0;
     }
-    // text → file; .gz output is compressed in 8 MB blocks by several threads (independent gzip members, in order)
+    // text → file; .gz output is compressed in 1 MB blocks by several threads (independent gzip members, in order)
     void write(const char *s, size_t n) {
         if (!n) return;
         if (!gz) { fwrite(s, 1, n, fp); return; }
-        const size_t BLK = 8u << 20;
+        const size_t BLK = 1u << 20;
         std::deque<std::future<std::string>> inflight;
         for (size_t o = 0; o < n; o += BLK) {
             const size_t len = std::min(BLK, n - o);
@@ -469,15 +498,19 @@ int main(int argc, char **argv) {
             cv.notify_all();
             cur = new Batch();
         };
-        auto add_seq = [&](const std::string &sq) { cur->seq.insert(cur->seq.end(), sq.begin(), sq.end()); cur->off.push_back(cur->seq.size()); };
-        std::string id, seq, id2, seq2;
+        auto end_seq = [&]() { cur->off.push_back(cur->seq.size()); };
+        std::string id, id2;
         if (paired) {
             Reader r1, r2;
             if (!r1.open(o.read1)) die("%s: no such file", o.read1.c_str());
             if (!r2.open(o.read2)) die("%s: no such file", o.read2.c_str());
             logf("INFO", "reading from paired-end files: %s, %s", o.read1.c_str(), o.read2.c_str());
-            while (r1.next(id, seq) && r2.next(id2, seq2)) {          // S:806-867: ID of read1
-                cur->ids.push_back(id); add_seq(seq); add_seq(seq2);
+            for (;;) {                                                // S:806-867: ID of read1
+                const size_t mark = cur->seq.size();
+                if (!r1.next(id, cur->seq)) break;
+                const size_t mid = cur->seq.size();
+                if (!r2.next(id2, cur->seq)) { cur->seq.resize(mark); break; }
+                cur->ids.push_back(id); cur->off.push_back(mid); end_seq();
                 if (cur->ids.size() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
             }
             r1.close(); r2.close();
@@ -487,20 +520,21 @@ int main(int argc, char **argv) {
                 Reader r;
                 if (!r.open(file)) die("%s: no such file", file.c_str());
                 if (o.whole_file) {                                   // S:885-937 (the N-run follows every record after the second)
-                    std::string qid, whole;
+                    std::string qid;
                     bool first = true;
-                    while (r.next(id, seq)) {
-                        if (first) { qid = o.use_filename ? trim_ext(file) : (!o.query_id.empty() ? o.query_id : id); whole = seq; first = false; }
-                        else { whole += seq; whole.append((size_t)(kmax - 1), 'N'); }
+                    const size_t mark = cur->seq.size();
+                    while (r.next(id, cur->seq)) {
+                        if (first) { qid = o.use_filename ? trim_ext(file) : (!o.query_id.empty() ? o.query_id : id); first = false; }
+                        else cur->seq.insert(cur->seq.end(), (size_t)(kmax - 1), (uint8_t)'N');
                     }
-                    if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); r.close(); continue; }
-                    cur->ids.push_back(qid); add_seq(whole);
+                    if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); cur->seq.resize(mark); r.close(); continue; }
+                    cur->ids.push_back(qid); end_seq();
                     if (cur->seq.size() >= o.batch_bytes) emit();
                 } else {
                     bool any = false;
-                    while (r.next(id, seq)) {
+                    while (r.next(id, cur->seq)) {
                         any = true;
-                        cur->ids.push_back(id); add_seq(seq);
+                        cur->ids.push_back(id); end_seq();
                         if (cur->ids.size() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
                     }
                     if (!any) logf("WARN", "no valid sequences in file: %s", file.c_str());

@@ -364,6 +364,28 @@ def test_cli_tsv_is_byte_identical_to_the_oracle_formatter(oracle, small_db, tmp
     o4 = O.default_opts(); o4.min_query_cov = 0.1
     exp4 = O.format_tsv(odb, [b"myquery"], odb.search([whole], opts=o4))
     assert open(out4).read() == exp4
+    # untidy input: CRLF line ends, multi-line FASTQ, blank lines between records, wrapped FASTA without a final newline
+    sub, sid = reads[:40], ids[:40]
+    messy = str(tmp_path / "messy.fq")
+    with open(messy, "wb") as f:
+        for i, (n, r) in enumerate(zip(sid, sub)):
+            h = len(r) // 2
+            if i % 3 == 0:
+                f.write(b"@" + n + b" some description\r\n" + r + b"\r\n+\r\n" + b"I" * len(r) + b"\r\n")
+            elif i % 3 == 1:
+                f.write(b"\n@" + n + b"\tx\n" + r[:h] + b"\n" + r[h:] + b"\n+" + n + b"\n" + b"@" * h + b"\n" + b"+" * (len(r) - h) + b"\n")
+            else:
+                f.write(b"@" + n + b"\n" + r + b"\n+\n" + b"5" * len(r) + b"\n\n")
+    out5 = str(tmp_path / "o5.tsv")
+    _run_cli(["-d", dbdir, messy, "-o", out5])
+    assert open(out5).read() == O.format_tsv(odb, sid, odb.search(sub))
+    messy_fa = str(tmp_path / "messy.fa")
+    with open(messy_fa, "wb") as f:
+        for i, (n, r) in enumerate(zip(sid, sub)):
+            f.write(b">" + n + b" d\n" + b"\n".join(r[j:j + 60] for j in range(0, len(r), 60)) + (b"\n" if i + 1 < len(sub) else b""))
+    out6 = str(tmp_path / "o6.tsv")
+    _run_cli(["-d", dbdir, messy_fa, "-o", out6])
+    assert open(out6).read() == O.format_tsv(odb, sid, odb.search(sub))
 
 
 def test_cli_several_databases_are_merged_like_kmcp_merge(oracle, small_db, tmp_path):
