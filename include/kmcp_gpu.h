@@ -225,6 +225,40 @@ typedef struct {
 void kmcpg_default_index_params(kmcpg_index_params *p);
 int kmcpg_index_fasta(kmcpg_ctx *ctx, const kmcpg_index_params *p, const char *const *files, int n_files, const char *out_dir);
 
+/* ---- `kmcp profile` stage 1/4 straight from the result stream ----------------------------------
+ * Replaces the first pass of kmcp/cmd/profile.go:761-990 (+ parseMatchResult, util-profile.go:94-182) over the
+ * search TSV: per reference genome and chunk, Match / UniqMatch / UniqMatchHic, without the text round trip.
+ * qCov and FPR are compared after the same rounding the TSV applies (%.4f / %.4e), so the counters are the ones the
+ * reference computes from the file.  Taxonomy (`--level species`) is not applied.  Rows of a query must be sorted
+ * by qCov (the search default), as `profile` assumes. */
+typedef struct {
+    double min_query_cov;     /* profile -t/--min-query-cov (0.55) */
+    double max_fpr;           /* profile -f/--max-fpr (0.01) */
+    int32_t top_n_scores;     /* profile -n/--keep-top-qcovs (0: off) */
+    int32_t keep_perfect;     /* --keep-perfect-matches */
+    int32_t keep_main;        /* --keep-main-matches */
+    double max_qcov_gap;      /* --max-qcov-gap (0.4) */
+    double hic_min_qcov;      /* -H/--min-hic-ureads-qcov (0.75) */
+} kmcpg_refcount_params;
+typedef struct kmcpg_refcounts kmcpg_refcounts;
+typedef struct {
+    const char *name;         /* reference (target name); library-owned */
+    uint64_t genome_size;
+    uint32_t n_chunks, _pad;
+    const double *match, *uniq_match, *uniq_match_hic;   /* n_chunks each: Target.Match/UniqMatch/UniqMatchHic */
+} kmcpg_refcount_row;
+typedef struct {
+    uint64_t n_reads;         /* queries with at least one kept row (nReads) */
+    uint32_t n_refs, _pad;    /* references with at least one kept row, in database order */
+    const kmcpg_refcount_row *rows;   /* valid until the next add/get/free on the accumulator */
+} kmcpg_refcount_table;
+void kmcpg_default_refcount_params(kmcpg_refcount_params *p);
+/* targets from the database open in ctx, or (ctx NULL) from the block headers under db_dir (…/R001; host only) */
+int kmcpg_refcounts_create(kmcpg_ctx *ctx, const char *db_dir, const kmcpg_refcount_params *p, kmcpg_refcounts **out);
+int kmcpg_refcounts_add(kmcpg_refcounts *rc, const kmcpg_results *r);     /* one batch of kmcpg_engine_search, in input order */
+int kmcpg_refcounts_get(kmcpg_refcounts *rc, kmcpg_refcount_table *out);
+void kmcpg_refcounts_free(kmcpg_refcounts *rc);
+
 /* ---- synthetic workloads (bench/test tooling; seeded pure functions, mirrored in oracle/oracle.py) ------ */
 /* d_out[i*read_len .. ) = read (first+i) of the seeded read set; returns device pointers */
 int kmcpg_synth_reads(kmcpg_ctx *ctx, uint64_t seed, uint64_t first, uint32_t n_reads, uint32_t read_len,

@@ -110,12 +110,27 @@ class SynthDb(C.Structure):
 
 
 # every symbol include/kmcp_gpu.h declares (checked by tests/test_abi.py without a GPU)
+class RefcountParams(C.Structure):
+    _fields_ = [("min_query_cov", C.c_double), ("max_fpr", C.c_double), ("top_n_scores", C.c_int32), ("keep_perfect", C.c_int32),
+                ("keep_main", C.c_int32), ("max_qcov_gap", C.c_double), ("hic_min_qcov", C.c_double)]
+
+
+class RefcountRow(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("genome_size", C.c_uint64), ("n_chunks", C.c_uint32), ("_pad", C.c_uint32),
+                ("match", C.POINTER(C.c_double)), ("uniq_match", C.POINTER(C.c_double)), ("uniq_match_hic", C.POINTER(C.c_double))]
+
+
+class RefcountTable(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_refs", C.c_uint32), ("_pad", C.c_uint32), ("rows", C.POINTER(RefcountRow))]
+
+
 ABI_SYMBOLS = [
     "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
     "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_free_hits", "kmcpg_host_alloc",
     "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
     "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search",
     "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_synth_genomes", "kmcpg_build_synth_db", "kmcpg_write_block",
+    "kmcpg_default_refcount_params", "kmcpg_refcounts_create", "kmcpg_refcounts_add", "kmcpg_refcounts_get", "kmcpg_refcounts_free",
 ]
 
 _lib = None
@@ -163,6 +178,13 @@ def load() -> C.CDLL:
     L.kmcpg_engine_search.argtypes = [vp, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
     L.kmcpg_free_results.argtypes = [C.POINTER(Results)]
     L.kmcpg_free_results.restype = None
+    L.kmcpg_default_refcount_params.argtypes = [C.POINTER(RefcountParams)]
+    L.kmcpg_default_refcount_params.restype = None
+    L.kmcpg_refcounts_create.argtypes = [vp, C.c_char_p, C.POINTER(RefcountParams), C.POINTER(vp)]
+    L.kmcpg_refcounts_add.argtypes = [vp, C.POINTER(Results)]
+    L.kmcpg_refcounts_get.argtypes = [vp, C.POINTER(RefcountTable)]
+    L.kmcpg_refcounts_free.argtypes = [vp]
+    L.kmcpg_refcounts_free.restype = None
     L.kmcpg_query_fpr.restype = C.c_double
     L.kmcpg_query_fpr.argtypes = [C.c_int, C.c_int, C.c_double]
     L.kmcpg_default_index_params.argtypes = [C.POINTER(IndexParams)]
@@ -376,29 +398,21 @@ class Context:
             setattr(o, k, v)
         return o
 
-    def engine_search(self, buf: np.ndarray, off: np.ndarray, opts: Optional[EngineOpts] = None) -> EngineResults:
+    def engine_search(self, buf: np.ndarray, off: np.ndarray, opts: Optional[EngineOpts] = None, refcounts: Optional[int] = None) -> EngineResults:
         o = opts or self.default_engine_opts()
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint64)
-        return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o)
+        return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o, refcounts=refcounts)
 
-    def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts, copy: bool = True) -> EngineResults:
-        r = Results()
-        self._check(self._L.kmcpg_engine_search(self._h, C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r)))
-        nq = r.n_queries
-        if not copy:
-            out = EngineResults(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint64), np.zeros(0, MATCH_DTYPE),
-                                r.ms_gpu_total, int(r.probe_row_bytes), int(r.kernel_launches))
-            out.n_matches = int(r.n_matches); out.ms_post = r.ms_post; out.ms_total = r.ms_total
-            self._L.kmcpg_free_results(C.byref(r))
-            return out
-        out = EngineResults(_np_from(r.query_len, nq, 4, np.int32), _np_from(r.n_kmers, nq, 4, np.int32),
-                            _np_from(r.k_used, nq, 4, np.int32), _np_from(r.match_off, nq + 1, 8, np.uint64),
-                            _np_from(r.matches, r.n_matches, C.sizeof(Match), MATCH_DTYPE), r.ms_gpu_total,
-                            int(r.probe_row_bytes), int(r.kernel_launches))
-        out.n_matches = int(r.n_matches); out.ms_post = r.ms_post; out.ms_total = r.ms_total
-        self._L.kmcpg_free_results(C.byref(r))
-        return out
+    # ---- `kmcp profile` stage-1 counters (kmcpg_refcounts_*) ----
+    def refcounts_create(self, **kw) -> int:
+        return refcounts_create(self._h, None, **kw)
+
+    def refcounts_get(self, rc: int):
+        return refcounts_get(rc)
+
+    def refcounts_free(self, rc: int):
+        self._L.kmcpg_refcounts_free(rc)
 
     # ---- memory helpers ----
     def device_alloc(self, nbytes: int) -> int:
@@ -453,3 +467,51 @@ def pinned_array(nbytes: int, dtype=np.uint8) -> Tuple[np.ndarray, int]:
     ptr = host_alloc(nbytes)
     buf = (C.c_uint8 * nbytes).from_address(ptr)
     return np.frombuffer(buf, dtype=dtype), ptr
+
+
+def refcounts_create(ctx_handle, db_dir: Optional[str], **kw) -> int:
+    """accumulator over the database of a context, or (ctx_handle None) over the block headers in db_dir (host only)"""
+    L = load()
+    p = RefcountParams()
+    L.kmcpg_default_refcount_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    h = C.c_void_p()
+    rc = L.kmcpg_refcounts_create(ctx_handle, db_dir.encode() if db_dir else None, C.byref(p), C.byref(h))
+    if rc:
+        raise KmcpGpuError(rc, (L.kmcpg_last_error(None) or b"").decode())
+    return h.value
+
+
+def refcounts_add_matches(rc: int, match_off: np.ndarray, matches: np.ndarray):
+    """feed per-query match lists (MATCH_DTYPE, offsets n_queries+1) that were produced elsewhere"""
+    L = load()
+    r = Results()
+    off = np.ascontiguousarray(match_off, dtype=np.uint64)
+    m = np.ascontiguousarray(matches, dtype=MATCH_DTYPE)
+    r.n_queries = len(off) - 1
+    r.n_matches = len(m)
+    r.match_off = C.cast(off.ctypes.data, C.POINTER(C.c_uint64))
+    r.matches = C.cast(m.ctypes.data, C.POINTER(Match))
+    rcode = L.kmcpg_refcounts_add(rc, C.byref(r))
+    if rcode:
+        raise KmcpGpuError(rcode, "kmcpg_refcounts_add")
+
+
+def refcounts_get(rc: int):
+    """(n_reads, {reference: (genome_size, match[], uniq[], uniq_hic[])})"""
+    L = load()
+    t = RefcountTable()
+    rcode = L.kmcpg_refcounts_get(rc, C.byref(t))
+    if rcode:
+        raise KmcpGpuError(rcode, "kmcpg_refcounts_get")
+    out = {}
+    for i in range(t.n_refs):
+        r = t.rows[i]
+        n = r.n_chunks
+        out[r.name.decode()] = (int(r.genome_size), [r.match[j] for j in range(n)], [r.uniq_match[j] for j in range(n)], [r.uniq_match_hic[j] for j in range(n)])
+    return int(t.n_reads), out
+
+
+def refcounts_free(rc: int):
+    load().kmcpg_refcounts_free(rc)

@@ -74,7 +74,8 @@ struct Less {                       // the engine's match order (U:105-145), use
 };
 
 struct Opts {
-    std::string out_file = "-", read1, read2, sort_by = "qcov", query_id, log_file;
+    std::string out_file = "-", read1, read2, sort_by = "qcov", query_id, log_file, ref_counts_file;
+    double rc_min_qcov = 0.55, rc_max_fpr = 0.01;   // `kmcp profile` -t / -f for --ref-counts
     std::vector<std::string> db_dirs, files, name_maps;   // several -d: every database is searched, results merged as `kmcp merge` does
     int dedup = 256, min_kmers = 10, min_qlen = 30, top_scores = 0, threads = 0, device = 0;
     double qcov = 0.55, tcov = 0, max_fpr = 0.01;
@@ -111,7 +112,11 @@ void usage() {
         "  -w, --load-whole-db / --low-mem  accepted for compatibility (the index always lives in HBM)\n"
         "  -j, --threads int                host threads for the post-filter (default all)\n"
         "  -q, --quiet / --log string       logging\n"
-        "      --gpu int                    CUDA device ordinal (default 0)\n",
+        "      --gpu int                    CUDA device ordinal (default 0)\n"
+        "      --ref-counts file            also write the per-reference, per-chunk read counters of `kmcp profile` stage 1/4\n"
+        "                                   (match, uniqMatch, uniqMatchHic), computed from the result stream\n"
+        "      --ref-counts-min-qcov float  profile -t/--min-query-cov for --ref-counts (default 0.55)\n"
+        "      --ref-counts-max-fpr float   profile -f/--max-fpr for --ref-counts (default 0.01)\n",
         stderr);
 }
 
@@ -344,6 +349,9 @@ int main(int argc, char **argv) {
         auto sval = [&]() -> std::string { return has_eq ? val : std::string(need(i)); };
         if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (a == "-d" || a == "--db-dir") o.db_dirs.push_back(sval());
+        else if (a == "--ref-counts") o.ref_counts_file = sval();
+        else if (a == "--ref-counts-min-qcov") o.rc_min_qcov = atof(sval().c_str());
+        else if (a == "--ref-counts-max-fpr") o.rc_max_fpr = atof(sval().c_str());
         else if (a == "-o" || a == "--out-file") o.out_file = sval();
         else if (a == "-1" || a == "--read1") o.read1 = sval();
         else if (a == "-2" || a == "--read2") o.read2 = sval();
@@ -451,6 +459,15 @@ int main(int argc, char **argv) {
             auto it = db.name_map.find(db.targets[(size_t)t].name);
             if (it != db.name_map.end()) db.mapped[(size_t)t] = &it->second;
         }
+    }
+    kmcpg_refcounts *refcounts = nullptr;
+    if (!o.ref_counts_file.empty()) {
+        if (dbs.size() != 1) die("--ref-counts needs exactly one -d database");
+        if (sort_by != 0 || o.do_not_sort) die("--ref-counts needs matches sorted by qcov (the default), as `kmcp profile` does");
+        kmcpg_refcount_params rp;
+        kmcpg_default_refcount_params(&rp);
+        rp.min_query_cov = o.rc_min_qcov; rp.max_fpr = o.rc_max_fpr;
+        if (kmcpg_refcounts_create(dbs[0].ctx, nullptr, &rp, &refcounts)) die("%s", kmcpg_last_error(dbs[0].ctx));
     }
     logf("INFO", "-------------------- [main parameters] --------------------");
     logf("INFO", "  minimum    query length: %d", o.min_qlen);
@@ -623,6 +640,7 @@ int main(int argc, char **argv) {
             w.write(all);
             for (auto v : nmatched) matched += v;
             total += nq;
+            if (refcounts && kmcpg_refcounts_add(refcounts, &job->res[0])) die("--ref-counts: inconsistent chunk numbering in the database");
             for (auto &r : job->res) kmcpg_free_results(&r);
             delete job->batch;
             delete job;
@@ -667,6 +685,25 @@ int main(int argc, char **argv) {
                      (unsigned long long)matched, total ? (double)matched / (double)total * 100 : NAN);
     w.write(line, (size_t)n);
     w.close();
+    if (refcounts) {
+        kmcpg_refcount_table tb;
+        kmcpg_refcounts_get(refcounts, &tb);
+        Writer rw;
+        rw.open(o.ref_counts_file);
+        std::string t = "#ref\tchunkIdx\tchunks\tgenomeSize\tmatch\tuniqMatch\tuniqMatchHic\n";
+        for (uint32_t i = 0; i < tb.n_refs; i++)
+            for (uint32_t c = 0; c < tb.rows[i].n_chunks; c++) {
+                int k = snprintf(line, sizeof(line), "\t%u\t%u\t%llu\t%.17g\t%.17g\t%.17g\n", c, tb.rows[i].n_chunks, (unsigned long long)tb.rows[i].genome_size,
+                                 tb.rows[i].match[c], tb.rows[i].uniq_match[c], tb.rows[i].uniq_match_hic[c]);
+                t += tb.rows[i].name; t.append(line, (size_t)k);
+            }
+        int k = snprintf(line, sizeof(line), "# reads: %llu\n# references: %u\n", (unsigned long long)tb.n_reads, tb.n_refs);
+        t.append(line, (size_t)k);
+        rw.write(t);
+        rw.close();
+        logf("INFO", "reference counters of %u references saved to: %s", tb.n_refs, o.ref_counts_file.c_str());
+        kmcpg_refcounts_free(refcounts);
+    }
     for (auto &db : dbs) kmcpg_close(db.ctx);
     logf("INFO", "");
     logf("INFO", "elapsed time: %.3fs", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());

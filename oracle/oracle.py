@@ -540,6 +540,86 @@ def format_tsv(db: DB, ids: Sequence[bytes], res: SearchResult, keep_unmatched: 
     return "".join(out)
 
 
+def profile_stage1(tsv: str, min_qcov: float = 0.55, max_fpr: float = 0.01, top_n_scores: int = 0, keep_perfect: bool = False,
+                   keep_main: bool = False, max_qcov_gap: float = 0.4, hic_min_qcov: float = 0.75):
+    """`kmcp profile` stage 1/4 (profile.go:761-990) on the text of a search result, without taxonomy (`--level species`
+    off): per reference, per chunk, Match (every kept row adds 1/rows-of-that-reference), UniqMatch (reads whose kept
+    rows name one reference) and UniqMatchHic (those with qCov >= -H).  Values are parsed from the TSV text exactly as
+    parseMatchResult does (util-profile.go:94-182): rows with qCov < -t or FPR > -f never reach the loop.
+    Returns (n_reads, {reference: (genome_size, match[], uniq[], uniq_hic[])})."""
+    profile = {}
+    n_reads = 0
+    state = {"matches": {}}
+
+    def flush():
+        nonlocal n_reads
+        matches = state["matches"]
+        if not matches:
+            return
+        n_reads += 1
+        for name, ms in matches.items():
+            first = True
+            for (frag, idx_num, gsize, qcov) in ms:
+                t = profile.get(name)
+                if t is None:
+                    t = profile[name] = (gsize, [0.0] * idx_num, [0.0] * idx_num, [0.0] * idx_num)
+                if first:
+                    if len(matches) == 1:
+                        t[2][frag] += 1
+                        if qcov >= hic_min_qcov:
+                            t[3][frag] += 1
+                    first = False
+                t[1][frag] += 1.0 / float(len(ms))
+        state["matches"] = {}
+
+    prev = None
+    p_score, n_score, process = 1024.0, 0, True
+    for line in tsv.split("\n"):
+        if line == "" or line[0] == "#":
+            continue
+        it = line.split("\t")
+        qcov = float(it[11])
+        if qcov < min_qcov:
+            continue
+        if float(it[3]) > max_fpr:
+            continue
+        query = it[0]
+        if prev != query:
+            flush()
+            p_score, n_score, process = 1024.0, 0, True
+        elif keep_perfect:
+            if not process:
+                prev = query
+                continue
+            if p_score == 1 and qcov < 1:
+                process = False
+                prev = query
+                continue
+        elif keep_main and p_score <= 1:
+            if not process:
+                prev = query
+                continue
+            if p_score - qcov > max_qcov_gap:
+                process = False
+                prev = query
+                continue
+        if top_n_scores > 0:
+            if not process:
+                prev = query
+                continue
+            if qcov < p_score:
+                n_score += 1
+                if n_score > top_n_scores:
+                    process = False
+                    prev = query
+                    continue
+        state["matches"].setdefault(it[5], []).append((int(it[6]), int(it[7]), int(it[8]), qcov))
+        prev = query
+        p_score = qcov
+    flush()
+    return n_reads, profile
+
+
 # ------------------------------------------------------------------------------------------------
 # seeded synthetic data — the SAME pure functions are implemented in kmcp_b200/csrc/synth.cu so that
 # bench-scale inputs can be made on the device; tests compare the two generators byte for byte.

@@ -335,6 +335,21 @@ def test_cli_tsv_is_byte_identical_to_the_oracle_formatter(oracle, small_db, tmp
     _run_cli(["-d", dbdir, fq, "-o", out])
     exp = O.format_tsv(odb, ids, odb.search(reads))
     assert gzip.open(out, "rb").read().decode() == exp
+    # --ref-counts: `kmcp profile` stage-1 counters from the result stream == the oracle's stage 1 over the expected TSV
+    rcf = str(tmp_path / "refcounts.tsv")
+    _run_cli(["-d", dbdir, fq, "-o", out, "--ref-counts", rcf, "--ref-counts-min-qcov", "0.6", "--ref-counts-max-fpr", "0.001"])
+    assert gzip.open(out, "rb").read().decode() == exp
+    exp_reads, exp_prof = O.profile_stage1(exp, min_qcov=0.6, max_fpr=0.001)
+    got_prof, got_reads = {}, None
+    for l in open(rcf).read().splitlines():
+        if l.startswith("# reads: "):
+            got_reads = int(l.split(": ")[1])
+        if l.startswith("#"):
+            continue
+        name, c, n, gs, m, u, hc = l.split("\t")
+        t = got_prof.setdefault(name, (int(gs), [0.0] * int(n), [0.0] * int(n), [0.0] * int(n)))
+        t[1][int(c)], t[2][int(c)], t[3][int(c)] = float(m), float(u), float(hc)
+    assert got_reads == exp_reads and got_prof == exp_prof and len(exp_prof) >= 30
     # -K keeps unmatched rows; other thresholds; sort by jacc; top score
     out2 = str(tmp_path / "o2.tsv")
     _run_cli(["-d", dbdir, fq, "-o", out2, "-K", "-t", "0.4", "-c", "5", "-s", "jacc", "-n", "1", "-f", "0.05"])

@@ -61,6 +61,12 @@ def test_g1_g2_demo_profiling(oracle, demo_db):
             per_ref[r] = per_ref.get(r, 0) + 1
     assert unamb == 198911                                           # ANALYSIS.md:17,21
     assert sorted(per_ref.values(), reverse=True) == G1_UNAMBIGUOUS
+    # the same counts through the restated `profile` stage 1 (profile.go:761-990) fed with the search TSV, filters open
+    n_reads, prof = O.profile_stage1(O.format_tsv(db, ids, res), min_qcov=0.0, max_fpr=1.0)
+    assert n_reads == 308839
+    assert sorted((int(sum(t[2])) for t in prof.values()), reverse=True) == G1_UNAMBIGUOUS
+    assert abs(sum(sum(t[1]) for t in prof.values()) - sum(len({names[t] for t in res.hits["target"][int(res.hit_off[q]):int(res.hit_off[q + 1])]})
+                                                            for q in np.nonzero(nh > 0)[0])) < 1e-6
     # G2: the reference's own first rows (docs/tutorial/profiling/index.md:203-211), all 15 columns
     sub = O.SearchResult(res.query_len[:10], res.n_kmers[:10], res.k_used[:10], res.hit_off[:11], res.hits[:int(res.hit_off[10])])
     tsv = O.format_tsv(db, ids[:10], sub, trailer=False).splitlines()
