@@ -404,6 +404,26 @@ class Context:
         off = np.ascontiguousarray(off, dtype=np.uint64)
         return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o, refcounts=refcounts)
 
+    def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts, copy: bool = True, refcounts: Optional[int] = None) -> EngineResults:
+        r = Results()
+        self._check(self._L.kmcpg_engine_search(self._h, C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r)))
+        if refcounts is not None:       # `kmcp profile` stage-1 counters of this batch (kmcpg_refcounts_add)
+            self._check(self._L.kmcpg_refcounts_add(refcounts, C.byref(r)))
+        nq = r.n_queries
+        if not copy:
+            out = EngineResults(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint64), np.zeros(0, MATCH_DTYPE),
+                                r.ms_gpu_total, int(r.probe_row_bytes), int(r.kernel_launches))
+            out.n_matches = int(r.n_matches); out.ms_post = r.ms_post; out.ms_total = r.ms_total
+            self._L.kmcpg_free_results(C.byref(r))
+            return out
+        out = EngineResults(_np_from(r.query_len, nq, 4, np.int32), _np_from(r.n_kmers, nq, 4, np.int32),
+                            _np_from(r.k_used, nq, 4, np.int32), _np_from(r.match_off, nq + 1, 8, np.uint64),
+                            _np_from(r.matches, r.n_matches, C.sizeof(Match), MATCH_DTYPE), r.ms_gpu_total,
+                            int(r.probe_row_bytes), int(r.kernel_launches))
+        out.n_matches = int(r.n_matches); out.ms_post = r.ms_post; out.ms_total = r.ms_total
+        self._L.kmcpg_free_results(C.byref(r))
+        return out
+
     # ---- `kmcp profile` stage-1 counters (kmcpg_refcounts_*) ----
     def refcounts_create(self, **kw) -> int:
         return refcounts_create(self._h, None, **kw)

@@ -743,3 +743,23 @@ def test_c4_shape_wide_rows_many_blocks_sampled_oracle_parity():
     assert r["db"]["targets"] == 852050 and r["db"]["blocks"] == 32 and r["probe_launches"] >= 32
     assert r["probe_row_bytes_per_read"] == 130 * 3 * sum(-(-n // 8) for n in [26632] * 31 + [852050 - 31 * 26632])
     assert r["oracle_sample"]["identical"] and r["oracle_sample"]["hits"] > 100
+
+
+def test_refcounts_from_engine_batches(gpu_ctx, oracle, small_db):
+    """kmcpg_refcounts_add on the engine's own result batches == the oracle's profile stage 1 over the oracle's TSV"""
+    from kmcp_b200 import api
+    O = oracle
+    odb = O.DB(small_db)
+    gpu_ctx.open_db(small_db)
+    reads = helpers.make_reads(O, RSEED + 60, 3000, 40, 30000, GSEED)
+    ids = [b"r%d" % i for i in range(len(reads))]
+    exp_reads, exp = O.profile_stage1(O.format_tsv(odb, ids, odb.search(reads)), min_qcov=0.6, max_fpr=0.005, hic_min_qcov=0.8)
+    rc = gpu_ctx.refcounts_create(min_query_cov=0.6, max_fpr=0.005, hic_min_qcov=0.8)
+    try:
+        for lo in range(0, len(reads), 1100):                      # three engine batches, in input order
+            buf, off = api.pack_seqs(reads[lo:lo + 1100])
+            gpu_ctx.engine_search(buf, off, refcounts=rc)
+        got_reads, got = gpu_ctx.refcounts_get(rc)
+    finally:
+        gpu_ctx.refcounts_free(rc)
+    assert got_reads == exp_reads and got == exp and exp_reads > 1500
