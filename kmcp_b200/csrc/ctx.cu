@@ -314,9 +314,9 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
         bi++;
     }
     CU(cudaEventRecord(w.ev_a, st));
-    CU(cudaStreamWaitEvent(ctx->copy_st, w.ev_a, 0));
-    CU(cudaMemcpyAsync(w.h_cnt.p, w.counters.p, 16, cudaMemcpyDeviceToHost, ctx->copy_st));
-    CU(cudaEventRecord(w.ev_cnt, ctx->copy_st));
+    CU(cudaStreamWaitEvent(ctx->cnt_st, w.ev_a, 0));
+    CU(cudaMemcpyAsync(w.h_cnt.p, w.counters.p, 16, cudaMemcpyDeviceToHost, ctx->cnt_st));
+    CU(cudaEventRecord(w.ev_cnt, ctx->cnt_st));
     return KMCPG_OK;
 }
 
@@ -514,6 +514,9 @@ struct PartDone { uint32_t first_query, nq; uint64_t hit_dst, n_hits; cudaEvent_
 static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const std::vector<Part> &parts, const uint8_t *host_seq, const uint64_t *host_off,
                      const uint8_t *d_seq, const uint64_t *d_off, HitsPriv &res, Timing &tm, kmcpg_part_cb cb, void *user) {
     const uint32_t step = p.paired ? 2 : 1;
+    static const bool trace = getenv("KMCPG_TRACE") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto now = [&]() { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
     int rc = KMCPG_OK;
     std::vector<PartDone> done;
     size_t delivered = 0;
@@ -521,12 +524,15 @@ static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const 
     auto deliver = [&](size_t upto) -> int {
         for (; cb && delivered < done.size() && delivered <= upto; delivered++) {
             const PartDone &d = done[delivered];
+            const float ta = now();
             CU(cudaEventSynchronize(d.ev));
+            const float tb = now();
             kmcpg_part pt;
             pt.first_query = d.first_query; pt.n_queries = d.nq;
             pt.n_kmers = (const int32_t *)res.nk.p + d.first_query; pt.query_len = (const int32_t *)res.ql.p + d.first_query;
             pt.hits = (const kmcpg_hit *)res.hits.p + d.hit_dst; pt.n_hits = d.n_hits;
             cb(user, &pt);
+            if (trace) fprintf(stderr, "[trace] part %zu: d2h wait %.2f..%.2f cb ..%.2f (%u q, %llu hits)\n", delivered, ta, tb, now(), d.nq, (unsigned long long)d.n_hits);
         }
         return KMCPG_OK;
     };
@@ -541,11 +547,14 @@ static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const 
             if (host_seq) rc = enqueue_part(ctx, w, p, k, sb, host_seq, host_off + pt.a, host_off[pt.b] - host_off[pt.a]);
             else rc = enqueue_part(ctx, w, p, k, sb, nullptr, nullptr, 0);
             if (rc) return rc;
+            if (trace) fprintf(stderr, "[trace] part %zu enqueued at %.2f\n", i, now());
         }
         if (i >= 1) {
             WorkSet &w = ctx->ws[(i - 1) & 1];
+            const float tf = now();
             rc = finish_probes(ctx, w, p, res, tm);
             if (rc) return rc;
+            if (trace) fprintf(stderr, "[trace] part %zu probes finished: wait %.2f..%.2f\n", i - 1, tf, now());
             done.push_back({w.sb.query_base, w.nq, w.hit_dst, w.n_hits, w.ev_b});
             // its sort + copies run beside the probe of part i: hand part i-1 to the caller as soon as it has landed, while
             // the GPU keeps working
@@ -560,6 +569,7 @@ static int run_parts(kmcpg_ctx *ctx, const kmcpg_search_params &p, int k, const 
 static void abort_parts(kmcpg_ctx *ctx) {
     cudaStreamSynchronize(ctx->st);
     cudaStreamSynchronize(ctx->copy_st);
+    cudaStreamSynchronize(ctx->cnt_st);
     cudaStreamSynchronize(ctx->in_st);
     cudaStreamSynchronize(ctx->post_st);
     for (auto &w : ctx->ws) w.busy = false;
@@ -621,6 +631,7 @@ int kmcpg_create(int device, kmcpg_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->cnt_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->in_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     {   // the post stream gets the highest priority: its tiny sort/pack kernels slip in as soon as probe CTAs retire
         int lo = 0, hi = 0;
@@ -647,6 +658,7 @@ int kmcpg_close(kmcpg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     cudaStreamSynchronize(ctx->copy_st);
+    cudaStreamSynchronize(ctx->cnt_st);
     cudaStreamSynchronize(ctx->in_st);
     cudaStreamSynchronize(ctx->post_st);
     free_db(ctx);
@@ -657,6 +669,7 @@ int kmcpg_close(kmcpg_ctx *ctx) {
     ctx->pin_pool.clear();
     if (ctx->own_st) cudaStreamDestroy(ctx->own_st);
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
+    if (ctx->cnt_st) cudaStreamDestroy(ctx->cnt_st);
     if (ctx->in_st) cudaStreamDestroy(ctx->in_st);
     if (ctx->post_st) cudaStreamDestroy(ctx->post_st);
     delete ctx;

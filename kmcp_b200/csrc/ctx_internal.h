@@ -104,6 +104,8 @@ struct kmcpg_ctx {
     cudaStream_t st = nullptr;        // compute stream (own_st or the caller's)
     cudaStream_t own_st = nullptr;
     cudaStream_t copy_st = nullptr;   // device→host transfers that overlap the kernels
+    cudaStream_t cnt_st = nullptr;    // the 16-byte hit counters of a part: its own stream, so that the wait for part i's probes does not
+                                      // sit in front of part i-1's result copies (streams are FIFO)
     cudaStream_t post_st = nullptr;   // hit-list sort + pack of a finished part (tiny kernels, concurrent with the next probe)
     cudaStream_t in_st = nullptr;     // host→device input staging (its own queue, so it never waits behind result copies)
     bool has_db = false;

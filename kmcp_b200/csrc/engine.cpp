@@ -168,6 +168,7 @@ struct ResPriv {
 struct Round {
     std::vector<uint32_t> queries;        // local index → global query
     std::vector<uint64_t> off;            // local index → range in `matches`
+    uint64_t *offp = nullptr;             // = off.data(), or the result's own offset array when this round is the whole answer
     BigBuf buf;                           // kmcpg_match[n]
     size_t n = 0;
     kmcpg_match *matches() const { return (kmcpg_match *)buf.p; }
@@ -291,8 +292,10 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
             rounds.emplace_back();
             Round &R = rounds.back();
             const int ridx = (int)rounds.size() - 1;
-            R.off.assign((size_t)ln_total + 1, 0);
             const bool single = (ik == 0 && tries == 0 && cur_all);
+            const bool whole_answer = single && tries_max == 1 && info.n_ks == 1;      // offsets go straight into the result
+            if (whole_answer) { R.offp = r_off; r_off[0] = 0; }
+            else { R.off.assign((size_t)ln_total + 1, 0); R.offp = R.off.data(); }
             if (!single && q_round.empty()) { q_round.assign(nq, -1); q_local.assign(nq, 0); }
             std::vector<uint32_t> retry;
 
@@ -303,7 +306,11 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                 count.assign(ln, 0);
                 const size_t need = (R.n + std::max<uint64_t>(hits.n_hits, 1)) * sizeof(kmcpg_match);
                 if (R.buf.cap < need) {
-                    BigBuf nb = big_acquire(need + need / 2);
+                    // first part of a round: size the array for the whole round from this part's hit density
+                    size_t want = need + need / 2;
+                    if (R.n == 0 && ln > 0 && ln < ln_total)
+                        want = std::max(want, (size_t)((double)hits.n_hits * ((double)ln_total / (double)ln) * 1.2 + 4096) * sizeof(kmcpg_match));
+                    BigBuf nb = big_acquire(want);
                     if (R.n) memcpy(nb.p, R.buf.p, R.n * sizeof(kmcpg_match));
                     big_release(R.buf);
                     R.buf = nb;
@@ -336,14 +343,14 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                     memcpy(r_qlen + q0, hits.query_len, (size_t)ln * 4);
                     memcpy(r_nk + q0, hits.n_kmers, (size_t)ln * 4);
                     std::fill(r_k + q0, r_k + q0 + ln, (int32_t)k);
-                    uint64_t acc = R.off[q0];
-                    for (uint32_t l = 0; l < ln; l++) { acc += cp[l]; R.off[q0 + l + 1] = acc; }
+                    uint64_t acc = R.offp[q0];
+                    for (uint32_t l = 0; l < ln; l++) { acc += cp[l]; R.offp[q0 + l + 1] = acc; }
                 } else {
                     for (uint32_t l = 0; l < ln; l++) {
                         const uint32_t gl = q0 + l;                                    // index inside the round
                         const uint32_t q = curp ? curp[gl] : gl;
                         const int n = hits.n_kmers[l];
-                        R.off[gl + 1] = R.off[gl] + cp[l];
+                        R.offp[gl + 1] = R.offp[gl] + cp[l];
                         r_qlen[q] = hits.query_len[l];
                         r_k[q] = k;
                         if (n == 0) { if (tries == 0) r_nk[q] = 0; continue; }         // U:778-786, U:854-869: final, unmatched
@@ -355,35 +362,22 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
                 out->ms_post += ms_since(Tp);
             };
 
-            // big rounds are cut into chunks: a second thread drives the device through chunk c+1 while this thread filters
-            // chunk c (kmcpg_search_batch_cb offers the same overlap at part granularity to hosts that prefer a callback)
-            const uint32_t CHUNK_Q = 320u << 10;
-            const uint32_t n_chunks = ln_total > 2 * CHUNK_Q ? (ln_total + CHUNK_Q - 1) / CHUNK_Q : 1;
-            auto chunk_lo = [&](uint32_t c) { return (uint32_t)((uint64_t)ln_total * c / n_chunks); };
-            auto run_search = [&](uint32_t c, kmcpg_hits *h) -> int {
-                const uint32_t a = chunk_lo(c), b = chunk_lo(c + 1);
-                return kmcpg_search_batch(ctx, &p, bs, bo + (size_t)a * step, (b - a) * step, h);
-            };
+            // one device call per round: the executor hands over every part (≈ 250 k reads) as soon as its hits have landed in
+            // host memory and has the next part's kernels enqueued by then, so the filtering below runs beside the GPU work;
+            // only the last part's filtering is exposed
             {
-                kmcpg_hits hits[2];
-                std::future<int> fut = std::async(std::launch::async, run_search, 0u, &hits[0]);
-                for (uint32_t c = 0; c < n_chunks; c++) {
-                    rc = fut.get();
-                    if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
-                    if (c + 1 < n_chunks) fut = std::async(std::launch::async, run_search, c + 1, &hits[(c + 1) & 1]);
-                    const kmcpg_hits &h = hits[c & 1];
-                    kmcpg_part part;
-                    part.first_query = 0; part.n_queries = h.n_queries; part.n_kmers = h.n_kmers; part.query_len = h.query_len;
-                    part.hits = h.hits; part.n_hits = h.n_hits;
-                    absorb(part, chunk_lo(c));
-                    out->ms_gpu_total += h.ms_total; out->probe_row_bytes += h.probe_row_bytes; out->kernel_launches += h.kernel_launches;
-                    kmcpg_free_hits(&hits[c & 1]);
-                }
+                std::function<void(const kmcpg_part &)> fn = [&](const kmcpg_part &pt) { absorb(pt, pt.first_query); };
+                kmcpg_hits h;
+                rc = kmcpg_search_batch_cb(ctx, &p, bs, bo, ln_total * step,
+                                           [](void *user, const kmcpg_part *pt) { (*(std::function<void(const kmcpg_part &)> *)user)(*pt); }, &fn, &h);
+                if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
+                out->ms_gpu_total += h.ms_total; out->probe_row_bytes += h.probe_row_bytes; out->kernel_launches += h.kernel_launches;
+                kmcpg_free_hits(&h);
             }
             if (single && (tries_max > 1 || info.n_ks > 1) && !retry.empty()) {
                 // more rounds will follow: remember where round 0 put every matched query
                 q_round.assign(nq, -1); q_local.assign(nq, 0);
-                for (uint32_t l = 0; l < ln_total; l++) if (R.off[l + 1] > R.off[l]) { q_round[l] = 0; q_local[l] = l; }
+                for (uint32_t l = 0; l < ln_total; l++) if (R.offp[l + 1] > R.offp[l]) { q_round[l] = 0; q_local[l] = l; }
             }
             if (!cur_all) R.queries.swap(cur);
             cur_all = false;
@@ -398,13 +392,13 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
     if (rounds.size() == 1) {
         // the common case: one round over all queries — its flat array already is the answer
         priv->matches = rounds[0].buf; rounds[0].buf = BigBuf();
-        memcpy(r_off, rounds[0].off.data(), ((size_t)nq + 1) * 8);
+        if (rounds[0].offp != r_off) memcpy(r_off, rounds[0].offp, ((size_t)nq + 1) * 8);
         out->n_matches = rounds[0].n;
     } else {
         r_off[0] = 0;
         for (uint32_t q = 0; q < nq; q++) {
             uint64_t c = 0;
-            if (!q_round.empty() && q_round[q] >= 0) { const Round &R = rounds[q_round[q]]; c = R.off[q_local[q] + 1] - R.off[q_local[q]]; }
+            if (!q_round.empty() && q_round[q] >= 0) { const Round &R = rounds[q_round[q]]; c = R.offp[q_local[q] + 1] - R.offp[q_local[q]]; }
             r_off[q + 1] = r_off[q] + c;
         }
         priv->matches = big_acquire(std::max<uint64_t>(r_off[nq], 1) * sizeof(kmcpg_match));
@@ -412,7 +406,7 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
         for (uint32_t q = 0; q < nq; q++)
             if (!q_round.empty() && q_round[q] >= 0) {
                 const Round &R = rounds[q_round[q]];
-                memcpy(dst + r_off[q], R.matches() + R.off[q_local[q]], (r_off[q + 1] - r_off[q]) * sizeof(kmcpg_match));
+                memcpy(dst + r_off[q], R.matches() + R.offp[q_local[q]], (r_off[q + 1] - r_off[q]) * sizeof(kmcpg_match));
             }
         out->n_matches = r_off[nq];
         for (auto &R : rounds) big_release(R.buf);

@@ -617,8 +617,8 @@ def test_cli_index_then_search_roundtrip(oracle, tmp_path):
     assert open(tsv).read() == O.format_tsv(odb, ids, odb.search(reads))
 
 
-def test_engine_chunked_round_overlaps_search_and_postfilter(gpu_ctx, oracle, small_db):
-    """> 768 k queries: the engine cuts the round into chunks searched by a second thread while the first filters"""
+def test_engine_big_round_filters_parts_while_the_gpu_works(gpu_ctx, oracle, small_db):
+    """800 k queries = several parts: the engine filters every delivered part inside the executor's callback"""
     O = oracle
     odb = O.DB(small_db)
     gpu_ctx.open_db(small_db)
