@@ -223,10 +223,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner out of stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]             # keeps NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        gloo = dist.new_group(backend="gloo")
     stream = torch.cuda.Stream()
     ctx = api.Context(local_rank)
     ctx.set_stream(stream.cuda_stream)
@@ -307,18 +306,32 @@ def main():
             e2e_s = time.perf_counter() - t0
             d2h_bytes = int(12 * n_hits / args.steps + 8 * READS_PER_STEP)
         else:
-            stage = torch.empty(step_bytes, dtype=torch.uint8, device="cuda")
+            # two staging buffers: step s+1 is copied to rank 0's GPU and broadcast (side stream) while step s is searched
+            stage = [torch.empty(step_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+            side = torch.cuda.Stream()
+            staged = [torch.cuda.Event(), torch.cuda.Event()]
+            dev = torch.device("cuda", local_rank)
+
+            def prefetch(s):
+                with torch.cuda.stream(side):
+                    if rank == 0:
+                        stage[s & 1].copy_(torch.from_numpy(h_reads[s * step_bytes:(s + 1) * step_bytes]), non_blocking=True)
+                    dist.broadcast(stage[s & 1], src=0)                                # NCCL over NVLink: the only data-path collective
+                    staged[s & 1].record(side)
+
+            # untimed: the first gather builds NCCL's point-to-point channels
+            multigpu.gather_hits_padded(np.zeros(1024, dtype=api.HIT_DTYPE), rank, world, dev)
+            multigpu.gather_hits_padded(np.zeros(900_000, dtype=api.HIT_DTYPE), rank, world, dev)
             barrier()
             t0 = time.perf_counter()
+            prefetch(0)
             for s in range(args.steps):
-                if rank == 0:
-                    stage.copy_(torch.from_numpy(h_reads[s * step_bytes:(s + 1) * step_bytes]), non_blocking=True)
-                dist.broadcast(stage, src=0)                                           # NCCL over NVLink: the only collective
-                stream.synchronize()
-                o = ctx.search_batch_ptr(stage.data_ptr(), d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes)
-                hits = o.hits.copy()
-                hits["target"] += np.uint32(rank * BLOCK_SIZE)                         # global target numbering across shards
-                merged = multigpu.gather_hits(hits, rank, world, group=gloo, order="none")   # host concat on rank 0
+                staged[s & 1].synchronize()
+                if s + 1 < args.steps:
+                    prefetch(s + 1)
+                o = ctx.search_batch_ptr(stage[s & 1].data_ptr(), d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes)
+                # hit lists (disjoint by target) → rank 0: one padded NCCL gather, global target numbering added on the way
+                merged = multigpu.gather_hits_padded(o.hits, rank, world, dev, target_base=rank * BLOCK_SIZE)
                 if rank == 0:
                     e2e_matches += len(merged)
             barrier()
@@ -370,7 +383,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": step_bytes + off_np.nbytes, "d2h_bytes_per_step": d2h_bytes,
                     "matches_per_step": int(e2e_matches / args.steps), "ms_per_step": e2e_s / args.steps * 1e3, "breakdown_ms_per_step": e2e_break,
                     "path": "kmcpg_engine_search (pinned host reads → H2D → kernels → D2H hits → host tCov/FPR/sort)" if world == 1 else
-                            "rank0 H2D → ncclBroadcast → kmcpg_search_batch_device on every rank → host concat on rank 0 (gloo)"},
+                            "rank0 pinned reads → H2D → ncclBroadcast (prefetched one step ahead) → kmcpg_search_batch_device on every rank → padded NCCL gather of the hit lists → rank 0 host"},
             "gpu_launches": int(launches), "clocks": clocks,
             "stage_ms_per_step": {"hash": sum(o.ms_hash for o in outs) / args.steps, "locs": sum(o.ms_locs for o in outs) / args.steps,
                                   "probe": probe_ms / args.steps, "call_wall": sum(o.ms_total for o in outs) / args.steps},

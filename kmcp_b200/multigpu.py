@@ -45,3 +45,28 @@ def gather_hits(hits: np.ndarray, rank: int, world: int, group=None, dst: int = 
     if raw.numel():
         dist.send(raw, dst=dst, group=group)
     return None
+
+
+def gather_hits_padded(hits: np.ndarray, rank: int, world: int, device, group=None, dst: int = 0, target_base: int = 0):
+    """the same gather as one padded collective on `device` (NCCL over NVLink when device is this rank's GPU; works on
+    a gloo group with device "cpu" too): sizes by all_gather, then one gather of buffers padded to the largest list.
+    `target_base` is added to the target column on the way (shards that number their targets locally).
+    Rank `dst` gets the concatenation in rank order, the others None."""
+    h32 = np.ascontiguousarray(hits).view(np.uint32).reshape(-1, 3)
+    n = torch.tensor([h32.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    mx = max(max(sizes), 1)
+    buf = torch.zeros((mx, 3), dtype=torch.int32, device=device)
+    if h32.shape[0]:
+        buf[:h32.shape[0]].copy_(torch.from_numpy(h32.view(np.int32)), non_blocking=True)
+        if target_base:
+            buf[:h32.shape[0], 1] += int(np.int32(np.uint32(target_base)))
+    if rank == dst:
+        outs = [torch.empty_like(buf) for _ in range(world)]
+        dist.gather(buf, outs, dst=dst, group=group)
+        allb = torch.cat([o[:sizes[i]] for i, o in enumerate(outs)]).cpu().numpy()
+        return np.ascontiguousarray(allb).view(np.uint32).reshape(-1).view(hits.dtype)
+    dist.gather(buf, None, dst=dst, group=group)
+    return None

@@ -42,12 +42,16 @@ def _worker(rank, world, port, r001, out_path):
     for f in ("query", "target", "count"):
         local[f] = res.hits[f][mine]
     merged = multigpu.gather_hits(local, rank, world)
+    padded = multigpu.gather_hits_padded(local, rank, world, "cpu")           # the NCCL-shaped gather, here on gloo
+    shifted = multigpu.gather_hits_padded(local, rank, world, "cpu", target_base=1000 * rank)
     if rank == 0:
         full = np.zeros(len(res.hits), dtype=dt)
         for f in ("query", "target", "count"):
             full[f] = res.hits[f]
         full = full[np.lexsort((full["target"], full["query"]))]
         ok = np.array_equal(merged, full) and len(full) > 500 and 0 < len(local) < len(full)
+        ok = ok and np.array_equal(padded[np.lexsort((padded["target"], padded["query"]))], full)
+        ok = ok and np.array_equal(shifted[:len(local)], local) and int(shifted["target"].astype(np.int64).sum() - padded["target"].astype(np.int64).sum()) == 1000 * (len(full) - len(local))
         open(out_path, "w").write("ok" if ok else "mismatch %d %d %d" % (len(merged), len(full), len(local)))
     dist.barrier()
     dist.destroy_process_group()
