@@ -48,6 +48,7 @@ int kmcpg_set_stream(kmcpg_ctx *ctx, void *cuda_stream);
 typedef struct {
     int32_t shard_rank;   /* this context keeps the blocks assigned to shard_rank of shard_world (greedy by bytes, */
     int32_t shard_world;  /* largest first); 0/1 = keep everything.  Target numbering stays global in every shard. */
+                          /* A DB with FEWER blocks than shards is cut by column (= target) ranges instead: see kmcpg_shard_pieces. */
     int64_t max_resident_bytes; /* 0 = no limit; otherwise fail with KMCPG_ENOMEM instead of oversubscribing HBM */
 } kmcpg_db_opts;
 
@@ -78,6 +79,17 @@ typedef struct {
 /* the block → shard assignment kmcpg_open_db uses (host only, no device needed): blocks sorted by re-pitched
  * bytes, largest first onto the least loaded shard; owner[i] = shard of block i in __db.yml order */
 int kmcpg_shard_plan(const char *dir, int shard_world, int32_t *owner, int32_t n_owner);
+/* the same plan as pieces (host only): with at least as many blocks as shards every piece is a whole block; with fewer
+ * blocks than shards (e.g. one wide block on 8 GPUs) blocks are cut by column range — the columns of all blocks in units
+ * of 128 targets (16 row bytes), weighted by numSigs, laid end to end and dealt out in shard_world equal-cost stretches.
+ * Rows stay aligned and counts are per target, so the shards' hit lists are still disjoint by target and are only
+ * concatenated.  Returns the number of pieces (every column of every block in exactly one piece). */
+typedef struct {
+    int32_t block, shard;      /* block in __db.yml order; owning shard */
+    uint32_t col0, n_cols;     /* resident columns of the block: [col0, col0 + n_cols), col0 a multiple of 128 */
+    uint64_t resident_bytes;   /* numSigs x re-pitched row bytes of the piece */
+} kmcpg_shard_piece;
+int kmcpg_shard_pieces(const char *dir, int shard_world, kmcpg_shard_piece *out, int32_t cap);
 /* dir = the directory holding __db.yml (normally <db>/R001, S:299-324) */
 int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts);
 int kmcpg_db_info(const kmcpg_ctx *ctx, kmcpg_db_info_t *out);
@@ -199,6 +211,14 @@ typedef struct {
 void kmcpg_default_engine_opts(kmcpg_engine_opts *o);
 int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off,
                         uint32_t n_seqs, kmcpg_results *out);
+/* the same engine over ONE database sharded across several contexts of this process (normally one per GPU of the box,
+ * each opened with kmcpg_open_db(shard_rank = i, shard_world = n_ctx)): every context receives the whole batch (its own
+ * H2D copy from the caller's buffer) and probes it against its resident blocks on its own host thread; the per-shard hit
+ * lists — disjoint by target — are merged part by part in (query, target) order while the GPUs work on the next parts, and
+ * the thresholds / sort / top-N / --try-se / multi-k logic then runs on the union exactly as for one context, so the result
+ * is identical to kmcpg_engine_search on a context holding the whole database (block fan-out + gather of U:939-964). */
+int kmcpg_engine_search_sharded(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq,
+                                const uint64_t *off, uint32_t n_seqs, kmcpg_results *out);
 void kmcpg_free_results(kmcpg_results *r);
 /* QueryFPRWithCacheWithConstantFPR's underlying function (F:32-50, F:140-193), bit-exact with Go */
 double kmcpg_query_fpr(int n, int c, double p);

@@ -29,6 +29,10 @@ class DbOpts(C.Structure):
     _fields_ = [("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("max_resident_bytes", C.c_int64)]
 
 
+class ShardPiece(C.Structure):
+    _fields_ = [("block", C.c_int32), ("shard", C.c_int32), ("col0", C.c_uint32), ("n_cols", C.c_uint32), ("resident_bytes", C.c_uint64)]
+
+
 class DbInfo(C.Structure):
     _fields_ = [("n_ks", C.c_int32), ("ks", C.c_int32 * 8), ("canonical", C.c_int32), ("num_hashes", C.c_int32),
                 ("scaled", C.c_int32), ("scale", C.c_uint32), ("minimizer", C.c_int32), ("minimizer_w", C.c_uint32),
@@ -125,10 +129,10 @@ class RefcountTable(C.Structure):
 
 
 ABI_SYMBOLS = [
-    "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
+    "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_shard_pieces", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
     "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_free_hits", "kmcpg_host_alloc",
     "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
-    "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search",
+    "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search", "kmcpg_engine_search_sharded",
     "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_synth_genomes", "kmcpg_build_synth_db", "kmcpg_write_block",
     "kmcpg_default_refcount_params", "kmcpg_refcounts_create", "kmcpg_refcounts_add", "kmcpg_refcounts_get", "kmcpg_refcounts_free",
 ]
@@ -154,6 +158,7 @@ def load() -> C.CDLL:
     L.kmcpg_last_error.argtypes = [vp]
     L.kmcpg_open_db.argtypes = [vp, C.c_char_p, C.POINTER(DbOpts)]
     L.kmcpg_shard_plan.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.c_int32]
+    L.kmcpg_shard_pieces.argtypes = [C.c_char_p, C.c_int, C.POINTER(ShardPiece), C.c_int32]
     L.kmcpg_db_info.argtypes = [vp, C.POINTER(DbInfo)]
     L.kmcpg_target.argtypes = [vp, C.c_int64, C.POINTER(TargetInfo)]
     L.kmcpg_default_params.argtypes = [C.POINTER(SearchParams)]
@@ -176,6 +181,9 @@ def load() -> C.CDLL:
     L.kmcpg_default_engine_opts.argtypes = [C.POINTER(EngineOpts)]
     L.kmcpg_default_engine_opts.restype = None
     L.kmcpg_engine_search.argtypes = [vp, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
+    L.kmcpg_engine_search_sharded.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
+    L.kmcpg_internal_merge_hits.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64), C.c_int, vp]     # test hook, not part of the ABI
+    L.kmcpg_internal_merge_hits.restype = None
     L.kmcpg_free_results.argtypes = [C.POINTER(Results)]
     L.kmcpg_free_results.restype = None
     L.kmcpg_default_refcount_params.argtypes = [C.POINTER(RefcountParams)]
@@ -398,15 +406,24 @@ class Context:
             setattr(o, k, v)
         return o
 
-    def engine_search(self, buf: np.ndarray, off: np.ndarray, opts: Optional[EngineOpts] = None, refcounts: Optional[int] = None) -> EngineResults:
+    def engine_search(self, buf: np.ndarray, off: np.ndarray, opts: Optional[EngineOpts] = None, refcounts: Optional[int] = None,
+                      shards: Sequence["Context"] = ()) -> EngineResults:
         o = opts or self.default_engine_opts()
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint64)
-        return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o, refcounts=refcounts)
+        return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o, refcounts=refcounts, shards=shards)
 
-    def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts, copy: bool = True, refcounts: Optional[int] = None) -> EngineResults:
+    def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts, copy: bool = True, refcounts: Optional[int] = None,
+                          shards: Sequence["Context"] = ()) -> EngineResults:
         r = Results()
-        self._check(self._L.kmcpg_engine_search(self._h, C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r)))
+        if shards:      # this context + `shards` hold one database between them (kmcpg_engine_search_sharded)
+            hs = (C.c_void_p * (1 + len(shards)))(self._h, *[c._h for c in shards])
+            rc = self._L.kmcpg_engine_search_sharded(hs, 1 + len(shards), C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r))
+            if rc:
+                msgs = [self._L.kmcpg_last_error(c._h).decode() for c in (self, *shards)]
+                raise KmcpGpuError(rc, "; ".join(m for m in msgs if m))
+        else:
+            self._check(self._L.kmcpg_engine_search(self._h, C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r)))
         if refcounts is not None:       # `kmcp profile` stage-1 counters of this batch (kmcpg_refcounts_add)
             self._check(self._L.kmcpg_refcounts_add(refcounts, C.byref(r)))
         nq = r.n_queries
@@ -468,6 +485,28 @@ def shard_plan(r001_dir: str, world: int):
     if n < 0:
         raise KmcpGpuError(n, L.kmcpg_last_error(None).decode())
     return [int(buf[i]) for i in range(n)]
+
+
+def shard_pieces(r001_dir: str, world: int):
+    """the plan as pieces [(block, shard, col0, n_cols, resident_bytes)] (host only): whole blocks, or column ranges when
+    the DB has fewer blocks than shards"""
+    L = load()
+    buf = (ShardPiece * 65536)()
+    n = L.kmcpg_shard_pieces(r001_dir.encode(), world, buf, 65536)
+    if n < 0:
+        raise KmcpGpuError(n, L.kmcpg_last_error(None).decode())
+    return [(int(b.block), int(b.shard), int(b.col0), int(b.n_cols), int(b.resident_bytes)) for b in buf[:n]]
+
+
+def merge_hit_lists(lists: Sequence[np.ndarray]) -> np.ndarray:
+    """the k-way (query, target) merge the sharded engine applies to per-shard hit lists (host only test hook)"""
+    L = load()
+    arrs = [np.ascontiguousarray(a, dtype=HIT_DTYPE) for a in lists]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    ns = (C.c_uint64 * len(arrs))(*[len(a) for a in arrs])
+    out = np.zeros(sum(len(a) for a in arrs), dtype=HIT_DTYPE)
+    L.kmcpg_internal_merge_hits(ptrs, ns, len(arrs), out.ctypes.data)
+    return out
 
 
 def host_alloc(nbytes: int) -> int:

@@ -77,7 +77,9 @@ struct Opts {
     std::string out_file = "-", read1, read2, sort_by = "qcov", query_id, log_file, ref_counts_file;
     double rc_min_qcov = 0.55, rc_max_fpr = 0.01;   // `kmcp profile` -t / -f for --ref-counts
     std::vector<std::string> db_dirs, files, name_maps;   // several -d: every database is searched, results merged as `kmcp merge` does
-    int dedup = 256, min_kmers = 10, min_qlen = 30, top_scores = 0, threads = 0, device = 0;
+    int dedup = 256, min_kmers = 10, min_qlen = 30, top_scores = 0, threads = 0;
+    std::vector<int> devices{0};     // --gpu N, or --gpus LIST|all: every database is sharded over these devices
+    bool all_devices = false;
     double qcov = 0.55, tcov = 0, max_fpr = 0.01;
     bool try_se = false, whole_file = false, use_filename = false, default_name_map = false, keep_unmatched = false, no_header = false,
          do_not_sort = false;
@@ -113,6 +115,8 @@ void usage() {
         "  -j, --threads int                host threads for the post-filter (default all)\n"
         "  -q, --quiet / --log string       logging\n"
         "      --gpu int                    CUDA device ordinal (default 0)\n"
+        "      --gpus list|all              several devices, e.g. 0,1,2,3: every database is sharded over them by index block\n"
+        "                                   (by column range when it has fewer blocks than devices); every device sees every read\n"
         "      --ref-counts file            also write the per-reference, per-chunk read counters of `kmcp profile` stage 1/4\n"
         "                                   (match, uniqMatch, uniqMatchHic), computed from the result stream\n"
         "      --ref-counts-min-qcov float  profile -t/--min-query-cov for --ref-counts (default 0.55)\n"
@@ -376,7 +380,20 @@ int main(int argc, char **argv) {
         else if (a == "-j" || a == "--threads") o.threads = atoi(sval().c_str());
         else if (a == "-q" || a == "--quiet") g_quiet = true;
         else if (a == "--log") o.log_file = sval();
-        else if (a == "--gpu") o.device = atoi(sval().c_str());
+        else if (a == "--gpu") o.devices.assign(1, atoi(sval().c_str()));
+        else if (a == "--gpus") {
+            const std::string v = sval();
+            o.devices.clear();
+            if (v == "all") o.all_devices = true;
+            else
+                for (size_t b = 0; b <= v.size();) {
+                    size_t e = v.find(',', b);
+                    if (e == std::string::npos) e = v.size();
+                    if (e > b) o.devices.push_back(atoi(v.substr(b, e - b).c_str()));
+                    b = e + 1;
+                }
+            if (!o.all_devices && o.devices.empty()) die("invalid value for flag --gpus: %s", v.c_str());
+        }
         else if (a == "-i" || a == "--infile-list") { Reader r; std::string f = sval(), l; if (!r.open(f)) die("fail to read %s", f.c_str()); while (r.getline(l)) if (!l.empty()) o.files.push_back(l); r.close(); }
         else if (a.size() > 1 && a[0] == '-' && a != "-") die("unknown flag: %s", a.c_str());
         else o.files.push_back(a);
@@ -415,7 +432,7 @@ int main(int argc, char **argv) {
     // ---- databases (S:299-324): every child directory of a -d holding __db.yml; several -d = several databases ----
     struct Db {
         std::string dir;
-        kmcpg_ctx *ctx = nullptr;
+        std::vector<kmcpg_ctx *> ctxs;      // one per device: shard i of ctxs.size() (a single context holds the whole database)
         kmcpg_db_info_t info;
         std::vector<kmcpg_target_t> targets;
         std::vector<const std::string *> mapped;
@@ -439,14 +456,53 @@ int main(int argc, char **argv) {
         dbs.emplace_back();
         dbs.back().dir = subs[0];
     }
+    if (o.all_devices) {                  // every visible device: probe the ordinals until one is refused
+        for (int d = 0; d < 64; d++) {
+            kmcpg_ctx *probe = nullptr;
+            if (kmcpg_create(d, &probe)) break;
+            kmcpg_close(probe);
+            o.devices.push_back(d);
+        }
+        if (o.devices.empty()) die("%s", kmcpg_last_error(nullptr));
+    }
     for (auto &db : dbs) {
-        if (kmcpg_create(o.device, &db.ctx)) die("%s", kmcpg_last_error(nullptr));
-        logf("INFO", "loading database into HBM: %s", db.dir.c_str());
+        const int world = (int)o.devices.size();
+        logf("INFO", "loading database into HBM: %s%s", db.dir.c_str(), world > 1 ? " (sharded)" : "");
         auto t_db = std::chrono::steady_clock::now();
-        if (kmcpg_open_db(db.ctx, db.dir.c_str(), nullptr)) die("open kmcp db: %s: %s", db.dir.c_str(), kmcpg_last_error(db.ctx));
-        kmcpg_db_info(db.ctx, &db.info);
-        logf("INFO", "database loaded: %s (%d blocks, %lld targets, %.2f GB in HBM, %.1f s)", db.dir.c_str(), db.info.n_blocks, (long long)db.info.n_targets,
-             db.info.resident_bytes / 1e9, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_db).count());
+        std::vector<kmcpg_ctx *> shard((size_t)world, nullptr);
+        std::vector<std::string> errs((size_t)world);
+        auto load = [&](int r) {          // shards load side by side: each reads only the blocks (or column ranges) it keeps
+            if (kmcpg_create(o.devices[(size_t)r], &shard[(size_t)r])) { errs[(size_t)r] = kmcpg_last_error(nullptr); return; }
+            kmcpg_db_opts dopt;
+            memset(&dopt, 0, sizeof(dopt));
+            dopt.shard_rank = r; dopt.shard_world = world;
+            if (kmcpg_open_db(shard[(size_t)r], db.dir.c_str(), world > 1 ? &dopt : nullptr)) errs[(size_t)r] = kmcpg_last_error(shard[(size_t)r]);
+        };
+        {
+            std::vector<std::thread> lt;
+            for (int r = 1; r < world; r++) lt.emplace_back(load, r);
+            load(0);
+            for (auto &t : lt) t.join();
+        }
+        for (int r = 0; r < world; r++) if (!errs[(size_t)r].empty()) die("open kmcp db: %s: %s", db.dir.c_str(), errs[(size_t)r].c_str());
+        double gb = 0;
+        for (int r = 0; r < world; r++) {
+            kmcpg_db_info_t si;
+            kmcpg_db_info(shard[(size_t)r], &si);
+            if (r == 0) db.info = si;
+            if (world > 1 && si.n_resident_blocks == 0) {
+                // fewer 128-target column units than devices: this device would hash every read and probe nothing
+                logf("WARN", "device %d gets no part of %s and stays idle", o.devices[(size_t)r], db.dir.c_str());
+                kmcpg_close(shard[(size_t)r]);
+                continue;
+            }
+            gb += si.resident_bytes / 1e9;
+            if (world > 1) logf("INFO", "  device %d: %d block piece(s), %.2f GB", o.devices[(size_t)r], si.n_resident_blocks, si.resident_bytes / 1e9);
+            db.ctxs.push_back(shard[(size_t)r]);
+        }
+        if (db.ctxs.empty()) die("invalid kmcp database (no index blocks): %s", db.dir.c_str());
+        logf("INFO", "database loaded: %s (%d blocks, %lld targets, %.2f GB in HBM on %zu device(s), %.1f s)", db.dir.c_str(), db.info.n_blocks,
+             (long long)db.info.n_targets, gb, db.ctxs.size(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t_db).count());
         if (o.qcov <= db.info.fpr)      // S:405-409
             logf("WARN", "the value of -t/--min-query-cov (%f) is <= FPR (%f) of the database, you may get many false positives", o.qcov, db.info.fpr);
         if (db.info.ks[0] != dbs[0].info.ks[0]) die("databases with different k cannot be searched together");
@@ -455,7 +511,7 @@ int main(int argc, char **argv) {
         db.targets.resize((size_t)db.info.n_targets);
         db.mapped.assign((size_t)db.info.n_targets, nullptr);
         for (int64_t t = 0; t < db.info.n_targets; t++) {
-            kmcpg_target(db.ctx, t, &db.targets[(size_t)t]);
+            kmcpg_target(db.ctxs[0], t, &db.targets[(size_t)t]);
             auto it = db.name_map.find(db.targets[(size_t)t].name);
             if (it != db.name_map.end()) db.mapped[(size_t)t] = &it->second;
         }
@@ -467,7 +523,7 @@ int main(int argc, char **argv) {
         kmcpg_refcount_params rp;
         kmcpg_default_refcount_params(&rp);
         rp.min_query_cov = o.rc_min_qcov; rp.max_fpr = o.rc_max_fpr;
-        if (kmcpg_refcounts_create(dbs[0].ctx, nullptr, &rp, &refcounts)) die("%s", kmcpg_last_error(dbs[0].ctx));
+        if (kmcpg_refcounts_create(dbs[0].ctxs[0], nullptr, &rp, &refcounts)) die("%s", kmcpg_last_error(dbs[0].ctxs[0]));
     }
     logf("INFO", "-------------------- [main parameters] --------------------");
     logf("INFO", "  minimum    query length: %d", o.min_qlen);
@@ -662,8 +718,16 @@ int main(int argc, char **argv) {
         Job *job = new Job();
         job->batch = bt;
         job->res.resize(dbs.size());
-        for (size_t d = 0; d < dbs.size(); d++)
-            if (kmcpg_engine_search(dbs[d].ctx, &eo, bt->seq.data(), bt->off.data(), (uint32_t)(bt->off.size() - 1), &job->res[d])) die("%s", kmcpg_last_error(dbs[d].ctx));
+        for (size_t d = 0; d < dbs.size(); d++) {
+            const uint32_t ns = (uint32_t)(bt->off.size() - 1);
+            const int rc = dbs[d].ctxs.size() == 1 ? kmcpg_engine_search(dbs[d].ctxs[0], &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d])
+                                                   : kmcpg_engine_search_sharded(dbs[d].ctxs.data(), (int)dbs[d].ctxs.size(), &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d]);
+            if (rc) {
+                std::string msg;
+                for (auto *c : dbs[d].ctxs) { const char *m = kmcpg_last_error(c); if (m && *m) { msg = m; break; } }
+                die("search failed (%d): %s", rc, msg.c_str());
+            }
+        }
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [&] { return out_q.size() < 2; });
         out_q.push_back(job);
@@ -704,7 +768,7 @@ int main(int argc, char **argv) {
         logf("INFO", "reference counters of %u references saved to: %s", tb.n_refs, o.ref_counts_file.c_str());
         kmcpg_refcounts_free(refcounts);
     }
-    for (auto &db : dbs) kmcpg_close(db.ctx);
+    for (auto &db : dbs) for (auto *c : db.ctxs) kmcpg_close(c);
     logf("INFO", "");
     logf("INFO", "elapsed time: %.3fs", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
     if (g_log) fclose(g_log);

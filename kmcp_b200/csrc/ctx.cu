@@ -42,9 +42,13 @@ uint32_t pitch_for(uint32_t row_bytes) {
     return (row_bytes + 15) / 16 * 16;
 }
 
-void layout_block(DeviceBlock &b, const BlockMeta &m) {
-    b.pitch = pitch_for((uint32_t)m.row_bytes);
-    b.row16 = ((uint32_t)m.row_bytes + 15) / 16;
+void layout_block(DeviceBlock &b, const BlockMeta &m, uint32_t col0, uint32_t n_cols) {
+    if (n_cols == 0) { col0 = 0; n_cols = (uint32_t)m.n_names; }      // the whole block
+    b.col0 = col0; b.n_cols = n_cols;
+    b.whole = col0 == 0 && n_cols == (uint32_t)m.n_names;
+    b.row_bytes = b.whole ? (uint32_t)m.row_bytes : (n_cols + 7) / 8;
+    b.pitch = pitch_for(b.row_bytes);
+    b.row16 = (b.row_bytes + 15) / 16;
     uint32_t g = 1;
     while (g < b.row16 && g < 8) g <<= 1;       // informational: the probe kernel derives its task geometry from row_bytes
     b.G = g;
@@ -117,6 +121,48 @@ static void plan_shards(const DbMeta &m, int world, std::vector<int> &owner, std
         int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
         owner[i] = best;
         load[best] += bytes_of(i);
+    }
+}
+
+// The pieces every shard keeps.  A DB with at least as many blocks as shards is split by whole blocks
+// (plan_shards).  With FEWER blocks than shards, blocks are cut by column range: the columns of all blocks, in units of
+// 128 targets (16 row bytes) weighted by the block's numSigs, are laid end to end and shard s takes the s-th of `world`
+// equal-cost stretches — so a shard holds a contiguous run of columns that may span a block boundary.
+void plan_pieces(const DbMeta &m, int world, std::vector<ShardPiece> &pieces, std::vector<uint64_t> &load) {
+    pieces.clear();
+    load.assign(world, 0);
+    if (world <= 1 || m.blocks.size() >= (size_t)world) {
+        std::vector<int> owner;
+        plan_shards(m, world < 1 ? 1 : world, owner, load);
+        for (size_t i = 0; i < m.blocks.size(); i++) pieces.push_back({(int)i, owner[i], 0u, (uint32_t)m.blocks[i].n_names});
+        return;
+    }
+    const uint32_t UNIT = 128;
+    std::vector<uint64_t> units(m.blocks.size());
+    long double total = 0;
+    for (size_t i = 0; i < m.blocks.size(); i++) {
+        units[i] = ((uint64_t)m.blocks[i].n_names + UNIT - 1) / UNIT;
+        total += (long double)units[i] * (long double)m.blocks[i].num_sigs;
+    }
+    long double done = 0;             // cost of the units already handed out
+    int s = 0;
+    for (size_t i = 0; i < m.blocks.size(); i++) {
+        const long double w = (long double)m.blocks[i].num_sigs;
+        uint64_t u = 0;
+        while (u < units[i]) {
+            // units of this block that still fit below the end of shard s's stretch (at least one, so every piece is non-empty)
+            const long double end_s = s + 1 >= world ? total : total * (long double)(s + 1) / (long double)world;
+            uint64_t take = w > 0 ? (uint64_t)((end_s - done) / w + 0.5L) : units[i] - u;
+            if (s + 1 >= world) take = units[i] - u;
+            take = std::max<uint64_t>(1, std::min<uint64_t>(take, units[i] - u));
+            const uint32_t c0 = (uint32_t)(u * UNIT);
+            const uint32_t c1 = (uint32_t)std::min<uint64_t>((u + take) * UNIT, (uint64_t)m.blocks[i].n_names);
+            pieces.push_back({(int)i, s, c0, c1 - c0});
+            load[s] += (uint64_t)m.blocks[i].num_sigs * pitch_for((c1 - c0 + 7) / 8);
+            u += take;
+            done += (long double)take * w;
+            if (s + 1 < world && done + 0.5L * w >= total * (long double)(s + 1) / (long double)world) s++;
+        }
     }
 }
 
@@ -303,8 +349,8 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
         CU(cudaEventRecord(w.probe_ev[bi * 3 + 1], st));
         ProbeArgs pa;
         memset(&pa, 0, sizeof(pa));
-        pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = (uint32_t)bm.row_bytes;
-        pa.n_names = (uint32_t)bm.n_names; pa.target_base = (uint32_t)bm.target_base; pa.num_hashes = H;
+        pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = b.row_bytes;
+        pa.n_names = b.n_cols; pa.target_base = (uint32_t)(bm.target_base + b.col0); pa.num_hashes = H;
         pa.locs = w.locs.as<uint32_t>(); pa.slot_off = w.slot_off.as<uint64_t>();
         pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = w.nq; pa.paired = p.paired;
         pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
@@ -689,25 +735,26 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
     int world = opts && opts->shard_world > 1 ? opts->shard_world : 1;
     int rank = opts && world > 1 ? opts->shard_rank : 0;
     if (rank < 0 || rank >= world) return fail(ctx, KMCPG_EINVAL, "shard_rank out of range");
-    std::vector<int> owner;
+    std::vector<ShardPiece> pieces;
     std::vector<uint64_t> load;
-    plan_shards(m, world, owner, load);
+    plan_pieces(m, world, pieces, load);
     if (opts && opts->max_resident_bytes > 0 && (int64_t)load[rank] > opts->max_resident_bytes)
         return fail(ctx, KMCPG_ENOMEM, "resident blocks exceed max_resident_bytes");
     ctx->resident_of.assign(m.blocks.size(), -1);
     const size_t CHUNK = 256ull << 20;
     CU(ctx->h_stage.ensure(CHUNK));
-    for (size_t i = 0; i < m.blocks.size(); i++) {
-        if (owner[i] != rank) continue;
+    for (const ShardPiece &pc : pieces) {
+        if (pc.shard != rank) continue;
+        const size_t i = (size_t)pc.block;
         const BlockMeta &bm = m.blocks[i];
         if (bm.num_sigs >= (1ull << 32) - 1) return fail(ctx, KMCPG_EUNSUPPORTED, "blocks with >= 2^32-1 signatures are not supported");
         DeviceBlock b;
         b.meta_idx = (int)i;
-        layout_block(b, bm);
+        layout_block(b, bm, pc.col0, pc.n_cols);
         b.bytes = (size_t)bm.num_sigs * b.pitch;
         CU(cudaMalloc((void **)&b.d_rows, std::max<size_t>(b.bytes, 16)));
         ctx->blocks.push_back(b);
-        ctx->resident_of[i] = (int)ctx->blocks.size() - 1;
+        if (ctx->resident_of[i] < 0) ctx->resident_of[i] = (int)ctx->blocks.size() - 1;
         FILE *f = fopen(bm.path.c_str(), "rb");
         if (!f) return fail(ctx, KMCPG_EIO, "cannot open " + bm.path);
         fseek(f, (long)bm.data_offset, SEEK_SET);
@@ -719,14 +766,15 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
             if (fread(ctx->h_stage.p, 1, bytes, f) != bytes) { fclose(f); return fail(ctx, KMCPG_EIO, "kmcp: truncated index file: " + bm.path); }
             cudaError_t e = ctx->d_tmp.ensure(bytes);
             if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_tmp.p, ctx->h_stage.p, bytes, cudaMemcpyHostToDevice, ctx->st);
-            if (e == cudaSuccess) e = launch_repitch(ctx->d_tmp.as<uint8_t>(), b.d_rows + r0 * b.pitch, nr, (uint32_t)bm.row_bytes, b.pitch, ctx->st);
+            // whole rows travel; the re-pitch kernel keeps the bytes [col0/8, col0/8 + row_bytes) of every row
+            if (e == cudaSuccess) e = launch_repitch_cols(ctx->d_tmp.as<uint8_t>(), b.d_rows + r0 * b.pitch, nr, (uint32_t)bm.row_bytes, b.col0 / 8, b.row_bytes, b.pitch, ctx->st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
             if (e != cudaSuccess) { fclose(f); CU(e); }
         }
         fclose(f);
-        ctx->sum_row_bytes += bm.row_bytes;
+        ctx->sum_row_bytes += b.row_bytes;
         ctx->resident_bytes += (int64_t)b.bytes;
-        ctx->disk_bytes += (int64_t)(bm.num_sigs * (uint64_t)bm.row_bytes);
+        ctx->disk_bytes += (int64_t)(bm.num_sigs * (uint64_t)b.row_bytes);
     }
     ctx->target_sizes.resize((size_t)m.n_targets);
     for (auto &bm : m.blocks)
@@ -742,11 +790,29 @@ int kmcpg_shard_plan(const char *dir, int shard_world, int32_t *owner_out, int32
     int rc = read_db_meta(dir, m, err);
     if (rc) return fail(nullptr, rc, err);
     if ((size_t)n_owner < m.blocks.size()) return fail(nullptr, KMCPG_EINVAL, "owner array too small");
-    std::vector<int> owner;
+    std::vector<ShardPiece> pieces;
     std::vector<uint64_t> load;
-    plan_shards(m, shard_world, owner, load);
-    for (size_t i = 0; i < owner.size(); i++) owner_out[i] = owner[i];
-    return (int)owner.size();
+    plan_pieces(m, shard_world, pieces, load);
+    for (size_t i = 0; i < m.blocks.size(); i++) owner_out[i] = -1;
+    for (const ShardPiece &pc : pieces) if (owner_out[pc.block] < 0) owner_out[pc.block] = pc.shard;   // a split block: the shard of its first columns
+    return (int)m.blocks.size();
+}
+
+int kmcpg_shard_pieces(const char *dir, int shard_world, kmcpg_shard_piece *out, int32_t cap) {
+    if (!dir || shard_world < 1 || (cap > 0 && !out)) return KMCPG_EINVAL;
+    DbMeta m;
+    std::string err;
+    int rc = read_db_meta(dir, m, err);
+    if (rc) return fail(nullptr, rc, err);
+    std::vector<ShardPiece> pieces;
+    std::vector<uint64_t> load;
+    plan_pieces(m, shard_world, pieces, load);
+    if ((size_t)cap < pieces.size()) return fail(nullptr, KMCPG_EINVAL, "piece array too small");
+    for (size_t i = 0; i < pieces.size(); i++) {
+        out[i].block = pieces[i].block; out[i].shard = pieces[i].shard; out[i].col0 = pieces[i].col0; out[i].n_cols = pieces[i].n_cols;
+        out[i].resident_bytes = m.blocks[pieces[i].block].num_sigs * (uint64_t)pitch_for((pieces[i].n_cols + 7) / 8);
+    }
+    return (int)pieces.size();
 }
 
 int kmcpg_db_info(const kmcpg_ctx *ctx, kmcpg_db_info_t *o) {
@@ -770,7 +836,9 @@ int kmcpg_target(const kmcpg_ctx *ctx, int64_t g, kmcpg_target_t *o) {
     if (bl.empty() || g < bl[lo].target_base || g >= bl[lo].target_base + bl[lo].n_names) return KMCPG_EINVAL;
     int c = (int)(g - bl[lo].target_base);
     o->name = bl[lo].names[c].c_str(); o->index = bl[lo].indices[c]; o->genome_size = bl[lo].gsizes[c]; o->n_kmers = bl[lo].sizes[c];
-    o->block = (int32_t)lo; o->col = c; o->resident = ctx->resident_of[lo] >= 0;
+    o->block = (int32_t)lo; o->col = c; o->resident = 0;
+    for (const DeviceBlock &b : ctx->blocks)
+        if (b.meta_idx == (int)lo && (uint32_t)c >= b.col0 && (uint32_t)c < b.col0 + b.n_cols) { o->resident = 1; break; }
     return KMCPG_OK;
 }
 
@@ -964,8 +1032,8 @@ int kmcpg_count_codes(kmcpg_ctx *ctx, const uint64_t *codes, uint64_t n, uint32_
             CU(launch_locs(w.codes.as<uint64_t>(), n, H, b.fm, w.locs.as<uint32_t>(), st));
             ProbeArgs pa;
             memset(&pa, 0, sizeof(pa));
-            pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = (uint32_t)bm.row_bytes;
-            pa.n_names = (uint32_t)bm.n_names; pa.target_base = (uint32_t)bm.target_base; pa.num_hashes = H;
+            pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = b.row_bytes;
+            pa.n_names = b.n_cols; pa.target_base = (uint32_t)(bm.target_base + b.col0); pa.num_hashes = H;
             pa.locs = w.locs.as<uint32_t>(); pa.slot_off = w.slot_off.as<uint64_t>();
             pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = 1; pa.paired = 0;
             pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();

@@ -45,13 +45,20 @@ struct HostBuf {
     template <class T> T *as() const { return (T *)p; }
 };
 
+// one resident piece of a block: all of its columns (the usual case) or, when a DB has fewer blocks than shards, a
+// column range [col0, col0+n_cols) of it (rows stay aligned, counts are per target: no reduction between shards)
 struct DeviceBlock {
     int meta_idx = -1;
     uint8_t *d_rows = nullptr;
     size_t bytes = 0;
     uint32_t pitch = 0, row16 = 0, G = 1, chunks = 1;
+    uint32_t col0 = 0, n_cols = 0;   // resident columns (targets) of block meta_idx; col0 is a multiple of 8
+    uint32_t row_bytes = 0;          // (n_cols+7)/8: the un-padded bytes of one resident row
     FastMod fm;
+    bool whole = true;               // every column of the block is resident here
 };
+
+struct ShardPiece { int block; int shard; uint32_t col0, n_cols; };
 
 struct PinBuf {
     void *p = nullptr;
@@ -128,7 +135,8 @@ namespace kmcpg {
 
 int fail(kmcpg_ctx *c, int code, const std::string &msg);
 uint32_t pitch_for(uint32_t row_bytes);
-void layout_block(DeviceBlock &b, const BlockMeta &m);
+void layout_block(DeviceBlock &b, const BlockMeta &m, uint32_t col0 = 0, uint32_t n_cols = 0);
+void plan_pieces(const DbMeta &m, int world, std::vector<ShardPiece> &pieces, std::vector<uint64_t> &load);
 void free_db(kmcpg_ctx *ctx);
 int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out);
 int pin_acquire(kmcpg_ctx *ctx, size_t bytes, PinBuf &out);

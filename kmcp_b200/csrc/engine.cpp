@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <future>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -216,6 +217,134 @@ size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_part &hits, uint64_t 
     return w;
 }
 
+// ---- one database sharded over several contexts (one per GPU) ------------------------------------------------------
+// what a shard's delivery callback keeps of a part (the executor's own arrays are only valid during the callback)
+struct ShardPart {
+    uint32_t first_query = 0, n_queries = 0;
+    std::vector<kmcpg_hit> hits;
+    std::vector<int32_t> n_kmers, query_len;      // kept by shard 0 only (identical in every shard: they depend on the reads alone)
+};
+
+// k-way merge of per-shard hit lists, each sorted by (query, target) and disjoint by target, into one list in the same order
+void merge_shard_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out) {
+    std::vector<uint64_t> pos((size_t)k, 0);
+    auto key = [](const kmcpg_hit &h) { return (uint64_t)h.query << 32 | h.target; };
+    uint64_t w = 0;
+    for (;;) {
+        int best = -1;
+        uint64_t bk = 0;
+        for (int s = 0; s < k; s++)
+            if (pos[s] < n[s]) { const uint64_t ks = key(lists[s][pos[s]]); if (best < 0 || ks < bk) { best = s; bk = ks; } }
+        if (best < 0) break;
+        // the run of this list below the next smallest head moves as one block
+        uint64_t lim = ~0ull;
+        for (int s = 0; s < k; s++)
+            if (s != best && pos[s] < n[s]) lim = std::min(lim, key(lists[s][pos[s]]));
+        uint64_t e = pos[best] + 1;
+        while (e < n[best] && key(lists[best][e]) < lim) e++;
+        memcpy(out + w, lists[best] + pos[best], (e - pos[best]) * sizeof(kmcpg_hit));
+        w += e - pos[best];
+        pos[best] = e;
+    }
+}
+
+// One device round on every shard at once: a host thread per context runs the streamed search, the calling thread merges
+// part p of all shards as soon as every shard has delivered it and hands the union to `absorb` — while the GPUs are already
+// probing the next parts.  Parts are cut from the read lengths alone, so every shard delivers the same parts.
+// `search(shard, cb, user, summary)` is the streamed device call of one shard (kmcpg_search_batch_cb; a stand-in in the host-only self-test).
+using ShardSearch = std::function<int(int, kmcpg_part_cb, void *, kmcpg_hits *)>;
+
+int sharded_round(int n_ctx, const ShardSearch &search, const std::function<void(const kmcpg_part &)> &absorb, kmcpg_results *out) {
+    struct Shard {
+        std::vector<std::unique_ptr<ShardPart>> parts;
+        bool finished = false;
+        int rc = KMCPG_OK;
+        kmcpg_hits summary;
+        std::function<void(const kmcpg_part &)> on_part;
+    };
+    std::vector<Shard> sh((size_t)n_ctx);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::thread> th;
+    for (int s = 0; s < n_ctx; s++) {
+        memset(&sh[s].summary, 0, sizeof(kmcpg_hits));
+        sh[s].on_part = [&, s](const kmcpg_part &pt) {
+            std::unique_ptr<ShardPart> sp(new ShardPart());
+            sp->first_query = pt.first_query; sp->n_queries = pt.n_queries;
+            sp->hits.assign(pt.hits, pt.hits + pt.n_hits);
+            if (s == 0) { sp->n_kmers.assign(pt.n_kmers, pt.n_kmers + pt.n_queries); sp->query_len.assign(pt.query_len, pt.query_len + pt.n_queries); }
+            std::lock_guard<std::mutex> lk(mu);
+            sh[s].parts.push_back(std::move(sp));
+            cv.notify_all();
+        };
+        th.emplace_back([&, s] {
+            int rc = search(s, [](void *user, const kmcpg_part *pt) { (*(std::function<void(const kmcpg_part &)> *)user)(*pt); }, &sh[s].on_part, &sh[s].summary);
+            std::lock_guard<std::mutex> lk(mu);
+            sh[s].rc = rc; sh[s].finished = true;
+            cv.notify_all();
+        });
+    }
+    int rc = KMCPG_OK;
+    std::vector<kmcpg_hit> merged;
+    std::vector<const kmcpg_hit *> lists((size_t)n_ctx);
+    std::vector<uint64_t> counts((size_t)n_ctx);
+    std::vector<ShardPart *> cur((size_t)n_ctx, nullptr);
+    for (size_t pi = 0; rc == KMCPG_OK; pi++) {
+        bool all_have = false;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] {
+                bool have = true, stuck = false;
+                for (auto &x : sh) { if (x.parts.size() <= pi) { have = false; if (x.finished) stuck = true; } }
+                all_have = have;
+                return have || stuck;
+            });
+            if (!all_have) {
+                // a shard ended without part pi: the regular end (every shard finished with exactly pi parts) or a failure
+                for (auto &x : sh) if (x.finished && x.rc) rc = x.rc;
+                if (rc == KMCPG_OK) {
+                    cv.wait(lk, [&] { for (auto &x : sh) if (!x.finished) return false; return true; });
+                    for (auto &x : sh) { if (x.rc) rc = x.rc; else if (x.parts.size() != pi) rc = KMCPG_EINVAL; }
+                }
+                break;
+            }
+            // the part objects are heap-stable; the vectors holding them may be regrown by the shard threads, so take the pointers here
+            for (int s = 0; s < n_ctx; s++) { cur[s] = sh[s].parts[pi].get(); lists[s] = cur[s]->hits.data(); counts[s] = cur[s]->hits.size(); }
+        }
+        const ShardPart &p0 = *cur[0];
+        uint64_t total = 0;
+        for (int s = 0; s < n_ctx; s++) {
+            const ShardPart &ps = *cur[s];
+            if (ps.first_query != p0.first_query || ps.n_queries != p0.n_queries) rc = KMCPG_EINVAL;   // cannot happen: same reads, same cuts
+            total += counts[s];
+        }
+        if (rc) break;
+        merged.resize(std::max<uint64_t>(total, 1));
+        merge_shard_hits(lists.data(), counts.data(), n_ctx, merged.data());
+        kmcpg_part pt;
+        pt.first_query = p0.first_query; pt.n_queries = p0.n_queries;
+        pt.n_kmers = p0.n_kmers.data(); pt.query_len = p0.query_len.data();
+        pt.hits = merged.data(); pt.n_hits = total;
+        absorb(pt);
+        for (int s = 0; s < n_ctx; s++) { std::lock_guard<std::mutex> lk(mu); sh[s].parts[pi].reset(); }
+    }
+    for (auto &t : th) t.join();
+    float ms = 0;
+    for (int s = 0; s < n_ctx; s++) {
+        if (rc == KMCPG_OK && sh[s].rc) rc = sh[s].rc;
+        if (sh[s].rc == KMCPG_OK) {
+            ms = std::max(ms, sh[s].summary.ms_total);
+            out->probe_row_bytes += sh[s].summary.probe_row_bytes; out->kernel_launches += sh[s].summary.kernel_launches;
+            kmcpg_free_hits(&sh[s].summary);
+        }
+    }
+    out->ms_gpu_total += ms;
+    return rc;
+}
+
+int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
+                       kmcpg_results *out);
+
 }  // namespace
 
 extern "C" {
@@ -231,9 +360,37 @@ double kmcpg_query_fpr(int n, int c, double p) { return query_fpr(n, c, p); }
 
 int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs, kmcpg_results *out) {
     if (!ctx || !o || !out) return KMCPG_EINVAL;
+    return engine_search_impl(&ctx, 1, o, seq, off, n_seqs, out);
+}
+
+int kmcpg_engine_search_sharded(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
+                                kmcpg_results *out) {
+    if (!ctxs || n_ctx < 1 || n_ctx > 64 || !o || !out) return KMCPG_EINVAL;
+    for (int i = 0; i < n_ctx; i++) {
+        if (!ctxs[i]) return KMCPG_EINVAL;
+        for (int j = 0; j < i; j++) if (ctxs[j] == ctxs[i]) return KMCPG_EINVAL;      // a context runs one call at a time
+    }
+    return engine_search_impl(ctxs, n_ctx, o, seq, off, n_seqs, out);
+}
+
+}  // extern "C"
+
+namespace {
+
+int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
+                       kmcpg_results *out) {
+    kmcpg_ctx *ctx = ctxs[0];
     kmcpg_db_info_t info;
     int rc = kmcpg_db_info(ctx, &info);
     if (rc) return rc;
+    for (int i = 1; i < n_ctx; i++) {                 // every shard must hold (a part of) the same database
+        kmcpg_db_info_t oi;
+        rc = kmcpg_db_info(ctxs[i], &oi);
+        if (rc) return rc;
+        if (oi.n_targets != info.n_targets || oi.n_blocks != info.n_blocks || oi.n_ks != info.n_ks || memcmp(oi.ks, info.ks, sizeof(info.ks)) ||
+            oi.fpr != info.fpr || oi.num_hashes != info.num_hashes)
+            return KMCPG_EINVAL;
+    }
     memset(out, 0, sizeof(*out));
     auto T0 = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -365,7 +522,15 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
             // one device call per round: the executor hands over every part (≈ 250 k reads) as soon as its hits have landed in
             // host memory and has the next part's kernels enqueued by then, so the filtering below runs beside the GPU work;
             // only the last part's filtering is exposed
-            {
+            if (n_ctx > 1) {
+                std::function<void(const kmcpg_part &)> fn = [&](const kmcpg_part &pt) { absorb(pt, pt.first_query); };
+                const uint32_t round_seqs = ln_total * step;
+                ShardSearch dev = [&](int s, kmcpg_part_cb cb, void *user, kmcpg_hits *summary) {
+                    return kmcpg_search_batch_cb(ctxs[s], &p, bs, bo, round_seqs, cb, user, summary);
+                };
+                rc = sharded_round(n_ctx, dev, fn, out);
+                if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
+            } else {
                 std::function<void(const kmcpg_part &)> fn = [&](const kmcpg_part &pt) { absorb(pt, pt.first_query); };
                 kmcpg_hits h;
                 rc = kmcpg_search_batch_cb(ctx, &p, bs, bo, ln_total * step,
@@ -416,6 +581,71 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
     out->match_off = r_off; out->matches = (kmcpg_match *)priv->matches.p;
     out->_priv = priv;
     out->ms_total = ms_since(T0);
+    return KMCPG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// test hook (tests/test_abi.py, no GPU needed): the k-way merge the sharded engine applies to the per-shard hit lists
+void kmcpg_internal_merge_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out) { merge_shard_hits(lists, n, k, out); }
+
+// test hook (host only): the threaded part-by-part merger of the sharded engine driven by stand-in shards that deliver
+// seeded hit lists with random delays; fail_shard >= 0 makes that shard return KMCPG_ECUDA before part fail_part.
+// Returns 0 when every merged part equals the expected union (or, with a failure injected, the propagated error code).
+int kmcpg_internal_sharded_selftest(int n_shards, int n_parts, int fail_shard, int fail_part, uint64_t seed) {
+    if (n_shards < 1 || n_shards > 64 || n_parts < 0) return KMCPG_EINVAL;
+    const uint32_t QP = 257, NT = 97;                       // queries per part, targets
+    auto rnd = [](uint64_t &x) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    uint64_t st = seed * 2654435761ull + 88172645463325252ull;
+    std::vector<std::vector<kmcpg_hit>> expect((size_t)n_parts);
+    std::vector<std::vector<std::vector<kmcpg_hit>>> per((size_t)n_shards, std::vector<std::vector<kmcpg_hit>>((size_t)n_parts));
+    std::vector<std::vector<int32_t>> nk((size_t)n_parts), ql((size_t)n_parts);
+    for (int pi = 0; pi < n_parts; pi++) {
+        for (uint32_t q = 0; q < QP; q++) {
+            nk[pi].push_back((int32_t)(rnd(st) % 130)); ql[pi].push_back(150);
+            for (uint32_t t = 0; t < NT; t++)
+                if (rnd(st) % 5 == 0) {
+                    kmcpg_hit h{(uint32_t)pi * QP + q, t, (uint32_t)(rnd(st) % 130 + 1)};
+                    expect[pi].push_back(h);
+                    per[(t * 7 + 3) % (uint32_t)n_shards][pi].push_back(h);
+                }
+        }
+    }
+    ShardSearch fake = [&](int s, kmcpg_part_cb cb, void *user, kmcpg_hits *summary) {
+        uint64_t ls = seed + 977 * (uint64_t)(s + 1);
+        for (int pi = 0; pi < n_parts; pi++) {
+            if (s == fail_shard && pi == fail_part) return (int)KMCPG_ECUDA;
+            std::this_thread::sleep_for(std::chrono::microseconds(rnd(ls) % 300));
+            std::vector<kmcpg_hit> tmp = per[s][pi];         // the executor's arrays are only valid during the callback
+            kmcpg_part pt;
+            pt.first_query = (uint32_t)pi * QP; pt.n_queries = QP;
+            pt.n_kmers = nk[pi].data(); pt.query_len = ql[pi].data();
+            pt.hits = tmp.data(); pt.n_hits = tmp.size();
+            cb(user, &pt);
+            std::fill(tmp.begin(), tmp.end(), kmcpg_hit{0, 0, 0});
+        }
+        if (s == fail_shard && fail_part >= n_parts) return (int)KMCPG_ECUDA;
+        summary->ms_total = 1.0f; summary->kernel_launches = 3; summary->probe_row_bytes = 10;
+        return (int)KMCPG_OK;
+    };
+    int seen = 0;
+    bool same = true;
+    std::function<void(const kmcpg_part &)> absorb = [&](const kmcpg_part &pt) {
+        if (seen >= n_parts) { same = false; return; }
+        const auto &e = expect[seen];
+        if (pt.first_query != (uint32_t)seen * QP || pt.n_queries != QP || pt.n_hits != e.size()) same = false;
+        else if (!e.empty() && memcmp(pt.hits, e.data(), e.size() * sizeof(kmcpg_hit))) same = false;
+        else if (memcmp(pt.n_kmers, nk[seen].data(), QP * 4) || memcmp(pt.query_len, ql[seen].data(), QP * 4)) same = false;
+        seen++;
+    };
+    kmcpg_results out;
+    memset(&out, 0, sizeof(out));
+    int rc = sharded_round(n_shards, fake, absorb, &out);
+    if (rc) return rc;
+    if (!same || seen != n_parts) return KMCPG_EINVAL;
+    if (out.kernel_launches != 3u * (uint32_t)n_shards || out.probe_row_bytes != 10ull * (uint64_t)n_shards) return KMCPG_EINVAL;
     return KMCPG_OK;
 }
 

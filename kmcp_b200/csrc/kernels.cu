@@ -1245,6 +1245,18 @@ __global__ void repitch_kernel(const uint8_t *__restrict__ src, uint8_t *__restr
         dst[i] = x < row_bytes ? src[r * row_bytes + x] : 0;
     }
 }
+// same for a column range of the rows: bytes [src_off, src_off + row_bytes) of every src row (stride src_stride)
+__global__ void repitch_cols_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint64_t n_rows, uint32_t src_stride, uint32_t src_off,
+                                    uint32_t row_bytes, uint32_t pitch) {
+    const uint64_t total = n_rows * pitch;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        uint64_t r = i / pitch;
+        uint32_t x = (uint32_t)(i - r * pitch);
+        dst[i] = x < row_bytes ? src[r * src_stride + src_off + x] : 0;
+    }
+}
 __global__ void unpitch_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch) {
     const uint64_t total = n_rows * row_bytes;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1273,6 +1285,13 @@ cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_
 cudaError_t launch_repitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch, cudaStream_t st) {
     if (!n_rows) return cudaSuccess;
     repitch_kernel<<<148 * 16, 256, 0, st>>>(src, dst, n_rows, row_bytes, pitch);
+    return cudaGetLastError();
+}
+cudaError_t launch_repitch_cols(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t src_stride, uint32_t src_off, uint32_t row_bytes, uint32_t pitch,
+                                cudaStream_t st) {
+    if (!n_rows) return cudaSuccess;
+    if (src_off == 0 && src_stride == row_bytes) return launch_repitch(src, dst, n_rows, row_bytes, pitch, st);
+    repitch_cols_kernel<<<148 * 16, 256, 0, st>>>(src, dst, n_rows, src_stride, src_off, row_bytes, pitch);
     return cudaGetLastError();
 }
 cudaError_t launch_unpitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch, cudaStream_t st) {

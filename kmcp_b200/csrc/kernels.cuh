@@ -121,6 +121,9 @@ cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st);
 // rows (unpadded, row_bytes each) → dst with `pitch` bytes per row, zero padded
 cudaError_t launch_repitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch,
                            cudaStream_t st);
+// the bytes [src_off, src_off + row_bytes) of every src row (src_stride bytes apart) → dst rows of `pitch` bytes
+cudaError_t launch_repitch_cols(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t src_stride, uint32_t src_off, uint32_t row_bytes,
+                                uint32_t pitch, cudaStream_t st);
 cudaError_t launch_unpitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch,
                            cudaStream_t st);
 // sorted (key,val) pairs → kmcpg_hit records, query index rebased by query_base

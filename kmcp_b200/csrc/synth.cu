@@ -297,6 +297,7 @@ int kmcpg_write_block(kmcpg_ctx *ctx, int rb, const char *path) {
     CU(cudaSetDevice(ctx->device));
     const DeviceBlock &b = ctx->blocks[rb];
     const BlockMeta &bm = ctx->meta.blocks[b.meta_idx];
+    if (!b.whole) return fail(ctx, KMCPG_EUNSUPPORTED, "this context holds only a column range of the block");
     const size_t bytes = (size_t)bm.num_sigs * bm.row_bytes;
     CU(ctx->d_tmp.ensure(std::max<size_t>(bytes, 16)));
     CU(launch_unpitch(b.d_rows, ctx->d_tmp.as<uint8_t>(), bm.num_sigs, (uint32_t)bm.row_bytes, b.pitch, ctx->st));

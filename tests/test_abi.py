@@ -98,3 +98,98 @@ def test_shard_plan_reads_headers_and_reports_format_errors(oracle, tmp_path):
     with pytest.raises(api.KmcpGpuError) as e:
         api.shard_plan(str(tmp_path / "nope"), 2)
     assert e.value.code == api.KMCPG_EIO
+
+
+def _check_pieces(pieces, n_names, world):
+    """every column of every block in exactly one piece, cuts on 128-target boundaries, shards in order"""
+    by_block = {}
+    for b, s, c0, nc, _bytes in pieces:
+        assert 0 <= s < world and nc > 0 and c0 % 128 == 0
+        by_block.setdefault(b, []).append((c0, nc, s))
+    assert sorted(by_block) == list(range(len(n_names)))
+    for b, lst in by_block.items():
+        lst.sort()
+        pos = 0
+        for c0, nc, _s in lst:
+            assert c0 == pos
+            pos += nc
+        assert pos == n_names[b]
+
+
+def test_shard_pieces_whole_blocks_and_column_ranges(oracle, tmp_path):
+    """kmcpg_shard_pieces (host only): whole blocks while blocks >= shards, balanced column ranges when a DB has fewer
+    blocks than shards"""
+    import parity_helpers as helpers
+    from kmcp_b200 import api
+    O = oracle
+    sp = O.sketch_params(21)
+    # 300 genomes x 5 chunks = 1500 targets; one block of 1500 and one DB of 3 blocks (640 + 640 + 220)
+    targets = helpers.make_synth_targets(O, sp, 5, 300, 1200, 5, 30)
+    one = O.build_db(targets, str(tmp_path / "one"), sp, num_hashes=1, fpr=0.3, block_size=1500)
+    three = O.build_db(targets, str(tmp_path / "three"), sp, num_hashes=1, fpr=0.3, block_size=640)
+    # whole blocks: identical to the block plan
+    for world in (1, 2, 3):
+        pcs = api.shard_pieces(three, world)
+        assert [(p[0], p[2], p[3]) for p in pcs] == [(0, 0, 640), (1, 0, 640), (2, 0, 220)]
+        assert [p[1] for p in pcs] == api.shard_plan(three, world)
+        assert set(p[1] for p in pcs) == set(range(world))
+    # fewer blocks than shards: column ranges
+    for r001, n_names in ((one, [1500]), (three, [640, 640, 220])):
+        for world in (2, 4, 5, 8, 12, 16):
+            if world <= len(n_names):
+                continue
+            pcs = api.shard_pieces(r001, world)
+            _check_pieces(pcs, n_names, world)
+            shards = [p[1] for p in pcs]
+            assert shards == sorted(shards)                       # a shard holds one contiguous stretch of the column space
+            used = sorted(set(shards))
+            units = sum((n + 127) // 128 for n in n_names)
+            assert used == list(range(min(world, len(used))))
+            if units >= world:
+                assert len(used) == world
+                load = {}
+                for p in pcs:
+                    load[p[1]] = load.get(p[1], 0) + p[4]
+                assert max(load.values()) <= 2.1 * (sum(load.values()) / world) + 1     # within one 128-target unit of the mean
+            assert api.shard_plan(r001, world)[0] == 0
+    # 1500 targets over 4 shards: 12 units of 128 -> 3 units each
+    assert [(p[2], p[3]) for p in api.shard_pieces(one, 4)] == [(0, 384), (384, 384), (768, 384), (1152, 348)]
+
+
+def test_sharded_engine_hit_merge_is_the_canonical_order():
+    """the k-way merge of per-shard hit lists (disjoint by target, each sorted by (query, target)) = the one-context order"""
+    import numpy as np
+    from kmcp_b200 import api
+    rng = np.random.default_rng(5)
+    for k in (1, 2, 3, 8):
+        n = 5000
+        allh = np.zeros(n, dtype=api.HIT_DTYPE)
+        pairs = rng.choice(400 * 300, size=n, replace=False)
+        allh["query"], allh["target"] = pairs // 300, pairs % 300
+        allh["count"] = rng.integers(1, 200, n)
+        allh = allh[np.lexsort((allh["target"], allh["query"]))]
+        owner = rng.integers(0, k, 300)                          # targets → shards (interleaved, like greedy block plans)
+        lists = [allh[owner[allh["target"]] == s] for s in range(k)]
+        if k == 3:
+            lists[1] = lists[1][:0]                              # an empty shard list
+            allh = allh[owner[allh["target"]] != 1]
+        got = api.merge_hit_lists(lists)
+        assert np.array_equal(got, allh)
+    assert len(api.merge_hit_lists([np.zeros(0, api.HIT_DTYPE), np.zeros(0, api.HIT_DTYPE)])) == 0
+
+
+@pytest.mark.timeout(120)
+def test_sharded_round_merger_with_stand_in_shards():
+    """the threaded part-by-part merger of kmcpg_engine_search_sharded, driven on the host by stand-in shards that deliver
+    seeded hit lists with random delays: every merged part equals the union, errors of a shard surface, nothing hangs"""
+    from kmcp_b200 import api
+    L = api.load()
+    f = L.kmcpg_internal_sharded_selftest
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]
+    for shards in (1, 2, 3, 8):
+        for parts in (0, 1, 2, 7, 40):
+            for seed in (1, 2):
+                assert f(shards, parts, -1, 0, seed) == 0, (shards, parts, seed)
+    # a failing shard: first part, a middle part, after its last part; the error code comes back and every thread is joined
+    for shards, parts, fs, fp in ((2, 5, 0, 0), (2, 5, 1, 3), (3, 6, 2, 6), (8, 10, 5, 9), (1, 3, 0, 1), (4, 0, 1, 0)):
+        assert f(shards, parts, fs, fp, 9) == api.KMCPG_ECUDA, (shards, parts, fs, fp)
