@@ -124,26 +124,97 @@ void usage() {
         stderr);
 }
 
+// inflate on a thread of its own: 4 MB chunks travel through a short queue to the parsing thread, so the two mates of a
+// paired-end run (and the next file of a list) are decompressed side by side with the parsing (the reference reads through
+// pgzip/xopen readers that also decompress ahead of the parser)
+struct InflateAhead {
+    static constexpr size_t CHUNK = 4u << 20, DEPTH = 4;
+    struct Chunk { std::vector<char> data; int n = 0; };
+    gzFile f = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Chunk *> ready, spare;
+    Chunk *cur = nullptr;
+    size_t cur_pos = 0;
+    bool stop = false, done = false;
+    void start(gzFile file) {
+        f = file;
+        th = std::thread([this] {
+            for (;;) {
+                Chunk *c = nullptr;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || ready.size() < DEPTH; });
+                    if (stop) return;
+                    if (!spare.empty()) { c = spare.front(); spare.pop_front(); }
+                }
+                if (!c) { c = new Chunk(); c->data.resize(CHUNK); }
+                c->n = gzread(f, c->data.data(), (unsigned)CHUNK);
+                const bool last = c->n <= 0;           // 0: end of file, < 0: error (reported by the consumer)
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    ready.push_back(c);
+                    if (last) done = true;
+                }
+                cv.notify_all();
+                if (last) return;
+            }
+        });
+    }
+    // like gzread: bytes copied (> 0), 0 at end of file, < 0 on a read error
+    int read(char *dst, size_t cap) {
+        if (!cur || cur_pos == (size_t)cur->n) {
+            std::unique_lock<std::mutex> lk(mu);
+            if (cur) { spare.push_back(cur); cur = nullptr; cv.notify_all(); }
+            cv.wait(lk, [&] { return !ready.empty(); });
+            cur = ready.front(); ready.pop_front(); cur_pos = 0;
+            cv.notify_all();
+            if (cur->n <= 0) { const int r = cur->n; ready.push_front(cur); cur = nullptr; return r; }   // stays at the head: every later read sees it too
+        }
+        const size_t n = std::min(cap, (size_t)cur->n - cur_pos);
+        memcpy(dst, cur->data.data() + cur_pos, n);
+        cur_pos += n;
+        return (int)n;
+    }
+    void finish() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        for (Chunk *c : ready) delete c;
+        for (Chunk *c : spare) delete c;
+        delete cur;
+        ready.clear(); spare.clear(); cur = nullptr;
+    }
+};
+
 struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default reader: ID = header up to first blank)
     gzFile f = nullptr;
     std::string path;
     std::vector<char> buf;   // block buffer: lines are found with memchr, no per-line allocation
     size_t pos = 0, end = 0;
     bool eof = false;
-    bool open(const std::string &p) {
+    InflateAhead *ahead = nullptr;
+    bool open(const std::string &p, bool inflate_ahead = false) {
         path = p;
         f = p == "-" ? gzdopen(0, "rb") : gzopen(p.c_str(), "rb");
         if (f) gzbuffer(f, 1 << 20);
         buf.resize(16u << 20);
         pos = end = 0; eof = false;
+        if (f && inflate_ahead) { ahead = new InflateAhead(); ahead->start(f); }
         return f != nullptr;
     }
-    void close() { if (f) gzclose(f); f = nullptr; }
+    void close() {
+        if (ahead) { ahead->finish(); delete ahead; ahead = nullptr; }
+        if (f) gzclose(f);
+        f = nullptr;
+    }
     bool fill() {            // keeps [pos, end), reads more behind it; false at end of file
         if (eof) return false;
         if (pos) { memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
         if (end == buf.size()) buf.resize(buf.size() * 2);
-        int r = gzread(f, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
+        const size_t room = std::min<size_t>(buf.size() - end, 1u << 30);
+        int r = ahead ? ahead->read(buf.data() + end, room) : gzread(f, buf.data() + end, (unsigned)room);
         if (r < 0) die("read error in %s", path.c_str());
         if (r == 0) { eof = true; return false; }
         end += (size_t)r;
@@ -339,8 +410,53 @@ int index_main(int argc, char **argv) {
     return 0;
 }
 
+// kmcp-gpu parse [--ahead] [-1 a -2 b | files...]: the FASTA/Q reader alone (no GPU): one line per record,
+// "id<TAB>length<TAB>crc32 of the sequence bytes"; with -1/-2 the mates alternate.  Used by the host-only tests.
+int parse_main(int argc, char **argv) {
+    std::vector<std::string> files;
+    std::string r1, r2;
+    bool ahead = false;
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--ahead") ahead = true;
+        else if (a == "-1" && i + 1 < argc) r1 = argv[++i];
+        else if (a == "-2" && i + 1 < argc) r2 = argv[++i];
+        else files.push_back(a);
+    }
+    std::string id, out;
+    std::vector<uint8_t> seq;
+    char line[64];
+    auto emit = [&]() {
+        int n = snprintf(line, sizeof(line), "\t%zu\t%08lx\n", seq.size(), (unsigned long)crc32(0L, seq.data(), (uInt)seq.size()));
+        out += id; out.append(line, (size_t)n);
+        seq.clear();
+        if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+    };
+    if (!r1.empty() && !r2.empty()) {
+        Reader a, b;
+        if (!a.open(r1, ahead) || !b.open(r2, ahead)) die("no such file");
+        for (;;) {
+            if (!a.next(id, seq)) break;
+            emit();
+            if (!b.next(id, seq)) break;
+            emit();
+        }
+        a.close(); b.close();
+    } else {
+        for (auto &f : files) {
+            Reader r;
+            if (!r.open(f, ahead)) die("%s: no such file", f.c_str());
+            while (r.next(id, seq)) emit();
+            r.close();
+        }
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "index")) return index_main(argc, argv);
+    if (argc > 1 && !strcmp(argv[1], "parse")) return parse_main(argc, argv);
     Opts o;
     int ai = 1;
     if (ai < argc && !strcmp(argv[ai], "search")) ai++;
@@ -575,8 +691,8 @@ int main(int argc, char **argv) {
         std::string id, id2;
         if (paired) {
             Reader r1, r2;
-            if (!r1.open(o.read1)) die("%s: no such file", o.read1.c_str());
-            if (!r2.open(o.read2)) die("%s: no such file", o.read2.c_str());
+            if (!r1.open(o.read1, true)) die("%s: no such file", o.read1.c_str());      // the two mates inflate side by side
+            if (!r2.open(o.read2, true)) die("%s: no such file", o.read2.c_str());
             logf("INFO", "reading from paired-end files: %s, %s", o.read1.c_str(), o.read2.c_str());
             for (;;) {                                                // S:806-867: ID of read1
                 const size_t mark = cur->seq.size();
@@ -591,7 +707,7 @@ int main(int argc, char **argv) {
             for (auto &file : files) {
                 logf("INFO", "reading sequence file: %s", file.c_str());
                 Reader r;
-                if (!r.open(file)) die("%s: no such file", file.c_str());
+                if (!r.open(file, true)) die("%s: no such file", file.c_str());
                 if (o.whole_file) {                                   // S:885-937 (the N-run follows every record after the second)
                     std::string qid;
                     bool first = true;
