@@ -182,7 +182,7 @@ def load() -> C.CDLL:
     L.kmcpg_default_engine_opts.restype = None
     L.kmcpg_engine_search.argtypes = [vp, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
     L.kmcpg_engine_search_sharded.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
-    L.kmcpg_internal_merge_hits.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64), C.c_int, vp]     # test hook, not part of the ABI
+    L.kmcpg_internal_merge_hits.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64), C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int]     # test hook, not part of the ABI
     L.kmcpg_internal_merge_hits.restype = None
     L.kmcpg_free_results.argtypes = [C.POINTER(Results)]
     L.kmcpg_free_results.restype = None
@@ -498,14 +498,15 @@ def shard_pieces(r001_dir: str, world: int):
     return [(int(b.block), int(b.shard), int(b.col0), int(b.n_cols), int(b.resident_bytes)) for b in buf[:n]]
 
 
-def merge_hit_lists(lists: Sequence[np.ndarray]) -> np.ndarray:
-    """the k-way (query, target) merge the sharded engine applies to per-shard hit lists (host only test hook)"""
+def merge_hit_lists(lists: Sequence[np.ndarray], first_query: int = 0, n_queries: int = 0, threads: int = 1) -> np.ndarray:
+    """the k-way (query, target) merge the sharded engine applies to per-shard hit lists (host only test hook); with
+    threads > 1 the query range [first_query, first_query + n_queries) is split over worker threads"""
     L = load()
     arrs = [np.ascontiguousarray(a, dtype=HIT_DTYPE) for a in lists]
     ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     ns = (C.c_uint64 * len(arrs))(*[len(a) for a in arrs])
     out = np.zeros(sum(len(a) for a in arrs), dtype=HIT_DTYPE)
-    L.kmcpg_internal_merge_hits(ptrs, ns, len(arrs), out.ctypes.data)
+    L.kmcpg_internal_merge_hits(ptrs, ns, len(arrs), out.ctypes.data, first_query, n_queries, threads)
     return out
 
 

@@ -225,27 +225,78 @@ struct ShardPart {
     std::vector<int32_t> n_kmers, query_len;      // kept by shard 0 only (identical in every shard: they depend on the reads alone)
 };
 
-// k-way merge of per-shard hit lists, each sorted by (query, target) and disjoint by target, into one list in the same order
-void merge_shard_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out) {
-    std::vector<uint64_t> pos((size_t)k, 0);
-    auto key = [](const kmcpg_hit &h) { return (uint64_t)h.query << 32 | h.target; };
-    uint64_t w = 0;
-    for (;;) {
-        int best = -1;
-        uint64_t bk = 0;
-        for (int s = 0; s < k; s++)
-            if (pos[s] < n[s]) { const uint64_t ks = key(lists[s][pos[s]]); if (best < 0 || ks < bk) { best = s; bk = ks; } }
-        if (best < 0) break;
-        // the run of this list below the next smallest head moves as one block
-        uint64_t lim = ~0ull;
-        for (int s = 0; s < k; s++)
-            if (s != best && pos[s] < n[s]) lim = std::min(lim, key(lists[s][pos[s]]));
-        uint64_t e = pos[best] + 1;
-        while (e < n[best] && key(lists[best][e]) < lim) e++;
-        memcpy(out + w, lists[best] + pos[best], (e - pos[best]) * sizeof(kmcpg_hit));
-        w += e - pos[best];
-        pos[best] = e;
+// Union of per-shard hit lists — each sorted by (query, target), disjoint by target — in the same (query, target) order, for the
+// queries [q_lo, q_hi) the lists hold.  A counting pass per query, a scatter in shard order (so every query's segment is a
+// concatenation of sorted runs), then the segments that are not yet ascending by target (shards whose target ranges interleave,
+// as whole-block plans produce) are sorted; column-range shards arrive in target order and only pay the check.
+void merge_shard_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out, uint32_t q_lo, uint32_t q_hi, std::vector<uint64_t> &pos) {
+    const size_t nq = (size_t)(q_hi - q_lo);
+    pos.assign(nq + 1, 0);
+    int contributing = 0;
+    for (int s = 0; s < k; s++) {
+        const kmcpg_hit *h = lists[s];
+        for (uint64_t i = 0; i < n[s]; i++) pos[(size_t)(h[i].query - q_lo) + 1]++;
+        contributing += n[s] > 0;
     }
+    for (size_t q = 0; q < nq; q++) pos[q + 1] += pos[q];            // pos[q] = start of query q's segment
+    if (contributing <= 1) {                                         // nothing to interleave
+        for (int s = 0; s < k; s++) if (n[s]) memcpy(out, lists[s], n[s] * sizeof(kmcpg_hit));
+        return;
+    }
+    for (int s = 0; s < k; s++) {
+        const kmcpg_hit *h = lists[s];
+        for (uint64_t i = 0; i < n[s]; i++) out[pos[(size_t)(h[i].query - q_lo)]++] = h[i];
+    }
+    // pos[q] is now the END of segment q; its start is the end of segment q-1
+    uint64_t b = 0;
+    for (size_t q = 0; q < nq; q++) {
+        const uint64_t e = pos[q];
+        if (e - b > 1) {
+            bool asc = true;
+            for (uint64_t i = b + 1; i < e; i++) if (out[i].target < out[i - 1].target) { asc = false; break; }
+            if (!asc) std::sort(out + b, out + e, [](const kmcpg_hit &x, const kmcpg_hit &y) { return x.target < y.target; });
+        }
+        b = e;
+    }
+}
+
+// the same split over query ranges: thread t takes the queries [first + nq·t/T, first + nq·(t+1)/T) of every list (found by
+// binary search) and writes its stretch of the output, whose start is the number of hits in front of that range
+void merge_shard_hits_mt(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out, uint32_t first_query, uint32_t n_queries, int threads) {
+    uint64_t total = 0;
+    for (int s = 0; s < k; s++) total += n[s];
+    int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, threads), total / 65536 + 1));
+    T = std::min(T, pool().size() + 1);
+    if ((uint32_t)T > n_queries) T = (int)std::max<uint32_t>(1, n_queries);
+    if (T <= 1) {
+        std::vector<uint64_t> pos;
+        merge_shard_hits(lists, n, k, out, first_query, first_query + n_queries, pos);
+        return;
+    }
+    std::vector<uint64_t> cut((size_t)(T + 1) * (size_t)k);          // cut[t*k + s]: first hit of list s at or after thread t's first query
+    std::vector<uint32_t> qcut((size_t)T + 1);
+    for (int t = 0; t <= T; t++) {
+        const uint64_t q = (uint64_t)first_query + (uint64_t)n_queries * (uint64_t)t / (uint64_t)T;
+        qcut[t] = (uint32_t)q;
+        for (int s = 0; s < k; s++) {
+            if (t == 0) { cut[s] = 0; continue; }
+            if (t == T) { cut[(size_t)t * k + s] = n[s]; continue; }
+            const kmcpg_hit *b = lists[s], *e = lists[s] + n[s];
+            cut[(size_t)t * k + s] = (uint64_t)(std::lower_bound(b, e, q, [](const kmcpg_hit &h, uint64_t qq) { return (uint64_t)h.query < qq; }) - b);
+        }
+    }
+    std::function<void(int)> work = [&](int t) {
+        std::vector<const kmcpg_hit *> sub((size_t)k);
+        std::vector<uint64_t> cnt((size_t)k), pos;
+        uint64_t o = 0;
+        for (int s = 0; s < k; s++) {
+            sub[s] = lists[s] + cut[(size_t)t * k + s];
+            cnt[s] = cut[(size_t)(t + 1) * k + s] - cut[(size_t)t * k + s];
+            o += cut[(size_t)t * k + s];
+        }
+        merge_shard_hits(sub.data(), cnt.data(), k, out + o, qcut[t], qcut[t + 1], pos);
+    };
+    pool().parallel(T, work);
 }
 
 // One device round on every shard at once: a host thread per context runs the streamed search, the calling thread merges
@@ -254,7 +305,7 @@ void merge_shard_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, k
 // `search(shard, cb, user, summary)` is the streamed device call of one shard (kmcpg_search_batch_cb; a stand-in in the host-only self-test).
 using ShardSearch = std::function<int(int, kmcpg_part_cb, void *, kmcpg_hits *)>;
 
-int sharded_round(int n_ctx, const ShardSearch &search, const std::function<void(const kmcpg_part &)> &absorb, kmcpg_results *out) {
+int sharded_round(int n_ctx, const ShardSearch &search, const std::function<void(const kmcpg_part &)> &absorb, kmcpg_results *out, int threads) {
     struct Shard {
         std::vector<std::unique_ptr<ShardPart>> parts;
         bool finished = false;
@@ -320,7 +371,7 @@ int sharded_round(int n_ctx, const ShardSearch &search, const std::function<void
         }
         if (rc) break;
         merged.resize(std::max<uint64_t>(total, 1));
-        merge_shard_hits(lists.data(), counts.data(), n_ctx, merged.data());
+        merge_shard_hits_mt(lists.data(), counts.data(), n_ctx, merged.data(), p0.first_query, p0.n_queries, threads);
         kmcpg_part pt;
         pt.first_query = p0.first_query; pt.n_queries = p0.n_queries;
         pt.n_kmers = p0.n_kmers.data(); pt.query_len = p0.query_len.data();
@@ -528,7 +579,7 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
                 ShardSearch dev = [&](int s, kmcpg_part_cb cb, void *user, kmcpg_hits *summary) {
                     return kmcpg_search_batch_cb(ctxs[s], &p, bs, bo, round_seqs, cb, user, summary);
                 };
-                rc = sharded_round(n_ctx, dev, fn, out);
+                rc = sharded_round(n_ctx, dev, fn, out, threads);
                 if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
             } else {
                 std::function<void(const kmcpg_part &)> fn = [&](const kmcpg_part &pt) { absorb(pt, pt.first_query); };
@@ -589,7 +640,15 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
 extern "C" {
 
 // test hook (tests/test_abi.py, no GPU needed): the k-way merge the sharded engine applies to the per-shard hit lists
-void kmcpg_internal_merge_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out) { merge_shard_hits(lists, n, k, out); }
+void kmcpg_internal_merge_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out, uint32_t first_query, uint32_t n_queries, int threads) {
+    if (n_queries == 0) {                 // range not given: take it from the lists
+        uint32_t lo = ~0u, hi = 0;
+        for (int s = 0; s < k; s++) if (n[s]) { lo = std::min(lo, lists[s][0].query); hi = std::max(hi, lists[s][n[s] - 1].query); }
+        if (lo == ~0u) return;
+        first_query = lo; n_queries = hi - lo + 1;
+    }
+    merge_shard_hits_mt(lists, n, k, out, first_query, n_queries, std::max(1, threads));
+}
 
 // test hook (host only): the threaded part-by-part merger of the sharded engine driven by stand-in shards that deliver
 // seeded hit lists with random delays; fail_shard >= 0 makes that shard return KMCPG_ECUDA before part fail_part.
@@ -642,7 +701,7 @@ int kmcpg_internal_sharded_selftest(int n_shards, int n_parts, int fail_shard, i
     };
     kmcpg_results out;
     memset(&out, 0, sizeof(out));
-    int rc = sharded_round(n_shards, fake, absorb, &out);
+    int rc = sharded_round(n_shards, fake, absorb, &out, 1 + (int)(seed % 4));
     if (rc) return rc;
     if (!same || seen != n_parts) return KMCPG_EINVAL;
     if (out.kernel_launches != 3u * (uint32_t)n_shards || out.probe_row_bytes != 10ull * (uint64_t)n_shards) return KMCPG_EINVAL;

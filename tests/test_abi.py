@@ -175,6 +175,17 @@ def test_sharded_engine_hit_merge_is_the_canonical_order():
             allh = allh[owner[allh["target"]] != 1]
         got = api.merge_hit_lists(lists)
         assert np.array_equal(got, allh)
+    # the threaded form: query ranges found by binary search, every thread writes its own stretch of the output
+    for k, nq, n, base in ((2, 3000, 200000, 0), (8, 250000, 800000, 1000), (5, 7, 5000, 50), (3, 100000, 40000, 0)):
+        allh = np.zeros(n, dtype=api.HIT_DTYPE)
+        pairs = rng.choice(nq * 1000, size=n, replace=False)
+        allh["query"], allh["target"] = pairs // 1000 + base, pairs % 1000
+        allh["count"] = rng.integers(1, 200, n)
+        allh = allh[np.lexsort((allh["target"], allh["query"]))]
+        owner = rng.integers(0, k, 1000)
+        lists = [allh[owner[allh["target"]] == s] for s in range(k)]
+        for threads in (2, 5, 16):
+            assert np.array_equal(api.merge_hit_lists(lists, base, nq, threads), allh), (k, nq, threads)
     assert len(api.merge_hit_lists([np.zeros(0, api.HIT_DTYPE), np.zeros(0, api.HIT_DTYPE)])) == 0
 
 

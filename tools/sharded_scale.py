@@ -4,11 +4,13 @@ kmcpg_engine_search_sharded from pinned host reads, next to the one-context engi
 Strong scaling: the same index and the same reads at every device count.  Prints one JSON line.
 
   GPUS=0,1 NR=1000000 python tools/sharded_scale.py
+  GPUS=0,1,2,3,4,5,6,7 WORLDS=2,4,8 python tools/sharded_scale.py
 """
 import json
 import os
 import shutil
 import sys
+import threading
 import time
 
 import numpy as np
@@ -18,6 +20,7 @@ sys.path.insert(0, ROOT)
 from kmcp_b200 import api
 
 GPUS = [int(x) for x in os.environ.get("GPUS", "0,1").split(",")]
+WORLDS = [int(x) for x in os.environ.get("WORLDS", str(len(GPUS))).split(",")]       # shard counts to time, e.g. 2,4,8 (devices GPUS[:world])
 NG, GL = int(os.environ.get("NG", 1000)), int(os.environ.get("GL", 4_000_000))
 NR, REPS = int(os.environ.get("NR", 1_000_000)), int(os.environ.get("REPS", 3))
 RL, K, NCH, OV = 150, 21, 10, 150
@@ -93,30 +96,38 @@ def main():
         t1, r1 = timed(lambda: whole.engine_search_ptr(pin_ptr, off_ptr, NR, eo, copy=False), REPS)
         out["one_context"] = {"ms": round(t1 * 1e3, 2), "reads_per_s": round(NR / t1), "matches": r1.n_matches,
                               "probe_row_bytes_per_read": round(r1.probe_row_bytes / NR)}
-        t0 = time.perf_counter()
-        shards = []
-        for rank, dev in enumerate(GPUS):
-            c = api.Context(dev)
-            c.open_db(r001, shard_rank=rank, shard_world=len(GPUS))
-            shards.append(c)
-        out["shards"] = [{"device": dev, "pieces": c.db_info().n_resident_blocks, "row_bytes": int(c.db_info().sum_row_bytes),
-                          "GB": round(c.db_info().resident_bytes / 1e9, 3)} for dev, c in zip(GPUS, shards)]
-        out["shard_load_s"] = round(time.perf_counter() - t0, 1)
-        live = [c for c in shards if c.db_info().n_resident_blocks > 0]
-        tn, rn = timed(lambda: live[0].engine_search_ptr(pin_ptr, off_ptr, NR, eo, copy=False, shards=live[1:]), REPS)
-        out["sharded"] = {"ms": round(tn * 1e3, 2), "reads_per_s": round(NR / tn), "matches": rn.n_matches,
-                          "probe_row_bytes_per_read": round(rn.probe_row_bytes / NR), "gpu_ms_max_shard": round(rn.ms_gpu_total, 2),
-                          "post_ms": round(rn.ms_post, 2)}
-        out["speedup"] = round(t1 / tn, 3)
-        # identical results on a slice (full arrays copied out)
         n_chk = min(NR, 50_000)
         a = whole.engine_search_ptr(pin_ptr, off_ptr, n_chk, eo)
-        b = live[0].engine_search_ptr(pin_ptr, off_ptr, n_chk, eo, shards=live[1:])
-        out["identical_on_first_%d" % n_chk] = bool(np.array_equal(a.match_off, b.match_off) and np.array_equal(a.matches, b.matches)
-                                                    and np.array_equal(a.n_kmers, b.n_kmers))
-        out["matches_equal"] = r1.n_matches == rn.n_matches
-        for c in shards:
-            c.close()
+        out["sharded"] = []
+        for world in WORLDS:
+            devs = GPUS[:world] if len(GPUS) >= world else (GPUS * world)[:world]
+            t0 = time.perf_counter()
+            shards = [None] * world
+
+            def load(rank):
+                c = api.Context(devs[rank])
+                c.open_db(r001, shard_rank=rank, shard_world=world)
+                shards[rank] = c
+
+            th = [threading.Thread(target=load, args=(r,)) for r in range(world)]       # ctypes releases the GIL: shards load side by side
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            load_s = time.perf_counter() - t0
+            live = [c for c in shards if c is not None and c.db_info().n_resident_blocks > 0]
+            tn, rn = timed(lambda: live[0].engine_search_ptr(pin_ptr, off_ptr, NR, eo, copy=False, shards=live[1:]), REPS)
+            b = live[0].engine_search_ptr(pin_ptr, off_ptr, n_chk, eo, shards=live[1:])
+            same = bool(np.array_equal(a.match_off, b.match_off) and np.array_equal(a.matches, b.matches) and np.array_equal(a.n_kmers, b.n_kmers))
+            out["sharded"].append({"world": world, "devices": devs, "row_bytes": [int(c.db_info().sum_row_bytes) for c in live],
+                                   "load_s": round(load_s, 2), "ms": round(tn * 1e3, 2), "reads_per_s": round(NR / tn), "matches": rn.n_matches,
+                                   "probe_row_bytes_per_read": round(rn.probe_row_bytes / NR), "gpu_ms_max_shard": round(rn.ms_gpu_total, 2),
+                                   "post_ms": round(rn.ms_post, 2), "speedup_vs_one_context": round(t1 / tn, 3),
+                                   "identical_on_first_%d" % n_chk: same, "matches_equal": r1.n_matches == rn.n_matches})
+            for c in shards:
+                if c is not None:
+                    c.close()
+            print(json.dumps(out["sharded"][-1]), file=sys.stderr, flush=True)       # progress: survives a cut-off call
         api.host_free(pin_ptr); api.host_free(off_ptr)
     finally:
         whole.close()
