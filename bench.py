@@ -152,8 +152,30 @@ def time_cpu_port(r001, reads_u8, n_reads, target_seconds=12.0):
     return n1 / dt, cores, n1
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the CPU port of the reference algorithm, rank 0 only."""
+def stage_reference_dbs(tmp, world, n_reads_total):
+    """the index of every shard of this arm's config (world blocks of 10,000 targets, seeds GENOME_SEED + r) as .uniki files the
+    CPU port can open, plus the seeded reads: built by the GPU index builder (byte-identical to the oracle's builder,
+    tests/test_gpu_parity.py) because the 1.4 GB blocks take minutes on the CPU.  Returns ([R001 dirs], reads u8)."""
+    from kmcp_b200 import api
+    ctx = api.Context(0)
+    try:
+        dirs = []
+        for r in range(world):
+            ctx.build_synth_db(GENOME_SEED + r, N_GENOMES, GENOME_LEN, k=K, n_chunks=N_CHUNKS, overlap=OVERLAP, num_hashes=H, fpr=FPR, block_size=BLOCK_SIZE)
+            dirs.append(dump_db_for_cpu(ctx, os.path.join(tmp, "shard%d" % r)))
+        d = ctx.device_alloc(n_reads_total * READ_LEN)
+        ctx.synth_reads(READ_SEED, 0, n_reads_total, READ_LEN, GENOME_SEED, N_GENOMES, GENOME_LEN, d)
+        reads = ctx.d2h(d, n_reads_total * READ_LEN)
+        ctx.device_free(d)
+    finally:
+        ctx.close()
+    return dirs, reads
+
+
+def run_reference(args, rank, world, stage=stage_reference_dbs):
+    """--impl reference: the CPU port of the reference algorithm, rank 0 only, on this arm's config: at N ranks the index is
+    N blocks of 10,000 targets (one per GPU in the b200 arm), every read is searched against all of them, and `value`
+    counts read x shard probes exactly as the b200 arm does."""
     if rank != 0:
         return
     from oracle import oracle as O
@@ -162,40 +184,43 @@ def run_reference(args, rank, world):
     shutil.rmtree(tmp, ignore_errors=True)
     os.makedirs(tmp)
     built_by = "gpu index builder (byte-identical to the oracle builder, tests/test_gpu_parity.py)"
+    step_reads = max(1000, (50_000 if SCALE == "full" else 5_000) // world)      # the CPU work per step stays the same at every N
+    n_total = step_reads * (args.steps + args.warmup)
     try:
-        from kmcp_b200 import api
-        ctx = api.Context(0)
-        ctx.build_synth_db(GENOME_SEED, N_GENOMES, GENOME_LEN, k=K, n_chunks=N_CHUNKS, overlap=OVERLAP, num_hashes=H, fpr=FPR, block_size=BLOCK_SIZE)
-        r001 = dump_db_for_cpu(ctx, tmp)
-        step_reads = 50_000 if SCALE == "full" else 5_000
-        n_total = step_reads * (args.steps + args.warmup)
-        d = ctx.device_alloc(n_total * READ_LEN)
-        ctx.synth_reads(READ_SEED, 0, n_total, READ_LEN, GENOME_SEED, N_GENOMES, GENOME_LEN, d)
-        reads = ctx.d2h(d, n_total * READ_LEN)
-        ctx.device_free(d)
-        ctx.close()
+        dirs, reads = stage(tmp, world, n_total)
     except Exception as e:  # no usable GPU: nothing to build the 1.4 GB index with in reasonable time
+        shutil.rmtree(tmp, ignore_errors=True)
         print(json.dumps({"impl": "reference", "unavailable": "cannot stage the synthetic index without the GPU builder: %s" % str(e)[:120]}))
         return
-    odb = O.DB(r001)
+    odbs = [O.DB(d) for d in dirs]
     cores = os.cpu_count() or 1
     off = np.arange(step_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    n_hits = [0]
+
     def step(i):
-        odb.search(packed=(reads[i * step_reads * READ_LEN:(i + 1) * step_reads * READ_LEN], off), threads=cores, algo=1)   # explicit: torchrun sets OMP_NUM_THREADS=1
+        batch = reads[i * step_reads * READ_LEN:(i + 1) * step_reads * READ_LEN]
+        for odb in odbs:          # explicit thread count: torchrun sets OMP_NUM_THREADS=1
+            n_hits[0] += len(odb.search(packed=(batch, off), threads=cores, algo=1).hits)
+
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()
     for i in range(args.steps):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
-    v = step_reads * args.steps / dt
+    v = world * step_reads * args.steps / dt
+    for odb in odbs:
+        odb.close()
     shutil.rmtree(tmp, ignore_errors=True)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u8 bitset",
-        "data": "synthetic", "config": {"workload": workload_name(), "reads_per_step_cpu_sample": step_reads, "db_built_by": built_by},
+        "data": "synthetic", "config": {"workload": workload_name(), "reads_per_step_cpu_sample": step_reads, "db_built_by": built_by,
+                                        "blocks_searched": world,
+                                        "multi_gpu_units": "value counts read×shard probes (every read against each of the %d 10k-target blocks)" % world if world > 1 else "reads"},
+        "job_reads_per_s": step_reads * args.steps / dt,
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port",
-                         "sample": "%d reads per step, restated reference algorithm (oracle algo=1), OpenMP all threads" % step_reads},
+                         "sample": "%d reads per step against %d block(s), restated reference algorithm (oracle algo=1), OpenMP all threads" % (step_reads, world)},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
