@@ -204,3 +204,24 @@ def test_sharded_round_merger_with_stand_in_shards():
     # a failing shard: first part, a middle part, after its last part; the error code comes back and every thread is joined
     for shards, parts, fs, fp in ((2, 5, 0, 0), (2, 5, 1, 3), (3, 6, 2, 6), (8, 10, 5, 9), (1, 3, 0, 1), (4, 0, 1, 0)):
         assert f(shards, parts, fs, fp, 9) == api.KMCPG_ECUDA, (shards, parts, fs, fp)
+
+
+def _build_c_host(tmp_path):
+    """examples/search_host.c: a strict C99 host of the C ABI (what a cgo/JNI/ctypes binding does, without the runtime)"""
+    import subprocess
+    exe = str(tmp_path / "search_host")
+    lib_dir = os.path.join(ROOT, "kmcp_b200")
+    p = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "search_host.c"),
+                        "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lkmcp_gpu", "-Wl,-rpath," + lib_dir, "-o", exe], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    return exe
+
+
+def test_header_is_plain_c99_and_a_c_host_links_and_fails_loudly_without_a_device(tmp_path):
+    import subprocess
+    import torch
+    exe = _build_c_host(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (tests/test_gpu_sharded.py runs the C host against a database)")
+    p = subprocess.run([exe, str(tmp_path / "no_db"), "ACGT" * 40], capture_output=True)
+    assert p.returncode == 2 and b"no CPU fallback" in p.stderr and p.stdout == b""

@@ -197,3 +197,22 @@ def test_cli_gpus_flag_shards_the_database(oracle, small_db, wide_db, tmp_path):
         _run_cli(["-d", os.path.dirname(r001), fq, "-o", one, "-K"])
         _run_cli(["-d", os.path.dirname(r001), fq, "-o", many, "-K", "--gpus", "0,0,0"])
         assert open(one).read() == open(many).read() == O.format_tsv(odb, ids, odb.search(reads), keep_unmatched=True)
+
+
+def test_plain_c_host_prints_the_same_hits(oracle, small_db, tmp_path):
+    """examples/search_host.c (strict C99, no Python in the loop) against the ctypes binding on the same database and reads"""
+    import subprocess
+    from test_abi import _build_c_host
+    from kmcp_b200 import api
+    O = oracle
+    reads = helpers.make_reads(O, RSEED + 8, 40, 40, 30000, GSEED)
+    buf, off = api.pack_seqs(reads)
+    with api.Context(0) as ctx:
+        ctx.open_db(small_db)
+        r = ctx.search_batch(buf, off)
+        exp = "".join("%d\t%s\t%d\t%d\t%d\n" % (h["query"], ctx.target(int(h["target"])).name.decode(), ctx.target(int(h["target"])).index & 0xFFFF,
+                                                h["count"], r.n_kmers[int(h["query"])]) for h in r.hits)
+    assert len(r.hits) > 20
+    p = subprocess.run([_build_c_host(tmp_path), small_db] + [x.decode() for x in reads], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout.decode() == exp
