@@ -158,6 +158,7 @@ int kmcpg_search_batch_cb(kmcpg_ctx *ctx, const kmcpg_search_params *p, const ui
 int kmcpg_host_alloc(void **p, size_t bytes);
 int kmcpg_host_free(void *p);
 /* device memory helpers for callers without a CUDA binding (tests, bench, NCCL staging) */
+int kmcpg_device_memory(kmcpg_ctx *ctx, size_t *free_bytes, size_t *total_bytes);   /* cudaMemGetInfo of the context's device */
 int kmcpg_device_alloc(kmcpg_ctx *ctx, void **p, size_t bytes);
 int kmcpg_device_free(kmcpg_ctx *ctx, void *p);
 int kmcpg_memcpy_h2d(kmcpg_ctx *ctx, void *d, const void *h, size_t bytes);
@@ -219,6 +220,14 @@ int kmcpg_engine_search(kmcpg_ctx *ctx, const kmcpg_engine_opts *o, const uint8_
  * is identical to kmcpg_engine_search on a context holding the whole database (block fan-out + gather of U:939-964). */
 int kmcpg_engine_search_sharded(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq,
                                 const uint64_t *off, uint32_t n_seqs, kmcpg_results *out);
+/* the other way to use several GPUs, for databases that fit every one of them: each context holds the WHOLE database
+ * (kmcpg_open_db without shard options) and the READS are split — contiguous query ranges with about the same number of
+ * sequence bytes, one per context, each searched by kmcpg_engine_search on its own host thread (so hashing, the input copy
+ * and the host post-filter are divided as well, which block shards cannot do); queries are independent, so the result is
+ * the concatenation of the ranges' results and equals kmcpg_engine_search on one context.  Contexts holding only a shard are
+ * refused with KMCPG_EINVAL. */
+int kmcpg_engine_search_replicas(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq,
+                                 const uint64_t *off, uint32_t n_seqs, kmcpg_results *out);
 void kmcpg_free_results(kmcpg_results *r);
 /* QueryFPRWithCacheWithConstantFPR's underlying function (F:32-50, F:140-193), bit-exact with Go */
 double kmcpg_query_fpr(int n, int c, double p);

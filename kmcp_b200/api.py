@@ -131,8 +131,8 @@ class RefcountTable(C.Structure):
 ABI_SYMBOLS = [
     "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_shard_pieces", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
     "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_free_hits", "kmcpg_host_alloc",
-    "kmcpg_host_free", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
-    "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search", "kmcpg_engine_search_sharded",
+    "kmcpg_host_free", "kmcpg_device_memory", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
+    "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search", "kmcpg_engine_search_sharded", "kmcpg_engine_search_replicas",
     "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_synth_genomes", "kmcpg_build_synth_db", "kmcpg_write_block",
     "kmcpg_default_refcount_params", "kmcpg_refcounts_create", "kmcpg_refcounts_add", "kmcpg_refcounts_get", "kmcpg_refcounts_free",
 ]
@@ -170,6 +170,7 @@ def load() -> C.CDLL:
     L.kmcpg_free_hits.restype = None
     L.kmcpg_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.kmcpg_host_free.argtypes = [vp]
+    L.kmcpg_device_memory.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.kmcpg_device_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
     L.kmcpg_device_free.argtypes = [vp, vp]
     L.kmcpg_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -182,6 +183,7 @@ def load() -> C.CDLL:
     L.kmcpg_default_engine_opts.restype = None
     L.kmcpg_engine_search.argtypes = [vp, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
     L.kmcpg_engine_search_sharded.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
+    L.kmcpg_engine_search_replicas.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(EngineOpts), vp, vp, C.c_uint32, C.POINTER(Results)]
     L.kmcpg_internal_merge_hits.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64), C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int]     # test hook, not part of the ABI
     L.kmcpg_internal_merge_hits.restype = None
     L.kmcpg_free_results.argtypes = [C.POINTER(Results)]
@@ -407,20 +409,24 @@ class Context:
         return o
 
     def engine_search(self, buf: np.ndarray, off: np.ndarray, opts: Optional[EngineOpts] = None, refcounts: Optional[int] = None,
-                      shards: Sequence["Context"] = ()) -> EngineResults:
+                      shards: Sequence["Context"] = (), replicas: Sequence["Context"] = ()) -> EngineResults:
         o = opts or self.default_engine_opts()
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint64)
-        return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o, refcounts=refcounts, shards=shards)
+        return self.engine_search_ptr(buf.ctypes.data, off.ctypes.data, len(off) - 1, o, refcounts=refcounts, shards=shards, replicas=replicas)
 
     def engine_search_ptr(self, seq_ptr: int, off_ptr: int, n_seqs: int, o: EngineOpts, copy: bool = True, refcounts: Optional[int] = None,
-                          shards: Sequence["Context"] = ()) -> EngineResults:
+                          shards: Sequence["Context"] = (), replicas: Sequence["Context"] = ()) -> EngineResults:
         r = Results()
-        if shards:      # this context + `shards` hold one database between them (kmcpg_engine_search_sharded)
-            hs = (C.c_void_p * (1 + len(shards)))(self._h, *[c._h for c in shards])
-            rc = self._L.kmcpg_engine_search_sharded(hs, 1 + len(shards), C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r))
+        if shards or replicas:
+            # this context + `shards` hold one database between them (kmcpg_engine_search_sharded), or this context and
+            # `replicas` each hold all of it and the reads are split (kmcpg_engine_search_replicas)
+            others = list(shards or replicas)
+            hs = (C.c_void_p * (1 + len(others)))(self._h, *[c._h for c in others])
+            fn = self._L.kmcpg_engine_search_sharded if shards else self._L.kmcpg_engine_search_replicas
+            rc = fn(hs, 1 + len(others), C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r))
             if rc:
-                msgs = [self._L.kmcpg_last_error(c._h).decode() for c in (self, *shards)]
+                msgs = [self._L.kmcpg_last_error(c._h).decode() for c in (self, *others)]
                 raise KmcpGpuError(rc, "; ".join(m for m in msgs if m))
         else:
             self._check(self._L.kmcpg_engine_search(self._h, C.byref(o), seq_ptr, off_ptr, n_seqs, C.byref(r)))
@@ -452,6 +458,12 @@ class Context:
         self._L.kmcpg_refcounts_free(rc)
 
     # ---- memory helpers ----
+    def device_memory(self) -> Tuple[int, int]:
+        """(free, total) bytes of this context's device"""
+        f, t = C.c_size_t(), C.c_size_t()
+        self._check(self._L.kmcpg_device_memory(self._h, C.byref(f), C.byref(t)))
+        return int(f.value), int(t.value)
+
     def device_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._check(self._L.kmcpg_device_alloc(self._h, C.byref(p), nbytes))

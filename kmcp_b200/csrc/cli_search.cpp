@@ -80,6 +80,7 @@ struct Opts {
     int dedup = 256, min_kmers = 10, min_qlen = 30, top_scores = 0, threads = 0;
     std::vector<int> devices{0};     // --gpu N, or --gpus LIST|all: every database is sharded over these devices
     bool all_devices = false;
+    std::string gpu_mode = "auto";   // --gpu-mode: shard (index split over the devices), replicate (reads split), auto (replicate when the index fits)
     double qcov = 0.55, tcov = 0, max_fpr = 0.01;
     bool try_se = false, whole_file = false, use_filename = false, default_name_map = false, keep_unmatched = false, no_header = false,
          do_not_sort = false;
@@ -117,6 +118,9 @@ void usage() {
         "      --gpu int                    CUDA device ordinal (default 0)\n"
         "      --gpus list|all              several devices, e.g. 0,1,2,3: every database is sharded over them by index block\n"
         "                                   (by column range when it has fewer blocks than devices); every device sees every read\n"
+        "      --gpu-mode string            with several devices: \"shard\" splits the index (every device searches every read),\n"
+        "                                   \"replicate\" loads the whole index on every device and splits the reads,\n"
+        "                                   \"auto\" (default) replicates when the index fits into every device's free memory\n"
         "      --ref-counts file            also write the per-reference, per-chunk read counters of `kmcp profile` stage 1/4\n"
         "                                   (match, uniqMatch, uniqMatchHic), computed from the result stream\n"
         "      --ref-counts-min-qcov float  profile -t/--min-query-cov for --ref-counts (default 0.55)\n"
@@ -497,6 +501,7 @@ int main(int argc, char **argv) {
         else if (a == "-q" || a == "--quiet") g_quiet = true;
         else if (a == "--log") o.log_file = sval();
         else if (a == "--gpu") o.devices.assign(1, atoi(sval().c_str()));
+        else if (a == "--gpu-mode") o.gpu_mode = sval();
         else if (a == "--gpus") {
             const std::string v = sval();
             o.devices.clear();
@@ -529,6 +534,7 @@ int main(int argc, char **argv) {
     if (o.qcov < 0 || o.qcov > 1) die("value of -t/--min-query-cov should be in range [0, 1]");
     if (o.tcov < 0 || o.tcov > 1) die("value of -T/-target-cov should be in range [0, 1]");
     if (o.do_not_sort && o.top_scores > 0) logf("WARN", "flag -n/--keep-top-scores ignored when -S/--do-not-sort given");
+    if (o.gpu_mode != "auto" && o.gpu_mode != "shard" && o.gpu_mode != "replicate") die("invalid value for flag --gpu-mode: %s. Available: auto/shard/replicate", o.gpu_mode.c_str());
 
     logf("INFO", "kmcp-gpu (B200 search path of kmcp v0.9.5)");
     logf("INFO", "checking input files ...");
@@ -549,6 +555,7 @@ int main(int argc, char **argv) {
     struct Db {
         std::string dir;
         std::vector<kmcpg_ctx *> ctxs;      // one per device: shard i of ctxs.size() (a single context holds the whole database)
+        bool replicas = false;              // every context holds the whole database and the reads are split instead
         kmcpg_db_info_t info;
         std::vector<kmcpg_target_t> targets;
         std::vector<const std::string *> mapped;
@@ -583,16 +590,32 @@ int main(int argc, char **argv) {
     }
     for (auto &db : dbs) {
         const int world = (int)o.devices.size();
-        logf("INFO", "loading database into HBM: %s%s", db.dir.c_str(), world > 1 ? " (sharded)" : "");
         auto t_db = std::chrono::steady_clock::now();
         std::vector<kmcpg_ctx *> shard((size_t)world, nullptr);
         std::vector<std::string> errs((size_t)world);
-        auto load = [&](int r) {          // shards load side by side: each reads only the blocks (or column ranges) it keeps
-            if (kmcpg_create(o.devices[(size_t)r], &shard[(size_t)r])) { errs[(size_t)r] = kmcpg_last_error(nullptr); return; }
+        size_t min_free = ~(size_t)0;
+        for (int r = 0; r < world; r++) {
+            if (kmcpg_create(o.devices[(size_t)r], &shard[(size_t)r])) die("%s", kmcpg_last_error(nullptr));
+            size_t fr = 0, tot = 0;
+            if (world > 1 && kmcpg_device_memory(shard[(size_t)r], &fr, &tot) == KMCPG_OK) min_free = std::min(min_free, fr);
+        }
+        if (world > 1) {
+            // replicate when the whole index (plus 8 GB of batch work space) fits into every device; otherwise split it
+            uint64_t db_bytes = 0;
+            std::vector<kmcpg_shard_piece> pcs(1 << 16);
+            const int np = kmcpg_shard_pieces(db.dir.c_str(), 1, pcs.data(), (int32_t)pcs.size());
+            if (np < 0) die("open kmcp db: %s: %s", db.dir.c_str(), kmcpg_last_error(nullptr));
+            for (int i = 0; i < np; i++) db_bytes += pcs[(size_t)i].resident_bytes;
+            const bool fits = min_free != ~(size_t)0 && db_bytes + (8ull << 30) <= (uint64_t)min_free;
+            db.replicas = o.gpu_mode == "replicate" || (o.gpu_mode == "auto" && fits);
+            if (o.gpu_mode == "replicate" && !fits) logf("WARN", "--gpu-mode replicate: the index (%.1f GB) may not fit into every device", db_bytes / 1e9);
+        }
+        logf("INFO", "loading database into HBM: %s%s", db.dir.c_str(), world > 1 ? (db.replicas ? " (a replica per device, reads are split)" : " (sharded over the devices)") : "");
+        auto load = [&](int r) {          // devices load side by side: each reads only the blocks (or column ranges) it keeps
             kmcpg_db_opts dopt;
             memset(&dopt, 0, sizeof(dopt));
             dopt.shard_rank = r; dopt.shard_world = world;
-            if (kmcpg_open_db(shard[(size_t)r], db.dir.c_str(), world > 1 ? &dopt : nullptr)) errs[(size_t)r] = kmcpg_last_error(shard[(size_t)r]);
+            if (kmcpg_open_db(shard[(size_t)r], db.dir.c_str(), world > 1 && !db.replicas ? &dopt : nullptr)) errs[(size_t)r] = kmcpg_last_error(shard[(size_t)r]);
         };
         {
             std::vector<std::thread> lt;
@@ -655,6 +678,12 @@ int main(int argc, char **argv) {
         w.write(h, strlen(h));
     }
 
+    {   // replicas split every batch between them: keep each device's share at the usual batch size
+        size_t nrep = 1;
+        for (auto &db : dbs) if (db.replicas) nrep = std::max(nrep, db.ctxs.size());
+        o.batch_reads = std::min<size_t>(o.batch_reads * nrep, (size_t)1 << 22);
+        o.batch_bytes = std::min<size_t>(o.batch_bytes * nrep, (size_t)2 << 30);
+    }
     kmcpg_engine_opts eo;
     kmcpg_default_engine_opts(&eo);
     eo.min_query_len = o.min_qlen; eo.min_matched = o.min_kmers; eo.dedup_threshold = o.dedup; eo.min_query_cov = o.qcov; eo.min_target_cov = o.tcov;
@@ -836,8 +865,10 @@ int main(int argc, char **argv) {
         job->res.resize(dbs.size());
         for (size_t d = 0; d < dbs.size(); d++) {
             const uint32_t ns = (uint32_t)(bt->off.size() - 1);
-            const int rc = dbs[d].ctxs.size() == 1 ? kmcpg_engine_search(dbs[d].ctxs[0], &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d])
-                                                   : kmcpg_engine_search_sharded(dbs[d].ctxs.data(), (int)dbs[d].ctxs.size(), &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d]);
+            const int nc = (int)dbs[d].ctxs.size();
+            const int rc = nc == 1           ? kmcpg_engine_search(dbs[d].ctxs[0], &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d])
+                           : dbs[d].replicas ? kmcpg_engine_search_replicas(dbs[d].ctxs.data(), nc, &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d])
+                                             : kmcpg_engine_search_sharded(dbs[d].ctxs.data(), nc, &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d]);
             if (rc) {
                 std::string msg;
                 for (auto *c : dbs[d].ctxs) { const char *m = kmcpg_last_error(c); if (m && *m) { msg = m; break; } }

@@ -842,6 +842,14 @@ int kmcpg_target(const kmcpg_ctx *ctx, int64_t g, kmcpg_target_t *o) {
     return KMCPG_OK;
 }
 
+// internal (engine.cpp): 1 when every block of the DB is resident here with all of its columns (not a shard)
+int kmcpg_internal_holds_whole_db(const kmcpg_ctx *ctx) {
+    if (!ctx || !ctx->has_db) return 0;
+    size_t whole = 0;
+    for (const DeviceBlock &b : ctx->blocks) whole += b.whole;
+    return whole == ctx->meta.blocks.size() && ctx->blocks.size() == ctx->meta.blocks.size();
+}
+
 // internal (engine.cpp): Sizes[t] of every target as float64, valid while the DB is open
 const double *kmcpg_internal_target_sizes(const kmcpg_ctx *ctx) { return ctx && ctx->has_db ? ctx->target_sizes.data() : nullptr; }
 
@@ -911,6 +919,13 @@ int kmcpg_host_alloc(void **p, size_t bytes) {
     return KMCPG_OK;
 }
 int kmcpg_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? KMCPG_OK : KMCPG_ECUDA; }
+
+int kmcpg_device_memory(kmcpg_ctx *ctx, size_t *free_bytes, size_t *total_bytes) {
+    if (!ctx || !free_bytes || !total_bytes) return KMCPG_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemGetInfo(free_bytes, total_bytes));
+    return KMCPG_OK;
+}
 
 int kmcpg_device_alloc(kmcpg_ctx *ctx, void **p, size_t bytes) {
     if (!ctx || !p) return KMCPG_EINVAL;

@@ -115,6 +115,10 @@ class WorkerPool {
     // runs fn(0..n-1); the caller executes task 0, workers the rest (n-1 <= size())
     void parallel(int n, const std::function<void(int)> &fn) {
         if (n <= 1) { if (n == 1) fn(0); return; }
+        // one job at a time: a caller that finds the pool busy (several engine calls on different contexts run at once)
+        // does its tasks itself — those callers are already parallel to each other
+        std::unique_lock<std::mutex> job(job_mu_, std::try_to_lock);
+        if (!job.owns_lock()) { for (int i = 0; i < n; i++) fn(i); return; }
         {
             std::lock_guard<std::mutex> lk(mu_);
             fn_ = &fn; n_ = n; pending_ = n - 1; gen_++;
@@ -147,7 +151,7 @@ class WorkerPool {
         }
     }
     std::vector<std::thread> th_;
-    std::mutex mu_;
+    std::mutex mu_, job_mu_;
     std::condition_variable cv_, done_;
     const std::function<void(int)> *fn_ = nullptr;
     int n_ = 0, pending_ = 0;
@@ -394,7 +398,14 @@ int sharded_round(int n_ctx, const ShardSearch &search, const std::function<void
 }
 
 int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
-                       kmcpg_results *out);
+                       kmcpg_results *out, FprCache *shared_cache = nullptr);
+
+// the calling thread's FPR memo for this database's p (F:140-193); handed to helper threads so they all fill ONE table
+FprCache *thread_fpr_cache(double fpr) {
+    static thread_local FprCache tl_cache;
+    tl_cache.reset(fpr);
+    return &tl_cache;
+}
 
 }  // namespace
 
@@ -429,7 +440,7 @@ int kmcpg_engine_search_sharded(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_e
 namespace {
 
 int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
-                       kmcpg_results *out) {
+                       kmcpg_results *out, FprCache *shared_cache) {
     kmcpg_ctx *ctx = ctxs[0];
     kmcpg_db_info_t info;
     int rc = kmcpg_db_info(ctx, &info);
@@ -447,9 +458,7 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
     auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     const uint32_t step = o->paired ? 2 : 1;
     const uint32_t nq = n_seqs / step;
-    static thread_local FprCache tl_cache;
-    tl_cache.reset(info.fpr);
-    FprCache *cache = &tl_cache;          // worker threads must share THIS instance, not their own thread_local
+    FprCache *cache = shared_cache ? shared_cache : thread_fpr_cache(info.fpr);      // worker threads share THIS instance, not their own thread_local
     const double *tsize = kmcpg_internal_target_sizes(ctx);
 
     ResPriv *priv = new ResPriv();
@@ -635,9 +644,175 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
     return KMCPG_OK;
 }
 
+// ---- the whole database on every context, the READS split between them ------------------------------------------------
+// For databases that fit every GPU this is the better split: a context hashes and probes only its share of the queries
+// (block / column shards all hash every read and all copy the whole batch), and the host post-filter runs once per replica
+// in parallel.  Queries are independent, so the answer is the concatenation of the per-range answers.
+using ReplicaSearch = std::function<int(int, const uint64_t *, uint32_t, kmcpg_results *)>;   // (replica, off of its range, n_seqs, out)
+
+kmcpg_results alloc_results(uint32_t nq, uint64_t n_matches) {
+    kmcpg_results r;
+    memset(&r, 0, sizeof(r));
+    ResPriv *priv = new ResPriv();
+    priv->query_len = big_acquire((size_t)nq * 4); priv->n_kmers = big_acquire((size_t)nq * 4); priv->k_used = big_acquire((size_t)nq * 4);
+    priv->match_off = big_acquire(((size_t)nq + 1) * 8);
+    priv->matches = big_acquire(std::max<uint64_t>(n_matches, 1) * sizeof(kmcpg_match));
+    r.n_queries = nq; r.n_matches = n_matches;
+    r.query_len = (int32_t *)priv->query_len.p; r.n_kmers = (int32_t *)priv->n_kmers.p; r.k_used = (int32_t *)priv->k_used.p;
+    r.match_off = (uint64_t *)priv->match_off.p; r.matches = (kmcpg_match *)priv->matches.p;
+    r.match_off[0] = 0;
+    r._priv = priv;
+    return r;
+}
+
+int replicas_impl(int n_rep, const ReplicaSearch &search, bool paired, const uint64_t *off, uint32_t n_seqs, kmcpg_results *out) {
+    auto T0 = std::chrono::steady_clock::now();
+    const uint32_t step = paired ? 2 : 1;
+    if (paired && (n_seqs & 1)) return KMCPG_EINVAL;
+    const uint32_t nq = n_seqs / step;
+    // contiguous query ranges with about the same number of sequence bytes (by count when there are no bytes)
+    std::vector<uint32_t> cut((size_t)n_rep + 1, nq);
+    cut[0] = 0;
+    const uint64_t b0 = n_seqs ? off[0] : 0, total = n_seqs ? off[n_seqs] - off[0] : 0;
+    for (int r = 1; r < n_rep; r++) {
+        uint32_t q;
+        if (total == 0) q = (uint32_t)((uint64_t)nq * (uint64_t)r / (uint64_t)n_rep);
+        else {
+            const uint64_t want = b0 + (uint64_t)((long double)total * (long double)r / (long double)n_rep);
+            uint32_t lo = cut[r - 1], hi = nq;                      // first query whose first byte is at or after `want`
+            while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (off[(size_t)mid * step] < want) lo = mid + 1; else hi = mid; }
+            q = lo;
+        }
+        cut[r] = std::max(cut[r - 1], std::min(q, nq));
+    }
+    std::vector<kmcpg_results> res((size_t)n_rep);
+    std::vector<int> rcs((size_t)n_rep, KMCPG_OK);
+    for (auto &r : res) memset(&r, 0, sizeof(r));
+    {
+        std::vector<std::thread> th;
+        auto run = [&](int r) { if (cut[r + 1] > cut[r]) rcs[r] = search(r, off + (size_t)cut[r] * step, (cut[r + 1] - cut[r]) * step, &res[r]); };
+        for (int r = 1; r < n_rep; r++) th.emplace_back(run, r);
+        run(0);
+        for (auto &t : th) t.join();
+    }
+    int rc = KMCPG_OK;
+    for (int r = 0; r < n_rep; r++) if (rcs[r] && !rc) rc = rcs[r];
+    if (rc) {
+        for (int r = 0; r < n_rep; r++) if (!rcs[r] && res[r]._priv) kmcpg_free_results(&res[r]);
+        return rc;
+    }
+    std::vector<uint64_t> mbase((size_t)n_rep + 1, 0);
+    for (int r = 0; r < n_rep; r++) {
+        if (cut[r + 1] > cut[r] && res[r].n_queries != cut[r + 1] - cut[r]) rc = KMCPG_EINVAL;     // cannot happen
+        mbase[r + 1] = mbase[r] + (cut[r + 1] > cut[r] ? res[r].n_matches : 0);
+    }
+    if (rc) { for (auto &r : res) if (r._priv) kmcpg_free_results(&r); return rc; }
+    *out = alloc_results(nq, mbase[n_rep]);
+    std::function<void(int)> copy = [&](int r) {                    // every replica's answer moves to its place, side by side
+        const uint32_t a = cut[r], n = cut[r + 1] - cut[r];
+        if (!n) return;
+        const kmcpg_results &x = res[r];
+        memcpy(out->query_len + a, x.query_len, (size_t)n * 4);
+        memcpy(out->n_kmers + a, x.n_kmers, (size_t)n * 4);
+        memcpy(out->k_used + a, x.k_used, (size_t)n * 4);
+        for (uint32_t i = 0; i < n; i++) out->match_off[(size_t)a + i + 1] = mbase[r] + x.match_off[i + 1];
+        kmcpg_match *dst = out->matches + mbase[r];
+        for (uint64_t i = 0; i < x.n_matches; i++) { dst[i] = x.matches[i]; dst[i].query += a; }
+    };
+    const int T = std::min(n_rep, pool().size() + 1);               // the pool runs at most size()+1 tasks of a job
+    std::function<void(int)> lane = [&](int t) { for (int r = t; r < n_rep; r += T) copy(r); };
+    pool().parallel(T, lane);
+    for (int r = 0; r < n_rep; r++) {
+        if (!res[r]._priv) continue;
+        out->ms_gpu_total = std::max(out->ms_gpu_total, res[r].ms_gpu_total); out->ms_post = std::max(out->ms_post, res[r].ms_post);
+        out->probe_row_bytes += res[r].probe_row_bytes; out->kernel_launches += res[r].kernel_launches;
+        kmcpg_free_results(&res[r]);
+    }
+    out->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - T0).count();
+    return KMCPG_OK;
+}
+
 }  // namespace
 
+extern "C" int kmcpg_internal_holds_whole_db(const kmcpg_ctx *ctx);
+
 extern "C" {
+
+int kmcpg_engine_search_replicas(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
+                                 kmcpg_results *out) {
+    if (!ctxs || n_ctx < 1 || n_ctx > 64 || !o || !out || (n_seqs && (!seq || !off))) return KMCPG_EINVAL;
+    kmcpg_db_info_t info;
+    for (int i = 0; i < n_ctx; i++) {
+        if (!ctxs[i]) return KMCPG_EINVAL;
+        for (int j = 0; j < i; j++) if (ctxs[j] == ctxs[i]) return KMCPG_EINVAL;
+        kmcpg_db_info_t oi;
+        int rc = kmcpg_db_info(ctxs[i], &oi);
+        if (rc) return rc;
+        if (!kmcpg_internal_holds_whole_db(ctxs[i])) return KMCPG_EINVAL;            // a shard cannot answer alone
+        if (i == 0) info = oi;
+        else if (oi.n_targets != info.n_targets || oi.n_blocks != info.n_blocks || oi.disk_bytes != info.disk_bytes || oi.fpr != info.fpr ||
+                 oi.n_ks != info.n_ks || memcmp(oi.ks, info.ks, sizeof(info.ks)) || oi.num_hashes != info.num_hashes)
+            return KMCPG_EINVAL;
+    }
+    memset(out, 0, sizeof(*out));
+    FprCache *cache = thread_fpr_cache(info.fpr);       // one memo for all replicas
+    ReplicaSearch dev = [&](int r, const uint64_t *off_r, uint32_t n_r, kmcpg_results *res) {
+        return engine_search_impl(&ctxs[r], 1, o, seq, off_r, n_r, res, cache);
+    };
+    return replicas_impl(n_ctx, dev, o->paired != 0, off, n_seqs, out);
+}
+
+// test hook (host only): replicas_impl with stand-in replicas whose answer is a seeded function of the GLOBAL query index, so the
+// concatenation over n_rep ranges must equal the answer of one replica over the whole batch.  fail_rep >= 0: that replica fails.
+int kmcpg_internal_replicas_selftest(int n_rep, uint32_t nq, int paired, int fail_rep, uint64_t seed) {
+    if (n_rep < 1 || n_rep > 64) return KMCPG_EINVAL;
+    auto mix = [](uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; };
+    const uint32_t step = paired ? 2 : 1, n_seqs = nq * step;
+    std::vector<uint64_t> off((size_t)n_seqs + 1);
+    off[0] = 1000;                                        // a batch that does not start at offset 0
+    for (uint32_t i = 0; i < n_seqs; i++) {
+        const uint64_t h = mix(seed * 1315423911ull + i);
+        off[i + 1] = off[i] + (h % 7 == 0 ? 0 : (h % 5 == 0 ? 20000 : 100 + h % 100));
+    }
+    ReplicaSearch fake = [&](int r, const uint64_t *off_r, uint32_t n_r, kmcpg_results *res) {
+        if (r == fail_rep) return (int)KMCPG_ECUDA;
+        const uint32_t base = (uint32_t)((off_r - off.data()) / step), n = n_r / step;
+        std::vector<uint32_t> cnt(n);
+        uint64_t tot = 0;
+        for (uint32_t q = 0; q < n; q++) { cnt[q] = (uint32_t)(mix(seed + 7 * (uint64_t)(base + q)) % 4); tot += cnt[q]; }
+        *res = alloc_results(n, tot);
+        uint64_t w = 0;
+        for (uint32_t q = 0; q < n; q++) {
+            const uint32_t g = base + q;
+            res->query_len[q] = (int32_t)(off_r[(size_t)q * step + step] - off_r[(size_t)q * step]);
+            res->n_kmers[q] = (int32_t)(mix(g) % 130); res->k_used[q] = 21;
+            for (uint32_t j = 0; j < cnt[q]; j++) {
+                kmcpg_match &m = res->matches[w++];
+                m.query = q; m.target = (uint32_t)(mix(g * 31ull + j) % 1000); m.count = j + 1; m._pad = 0;
+                m.fpr = 1e-9 * g; m.qcov = 0.5 + j; m.tcov = 0.25 * g; m.jacc = (double)j / (g + 1.0);
+            }
+            res->match_off[q + 1] = w;
+        }
+        res->ms_gpu_total = 1.0f + r; res->ms_post = 0.5f; res->probe_row_bytes = 10; res->kernel_launches = 2;
+        std::this_thread::sleep_for(std::chrono::microseconds(mix(seed + r) % 500));
+        return (int)KMCPG_OK;
+    };
+    kmcpg_results one, many;
+    memset(&one, 0, sizeof(one)); memset(&many, 0, sizeof(many));
+    int rc = replicas_impl(n_rep, fake, paired != 0, off.data(), n_seqs, &many);
+    if (rc) return rc;
+    const int fr = fail_rep; fail_rep = -1;
+    rc = replicas_impl(1, fake, paired != 0, off.data(), n_seqs, &one);
+    fail_rep = fr;
+    if (rc) { kmcpg_free_results(&many); return rc; }
+    bool same = one.n_queries == many.n_queries && one.n_matches == many.n_matches && one.n_queries == nq;
+    if (same && nq) same = !memcmp(one.query_len, many.query_len, (size_t)nq * 4) && !memcmp(one.n_kmers, many.n_kmers, (size_t)nq * 4) &&
+                           !memcmp(one.k_used, many.k_used, (size_t)nq * 4);
+    if (same) same = !memcmp(one.match_off, many.match_off, ((size_t)nq + 1) * 8);
+    if (same && one.n_matches) same = !memcmp(one.matches, many.matches, one.n_matches * sizeof(kmcpg_match));
+    kmcpg_free_results(&one); kmcpg_free_results(&many);
+    return same ? KMCPG_OK : KMCPG_EINVAL;
+}
 
 // test hook (tests/test_abi.py, no GPU needed): the k-way merge the sharded engine applies to the per-shard hit lists
 void kmcpg_internal_merge_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out, uint32_t first_query, uint32_t n_queries, int threads) {

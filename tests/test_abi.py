@@ -225,3 +225,19 @@ def test_header_is_plain_c99_and_a_c_host_links_and_fails_loudly_without_a_devic
         pytest.skip("a GPU is present (tests/test_gpu_sharded.py runs the C host against a database)")
     p = subprocess.run([exe, str(tmp_path / "no_db"), "ACGT" * 40], capture_output=True)
     assert p.returncode == 2 and b"no CPU fallback" in p.stderr and p.stdout == b""
+
+
+@pytest.mark.timeout(180)
+def test_replicas_split_and_concatenation_with_stand_in_replicas():
+    """kmcpg_engine_search_replicas' host logic (byte-balanced query ranges, one thread per replica, answers moved side by side
+    into one result) with stand-in replicas whose answer is a function of the global query index: n ranges == one range"""
+    from kmcp_b200 import api
+    L = api.load()
+    f = L.kmcpg_internal_replicas_selftest
+    f.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_uint64]
+    for n_rep in (1, 2, 3, 8, 20, 64):
+        for nq in (0, 1, 2, 7, 1000, 30011):
+            for paired in (0, 1):
+                assert f(n_rep, nq, paired, -1, 3 + nq) == 0, (n_rep, nq, paired)
+    for n_rep, nq, fail in ((2, 1000, 0), (2, 1000, 1), (8, 5000, 5), (3, 10, 2)):
+        assert f(n_rep, nq, 0, fail, 11) == api.KMCPG_ECUDA, (n_rep, nq, fail)

@@ -183,8 +183,54 @@ def test_sharded_engine_several_parts(oracle, small_db):
             _close(ctxs)
 
 
-def test_cli_gpus_flag_shards_the_database(oracle, small_db, wide_db, tmp_path):
-    """kmcp-gpu search --gpus 0,0,0: three shard contexts (here all on device 0) give the byte-identical TSV"""
+def test_replicas_engine_equals_one_context(oracle, small_db, wide_db):
+    """the whole database on every context, the reads split between them: concatenated answers == the one-context answer"""
+    from kmcp_b200 import api
+    O = oracle
+    for r001, ng, gl, gs, n_rep in ((small_db, 40, 30000, GSEED, 3), (wide_db, 150, 12000, GSEED + 1, 2)):
+        rng = np.random.default_rng(9)
+        reads = helpers.make_reads(O, RSEED + 12, 3000, ng, gl, gs) + helpers.edge_reads(21)
+        long_read = O.synth_genome(gs, 1, gl)[:9000]                   # one long query among the short ones unbalances the ranges
+        reads.insert(700, long_read)
+        buf, off = api.pack_seqs(reads)
+        r1 = helpers.make_reads(O, RSEED + 1, 500, ng, gl, gs)
+        r2 = helpers.make_reads(O, RSEED + 2, 500, ng, gl, gs)
+        r2[5] = b"ACGT"; r1[6] = b""; r2[6] = b""
+        pbuf, poff = api.pack_seqs([x for p in zip(r1, r2) for x in p])
+        ctxs = []
+        try:
+            for _ in range(n_rep):
+                c = api.Context(0)
+                c.open_db(r001)
+                ctxs.append(c)
+            for kw in (dict(), dict(min_query_cov=0.7, sort_by=2, top_n_scores=1), dict(do_not_sort=1), dict(dedup_threshold=50)):
+                one = ctxs[0].engine_search(buf, off, ctxs[0].default_engine_opts(**kw))
+                many = ctxs[0].engine_search(buf, off, ctxs[0].default_engine_opts(**kw), replicas=ctxs[1:])
+                _same_results(many, one)
+            assert len(one.matches) > 1000
+            for kw in (dict(paired=1), dict(paired=1, try_se=1, min_query_cov=0.6)):
+                one = ctxs[0].engine_search(pbuf, poff, ctxs[0].default_engine_opts(**kw))
+                many = ctxs[0].engine_search(pbuf, poff, ctxs[0].default_engine_opts(**kw), replicas=ctxs[1:])
+                _same_results(many, one)
+            # fewer queries than replicas, and an empty batch
+            sb, so = api.pack_seqs(reads[:2])
+            _same_results(ctxs[0].engine_search(sb, so, replicas=ctxs[1:]), ctxs[0].engine_search(sb, so))
+            e = ctxs[0].engine_search(np.zeros(1, np.uint8), np.zeros(1, np.uint64), replicas=ctxs[1:])
+            assert len(e.matches) == 0 and len(e.match_off) == 1
+            # a context that holds only a shard cannot be a replica
+            with api.Context(0) as sh:
+                sh.open_db(r001, shard_rank=0, shard_world=2)
+                with pytest.raises(api.KmcpGpuError) as err:
+                    ctxs[0].engine_search(buf, off, replicas=[sh])
+                assert err.value.code == api.KMCPG_EINVAL
+            free, total = ctxs[0].device_memory()
+            assert 0 < free <= total
+        finally:
+            _close(ctxs)
+
+
+def test_cli_gpus_flag_shards_or_replicates_the_database(oracle, small_db, wide_db, tmp_path):
+    """kmcp-gpu search --gpus 0,0,0 (three contexts, here all on device 0) in every --gpu-mode gives the byte-identical TSV"""
     from test_gpu_parity import _run_cli, _write_fastq
     O = oracle
     for r001, ng, gl, gs in ((small_db, 40, 30000, GSEED), (wide_db, 150, 12000, GSEED + 1)):
@@ -193,10 +239,14 @@ def test_cli_gpus_flag_shards_the_database(oracle, small_db, wide_db, tmp_path):
         ids = [b"read_%d/1" % i for i in range(len(reads))]
         fq = str(tmp_path / "q.fq")
         _write_fastq(fq, ids, reads, gz=False)
-        one, many = str(tmp_path / "one.tsv"), str(tmp_path / "many.tsv")
+        exp = O.format_tsv(odb, ids, odb.search(reads), keep_unmatched=True)
+        one = str(tmp_path / "one.tsv")
         _run_cli(["-d", os.path.dirname(r001), fq, "-o", one, "-K"])
-        _run_cli(["-d", os.path.dirname(r001), fq, "-o", many, "-K", "--gpus", "0,0,0"])
-        assert open(one).read() == open(many).read() == O.format_tsv(odb, ids, odb.search(reads), keep_unmatched=True)
+        assert open(one).read() == exp
+        for mode in ("shard", "replicate", "auto"):
+            many = str(tmp_path / ("many_%s.tsv" % mode))
+            _run_cli(["-d", os.path.dirname(r001), fq, "-o", many, "-K", "--gpus", "0,0,0", "--gpu-mode", mode])
+            assert open(many).read() == exp, mode
 
 
 def test_plain_c_host_prints_the_same_hits(oracle, small_db, tmp_path):
