@@ -222,7 +222,7 @@ def test_header_is_plain_c99_and_a_c_host_links_and_fails_loudly_without_a_devic
     import torch
     exe = _build_c_host(tmp_path)
     if torch.cuda.is_available():
-        pytest.skip("a GPU is present (tests/test_gpu_sharded.py runs the C host against a database)")
+        pytest.skip("a GPU is present (tests/test_zz_gpu_sharded.py runs the C host against a database)")
     p = subprocess.run([exe, str(tmp_path / "no_db"), "ACGT" * 40], capture_output=True)
     assert p.returncode == 2 and b"no CPU fallback" in p.stderr and p.stdout == b""
 
