@@ -92,7 +92,7 @@ void big_release(BigBuf &b) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     g_pool.push_back(b);
     b = BigBuf();
-    while (g_pool.size() > 16) {
+    while (g_pool.size() > 64) {          // several engine calls may run at once (one per replica): keep their arrays too
         size_t m = 0;
         for (size_t i = 1; i < g_pool.size(); i++) if (g_pool[i].cap < g_pool[m].cap) m = i;
         free(g_pool[m].p);
