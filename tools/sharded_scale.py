@@ -1,5 +1,5 @@
 """One process, several GPUs (dev tool): the C2 index (one block of 10,000 targets) sharded by column range over the
-devices in GPUS (default "0,1"; "0,0" puts both shards on one GPU for a functional run), timed through
+devices in GPUS — and, MODES=replicas, loaded whole on every device with the reads split instead — (default "0,1"; "0,0" puts both shards on one GPU for a functional run), timed through
 kmcpg_engine_search_sharded from pinned host reads, next to the one-context engine on device GPUS[0].
 Strong scaling: the same index and the same reads at every device count.  Prints one JSON line.
 
@@ -21,6 +21,7 @@ from kmcp_b200 import api
 
 GPUS = [int(x) for x in os.environ.get("GPUS", "0,1").split(",")]
 WORLDS = [int(x) for x in os.environ.get("WORLDS", str(len(GPUS))).split(",")]       # shard counts to time, e.g. 2,4,8 (devices GPUS[:world])
+MODES = os.environ.get("MODES", "shard,replicas").split(",")   # shard: index cut over the devices; replicas: whole index everywhere, reads split
 NG, GL = int(os.environ.get("NG", 1000)), int(os.environ.get("GL", 4_000_000))
 NR, REPS = int(os.environ.get("NR", 1_000_000)), int(os.environ.get("REPS", 3))
 RL, K, NCH, OV = 150, 21, 10, 150
@@ -99,14 +100,17 @@ def main():
         n_chk = min(NR, 50_000)
         a = whole.engine_search_ptr(pin_ptr, off_ptr, n_chk, eo)
         out["sharded"] = []
-        for world in WORLDS:
+        for mode, world in [(m, w) for m in MODES for w in WORLDS]:
             devs = GPUS[:world] if len(GPUS) >= world else (GPUS * world)[:world]
             t0 = time.perf_counter()
             shards = [None] * world
 
             def load(rank):
                 c = api.Context(devs[rank])
-                c.open_db(r001, shard_rank=rank, shard_world=world)
+                if mode == "replicas":
+                    c.open_db(r001)
+                else:
+                    c.open_db(r001, shard_rank=rank, shard_world=world)
                 shards[rank] = c
 
             th = [threading.Thread(target=load, args=(r,)) for r in range(world)]       # ctypes releases the GIL: shards load side by side
@@ -116,10 +120,11 @@ def main():
                 t.join()
             load_s = time.perf_counter() - t0
             live = [c for c in shards if c is not None and c.db_info().n_resident_blocks > 0]
-            tn, rn = timed(lambda: live[0].engine_search_ptr(pin_ptr, off_ptr, NR, eo, copy=False, shards=live[1:]), REPS)
-            b = live[0].engine_search_ptr(pin_ptr, off_ptr, n_chk, eo, shards=live[1:])
+            kw = {"replicas": live[1:]} if mode == "replicas" else {"shards": live[1:]}
+            tn, rn = timed(lambda: live[0].engine_search_ptr(pin_ptr, off_ptr, NR, eo, copy=False, **kw), REPS)
+            b = live[0].engine_search_ptr(pin_ptr, off_ptr, n_chk, eo, **kw)
             same = bool(np.array_equal(a.match_off, b.match_off) and np.array_equal(a.matches, b.matches) and np.array_equal(a.n_kmers, b.n_kmers))
-            out["sharded"].append({"world": world, "devices": devs, "row_bytes": [int(c.db_info().sum_row_bytes) for c in live],
+            out["sharded"].append({"mode": mode, "world": world, "devices": devs, "row_bytes": [int(c.db_info().sum_row_bytes) for c in live],
                                    "load_s": round(load_s, 2), "ms": round(tn * 1e3, 2), "reads_per_s": round(NR / tn), "matches": rn.n_matches,
                                    "probe_row_bytes_per_read": round(rn.probe_row_bytes / NR), "gpu_ms_max_shard": round(rn.ms_gpu_total, 2),
                                    "post_ms": round(rn.ms_post, 2), "speedup_vs_one_context": round(t1 / tn, 3),
