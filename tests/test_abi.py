@@ -241,3 +241,17 @@ def test_replicas_split_and_concatenation_with_stand_in_replicas():
                 assert f(n_rep, nq, paired, -1, 3 + nq) == 0, (n_rep, nq, paired)
     for n_rep, nq, fail in ((2, 1000, 0), (2, 1000, 1), (8, 5000, 5), (3, 10, 2)):
         assert f(n_rep, nq, 0, fail, 11) == api.KMCPG_ECUDA, (n_rep, nq, fail)
+
+
+def test_binding_copies_records_out_of_library_memory():
+    """api._np_from: one byte copy of the records behind a ctypes pointer; the result must not alias library memory"""
+    import numpy as np
+    from kmcp_b200 import api
+    src = np.zeros(1000, dtype=api.MATCH_DTYPE)
+    src["query"] = np.arange(1000); src["fpr"] = np.linspace(0, 1, 1000); src["jacc"] = 0.25
+    out = api._np_from(C.cast(src.ctypes.data, C.POINTER(api.Match)), 1000, C.sizeof(api.Match), api.MATCH_DTYPE)
+    assert out.dtype == api.MATCH_DTYPE and np.array_equal(out, src)
+    src["query"] = 0
+    assert out["query"][999] == 999 and out.flags.writeable
+    assert C.sizeof(api.Match) == api.MATCH_DTYPE.itemsize == 48 and C.sizeof(api.Hit) == api.HIT_DTYPE.itemsize == 12
+    assert len(api._np_from(None, 0, 12, api.HIT_DTYPE)) == 0
