@@ -1,0 +1,203 @@
+"""Host-only tests of kmcp_b200/csrc/fastgz.h, the gzip decoder of the CLI's read ingest (the
+reference reads its inputs through xopen + pgzip, search.go S:793-1000).  `kmcp-gpu gunzip` runs the decoder alone.
+zlib (through Python) is the checker: every stream zlib can produce must decode to the same bytes, and every damaged
+stream must be refused — never accepted with different bytes, never crash (a sanitizer build of the decoder runs the
+damaged variants in-process)."""
+import gzip
+import os
+import random
+import struct
+import subprocess
+import zlib
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "kmcp_b200", "kmcp-gpu")
+
+
+def _gunzip(path, *args, ok=True):
+    if not os.path.exists(EXE):
+        pytest.fail("kmcp_b200/kmcp-gpu is not built: run __graft_entry__.build()")
+    p = subprocess.run([EXE, "gunzip", *args, path], capture_output=True, timeout=300)
+    if ok:
+        assert p.returncode == 0, p.stderr.decode()
+    return p
+
+
+def _gz(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8):
+    c = zlib.compressobj(level, zlib.DEFLATED, 31, mem, strategy)
+    return c.compress(data) + c.flush()
+
+
+def _corpus():
+    rnd = random.Random(11)
+    fq = b"".join(b"@read%d len=150\n%s\n+\n%s\n" % (i, bytes(rnd.choice(b"ACGT") for _ in range(150)),
+                                                    bytes(rnd.choice(b"FFFFFFFF:,#") for _ in range(150))) for i in range(1500))
+    far = os.urandom(300)
+    return {
+        "empty": b"",
+        "one": b"x",
+        "fastq": fq,
+        "random": os.urandom(200_000),                                             # stored blocks at any level
+        "zeros": bytes(3_000_000),                                                 # distance 1, length 258, window slides
+        "bytes": bytes(range(256)) * 300,
+        "far": (far + os.urandom(32768 - 300)) * 40,                               # matches at distance exactly 32768
+        "text": b" ".join(rnd.choice([b"kmer", b"bloom", b"index", b"read", b"chunk", b"%d" % rnd.randrange(10 ** 6)]) for _ in range(200_000)),
+        "skewed": bytes(rnd.choice(b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaab") if rnd.random() < 0.999 else rnd.randrange(256) for _ in range(400_000)),
+    }
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return _corpus()
+
+
+def test_every_zlib_stream_decodes_to_the_same_bytes(corpus, tmp_path):
+    n = 0
+    for name, data in corpus.items():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+                if level in (0, 9) and strategy not in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED):
+                    continue
+                p = str(tmp_path / "a.gz")
+                open(p, "wb").write(_gz(data, level, strategy, mem=1 if level == 1 else 8))
+                assert _gunzip(p).stdout == data, (name, level, strategy)
+                n += 1
+    assert n > 100
+
+
+def test_small_reads_and_small_output_chunks(corpus, tmp_path):
+    """input arriving a few bytes at a time (pipes) and callers asking for tiny pieces see the same stream"""
+    for name in ("fastq", "far", "random", "skewed"):
+        data = corpus[name][:150_000]
+        p = str(tmp_path / "a.gz")
+        open(p, "wb").write(_gz(data[:60_000], 6) + _gz(data[60_000:], 1, zlib.Z_FIXED))
+        for rs, ck in ((1, 1 << 20), (7, 13), (4096, 1), (65536, 70_000)):
+            if ck == 1 and name != "fastq":
+                continue
+            assert _gunzip(p, "--read-size", str(rs), "--chunk", str(ck)).stdout == data, (name, rs, ck)
+    with open(str(tmp_path / "a.gz"), "rb") as f:                                # from a pipe
+        q = subprocess.run([EXE, "gunzip", "-"], stdin=f, capture_output=True, timeout=60)
+    assert q.returncode == 0 and q.stdout == corpus["skewed"][:150_000]
+
+
+def test_members_headers_plain_input_and_trailing_garbage(corpus, tmp_path):
+    fq = corpus["fastq"]
+    p = str(tmp_path / "m.gz")
+    # several members (pgzip / bgzip / `cat a.gz b.gz`), empty members in between, a member with a file name (gzip.GzipFile)
+    import io
+    named = io.BytesIO()
+    with gzip.GzipFile(filename="reads.fq", mode="wb", fileobj=named, mtime=12345) as g:
+        g.write(fq[5000:9000])
+    blob = _gz(fq[:5000]) + _gz(b"") + named.getvalue() + _gz(b"") + _gz(fq[9000:], 9)
+    open(p, "wb").write(blob)
+    assert _gunzip(p).stdout == fq
+    # all optional header fields at once: FEXTRA (a BGZF-style subfield), FNAME, FCOMMENT, FHCRC
+    raw = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = raw.compress(fq) + raw.flush()
+    extra = b"BC" + struct.pack("<HH", 2, 0xBEEF)
+    hdr = b"\x1f\x8b\x08" + bytes([2 | 4 | 8 | 16]) + struct.pack("<IBB", 0, 0, 255) + struct.pack("<H", len(extra)) + extra + b"name.fq\0" + b"a comment\0"
+    hdr += struct.pack("<H", zlib.crc32(hdr) & 0xFFFF)
+    tail = struct.pack("<II", zlib.crc32(fq), len(fq) & 0xFFFFFFFF)
+    open(p, "wb").write(hdr + body + tail)
+    assert _gunzip(p).stdout == fq
+    # trailing garbage after a complete member is ignored (gzread does the same); zero padding too
+    open(p, "wb").write(hdr + body + tail + b"\0" * 700)
+    assert _gunzip(p).stdout == fq
+    open(p, "wb").write(_gz(fq) + b"garbage that is not gzip")
+    assert _gunzip(p).stdout == fq
+    # input that is not gzip passes through unchanged
+    for plain in (b"", b"A", b"\x1f", b">s\nACGT\n", fq, b"\x1f\x8c not gzip either"):
+        open(p, "wb").write(plain)
+        assert _gunzip(p).stdout == plain
+    # wrong CRC, wrong length, reserved flag bits, unknown method
+    for bad in (hdr + body + struct.pack("<II", zlib.crc32(fq) ^ 1, len(fq)), hdr + body + struct.pack("<II", zlib.crc32(fq), len(fq) + 1),
+                b"\x1f\x8b\x08\x20" + hdr[4:] + body + tail, b"\x1f\x8b\x07" + hdr[3:] + body + tail, hdr + body + tail[:5], hdr[:7], hdr + body[:-3]):
+        open(p, "wb").write(bad)
+        r = _gunzip(p, ok=False)
+        assert r.returncode == 1 and b"kmcp-gpu gunzip" in r.stderr, bad[:12]
+
+
+def test_hand_made_deflate_streams(tmp_path):
+    """block types and code shapes zlib never emits: an empty stored block between others, a distance code with one symbol,
+    the longest code lengths, a match that reaches back before the start of the member (must be refused)"""
+    class W:
+        def __init__(self): self.acc, self.n, self.out = 0, 0, bytearray()
+        def bits(self, v, n):
+            self.acc |= v << self.n; self.n += n
+            while self.n >= 8: self.out.append(self.acc & 255); self.acc >>= 8; self.n -= 8
+        def code(self, v, n): self.bits(int(bin(v)[2:].zfill(n)[::-1], 2), n)       # Huffman codes go MSB first
+        def align(self):
+            if self.n: self.out.append(self.acc & 255); self.acc = 0; self.n = 0
+    def member(raw, plain):
+        return b"\x1f\x8b\x08\0\0\0\0\0\0\xff" + bytes(raw) + struct.pack("<II", zlib.crc32(plain), len(plain))
+    p = str(tmp_path / "h.gz")
+    # fixed-Huffman block "abc" + match(len 3, dist 3), empty stored block, fixed block with a 258-long run at distance 1
+    w = W()
+    w.bits(0, 1); w.bits(1, 2)
+    for ch in b"abc": w.code(0x30 + ch, 8)
+    w.code(1, 7); w.code(2, 5)                     # length 3 (symbol 257), distance 3 (symbol 2)
+    w.code(0, 7)                                   # end of block
+    w.bits(0, 1); w.bits(0, 2); w.align(); w.out += struct.pack("<HH", 0, 0xFFFF)
+    w.bits(1, 1); w.bits(1, 2)
+    w.code(0x30 + ord("z"), 8)
+    w.code(0xC5, 8); w.code(0, 5)                  # length 258 (symbol 285), distance 1
+    w.code(0, 7); w.align()
+    plain = b"abcabc" + b"z" * 259
+    open(p, "wb").write(member(w.out, plain))
+    assert zlib.decompress(bytes(w.out), -15) == plain
+    assert _gunzip(p).stdout == plain
+    # a match before the start of the member
+    w = W()
+    w.bits(1, 1); w.bits(1, 2); w.code(0x30 + ord("a"), 8); w.code(1, 7); w.code(2, 5); w.code(0, 7); w.align()
+    open(p, "wb").write(_gz(b"0123456789") + member(w.out, b"aaaa"))            # the previous member's bytes are not history
+    r = _gunzip(p, ok=False)
+    assert r.returncode == 1 and b"too far back" in r.stderr
+    # reserved block type
+    w = W(); w.bits(1, 1); w.bits(3, 2); w.align()
+    open(p, "wb").write(member(w.out, b""))
+    assert _gunzip(p, ok=False).returncode == 1
+
+
+def test_big_stream_matches_zlib_and_reader_agrees(corpus, tmp_path):
+    """tens of MB through the 1 MB window (many slides), then the same file through the FASTQ reader"""
+    rnd = random.Random(5)
+    recs = []
+    for i in range(120_000):
+        s = bytes(rnd.choice(b"ACGT") for _ in range(30)) * 5
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"F" * 150))
+    data = b"".join(recs)
+    p = str(tmp_path / "big.fq.gz")
+    open(p, "wb").write(_gz(data[:len(data) // 2], 6) + _gz(data[len(data) // 2:], 1))
+    r = _gunzip(p)
+    assert zlib.crc32(r.stdout) == zlib.crc32(data) and len(r.stdout) == len(data)
+    q = subprocess.run([EXE, "parse", "--ahead", p], capture_output=True, timeout=300)
+    assert q.returncode == 0
+    lines = q.stdout.split(b"\n")
+    assert len(lines) == 120_001 and lines[0].startswith(b"r0\t150\t") and lines[119_999].startswith(b"r119999\t150\t")
+    # a damaged file stops the reader with an error instead of a short result
+    blob = bytearray(open(p, "rb").read())
+    blob[len(blob) // 3] ^= 0x10
+    open(p, "wb").write(bytes(blob))
+    q = subprocess.run([EXE, "parse", p], capture_output=True, timeout=300)
+    assert q.returncode != 0 and b"read error" in q.stderr
+
+
+def test_damaged_streams_under_sanitizers(corpus, tmp_path):
+    """truncations, bit flips, overwritten and deleted stretches: refused or decoded to the same bytes, and clean under ASan/UBSan"""
+    exe = str(tmp_path / "fuzz")
+    c = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        "-I", os.path.join(ROOT, "kmcp_b200", "csrc"), os.path.join(ROOT, "tests", "fastgz_fuzz.cpp"), "-o", exe],
+                       capture_output=True, timeout=300)
+    if c.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + c.stderr.decode()[-200:])
+    for name, level, strategy in (("fastq", 6, zlib.Z_DEFAULT_STRATEGY), ("text", 9, zlib.Z_DEFAULT_STRATEGY), ("skewed", 1, zlib.Z_FIXED),
+                                  ("random", 6, zlib.Z_DEFAULT_STRATEGY), ("far", 6, zlib.Z_DEFAULT_STRATEGY), ("bytes", 6, zlib.Z_HUFFMAN_ONLY)):
+        p = str(tmp_path / "f.gz")
+        d = corpus[name][:120_000]
+        open(p, "wb").write(_gz(d[:50_000], level, strategy) + _gz(d[50_000:], level, strategy))
+        r = subprocess.run([exe, p, "150", "50000"], capture_output=True, timeout=600)
+        assert r.returncode == 0, (name, r.stdout.decode(), r.stderr.decode()[-2000:])
+        # the driver fails when a variant is accepted with bytes gzread would not have produced for it
+        assert b"variants 150" in r.stdout
