@@ -30,6 +30,9 @@
 
 #include "../../include/kmcp_gpu.h"
 #include "fastgz.h"
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace {
 
@@ -196,6 +199,33 @@ struct InflateAhead {
     }
 };
 
+// offsets (base + i) of every '\n' in p[0, n): 64 bytes per step with AVX2 where the CPU has it
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void scan_newlines_avx2(const char *p, size_t n, uint32_t base, std::vector<uint32_t> &out) {
+    const __m256i nl = _mm256_set1_epi8('\n');
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const uint32_t m0 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)(p + i)), nl));
+        const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)(p + i + 32)), nl));
+        uint64_t m = (uint64_t)m0 | ((uint64_t)m1 << 32);
+        while (m) { out.push_back(base + (uint32_t)i + (uint32_t)__builtin_ctzll(m)); m &= m - 1; }
+    }
+    for (; i < n; i++) if (p[i] == '\n') out.push_back(base + (uint32_t)i);
+}
+#endif
+void scan_newlines(const char *p, size_t n, uint32_t base, std::vector<uint32_t> &out) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { scan_newlines_avx2(p, n, base, out); return; }
+#endif
+    for (const char *q = p, *e = p + n; q < e;) {
+        const char *h = (const char *)memchr(q, '\n', (size_t)(e - q));
+        if (!h) break;
+        out.push_back(base + (uint32_t)(h - p));
+        q = h + 1;
+    }
+}
+
 struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default reader: ID = header up to first blank)
     int fd = -1;
     fastgz::Inflater *f = nullptr;       // gzip members are inflated, anything else passes through (as gzread does)
@@ -204,6 +234,10 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     size_t pos = 0, end = 0;
     bool eof = false;
     InflateAhead *ahead = nullptr;
+    // line ends of buf[0, end) (offsets of '\n'), kept for the four-line FASTQ fast path: found 64 bytes at a time when the
+    // buffer is filled instead of one memchr call per (short) line
+    std::vector<uint32_t> nl;
+    size_t nl_i = 0;
     bool open(const std::string &p, bool inflate_ahead = false) {
         path = p;
         fd = p == "-" ? 0 : ::open(p.c_str(), O_RDONLY);
@@ -215,6 +249,7 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         }
         buf.resize(16u << 20);
         pos = end = 0; eof = false;
+        nl.clear(); nl_i = 0;
         if (f && inflate_ahead) { ahead = new InflateAhead(); ahead->start(f); }
         return f != nullptr;
     }
@@ -227,13 +262,50 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     }
     bool fill() {            // keeps [pos, end), reads more behind it; false at end of file
         if (eof) return false;
-        if (pos) { memmove(buf.data(), buf.data() + pos, end - pos); end -= pos; pos = 0; }
+        if (pos) {
+            memmove(buf.data(), buf.data() + pos, end - pos);
+            size_t w = 0;                                  // line ends behind pos move with the bytes
+            for (size_t i = nl_i; i < nl.size(); i++) if (nl[i] >= pos) nl[w++] = nl[i] - (uint32_t)pos;
+            nl.resize(w); nl_i = 0;
+            end -= pos; pos = 0;
+        }
         if (end == buf.size()) buf.resize(buf.size() * 2);
         const size_t room = std::min<size_t>(buf.size() - end, 1u << 30);
         const int r = ahead ? ahead->read(buf.data() + end, room) : (int)f->read(buf.data() + end, room);
         if (r < 0) die("read error in %s: %s", path.c_str(), f->error());
         if (r == 0) { eof = true; return false; }
+        if (end + (size_t)r < ((size_t)1 << 32)) scan_newlines(buf.data() + end, (size_t)r, (uint32_t)end, nl);
+        else { nl.clear(); nl_i = 0; fast_ok = false; }          // a single line of gigabytes: offsets no longer fit
         end += (size_t)r;
+        return true;
+    }
+    bool fast_ok = true;
+    // A FASTQ record written as exactly four lines (header, sequence, '+', quality of the same length) taken from the line-end
+    // table: the ID is returned as a range of the buffer (valid until the next call), the sequence is appended to dst.
+    // false = not such a record here (FASTA, wrapped FASTQ, blank lines, the unterminated tail of a file): the general
+    // reader below takes it from the same position.
+    template <class V>
+    bool next_four_line(const char *&idp, size_t &idn, V &dst) {
+        if (!fast_ok) return false;
+        for (;;) {
+            while (nl_i < nl.size() && nl[nl_i] < pos) nl_i++;
+            if (nl.size() - nl_i >= 4) break;
+            if (!fill()) return false;
+        }
+        const char *b = buf.data();
+        const size_t h0 = pos, s0 = (size_t)nl[nl_i] + 1, p0 = (size_t)nl[nl_i + 1] + 1, q0 = (size_t)nl[nl_i + 2] + 1;
+        size_t h1 = nl[nl_i], s1 = nl[nl_i + 1], q1 = nl[nl_i + 3];
+        if (b[h0] != '@' || b[p0] != '+') return false;          // an empty line holds its own '\n' here, so both tests also refuse blank lines
+        while (h1 > h0 && b[h1 - 1] == '\r') h1--;
+        while (s1 > s0 && b[s1 - 1] == '\r') s1--;
+        while (q1 > q0 && b[q1 - 1] == '\r') q1--;
+        if (q1 - q0 != s1 - s0) return false;
+        size_t e = h0 + 1;
+        while (e < h1 && b[e] != ' ' && b[e] != '\t') e++;
+        idp = b + h0 + 1; idn = e - h0 - 1;
+        dst.insert(dst.end(), b + s0, b + s1);
+        pos = (size_t)nl[nl_i + 3] + 1;
+        nl_i += 4;
         return true;
     }
     // next line without its end-of-line bytes; the pointer is valid until the next call
@@ -263,6 +335,7 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     template <class V>
     bool next(std::string &id, V &dst) {
         const char *l; size_t n;
+        if (next_four_line(l, n, dst)) { id.assign(l, n); return true; }
         do { if (!line(l, n)) return false; } while (n == 0);
         if (l[0] != '>' && l[0] != '@') die("invalid FASTA/Q record in %s", path.c_str());
         const bool fq = l[0] == '@';
@@ -431,10 +504,11 @@ int index_main(int argc, char **argv) {
 int parse_main(int argc, char **argv) {
     std::vector<std::string> files;
     std::string r1, r2;
-    bool ahead = false;
+    bool ahead = false, count_only = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--ahead") ahead = true;
+        else if (a == "--count") count_only = true;          // the reader's rate alone: records and bases to stderr, no per-record output
         else if (a == "-1" && i + 1 < argc) r1 = argv[++i];
         else if (a == "-2" && i + 1 < argc) r2 = argv[++i];
         else files.push_back(a);
@@ -448,6 +522,25 @@ int parse_main(int argc, char **argv) {
         seq.clear();
         if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
     };
+    if (count_only) {
+        const auto t0 = std::chrono::steady_clock::now();
+        uint64_t n = 0, bases = 0;
+        std::vector<char> ids;                               // what the search pipeline keeps of a record: ID and sequence, back to back
+        std::vector<uint64_t> id_off, off;
+        for (auto &f : files) {
+            Reader r;
+            if (!r.open(f, ahead)) die("%s: no such file", f.c_str());
+            while (r.next(id, seq)) {
+                n++; ids.insert(ids.end(), id.begin(), id.end()); id_off.push_back(ids.size()); off.push_back(seq.size());
+                if (off.size() >= (1u << 18)) { bases += seq.size(); seq.clear(); ids.clear(); id_off.clear(); off.clear(); }
+            }
+            r.close();
+        }
+        bases += seq.size();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "%llu records, %llu bases, %.3f s, %.2f M records/s\n", (unsigned long long)n, (unsigned long long)bases, dt, n / dt / 1e6);
+        return 0;
+    }
     if (!r1.empty() && !r2.empty()) {
         Reader a, b;
         if (!a.open(r1, ahead) || !b.open(r2, ahead)) die("no such file");
@@ -730,7 +823,15 @@ int main(int argc, char **argv) {
 
     // ---- three-stage pipeline: reader thread (inflate + parse + pack) → this thread (GPU engine, every database) →
     //      writer thread (merge across databases, TSV formatting on several threads, parallel gzip), all in input order ----
-    struct Batch { std::vector<std::string> ids; std::vector<uint8_t> seq; std::vector<uint64_t> off{0}; uint64_t base = 0; };
+    struct Batch {
+        std::vector<char> id_buf;             // the IDs back to back: no allocation per read
+        std::vector<uint64_t> id_off{0};
+        std::vector<uint8_t> seq;
+        std::vector<uint64_t> off{0};
+        uint64_t base = 0;
+        size_t n_ids() const { return id_off.size() - 1; }
+        void add_id(const std::string &id) { id_buf.insert(id_buf.end(), id.begin(), id.end()); id_off.push_back(id_buf.size()); }
+    };
     struct Job { Batch *batch = nullptr; std::vector<kmcpg_results> res; };
     std::mutex mu;
     std::condition_variable cv;
@@ -744,10 +845,10 @@ int main(int argc, char **argv) {
         Batch *cur = new Batch();
         uint64_t next_base = 0;
         auto emit = [&]() {
-            if (cur->ids.empty()) return;
+            if (cur->n_ids() == 0) return;
             if (cur->seq.empty()) cur->seq.push_back(0);
             cur->base = next_base;
-            next_base += cur->ids.size();
+            next_base += cur->n_ids();
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return in_q.size() < 2; });
             in_q.push_back(cur);
@@ -766,8 +867,8 @@ int main(int argc, char **argv) {
                 if (!r1.next(id, cur->seq)) break;
                 const size_t mid = cur->seq.size();
                 if (!r2.next(id2, cur->seq)) { cur->seq.resize(mark); break; }
-                cur->ids.push_back(id); cur->off.push_back(mid); end_seq();
-                if (cur->ids.size() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
+                cur->add_id(id); cur->off.push_back(mid); end_seq();
+                if (cur->n_ids() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
             }
             r1.close(); r2.close();
         } else {
@@ -784,14 +885,14 @@ int main(int argc, char **argv) {
                         else cur->seq.insert(cur->seq.end(), (size_t)(kmax - 1), (uint8_t)'N');
                     }
                     if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); cur->seq.resize(mark); r.close(); continue; }
-                    cur->ids.push_back(qid); end_seq();
+                    cur->add_id(qid); end_seq();
                     if (cur->seq.size() >= o.batch_bytes) emit();
                 } else {
                     bool any = false;
                     while (r.next(id, cur->seq)) {
                         any = true;
-                        cur->ids.push_back(id); end_seq();
-                        if (cur->ids.size() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
+                        cur->add_id(id); end_seq();
+                        if (cur->n_ids() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
                     }
                     if (!any) logf("WARN", "no valid sequences in file: %s", file.c_str());
                 }
@@ -818,7 +919,7 @@ int main(int argc, char **argv) {
                 cv.notify_all();
             }
             const Batch &bt = *job->batch;
-            const uint32_t nq = (uint32_t)bt.ids.size();
+            const uint32_t nq = (uint32_t)bt.n_ids();
             std::vector<std::string> text(FT);
             std::vector<uint64_t> nmatched(FT, 0);
             auto fmt = [&](int t) {
@@ -828,7 +929,8 @@ int main(int argc, char **argv) {
                 out.reserve((size_t)(hi - lo) * 96);
                 std::vector<std::pair<kmcpg_match, int>> merged;      // (match, database) of one query when several databases are searched
                 for (uint32_t q = lo; q < hi; q++) {
-                    const std::string &id = bt.ids[q];
+                    const char *const idp = bt.id_buf.data() + bt.id_off[q];
+                    const size_t idn = (size_t)(bt.id_off[q + 1] - bt.id_off[q]);
                     const kmcpg_results &r0 = job->res[0];
                     uint64_t hits = 0;
                     for (auto &r : job->res) hits += r.match_off[q + 1] - r.match_off[q];
@@ -836,7 +938,7 @@ int main(int argc, char **argv) {
                         if (!o.keep_unmatched) continue;
                         int n = snprintf(line, sizeof(line), "\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%llu\n", r0.query_len[q], r0.n_kmers[q], r0.k_used[q],     // S:460-511
                                          (unsigned long long)(bt.base + q));
-                        out.append(id); out.append(line, (size_t)n);
+                        out.append(idp, idn); out.append(line, (size_t)n);
                         continue;
                     }
                     nmatched[t]++;
@@ -844,7 +946,7 @@ int main(int argc, char **argv) {
                         const kmcpg_target_t &tg = db.targets[m.target];
                         const std::string *mp = db.mapped[m.target];
                         int n1 = snprintf(line, sizeof(line), "\t%d\t%d\t%.4e\t%llu\t", r.query_len[q], r.n_kmers[q], m.fpr, (unsigned long long)hits);
-                        out.append(id); out.append(line, (size_t)n1);
+                        out.append(idp, idn); out.append(line, (size_t)n1);
                         if (mp) out.append(*mp); else out.append(tg.name);
                         int n2 = snprintf(line, sizeof(line), "\t%u\t%u\t%llu\t%d\t%u\t%.4f\t%.4f\t%.4f\t%llu\n", tg.index & 0xFFFFu, tg.index >> 16,          // S:532-539
                                           (unsigned long long)tg.genome_size, r.k_used[q], m.count, m.qcov, m.tcov, m.jacc, (unsigned long long)(bt.base + q));

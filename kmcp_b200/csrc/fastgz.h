@@ -166,6 +166,22 @@ class Inflater {
         uint8_t *d = (uint8_t *)dst;
         size_t got = 0;
         while (got < cap) {
+            if (state_ == ST_PLAIN && drain_ == out_next_ && !failed_) {
+                // not gzip: the bytes go straight to the caller, past the window
+                if (in_next_ < in_end_) {
+                    const size_t n = std::min(cap - got, (size_t)(in_end_ - in_next_));
+                    memcpy(d + got, in_next_, n);
+                    in_next_ += n; got += n;
+                    continue;
+                }
+                if (in_eof_) { if (io_error_) { fail("read error"); failed_ = true; continue; } state_ = ST_END; break; }
+                const ssize_t r = rd_(d + got, cap - got);
+                if (r < 0) { io_error_ = true; in_eof_ = true; continue; }
+                if (r == 0) { in_eof_ = true; continue; }
+                got += (size_t)r;
+                if (got) break;                  // like read(2): hand over what there is
+                continue;
+            }
             if (drain_ == out_next_) {
                 if (failed_) return got ? (ssize_t)got : -1;
                 if (state_ == ST_END) break;
