@@ -199,8 +199,7 @@ class Inflater {
     bool is_gzip() const { return saw_gzip_; }
     uint64_t members() const { return members_; }
 
-  private:
-    static constexpr size_t IN_CAP = 1u << 20, PAD = 64, HIST = 32768, OUT_CAP = 1u << 20, SLACK = 512;
+    // ---- table construction (also used by the chunk-parallel decoder in pargz.h) ------------------------------------------
     static constexpr int LBITS = 11, DBITS = 8;
     static constexpr size_t LT_SIZE = (1u << LBITS) + (1u << 15), DT_SIZE = (1u << DBITS) + (1u << 15);
     // Table entry.  bits 0-5: bits to take from the stream for this symbol, code AND extra bits together, so the bit buffer
@@ -211,8 +210,6 @@ class Inflater {
     static constexpr uint32_t E_LIT = 0x8000, E_EXC = 0x4000, E_LIT2 = 0x2000, E_SUB = 0x1000;
     static constexpr uint32_t E_EOB = E_EXC | (0u << 16), E_BAD = E_EXC | (1u << 16);
     static uint32_t code_bits(uint32_t codelen, uint32_t extra) { return (codelen + extra) | (codelen << 8); }
-
-    enum State { ST_MEMBER, ST_BLOCK, ST_HUFF, ST_STORED, ST_TRAILER, ST_PLAIN, ST_END };
 
     static uint32_t rev_bits(uint32_t code, int len) {
         uint32_t r = 0;
@@ -305,6 +302,10 @@ class Inflater {
             build_table(dt.data(), DT_SIZE, DBITS, d, 32, false);
         }
     };
+
+  private:
+    static constexpr size_t IN_CAP = 1u << 20, PAD = 64, HIST = 32768, OUT_CAP = 1u << 20, SLACK = 512;
+    enum State { ST_MEMBER, ST_BLOCK, ST_HUFF, ST_STORED, ST_TRAILER, ST_PLAIN, ST_END };
 
     bool fail(const char *msg) { err_ = msg; return false; }
 
@@ -540,7 +541,7 @@ class Inflater {
     }
 
     // one compressed block's symbols.  1: end of block, 0: the output window is full (call again), -1: error
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(__SANITIZE_THREAD__)      // (ifunc resolvers run before TSan is up)
     __attribute__((target_clones("bmi2", "default")))      // shrx/bzhi where the CPU has them (one variable shift per symbol)
 #endif
     int huff() {

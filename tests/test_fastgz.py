@@ -1,4 +1,4 @@
-"""Host-only tests of kmcp_b200/csrc/fastgz.h, the gzip decoder of the CLI's read ingest (the
+"""Host-only tests of kmcp_b200/csrc/fastgz.h and pargz.h, the gzip decoders of the CLI's read ingest (the
 reference reads its inputs through xopen + pgzip, search.go S:793-1000).  `kmcp-gpu gunzip` runs the decoder alone.
 zlib (through Python) is the checker: every stream zlib can produce must decode to the same bytes, and every damaged
 stream must be refused — never accepted with different bytes, never crash (a sanitizer build of the decoder runs the
@@ -188,7 +188,7 @@ def test_damaged_streams_under_sanitizers(corpus, tmp_path):
     """truncations, bit flips, overwritten and deleted stretches: refused or decoded to the same bytes, and clean under ASan/UBSan"""
     exe = str(tmp_path / "fuzz")
     c = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
-                        "-I", os.path.join(ROOT, "kmcp_b200", "csrc"), os.path.join(ROOT, "tests", "fastgz_fuzz.cpp"), "-o", exe],
+                        "-pthread", "-I", os.path.join(ROOT, "kmcp_b200", "csrc"), os.path.join(ROOT, "tests", "fastgz_fuzz.cpp"), "-o", exe],
                        capture_output=True, timeout=300)
     if c.returncode != 0:
         pytest.skip("no sanitizer runtime for g++ here: " + c.stderr.decode()[-200:])
@@ -199,5 +199,134 @@ def test_damaged_streams_under_sanitizers(corpus, tmp_path):
         open(p, "wb").write(_gz(d[:50_000], level, strategy) + _gz(d[50_000:], level, strategy))
         r = subprocess.run([exe, p, "150", "50000"], capture_output=True, timeout=600)
         assert r.returncode == 0, (name, r.stdout.decode(), r.stderr.decode()[-2000:])
-        # the driver fails when a variant is accepted with bytes gzread would not have produced for it
+        # the driver fails when a variant is accepted with bytes gzread would not have produced for it, or when the
+        # chunk-parallel decoder disagrees with the sequential one
         assert b"variants 150" in r.stdout
+    # the worker / consumer hand-offs of the chunk-parallel decoder under ThreadSanitizer
+    tsan = str(tmp_path / "fuzz_tsan")
+    c = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I", os.path.join(ROOT, "kmcp_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "fastgz_fuzz.cpp"), "-o", tsan], capture_output=True, timeout=300)
+    if c.returncode == 0:
+        d = corpus["fastq"]
+        open(p, "wb").write(_gz(d[:300_000], 6) + _gz(d[300_000:], 6))
+        r = subprocess.run([tsan, p, "25", "300000"], capture_output=True, timeout=600)
+        if r.returncode != 0 and b"ThreadSanitizer" not in r.stderr and b"variant" not in r.stdout and b"failed" not in r.stdout:
+            pytest.skip("ThreadSanitizer cannot run here")                      # e.g. an unsupported address-space layout
+        assert r.returncode == 0 and b"variants 25" in r.stdout, (r.stdout.decode(), r.stderr.decode()[-3000:])
+
+
+# ---- pargz.h: one gzip stream decoded by several threads ---------------------------------------------------------------
+def _par(path, threads=3, par_chunk=65536, ok=True, chunk=None):
+    args = ["--threads", str(threads), "--par-chunk", str(par_chunk), "--stats"] + (["--chunk", str(chunk)] if chunk else [])
+    return _gunzip(path, *args, ok=ok)
+
+
+def _stats(p):
+    import re
+    m = re.search(rb"chunks used (\d+), stretches decoded again in order (\d+), symbols resolved (\d+)", p.stderr)
+    return tuple(int(x) for x in m.groups())
+
+
+def test_parallel_decoder_gives_the_same_bytes(corpus, tmp_path):
+    """every stream of the corpus cut into 64 KB chunks: block starts found by the workers, windows passed on, markers resolved"""
+    p = str(tmp_path / "a.gz")
+    used_total = 0
+    for name, data in corpus.items():
+        for level, strategy in ((6, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_FILTERED), (6, zlib.Z_FIXED), (0, zlib.Z_DEFAULT_STRATEGY),
+                                (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
+            z = _gz(data, level, strategy)
+            if len(z) < 18:
+                continue
+            open(p, "wb").write(z)
+            r = _par(p, threads=1 + (len(z) % 4))
+            assert r.stdout == data, (name, level, strategy)
+            used, redone, _ = _stats(r)
+            used_total += used
+            if strategy == zlib.Z_DEFAULT_STRATEGY and level == 6 and name in ("fastq", "text", "skewed"):
+                assert used >= max(1, len(z) // 65536 - 1) and redone <= 2, (name, used, redone)        # dynamic blocks: every chunk is used
+    assert used_total > 100
+    # a FASTQ stream big enough for many chunks at the default chunk size too, odd output piece sizes
+    big = corpus["fastq"] * 40
+    open(p, "wb").write(_gz(big, 6))
+    for th, pc, ck in ((4, 65536, 1000), (2, 300_000, None), (8, 2 << 20, None)):
+        r = _par(p, threads=th, par_chunk=pc, chunk=ck)
+        assert zlib.crc32(r.stdout) == zlib.crc32(big) and len(r.stdout) == len(big), (th, pc)
+
+
+def test_parallel_decoder_members_garbage_and_block_kinds(corpus, tmp_path):
+    p = str(tmp_path / "m.gz")
+    fq, rnd_bytes, text = corpus["fastq"], corpus["random"], corpus["text"]
+    # many members of every kind back to back (bgzip / pgzip style and `cat`), empty ones, stored and fixed blocks in between
+    parts = [fq[:100_000], b"", rnd_bytes[:150_000], text[:300_000], b"x", fq[100_000:], text[300_000:]]
+    blob = b"".join(_gz(d, lv, st) for d, lv, st in zip(parts, (6, 6, 6, 9, 1, 6, 1), (0, 0, 0, 0, zlib.Z_FIXED, zlib.Z_FIXED, 0)))
+    open(p, "wb").write(blob)
+    whole = b"".join(parts)
+    for th in (1, 3):
+        assert _par(p, threads=th).stdout == whole
+    open(p, "wb").write(blob + b"\0" * 100_000)                  # zero padding / garbage behind the last member is ignored
+    assert _par(p).stdout == whole
+    open(p, "wb").write(blob + b"not gzip " * 30_000)
+    assert _par(p).stdout == whole
+    # 64 KB members as bgzip writes them: every chunk holds several member starts
+    bg = b"".join(_gz(text[i:i + 60_000]) for i in range(0, len(text), 60_000))
+    open(p, "wb").write(bg)
+    assert _par(p, par_chunk=65536).stdout == text
+    # one flush per 10 KB: empty stored blocks and byte-aligned block starts all over the stream
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    z = b"".join(c.compress(fq[i:i + 10_000]) + c.flush(zlib.Z_FULL_FLUSH if i % 30_000 == 0 else zlib.Z_SYNC_FLUSH) for i in range(0, len(fq), 10_000)) + c.flush()
+    open(p, "wb").write(z)
+    assert _par(p).stdout == fq
+    # not gzip / too small / a pipe: refused up front (the reader falls back to the sequential decoder)
+    open(p, "wb").write(b"@r\nACGT\n+\nIIII\n" * 10)
+    assert _par(p, ok=False).returncode == 2
+
+
+def test_parallel_decoder_refuses_damaged_streams(corpus, tmp_path):
+    """a flipped bit anywhere: an error (CRC, length or a broken code), never other bytes, never a hang"""
+    p = str(tmp_path / "d.gz")
+    fq = corpus["fastq"] * 3
+    good = _gz(fq[:700_000], 6) + _gz(fq[700_000:], 6)
+    rnd = random.Random(9)
+    for trial in range(40):
+        blob = bytearray(good)
+        kind = trial % 4
+        if kind == 0:
+            blob[rnd.randrange(12, len(blob) - 8)] ^= 1 << rnd.randrange(8)
+        elif kind == 1:
+            blob = blob[:rnd.randrange(20, len(blob) - 1)]
+        elif kind == 2:
+            a = rnd.randrange(12, len(blob) - 100)
+            blob[a:a + rnd.randrange(1, 80)] = os.urandom(5)
+        else:
+            blob[-rnd.randrange(1, 9)] ^= 0x40                                           # CRC-32 / ISIZE of the last member
+        open(p, "wb").write(bytes(blob))
+        r = _par(p, threads=1 + trial % 4, par_chunk=65536, ok=False)
+        s = _gunzip(p, ok=False)
+        assert r.returncode in (0, 1), r.stderr
+        assert (r.returncode == 0) == (s.returncode == 0), (trial, kind, r.stderr, s.stderr)      # the sequential decoder agrees
+        if r.returncode == 0:
+            assert r.stdout == s.stdout
+        else:
+            assert s.stdout.startswith(r.stdout) or r.stdout.startswith(s.stdout)            # what came out before the error is real data
+
+
+def test_reader_uses_the_parallel_decoder(corpus, tmp_path):
+    """kmcp-gpu parse --inflate-threads N: same records as the sequential reader, single and paired files"""
+    rnd = random.Random(2)
+    recs = [(b"q%d" % i, bytes(rnd.choice(b"ACGT") for _ in range(rnd.choice([50, 150, 151])))) for i in range(40_000)]
+    a, b = str(tmp_path / "a.fq.gz"), str(tmp_path / "b.fq.gz")
+    with gzip.open(a, "wb", compresslevel=6) as f:
+        for i, s in recs:
+            f.write(b"@" + i + b" d\n" + s + b"\n+\n" + b"F" * len(s) + b"\n")
+    with gzip.open(b, "wb", compresslevel=1) as f:
+        for i, s in recs:
+            f.write(b"@" + i + b"/2\n" + s[::-1] + b"\n+\n" + b"#" * len(s) + b"\n")
+    def parse(*args):
+        q = subprocess.run([EXE, "parse", *args], capture_output=True, timeout=300)
+        assert q.returncode == 0, q.stderr.decode()
+        return q.stdout
+    env_small = ["--inflate-threads", "3", "--inflate-chunk", "65536"]
+    assert parse(*env_small, a) == parse("--inflate-threads", "1", a)
+    assert parse(*env_small, "--ahead", "-1", a, "-2", b) == parse("--inflate-threads", "1", "-1", a, "-2", b)
+    exp = b"".join(b"%s\t%d\t%08x\n" % (i, len(s), zlib.crc32(s)) for i, s in recs)
+    assert parse(*env_small, "--ahead", a) == exp
