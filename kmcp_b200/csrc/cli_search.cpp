@@ -129,6 +129,7 @@ void usage() {
         "      --gpu-mode string            with several devices: \"shard\" splits the index (every device searches every read),\n"
         "                                   \"replicate\" loads the whole index on every device and splits the reads,\n"
         "                                   \"auto\" (default) replicates when the index fits into every device's free memory\n"
+        "      --compression-level int      level of the .gz output, 1-9 (default 4)\n"
         "      --inflate-threads int        threads that decompress ONE .gz input side by side (chunk-parallel inflate; default: by itself\n"
         "                                   on machines with >= 32 hardware threads for files >= 32 MB; 1 = sequential decoder)\n"
         "      --ref-counts file            also write the per-reference, per-chunk read counters of `kmcp profile` stage 1/4\n"
@@ -386,10 +387,10 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
 };
 
 // one complete gzip member for a block of text (concatenated members are a valid .gz stream, as pgzip writes them)
-std::string gz_member(const char *data, size_t n) {
+std::string gz_member(const char *data, size_t n, int level) {
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
-    if (deflateInit2(&zs, 6, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib init failed");
+    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib init failed");
     std::string out(deflateBound(&zs, (uLong)n) + 64, '\0');
     zs.next_in = (Bytef *)data; zs.avail_in = (uInt)n;
     zs.next_out = (Bytef *)&out[0]; zs.avail_out = (uInt)out.size();
@@ -399,30 +400,68 @@ std::string gz_member(const char *data, size_t n) {
     return out;
 }
 
+int g_compression_level = 4;      // --compression-level (the reference's pgzip default is a fast level as well)
+
+// text → file.  ".gz" output is compressed in 1 MB blocks by several threads (independent gzip members, written in order) and
+// write() only queues the text: the next batch is formatted while this one is still being compressed and written.
 struct Writer {
     FILE *fp = nullptr;
     bool gz = false;
-    int threads = 32;
+    size_t max_inflight = 64;                       // blocks being compressed or waiting to be written
+    std::thread flusher;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::future<std::string>> q;
+    bool closing = false;
     void open(const std::string &p) {
         if (p == "-") fp = stdout;
         else { fp = fopen(p.c_str(), "wb"); if (!fp) die("fail to write %s", p.c_str()); }
         gz = p.size() > 3 && p.compare(p.size() - 3, 3, ".gz") == 0;
-    }
-    // text → file; .gz output is compressed in 1 MB blocks by several threads (independent gzip members, in order)
-    void write(const char *s, size_t n) {
-        if (!n) return;
-        if (!gz) { fwrite(s, 1, n, fp); return; }
-        const size_t BLK = 1u << 20;
-        std::deque<std::future<std::string>> inflight;
-        for (size_t o = 0; o < n; o += BLK) {
-            const size_t len = std::min(BLK, n - o);
-            inflight.push_back(std::async(std::launch::async, gz_member, s + o, len));
-            if ((int)inflight.size() >= threads) { std::string z = inflight.front().get(); inflight.pop_front(); fwrite(z.data(), 1, z.size(), fp); }
+        if (gz) {
+            max_inflight = std::max<size_t>(8, std::min<size_t>(64, std::thread::hardware_concurrency()));
+            flusher = std::thread([this] {
+                for (;;) {
+                    std::future<std::string> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return !q.empty() || closing; });
+                        if (q.empty()) return;
+                        f = std::move(q.front());
+                    }
+                    const std::string z = f.get();                 // members leave in the order they were queued
+                    if (fwrite(z.data(), 1, z.size(), fp) != z.size()) die("write error");
+                    std::lock_guard<std::mutex> lk(mu);
+                    q.pop_front();                                 // only now: the block counts as in flight until it is on disk
+                    cv.notify_all();
+                }
+            });
         }
-        while (!inflight.empty()) { std::string z = inflight.front().get(); inflight.pop_front(); fwrite(z.data(), 1, z.size(), fp); }
     }
-    void write(const std::string &t) { write(t.data(), t.size()); }
-    void close() { if (fp && fp != stdout) fclose(fp); else if (fp) fflush(fp); }
+    void write(std::string &&t) {
+        if (t.empty()) return;
+        if (!gz) { if (fwrite(t.data(), 1, t.size(), fp) != t.size()) die("write error"); return; }
+        const size_t BLK = 1u << 20;
+        auto keep = std::make_shared<const std::string>(std::move(t));
+        const int level = g_compression_level;
+        for (size_t o = 0; o < keep->size(); o += BLK) {
+            const size_t len = std::min(BLK, keep->size() - o);
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return q.size() < max_inflight; });
+            q.push_back(std::async(std::launch::async, [keep, o, len, level] { return gz_member(keep->data() + o, len, level); }));
+            cv.notify_all();
+        }
+    }
+    void write(const char *s, size_t n) { write(std::string(s, n)); }
+    void write(const std::string &t) { write(std::string(t)); }
+    void close() {
+        if (flusher.joinable()) {
+            { std::lock_guard<std::mutex> lk(mu); closing = true; }
+            cv.notify_all();
+            flusher.join();
+        }
+        if (fp && fp != stdout) fclose(fp); else if (fp) fflush(fp);
+        fp = nullptr;
+    }
 };
 
 
@@ -629,8 +668,30 @@ int gunzip_main(int argc, char **argv) {
     return 0;
 }
 
+// kmcp-gpu gzip-write <text file> <out[.gz]> [piece bytes]: the result writer alone (no GPU), fed in pieces the size of a
+// batch's TSV text; prints its rate.  Used by the host-only tests and to size the writer.
+int gzip_write_main(int argc, char **argv) {
+    if (argc < 4) { fputs("usage: kmcp-gpu gzip-write <text file> <out[.gz]> [piece bytes]\n", stderr); return 2; }
+    FILE *f = fopen(argv[2], "rb");
+    if (!f) die("%s: no such file", argv[2]);
+    std::string text;
+    std::vector<char> buf(1u << 24);
+    for (size_t n; (n = fread(buf.data(), 1, buf.size(), f)) > 0;) text.append(buf.data(), n);
+    fclose(f);
+    const size_t piece = argc > 4 ? (size_t)atol(argv[4]) : (size_t)19 << 20;
+    Writer w;
+    w.open(argv[3]);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t o = 0; o < text.size(); o += piece) w.write(text.data() + o, std::min(piece, text.size() - o));
+    w.close();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "%zu bytes in %.3f s: %.1f MB/s\n", text.size(), dt, text.size() / dt / 1e6);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "index")) return index_main(argc, argv);
+    if (argc > 1 && !strcmp(argv[1], "gzip-write")) return gzip_write_main(argc, argv);
     if (argc > 1 && !strcmp(argv[1], "gunzip")) return gunzip_main(argc, argv);
     if (argc > 1 && !strcmp(argv[1], "parse")) return parse_main(argc, argv);
     Opts o;
@@ -674,6 +735,7 @@ int main(int argc, char **argv) {
         else if (a == "--log") o.log_file = sval();
         else if (a == "--gpu") o.devices.assign(1, atoi(sval().c_str()));
         else if (a == "--gpu-mode") o.gpu_mode = sval();
+        else if (a == "--compression-level") { g_compression_level = atoi(sval().c_str()); if (g_compression_level < 1 || g_compression_level > 9) die("--compression-level should be in range [1, 9]"); }
         else if (a == "--inflate-threads") g_inflate_threads = atoi(sval().c_str());
         else if (a == "--inflate-chunk") g_inflate_chunk = (size_t)atol(sval().c_str());
         else if (a == "--gpus") {
@@ -1021,7 +1083,7 @@ int main(int argc, char **argv) {
             for (auto &t : text) sz += t.size();
             all.reserve(sz);
             for (auto &t : text) all += t;
-            w.write(all);
+            w.write(std::move(all));
             for (auto v : nmatched) matched += v;
             total += nq;
             if (refcounts && kmcpg_refcounts_add(refcounts, &job->res[0])) die("--ref-counts: inconsistent chunk numbering in the database");

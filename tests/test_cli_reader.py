@@ -69,3 +69,91 @@ def test_reader_paired_files_stop_at_the_shorter_mate(files, ahead):
         exp += _line(i, s) + _line(i + b"/2", s[::-1])
     exp += _line(*recs[4000])                                    # mate 1 was read before mate 2 ran out (S:806-867)
     assert _parse(ahead + ["-1", files["fq_gz"], "-2", files["fq2_gz"]]) == exp
+
+
+def _py_records(data):
+    """what the reader must return for a FASTA/Q byte string (bio/seqio/fastx semantics as used by search.go: ID up to the
+    first blank, sequence lines joined, FASTQ quality read until it is as long as the sequence)"""
+    lines = [l.rstrip(b"\r\n") for l in data.split(b"\n")]
+    if lines and lines[-1] == b"" and data.endswith(b"\n"):
+        lines.pop()
+    out, i = [], 0
+    while i < len(lines):
+        if lines[i] == b"":
+            i += 1
+            continue
+        h = lines[i]
+        assert h[:1] in (b">", b"@")
+        rid = h[1:].split(b" ")[0].split(b"\t")[0]
+        i += 1
+        if h[:1] == b"@":
+            seq = lines[i] if i < len(lines) else b""
+            i += 1
+            while i < len(lines) and not lines[i].startswith(b"+"):
+                seq += lines[i]
+                i += 1
+            i += 1                                    # the '+' line
+            got = 0
+            while got < len(seq) and i < len(lines):
+                got += len(lines[i])
+                i += 1
+        else:
+            seq = b""
+            while i < len(lines) and not lines[i].startswith(b">"):
+                seq += lines[i]
+                i += 1
+        out.append((rid, seq))
+    return out
+
+
+def test_reader_random_mixtures_of_record_styles(tmp_path):
+    """four-line records (the table-driven fast path), wrapped FASTQ, blank lines, CRLF, '@'/'+' at the start of quality
+    lines, a missing final newline — in random order, so the fast path and the general reader hand over to each other at
+    every kind of boundary; plain, gzip and chunk-parallel gzip input"""
+    rnd = random.Random(17)
+
+    def seq(n):
+        return bytes(rnd.choice(b"ACGTN") for _ in range(n))
+
+    for trial in range(12):
+        eol = b"\r\n" if trial % 4 == 3 else b"\n"
+        parts = []
+        n = rnd.choice([1, 5, 300, 3000])
+        for i in range(n):
+            s = seq(rnd.choice([0, 1, 20, 150, 151, 400]))
+            rid = b"x%d_%d" % (trial, i)
+            style = rnd.choice(["four", "four", "four", "four", "wrapped", "blank", "atqual"])
+            q = bytes(rnd.choice(b"FI#5") for _ in range(len(s)))
+            if style == "four" or (style != "blank" and len(s) == 0):
+                parts.append(b"@" + rid + rnd.choice([b"", b" desc", b"\tdesc 2"]) + eol + s + eol + b"+" + eol + q + eol)
+            elif style == "atqual":
+                q = (b"@" + q[1:]) if rnd.random() < 0.5 else (b"+" + q[1:])
+                parts.append(b"@" + rid + eol + s + eol + b"+" + rid + eol + q + eol)
+            elif style == "blank":
+                parts.append(eol + b"@" + rid + eol + s + eol + b"+" + eol + q + eol + (eol if rnd.random() < 0.5 else b""))
+            else:
+                w = rnd.choice([7, 60])
+                sl = [s[j:j + w] for j in range(0, len(s), w)]
+                ql = [q[j:j + w] for j in range(0, len(q), w)]
+                parts.append(b"@" + rid + eol + eol.join(sl) + eol + b"+" + eol + eol.join(ql) + eol)
+        data = b"".join(parts)
+        if trial % 3 == 1:
+            data = data.rstrip(b"\r\n")
+        exp = "".join(_line(i, s) for i, s in _py_records(data))
+        p = str(tmp_path / ("t%d.fq" % trial))
+        open(p, "wb").write(data)
+        assert _parse([p]) == exp, trial
+        assert _parse(["--ahead", p]) == exp, trial
+        with gzip.open(p + ".gz", "wb") as f:
+            f.write(data)
+        assert _parse([p + ".gz"]) == exp, trial
+        assert _parse(["--ahead", "--inflate-threads", "3", "--inflate-chunk", "65536", p + ".gz"]) == exp, trial
+    # FASTA with wrapped lines between FASTQ files, empty file, file of blank lines only
+    fa = str(tmp_path / "g.fa")
+    recs = [(b"c%d" % i, seq(rnd.choice([0, 59, 60, 61, 5000]))) for i in range(50)]
+    open(fa, "wb").write(b"".join(b">" + i + b" x\n" + b"".join(s[j:j + 60] + b"\n" for j in range(0, len(s), 60)) for i, s in recs))
+    empty, blank = str(tmp_path / "e.fq"), str(tmp_path / "b.fq")
+    open(empty, "wb").close()
+    open(blank, "wb").write(b"\n\n\n")
+    assert _parse([empty, fa, blank, str(tmp_path / "t0.fq")]) == "".join(_line(i, s) for i, s in recs) + \
+        "".join(_line(i, s) for i, s in _py_records(open(str(tmp_path / "t0.fq"), "rb").read()))

@@ -330,3 +330,22 @@ def test_reader_uses_the_parallel_decoder(corpus, tmp_path):
     assert parse(*env_small, "--ahead", "-1", a, "-2", b) == parse("--inflate-threads", "1", "-1", a, "-2", b)
     exp = b"".join(b"%s\t%d\t%08x\n" % (i, len(s), zlib.crc32(s)) for i, s in recs)
     assert parse(*env_small, "--ahead", a) == exp
+
+
+def test_result_writer_gz_members_in_order(corpus, tmp_path):
+    """kmcp-gpu gzip-write: the CLI's .gz result writer alone (1 MB members compressed side by side, written in order,
+    queued asynchronously) — zlib, the sequential decoder and the chunk-parallel decoder all read the text back"""
+    text = corpus["text"] * 3 + corpus["fastq"]
+    src, out = str(tmp_path / "t.tsv"), str(tmp_path / "o.tsv.gz")
+    open(src, "wb").write(text)
+    for piece in (str(19 << 20), "700001", "1"[:1] + "000"):
+        r = subprocess.run([EXE, "gzip-write", src, out, piece], capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()
+        blob = open(out, "rb").read()
+        assert gzip.decompress(blob) == text
+        assert blob.count(b"\x1f\x8b\x08") >= len(text) // (1 << 20)            # many members
+    assert _gunzip(out).stdout == text
+    assert _par(out, threads=3, par_chunk=65536).stdout == text
+    plain = str(tmp_path / "o.tsv")
+    assert subprocess.run([EXE, "gzip-write", src, plain], capture_output=True, timeout=300).returncode == 0
+    assert open(plain, "rb").read() == text
