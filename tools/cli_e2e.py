@@ -30,13 +30,22 @@ def main():
     n_gz = min(n_reads, 1_000_000)
     fqgz = os.path.join(tmp, "reads_1m.fq.gz")
     rec[:n_gz].tofile(os.path.join(tmp, "reads_1m.fq"))
-    subprocess.run("gzip -1 -c %s/reads_1m.fq > %s" % (tmp, fqgz), shell=True, check=True)
+    subprocess.run("gzip -6 -c %s/reads_1m.fq > %s" % (tmp, fqgz), shell=True, check=True)
+    # the reader stages alone (no GPU involved): inflate and parse rates of this box
+    stages = {}
+    for nm, args in (("parse plain", ["parse", "--count", fq]), ("parse gz sequential", ["parse", "--count", "--ahead", "--inflate-threads", "1", fqgz]),
+                     ("parse gz 8 threads", ["parse", "--count", "--ahead", "--inflate-threads", "8", fqgz])):
+        stages[nm] = subprocess.run([os.path.join(ROOT, "kmcp_b200", "kmcp-gpu")] + args, capture_output=True).stderr.decode().strip()
     exe = os.path.join(ROOT, "kmcp_b200", "kmcp-gpu")
     out = []
-    for name, inp, n, outp in [("fastq -> tsv", fq, n_reads, "o.tsv"), ("fastq -> tsv.gz", fq, n_reads, "o.tsv.gz"),
-                               ("fastq.gz -> tsv.gz", fqgz, n_gz, "o1.tsv.gz")]:
+    for name, inp, n, outp, extra in [("fastq -> tsv", fq, n_reads, "o.tsv", []), ("fastq -> tsv.gz", fq, n_reads, "o.tsv.gz", []),
+                                      ("fastq -> tsv.gz level 6", fq, n_reads, "o6.tsv.gz", ["--compression-level", "6"]),
+                                      ("fastq.gz -> tsv.gz (sequential inflate)", fqgz, n_gz, "o1.tsv.gz", ["--inflate-threads", "1"]),
+                                      ("fastq.gz -> tsv.gz (4 inflate threads)", fqgz, n_gz, "o4.tsv.gz", ["--inflate-threads", "4"]),
+                                      ("fastq.gz -> tsv.gz (8 inflate threads)", fqgz, n_gz, "o8.tsv.gz", ["--inflate-threads", "8"]),
+                                      ("fastq.gz -> tsv.gz (default)", fqgz, n_gz, "od.tsv.gz", [])]:
         t0 = time.time()
-        p = subprocess.run([exe, "search", "-d", tmp, inp, "-o", os.path.join(tmp, outp)], capture_output=True)
+        p = subprocess.run([exe, "search", "-d", tmp, inp, "-o", os.path.join(tmp, outp)] + extra, capture_output=True)
         wall = time.time() - t0
         log = p.stderr.decode()
         assert p.returncode == 0, log
@@ -47,7 +56,7 @@ def main():
                     "search_reads_per_s": round(float(speed.group(1)) * 1e6 / 60) if speed else None,
                     "out_bytes": os.path.getsize(os.path.join(tmp, outp))})
     a = subprocess.run("zcat %s/o.tsv.gz | md5sum; md5sum < %s/o.tsv" % (tmp, tmp), shell=True, capture_output=True).stdout.decode().split()
-    print(json.dumps({"cases": out, "gz_equals_plain": a[0] == a[2]}, indent=1))
+    print(json.dumps({"cases": out, "reader_stages": stages, "gz_equals_plain": a[0] == a[2]}, indent=1))
     subprocess.run(["rm", "-rf", tmp])
 
 if __name__ == "__main__":
