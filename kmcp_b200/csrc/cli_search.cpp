@@ -476,6 +476,182 @@ std::string trim_ext(const std::string &file) {     // filepathTrimExtension: st
     return b;
 }
 
+// ---- reader stage: files → packed batches ---------------------------------------------------------------------------------
+// what the engine call takes: the sequences of the batch back to back + offsets (two per query for paired-end input), the IDs in
+// one arena (no allocation per read)
+struct Batch {
+    std::vector<char> id_buf;
+    std::vector<uint64_t> id_off{0};
+    std::vector<uint8_t> seq;
+    std::vector<uint64_t> off{0};
+    uint64_t base = 0;
+    size_t n_ids() const { return id_off.size() - 1; }
+    void add_id(const char *p, size_t n) { id_buf.insert(id_buf.end(), p, p + n); id_off.push_back(id_buf.size()); }
+    void add_id(const std::string &id) { add_id(id.data(), id.size()); }
+};
+
+// One input file parsed on a thread of its own into blocks of records (IDs and sequences back to back), a short queue ahead of
+// the thread that builds the batches: with paired-end input the two mates are inflated AND parsed side by side, and the batch
+// builder only copies.
+struct RecordStream {
+    static constexpr size_t BLOCK_RECS = 1u << 15, BLOCK_BYTES = 64u << 20, DEPTH = 4;
+    struct Block {
+        std::vector<char> ids;
+        std::vector<uint8_t> seq;
+        std::vector<uint32_t> id_end, seq_end;       // ends of record i inside ids / seq
+        size_t n() const { return id_end.size(); }
+        void clear() { ids.clear(); seq.clear(); id_end.clear(); seq_end.clear(); }
+    };
+    Reader r;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Block *> ready, spare;
+    bool stop = false, done = false;
+    Block *cur = nullptr;
+    size_t i = 0;
+    bool open(const std::string &path) {
+        if (!r.open(path, true)) return false;
+        th = std::thread([this] {
+            std::string id;
+            for (;;) {
+                Block *b = nullptr;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || ready.size() < DEPTH; });
+                    if (stop) return;
+                    if (!spare.empty()) { b = spare.front(); spare.pop_front(); }
+                }
+                if (!b) b = new Block();
+                b->clear();
+                bool more = true;
+                while (b->n() < BLOCK_RECS && b->seq.size() < BLOCK_BYTES) {
+                    if (!r.next(id, b->seq)) { more = false; break; }
+                    b->ids.insert(b->ids.end(), id.begin(), id.end());
+                    b->id_end.push_back((uint32_t)b->ids.size());
+                    b->seq_end.push_back((uint32_t)b->seq.size());
+                }
+                std::lock_guard<std::mutex> lk(mu);
+                if (b->n()) ready.push_back(b); else spare.push_back(b);
+                if (!more) done = true;
+                cv.notify_all();
+                if (!more) return;
+            }
+        });
+        return true;
+    }
+    // the next block of records, nullptr at the end of the file; the previous one goes back to the parser
+    Block *next_block() {
+        std::unique_lock<std::mutex> lk(mu);
+        if (cur) { spare.push_back(cur); cur = nullptr; cv.notify_all(); }
+        cv.wait(lk, [&] { return !ready.empty() || done; });
+        if (ready.empty()) return nullptr;
+        cur = ready.front(); ready.pop_front(); i = 0;
+        cv.notify_all();
+        return cur;
+    }
+    // record by record: false at the end of the file
+    bool next(const char *&id, size_t &idn, const uint8_t *&sq, size_t &sn) {
+        if (!cur || i == cur->n()) { if (!next_block()) return false; }
+        const size_t a = i ? cur->id_end[i - 1] : 0, c = i ? cur->seq_end[i - 1] : 0;
+        id = cur->ids.data() + a; idn = cur->id_end[i] - a;
+        sq = cur->seq.data() + c; sn = cur->seq_end[i] - c;
+        i++;
+        return true;
+    }
+    void close() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        for (Block *b : ready) delete b;
+        for (Block *b : spare) delete b;
+        delete cur;
+        ready.clear(); spare.clear(); cur = nullptr;
+        r.close();
+    }
+};
+
+struct ReaderConfig {
+    bool paired = false, whole_file = false, use_filename = false;
+    std::string read1, read2, query_id;
+    std::vector<std::string> files;
+    size_t batch_reads = 1u << 18, batch_bytes = 256u << 20;
+    int kmax = 21;
+};
+
+// S:793-1000: the input files as batches, in order; `emit` takes the batch over
+void read_batches(const ReaderConfig &c, const std::function<void(Batch *)> &emit_fn) {
+    Batch *cur = new Batch();
+    auto emit = [&]() {
+        if (cur->n_ids() == 0) return;
+        if (cur->seq.empty()) cur->seq.push_back(0);
+        emit_fn(cur);
+        cur = new Batch();
+    };
+    auto full = [&]() { return cur->n_ids() >= c.batch_reads || cur->seq.size() >= c.batch_bytes; };
+    if (c.paired) {
+        RecordStream r1, r2;
+        if (!r1.open(c.read1)) die("%s: no such file", c.read1.c_str());
+        if (!r2.open(c.read2)) die("%s: no such file", c.read2.c_str());
+        logf("INFO", "reading from paired-end files: %s, %s", c.read1.c_str(), c.read2.c_str());
+        const char *id1, *id2; const uint8_t *s1, *s2; size_t n1, n2, l1, l2;
+        for (;;) {                                                    // S:806-867: ID of read1; ends with the shorter file
+            if (!r1.next(id1, n1, s1, l1)) break;
+            if (!r2.next(id2, n2, s2, l2)) break;
+            cur->add_id(id1, n1);
+            cur->seq.insert(cur->seq.end(), s1, s1 + l1); cur->off.push_back(cur->seq.size());
+            cur->seq.insert(cur->seq.end(), s2, s2 + l2); cur->off.push_back(cur->seq.size());
+            if (full()) emit();
+        }
+        r1.close(); r2.close();
+    } else {
+        std::string id;
+        for (auto &file : c.files) {
+            logf("INFO", "reading sequence file: %s", file.c_str());
+            if (c.whole_file) {                                       // S:885-937 (the N-run follows every record after the second)
+                Reader r;
+                if (!r.open(file, true)) die("%s: no such file", file.c_str());
+                std::string qid;
+                bool first = true;
+                const size_t mark = cur->seq.size();
+                while (r.next(id, cur->seq)) {
+                    if (first) { qid = c.use_filename ? trim_ext(file) : (!c.query_id.empty() ? c.query_id : id); first = false; }
+                    else cur->seq.insert(cur->seq.end(), (size_t)(c.kmax - 1), (uint8_t)'N');
+                }
+                r.close();
+                if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); cur->seq.resize(mark); continue; }
+                cur->add_id(qid); cur->off.push_back(cur->seq.size());
+                if (cur->seq.size() >= c.batch_bytes) emit();
+            } else {
+                RecordStream rs;
+                if (!rs.open(file)) die("%s: no such file", file.c_str());
+                bool any = false;
+                while (RecordStream::Block *b = rs.next_block()) {   // whole blocks are appended: three copies and two offset loops
+                    any = true;
+                    size_t at = 0;                                    // records of the block already taken
+                    while (at < b->n()) {
+                        const size_t room = c.batch_reads > cur->n_ids() ? c.batch_reads - cur->n_ids() : 1;
+                        const size_t take = std::min(room, b->n() - at);
+                        const size_t i0 = at ? b->id_end[at - 1] : 0, i1 = b->id_end[at + take - 1];
+                        const size_t s0 = at ? b->seq_end[at - 1] : 0, s1 = b->seq_end[at + take - 1];
+                        const uint64_t ib = cur->id_buf.size() - i0, sb = cur->seq.size() - s0;
+                        cur->id_buf.insert(cur->id_buf.end(), b->ids.begin() + (ptrdiff_t)i0, b->ids.begin() + (ptrdiff_t)i1);
+                        cur->seq.insert(cur->seq.end(), b->seq.begin() + (ptrdiff_t)s0, b->seq.begin() + (ptrdiff_t)s1);
+                        for (size_t k = at; k < at + take; k++) { cur->id_off.push_back(ib + b->id_end[k]); cur->off.push_back(sb + b->seq_end[k]); }
+                        at += take;
+                        if (full()) emit();
+                    }
+                }
+                rs.close();
+                if (!any) logf("WARN", "no valid sequences in file: %s", file.c_str());
+            }
+        }
+    }
+    emit();
+    delete cur;
+}
+
+
 void load_kv(const std::string &path, std::map<std::string, std::string> &m) {
     Reader r;
     if (!r.open(path)) die("fail to read name mapping file: %s", path.c_str());
@@ -563,10 +739,14 @@ int index_main(int argc, char **argv) {
 int parse_main(int argc, char **argv) {
     std::vector<std::string> files;
     std::string r1, r2;
-    bool ahead = false, count_only = false;
+    bool ahead = false, count_only = false, batches = false, whole = false;
+    size_t batch_reads = 1u << 18;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--ahead") ahead = true;
+        else if (a == "--batches") batches = true;           // through the search command's batch builder (parser threads per file)
+        else if (a == "--batch-reads" && i + 1 < argc) batch_reads = (size_t)atol(argv[++i]);
+        else if (a == "-g") whole = true;
         else if (a == "--count") count_only = true;          // the reader's rate alone: records and bases to stderr, no per-record output
         else if (a == "--inflate-threads" && i + 1 < argc) g_inflate_threads = atoi(argv[++i]);
         else if (a == "--inflate-chunk" && i + 1 < argc) g_inflate_chunk = (size_t)atol(argv[++i]);
@@ -583,6 +763,34 @@ int parse_main(int argc, char **argv) {
         seq.clear();
         if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
     };
+    if (batches) {
+        // one line per query of every batch: id, then length and CRC-32 of each of its sequences; "# batch" lines in between
+        ReaderConfig rc;
+        rc.paired = !r1.empty() && !r2.empty(); rc.read1 = r1; rc.read2 = r2; rc.files = files; rc.whole_file = whole; rc.batch_reads = batch_reads;
+        const auto t0 = std::chrono::steady_clock::now();
+        uint64_t nq = 0;
+        read_batches(rc, [&](Batch *bt) {
+            const size_t step = rc.paired ? 2 : 1;
+            if (!count_only) {
+                out += "# batch of " + std::to_string(bt->n_ids()) + "\n";
+                for (size_t q = 0; q < bt->n_ids(); q++) {
+                    out.append(bt->id_buf.data() + bt->id_off[q], (size_t)(bt->id_off[q + 1] - bt->id_off[q]));
+                    for (size_t m = 0; m < step; m++) {
+                        const uint64_t a = bt->off[q * step + m], b = bt->off[q * step + m + 1];
+                        int n = snprintf(line, sizeof(line), "\t%llu\t%08lx", (unsigned long long)(b - a), (unsigned long)crc32(0L, bt->seq.data() + a, (uInt)(b - a)));
+                        out.append(line, (size_t)n);
+                    }
+                    out += '\n';
+                }
+                fwrite(out.data(), 1, out.size(), stdout); out.clear();
+            }
+            nq += bt->n_ids();
+            delete bt;
+        });
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (count_only) fprintf(stderr, "%llu queries, %.3f s, %.2f M queries/s\n", (unsigned long long)nq, dt, nq / dt / 1e6);
+        return 0;
+    }
     if (count_only) {
         const auto t0 = std::chrono::steady_clock::now();
         uint64_t n = 0, bases = 0;
@@ -928,15 +1136,6 @@ int main(int argc, char **argv) {
 
     // ---- three-stage pipeline: reader thread (inflate + parse + pack) → this thread (GPU engine, every database) →
     //      writer thread (merge across databases, TSV formatting on several threads, parallel gzip), all in input order ----
-    struct Batch {
-        std::vector<char> id_buf;             // the IDs back to back: no allocation per read
-        std::vector<uint64_t> id_off{0};
-        std::vector<uint8_t> seq;
-        std::vector<uint64_t> off{0};
-        uint64_t base = 0;
-        size_t n_ids() const { return id_off.size() - 1; }
-        void add_id(const std::string &id) { id_buf.insert(id_buf.end(), id.begin(), id.end()); id_off.push_back(id_buf.size()); }
-    };
     struct Job { Batch *batch = nullptr; std::vector<kmcpg_results> res; };
     std::mutex mu;
     std::condition_variable cv;
@@ -947,65 +1146,19 @@ int main(int argc, char **argv) {
     const int kmax = dbs[0].info.ks[0];
 
     std::thread reader([&] {
-        Batch *cur = new Batch();
+        ReaderConfig rc;
+        rc.paired = paired; rc.read1 = o.read1; rc.read2 = o.read2; rc.files = files;
+        rc.whole_file = o.whole_file; rc.use_filename = o.use_filename; rc.query_id = o.query_id;
+        rc.batch_reads = o.batch_reads; rc.batch_bytes = o.batch_bytes; rc.kmax = kmax;
         uint64_t next_base = 0;
-        auto emit = [&]() {
-            if (cur->n_ids() == 0) return;
-            if (cur->seq.empty()) cur->seq.push_back(0);
-            cur->base = next_base;
-            next_base += cur->n_ids();
+        read_batches(rc, [&](Batch *bt) {
+            bt->base = next_base;
+            next_base += bt->n_ids();
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return in_q.size() < 2; });
-            in_q.push_back(cur);
+            in_q.push_back(bt);
             cv.notify_all();
-            cur = new Batch();
-        };
-        auto end_seq = [&]() { cur->off.push_back(cur->seq.size()); };
-        std::string id, id2;
-        if (paired) {
-            Reader r1, r2;
-            if (!r1.open(o.read1, true)) die("%s: no such file", o.read1.c_str());      // the two mates inflate side by side
-            if (!r2.open(o.read2, true)) die("%s: no such file", o.read2.c_str());
-            logf("INFO", "reading from paired-end files: %s, %s", o.read1.c_str(), o.read2.c_str());
-            for (;;) {                                                // S:806-867: ID of read1
-                const size_t mark = cur->seq.size();
-                if (!r1.next(id, cur->seq)) break;
-                const size_t mid = cur->seq.size();
-                if (!r2.next(id2, cur->seq)) { cur->seq.resize(mark); break; }
-                cur->add_id(id); cur->off.push_back(mid); end_seq();
-                if (cur->n_ids() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
-            }
-            r1.close(); r2.close();
-        } else {
-            for (auto &file : files) {
-                logf("INFO", "reading sequence file: %s", file.c_str());
-                Reader r;
-                if (!r.open(file, true)) die("%s: no such file", file.c_str());
-                if (o.whole_file) {                                   // S:885-937 (the N-run follows every record after the second)
-                    std::string qid;
-                    bool first = true;
-                    const size_t mark = cur->seq.size();
-                    while (r.next(id, cur->seq)) {
-                        if (first) { qid = o.use_filename ? trim_ext(file) : (!o.query_id.empty() ? o.query_id : id); first = false; }
-                        else cur->seq.insert(cur->seq.end(), (size_t)(kmax - 1), (uint8_t)'N');
-                    }
-                    if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); cur->seq.resize(mark); r.close(); continue; }
-                    cur->add_id(qid); end_seq();
-                    if (cur->seq.size() >= o.batch_bytes) emit();
-                } else {
-                    bool any = false;
-                    while (r.next(id, cur->seq)) {
-                        any = true;
-                        cur->add_id(id); end_seq();
-                        if (cur->n_ids() >= o.batch_reads || cur->seq.size() >= o.batch_bytes) emit();
-                    }
-                    if (!any) logf("WARN", "no valid sequences in file: %s", file.c_str());
-                }
-                r.close();
-            }
-        }
-        emit();
-        delete cur;
+        });
         std::lock_guard<std::mutex> lk(mu);
         in_done = true;
         cv.notify_all();

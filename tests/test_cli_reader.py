@@ -157,3 +157,46 @@ def test_reader_random_mixtures_of_record_styles(tmp_path):
     open(blank, "wb").write(b"\n\n\n")
     assert _parse([empty, fa, blank, str(tmp_path / "t0.fq")]) == "".join(_line(i, s) for i, s in recs) + \
         "".join(_line(i, s) for i, s in _py_records(open(str(tmp_path / "t0.fq"), "rb").read()))
+
+
+def _batches(args):
+    """records of `kmcp-gpu parse --batches`: [(id, [(len, crc), ...])], and the batch sizes"""
+    out = _parse(["--batches"] + args)
+    recs, sizes = [], []
+    for l in out.splitlines():
+        if l.startswith("# batch of "):
+            sizes.append(int(l.split()[-1]))
+            continue
+        f = l.split("\t")
+        recs.append((f[0], [(int(f[i]), f[i + 1]) for i in range(1, len(f), 2)]))
+    return recs, sizes
+
+
+def test_batch_builder_single_paired_and_whole_file(files, tmp_path):
+    """the search command's own batch builder (S:793-1000) behind `parse --batches`: a parser thread per input file, blocks of
+    records appended to the batches (single-end) or zipped pair by pair (paired-end, ends with the shorter file), -g whole files"""
+    recs = files["recs"]
+    crc = lambda s: "%08x" % zlib.crc32(s)
+    # single-end, three files, batches of 1000 reads: every record once, in order, batches full except the last
+    got, sizes = _batches(["--batch-reads", "1000", files["fa"], files["fq_plain"], files["fq_gz"]])
+    exp = [(i.decode(), [(len(s), crc(s))]) for i, s in recs[:1500] + recs[:500] + recs]
+    assert got == exp
+    assert sum(sizes) == len(exp) and all(x == 1000 for x in sizes[:-1]) and 0 < sizes[-1] <= 1000
+    for extra in ([], ["--inflate-threads", "3", "--inflate-chunk", "65536"]):
+        got, sizes = _batches(extra + ["--batch-reads", "777", "-1", files["fq_gz"], "-2", files["fq2_gz"]])
+        assert got == [(i.decode(), [(len(s), crc(s)), (len(s), crc(s[::-1]))]) for i, s in recs[:4000]]
+        assert all(x == 777 for x in sizes[:-1]) and sum(sizes) == 4000
+    # default batch size: one batch
+    got, sizes = _batches([files["fq_gz"]])
+    assert sizes == [len(recs)] and got[-1][0] == recs[-1][0].decode()
+    # -g: a file is ONE query; as in the reference (S:899-913) the run of k-1 = 20 'N' FOLLOWS every record from the second on
+    got, sizes = _batches(["-g", files["fa"], files["fq_plain"]])
+    joined = [rs[0][1] + b"".join(s + b"N" * 20 for _, s in rs[1:]) for rs in (recs[:1500], recs[:500])]
+    assert got == [(recs[0][0].decode(), [(len(j), crc(j))]) for j in joined] and sizes == [2]
+    # files without records
+    e = str(tmp_path / "e.fq")
+    open(e, "wb").close()
+    got, sizes = _batches([e, files["fq_plain"], e])
+    assert len(got) == 500 and sizes == [500]
+    assert _batches([e]) == ([], [])
+    assert _batches(["-1", e, "-2", files["fq_gz"]]) == ([], [])
