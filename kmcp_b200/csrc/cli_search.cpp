@@ -308,6 +308,8 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     template <class V>
     bool next_four_line(const char *&idp, size_t &idn, V &dst) {
         if (!fast_ok) return false;
+        if (pos == end && !fill()) return false;
+        if (buf[pos] != '@') return false;                     // FASTA (or a blank line): do not wait for four lines of a genome
         for (;;) {
             while (nl_i < nl.size() && nl[nl_i] < pos) nl_i++;
             if (nl.size() - nl_i >= 4) break;
