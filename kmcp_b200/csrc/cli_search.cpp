@@ -335,8 +335,8 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     bool line(const char *&sp, size_t &n) {
         size_t scanned = pos;
         for (;;) {
-            const char *nl = (const char *)memchr(buf.data() + scanned, '\n', end - scanned);
-            if (nl) { sp = buf.data() + pos; n = (size_t)(nl - sp); pos = (size_t)(nl - buf.data()) + 1; break; }
+            const char *eol = (const char *)memchr(buf.data() + scanned, '\n', end - scanned);
+            if (eol) { sp = buf.data() + pos; n = (size_t)(eol - sp); pos = (size_t)(eol - buf.data()) + 1; break; }
             const size_t had = end - pos;
             if (!fill()) { if (pos == end) return false; sp = buf.data() + pos; n = end - pos; pos = end; break; }
             scanned = pos + had;
