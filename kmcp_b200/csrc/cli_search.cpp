@@ -11,6 +11,7 @@
 #include <errno.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include <chrono>
@@ -132,6 +133,7 @@ void usage() {
         "      --compression-level int      level of the .gz output, 1-9 (default 4)\n"
         "      --inflate-threads int        threads that decompress ONE .gz input side by side (chunk-parallel inflate; default: by itself\n"
         "                                   on machines with >= 32 hardware threads for files >= 32 MB; 1 = sequential decoder)\n"
+        "      --parse-threads int          threads that parse ONE FASTQ input side by side (default 1: one parser thread per input)\n"
         "      --ref-counts file            also write the per-reference, per-chunk read counters of `kmcp profile` stage 1/4\n"
         "                                   (match, uniqMatch, uniqMatchHic), computed from the result stream\n"
         "      --ref-counts-min-qcov float  profile -t/--min-query-cov for --ref-counts (default 0.55)\n"
@@ -271,6 +273,9 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         fd = -1;
     }
     ssize_t raw_read(void *dst, size_t n) { return pf ? pf->read(dst, n) : f->read(dst, n); }
+    // the decoded text itself (for callers that cut it into records themselves); like read(2)
+    int read_text(char *dst, size_t n) { n = std::min<size_t>(n, 1u << 30); return ahead ? ahead->read(dst, n) : (int)raw_read(dst, n); }
+    const char *error() const { return pf ? pf->error() : (f ? f->error() : ""); }
     // worker threads for one input: --inflate-threads N, or by itself on big machines for big seekable gzip files
     static int inflate_threads(int h) {
         if (g_inflate_threads == 1 || !fastgz::ParallelInflater::usable(h)) return 1;
@@ -492,30 +497,71 @@ struct Batch {
     void add_id(const std::string &id) { add_id(id.data(), id.size()); }
 };
 
-// One input file parsed on a thread of its own into blocks of records (IDs and sequences back to back), a short queue ahead of
-// the thread that builds the batches: with paired-end input the two mates are inflated AND parsed side by side, and the batch
-// builder only copies.
+int g_parse_threads = 0;                // --parse-threads: 0 = decide per file, 1 = one parser thread per input
+size_t g_parse_piece = 8u << 20;        // --parse-piece: bytes of text per task of the parallel parser
+std::atomic<uint64_t> g_stat_pieces{0}, g_stat_fallbacks{0};      // pieces parsed by the workers / files handed back to the general reader
+
+// One input file parsed into blocks of records (IDs and sequences back to back) ahead of the thread that builds the batches:
+// with paired-end input the two mates are inflated AND parsed side by side, and the batch builder only copies.
+//
+// Two ways to get the blocks.  The plain one is a thread that calls the reader record by record.  For regular files on machines
+// with cores to spare the text itself is cut into pieces of ~8 MB at record boundaries (a line that starts with '@' whose second
+// next line starts with '+' — a quality line that starts with '@' is followed by a header and a sequence, never by a '+' line) and
+// the pieces are parsed by several workers.  A worker accepts a piece only if EVERY record in it is written as exactly four lines
+// ('@' header, sequence, '+' line, quality of the same length); such a piece starts and ends on record boundaries and parses to
+// what the general reader returns for it.  The first piece that is anything else (FASTA, wrapped FASTQ, blank lines, a truncated
+// last record) ends the parallel mode: the file is opened again, the records already handed out are skipped, and the plain
+// thread carries on — the result is the general reader's in every case.
 struct RecordStream {
     static constexpr size_t BLOCK_RECS = 1u << 15, BLOCK_BYTES = 64u << 20, DEPTH = 4;
+    static constexpr size_t PIECE_MAX = 256u << 20;
     struct Block {
         std::vector<char> ids;
         std::vector<uint8_t> seq;
         std::vector<uint32_t> id_end, seq_end;       // ends of record i inside ids / seq
+        bool bad = false;                            // parallel mode: the piece was not made of four-line records
         size_t n() const { return id_end.size(); }
-        void clear() { ids.clear(); seq.clear(); id_end.clear(); seq_end.clear(); }
+        void clear() { ids.clear(); seq.clear(); id_end.clear(); seq_end.clear(); bad = false; }
     };
+    struct Text { std::vector<char> d; size_t n = 0; };
     Reader r;
-    std::thread th;
+    std::string path;
+    std::thread th;                                  // the plain parser, or the cutter of the parallel mode
+    std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv;
     std::deque<Block *> ready, spare;
     bool stop = false, done = false;
     Block *cur = nullptr;
     size_t i = 0;
-    bool open(const std::string &path) {
-        if (!r.open(path, true)) return false;
-        th = std::thread([this] {
+    uint64_t delivered = 0;                          // records handed out so far
+    // parallel mode
+    bool par = false;
+    std::deque<std::pair<uint64_t, Text *>> work_q;  // pieces waiting for a worker
+    std::deque<Text *> text_pool;
+    std::map<uint64_t, Block *> parsed;              // finished pieces by number
+    uint64_t cut_n = 0, next_n = 0;                  // pieces cut / pieces handed out
+    size_t max_inflight = 8;
+
+    static int parse_threads(const std::string &p) {
+        if (g_parse_threads == 1 || p == "-") return 1;
+        struct stat st;
+        if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return 1;
+        // opt-in until it has been timed on the GPU box: on the 8 vCPUs it was written on the extra copies eat the gain
+        return g_parse_threads > 1 ? g_parse_threads : 1;
+    }
+    bool open(const std::string &p) {
+        path = p;
+        if (!r.open(p, true)) return false;
+        const int P = parse_threads(p);
+        if (P >= 2) start_parallel(P); else start_plain(0);
+        return true;
+    }
+    void start_plain(uint64_t skip) {
+        th = std::thread([this, skip] {
             std::string id;
+            std::vector<uint8_t> scratch;
+            for (uint64_t k = 0; k < skip; k++) { scratch.clear(); if (!r.next(id, scratch)) break; }     // handed out before the restart
             for (;;) {
                 Block *b = nullptr;
                 {
@@ -540,17 +586,185 @@ struct RecordStream {
                 if (!more) return;
             }
         });
-        return true;
     }
+
+    // ---- parallel mode ------------------------------------------------------------------------------------------------------
+    // where to cut d[0, n): the start of the last line that begins a record and has its two following line starts inside the
+    // text; 0 = no such line
+    static size_t cut_point(const char *d, size_t n) {
+        size_t e = n;                                 // lines are looked at from the end: [ls, e) is the current one
+        size_t s1 = 0, s2 = 0;                        // starts of the next line and the one after it
+        int have = 0;
+        while (e > 0) {
+            const char *q = e >= 2 ? (const char *)memrchr(d, '\n', e - 1) : nullptr;      // the line end in front of this line
+            const size_t ls = q ? (size_t)(q - d) + 1 : 0;
+            if (have >= 2 && d[ls] == '@' && d[s2] == '+' && ls > 0) return ls;
+            s2 = s1; s1 = ls; have++;
+            if (n - ls > (4u << 20) && have > 64) break;          // far from the end and still nothing: not this kind of file
+            e = ls ? ls : 0;
+            if (!ls) break;
+        }
+        return 0;
+    }
+    // a piece → records, or bad
+    static void parse_piece(const Text &t, Block &b, std::vector<uint32_t> &nl) {
+        b.clear();
+        nl.clear();
+        scan_newlines(t.d.data(), t.n, 0, nl);
+        const char *d = t.d.data();
+        if (nl.empty() || nl.size() % 4 != 0 || nl.back() + 1 != t.n) { b.bad = true; return; }
+        b.id_end.reserve(nl.size() / 4); b.seq_end.reserve(nl.size() / 4);
+        b.seq.reserve(t.n / 2); b.ids.reserve(t.n / 8);
+        size_t h0 = 0;
+        for (size_t k = 0; k < nl.size(); k += 4) {
+            const size_t s0 = (size_t)nl[k] + 1, p0 = (size_t)nl[k + 1] + 1, q0 = (size_t)nl[k + 2] + 1;
+            size_t h1 = nl[k], s1 = nl[k + 1], q1 = nl[k + 3];
+            if (d[h0] != '@' || d[p0] != '+') { b.bad = true; return; }
+            while (h1 > h0 && d[h1 - 1] == '\r') h1--;
+            while (s1 > s0 && d[s1 - 1] == '\r') s1--;
+            while (q1 > q0 && d[q1 - 1] == '\r') q1--;
+            if (q1 - q0 != s1 - s0) { b.bad = true; return; }
+            size_t e = h0 + 1;
+            while (e < h1 && d[e] != ' ' && d[e] != '\t') e++;
+            b.ids.insert(b.ids.end(), d + h0 + 1, d + e);
+            b.seq.insert(b.seq.end(), (const uint8_t *)d + s0, (const uint8_t *)d + s1);
+            b.id_end.push_back((uint32_t)b.ids.size());
+            b.seq_end.push_back((uint32_t)b.seq.size());
+            h0 = (size_t)nl[k + 3] + 1;
+        }
+    }
+    void start_parallel(int P) {
+        par = true;
+        max_inflight = (size_t)P * 2 + 2;
+        for (int w = 0; w < P; w++)
+            workers.emplace_back([this] {
+                std::vector<uint32_t> nl;
+                for (;;) {
+                    std::pair<uint64_t, Text *> job;
+                    Block *b = nullptr;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return stop || !work_q.empty(); });
+                        if (stop) return;
+                        job = work_q.front(); work_q.pop_front();
+                        if (!spare.empty()) { b = spare.front(); spare.pop_front(); }
+                    }
+                    if (!b) b = new Block();
+                    if (job.second->n == 0) { b->clear(); b->bad = true; }        // the cutter found no record boundary
+                    else parse_piece(*job.second, *b, nl);
+                    std::lock_guard<std::mutex> lk(mu);
+                    parsed[job.first] = b;
+                    text_pool.push_back(job.second);
+                    cv.notify_all();
+                }
+            });
+        th = std::thread([this] {
+            const size_t PIECE = std::max<size_t>(g_parse_piece, 64);
+            std::vector<char> carry;
+            bool eof = false;
+            auto give = [&](Text *t) {
+                std::lock_guard<std::mutex> lk(mu);
+                work_q.push_back({cut_n++, t});
+                cv.notify_all();
+            };
+            while (!eof) {
+                Text *t = nullptr;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || cut_n - next_n < max_inflight; });
+                    if (stop) return;
+                    if (!text_pool.empty()) { t = text_pool.front(); text_pool.pop_front(); }
+                }
+                if (!t) t = new Text();
+                if (t->d.size() < PIECE + (1u << 20)) t->d.resize(PIECE + (1u << 20));
+                t->n = carry.size();
+                if (t->n > t->d.size()) t->d.resize(t->n + PIECE);
+                if (t->n) memcpy(t->d.data(), carry.data(), t->n);
+                carry.clear();
+                size_t want = PIECE;
+                size_t cut = 0;
+                for (;;) {
+                    while (t->n < want) {                             // fill up to the piece size
+                        if (t->d.size() < want + 1) t->d.resize(want + 1);
+                        const int got = r.read_text(t->d.data() + t->n, want - t->n);
+                        if (got < 0) die("read error in %s: %s", path.c_str(), r.error());
+                        if (got == 0) { eof = true; break; }
+                        t->n += (size_t)got;
+                    }
+                    if (eof) {                                        // the rest of the file is the last piece
+                        if (t->n && t->d[t->n - 1] != '\n') t->d[t->n++] = '\n';
+                        cut = t->n;
+                        break;
+                    }
+                    cut = cut_point(t->d.data(), t->n);
+                    if (cut) break;
+                    if (want >= PIECE_MAX) { cut = 0; break; }        // no record boundary in 256 MB of text
+                    want *= 2;                                        // very long records: look at more text
+                }
+                if (!eof && !cut) { t->n = 0; give(t); break; }      // an empty piece tells the consumer to fall back
+                if (eof && !t->n) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    text_pool.push_back(t);
+                    break;
+                }
+                carry.assign(t->d.data() + cut, t->d.data() + t->n);
+                t->n = cut;
+                give(t);
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            done = true;
+            cv.notify_all();
+        });
+    }
+    void stop_threads() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        for (auto &w : workers) w.join();
+        workers.clear();
+        for (auto &j : work_q) delete j.second;
+        for (Text *t : text_pool) delete t;
+        for (auto &kv : parsed) delete kv.second;
+        work_q.clear(); text_pool.clear(); parsed.clear();
+    }
+
     // the next block of records, nullptr at the end of the file; the previous one goes back to the parser
     Block *next_block() {
-        std::unique_lock<std::mutex> lk(mu);
-        if (cur) { spare.push_back(cur); cur = nullptr; cv.notify_all(); }
-        cv.wait(lk, [&] { return !ready.empty() || done; });
-        if (ready.empty()) return nullptr;
-        cur = ready.front(); ready.pop_front(); i = 0;
-        cv.notify_all();
-        return cur;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            if (cur) { spare.push_back(cur); cur = nullptr; cv.notify_all(); }
+            if (!par) {
+                cv.wait(lk, [&] { return !ready.empty() || done; });
+                if (ready.empty()) return nullptr;
+                cur = ready.front(); ready.pop_front(); i = 0;
+                delivered += cur->n();
+                cv.notify_all();
+                return cur;
+            }
+            cv.wait(lk, [&] { return parsed.count(next_n) || (done && next_n == cut_n); });
+            auto it = parsed.find(next_n);
+            if (it == parsed.end()) return nullptr;
+            Block *b = it->second;
+            parsed.erase(it);
+            next_n++;
+            cv.notify_all();
+            if (!b->bad) {
+                g_stat_pieces++;
+                if (!b->n()) { spare.push_back(b); continue; }
+                cur = b; i = 0;
+                delivered += b->n();
+                return cur;
+            }
+            // not (only) four-line records: the general reader takes over behind the records handed out so far
+            delete b;
+            g_stat_fallbacks++;
+            lk.unlock();
+            stop_threads();
+            r.close();
+            if (!r.open(path, true)) die("%s: no such file", path.c_str());
+            { std::lock_guard<std::mutex> g(mu); stop = false; done = false; par = false; }
+            start_plain(delivered);
+        }
     }
     // record by record: false at the end of the file
     bool next(const char *&id, size_t &idn, const uint8_t *&sq, size_t &sn) {
@@ -562,9 +776,7 @@ struct RecordStream {
         return true;
     }
     void close() {
-        { std::lock_guard<std::mutex> lk(mu); stop = true; }
-        cv.notify_all();
-        if (th.joinable()) th.join();
+        stop_threads();
         for (Block *b : ready) delete b;
         for (Block *b : spare) delete b;
         delete cur;
@@ -751,6 +963,8 @@ int parse_main(int argc, char **argv) {
         else if (a == "-g") whole = true;
         else if (a == "--count") count_only = true;          // the reader's rate alone: records and bases to stderr, no per-record output
         else if (a == "--inflate-threads" && i + 1 < argc) g_inflate_threads = atoi(argv[++i]);
+        else if (a == "--parse-threads" && i + 1 < argc) g_parse_threads = atoi(argv[++i]);
+        else if (a == "--parse-piece" && i + 1 < argc) g_parse_piece = (size_t)atol(argv[++i]);
         else if (a == "--inflate-chunk" && i + 1 < argc) g_inflate_chunk = (size_t)atol(argv[++i]);
         else if (a == "-1" && i + 1 < argc) r1 = argv[++i];
         else if (a == "-2" && i + 1 < argc) r2 = argv[++i];
@@ -790,7 +1004,9 @@ int parse_main(int argc, char **argv) {
             delete bt;
         });
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (count_only) fprintf(stderr, "%llu queries, %.3f s, %.2f M queries/s\n", (unsigned long long)nq, dt, nq / dt / 1e6);
+        if (count_only)
+            fprintf(stderr, "%llu queries, %.3f s, %.2f M queries/s (pieces parsed in parallel: %llu, files handed back to the general reader: %llu)\n",
+                    (unsigned long long)nq, dt, nq / dt / 1e6, (unsigned long long)g_stat_pieces.load(), (unsigned long long)g_stat_fallbacks.load());
         return 0;
     }
     if (count_only) {
@@ -947,6 +1163,8 @@ int main(int argc, char **argv) {
         else if (a == "--gpu-mode") o.gpu_mode = sval();
         else if (a == "--compression-level") { g_compression_level = atoi(sval().c_str()); if (g_compression_level < 1 || g_compression_level > 9) die("--compression-level should be in range [1, 9]"); }
         else if (a == "--inflate-threads") g_inflate_threads = atoi(sval().c_str());
+        else if (a == "--parse-threads") g_parse_threads = atoi(sval().c_str());
+        else if (a == "--parse-piece") g_parse_piece = (size_t)atol(sval().c_str());
         else if (a == "--inflate-chunk") g_inflate_chunk = (size_t)atol(sval().c_str());
         else if (a == "--gpus") {
             const std::string v = sval();

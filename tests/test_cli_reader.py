@@ -71,6 +71,19 @@ def test_reader_paired_files_stop_at_the_shorter_mate(files, ahead):
     assert _parse(ahead + ["-1", files["fq_gz"], "-2", files["fq2_gz"]]) == exp
 
 
+def _batches(args):
+    """records of `kmcp-gpu parse --batches`: [(id, [(len, crc), ...])], and the batch sizes"""
+    out = _parse(["--batches"] + args)
+    recs, sizes = [], []
+    for l in out.splitlines():
+        if l.startswith("# batch of "):
+            sizes.append(int(l.split()[-1]))
+            continue
+        f = l.split("\t")
+        recs.append((f[0], [(int(f[i]), f[i + 1]) for i in range(1, len(f), 2)]))
+    return recs, sizes
+
+
 def _py_records(data):
     """what the reader must return for a FASTA/Q byte string (bio/seqio/fastx semantics as used by search.go: ID up to the
     first blank, sequence lines joined, FASTQ quality read until it is as long as the sequence)"""
@@ -148,6 +161,13 @@ def test_reader_random_mixtures_of_record_styles(tmp_path):
             f.write(data)
         assert _parse([p + ".gz"]) == exp, trial
         assert _parse(["--ahead", "--inflate-threads", "3", "--inflate-chunk", "65536", p + ".gz"]) == exp, trial
+        # the batch builder with several parser threads per file: four-line pieces in parallel, anything else by the general reader
+        want = [(i.decode(), [(len(s), "%08x" % zlib.crc32(s))]) for i, s in _py_records(data)]
+        for extra in (["--parse-threads", "3"], ["--parse-threads", "2", "--inflate-threads", "2", "--inflate-chunk", "65536"]):
+            assert _batches(extra + [p + ".gz"])[0] == want, (trial, extra)
+        assert _batches(["--parse-threads", "3", "--batch-reads", "100", p])[0] == want, trial
+        for piece in ("64", "1000", "20000"):                      # pieces far smaller than the files: cuts at record boundaries everywhere
+            assert _batches(["--parse-threads", "3", "--parse-piece", piece, p])[0] == want, (trial, piece)
     # FASTA with wrapped lines between FASTQ files, empty file, file of blank lines only
     fa = str(tmp_path / "g.fa")
     recs = [(b"c%d" % i, seq(rnd.choice([0, 59, 60, 61, 5000]))) for i in range(50)]
@@ -157,19 +177,6 @@ def test_reader_random_mixtures_of_record_styles(tmp_path):
     open(blank, "wb").write(b"\n\n\n")
     assert _parse([empty, fa, blank, str(tmp_path / "t0.fq")]) == "".join(_line(i, s) for i, s in recs) + \
         "".join(_line(i, s) for i, s in _py_records(open(str(tmp_path / "t0.fq"), "rb").read()))
-
-
-def _batches(args):
-    """records of `kmcp-gpu parse --batches`: [(id, [(len, crc), ...])], and the batch sizes"""
-    out = _parse(["--batches"] + args)
-    recs, sizes = [], []
-    for l in out.splitlines():
-        if l.startswith("# batch of "):
-            sizes.append(int(l.split()[-1]))
-            continue
-        f = l.split("\t")
-        recs.append((f[0], [(int(f[i]), f[i + 1]) for i in range(1, len(f), 2)]))
-    return recs, sizes
 
 
 def test_batch_builder_single_paired_and_whole_file(files, tmp_path):
@@ -182,7 +189,10 @@ def test_batch_builder_single_paired_and_whole_file(files, tmp_path):
     exp = [(i.decode(), [(len(s), crc(s))]) for i, s in recs[:1500] + recs[:500] + recs]
     assert got == exp
     assert sum(sizes) == len(exp) and all(x == 1000 for x in sizes[:-1]) and 0 < sizes[-1] <= 1000
-    for extra in ([], ["--inflate-threads", "3", "--inflate-chunk", "65536"]):
+    for piece in ("8388608", "50000", "3000"):
+        got2, sizes2 = _batches(["--parse-threads", "3", "--parse-piece", piece, "--batch-reads", "1000", files["fa"], files["fq_plain"], files["fq_gz"]])
+        assert got2 == exp and sizes2 == sizes, piece                        # FASTA and wrapped FASTQ fall back, the .gz file is cut into pieces
+    for extra in ([], ["--inflate-threads", "3", "--inflate-chunk", "65536"], ["--parse-threads", "4"], ["--parse-threads", "3", "--parse-piece", "30000"]):
         got, sizes = _batches(extra + ["--batch-reads", "777", "-1", files["fq_gz"], "-2", files["fq2_gz"]])
         assert got == [(i.decode(), [(len(s), crc(s)), (len(s), crc(s[::-1]))]) for i, s in recs[:4000]]
         assert all(x == 777 for x in sizes[:-1]) and sum(sizes) == 4000

@@ -34,7 +34,9 @@ def main():
     # the reader stages alone (no GPU involved): inflate and parse rates of this box
     stages = {}
     for nm, args in (("parse plain", ["parse", "--count", fq]), ("parse gz sequential", ["parse", "--count", "--ahead", "--inflate-threads", "1", fqgz]),
-                     ("parse gz 8 threads", ["parse", "--count", "--ahead", "--inflate-threads", "8", fqgz])):
+                     ("parse gz 8 threads", ["parse", "--count", "--ahead", "--inflate-threads", "8", fqgz]),
+                     ("batches plain", ["parse", "--batches", "--count", fq]), ("batches plain 4 parse threads", ["parse", "--batches", "--count", "--parse-threads", "4", fq]),
+                     ("batches plain 8 parse threads", ["parse", "--batches", "--count", "--parse-threads", "8", fq])):
         stages[nm] = subprocess.run([os.path.join(ROOT, "kmcp_b200", "kmcp-gpu")] + args, capture_output=True).stderr.decode().strip()
     exe = os.path.join(ROOT, "kmcp_b200", "kmcp-gpu")
     out = []
@@ -43,7 +45,9 @@ def main():
                                       ("fastq.gz -> tsv.gz (sequential inflate)", fqgz, n_gz, "o1.tsv.gz", ["--inflate-threads", "1"]),
                                       ("fastq.gz -> tsv.gz (4 inflate threads)", fqgz, n_gz, "o4.tsv.gz", ["--inflate-threads", "4"]),
                                       ("fastq.gz -> tsv.gz (8 inflate threads)", fqgz, n_gz, "o8.tsv.gz", ["--inflate-threads", "8"]),
-                                      ("fastq.gz -> tsv.gz (default)", fqgz, n_gz, "od.tsv.gz", [])]:
+                                      ("fastq.gz -> tsv.gz (default)", fqgz, n_gz, "od.tsv.gz", []),
+                                      ("fastq -> tsv, 4 parse threads", fq, n_reads, "op.tsv", ["--parse-threads", "4"]),
+                                      ("fastq.gz -> tsv.gz, 8 inflate + 4 parse threads", fqgz, n_gz, "op.tsv.gz", ["--inflate-threads", "8", "--parse-threads", "4"])]:
         t0 = time.time()
         p = subprocess.run([exe, "search", "-d", tmp, inp, "-o", os.path.join(tmp, outp)] + extra, capture_output=True)
         wall = time.time() - t0
