@@ -669,25 +669,46 @@ class ParallelInflater {
             cv_.notify_all();
         }
     }
-    // symbols → bytes: one table look-up per symbol (0..255 themselves, 0x8000+j the window's byte j)
+    // symbols → bytes.  Most symbols are plain bytes even in text that never gets rid of its markers, so 16 symbols at a time are
+    // tested for a marker and packed; only groups with a marker go through the window look-up.
     static void resolve(Item &it) {
         const Result &r = *it.r;
         try { it.out.resize(r.n_sym); } catch (const std::bad_alloc &) { it.bad = true; return; }
-        std::vector<uint8_t> lut(65536, 0);
-        for (int i = 0; i < 256; i++) lut[(size_t)i] = (uint8_t)i;
-        memcpy(lut.data() + 0x8000, it.win.data(), WIN);
         const uint16_t *s = r.sym.p + WIN;
+        const uint8_t *win = it.win.data();
         uint8_t *o = it.out.data();
         uint16_t lowest = 0xFFFF;
-        for (size_t i = 0; i < r.n_sym; i++) {
+        size_t i = 0;
+        const size_t n = r.n_sym;
+#if defined(__x86_64__)
+        i = resolve_sse(s, n, win, o, lowest);
+#endif
+        for (; i < n; i++) {
             const uint16_t v = s[i];
-            o[i] = lut[v];
-            const uint16_t m = (uint16_t)(v | (uint16_t)((int16_t)~v >> 15));     // markers keep their value, bytes become 0xFFFF
-            lowest = m < lowest ? m : lowest;
+            if (v & 0x8000) { o[i] = win[v & 0x7FFF]; lowest = v < lowest ? v : lowest; }
+            else o[i] = (uint8_t)v;
         }
         // a marker for window byte j stands for a copy from WIN - j bytes in front of the chunk: the member must be that old
         if (lowest != 0xFFFF && (uint64_t)(WIN - (lowest & 0x7FFF)) > it.member_out_before) it.bad = true;
     }
+#if defined(__x86_64__)
+    // SSE2 (part of x86-64): returns how many symbols were done (a multiple of 16)
+    static size_t resolve_sse(const uint16_t *s, size_t n, const uint8_t *win, uint8_t *o, uint16_t &lowest) {
+        size_t i = 0;
+        for (; i + 16 <= n; i += 16) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(s + i)), b = _mm_loadu_si128((const __m128i *)(s + i + 8));
+            if (_mm_movemask_epi8(_mm_or_si128(a, b)) & 0xAAAA) {                   // a high bit set in some symbol
+                for (size_t j = i; j < i + 16; j++) {
+                    const uint16_t v = s[j];
+                    if (v & 0x8000) { o[j] = win[v & 0x7FFF]; lowest = v < lowest ? v : lowest; }
+                    else o[j] = (uint8_t)v;
+                }
+            } else
+                _mm_storeu_si128((__m128i *)(o + i), _mm_packus_epi16(a, b));
+        }
+        return i;
+    }
+#endif
     bool ready_now(size_t k) { std::lock_guard<std::mutex> lk(mu_); return slots_[k].ready; }
     std::unique_ptr<Result> take(size_t k) {
         std::unique_lock<std::mutex> lk(mu_);
