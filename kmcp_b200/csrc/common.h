@@ -44,6 +44,10 @@ int read_db_meta(const std::string &dir, DbMeta &out, std::string &err);
 // X:153-304 writer (used by kmcpg_write_block and the device index builder)
 int write_block_file(const std::string &path, const BlockMeta &m, const uint8_t *rows_unpadded, std::string &err);
 
+// exactly `bytes` bytes at offset `off` of fd into dst, read as `threads` concurrent pread streams (the rows of a block come from
+// the page cache or an NVMe drive: one stream reaches neither's bandwidth); false on an I/O error or a short file
+bool pread_parallel(int fd, void *dst, size_t bytes, uint64_t off, int threads);
+
 // H:46-50 CalcSignatureSize
 uint64_t calc_signature_size(uint64_t n_elements, int num_hashes, double fpr);
 // F:32-50 QueryFPR, bit-exact with Go (math.Pow loop, big.Float prec-53 binomials)

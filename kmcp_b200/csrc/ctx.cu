@@ -12,6 +12,8 @@
 // Two work sets alternate, and the kernels of part i+1 are enqueued BEFORE the host waits for part i's hit
 // count, so the round trip and the result copies hide behind the next part's probe kernel.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -22,6 +24,7 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ctx_internal.h"
@@ -755,23 +758,25 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
         CU(cudaMalloc((void **)&b.d_rows, std::max<size_t>(b.bytes, 16)));
         ctx->blocks.push_back(b);
         if (ctx->resident_of[i] < 0) ctx->resident_of[i] = (int)ctx->blocks.size() - 1;
-        FILE *f = fopen(bm.path.c_str(), "rb");
-        if (!f) return fail(ctx, KMCPG_EIO, "cannot open " + bm.path);
-        fseek(f, (long)bm.data_offset, SEEK_SET);
+        const int fd = ::open(bm.path.c_str(), O_RDONLY);
+        if (fd < 0) return fail(ctx, KMCPG_EIO, "cannot open " + bm.path);
+        struct FdGuard { int fd; ~FdGuard() { ::close(fd); } } guard{fd};
         const uint64_t rows_per_chunk = std::max<uint64_t>(1, CHUNK / (uint64_t)bm.row_bytes);
-        if ((uint64_t)bm.row_bytes > CHUNK) { fclose(f); return fail(ctx, KMCPG_EUNSUPPORTED, "row wider than the staging buffer"); }
+        if ((uint64_t)bm.row_bytes > CHUNK) return fail(ctx, KMCPG_EUNSUPPORTED, "row wider than the staging buffer");
+        // a chunk is read by several streams at once (one fread stream does ~3 GB/s from the page cache, far below the H2D copy)
+        const int io_threads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 4));
         for (uint64_t r0 = 0; r0 < bm.num_sigs; r0 += rows_per_chunk) {
             uint64_t nr = std::min<uint64_t>(rows_per_chunk, bm.num_sigs - r0);
             size_t bytes = (size_t)nr * bm.row_bytes;
-            if (fread(ctx->h_stage.p, 1, bytes, f) != bytes) { fclose(f); return fail(ctx, KMCPG_EIO, "kmcp: truncated index file: " + bm.path); }
+            if (!pread_parallel(fd, ctx->h_stage.p, bytes, bm.data_offset + r0 * (uint64_t)bm.row_bytes, io_threads))
+                return fail(ctx, KMCPG_EIO, "kmcp: truncated index file: " + bm.path);
             cudaError_t e = ctx->d_tmp.ensure(bytes);
             if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_tmp.p, ctx->h_stage.p, bytes, cudaMemcpyHostToDevice, ctx->st);
             // whole rows travel; the re-pitch kernel keeps the bytes [col0/8, col0/8 + row_bytes) of every row
             if (e == cudaSuccess) e = launch_repitch_cols(ctx->d_tmp.as<uint8_t>(), b.d_rows + r0 * b.pitch, nr, (uint32_t)bm.row_bytes, b.col0 / 8, b.row_bytes, b.pitch, ctx->st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
-            if (e != cudaSuccess) { fclose(f); CU(e); }
+            CU(e);
         }
-        fclose(f);
         ctx->sum_row_bytes += b.row_bytes;
         ctx->resident_bytes += (int64_t)b.bytes;
         ctx->disk_bytes += (int64_t)(bm.num_sigs * (uint64_t)b.row_bytes);

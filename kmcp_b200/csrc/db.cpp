@@ -9,9 +9,44 @@
 #include <fstream>
 #include <sstream>
 
+#include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <thread>
+
 #include "common.h"
 
 namespace kmcpg {
+
+bool pread_parallel(int fd, void *dst, size_t bytes, uint64_t off, int threads) {
+    if (!bytes) return true;
+    const size_t SLICE = 4u << 20;                            // every stream takes the next 4 MB slice until none is left
+    const size_t n_slices = (bytes + SLICE - 1) / SLICE;
+    threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n_slices));
+    std::atomic<size_t> next{0};
+    std::atomic<bool> ok{true};
+    auto run = [&]() {
+        for (;;) {
+            const size_t s = next.fetch_add(1);
+            if (s >= n_slices || !ok.load()) return;
+            const size_t a = s * SLICE, e = std::min(bytes, a + SLICE);
+            size_t got = a;
+            while (got < e) {
+                const ssize_t r = pread(fd, (char *)dst + got, e - got, (off_t)(off + got));
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) { ok.store(false); return; }       // error, or the file ends inside the range
+                got += (size_t)r;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(run);
+    run();
+    for (auto &t : th) t.join();
+    return ok.load();
+}
 
 namespace {
 
@@ -285,3 +320,12 @@ uint64_t calc_signature_size(uint64_t ne, int h, double fpr) {
 }
 
 }  // namespace kmcpg
+
+// test hook (host only, tests/test_abi.py): the chunk reader of kmcpg_open_db on any file
+extern "C" int kmcpg_internal_pread_selftest(const char *path, uint64_t off, uint64_t bytes, int threads, void *dst) {
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return KMCPG_EIO;
+    const bool ok = kmcpg::pread_parallel(fd, dst, (size_t)bytes, off, threads);
+    ::close(fd);
+    return ok ? KMCPG_OK : KMCPG_EIO;
+}

@@ -255,3 +255,23 @@ def test_binding_copies_records_out_of_library_memory():
     assert out["query"][999] == 999 and out.flags.writeable
     assert C.sizeof(api.Match) == api.MATCH_DTYPE.itemsize == 48 and C.sizeof(api.Hit) == api.HIT_DTYPE.itemsize == 12
     assert len(api._np_from(None, 0, 12, api.HIT_DTYPE)) == 0
+
+
+def test_block_rows_are_read_by_several_streams(tmp_path):
+    """pread_parallel (the chunk reader of kmcpg_open_db): any offset / size / stream count gives the file's bytes; a range that
+    reaches past the end of the file is an error (a truncated index file), never a short read"""
+    import numpy as np
+    from kmcp_b200 import api
+    L = api.load()
+    f = L.kmcpg_internal_pread_selftest
+    f.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    data = np.random.default_rng(5).integers(0, 256, 23_456_789, dtype=np.uint8)
+    p = str(tmp_path / "rows.bin")
+    data.tofile(p)
+    for off, n, th in ((0, len(data), 8), (1, len(data) - 1, 3), (12345, 9_000_001, 16), (7, 1, 4), (100, 4 << 20, 2), (5, (4 << 20) + 1, 1), (0, 0, 4)):
+        dst = np.zeros(max(n, 1), dtype=np.uint8)
+        assert f(p.encode(), off, n, th, dst.ctypes.data) == 0, (off, n, th)
+        assert np.array_equal(dst[:n], data[off:off + n]), (off, n, th)
+    dst = np.zeros(1 << 20, dtype=np.uint8)
+    assert f(p.encode(), len(data) - 1000, 1001, 4, dst.ctypes.data) == api.KMCPG_EIO
+    assert f(str(tmp_path / "missing").encode(), 0, 10, 2, dst.ctypes.data) == api.KMCPG_EIO
