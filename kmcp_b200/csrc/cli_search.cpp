@@ -207,6 +207,7 @@ struct InflateAhead {
 
 int g_inflate_threads = 0;              // --inflate-threads: 0 = decide per file, 1 = always the sequential decoder
 size_t g_inflate_chunk = 2u << 20;      // --inflate-chunk: compressed bytes per task of the chunk-parallel decoder
+size_t g_inflate_cap = (size_t)256 << 20;   // --inflate-cap: most bytes a chunk may decode to before the sequential decoder takes over
 
 // offsets (base + i) of every '\n' in p[0, n): 64 bytes per step with AVX2 where the CPU has it
 #if defined(__x86_64__)
@@ -253,14 +254,11 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         fd = p == "-" ? 0 : ::open(p.c_str(), O_RDONLY);
         if (fd >= 0) {
             const int h = fd, T = inflate_threads(h);
-            if (T >= 2) pf = new fastgz::ParallelInflater(h, T, g_inflate_chunk);
-            else
-                f = new fastgz::Inflater([h](void *dst, size_t n) -> ssize_t {
-                    for (;;) { const ssize_t r = ::read(h, dst, n); if (r >= 0 || errno != EINTR) return r; }
-                });
+            if (T >= 2) pf = new fastgz::ParallelInflater(h, T, g_inflate_chunk, g_inflate_cap);
+            else f = sequential(h);
         }
         buf.resize(16u << 20);
-        pos = end = 0; eof = false;
+        pos = end = 0; eof = false; raw_total = 0;
         nl.clear(); nl_i = 0;
         if (fd >= 0 && inflate_ahead) { ahead = new InflateAhead(); ahead->start([this](void *dst, size_t n) { return raw_read(dst, n); }); }
         return fd >= 0;
@@ -272,7 +270,32 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         if (fd > 0) ::close(fd);
         fd = -1;
     }
-    ssize_t raw_read(void *dst, size_t n) { return pf ? pf->read(dst, n) : f->read(dst, n); }
+    static fastgz::Inflater *sequential(int h) {
+        return new fastgz::Inflater([h](void *dst, size_t n) -> ssize_t {
+            for (;;) { const ssize_t r = ::read(h, dst, n); if (r >= 0 || errno != EINTR) return r; }
+        });
+    }
+    uint64_t raw_total = 0;              // decoded bytes handed out so far
+    ssize_t raw_read(void *dst, size_t n) {
+        if (pf) {
+            const ssize_t r = pf->read(dst, n);
+            if (r >= 0 || !pf->too_big()) { if (r > 0) raw_total += (uint64_t)r; return r; }
+            // a stretch that expands beyond what the chunk-parallel decoder keeps in memory (compression ratios in the hundreds):
+            // the sequential decoder streams; it starts over and drops what was handed out already
+            delete pf; pf = nullptr;
+            if (lseek(fd, 0, SEEK_SET) != 0) return -1;
+            f = sequential(fd);
+            std::vector<char> scratch(4u << 20);
+            for (uint64_t left = raw_total; left;) {
+                const ssize_t k = f->read(scratch.data(), (size_t)std::min<uint64_t>(left, scratch.size()));
+                if (k <= 0) return -1;
+                left -= (uint64_t)k;
+            }
+        }
+        const ssize_t r = f->read(dst, n);
+        if (r > 0) raw_total += (uint64_t)r;
+        return r;
+    }
     // the decoded text itself (for callers that cut it into records themselves); like read(2)
     int read_text(char *dst, size_t n) { n = std::min<size_t>(n, 1u << 30); return ahead ? ahead->read(dst, n) : (int)raw_read(dst, n); }
     const char *error() const { return pf ? pf->error() : (f ? f->error() : ""); }
@@ -966,6 +989,7 @@ int parse_main(int argc, char **argv) {
         else if (a == "--parse-threads" && i + 1 < argc) g_parse_threads = atoi(argv[++i]);
         else if (a == "--parse-piece" && i + 1 < argc) g_parse_piece = (size_t)atol(argv[++i]);
         else if (a == "--inflate-chunk" && i + 1 < argc) g_inflate_chunk = (size_t)atol(argv[++i]);
+        else if (a == "--inflate-cap" && i + 1 < argc) g_inflate_cap = (size_t)atol(argv[++i]);
         else if (a == "-1" && i + 1 < argc) r1 = argv[++i];
         else if (a == "-2" && i + 1 < argc) r2 = argv[++i];
         else files.push_back(a);
@@ -1063,6 +1087,7 @@ int gunzip_main(int argc, char **argv) {
         else if (a == "--chunk" && i + 1 < argc) chunk = (size_t)atol(argv[++i]);
         else if (a == "--threads" && i + 1 < argc) threads = atoi(argv[++i]);          // > 0: the chunk-parallel decoder (pargz.h)
         else if (a == "--par-chunk" && i + 1 < argc) par_chunk = (size_t)atol(argv[++i]);
+        else if (a == "--par-cap" && i + 1 < argc) g_inflate_cap = (size_t)atol(argv[++i]);
         else if (a == "--stats") stats = true;
         else file = a;
     }
@@ -1071,11 +1096,11 @@ int gunzip_main(int argc, char **argv) {
     if (fd < 0) die("%s: no such file", file.c_str());
     if (threads > 0) {
         if (!fastgz::ParallelInflater::usable(fd)) { fprintf(stderr, "kmcp-gpu gunzip: %s: not a seekable gzip file\n", file.c_str()); return 2; }
-        fastgz::ParallelInflater inf(fd, threads, par_chunk);
+        fastgz::ParallelInflater inf(fd, threads, par_chunk, g_inflate_cap);
         std::vector<char> buf(chunk);
         for (;;) {
             const ssize_t r = inf.read(buf.data(), buf.size());
-            if (r < 0) { fprintf(stderr, "kmcp-gpu gunzip: %s: %s\n", file.c_str(), inf.error()); return 1; }
+            if (r < 0) { fprintf(stderr, "kmcp-gpu gunzip: %s: %s\n", file.c_str(), inf.error()); return inf.too_big() ? 4 : 1; }
             if (r == 0) break;
             if (fwrite(buf.data(), 1, (size_t)r, stdout) != (size_t)r) return 3;
         }
@@ -1166,6 +1191,7 @@ int main(int argc, char **argv) {
         else if (a == "--parse-threads") g_parse_threads = atoi(sval().c_str());
         else if (a == "--parse-piece") g_parse_piece = (size_t)atol(sval().c_str());
         else if (a == "--inflate-chunk") g_inflate_chunk = (size_t)atol(sval().c_str());
+        else if (a == "--inflate-cap") g_inflate_cap = (size_t)atol(sval().c_str());
         else if (a == "--gpus") {
             const std::string v = sval();
             o.devices.clear();

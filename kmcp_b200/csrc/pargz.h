@@ -57,6 +57,7 @@ struct ChunkResult {
     bool not_gzip = false;            // chunk 0 only
     bool at_eof = false;              // the last member ended and nothing (or only garbage) follows
     bool failed = false;
+    bool too_big = false;             // failed because the chunk decodes to more than the cap (a stream for the sequential decoder)
     std::string err;
     uint64_t start_bit = 0, end_bit = 0;
     // output: first the symbols written while the window in front of the chunk was unknown, then plain bytes.  Both arrays
@@ -117,7 +118,8 @@ struct Source {
 // the decoder of one chunk (or of a stretch that has to be decoded again in order)
 class ChunkDecoder {
   public:
-    ChunkDecoder(int fd, uint64_t file_size, size_t load_bytes) : src_(fd, file_size), load_(load_bytes) {
+    ChunkDecoder(int fd, uint64_t file_size, size_t load_bytes, size_t max_out = (size_t)256 << 20)
+        : src_(fd, file_size), load_(load_bytes), max_out_(max_out) {
         static const I::FixedTables fixed;
         fixed_ = &fixed;
         lt_dyn_.resize(I::LT_SIZE);
@@ -399,6 +401,7 @@ class ChunkDecoder {
             if (__builtin_expect(in >= in_safe || out >= out_limit, 0)) {
                 if (out >= out_limit) {
                     const size_t n = (size_t)(out - buf.p);
+                    if (n - WIN > max_out_) { R.too_big = true; fail(R, "chunk decodes to more than the cap of the parallel decoder"); break; }
                     buf.reserve(buf.cap + buf.cap / 2);
                     out = buf.p + n; out_limit = buf.p + buf.cap - SLACK;
                     continue;
@@ -494,6 +497,7 @@ class ChunkDecoder {
         while (stored_left_) {
             if ((size_t)(in_ - src_.z.data()) >= src_.z_len && !more_input()) return fail(R, "truncated stored block");
             const size_t n = std::min<size_t>(stored_left_, src_.z_len - (size_t)(in_ - src_.z.data()));
+            if (n_out + n > max_out_ + (1u << 20)) { R.too_big = true; return fail(R, "chunk decodes to more than the cap of the parallel decoder"); }
             if (WIN + n_out + n + SLACK > buf.cap) buf.reserve(std::max(buf.cap + buf.cap / 2, WIN + n_out + n + SLACK));
             T *out = buf.p + WIN + n_out;
             for (size_t i = 0; i < n; i++) out[i] = in_[i];
@@ -545,7 +549,7 @@ class ChunkDecoder {
     }
 
     Source src_;
-    size_t load_;
+    size_t load_, max_out_;
     const uint8_t *in_ = nullptr;
     uint64_t bb_ = 0;
     unsigned bc_ = 0;
@@ -583,7 +587,11 @@ class ParallelInflater {
         return pread(fd, m, 2, 0) == 2 && m[0] == 0x1f && m[1] == 0x8b;
     }
 
-    ParallelInflater(int fd, int threads, size_t chunk_bytes = 2u << 20) : fd_(fd), chunk_(std::max<size_t>(chunk_bytes, 65536)) {
+    // max_chunk_out: a chunk (or a stretch decoded again) that decodes to more bytes than this ends the stream with too_big() set —
+    // memory stays bounded by (2 * threads + 2) * 3 * max_chunk_out whatever the compression ratio; callers fall back to the
+    // sequential decoder, which streams
+    ParallelInflater(int fd, int threads, size_t chunk_bytes = 2u << 20, size_t max_chunk_out = (size_t)256 << 20)
+        : fd_(fd), chunk_(std::max<size_t>(chunk_bytes, 65536)), max_out_(std::max<size_t>(max_chunk_out, 1u << 16)) {
         struct stat st;
         file_size_ = fstat(fd, &st) == 0 ? (uint64_t)st.st_size : 0;
         n_chunks_ = (size_t)((file_size_ + chunk_ - 1) / chunk_);
@@ -621,6 +629,7 @@ class ParallelInflater {
         return (ssize_t)got;
     }
     const char *error() const { return err_.c_str(); }
+    bool too_big() const { return too_big_; }
     // how the stream was put together (tests and logs)
     uint64_t chunks_used() const { return used_; }
     uint64_t chunks_redone() const { return redone_; }
@@ -639,7 +648,7 @@ class ParallelInflater {
     };
 
     void work() {
-        pargz_detail::ChunkDecoder dec(fd_, file_size_, chunk_ + 65536);
+        pargz_detail::ChunkDecoder dec(fd_, file_size_, chunk_ + 65536, max_out_);
         for (;;) {
             size_t k = 0;
             std::shared_ptr<Item> job;
@@ -739,6 +748,7 @@ class ParallelInflater {
             if (!check_members(*it)) return false;
             const size_t total = it->r->n_sym + it->r->n_bytes;
             if (it->r->failed) {                                           // what it decoded before it broke is handed out first
+                too_big_ = it->r->too_big;
                 if (!total) return fail(it->r->err);
                 failed_ = true; err_ = it->r->err;
             }
@@ -807,7 +817,7 @@ class ParallelInflater {
     // decodes again, in order, from the end of the settled data up to the first block boundary at or behind stop
     bool redo(Result &rec, uint64_t stop) {
         redone_++;
-        pargz_detail::ChunkDecoder dec(fd_, file_size_, chunk_ + 65536);
+        pargz_detail::ChunkDecoder dec(fd_, file_size_, chunk_ + 65536, max_out_);
         const size_t n_hist = (size_t)std::min<uint64_t>(s_member_out_, WIN);
         try {
             dec.run_from(rec, cur_bit_, stop, tail_.data() + WIN - n_hist, n_hist);
@@ -852,7 +862,8 @@ class ParallelInflater {
     }
 
     int fd_;
-    size_t chunk_;
+    size_t chunk_, max_out_;
+    bool too_big_ = false;
     uint64_t file_size_ = 0;
     size_t n_chunks_ = 0, lookahead_ = 4;
     std::vector<Slot> slots_;

@@ -349,3 +349,19 @@ def test_result_writer_gz_members_in_order(corpus, tmp_path):
     plain = str(tmp_path / "o.tsv")
     assert subprocess.run([EXE, "gzip-write", src, plain], capture_output=True, timeout=300).returncode == 0
     assert open(plain, "rb").read() == text
+
+
+def test_parallel_decoder_memory_cap_and_reader_fallback(tmp_path):
+    """a stream that expands a few hundred times: the chunk-parallel decoder stops at its per-chunk cap (what it hands out up to
+    there is real data) and the reader carries on with the sequential decoder behind the bytes it already has"""
+    rec = b"@r\n" + b"A" * 150 + b"\n+\n" + b"F" * 150 + b"\n"
+    data = rec * 60_000
+    p = str(tmp_path / "rep.fq.gz")
+    open(p, "wb").write(_gz(data, 6))
+    r = _gunzip(p, "--threads", "3", "--par-chunk", "65536", "--par-cap", "1000000", ok=False)
+    assert r.returncode == 4 and b"cap of the parallel decoder" in r.stderr and data.startswith(r.stdout) and len(r.stdout) < len(data)
+    assert _gunzip(p, "--threads", "3", "--par-chunk", "65536").stdout == data           # under the default cap: decoded in parallel
+    q = subprocess.run([EXE, "parse", "--ahead", "--inflate-threads", "3", "--inflate-chunk", "65536", "--inflate-cap", "1000000", p],
+                       capture_output=True, timeout=300)
+    assert q.returncode == 0, q.stderr.decode()
+    assert q.stdout == (b"r\t150\t%08x\n" % zlib.crc32(b"A" * 150)) * 60_000
