@@ -400,6 +400,15 @@ int sharded_round(int n_ctx, const ShardSearch &search, const std::function<void
 int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
                        kmcpg_results *out, FprCache *shared_cache = nullptr);
 
+// Host-only test hook (kmcpg_internal_engine_standin): what the engine asks a context for — database facts, target sizes, one
+// streamed device call — answered from arrays, so the result handling (U:7466-7491, U:273-311) runs without a device.
+struct StandIn {
+    kmcpg_db_info_t info;
+    const double *tsize;
+    std::function<int(const kmcpg_search_params *, uint32_t, kmcpg_part_cb, void *, kmcpg_hits *)> device_call;
+};
+thread_local const StandIn *tl_standin = nullptr;
+
 // the calling thread's FPR memo for this database's p (F:140-193); handed to helper threads so they all fill ONE table
 FprCache *thread_fpr_cache(double fpr) {
     static thread_local FprCache tl_cache;
@@ -442,8 +451,11 @@ namespace {
 int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs,
                        kmcpg_results *out, FprCache *shared_cache) {
     kmcpg_ctx *ctx = ctxs[0];
+    const StandIn *standin = tl_standin;
     kmcpg_db_info_t info;
-    int rc = kmcpg_db_info(ctx, &info);
+    int rc = KMCPG_OK;
+    if (standin) info = standin->info;
+    else rc = kmcpg_db_info(ctx, &info);
     if (rc) return rc;
     for (int i = 1; i < n_ctx; i++) {                 // every shard must hold (a part of) the same database
         kmcpg_db_info_t oi;
@@ -459,7 +471,7 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
     const uint32_t step = o->paired ? 2 : 1;
     const uint32_t nq = n_seqs / step;
     FprCache *cache = shared_cache ? shared_cache : thread_fpr_cache(info.fpr);      // worker threads share THIS instance, not their own thread_local
-    const double *tsize = kmcpg_internal_target_sizes(ctx);
+    const double *tsize = standin ? standin->tsize : kmcpg_internal_target_sizes(ctx);
 
     ResPriv *priv = new ResPriv();
     priv->query_len = big_acquire((size_t)nq * 4); priv->n_kmers = big_acquire((size_t)nq * 4); priv->k_used = big_acquire((size_t)nq * 4);
@@ -593,11 +605,12 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
             } else {
                 std::function<void(const kmcpg_part &)> fn = [&](const kmcpg_part &pt) { absorb(pt, pt.first_query); };
                 kmcpg_hits h;
-                rc = kmcpg_search_batch_cb(ctx, &p, bs, bo, ln_total * step,
-                                           [](void *user, const kmcpg_part *pt) { (*(std::function<void(const kmcpg_part &)> *)user)(*pt); }, &fn, &h);
+                memset(&h, 0, sizeof(h));
+                const kmcpg_part_cb tramp = [](void *user, const kmcpg_part *pt) { (*(std::function<void(const kmcpg_part &)> *)user)(*pt); };
+                rc = standin ? standin->device_call(&p, ln_total * step, tramp, &fn, &h) : kmcpg_search_batch_cb(ctx, &p, bs, bo, ln_total * step, tramp, &fn, &h);
                 if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
                 out->ms_gpu_total += h.ms_total; out->probe_row_bytes += h.probe_row_bytes; out->kernel_launches += h.kernel_launches;
-                kmcpg_free_hits(&h);
+                if (!standin) kmcpg_free_hits(&h);
             }
             if (single && (tries_max > 1 || info.n_ks > 1) && !retry.empty()) {
                 // more rounds will follow: remember where round 0 put every matched query
@@ -812,6 +825,43 @@ int kmcpg_internal_replicas_selftest(int n_rep, uint32_t nq, int paired, int fai
     if (same && one.n_matches) same = !memcmp(one.matches, many.matches, one.n_matches * sizeof(kmcpg_match));
     kmcpg_free_results(&one); kmcpg_free_results(&many);
     return same ? KMCPG_OK : KMCPG_EINVAL;
+}
+
+// test hook (tests/test_engine_host.py, no GPU needed): kmcpg_engine_search's result handling over a given hit list.  The "device"
+// delivers the hits [(query, target, count), sorted by query then target] in parts of part_queries queries, with the n_kmers /
+// query_len arrays, exactly as kmcpg_search_batch_cb would; only single-round configurations (one k, no --try-se).
+int kmcpg_internal_engine_standin(const kmcpg_engine_opts *o, uint32_t n_queries, const int32_t *n_kmers, const int32_t *query_len, const kmcpg_hit *hits,
+                                  uint64_t n_hits, const double *target_sizes, int64_t n_targets, double fpr, int k, uint32_t part_queries, kmcpg_results *out) {
+    if (!o || !out || o->try_se || (n_queries && (!n_kmers || !query_len)) || (n_hits && !hits) || !target_sizes || part_queries == 0) return KMCPG_EINVAL;
+    StandIn si;
+    memset(&si.info, 0, sizeof(si.info));
+    si.info.n_ks = 1; si.info.ks[0] = k; si.info.fpr = fpr; si.info.n_targets = n_targets; si.info.num_hashes = 1; si.info.n_blocks = 1;
+    si.tsize = target_sizes;
+    const uint32_t step = o->paired ? 2 : 1;
+    si.device_call = [&](const kmcpg_search_params *, uint32_t n_seqs, kmcpg_part_cb cb, void *user, kmcpg_hits *summary) -> int {
+        if (n_seqs / step != n_queries) return KMCPG_EINVAL;
+        uint64_t h0 = 0;
+        for (uint32_t q0 = 0; q0 < n_queries; q0 += part_queries) {
+            const uint32_t nq = std::min(part_queries, n_queries - q0);
+            uint64_t h1 = h0;
+            while (h1 < n_hits && hits[h1].query < q0 + nq) h1++;
+            kmcpg_part pt;
+            pt.first_query = q0; pt.n_queries = nq;
+            pt.n_kmers = n_kmers + q0; pt.query_len = query_len + q0;
+            pt.hits = hits + h0; pt.n_hits = h1 - h0;
+            cb(user, &pt);
+            h0 = h1;
+        }
+        summary->n_queries = n_queries;
+        return h0 == n_hits ? KMCPG_OK : KMCPG_EINVAL;
+    };
+    std::vector<uint64_t> off((size_t)n_queries * step + 1, 0);          // the sequences themselves never reach the stand-in
+    const uint8_t dummy = 0;
+    kmcpg_ctx *none = nullptr;
+    tl_standin = &si;
+    const int rc = engine_search_impl(&none, 1, o, &dummy, off.data(), n_queries * step, out);
+    tl_standin = nullptr;
+    return rc;
 }
 
 // test hook (tests/test_abi.py, no GPU needed): the k-way merge the sharded engine applies to the per-shard hit lists
