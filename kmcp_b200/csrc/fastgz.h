@@ -555,6 +555,10 @@ class Inflater {
         const uint8_t *in_safe = in_eof_ ? in_end_ : (in_end_ - in_next_ > 16 ? in_end_ - 16 : in_next_);
         int ret = -1;
         const uint32_t LM = (1u << LBITS) - 1, DM = (1u << DBITS) - 1;
+        // `e` is always the table entry of the next symbol, looked up before the previous symbol's bytes were copied: after a
+        // refill all 64 bits of the buffer are stream bits, a symbol takes at most 48, so the 11 index bits behind it are valid
+        FASTGZ_REFILL();
+        uint32_t e = LT[bb & LM];
         for (;;) {
             if (__builtin_expect(in >= in_safe || out >= out_limit, 0)) {
                 if (out >= out_limit) { ret = 0; break; }
@@ -569,8 +573,6 @@ class Inflater {
                 // the tail of the input: zero padding follows; stop as soon as bits past the real end were used
                 if (in - (bc >> 3) > in_end_) { fail("truncated deflate stream"); break; }
             }
-            FASTGZ_REFILL();
-            uint32_t e = LT[bb & LM];
             if (e & E_LIT) {
                 // up to four lookups (eight literals, at most 44 bits) on one refill; both bytes are always stored, the
                 // second one is overwritten when the entry holds a single literal
@@ -587,20 +589,23 @@ class Inflater {
                     FASTGZ_LITERALS();
                     if (e & E_LIT) {
                         FASTGZ_LITERALS();
-                        if (e & E_LIT) {
-                            FASTGZ_LITERALS();
-                            if (e & E_LIT) continue;         // looked up once more than used: the next round starts over
-                        }
+                        if (e & E_LIT) FASTGZ_LITERALS();
                     }
                 }
 #undef FASTGZ_LITERALS
                 FASTGZ_REFILL();
+                if (e & E_LIT) continue;
             }
             if (__builtin_expect(e & E_EXC, 0)) {
                 if (e & E_SUB) {
                     bb >>= LBITS; bc -= LBITS;
                     e = LT[(e >> 16) + ((uint32_t)bb & ((1u << ((e >> 8) & 15)) - 1))];
-                    if (e & E_LIT) { bb >>= (e & 63); bc -= (e & 63); *out++ = (uint8_t)(e >> 16); continue; }
+                    if (e & E_LIT) {
+                        bb >>= (e & 63); bc -= (e & 63); *out++ = (uint8_t)(e >> 16);
+                        FASTGZ_REFILL();
+                        e = LT[bb & LM];
+                        continue;
+                    }
                 }
                 if (e & E_EXC) {
                     if ((e >> 16) == 0) { bb >>= (e & 63); bc -= (e & 63); ret = 1; break; }
@@ -624,6 +629,7 @@ class Inflater {
             tot = e & 63;
             bb >>= tot; bc -= tot;
             const uint32_t dist = (e >> 16) + (((uint32_t)saved & ((1u << tot) - 1)) >> ((e >> 8) & 15));
+            e = LT[bb & LM];                                   // the next symbol's entry travels while the bytes are copied
             if (__builtin_expect((size_t)(out - win_start) < dist, 0)) { fail("invalid distance too far back"); break; }
             const uint8_t *src = out - dist;
             uint8_t *dst = out;
@@ -644,6 +650,7 @@ class Inflater {
             } else {
                 do { *dst++ = *src++; } while (dst < out);
             }
+            FASTGZ_REFILL();
         }
         in_next_ = in; bitbuf_ = bb; bitcnt_ = bc; out_next_ = out;
         return ret;

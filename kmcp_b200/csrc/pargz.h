@@ -397,6 +397,9 @@ class ChunkDecoder {
         const uint32_t LM = (1u << I::LBITS) - 1, DM = (1u << I::DBITS) - 1;
         const uint8_t *in_safe = safe_end();
         bool ok = false;
+        // `e` is the table entry of the next symbol, looked up before the previous symbol's copy (see fastgz.h)
+        PARGZ_REFILL();
+        uint32_t e = LT[bb & LM];
         for (;;) {
             if (__builtin_expect(in >= in_safe || out >= out_limit, 0)) {
                 if (out >= out_limit) {
@@ -415,8 +418,6 @@ class ChunkDecoder {
                 }
                 if ((size_t)(in - src_.z.data()) - (bc >> 3) > src_.z_len) { fail(R, "truncated deflate stream"); break; }
             }
-            PARGZ_REFILL();
-            uint32_t e = LT[bb & LM];
             if (e & I::E_LIT) {
 #define PARGZ_LITERALS()                                        \
     do {                                                        \
@@ -431,20 +432,23 @@ class ChunkDecoder {
                     PARGZ_LITERALS();
                     if (e & I::E_LIT) {
                         PARGZ_LITERALS();
-                        if (e & I::E_LIT) {
-                            PARGZ_LITERALS();
-                            if (e & I::E_LIT) continue;
-                        }
+                        if (e & I::E_LIT) PARGZ_LITERALS();
                     }
                 }
 #undef PARGZ_LITERALS
                 PARGZ_REFILL();
+                if (e & I::E_LIT) continue;
             }
             if (__builtin_expect(e & I::E_EXC, 0)) {
                 if (e & I::E_SUB) {
                     bb >>= I::LBITS; bc -= I::LBITS;
                     e = LT[(e >> 16) + ((uint32_t)bb & ((1u << ((e >> 8) & 15)) - 1))];
-                    if (e & I::E_LIT) { bb >>= (e & 63); bc -= (e & 63); *out++ = (T)((e >> 16) & 0xFF); continue; }
+                    if (e & I::E_LIT) {
+                        bb >>= (e & 63); bc -= (e & 63); *out++ = (T)((e >> 16) & 0xFF);
+                        PARGZ_REFILL();
+                        e = LT[bb & LM];
+                        continue;
+                    }
                 }
                 if (e & I::E_EXC) {
                     if ((e >> 16) == 0) { bb >>= (e & 63); bc -= (e & 63); ok = true; break; }
@@ -467,6 +471,7 @@ class ChunkDecoder {
             tot = e & 63;
             bb >>= tot; bc -= tot;
             const uint32_t dist = (e >> 16) + (((uint32_t)saved & ((1u << tot) - 1)) >> ((e >> 8) & 15));
+            e = LT[bb & LM];
             // 16-bit symbols: the marker prefix makes every distance valid here, the consumer checks it when it resolves them
             if (__builtin_expect((size_t)(out - buf.p) - vstart_of<T>() < dist, 0)) { fail(R, "invalid distance too far back"); break; }
             const T *src = out - dist;
@@ -481,6 +486,7 @@ class ChunkDecoder {
             } else {
                 do { *dst++ = *src++; } while (dst < out);
             }
+            PARGZ_REFILL();
         }
         in_ = in; bb_ = bb; bc_ = bc;
         n_out = (size_t)(out - buf.p) - WIN;
