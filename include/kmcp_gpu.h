@@ -154,6 +154,45 @@ typedef void (*kmcpg_part_cb)(void *user, const kmcpg_part *part);
 int kmcpg_search_batch_cb(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *seq, const uint64_t *off,
                           uint32_t n_seqs, kmcpg_part_cb cb, void *user, kmcpg_hits *summary /* timings and totals; arrays stay valid until freed */);
 
+/* ---- the reader stage (host only, no device needed): replaces the reader loop of search.go (S:793-1000, fastx.Reader over
+ *      xopen/pgzip on one goroutine).  FASTA/Q files, plain or gzip → packed batches of queries in input order, ready for
+ *      kmcpg_search_batch / kmcpg_engine_search: paired-end files are zipped pair by pair and end with the shorter file
+ *      (S:806-867), `-g` makes one query of a whole file, its records joined as S:899-913 does.  Every input is decoded and
+ *      parsed on threads of its own (own gzip decoders: one .gz stream can be decoded by several threads). ------------------ */
+typedef struct kmcpg_reader kmcpg_reader;
+typedef struct {
+    const char *read1, *read2;        /* -1 / -2: paired-end files (both or neither) */
+    const char *const *files;         /* single-end files when read1/read2 are NULL; "-" = stdin */
+    int32_t n_files;
+    int32_t whole_file;               /* -g: every file is ONE query */
+    int32_t use_filename;             /* -G: the file name (extensions cut) is the ID of a -g query */
+    const char *query_id;             /* --query-id, or NULL */
+    int32_t k;                        /* largest k of the database: -g joins records with k-1 'N' (S:881) */
+    uint32_t batch_reads;             /* queries per batch, 0 = 262144 */
+    uint64_t batch_bytes;             /* sequence bytes per batch, 0 = 256 MB */
+    int32_t inflate_threads;          /* 0 = decided per file, 1 = sequential decoder, N = N threads on ONE .gz stream */
+    int32_t parse_threads;            /* 0, 1 = one parser thread per input, N = N threads on ONE FASTQ text */
+    void (*log)(void *user, const char *level, const char *msg);   /* the reference's log lines (S:800, 878, 920), or NULL */
+    void *log_user;
+    uint64_t inflate_chunk, inflate_cap, parse_piece;              /* test knobs, 0 = defaults */
+} kmcpg_reader_opts;
+typedef struct {
+    uint32_t n_queries, n_seqs;       /* n_seqs = n_queries, or 2 x n_queries for paired-end input */
+    const uint8_t *seq;               /* the sequences back to back */
+    const uint64_t *off;              /* n_seqs + 1 offsets into seq */
+    const char *ids;                  /* ID of query q = ids[id_off[q] .. id_off[q+1]) (ID of read 1 for pairs) */
+    const uint64_t *id_off;           /* n_queries + 1 */
+    uint64_t first_query;             /* position of the batch's first query in the whole input (Query.Idx, S:862) */
+    void *_priv;
+} kmcpg_read_batch;
+void kmcpg_default_reader_opts(kmcpg_reader_opts *o);
+int kmcpg_reader_open(const kmcpg_reader_opts *o, kmcpg_reader **out);
+/* 1: *out is the next batch (release it with kmcpg_reader_free_batch), 0: end of the input, < 0: error (kmcpg_reader_error) */
+int kmcpg_reader_next(kmcpg_reader *r, kmcpg_read_batch *out);
+void kmcpg_reader_free_batch(kmcpg_read_batch *b);
+const char *kmcpg_reader_error(const kmcpg_reader *r);
+int kmcpg_reader_close(kmcpg_reader *r);
+
 /* pinned host memory for batch buffers (so the H2D copy of kmcpg_search_batch runs at full PCIe speed) */
 int kmcpg_host_alloc(void **p, size_t bytes);
 int kmcpg_host_free(void *p);

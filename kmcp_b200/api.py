@@ -128,6 +128,21 @@ class RefcountTable(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_refs", C.c_uint32), ("_pad", C.c_uint32), ("rows", C.POINTER(RefcountRow))]
 
 
+READER_LOG = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_char_p)
+
+
+class ReaderOpts(C.Structure):
+    _fields_ = [("read1", C.c_char_p), ("read2", C.c_char_p), ("files", C.POINTER(C.c_char_p)), ("n_files", C.c_int32), ("whole_file", C.c_int32),
+                ("use_filename", C.c_int32), ("query_id", C.c_char_p), ("k", C.c_int32), ("batch_reads", C.c_uint32), ("batch_bytes", C.c_uint64),
+                ("inflate_threads", C.c_int32), ("parse_threads", C.c_int32), ("log", READER_LOG), ("log_user", C.c_void_p),
+                ("inflate_chunk", C.c_uint64), ("inflate_cap", C.c_uint64), ("parse_piece", C.c_uint64)]
+
+
+class ReadBatch(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("n_seqs", C.c_uint32), ("seq", C.POINTER(C.c_uint8)), ("off", C.POINTER(C.c_uint64)),
+                ("ids", C.POINTER(C.c_char)), ("id_off", C.POINTER(C.c_uint64)), ("first_query", C.c_uint64), ("_priv", C.c_void_p)]
+
+
 ABI_SYMBOLS = [
     "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_shard_pieces", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
     "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_free_hits", "kmcpg_host_alloc",
@@ -135,6 +150,7 @@ ABI_SYMBOLS = [
     "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search", "kmcpg_engine_search_sharded", "kmcpg_engine_search_replicas",
     "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_synth_genomes", "kmcpg_build_synth_db", "kmcpg_write_block",
     "kmcpg_default_refcount_params", "kmcpg_refcounts_create", "kmcpg_refcounts_add", "kmcpg_refcounts_get", "kmcpg_refcounts_free",
+    "kmcpg_default_reader_opts", "kmcpg_reader_open", "kmcpg_reader_next", "kmcpg_reader_free_batch", "kmcpg_reader_error", "kmcpg_reader_close",
 ]
 
 _lib = None
@@ -187,6 +203,15 @@ def load() -> C.CDLL:
     L.kmcpg_internal_merge_hits.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64), C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int]     # test hook, not part of the ABI
     L.kmcpg_internal_merge_hits.restype = None
     L.kmcpg_free_results.argtypes = [C.POINTER(Results)]
+    L.kmcpg_default_reader_opts.argtypes = [C.POINTER(ReaderOpts)]
+    L.kmcpg_default_reader_opts.restype = None
+    L.kmcpg_reader_open.argtypes = [C.POINTER(ReaderOpts), C.POINTER(vp)]
+    L.kmcpg_reader_next.argtypes = [vp, C.POINTER(ReadBatch)]
+    L.kmcpg_reader_free_batch.argtypes = [C.POINTER(ReadBatch)]
+    L.kmcpg_reader_free_batch.restype = None
+    L.kmcpg_reader_error.argtypes = [vp]
+    L.kmcpg_reader_error.restype = C.c_char_p
+    L.kmcpg_reader_close.argtypes = [vp]
     L.kmcpg_free_results.restype = None
     L.kmcpg_default_refcount_params.argtypes = [C.POINTER(RefcountParams)]
     L.kmcpg_default_refcount_params.restype = None
@@ -590,3 +615,43 @@ def refcounts_get(rc: int):
 
 def refcounts_free(rc: int):
     load().kmcpg_refcounts_free(rc)
+
+
+def read_batches(files: Sequence[str] = (), read1: Optional[str] = None, read2: Optional[str] = None, **kw):
+    """the reader stage (kmcpg_reader_*, host only): yields (first_query, ids [bytes], seq uint8 array, off uint64 array) per batch;
+    kw: whole_file, use_filename, query_id, k, batch_reads, batch_bytes, inflate_threads, parse_threads, inflate_chunk, parse_piece"""
+    L = load()
+    o = ReaderOpts()
+    L.kmcpg_default_reader_opts(C.byref(o))
+    keep = [f.encode() for f in files]
+    arr = (C.c_char_p * max(1, len(keep)))(*keep)
+    if read1 or read2:
+        o.read1 = read1.encode() if read1 else None
+        o.read2 = read2.encode() if read2 else None
+    else:
+        o.files, o.n_files = arr, len(keep)
+    for k_, v in kw.items():
+        setattr(o, k_, v.encode() if isinstance(v, str) else v)
+    h = C.c_void_p()
+    rc = L.kmcpg_reader_open(C.byref(o), C.byref(h))
+    if rc:
+        raise KmcpGpuError(rc, "kmcpg_reader_open")
+    try:
+        while True:
+            b = ReadBatch()
+            rc = L.kmcpg_reader_next(h, C.byref(b))
+            if rc == 0:
+                return
+            if rc < 0:
+                raise KmcpGpuError(rc, L.kmcpg_reader_error(h).decode())
+            nq, ns = b.n_queries, b.n_seqs
+            off = _np_from(b.off, ns + 1, 8, np.uint64)
+            id_off = _np_from(b.id_off, nq + 1, 8, np.uint64)
+            seq = _np_from(b.seq, int(off[-1]), 1, np.uint8)
+            raw = C.string_at(b.ids, int(id_off[-1])) if int(id_off[-1]) else b""
+            ids = [raw[int(id_off[q]):int(id_off[q + 1])] for q in range(nq)]
+            first = int(b.first_query)
+            L.kmcpg_reader_free_batch(C.byref(b))
+            yield first, ids, seq, off
+    finally:
+        L.kmcpg_reader_close(h)

@@ -30,13 +30,16 @@
 #include <vector>
 
 #include "../../include/kmcp_gpu.h"
-#include "fastgz.h"
-#include "pargz.h"
+#include "fastx_reader.h"
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
 
+extern "C" void kmcpg_internal_reader_stats(uint64_t *pieces, uint64_t *fallbacks);      // test hook of reader.cpp
+
 namespace {
+
+using fastx::Reader;
 
 bool g_quiet = false;
 FILE *g_log = nullptr;
@@ -141,281 +144,6 @@ void usage() {
         stderr);
 }
 
-// inflate on a thread of its own: 4 MB chunks travel through a short queue to the parsing thread, so the two mates of a
-// paired-end run (and the next file of a list) are decompressed side by side with the parsing (the reference reads through
-// pgzip/xopen readers that also decompress ahead of the parser).  The decoder is fastgz.h (about three times zlib's rate).
-struct InflateAhead {
-    static constexpr size_t CHUNK = 4u << 20, DEPTH = 4;
-    struct Chunk { std::vector<char> data; int n = 0; };
-    std::function<ssize_t(void *, size_t)> f;
-    std::thread th;
-    std::mutex mu;
-    std::condition_variable cv;
-    std::deque<Chunk *> ready, spare;
-    Chunk *cur = nullptr;
-    size_t cur_pos = 0;
-    bool stop = false, done = false;
-    void start(std::function<ssize_t(void *, size_t)> source) {
-        f = std::move(source);
-        th = std::thread([this] {
-            for (;;) {
-                Chunk *c = nullptr;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return stop || ready.size() < DEPTH; });
-                    if (stop) return;
-                    if (!spare.empty()) { c = spare.front(); spare.pop_front(); }
-                }
-                if (!c) { c = new Chunk(); c->data.resize(CHUNK); }
-                c->n = (int)f(c->data.data(), CHUNK);
-                const bool last = c->n <= 0;           // 0: end of file, < 0: error (reported by the consumer)
-                {
-                    std::lock_guard<std::mutex> lk(mu);
-                    ready.push_back(c);
-                    if (last) done = true;
-                }
-                cv.notify_all();
-                if (last) return;
-            }
-        });
-    }
-    // like gzread: bytes copied (> 0), 0 at end of file, < 0 on a read error
-    int read(char *dst, size_t cap) {
-        if (!cur || cur_pos == (size_t)cur->n) {
-            std::unique_lock<std::mutex> lk(mu);
-            if (cur) { spare.push_back(cur); cur = nullptr; cv.notify_all(); }
-            cv.wait(lk, [&] { return !ready.empty(); });
-            cur = ready.front(); ready.pop_front(); cur_pos = 0;
-            cv.notify_all();
-            if (cur->n <= 0) { const int r = cur->n; ready.push_front(cur); cur = nullptr; return r; }   // stays at the head: every later read sees it too
-        }
-        const size_t n = std::min(cap, (size_t)cur->n - cur_pos);
-        memcpy(dst, cur->data.data() + cur_pos, n);
-        cur_pos += n;
-        return (int)n;
-    }
-    void finish() {
-        { std::lock_guard<std::mutex> lk(mu); stop = true; }
-        cv.notify_all();
-        if (th.joinable()) th.join();
-        for (Chunk *c : ready) delete c;
-        for (Chunk *c : spare) delete c;
-        delete cur;
-        ready.clear(); spare.clear(); cur = nullptr;
-    }
-};
-
-int g_inflate_threads = 0;              // --inflate-threads: 0 = decide per file, 1 = always the sequential decoder
-size_t g_inflate_chunk = 2u << 20;      // --inflate-chunk: compressed bytes per task of the chunk-parallel decoder
-size_t g_inflate_cap = (size_t)256 << 20;   // --inflate-cap: most bytes a chunk may decode to before the sequential decoder takes over
-
-// offsets (base + i) of every '\n' in p[0, n): 64 bytes per step with AVX2 where the CPU has it
-#if defined(__x86_64__)
-__attribute__((target("avx2"))) void scan_newlines_avx2(const char *p, size_t n, uint32_t base, std::vector<uint32_t> &out) {
-    const __m256i nl = _mm256_set1_epi8('\n');
-    size_t i = 0;
-    for (; i + 64 <= n; i += 64) {
-        const uint32_t m0 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)(p + i)), nl));
-        const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)(p + i + 32)), nl));
-        uint64_t m = (uint64_t)m0 | ((uint64_t)m1 << 32);
-        while (m) { out.push_back(base + (uint32_t)i + (uint32_t)__builtin_ctzll(m)); m &= m - 1; }
-    }
-    for (; i < n; i++) if (p[i] == '\n') out.push_back(base + (uint32_t)i);
-}
-#endif
-void scan_newlines(const char *p, size_t n, uint32_t base, std::vector<uint32_t> &out) {
-#if defined(__x86_64__)
-    static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) { scan_newlines_avx2(p, n, base, out); return; }
-#endif
-    for (const char *q = p, *e = p + n; q < e;) {
-        const char *h = (const char *)memchr(q, '\n', (size_t)(e - q));
-        if (!h) break;
-        out.push_back(base + (uint32_t)(h - p));
-        q = h + 1;
-    }
-}
-
-struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default reader: ID = header up to first blank)
-    int fd = -1;
-    fastgz::Inflater *f = nullptr;       // gzip members are inflated, anything else passes through (as gzread does)
-    fastgz::ParallelInflater *pf = nullptr;   // big gzip files on machines with cores to spare: one stream decoded by several threads
-    std::string path;
-    std::vector<char> buf;   // block buffer: lines are found with memchr, no per-line allocation
-    size_t pos = 0, end = 0;
-    bool eof = false;
-    InflateAhead *ahead = nullptr;
-    // line ends of buf[0, end) (offsets of '\n'), kept for the four-line FASTQ fast path: found 64 bytes at a time when the
-    // buffer is filled instead of one memchr call per (short) line
-    std::vector<uint32_t> nl;
-    size_t nl_i = 0;
-    bool open(const std::string &p, bool inflate_ahead = false) {
-        path = p;
-        fd = p == "-" ? 0 : ::open(p.c_str(), O_RDONLY);
-        if (fd >= 0) {
-            const int h = fd, T = inflate_threads(h);
-            if (T >= 2) pf = new fastgz::ParallelInflater(h, T, g_inflate_chunk, g_inflate_cap);
-            else f = sequential(h);
-        }
-        buf.resize(16u << 20);
-        pos = end = 0; eof = false; raw_total = 0;
-        nl.clear(); nl_i = 0;
-        if (fd >= 0 && inflate_ahead) { ahead = new InflateAhead(); ahead->start([this](void *dst, size_t n) { return raw_read(dst, n); }); }
-        return fd >= 0;
-    }
-    void close() {
-        if (ahead) { ahead->finish(); delete ahead; ahead = nullptr; }
-        delete f; delete pf;
-        f = nullptr; pf = nullptr;
-        if (fd > 0) ::close(fd);
-        fd = -1;
-    }
-    static fastgz::Inflater *sequential(int h) {
-        return new fastgz::Inflater([h](void *dst, size_t n) -> ssize_t {
-            for (;;) { const ssize_t r = ::read(h, dst, n); if (r >= 0 || errno != EINTR) return r; }
-        });
-    }
-    uint64_t raw_total = 0;              // decoded bytes handed out so far
-    ssize_t raw_read(void *dst, size_t n) {
-        if (pf) {
-            const ssize_t r = pf->read(dst, n);
-            if (r >= 0 || !pf->too_big()) { if (r > 0) raw_total += (uint64_t)r; return r; }
-            // a stretch that expands beyond what the chunk-parallel decoder keeps in memory (compression ratios in the hundreds):
-            // the sequential decoder streams; it starts over and drops what was handed out already
-            delete pf; pf = nullptr;
-            if (lseek(fd, 0, SEEK_SET) != 0) return -1;
-            f = sequential(fd);
-            std::vector<char> scratch(4u << 20);
-            for (uint64_t left = raw_total; left;) {
-                const ssize_t k = f->read(scratch.data(), (size_t)std::min<uint64_t>(left, scratch.size()));
-                if (k <= 0) return -1;
-                left -= (uint64_t)k;
-            }
-        }
-        const ssize_t r = f->read(dst, n);
-        if (r > 0) raw_total += (uint64_t)r;
-        return r;
-    }
-    // the decoded text itself (for callers that cut it into records themselves); like read(2)
-    int read_text(char *dst, size_t n) { n = std::min<size_t>(n, 1u << 30); return ahead ? ahead->read(dst, n) : (int)raw_read(dst, n); }
-    const char *error() const { return pf ? pf->error() : (f ? f->error() : ""); }
-    // worker threads for one input: --inflate-threads N, or by itself on big machines for big seekable gzip files
-    static int inflate_threads(int h) {
-        if (g_inflate_threads == 1 || !fastgz::ParallelInflater::usable(h)) return 1;
-        if (g_inflate_threads > 1) return g_inflate_threads;
-        struct stat st;
-        if (fstat(h, &st) != 0 || st.st_size < (32 << 20)) return 1;
-        const int hw = (int)std::thread::hardware_concurrency();
-        const int T = std::min(8, hw / 8);              // the chunk-parallel decoder does ~1.7x the work: it pays from 4 threads on
-        return T >= 4 ? T : 1;
-    }
-    bool fill() {            // keeps [pos, end), reads more behind it; false at end of file
-        if (eof) return false;
-        if (pos) {
-            memmove(buf.data(), buf.data() + pos, end - pos);
-            size_t w = 0;                                  // line ends behind pos move with the bytes
-            for (size_t i = nl_i; i < nl.size(); i++) if (nl[i] >= pos) nl[w++] = nl[i] - (uint32_t)pos;
-            nl.resize(w); nl_i = 0;
-            end -= pos; pos = 0;
-        }
-        if (end == buf.size()) buf.resize(buf.size() * 2);
-        const size_t room = std::min<size_t>(buf.size() - end, 1u << 30);
-        const int r = ahead ? ahead->read(buf.data() + end, room) : (int)raw_read(buf.data() + end, room);
-        if (r < 0) die("read error in %s: %s", path.c_str(), pf ? pf->error() : f->error());
-        if (r == 0) { eof = true; return false; }
-        if (end + (size_t)r < ((size_t)1 << 32)) scan_newlines(buf.data() + end, (size_t)r, (uint32_t)end, nl);
-        else { nl.clear(); nl_i = 0; fast_ok = false; }          // a single line of gigabytes: offsets no longer fit
-        end += (size_t)r;
-        return true;
-    }
-    bool fast_ok = true;
-    // A FASTQ record written as exactly four lines (header, sequence, '+', quality of the same length) taken from the line-end
-    // table: the ID is returned as a range of the buffer (valid until the next call), the sequence is appended to dst.
-    // false = not such a record here (FASTA, wrapped FASTQ, blank lines, the unterminated tail of a file): the general
-    // reader below takes it from the same position.
-    template <class V>
-    bool next_four_line(const char *&idp, size_t &idn, V &dst) {
-        if (!fast_ok) return false;
-        if (pos == end && !fill()) return false;
-        if (buf[pos] != '@') return false;                     // FASTA (or a blank line): do not wait for four lines of a genome
-        for (;;) {
-            while (nl_i < nl.size() && nl[nl_i] < pos) nl_i++;
-            if (nl.size() - nl_i >= 4) break;
-            if (!fill()) return false;
-        }
-        const char *b = buf.data();
-        const size_t h0 = pos, s0 = (size_t)nl[nl_i] + 1, p0 = (size_t)nl[nl_i + 1] + 1, q0 = (size_t)nl[nl_i + 2] + 1;
-        size_t h1 = nl[nl_i], s1 = nl[nl_i + 1], q1 = nl[nl_i + 3];
-        if (b[h0] != '@' || b[p0] != '+') return false;          // an empty line holds its own '\n' here, so both tests also refuse blank lines
-        while (h1 > h0 && b[h1 - 1] == '\r') h1--;
-        while (s1 > s0 && b[s1 - 1] == '\r') s1--;
-        while (q1 > q0 && b[q1 - 1] == '\r') q1--;
-        if (q1 - q0 != s1 - s0) return false;
-        size_t e = h0 + 1;
-        while (e < h1 && b[e] != ' ' && b[e] != '\t') e++;
-        idp = b + h0 + 1; idn = e - h0 - 1;
-        dst.insert(dst.end(), b + s0, b + s1);
-        pos = (size_t)nl[nl_i + 3] + 1;
-        nl_i += 4;
-        return true;
-    }
-    // next line without its end-of-line bytes; the pointer is valid until the next call
-    bool line(const char *&sp, size_t &n) {
-        size_t scanned = pos;
-        for (;;) {
-            const char *eol = (const char *)memchr(buf.data() + scanned, '\n', end - scanned);
-            if (eol) { sp = buf.data() + pos; n = (size_t)(eol - sp); pos = (size_t)(eol - buf.data()) + 1; break; }
-            const size_t had = end - pos;
-            if (!fill()) { if (pos == end) return false; sp = buf.data() + pos; n = end - pos; pos = end; break; }
-            scanned = pos + had;
-        }
-        while (n && (sp[n - 1] == '\r' || sp[n - 1] == '\n')) n--;
-        return true;
-    }
-    int peek() {             // first byte of the next line, -1 at end of file
-        if (pos == end && !fill()) return -1;
-        return (unsigned char)buf[pos];
-    }
-    bool getline(std::string &out) {
-        const char *sp; size_t n;
-        if (!line(sp, n)) return false;
-        out.assign(sp, n);
-        return true;
-    }
-    // one record: ID into `id`, sequence bytes APPENDED to `dst`; false at end of file
-    template <class V>
-    bool next(std::string &id, V &dst) {
-        const char *l; size_t n;
-        if (next_four_line(l, n, dst)) { id.assign(l, n); return true; }
-        do { if (!line(l, n)) return false; } while (n == 0);
-        if (l[0] != '>' && l[0] != '@') die("invalid FASTA/Q record in %s", path.c_str());
-        const bool fq = l[0] == '@';
-        size_t e = 1;
-        while (e < n && l[e] != ' ' && l[e] != '\t') e++;
-        id.assign(l + 1, e - 1);
-        if (fq) {
-            if (!line(l, n)) return true;                // first line after the header is sequence
-            dst.insert(dst.end(), l, l + n);
-            size_t slen = n;
-            for (;;) {                                   // more sequence lines up to the '+' line (multi-line FASTQ)
-                if (!line(l, n)) return true;
-                if (n && l[0] == '+') break;
-                dst.insert(dst.end(), l, l + n); slen += n;
-            }
-            size_t got = 0;
-            while (got < slen && line(l, n)) got += n;
-        } else {
-            for (;;) {
-                const int c = peek();
-                if (c < 0 || c == '>') break;
-                if (!line(l, n)) break;
-                dst.insert(dst.end(), l, l + n);
-            }
-        }
-        return true;
-    }
-};
-
 // one complete gzip member for a block of text (concatenated members are a valid .gz stream, as pgzip writes them)
 std::string gz_member(const char *data, size_t n, int level) {
     z_stream zs;
@@ -430,6 +158,7 @@ std::string gz_member(const char *data, size_t n, int level) {
     return out;
 }
 
+fastx::Tuning g_tune;             // --inflate-threads, --parse-threads and the test knobs behind them
 int g_compression_level = 4;      // --compression-level (the reference's pgzip default is a fast level as well)
 
 // text → file.  ".gz" output is compressed in 1 MB blocks by several threads (independent gzip members, written in order) and
@@ -495,399 +224,50 @@ struct Writer {
 };
 
 
-std::string trim_ext(const std::string &file) {     // filepathTrimExtension: strip dir, .gz/.xz/.zst/.bz2, then one extension
-    std::string b = file.substr(file.find_last_of('/') == std::string::npos ? 0 : file.find_last_of('/') + 1);
-    for (const char *z : {".gz", ".xz", ".zst", ".bz2"}) {
-        size_t n = strlen(z);
-        if (b.size() > n && b.compare(b.size() - n, n, z) == 0) { b.resize(b.size() - n); break; }
-    }
-    size_t dot = b.find_last_of('.');
-    if (dot != std::string::npos && dot > 0) b.resize(dot);
-    return b;
-}
-
-// ---- reader stage: files → packed batches ---------------------------------------------------------------------------------
-// what the engine call takes: the sequences of the batch back to back + offsets (two per query for paired-end input), the IDs in
-// one arena (no allocation per read)
+// a batch from the library's reader stage (kmcpg_reader_*), released with the object
 struct Batch {
-    std::vector<char> id_buf;
-    std::vector<uint64_t> id_off{0};
-    std::vector<uint8_t> seq;
-    std::vector<uint64_t> off{0};
-    uint64_t base = 0;
-    size_t n_ids() const { return id_off.size() - 1; }
-    void add_id(const char *p, size_t n) { id_buf.insert(id_buf.end(), p, p + n); id_off.push_back(id_buf.size()); }
-    void add_id(const std::string &id) { add_id(id.data(), id.size()); }
+    kmcpg_read_batch b;
+    Batch() { memset(&b, 0, sizeof(b)); }
+    Batch(const Batch &) = delete;
+    Batch &operator=(const Batch &) = delete;
+    ~Batch() { kmcpg_reader_free_batch(&b); }
+    size_t n_ids() const { return b.n_queries; }
+    const char *id(size_t q) const { return b.ids + b.id_off[q]; }
+    size_t id_len(size_t q) const { return (size_t)(b.id_off[q + 1] - b.id_off[q]); }
 };
 
-int g_parse_threads = 0;                // --parse-threads: 0 = decide per file, 1 = one parser thread per input
-size_t g_parse_piece = 8u << 20;        // --parse-piece: bytes of text per task of the parallel parser
-std::atomic<uint64_t> g_stat_pieces{0}, g_stat_fallbacks{0};      // pieces parsed by the workers / files handed back to the general reader
-
-// One input file parsed into blocks of records (IDs and sequences back to back) ahead of the thread that builds the batches:
-// with paired-end input the two mates are inflated AND parsed side by side, and the batch builder only copies.
-//
-// Two ways to get the blocks.  The plain one is a thread that calls the reader record by record.  For regular files on machines
-// with cores to spare the text itself is cut into pieces of ~8 MB at record boundaries (a line that starts with '@' whose second
-// next line starts with '+' — a quality line that starts with '@' is followed by a header and a sequence, never by a '+' line) and
-// the pieces are parsed by several workers.  A worker accepts a piece only if EVERY record in it is written as exactly four lines
-// ('@' header, sequence, '+' line, quality of the same length); such a piece starts and ends on record boundaries and parses to
-// what the general reader returns for it.  The first piece that is anything else (FASTA, wrapped FASTQ, blank lines, a truncated
-// last record) ends the parallel mode: the file is opened again, the records already handed out are skipped, and the plain
-// thread carries on — the result is the general reader's in every case.
-struct RecordStream {
-    static constexpr size_t BLOCK_RECS = 1u << 15, BLOCK_BYTES = 64u << 20, DEPTH = 4;
-    static constexpr size_t PIECE_MAX = 256u << 20;
-    struct Block {
-        std::vector<char> ids;
-        std::vector<uint8_t> seq;
-        std::vector<uint32_t> id_end, seq_end;       // ends of record i inside ids / seq
-        bool bad = false;                            // parallel mode: the piece was not made of four-line records
-        size_t n() const { return id_end.size(); }
-        void clear() { ids.clear(); seq.clear(); id_end.clear(); seq_end.clear(); bad = false; }
-    };
-    struct Text { std::vector<char> d; size_t n = 0; };
-    Reader r;
-    std::string path;
-    std::thread th;                                  // the plain parser, or the cutter of the parallel mode
-    std::vector<std::thread> workers;
-    std::mutex mu;
-    std::condition_variable cv;
-    std::deque<Block *> ready, spare;
-    bool stop = false, done = false;
-    Block *cur = nullptr;
-    size_t i = 0;
-    uint64_t delivered = 0;                          // records handed out so far
-    // parallel mode
-    bool par = false;
-    std::deque<std::pair<uint64_t, Text *>> work_q;  // pieces waiting for a worker
-    std::deque<Text *> text_pool;
-    std::map<uint64_t, Block *> parsed;              // finished pieces by number
-    uint64_t cut_n = 0, next_n = 0;                  // pieces cut / pieces handed out
-    size_t max_inflight = 8;
-
-    static int parse_threads(const std::string &p) {
-        if (g_parse_threads == 1 || p == "-") return 1;
-        struct stat st;
-        if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return 1;
-        // opt-in until it has been timed on the GPU box: on the 8 vCPUs it was written on the extra copies eat the gain
-        return g_parse_threads > 1 ? g_parse_threads : 1;
-    }
-    bool open(const std::string &p) {
-        path = p;
-        if (!r.open(p, true)) return false;
-        const int P = parse_threads(p);
-        if (P >= 2) start_parallel(P); else start_plain(0);
-        return true;
-    }
-    void start_plain(uint64_t skip) {
-        th = std::thread([this, skip] {
-            std::string id;
-            std::vector<uint8_t> scratch;
-            for (uint64_t k = 0; k < skip; k++) { scratch.clear(); if (!r.next(id, scratch)) break; }     // handed out before the restart
-            for (;;) {
-                Block *b = nullptr;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return stop || ready.size() < DEPTH; });
-                    if (stop) return;
-                    if (!spare.empty()) { b = spare.front(); spare.pop_front(); }
-                }
-                if (!b) b = new Block();
-                b->clear();
-                bool more = true;
-                while (b->n() < BLOCK_RECS && b->seq.size() < BLOCK_BYTES) {
-                    if (!r.next(id, b->seq)) { more = false; break; }
-                    b->ids.insert(b->ids.end(), id.begin(), id.end());
-                    b->id_end.push_back((uint32_t)b->ids.size());
-                    b->seq_end.push_back((uint32_t)b->seq.size());
-                }
-                std::lock_guard<std::mutex> lk(mu);
-                if (b->n()) ready.push_back(b); else spare.push_back(b);
-                if (!more) done = true;
-                cv.notify_all();
-                if (!more) return;
-            }
-        });
-    }
-
-    // ---- parallel mode ------------------------------------------------------------------------------------------------------
-    // where to cut d[0, n): the start of the last line that begins a record and has its two following line starts inside the
-    // text; 0 = no such line
-    static size_t cut_point(const char *d, size_t n) {
-        size_t e = n;                                 // lines are looked at from the end: [ls, e) is the current one
-        size_t s1 = 0, s2 = 0;                        // starts of the next line and the one after it
-        int have = 0;
-        while (e > 0) {
-            const char *q = e >= 2 ? (const char *)memrchr(d, '\n', e - 1) : nullptr;      // the line end in front of this line
-            const size_t ls = q ? (size_t)(q - d) + 1 : 0;
-            if (have >= 2 && d[ls] == '@' && d[s2] == '+' && ls > 0) return ls;
-            s2 = s1; s1 = ls; have++;
-            if (n - ls > (4u << 20) && have > 64) break;          // far from the end and still nothing: not this kind of file
-            e = ls ? ls : 0;
-            if (!ls) break;
-        }
-        return 0;
-    }
-    // a piece → records, or bad
-    static void parse_piece(const Text &t, Block &b, std::vector<uint32_t> &nl) {
-        b.clear();
-        nl.clear();
-        scan_newlines(t.d.data(), t.n, 0, nl);
-        const char *d = t.d.data();
-        if (nl.empty() || nl.size() % 4 != 0 || nl.back() + 1 != t.n) { b.bad = true; return; }
-        b.id_end.reserve(nl.size() / 4); b.seq_end.reserve(nl.size() / 4);
-        b.seq.reserve(t.n / 2); b.ids.reserve(t.n / 8);
-        size_t h0 = 0;
-        for (size_t k = 0; k < nl.size(); k += 4) {
-            const size_t s0 = (size_t)nl[k] + 1, p0 = (size_t)nl[k + 1] + 1, q0 = (size_t)nl[k + 2] + 1;
-            size_t h1 = nl[k], s1 = nl[k + 1], q1 = nl[k + 3];
-            if (d[h0] != '@' || d[p0] != '+') { b.bad = true; return; }
-            while (h1 > h0 && d[h1 - 1] == '\r') h1--;
-            while (s1 > s0 && d[s1 - 1] == '\r') s1--;
-            while (q1 > q0 && d[q1 - 1] == '\r') q1--;
-            if (q1 - q0 != s1 - s0) { b.bad = true; return; }
-            size_t e = h0 + 1;
-            while (e < h1 && d[e] != ' ' && d[e] != '\t') e++;
-            b.ids.insert(b.ids.end(), d + h0 + 1, d + e);
-            b.seq.insert(b.seq.end(), (const uint8_t *)d + s0, (const uint8_t *)d + s1);
-            b.id_end.push_back((uint32_t)b.ids.size());
-            b.seq_end.push_back((uint32_t)b.seq.size());
-            h0 = (size_t)nl[k + 3] + 1;
-        }
-    }
-    void start_parallel(int P) {
-        par = true;
-        max_inflight = (size_t)P * 2 + 2;
-        for (int w = 0; w < P; w++)
-            workers.emplace_back([this] {
-                std::vector<uint32_t> nl;
-                for (;;) {
-                    std::pair<uint64_t, Text *> job;
-                    Block *b = nullptr;
-                    {
-                        std::unique_lock<std::mutex> lk(mu);
-                        cv.wait(lk, [&] { return stop || !work_q.empty(); });
-                        if (stop) return;
-                        job = work_q.front(); work_q.pop_front();
-                        if (!spare.empty()) { b = spare.front(); spare.pop_front(); }
-                    }
-                    if (!b) b = new Block();
-                    if (job.second->n == 0) { b->clear(); b->bad = true; }        // the cutter found no record boundary
-                    else parse_piece(*job.second, *b, nl);
-                    std::lock_guard<std::mutex> lk(mu);
-                    parsed[job.first] = b;
-                    text_pool.push_back(job.second);
-                    cv.notify_all();
-                }
-            });
-        th = std::thread([this] {
-            const size_t PIECE = std::max<size_t>(g_parse_piece, 64);
-            std::vector<char> carry;
-            bool eof = false;
-            auto give = [&](Text *t) {
-                std::lock_guard<std::mutex> lk(mu);
-                work_q.push_back({cut_n++, t});
-                cv.notify_all();
-            };
-            while (!eof) {
-                Text *t = nullptr;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return stop || cut_n - next_n < max_inflight; });
-                    if (stop) return;
-                    if (!text_pool.empty()) { t = text_pool.front(); text_pool.pop_front(); }
-                }
-                if (!t) t = new Text();
-                if (t->d.size() < PIECE + (1u << 20)) t->d.resize(PIECE + (1u << 20));
-                t->n = carry.size();
-                if (t->n > t->d.size()) t->d.resize(t->n + PIECE);
-                if (t->n) memcpy(t->d.data(), carry.data(), t->n);
-                carry.clear();
-                size_t want = PIECE;
-                size_t cut = 0;
-                for (;;) {
-                    while (t->n < want) {                             // fill up to the piece size
-                        if (t->d.size() < want + 1) t->d.resize(want + 1);
-                        const int got = r.read_text(t->d.data() + t->n, want - t->n);
-                        if (got < 0) die("read error in %s: %s", path.c_str(), r.error());
-                        if (got == 0) { eof = true; break; }
-                        t->n += (size_t)got;
-                    }
-                    if (eof) {                                        // the rest of the file is the last piece
-                        if (t->n && t->d[t->n - 1] != '\n') t->d[t->n++] = '\n';
-                        cut = t->n;
-                        break;
-                    }
-                    cut = cut_point(t->d.data(), t->n);
-                    if (cut) break;
-                    if (want >= PIECE_MAX) { cut = 0; break; }        // no record boundary in 256 MB of text
-                    want *= 2;                                        // very long records: look at more text
-                }
-                if (!eof && !cut) { t->n = 0; give(t); break; }      // an empty piece tells the consumer to fall back
-                if (eof && !t->n) {
-                    std::lock_guard<std::mutex> lk(mu);
-                    text_pool.push_back(t);
-                    break;
-                }
-                carry.assign(t->d.data() + cut, t->d.data() + t->n);
-                t->n = cut;
-                give(t);
-            }
-            std::lock_guard<std::mutex> lk(mu);
-            done = true;
-            cv.notify_all();
-        });
-    }
-    void stop_threads() {
-        { std::lock_guard<std::mutex> lk(mu); stop = true; }
-        cv.notify_all();
-        if (th.joinable()) th.join();
-        for (auto &w : workers) w.join();
-        workers.clear();
-        for (auto &j : work_q) delete j.second;
-        for (Text *t : text_pool) delete t;
-        for (auto &kv : parsed) delete kv.second;
-        work_q.clear(); text_pool.clear(); parsed.clear();
-    }
-
-    // the next block of records, nullptr at the end of the file; the previous one goes back to the parser
-    Block *next_block() {
-        for (;;) {
-            std::unique_lock<std::mutex> lk(mu);
-            if (cur) { spare.push_back(cur); cur = nullptr; cv.notify_all(); }
-            if (!par) {
-                cv.wait(lk, [&] { return !ready.empty() || done; });
-                if (ready.empty()) return nullptr;
-                cur = ready.front(); ready.pop_front(); i = 0;
-                delivered += cur->n();
-                cv.notify_all();
-                return cur;
-            }
-            cv.wait(lk, [&] { return parsed.count(next_n) || (done && next_n == cut_n); });
-            auto it = parsed.find(next_n);
-            if (it == parsed.end()) return nullptr;
-            Block *b = it->second;
-            parsed.erase(it);
-            next_n++;
-            cv.notify_all();
-            if (!b->bad) {
-                g_stat_pieces++;
-                if (!b->n()) { spare.push_back(b); continue; }
-                cur = b; i = 0;
-                delivered += b->n();
-                return cur;
-            }
-            // not (only) four-line records: the general reader takes over behind the records handed out so far
-            delete b;
-            g_stat_fallbacks++;
-            lk.unlock();
-            stop_threads();
-            r.close();
-            if (!r.open(path, true)) die("%s: no such file", path.c_str());
-            { std::lock_guard<std::mutex> g(mu); stop = false; done = false; par = false; }
-            start_plain(delivered);
-        }
-    }
-    // record by record: false at the end of the file
-    bool next(const char *&id, size_t &idn, const uint8_t *&sq, size_t &sn) {
-        if (!cur || i == cur->n()) { if (!next_block()) return false; }
-        const size_t a = i ? cur->id_end[i - 1] : 0, c = i ? cur->seq_end[i - 1] : 0;
-        id = cur->ids.data() + a; idn = cur->id_end[i] - a;
-        sq = cur->seq.data() + c; sn = cur->seq_end[i] - c;
-        i++;
-        return true;
-    }
-    void close() {
-        stop_threads();
-        for (Block *b : ready) delete b;
-        for (Block *b : spare) delete b;
-        delete cur;
-        ready.clear(); spare.clear(); cur = nullptr;
-        r.close();
-    }
-};
-
-struct ReaderConfig {
+struct ReaderSetup {
     bool paired = false, whole_file = false, use_filename = false;
     std::string read1, read2, query_id;
     std::vector<std::string> files;
-    size_t batch_reads = 1u << 18, batch_bytes = 256u << 20;
+    size_t batch_reads = 0, batch_bytes = 0;
     int kmax = 21;
 };
-
-// S:793-1000: the input files as batches, in order; `emit` takes the batch over
-void read_batches(const ReaderConfig &c, const std::function<void(Batch *)> &emit_fn) {
-    Batch *cur = new Batch();
-    auto emit = [&]() {
-        if (cur->n_ids() == 0) return;
-        if (cur->seq.empty()) cur->seq.push_back(0);
-        emit_fn(cur);
-        cur = new Batch();
-    };
-    auto full = [&]() { return cur->n_ids() >= c.batch_reads || cur->seq.size() >= c.batch_bytes; };
-    if (c.paired) {
-        RecordStream r1, r2;
-        if (!r1.open(c.read1)) die("%s: no such file", c.read1.c_str());
-        if (!r2.open(c.read2)) die("%s: no such file", c.read2.c_str());
-        logf("INFO", "reading from paired-end files: %s, %s", c.read1.c_str(), c.read2.c_str());
-        const char *id1, *id2; const uint8_t *s1, *s2; size_t n1, n2, l1, l2;
-        for (;;) {                                                    // S:806-867: ID of read1; ends with the shorter file
-            if (!r1.next(id1, n1, s1, l1)) break;
-            if (!r2.next(id2, n2, s2, l2)) break;
-            cur->add_id(id1, n1);
-            cur->seq.insert(cur->seq.end(), s1, s1 + l1); cur->off.push_back(cur->seq.size());
-            cur->seq.insert(cur->seq.end(), s2, s2 + l2); cur->off.push_back(cur->seq.size());
-            if (full()) emit();
-        }
-        r1.close(); r2.close();
-    } else {
-        std::string id;
-        for (auto &file : c.files) {
-            logf("INFO", "reading sequence file: %s", file.c_str());
-            if (c.whole_file) {                                       // S:885-937 (the N-run follows every record after the second)
-                Reader r;
-                if (!r.open(file, true)) die("%s: no such file", file.c_str());
-                std::string qid;
-                bool first = true;
-                const size_t mark = cur->seq.size();
-                while (r.next(id, cur->seq)) {
-                    if (first) { qid = c.use_filename ? trim_ext(file) : (!c.query_id.empty() ? c.query_id : id); first = false; }
-                    else cur->seq.insert(cur->seq.end(), (size_t)(c.kmax - 1), (uint8_t)'N');
-                }
-                r.close();
-                if (first) { logf("WARN", "no valid sequences in file: %s", file.c_str()); cur->seq.resize(mark); continue; }
-                cur->add_id(qid); cur->off.push_back(cur->seq.size());
-                if (cur->seq.size() >= c.batch_bytes) emit();
-            } else {
-                RecordStream rs;
-                if (!rs.open(file)) die("%s: no such file", file.c_str());
-                bool any = false;
-                while (RecordStream::Block *b = rs.next_block()) {   // whole blocks are appended: three copies and two offset loops
-                    any = true;
-                    size_t at = 0;                                    // records of the block already taken
-                    while (at < b->n()) {
-                        const size_t room = c.batch_reads > cur->n_ids() ? c.batch_reads - cur->n_ids() : 1;
-                        const size_t take = std::min(room, b->n() - at);
-                        const size_t i0 = at ? b->id_end[at - 1] : 0, i1 = b->id_end[at + take - 1];
-                        const size_t s0 = at ? b->seq_end[at - 1] : 0, s1 = b->seq_end[at + take - 1];
-                        const uint64_t ib = cur->id_buf.size() - i0, sb = cur->seq.size() - s0;
-                        cur->id_buf.insert(cur->id_buf.end(), b->ids.begin() + (ptrdiff_t)i0, b->ids.begin() + (ptrdiff_t)i1);
-                        cur->seq.insert(cur->seq.end(), b->seq.begin() + (ptrdiff_t)s0, b->seq.begin() + (ptrdiff_t)s1);
-                        for (size_t k = at; k < at + take; k++) { cur->id_off.push_back(ib + b->id_end[k]); cur->off.push_back(sb + b->seq_end[k]); }
-                        at += take;
-                        if (full()) emit();
-                    }
-                }
-                rs.close();
-                if (!any) logf("WARN", "no valid sequences in file: %s", file.c_str());
-            }
-        }
+// S:793-1000 through the library: every batch of the input, in order, to `take` (which owns it)
+void read_batches(const ReaderSetup &c, const std::function<void(Batch *)> &take) {
+    kmcpg_reader_opts ro;
+    kmcpg_default_reader_opts(&ro);
+    std::vector<const char *> fl;
+    for (auto &f : c.files) fl.push_back(f.c_str());
+    if (c.paired) { ro.read1 = c.read1.c_str(); ro.read2 = c.read2.c_str(); }
+    else { ro.files = fl.data(); ro.n_files = (int32_t)fl.size(); }
+    ro.whole_file = c.whole_file; ro.use_filename = c.use_filename; ro.query_id = c.query_id.empty() ? nullptr : c.query_id.c_str();
+    ro.k = c.kmax; ro.batch_reads = (uint32_t)c.batch_reads; ro.batch_bytes = c.batch_bytes;
+    ro.inflate_threads = g_tune.inflate_threads; ro.parse_threads = g_tune.parse_threads;
+    ro.inflate_chunk = g_tune.inflate_chunk; ro.inflate_cap = g_tune.inflate_cap; ro.parse_piece = g_tune.parse_piece;
+    ro.log = [](void *, const char *level, const char *msg) { logf(level, "%s", msg); };
+    kmcpg_reader *rd = nullptr;
+    if (kmcpg_reader_open(&ro, &rd) != KMCPG_OK) die("cannot start the reader: invalid input files");
+    for (;;) {
+        Batch *bt = new Batch();
+        const int rc = kmcpg_reader_next(rd, &bt->b);
+        if (rc == 1) { take(bt); continue; }
+        delete bt;
+        if (rc < 0) die("%s", kmcpg_reader_error(rd));
+        break;
     }
-    emit();
-    delete cur;
+    kmcpg_reader_close(rd);
 }
-
 
 void load_kv(const std::string &path, std::map<std::string, std::string> &m) {
     Reader r;
@@ -985,11 +365,11 @@ int parse_main(int argc, char **argv) {
         else if (a == "--batch-reads" && i + 1 < argc) batch_reads = (size_t)atol(argv[++i]);
         else if (a == "-g") whole = true;
         else if (a == "--count") count_only = true;          // the reader's rate alone: records and bases to stderr, no per-record output
-        else if (a == "--inflate-threads" && i + 1 < argc) g_inflate_threads = atoi(argv[++i]);
-        else if (a == "--parse-threads" && i + 1 < argc) g_parse_threads = atoi(argv[++i]);
-        else if (a == "--parse-piece" && i + 1 < argc) g_parse_piece = (size_t)atol(argv[++i]);
-        else if (a == "--inflate-chunk" && i + 1 < argc) g_inflate_chunk = (size_t)atol(argv[++i]);
-        else if (a == "--inflate-cap" && i + 1 < argc) g_inflate_cap = (size_t)atol(argv[++i]);
+        else if (a == "--inflate-threads" && i + 1 < argc) g_tune.inflate_threads = atoi(argv[++i]);
+        else if (a == "--parse-threads" && i + 1 < argc) g_tune.parse_threads = atoi(argv[++i]);
+        else if (a == "--parse-piece" && i + 1 < argc) g_tune.parse_piece = (size_t)atol(argv[++i]);
+        else if (a == "--inflate-chunk" && i + 1 < argc) g_tune.inflate_chunk = (size_t)atol(argv[++i]);
+        else if (a == "--inflate-cap" && i + 1 < argc) g_tune.inflate_cap = (size_t)atol(argv[++i]);
         else if (a == "-1" && i + 1 < argc) r1 = argv[++i];
         else if (a == "-2" && i + 1 < argc) r2 = argv[++i];
         else files.push_back(a);
@@ -1005,7 +385,7 @@ int parse_main(int argc, char **argv) {
     };
     if (batches) {
         // one line per query of every batch: id, then length and CRC-32 of each of its sequences; "# batch" lines in between
-        ReaderConfig rc;
+        ReaderSetup rc;
         rc.paired = !r1.empty() && !r2.empty(); rc.read1 = r1; rc.read2 = r2; rc.files = files; rc.whole_file = whole; rc.batch_reads = batch_reads;
         const auto t0 = std::chrono::steady_clock::now();
         uint64_t nq = 0;
@@ -1014,10 +394,10 @@ int parse_main(int argc, char **argv) {
             if (!count_only) {
                 out += "# batch of " + std::to_string(bt->n_ids()) + "\n";
                 for (size_t q = 0; q < bt->n_ids(); q++) {
-                    out.append(bt->id_buf.data() + bt->id_off[q], (size_t)(bt->id_off[q + 1] - bt->id_off[q]));
+                    out.append(bt->id(q), bt->id_len(q));
                     for (size_t m = 0; m < step; m++) {
-                        const uint64_t a = bt->off[q * step + m], b = bt->off[q * step + m + 1];
-                        int n = snprintf(line, sizeof(line), "\t%llu\t%08lx", (unsigned long long)(b - a), (unsigned long)crc32(0L, bt->seq.data() + a, (uInt)(b - a)));
+                        const uint64_t a = bt->b.off[q * step + m], b = bt->b.off[q * step + m + 1];
+                        int n = snprintf(line, sizeof(line), "\t%llu\t%08lx", (unsigned long long)(b - a), (unsigned long)crc32(0L, bt->b.seq + a, (uInt)(b - a)));
                         out.append(line, (size_t)n);
                     }
                     out += '\n';
@@ -1028,9 +408,11 @@ int parse_main(int argc, char **argv) {
             delete bt;
         });
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        uint64_t st[2] = {0, 0};
+        kmcpg_internal_reader_stats(&st[0], &st[1]);
         if (count_only)
             fprintf(stderr, "%llu queries, %.3f s, %.2f M queries/s (pieces parsed in parallel: %llu, files handed back to the general reader: %llu)\n",
-                    (unsigned long long)nq, dt, nq / dt / 1e6, (unsigned long long)g_stat_pieces.load(), (unsigned long long)g_stat_fallbacks.load());
+                    (unsigned long long)nq, dt, nq / dt / 1e6, (unsigned long long)st[0], (unsigned long long)st[1]);
         return 0;
     }
     if (count_only) {
@@ -1040,7 +422,7 @@ int parse_main(int argc, char **argv) {
         std::vector<uint64_t> id_off, off;
         for (auto &f : files) {
             Reader r;
-            if (!r.open(f, ahead)) die("%s: no such file", f.c_str());
+            if (!r.open(f, ahead, g_tune)) die("%s: no such file", f.c_str());
             while (r.next(id, seq)) {
                 n++; ids.insert(ids.end(), id.begin(), id.end()); id_off.push_back(ids.size()); off.push_back(seq.size());
                 if (off.size() >= (1u << 18)) { bases += seq.size(); seq.clear(); ids.clear(); id_off.clear(); off.clear(); }
@@ -1054,7 +436,7 @@ int parse_main(int argc, char **argv) {
     }
     if (!r1.empty() && !r2.empty()) {
         Reader a, b;
-        if (!a.open(r1, ahead) || !b.open(r2, ahead)) die("no such file");
+        if (!a.open(r1, ahead, g_tune) || !b.open(r2, ahead, g_tune)) die("no such file");
         for (;;) {
             if (!a.next(id, seq)) break;
             emit();
@@ -1065,7 +447,7 @@ int parse_main(int argc, char **argv) {
     } else {
         for (auto &f : files) {
             Reader r;
-            if (!r.open(f, ahead)) die("%s: no such file", f.c_str());
+            if (!r.open(f, ahead, g_tune)) die("%s: no such file", f.c_str());
             while (r.next(id, seq)) emit();
             r.close();
         }
@@ -1087,7 +469,7 @@ int gunzip_main(int argc, char **argv) {
         else if (a == "--chunk" && i + 1 < argc) chunk = (size_t)atol(argv[++i]);
         else if (a == "--threads" && i + 1 < argc) threads = atoi(argv[++i]);          // > 0: the chunk-parallel decoder (pargz.h)
         else if (a == "--par-chunk" && i + 1 < argc) par_chunk = (size_t)atol(argv[++i]);
-        else if (a == "--par-cap" && i + 1 < argc) g_inflate_cap = (size_t)atol(argv[++i]);
+        else if (a == "--par-cap" && i + 1 < argc) g_tune.inflate_cap = (size_t)atol(argv[++i]);
         else if (a == "--stats") stats = true;
         else file = a;
     }
@@ -1096,7 +478,7 @@ int gunzip_main(int argc, char **argv) {
     if (fd < 0) die("%s: no such file", file.c_str());
     if (threads > 0) {
         if (!fastgz::ParallelInflater::usable(fd)) { fprintf(stderr, "kmcp-gpu gunzip: %s: not a seekable gzip file\n", file.c_str()); return 2; }
-        fastgz::ParallelInflater inf(fd, threads, par_chunk, g_inflate_cap);
+        fastgz::ParallelInflater inf(fd, threads, par_chunk, g_tune.inflate_cap);
         std::vector<char> buf(chunk);
         for (;;) {
             const ssize_t r = inf.read(buf.data(), buf.size());
@@ -1140,7 +522,7 @@ int gzip_write_main(int argc, char **argv) {
     return 0;
 }
 
-int main(int argc, char **argv) {
+int run(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "index")) return index_main(argc, argv);
     if (argc > 1 && !strcmp(argv[1], "gzip-write")) return gzip_write_main(argc, argv);
     if (argc > 1 && !strcmp(argv[1], "gunzip")) return gunzip_main(argc, argv);
@@ -1187,11 +569,11 @@ int main(int argc, char **argv) {
         else if (a == "--gpu") o.devices.assign(1, atoi(sval().c_str()));
         else if (a == "--gpu-mode") o.gpu_mode = sval();
         else if (a == "--compression-level") { g_compression_level = atoi(sval().c_str()); if (g_compression_level < 1 || g_compression_level > 9) die("--compression-level should be in range [1, 9]"); }
-        else if (a == "--inflate-threads") g_inflate_threads = atoi(sval().c_str());
-        else if (a == "--parse-threads") g_parse_threads = atoi(sval().c_str());
-        else if (a == "--parse-piece") g_parse_piece = (size_t)atol(sval().c_str());
-        else if (a == "--inflate-chunk") g_inflate_chunk = (size_t)atol(sval().c_str());
-        else if (a == "--inflate-cap") g_inflate_cap = (size_t)atol(sval().c_str());
+        else if (a == "--inflate-threads") g_tune.inflate_threads = atoi(sval().c_str());
+        else if (a == "--parse-threads") g_tune.parse_threads = atoi(sval().c_str());
+        else if (a == "--parse-piece") g_tune.parse_piece = (size_t)atol(sval().c_str());
+        else if (a == "--inflate-chunk") g_tune.inflate_chunk = (size_t)atol(sval().c_str());
+        else if (a == "--inflate-cap") g_tune.inflate_cap = (size_t)atol(sval().c_str());
         else if (a == "--gpus") {
             const std::string v = sval();
             o.devices.clear();
@@ -1392,14 +774,11 @@ int main(int argc, char **argv) {
     const int kmax = dbs[0].info.ks[0];
 
     std::thread reader([&] {
-        ReaderConfig rc;
+        ReaderSetup rc;
         rc.paired = paired; rc.read1 = o.read1; rc.read2 = o.read2; rc.files = files;
         rc.whole_file = o.whole_file; rc.use_filename = o.use_filename; rc.query_id = o.query_id;
         rc.batch_reads = o.batch_reads; rc.batch_bytes = o.batch_bytes; rc.kmax = kmax;
-        uint64_t next_base = 0;
         read_batches(rc, [&](Batch *bt) {
-            bt->base = next_base;
-            next_base += bt->n_ids();
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return in_q.size() < 2; });
             in_q.push_back(bt);
@@ -1433,15 +812,15 @@ int main(int argc, char **argv) {
                 out.reserve((size_t)(hi - lo) * 96);
                 std::vector<std::pair<kmcpg_match, int>> merged;      // (match, database) of one query when several databases are searched
                 for (uint32_t q = lo; q < hi; q++) {
-                    const char *const idp = bt.id_buf.data() + bt.id_off[q];
-                    const size_t idn = (size_t)(bt.id_off[q + 1] - bt.id_off[q]);
+                    const char *const idp = bt.id(q);
+                    const size_t idn = bt.id_len(q);
                     const kmcpg_results &r0 = job->res[0];
                     uint64_t hits = 0;
                     for (auto &r : job->res) hits += r.match_off[q + 1] - r.match_off[q];
                     if (hits == 0) {
                         if (!o.keep_unmatched) continue;
                         int n = snprintf(line, sizeof(line), "\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%llu\n", r0.query_len[q], r0.n_kmers[q], r0.k_used[q],     // S:460-511
-                                         (unsigned long long)(bt.base + q));
+                                         (unsigned long long)(bt.b.first_query + q));
                         out.append(idp, idn); out.append(line, (size_t)n);
                         continue;
                     }
@@ -1453,7 +832,7 @@ int main(int argc, char **argv) {
                         out.append(idp, idn); out.append(line, (size_t)n1);
                         if (mp) out.append(*mp); else out.append(tg.name);
                         int n2 = snprintf(line, sizeof(line), "\t%u\t%u\t%llu\t%d\t%u\t%.4f\t%.4f\t%.4f\t%llu\n", tg.index & 0xFFFFu, tg.index >> 16,          // S:532-539
-                                          (unsigned long long)tg.genome_size, r.k_used[q], m.count, m.qcov, m.tcov, m.jacc, (unsigned long long)(bt.base + q));
+                                          (unsigned long long)tg.genome_size, r.k_used[q], m.count, m.qcov, m.tcov, m.jacc, (unsigned long long)(bt.b.first_query + q));
                         out.append(line, (size_t)n2);
                     };
                     if (job->res.size() == 1) {
@@ -1508,11 +887,11 @@ int main(int argc, char **argv) {
         job->batch = bt;
         job->res.resize(dbs.size());
         for (size_t d = 0; d < dbs.size(); d++) {
-            const uint32_t ns = (uint32_t)(bt->off.size() - 1);
+            const uint32_t ns = bt->b.n_seqs;
             const int nc = (int)dbs[d].ctxs.size();
-            const int rc = nc == 1           ? kmcpg_engine_search(dbs[d].ctxs[0], &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d])
-                           : dbs[d].replicas ? kmcpg_engine_search_replicas(dbs[d].ctxs.data(), nc, &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d])
-                                             : kmcpg_engine_search_sharded(dbs[d].ctxs.data(), nc, &eo, bt->seq.data(), bt->off.data(), ns, &job->res[d]);
+            const int rc = nc == 1           ? kmcpg_engine_search(dbs[d].ctxs[0], &eo, bt->b.seq, bt->b.off, ns, &job->res[d])
+                           : dbs[d].replicas ? kmcpg_engine_search_replicas(dbs[d].ctxs.data(), nc, &eo, bt->b.seq, bt->b.off, ns, &job->res[d])
+                                             : kmcpg_engine_search_sharded(dbs[d].ctxs.data(), nc, &eo, bt->b.seq, bt->b.off, ns, &job->res[d]);
             if (rc) {
                 std::string msg;
                 for (auto *c : dbs[d].ctxs) { const char *m = kmcpg_last_error(c); if (m && *m) { msg = m; break; } }
@@ -1564,4 +943,12 @@ int main(int argc, char **argv) {
     logf("INFO", "elapsed time: %.3fs", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
     if (g_log) fclose(g_log);
     return 0;
+}
+
+int main(int argc, char **argv) {
+    try {
+        return run(argc, argv);
+    } catch (const fastx::ReaderError &e) {       // a reader used directly (name maps, file lists, the parse subcommand)
+        die("%s", e.what());
+    }
 }

@@ -210,3 +210,63 @@ def test_batch_builder_single_paired_and_whole_file(files, tmp_path):
     assert len(got) == 500 and sizes == [500]
     assert _batches([e]) == ([], [])
     assert _batches(["-1", e, "-2", files["fq_gz"]]) == ([], [])
+
+
+def test_reader_abi_from_python(files, tmp_path):
+    """kmcpg_reader_* (include/kmcp_gpu.h), the reader stage behind the C ABI as a Go / C host would call it: batches in input
+    order with running query numbers, paired input, -g, errors reported through kmcpg_reader_error, early close"""
+    import numpy as np
+    from kmcp_b200 import api
+    recs = files["recs"]
+
+    def flat(gen, step=1):
+        out, sizes, nxt = [], [], 0
+        for first, ids, seq, off in gen:
+            assert first == nxt and len(off) == step * len(ids) + 1
+            nxt += len(ids)
+            sizes.append(len(ids))
+            for q, i in enumerate(ids):
+                out.append((i, [seq[int(off[q * step + m]):int(off[q * step + m + 1])].tobytes() for m in range(step)]))
+        return out, sizes
+
+    got, sizes = flat(api.read_batches([files["fa"], files["fq_plain"], files["fq_gz"]], batch_reads=1000))
+    assert got == [(i, [s]) for i, s in recs[:1500] + recs[:500] + recs]
+    assert all(x == 1000 for x in sizes[:-1]) and sum(sizes) == 8000
+    for kw in (dict(), dict(inflate_threads=3, inflate_chunk=65536, parse_threads=3, parse_piece=50000)):
+        got, sizes = flat(api.read_batches(read1=files["fq_gz"], read2=files["fq2_gz"], batch_reads=777, **kw), step=2)
+        assert got == [(i, [s, s[::-1]]) for i, s in recs[:4000]]
+    got, _ = flat(api.read_batches([files["fa"]], whole_file=1, k=31, query_id="genome"))
+    assert got == [(b"genome", [recs[0][1] + b"".join(s + b"N" * 30 for _, s in recs[1:1500])])]
+    got, _ = flat(api.read_batches([files["fa"]], whole_file=1, use_filename=1))
+    assert got[0][0] == b"c"                                   # c.fa with the extension cut
+    # errors: missing file, a file that is not FASTA/Q, only one of the two mates
+    for bad in ([str(tmp_path / "missing.fq")], [files["fq_plain"], str(tmp_path / "missing.fq")]):
+        with pytest.raises(api.KmcpGpuError) as e:
+            list(api.read_batches(bad))
+        assert "no such file" in str(e.value)
+    junk = str(tmp_path / "junk.txt")
+    open(junk, "wb").write(b"this is not a sequence file\n" * 10)
+    with pytest.raises(api.KmcpGpuError) as e:
+        list(api.read_batches([junk]))
+    assert "invalid FASTA/Q record" in str(e.value)
+    with pytest.raises(api.KmcpGpuError):
+        list(api.read_batches(read1=files["fq_gz"]))
+    with pytest.raises(api.KmcpGpuError):
+        list(api.read_batches([]))
+    # a damaged stream ends with the decoder's error, never with a short result
+    blob = bytearray(open(files["fq_gz"], "rb").read())
+    blob[len(blob) // 2] ^= 0x55
+    dmg = str(tmp_path / "damaged.fq.gz")
+    open(dmg, "wb").write(bytes(blob))
+    n = 0
+    with pytest.raises(api.KmcpGpuError) as e:
+        for first, ids, seq, off in api.read_batches([dmg], batch_reads=500):
+            n += len(ids)
+    assert "read error" in str(e.value) and "CRC-32" in str(e.value) and n < len(recs)
+    # closing a reader that still has most of its input in front of it does not hang
+    g = api.read_batches([files["fq_gz"], files["fq_gz"], files["fq_gz"]], batch_reads=100)
+    next(g)
+    g.close()
+    # the CLI reports reader errors the way the reference's checkError does: a message and a non-zero exit code
+    p = subprocess.run([EXE, "parse", "--batches", junk], capture_output=True, timeout=60)
+    assert p.returncode != 0 and b"invalid FASTA/Q record" in p.stderr
