@@ -270,3 +270,24 @@ def test_reader_abi_from_python(files, tmp_path):
     # the CLI reports reader errors the way the reference's checkError does: a message and a non-zero exit code
     p = subprocess.run([EXE, "parse", "--batches", junk], capture_output=True, timeout=60)
     assert p.returncode != 0 and b"invalid FASTA/Q record" in p.stderr
+
+
+def test_reader_abi_from_plain_c(files, tmp_path):
+    """examples/read_host.c: the reader stage from a strict C99 program (what cgo binds), no device involved"""
+    exe = str(tmp_path / "read_host")
+    lib_dir = os.path.join(ROOT, "kmcp_b200")
+    c = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "read_host.c"),
+                        "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lkmcp_gpu", "-Wl,-rpath," + lib_dir, "-o", exe], capture_output=True)
+    assert c.returncode == 0, c.stderr.decode()
+    recs = files["recs"]
+    p = subprocess.run([exe, files["fq_gz"]], capture_output=True, timeout=120)
+    assert p.returncode == 0, p.stderr.decode()
+    lines = p.stdout.decode().splitlines()
+    assert lines[-1] == "queries: %d" % len(recs) and len(lines) == 7
+    assert lines[0] == "batch first=0 queries=1000 bytes=%d id=r0 len=%d" % (sum(len(s) for _, s in recs[:1000]), len(recs[0][1]))
+    assert lines[3].startswith("batch first=3000 queries=1000 ") and " id=r3000 " in lines[3]
+    p = subprocess.run([exe, "-p", files["fq_gz"], files["fq2_gz"]], capture_output=True, timeout=120)
+    assert p.returncode == 0 and p.stdout.decode().splitlines()[-1] == "queries: 4000"
+    assert " id=r0 len=%d,%d" % (len(recs[0][1]), len(recs[0][1])) in p.stdout.decode().splitlines()[0]
+    p = subprocess.run([exe, str(tmp_path / "nothing.fq")], capture_output=True, timeout=120)
+    assert p.returncode == 3 and b"no such file" in p.stderr
