@@ -356,6 +356,7 @@ struct Batch {
     size_t n_ids() const { return id_off.size() - 1; }
     void add_id(const char *p, size_t n) { id_buf.insert(id_buf.end(), p, p + n); id_off.push_back(id_buf.size()); }
     void add_id(const std::string &id) { add_id(id.data(), id.size()); }
+    void clear() { id_buf.clear(); id_off.assign(1, 0); seq.clear(); off.assign(1, 0); base = 0; }      // the arrays keep their memory
 };
 
 inline std::atomic<uint64_t> g_stat_pieces{0}, g_stat_fallbacks{0};      // pieces parsed by the workers / files handed back to the general reader
@@ -664,6 +665,7 @@ struct ReaderConfig {
     size_t batch_reads = 1u << 18, batch_bytes = 256u << 20;
     int kmax = 21;
     Tuning tune;
+    std::function<Batch *()> new_batch;                              // where empty batches come from (a pool of used ones); may be empty
     std::function<void(const char *level, const char *msg)> log;      // the reference's log lines (S:800, 878, 920); may be empty
     void say(const char *level, const char *fmt, ...) const __attribute__((format(printf, 3, 4))) {
         if (!log) return;
@@ -678,13 +680,14 @@ struct ReaderConfig {
 
 // S:793-1000: the input files as batches, in order; `emit` takes the batch over
 inline void read_batches(const ReaderConfig &c, const std::function<void(Batch *)> &emit_fn) {
-    std::unique_ptr<Batch> cur(new Batch());
+    auto fresh = [&]() { return c.new_batch ? c.new_batch() : new Batch(); };
+    std::unique_ptr<Batch> cur(fresh());
     auto emit = [&]() {
         if (cur->n_ids() == 0) return;
         if (cur->seq.empty()) cur->seq.push_back(0);
         if (cur->id_buf.empty()) cur->id_buf.push_back(0);        // the arrays of a batch are never NULL
         Batch *full_batch = cur.release();
-        cur.reset(new Batch());
+        cur.reset(fresh());
         emit_fn(full_batch);
     };
     auto full = [&]() { return cur->n_ids() >= c.batch_reads || cur->seq.size() >= c.batch_bytes; };

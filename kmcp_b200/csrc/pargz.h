@@ -41,6 +41,8 @@ struct RawBuf {                       // growable, uninitialised
     RawBuf() = default;
     RawBuf(const RawBuf &) = delete;
     RawBuf &operator=(const RawBuf &) = delete;
+    RawBuf(RawBuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    RawBuf &operator=(RawBuf &&o) noexcept { if (this != &o) { free(p); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; } return *this; }
     ~RawBuf() { free(p); }
     void reserve(size_t n) {
         if (n <= cap) return;
@@ -626,9 +628,9 @@ class ParallelInflater {
             }
             const size_t n = std::min(cap - got, cur_len_ - pos_);
             // the stretch is the resolved symbols followed by the plain bytes
-            const size_t na = cur_->out.size();
+            const size_t na = cur_->r->n_sym;
             size_t c = 0;
-            if (pos_ < na) { c = std::min(n, na - pos_); memcpy(d + got, cur_->out.data() + pos_, c); }
+            if (pos_ < na) { c = std::min(n, na - pos_); memcpy(d + got, cur_->out.p + pos_, c); }
             if (c < n) memcpy(d + got + c, cur_->r->bytes.p + WIN + (pos_ + c - na), n - c);
             pos_ += n; got += n;
         }
@@ -649,8 +651,8 @@ class ParallelInflater {
         std::unique_ptr<Result> r;
         std::vector<uint8_t> win;          // the 32 KB in front of it (when it has symbols to resolve)
         uint64_t member_out_before = 0;    // bytes of the current member in front of it
-        std::vector<uint8_t> out;          // the symbols as bytes
-        bool resolved = false, bad = false;
+        pargz_detail::RawBuf<uint8_t> out; // the symbols as bytes
+        bool resolved = false, bad = false, oom = false;
     };
 
     void work() {
@@ -666,6 +668,10 @@ class ParallelInflater {
                 else k = next_++;
             }
             if (job) {
+                {
+                    std::lock_guard<std::mutex> lk(mu_);
+                    if (!byte_pool_.empty()) { job->out = std::move(byte_pool_.back()); byte_pool_.pop_back(); }
+                }
                 resolve(*job);
                 std::lock_guard<std::mutex> lk(mu_);
                 job->resolved = true;
@@ -673,6 +679,11 @@ class ParallelInflater {
                 continue;
             }
             std::unique_ptr<Result> r(new Result());
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!sym_pool_.empty()) { r->sym = std::move(sym_pool_.back()); sym_pool_.pop_back(); }
+                if (!byte_pool_.empty()) { r->bytes = std::move(byte_pool_.back()); byte_pool_.pop_back(); }
+            }
             try {
                 const uint64_t lo = (uint64_t)k * chunk_ * 8, hi = (uint64_t)(k + 1) * chunk_ * 8;
                 if (k == 0) dec.run_first(*r, hi);
@@ -688,10 +699,10 @@ class ParallelInflater {
     // tested for a marker and packed; only groups with a marker go through the window look-up.
     static void resolve(Item &it) {
         const Result &r = *it.r;
-        try { it.out.resize(r.n_sym); } catch (const std::bad_alloc &) { it.bad = true; return; }
+        try { it.out.reserve(r.n_sym + 16); } catch (const std::bad_alloc &) { it.bad = true; it.oom = true; return; }
         const uint16_t *s = r.sym.p + WIN;
         const uint8_t *win = it.win.data();
-        uint8_t *o = it.out.data();
+        uint8_t *o = it.out.p;
         uint16_t lowest = 0xFFFF;
         size_t i = 0;
         const size_t n = r.n_sym;
@@ -724,6 +735,14 @@ class ParallelInflater {
         return i;
     }
 #endif
+    // the arrays of a stretch that has been handed out (or dropped) go back to the workers
+    void recycle(const std::shared_ptr<Item> &it) {
+        if (!it) return;
+        std::lock_guard<std::mutex> lk(mu_);
+        if (it->r && it->r->sym.p && sym_pool_.size() < lookahead_) sym_pool_.push_back(std::move(it->r->sym));
+        if (it->r && it->r->bytes.p && byte_pool_.size() < 2 * lookahead_) byte_pool_.push_back(std::move(it->r->bytes));
+        if (it->out.p && byte_pool_.size() < 2 * lookahead_) byte_pool_.push_back(std::move(it->out));
+    }
     bool ready_now(size_t k) { std::lock_guard<std::mutex> lk(mu_); return slots_[k].ready; }
     std::unique_ptr<Result> take(size_t k) {
         std::unique_lock<std::mutex> lk(mu_);
@@ -734,6 +753,7 @@ class ParallelInflater {
 
     // hands out the next stretch: settles the place of as many decoded chunks as are ready, then waits for the oldest one's bytes
     bool advance() {
+        recycle(cur_);
         cur_.reset(); cur_len_ = 0; pos_ = 0;
         for (;;) {
             while (!settled_all_ && queue_.size() < lookahead_) {
@@ -750,7 +770,7 @@ class ParallelInflater {
                 delivered_++;
                 cv_.notify_all();
             }
-            if (it->bad) return fail(it->out.empty() && it->r->n_sym ? "out of memory" : "invalid distance too far back");
+            if (it->bad) return fail(it->oom ? "out of memory" : "invalid distance too far back");
             if (!check_members(*it)) return false;
             const size_t total = it->r->n_sym + it->r->n_bytes;
             if (it->r->failed) {                                           // what it decoded before it broke is handed out first
@@ -768,7 +788,7 @@ class ParallelInflater {
         const Result &r = *it.r;
         const size_t na = r.n_sym;
         auto crc_range = [&](uint64_t a, uint64_t b) {            // [a, b) of the stretch: symbols part, then bytes part
-            if (a < na) { const uint64_t e = std::min<uint64_t>(b, na); crc_ = Crc32::update(crc_, it.out.data() + a, (size_t)(e - a)); a = e; }
+            if (a < na) { const uint64_t e = std::min<uint64_t>(b, na); crc_ = Crc32::update(crc_, it.out.p + a, (size_t)(e - a)); a = e; }
             if (a < b) crc_ = Crc32::update(crc_, r.bytes.p + WIN + (a - na), (size_t)(b - a));
         };
         uint64_t from = 0;
@@ -878,6 +898,9 @@ class ParallelInflater {
     std::condition_variable cv_;
     size_t next_ = 0, delivered_ = 0;          // chunks handed to workers / chunks whose place in the look-ahead is free again
     std::deque<std::shared_ptr<Item>> resolve_q_;
+    // the big arrays of finished stretches go round: a fresh 17 MB allocation per chunk costs its page faults again every time
+    std::vector<pargz_detail::RawBuf<uint16_t>> sym_pool_;
+    std::vector<pargz_detail::RawBuf<uint8_t>> byte_pool_;
     bool stop_ = false;
     // state of the thread that calls read()
     size_t k_ = 0;                             // next chunk to settle

@@ -4,8 +4,31 @@
 
 #include "../../include/kmcp_gpu.h"
 
+namespace {
+// used batches go round: their arrays (tens of MB) are touched once instead of once per batch
+struct BatchPool {
+    std::mutex mu;
+    std::vector<fastx::Batch *> free;
+    ~BatchPool() { for (auto *b : free) delete b; }
+    fastx::Batch *get() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (free.empty()) return new fastx::Batch();
+        fastx::Batch *b = free.back();
+        free.pop_back();
+        return b;
+    }
+    void put(fastx::Batch *b) {
+        b->clear();
+        std::lock_guard<std::mutex> lk(mu);
+        if (free.size() < 6) free.push_back(b); else delete b;
+    }
+};
+struct BatchRef { fastx::Batch *b; std::shared_ptr<BatchPool> home; };     // what a kmcpg_read_batch points to
+}  // namespace
+
 struct kmcpg_reader {
     fastx::ReaderConfig cfg;
+    std::shared_ptr<BatchPool> pool = std::make_shared<BatchPool>();
     std::thread th;
     std::mutex mu;
     std::condition_variable cv;
@@ -48,6 +71,7 @@ int kmcpg_reader_open(const kmcpg_reader_opts *o, kmcpg_reader **out) {
     if (o->inflate_chunk) c.tune.inflate_chunk = (size_t)o->inflate_chunk;
     if (o->inflate_cap) c.tune.inflate_cap = (size_t)o->inflate_cap;
     if (o->parse_piece) c.tune.parse_piece = (size_t)o->parse_piece;
+    { std::shared_ptr<BatchPool> pool = r->pool; c.new_batch = [pool] { return pool->get(); }; }
     if (o->log) { auto fn = o->log; void *user = o->log_user; c.log = [fn, user](const char *level, const char *msg) { fn(user, level, msg); }; }
     r->th = std::thread([r] {
         try {
@@ -89,13 +113,15 @@ int kmcpg_reader_next(kmcpg_reader *r, kmcpg_read_batch *out) {
     out->seq = b->seq.data(); out->off = b->off.data();
     out->ids = b->id_buf.data(); out->id_off = b->id_off.data();
     out->first_query = b->base;
-    out->_priv = b;
+    out->_priv = new BatchRef{b, r->pool};
     return 1;
 }
 
 void kmcpg_reader_free_batch(kmcpg_read_batch *b) {
     if (!b || !b->_priv) return;
-    delete (fastx::Batch *)b->_priv;
+    BatchRef *ref = (BatchRef *)b->_priv;
+    ref->home->put(ref->b);                  // the pool outlives the reader for batches released after kmcpg_reader_close
+    delete ref;
     memset(b, 0, sizeof(*b));
 }
 
