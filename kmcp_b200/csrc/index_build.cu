@@ -15,7 +15,9 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <thread>
 #include <cub/cub.cuh>
 #include <numeric>
 #include <regex>
@@ -144,6 +146,68 @@ int load_genome(const std::string &file, const kmcpg_index_params &p, const std:
     }
     return KMCPG_OK;
 }
+
+// The input files loaded a few ahead of the thread that feeds the GPU, by several threads (inflate + parse + windows are pure
+// host work, about 0.25 GB/s per thread; the kernels need a tiny fraction of that time).  get(i) returns file i, in order.
+class GenomeLoader {
+  public:
+    GenomeLoader(const char *const *files, int n_files, const kmcpg_index_params &p, const std::vector<std::regex> &filters, const std::regex *name_re,
+                 int threads)
+        : files_(files), n_(n_files), p_(p), filters_(filters), name_re_(name_re), slots_((size_t)n_files) {
+        threads = std::max(1, std::min(threads, n_files));
+        window_ = 2 * threads + 2;
+        for (int t = 0; t < threads; t++) th_.emplace_back([this] { work(); });
+    }
+    ~GenomeLoader() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int get(int i, Genome &g, std::string &err) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return slots_[(size_t)i].ready; });
+        Slot &s = slots_[(size_t)i];
+        g = std::move(s.g);
+        err = s.err;
+        const int rc = s.rc;
+        s.g = Genome();
+        consumed_ = i + 1;
+        cv_.notify_all();
+        return rc;
+    }
+
+  private:
+    struct Slot { Genome g; int rc = KMCPG_OK; std::string err; bool ready = false; };
+    void work() {
+        for (;;) {
+            int i;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || (next_ < n_ && next_ < consumed_ + window_); });
+                if (stop_) return;
+                i = next_++;
+            }
+            Genome g;
+            std::string err;
+            const int rc = load_genome(files_[i], p_, filters_, name_re_, g, err);
+            std::lock_guard<std::mutex> lk(mu_);
+            Slot &s = slots_[(size_t)i];
+            s.g = std::move(g); s.rc = rc; s.err = err; s.ready = true;
+            cv_.notify_all();
+        }
+    }
+    const char *const *files_;
+    int n_;
+    const kmcpg_index_params &p_;
+    const std::vector<std::regex> &filters_;
+    const std::regex *name_re_;
+    std::vector<Slot> slots_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int next_ = 0, consumed_ = 0, window_ = 4;
+    bool stop_ = false;
+};
 
 // unique count of sorted segments: one warp per segment
 __global__ void count_unique_kernel(const uint64_t *__restrict__ codes, const int *__restrict__ seg_begin, const int *__restrict__ seg_end, uint32_t n_seg,
@@ -337,9 +401,10 @@ int kmcpg_index_fasta(kmcpg_ctx *ctx, const kmcpg_index_params *pin, const char 
             return KMCPG_OK;
         };
 
+        GenomeLoader loader(files, n_files, p, filters, name_re, std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / 4)));
         for (int fi = 0; fi < n_files; fi++) {
             Genome g;
-            int rc = load_genome(files[fi], p, filters, name_re, g, err);
+            int rc = loader.get(fi, g, err);
             if (rc) return fail(ctx, rc, err);
             if (pass == 0) {
                 first_target[fi] = (uint32_t)targets.size();
@@ -410,3 +475,30 @@ int kmcpg_index_fasta(kmcpg_ctx *ctx, const kmcpg_index_params *pin, const char 
 }
 
 }  // extern "C"
+
+// test hook (host only, tests/test_abi.py): the files through GenomeLoader on `threads` threads and one by one through load_genome —
+// a running FNV-1a over (name, genome size, split flag, every sequence) must agree.  Returns 0, or a KMCPG_E* code / -100 on a difference.
+extern "C" int kmcpg_internal_genome_loader_selftest(const char *const *files, int n_files, int k, int split_number, int split_overlap, int threads,
+                                                       uint64_t *digest_out) {
+    if (!files || n_files < 1) return KMCPG_EINVAL;
+    kmcpg_index_params p;
+    kmcpg_default_index_params(&p);
+    p.k = k; p.split_number = split_number < 1 ? 1 : split_number; p.split_overlap = split_overlap < 0 ? k - 1 : split_overlap;
+    std::vector<std::regex> filters;
+    auto fold = [](uint64_t h, const void *d, size_t n) { const uint8_t *b = (const uint8_t *)d; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } return h; };
+    auto digest = [&](uint64_t h, const Genome &g) {
+        h = fold(h, g.name.data(), g.name.size()); h = fold(h, &g.gsize, 8);
+        const uint8_t sp = g.split; h = fold(h, &sp, 1);
+        for (auto &s : g.seqs) { const uint64_t n = s.size(); h = fold(h, &n, 8); h = fold(h, s.data(), s.size()); }
+        return h;
+    };
+    uint64_t a = 1469598103934665603ull, b = a;
+    std::string err;
+    {
+        GenomeLoader loader(files, n_files, p, filters, nullptr, threads);
+        for (int i = 0; i < n_files; i++) { Genome g; const int rc = loader.get(i, g, err); if (rc) return rc; a = digest(a, g); }
+    }
+    for (int i = 0; i < n_files; i++) { Genome g; const int rc = load_genome(files[i], p, filters, nullptr, g, err); if (rc) return rc; b = digest(b, g); }
+    if (digest_out) *digest_out = a;
+    return a == b ? KMCPG_OK : -100;
+}

@@ -275,3 +275,31 @@ def test_block_rows_are_read_by_several_streams(tmp_path):
     dst = np.zeros(1 << 20, dtype=np.uint8)
     assert f(p.encode(), len(data) - 1000, 1001, 4, dst.ctypes.data) == api.KMCPG_EIO
     assert f(str(tmp_path / "missing").encode(), 0, 10, 2, dst.ctypes.data) == api.KMCPG_EIO
+
+
+def test_index_builder_loads_its_input_files_on_several_threads(tmp_path):
+    """GenomeLoader (index_build.cu, host part of kmcpg_index_fasta): files loaded ahead by several threads come out in order
+    and identical to loading them one by one; a missing file is reported at its place"""
+    import gzip
+    import random
+    from kmcp_b200 import api
+    L = api.load()
+    f = L.kmcpg_internal_genome_loader_selftest
+    f.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    rnd = random.Random(4)
+    paths = []
+    for i in range(37):
+        p = str(tmp_path / ("g%02d.fa%s" % (i, ".gz" if i % 3 == 0 else "")))
+        recs = b"".join(b">c%d_%d plasmid\n" % (i, j) + b"\n".join(bytes(rnd.choice(b"ACGTN") for _ in range(60)) for _ in range(rnd.randrange(1, 400))) + b"\n"
+                        for j in range(rnd.randrange(1, 4)))
+        (gzip.open if p.endswith(".gz") else open)(p, "wb").write(recs)
+        paths.append(p.encode())
+    arr = (C.c_char_p * len(paths))(*paths)
+    digests = set()
+    for threads, split in ((1, 1), (3, 1), (8, 10), (16, 10), (2, 5)):
+        d = C.c_uint64()
+        assert f(arr, len(paths), 21, split, -1, threads, C.byref(d)) == 0, (threads, split)
+        digests.add((split, d.value))
+    assert len(digests) == 3                     # one digest per split setting, whatever the thread count
+    bad = (C.c_char_p * 3)(paths[0], str(tmp_path / "missing.fa").encode(), paths[1])
+    assert f(bad, 3, 21, 1, -1, 4, None) == api.KMCPG_EIO
