@@ -303,3 +303,21 @@ def test_index_builder_loads_its_input_files_on_several_threads(tmp_path):
     assert len(digests) == 3                     # one digest per split setting, whatever the thread count
     bad = (C.c_char_p * 3)(paths[0], str(tmp_path / "missing.fa").encode(), paths[1])
     assert f(bad, 3, 21, 1, -1, 4, None) == api.KMCPG_EIO
+
+
+def test_go_stub_only_uses_what_the_header_declares():
+    """go/engine_gpu.go cannot be compiled here (no Go toolchain): at least every C.kmcpg_* / C.KMCPG_* name it uses must be
+    declared by include/kmcp_gpu.h, and the struct fields it touches must exist"""
+    import re
+    go = open(os.path.join(ROOT, "go", "engine_gpu.go")).read()
+    hdr = open(os.path.join(ROOT, "include", "kmcp_gpu.h")).read()
+    names = set(re.findall(r"\bC\.((?:kmcpg|KMCPG)_\w+)", go))
+    assert len(names) > 15
+    missing = [n for n in sorted(names) if not re.search(r"\b%s\b" % re.escape(n), hdr)]
+    assert not missing, missing
+    # the INTEGRATION.md code blocks and the source file say the same thing
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for block in re.findall(r"```go\n(.*?)```", doc, flags=re.S):
+        for line in block.splitlines():
+            if line.strip() and not line.strip().startswith("//") and '"fmt"' not in line:
+                assert line in go, line
