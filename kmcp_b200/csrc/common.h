@@ -48,6 +48,13 @@ int write_block_file(const std::string &path, const BlockMeta &m, const uint8_t 
 // the page cache or an NVMe drive: one stream reaches neither's bandwidth); false on an I/O error or a short file
 bool pread_parallel(int fd, void *dst, size_t bytes, uint64_t off, int threads);
 
+// FASTA/Q records of one file, plain or gzip, through the reader stage's parser and decoders (reader.cpp; usable from .cu files,
+// which do not see fastx_reader.h): header = the whole header line without '>' / '@', seq = the sequence lines joined.
+struct FastxFile;
+FastxFile *fastx_open(const std::string &path);                                            // nullptr: cannot open
+int fastx_next(FastxFile *f, std::string &header, std::string &seq, std::string &err);     // 1 a record, 0 end of file, -1 error (err)
+void fastx_close(FastxFile *f);
+
 // H:46-50 CalcSignatureSize
 uint64_t calc_signature_size(uint64_t n_elements, int num_hashes, double fpr);
 // F:32-50 QueryFPR, bit-exact with Go (math.Pow loop, big.Float prec-53 binomials)

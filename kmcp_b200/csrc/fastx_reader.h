@@ -161,6 +161,9 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     // buffer is filled instead of one memchr call per (short) line
     std::vector<uint32_t> nl;
     size_t nl_i = 0;
+    // callers that filter on the whole header line (the index builder's -B): the last record's header without '>' / '@'
+    bool keep_header = false;
+    std::string header;
     bool open(const std::string &p, bool inflate_ahead = false, const Tuning &t = Tuning()) {
         tune = t;
         path = p;
@@ -271,6 +274,7 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         size_t e = h0 + 1;
         while (e < h1 && b[e] != ' ' && b[e] != '\t') e++;
         idp = b + h0 + 1; idn = e - h0 - 1;
+        if (keep_header) header.assign(b + h0 + 1, h1 - h0 - 1);
         dst.insert(dst.end(), b + s0, b + s1);
         pos = (size_t)nl[nl_i + 3] + 1;
         nl_i += 4;
@@ -306,6 +310,7 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         if (next_four_line(l, n, dst)) { id.assign(l, n); return true; }
         do { if (!line(l, n)) return false; } while (n == 0);
         if (l[0] != '>' && l[0] != '@') fail("invalid FASTA/Q record in %s", path.c_str());
+        if (keep_header) header.assign(l + 1, n - 1);
         const bool fq = l[0] == '@';
         size_t e = 1;
         while (e < n && l[e] != ' ' && l[e] != '\t') e++;

@@ -26,6 +26,30 @@ struct BatchPool {
 struct BatchRef { fastx::Batch *b; std::shared_ptr<BatchPool> home; };     // what a kmcpg_read_batch points to
 }  // namespace
 
+#include "common.h"
+
+namespace kmcpg {
+struct FastxFile { fastx::Reader r; std::vector<char> seq; std::string id; };
+FastxFile *fastx_open(const std::string &path) {
+    FastxFile *f = new FastxFile();
+    f->r.keep_header = true;
+    fastx::Tuning t;
+    t.inflate_threads = 1;              // the index builder loads many files side by side: one decoder thread per file
+    if (!f->r.open(path, false, t)) { delete f; return nullptr; }
+    return f;
+}
+int fastx_next(FastxFile *f, std::string &header, std::string &seq, std::string &err) {
+    try {
+        f->seq.clear();
+        if (!f->r.next(f->id, f->seq)) return 0;
+        header = f->r.header;
+        seq.assign(f->seq.data(), f->seq.size());
+        return 1;
+    } catch (const std::exception &e) { err = e.what(); return -1; }
+}
+void fastx_close(FastxFile *f) { delete f; }
+}  // namespace kmcpg
+
 struct kmcpg_reader {
     fastx::ReaderConfig cfg;
     std::shared_ptr<BatchPool> pool = std::make_shared<BatchPool>();

@@ -294,6 +294,18 @@ def test_index_builder_loads_its_input_files_on_several_threads(tmp_path):
                         for j in range(rnd.randrange(1, 4)))
         (gzip.open if p.endswith(".gz") else open)(p, "wb").write(recs)
         paths.append(p.encode())
+    # the other shapes a sequence file comes in: FASTQ (four-line and wrapped), CRLF, blank lines, no final newline, lower case
+    extra = {
+        "q4.fq": b"".join(b"@r%d x\n%s\n+\n%s\n" % (j, bytes(rnd.choice(b"ACGT") for _ in range(200)), b"I" * 200) for j in range(300)),
+        "qw.fastq.gz": b"".join(b"@w%d\n%s\n%s\n+w%d\n%s\n%s\n" % (j, b"ACGTAC" * 10, b"GGTTAA" * 5, j, b"@" * 60, b"+" * 30) for j in range(50)),
+        "crlf.fa": b">a desc\r\nACGTACGTAC\r\nGGGG\r\n\r\n>b\r\nTTTTT\r\n",
+        "blank.fna": b"\n\n>x\nACGT\n\nACGT\n>y\n\n>z\nacgtn\n",
+        "nonl.fa": b">only\nACGTACGTACGTACGTACGTACGTACGT",
+    }
+    for name, data in extra.items():
+        p = str(tmp_path / name)
+        (gzip.open if name.endswith(".gz") else open)(p, "wb").write(data)
+        paths.append(p.encode())
     arr = (C.c_char_p * len(paths))(*paths)
     digests = set()
     for threads, split in ((1, 1), (3, 1), (8, 10), (16, 10), (2, 5)):
@@ -303,6 +315,14 @@ def test_index_builder_loads_its_input_files_on_several_threads(tmp_path):
     assert len(digests) == 3                     # one digest per split setting, whatever the thread count
     bad = (C.c_char_p * 3)(paths[0], str(tmp_path / "missing.fa").encode(), paths[1])
     assert f(bad, 3, 21, 1, -1, 4, None) == api.KMCPG_EIO
+    junk = str(tmp_path / "junk.fa")
+    open(junk, "wb").write(b"ACGT without a header line\n")
+    assert f((C.c_char_p * 2)(paths[0], junk.encode()), 2, 21, 1, -1, 2, None) == api.KMCPG_EIO      # not FASTA/Q: an error, as seqio/fastx gives
+    broken = str(tmp_path / "broken.fa.gz")
+    blob = bytearray(gzip.compress(b">g\n" + b"ACGT" * 20000 + b"\n"))
+    blob[len(blob) // 2] ^= 0x20
+    open(broken, "wb").write(bytes(blob))
+    assert f((C.c_char_p * 1)(broken.encode()), 1, 21, 1, -1, 1, None) == api.KMCPG_EIO             # a damaged .gz is not a short genome
 
 
 def test_go_stub_only_uses_what_the_header_declares():
