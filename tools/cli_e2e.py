@@ -47,9 +47,11 @@ def main():
                                       ("fastq.gz -> tsv.gz (8 inflate threads)", fqgz, n_gz, "o8.tsv.gz", ["--inflate-threads", "8"]),
                                       ("fastq.gz -> tsv.gz (default)", fqgz, n_gz, "od.tsv.gz", []),
                                       ("fastq -> tsv, 4 parse threads", fq, n_reads, "op.tsv", ["--parse-threads", "4"]),
-                                      ("fastq.gz -> tsv.gz, 8 inflate + 4 parse threads", fqgz, n_gz, "op.tsv.gz", ["--inflate-threads", "8", "--parse-threads", "4"])]:
+                                      ("fastq.gz -> tsv.gz, 8 inflate + 4 parse threads", fqgz, n_gz, "op.tsv.gz", ["--inflate-threads", "8", "--parse-threads", "4"]),
+                                      ("paired fastq.gz (the same file as both mates) -> tsv.gz", None, n_gz, "pe.tsv.gz", ["-1", fqgz, "-2", fqgz]),
+                                      ("paired fastq -> tsv", None, n_reads, "pe.tsv", ["-1", fq, "-2", fq])]:
         t0 = time.time()
-        p = subprocess.run([exe, "search", "-d", tmp, inp, "-o", os.path.join(tmp, outp)] + extra, capture_output=True)
+        p = subprocess.run([exe, "search", "-d", tmp] + ([inp] if inp else []) + ["-o", os.path.join(tmp, outp)] + extra, capture_output=True)
         wall = time.time() - t0
         log = p.stderr.decode()
         assert p.returncode == 0, log
