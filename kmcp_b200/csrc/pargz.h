@@ -141,10 +141,22 @@ class ChunkDecoder {
     }
     // a later chunk: look for a block header in [lo_bit, stop_bit), decode with an unknown window
     void run_search(ChunkResult &R, uint64_t lo_bit, uint64_t stop_bit) {
-        src_.load(lo_bit >> 3, load_);
-        uint64_t at;
-        if (!find_block(lo_bit, stop_bit, at)) return;
+        const uint64_t lo_byte = lo_bit >> 3;
+        src_.load(lo_byte > BACK ? lo_byte - BACK : 0, load_ + BACK);           // a member header may straddle the chunk's first bit
+        uint64_t at = 0, member_at = 0;
+        const bool have_member = find_member(lo_bit, stop_bit, member_at);
+        const bool have_block = find_block(lo_bit, have_member ? member_at : stop_bit, at);
+        if (!have_member && !have_block) return;
         R.found = true;
+        if (!have_block) {
+            // the first block boundary is the start of a gzip member (bgzip / pgzip files, `cat a.gz b.gz`): nothing in front of
+            // it can be copied from, so this chunk is plain bytes from its first symbol
+            R.start_bit = member_at;
+            seek(member_at);
+            start_bytes(R, nullptr, 0);
+            decode(R, stop_bit);
+            return;
+        }
         R.start_bit = at;
         seek(at);
         R.sym.reserve(WIN + (load_ * 4) + SLACK);
@@ -165,6 +177,7 @@ class ChunkDecoder {
 
   private:
     static constexpr size_t SLACK = 320;
+    static constexpr uint64_t BACK = 1024;        // how far in front of a chunk a member header that reaches into it may start
 
     uint64_t bitpos() const { return (src_.z_off + (uint64_t)(in_ - src_.z.data())) * 8 - bc_; }
     void seek(uint64_t bit) {
@@ -242,11 +255,12 @@ class ChunkDecoder {
         return left == 0 || (allow_single && nz == 1);
     }
     // is there a plausible non-final dynamic block header at bit `bit` of memory z (z must be readable for 400 bytes behind it)?
-    static bool plausible_block(const uint8_t *z, uint64_t bit) {
+    static bool plausible_block(const uint8_t *z, uint64_t bit, bool allow_final = false) {
         uint64_t w;
         memcpy(&w, z + (bit >> 3), 8);
         w >>= (bit & 7);
-        if ((w & 7) != 4) return false;                                   // BFINAL 0, BTYPE 2 (bits: 0, then 0 1)
+        if ((w & 6) != 4) return false;                                   // BTYPE 2 (bits 1-2: 0 then 1)
+        if ((w & 1) && !allow_final) return false;                        // BFINAL 0 unless the caller knows better
         const uint32_t hlit = (uint32_t)((w >> 3) & 31), hdist = (uint32_t)((w >> 8) & 31), hclen = (uint32_t)((w >> 13) & 15) + 4;
         if (hlit > 29 || hdist > 29) return false;
         Peek pk(z + (bit >> 3));
@@ -292,6 +306,43 @@ class ChunkDecoder {
             if (!l) continue;
             for (uint32_t i = I::rev_bits(next[l]++, l); i < 128; i += 1u << l) pt[i] = (uint16_t)(s | (l << 8));
         }
+    }
+    // the first gzip member whose first block starts in [lo_bit, hi_bit): magic, method and flag bytes, the optional header fields,
+    // then a first block that makes sense (a plausible dynamic header, final or not; a stored block whose two length fields agree;
+    // fixed-Huffman blocks cannot be told from noise and are taken as they are — the member's bytes have to decode anyway, and
+    // the consumer only uses the chunk if the data in front of it ends exactly here)
+    bool find_member(uint64_t lo_bit, uint64_t hi_bit, uint64_t &at) {
+        const uint64_t need_to = std::min<uint64_t>((hi_bit >> 3) + 1024, src_.file_size);
+        while (src_.z_off + src_.z_len < need_to && src_.more(load_)) {}
+        const uint8_t *z = src_.z.data();
+        const size_t n = src_.z_len;
+        size_t i = 0;
+        while (i + 18 <= n) {
+            const uint8_t *q = (const uint8_t *)memchr(z + i, 0x1f, n - i - 17);
+            if (!q) break;
+            i = (size_t)(q - z);
+            size_t p = i + 10;
+            const uint8_t flg = z[i + 3];
+            bool ok = z[i + 1] == 0x8b && z[i + 2] == 8 && !(flg & 0xE0);
+            if (ok && (flg & 4)) { if (p + 2 <= n) { const size_t xl = z[p] | (z[p + 1] << 8); p += 2 + xl; } else ok = false; }
+            for (int bit : {8, 16})
+                if (ok && (flg & bit)) { while (p < n && p < i + BACK && z[p]) p++; if (p >= n || z[p]) ok = false; else p++; }
+            if (ok && (flg & 2)) p += 2;
+            if (ok && p + 640 <= n) {
+                const uint64_t b = (src_.z_off + p) * 8;                  // the member's first block
+                if (b >= hi_bit) return false;
+                if (b >= lo_bit) {
+                    const uint32_t type = (z[p] >> 1) & 3;
+                    bool good = false;
+                    if (type == 2) good = plausible_block(z, (uint64_t)p * 8, true);
+                    else if (type == 1) good = true;
+                    else if (type == 0) good = ((z[p + 1] | (z[p + 2] << 8)) ^ (z[p + 3] | (z[p + 4] << 8))) == 0xFFFF;
+                    if (good) { at = b; return true; }
+                }
+            }
+            i++;
+        }
+        return false;
     }
     // first plausible block header in [lo_bit, hi_bit)
     bool find_block(uint64_t lo_bit, uint64_t hi_bit, uint64_t &at) {

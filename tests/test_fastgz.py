@@ -270,7 +270,23 @@ def test_parallel_decoder_members_garbage_and_block_kinds(corpus, tmp_path):
     # 64 KB members as bgzip writes them: every chunk holds several member starts
     bg = b"".join(_gz(text[i:i + 60_000]) for i in range(0, len(text), 60_000))
     open(p, "wb").write(bg)
-    assert _par(p, par_chunk=65536).stdout == text
+    r = _par(p, par_chunk=65536)
+    assert r.stdout == text
+    used, redone, resolved = _stats(r)
+    assert used >= len(bg) // 65536 - 1 and redone <= 1 and resolved == 0      # chunks start at member starts: plain bytes, nothing to resolve
+    # the same with members whose only block is the final one (what bgzip writes) and a long FNAME in every header
+    import io
+    parts = []
+    for i in range(0, len(text), 50_000):
+        m = io.BytesIO()
+        with gzip.GzipFile(filename="a_rather_long_file_name_%d.txt" % i, mode="wb", fileobj=m, compresslevel=1) as g:
+            g.write(text[i:i + 50_000])
+        parts.append(m.getvalue())
+    open(p, "wb").write(b"".join(parts))
+    r = _par(p, par_chunk=65536, threads=4)
+    assert r.stdout == text
+    used, redone, resolved = _stats(r)
+    assert used >= len(b"".join(parts)) // 65536 - 1 and redone <= 1 and resolved == 0
     # one flush per 10 KB: empty stored blocks and byte-aligned block starts all over the stream
     c = zlib.compressobj(6, zlib.DEFLATED, 31)
     z = b"".join(c.compress(fq[i:i + 10_000]) + c.flush(zlib.Z_FULL_FLUSH if i % 30_000 == 0 else zlib.Z_SYNC_FLUSH) for i in range(0, len(fq), 10_000)) + c.flush()
