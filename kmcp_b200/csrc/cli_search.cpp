@@ -486,8 +486,8 @@ int gunzip_main(int argc, char **argv) {
             if (r == 0) break;
             if (fwrite(buf.data(), 1, (size_t)r, stdout) != (size_t)r) return 3;
         }
-        if (stats) fprintf(stderr, "chunks used %llu, stretches decoded again in order %llu, symbols resolved %llu\n", (unsigned long long)inf.chunks_used(),
-                           (unsigned long long)inf.chunks_redone(), (unsigned long long)inf.symbols_resolved());
+        if (stats) fprintf(stderr, "chunks used %llu, stretches decoded again in order %llu, symbols resolved %llu%s\n", (unsigned long long)inf.chunks_used(),
+                           (unsigned long long)inf.chunks_redone(), (unsigned long long)inf.symbols_resolved(), inf.gave_up() ? ", gave up looking for block starts" : "");
         return 0;
     }
     fastgz::Inflater inf([fd, read_size](void *dst, size_t n) -> ssize_t { return ::read(fd, dst, std::min(n, read_size)); });

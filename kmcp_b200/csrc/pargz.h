@@ -177,6 +177,7 @@ class ChunkDecoder {
 
   private:
     static constexpr size_t SLACK = 320;
+    static constexpr uint64_t SEARCH_BYTES = 256u << 10;
     static constexpr uint64_t BACK = 1024;        // how far in front of a chunk a member header that reaches into it may start
 
     uint64_t bitpos() const { return (src_.z_off + (uint64_t)(in_ - src_.z.data())) * 8 - bc_; }
@@ -350,6 +351,9 @@ class ChunkDecoder {
         const uint64_t need_to = std::min<uint64_t>((hi_bit >> 3) + 1024, src_.file_size);
         while (src_.z_off + src_.z_len < need_to && src_.more(load_)) {}
         const uint64_t base_bit = src_.z_off * 8;
+        // compressors close a block after 16-64 K symbols (tens of KB); a quarter of a megabyte without a header means this
+        // stretch is stored blocks or one huge block, and looking further only burns time the consumer waits for
+        hi_bit = std::min(hi_bit, lo_bit + SEARCH_BYTES * 8);
         for (uint64_t b = lo_bit; b < hi_bit; b++) {
             const uint64_t rel = b - base_bit;
             if ((rel >> 3) + 640 > src_.z_len) return false;       // a header may reach ~570 bytes past its first bit
@@ -559,7 +563,8 @@ class ChunkDecoder {
             if (n_out + n > max_out_ + (1u << 20)) { R.too_big = true; return fail(R, "chunk decodes to more than the cap of the parallel decoder"); }
             if (WIN + n_out + n + SLACK > buf.cap) buf.reserve(std::max(buf.cap + buf.cap / 2, WIN + n_out + n + SLACK));
             T *out = buf.p + WIN + n_out;
-            for (size_t i = 0; i < n; i++) out[i] = in_[i];
+            if (sizeof(T) == 1) memcpy(out, in_, n);
+            else for (size_t i = 0; i < n; i++) out[i] = in_[i];
             n_out += n; in_ += n; stored_left_ -= (uint32_t)n;
         }
         return true;
@@ -692,6 +697,7 @@ class ParallelInflater {
     // how the stream was put together (tests and logs)
     uint64_t chunks_used() const { return used_; }
     uint64_t chunks_redone() const { return redone_; }
+    bool gave_up() const { return unprofitable_; }
     uint64_t symbols_resolved() const { return resolved_; }
 
   private:
@@ -713,7 +719,7 @@ class ParallelInflater {
             std::shared_ptr<Item> job;
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || !resolve_q_.empty() || (next_ < n_chunks_ && next_ < delivered_ + lookahead_); });
+                cv_.wait(lk, [&] { return stop_ || !resolve_q_.empty() || (!unprofitable_ && next_ < n_chunks_ && next_ < delivered_ + lookahead_); });
                 if (stop_) return;
                 if (!resolve_q_.empty()) { job = resolve_q_.front(); resolve_q_.pop_front(); }
                 else k = next_++;
@@ -867,7 +873,15 @@ class ParallelInflater {
             settled_all_ = true;
             return true;
         }
-        std::unique_ptr<Result> r = take(k_);
+        // a stream whose block starts the workers keep missing (stored or fixed-Huffman blocks: incompressible or tiny data) is
+        // decoded in order from here on; the chunks already under way are ignored
+        if (!unprofitable_ && redone_ >= 4 && redone_ > used_) {
+            std::lock_guard<std::mutex> lk(mu_);
+            unprofitable_ = true;
+        }
+        std::unique_ptr<Result> r;
+        if (unprofitable_ && k_ > 0) r.reset(new Result());
+        else r = take(k_);
         const size_t k = k_++;
         if (k == 0) {
             if (r->not_gzip) return fail("not a gzip file");
@@ -894,7 +908,12 @@ class ParallelInflater {
     // decodes again, in order, from the end of the settled data up to the first block boundary at or behind stop
     bool redo(Result &rec, uint64_t stop) {
         redone_++;
-        pargz_detail::ChunkDecoder dec(fd_, file_size_, chunk_ + 65536, max_out_);
+        if (!redo_dec_) redo_dec_.reset(new pargz_detail::ChunkDecoder(fd_, file_size_, chunk_ + 65536, max_out_));   // kept: its buffers stay warm
+        pargz_detail::ChunkDecoder &dec = *redo_dec_;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!byte_pool_.empty()) { rec.bytes = std::move(byte_pool_.back()); byte_pool_.pop_back(); }
+        }
         const size_t n_hist = (size_t)std::min<uint64_t>(s_member_out_, WIN);
         try {
             dec.run_from(rec, cur_bit_, stop, tail_.data() + WIN - n_hist, n_hist);
@@ -941,6 +960,8 @@ class ParallelInflater {
     int fd_;
     size_t chunk_, max_out_;
     bool too_big_ = false;
+    std::unique_ptr<pargz_detail::ChunkDecoder> redo_dec_;
+    bool unprofitable_ = false;              // guarded by mu_ (read by the workers), written by the thread that calls read()
     uint64_t file_size_ = 0;
     size_t n_chunks_ = 0, lookahead_ = 4;
     std::vector<Slot> slots_;

@@ -245,6 +245,12 @@ def test_parallel_decoder_gives_the_same_bytes(corpus, tmp_path):
             if strategy == zlib.Z_DEFAULT_STRATEGY and level == 6 and name in ("fastq", "text", "skewed"):
                 assert used >= max(1, len(z) // 65536 - 1) and redone <= 2, (name, used, redone)        # dynamic blocks: every chunk is used
     assert used_total > 100
+    # incompressible data is stored blocks, which have no header to look for: after a few misses the decoder stops looking and
+    # decodes in order (same bytes, no wasted work)
+    big_random = os.urandom(3_000_000)
+    open(p, "wb").write(_gz(big_random, 6))
+    r = _par(p, threads=3)
+    assert r.stdout == big_random and b"gave up looking for block starts" in r.stderr
     # a FASTQ stream big enough for many chunks at the default chunk size too, odd output piece sizes
     big = corpus["fastq"] * 40
     open(p, "wb").write(_gz(big, 6))
