@@ -9,6 +9,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -168,6 +169,23 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         tune = t;
         path = p;
         fd = p == "-" ? 0 : ::open(p.c_str(), O_RDONLY);
+        ext_err.clear(); child = -1; tool = nullptr;
+        if (fd > 0 && (tool = external_decoder(fd)) != nullptr) {
+            // xz / zstd / bzip2 input (the reference's xopen reads these too): the system's decompressor writes into a pipe
+            int pfd[2];
+            if (pipe(pfd) != 0) { ::close(fd); fd = -1; return false; }
+            child = fork();
+            if (child == 0) {
+                dup2(pfd[1], 1);
+                ::close(pfd[0]); ::close(pfd[1]);
+                execlp(tool, tool, "-dc", "--", p.c_str(), (char *)nullptr);
+                _exit(127);
+            }
+            ::close(pfd[1]);
+            ::close(fd);
+            fd = pfd[0];
+            if (child < 0) { ::close(fd); fd = -1; return false; }
+        }
         if (fd >= 0) {
             const int h = fd, T = inflate_threads(h);
             if (T >= 2) pf = new fastgz::ParallelInflater(h, T, tune.inflate_chunk, tune.inflate_cap);
@@ -189,7 +207,20 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         f = nullptr; pf = nullptr;
         if (fd > 0) ::close(fd);
         fd = -1;
+        if (child > 0) { int st; waitpid(child, &st, 0); child = -1; }     // its pipe is closed: it ends by itself
     }
+    // "xz" / "zstd" / "bzip2" when the file starts with that format's magic bytes
+    static const char *external_decoder(int h) {
+        uint8_t m[6] = {0, 0, 0, 0, 0, 0};
+        if (pread(h, m, 6, 0) < 4) return nullptr;
+        if (m[0] == 0xFD && m[1] == '7' && m[2] == 'z' && m[3] == 'X' && m[4] == 'Z' && m[5] == 0) return "xz";
+        if (m[0] == 0x28 && m[1] == 0xB5 && m[2] == 0x2F && m[3] == 0xFD) return "zstd";
+        if (m[0] == 'B' && m[1] == 'Z' && m[2] == 'h' && m[3] >= '1' && m[3] <= '9') return "bzip2";
+        return nullptr;
+    }
+    pid_t child = -1;
+    const char *tool = nullptr;
+    std::string ext_err;
     static fastgz::Inflater *sequential(int h) {
         return new fastgz::Inflater([h](void *dst, size_t n) -> ssize_t {
             for (;;) { const ssize_t r = ::read(h, dst, n); if (r >= 0 || errno != EINTR) return r; }
@@ -214,11 +245,20 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         }
         const ssize_t r = f->read(dst, n);
         if (r > 0) raw_total += (uint64_t)r;
+        if (r == 0 && child > 0) {              // the decompressor's verdict on the file
+            int st = 0;
+            waitpid(child, &st, 0);
+            child = -1;
+            if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+                ext_err = std::string(tool) + (WIFEXITED(st) && WEXITSTATUS(st) == 127 ? " is not installed: cannot read this file" : " could not decompress the file");
+                return -1;
+            }
+        }
         return r;
     }
     // the decoded text itself (for callers that cut it into records themselves); like read(2)
     int read_text(char *dst, size_t n) { n = std::min<size_t>(n, 1u << 30); return ahead ? ahead->read(dst, n) : (int)raw_read(dst, n); }
-    const char *error() const { return pf ? pf->error() : (f ? f->error() : ""); }
+    const char *error() const { return !ext_err.empty() ? ext_err.c_str() : pf ? pf->error() : (f ? f->error() : ""); }
     // worker threads for one input: --inflate-threads N, or by itself on big machines for big seekable gzip files
     int inflate_threads(int h) const {
         if (tune.inflate_threads == 1 || !fastgz::ParallelInflater::usable(h)) return 1;
@@ -241,7 +281,7 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         if (end == buf.size()) buf.resize(buf.size() * 2);
         const size_t room = std::min<size_t>(buf.size() - end, 1u << 30);
         const int r = ahead ? ahead->read(buf.data() + end, room) : (int)raw_read(buf.data() + end, room);
-        if (r < 0) fail("read error in %s: %s", path.c_str(), pf ? pf->error() : f->error());
+        if (r < 0) fail("read error in %s: %s", path.c_str(), error());
         if (r == 0) { eof = true; return false; }
         if (end + (size_t)r < ((size_t)1 << 32)) scan_newlines(buf.data() + end, (size_t)r, (uint32_t)end, nl);
         else { nl.clear(); nl_i = 0; fast_ok = false; }          // a single line of gigabytes: offsets no longer fit

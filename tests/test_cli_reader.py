@@ -291,3 +291,38 @@ def test_reader_abi_from_plain_c(files, tmp_path):
     assert " id=r0 len=%d,%d" % (len(recs[0][1]), len(recs[0][1])) in p.stdout.decode().splitlines()[0]
     p = subprocess.run([exe, str(tmp_path / "nothing.fq")], capture_output=True, timeout=120)
     assert p.returncode == 3 and b"no such file" in p.stderr
+
+
+def test_reader_xz_bzip2_zstd_inputs(files, tmp_path):
+    """the reference's xopen also reads .xz / .zst / .bz2 by their magic bytes: here the system's decompressor writes into a pipe;
+    a failing or missing decompressor is a read error, never a short result"""
+    import bz2
+    import lzma
+    import shutil
+    recs = files["recs"]
+    text = b"".join(b"@" + i + b"\n" + s + b"\n+\n" + b"F" * len(s) + b"\n" for i, s in recs)
+    exp = "".join(_line(i, s) for i, s in recs)
+    made = []
+    if shutil.which("xz"):
+        p = str(tmp_path / "r.fq.xz")
+        open(p, "wb").write(lzma.compress(text, preset=1))
+        made.append(p)
+    if shutil.which("bzip2"):
+        p = str(tmp_path / "r.fastq.bz2")
+        open(p, "wb").write(bz2.compress(text, 1))
+        made.append(p)
+    if not made:
+        pytest.skip("neither xz nor bzip2 installed")
+    for p in made:
+        assert _parse([p]) == exp
+        assert _parse(["--ahead", p]) == exp
+        got, _ = _batches(["--parse-threads", "3", "--parse-piece", "100000", p])       # a pipe: the plain parser thread
+        assert len(got) == len(recs)
+        blob = open(p, "rb").read()
+        open(p + ".cut", "wb").write(blob[:len(blob) // 2])
+        q = subprocess.run([EXE, "parse", p + ".cut"], capture_output=True, timeout=60)
+        assert q.returncode != 0 and b"could not decompress" in q.stderr
+    z = str(tmp_path / "r.fq.zst")
+    open(z, "wb").write(b"\x28\xb5\x2f\xfd" + b"not really zstd" * 10)
+    q = subprocess.run([EXE, "parse", z], capture_output=True, timeout=60)
+    assert q.returncode != 0 and (b"zstd is not installed" in q.stderr or b"could not decompress" in q.stderr)
