@@ -465,36 +465,36 @@ struct RecordStream {
         return true;
     }
     void start_plain(uint64_t skip) {
-        th = std::thread([this, skip] {
-          try {
-            std::string id;
-            std::vector<uint8_t> scratch;
-            for (uint64_t k = 0; k < skip; k++) { scratch.clear(); if (!r.next(id, scratch)) break; }     // handed out before the restart
-            for (;;) {
-                Block *b = nullptr;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return stop || ready.size() < DEPTH; });
-                    if (stop) return;
-                    if (!spare.empty()) { b = spare.front(); spare.pop_front(); }
-                }
-                if (!b) b = new Block();
-                b->clear();
-                bool more = true;
-                while (b->n() < BLOCK_RECS && b->seq.size() < BLOCK_BYTES) {
-                    if (!r.next(id, b->seq)) { more = false; break; }
-                    b->ids.insert(b->ids.end(), id.begin(), id.end());
-                    b->id_end.push_back((uint32_t)b->ids.size());
-                    b->seq_end.push_back((uint32_t)b->seq.size());
-                }
-                std::lock_guard<std::mutex> lk(mu);
-                if (b->n()) ready.push_back(b); else spare.push_back(b);
-                if (!more) done = true;
-                cv.notify_all();
-                if (!more) return;
+        th = std::thread([this, skip] { try { plain_loop(skip); } catch (const std::exception &e) { broke(e.what()); } });
+    }
+    // the plain parser: record by record into blocks, a few blocks ahead of the consumer
+    void plain_loop(uint64_t skip) {
+        std::string id;
+        std::vector<uint8_t> scratch;
+        for (uint64_t k = 0; k < skip; k++) { scratch.clear(); if (!r.next(id, scratch)) break; }     // handed out before the restart
+        for (;;) {
+            Block *b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || ready.size() < DEPTH; });
+                if (stop) return;
+                if (!spare.empty()) { b = spare.front(); spare.pop_front(); }
             }
-          } catch (const std::exception &e) { broke(e.what()); }
-        });
+            if (!b) b = new Block();
+            b->clear();
+            bool more = true;
+            while (b->n() < BLOCK_RECS && b->seq.size() < BLOCK_BYTES) {
+                if (!r.next(id, b->seq)) { more = false; break; }
+                b->ids.insert(b->ids.end(), id.begin(), id.end());
+                b->id_end.push_back((uint32_t)b->ids.size());
+                b->seq_end.push_back((uint32_t)b->seq.size());
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (b->n()) ready.push_back(b); else spare.push_back(b);
+            if (!more) done = true;
+            cv.notify_all();
+            if (!more) return;
+        }
     }
     // a parser thread ends with an error: the consumer gets it after the blocks that are complete
     void broke(const char *what) {
@@ -573,65 +573,65 @@ struct RecordStream {
                     cv.notify_all();
                 }
             });
-        th = std::thread([this] {
-          try {
-            const size_t PIECE = std::max<size_t>(tune.parse_piece, 64);
-            std::vector<char> carry;
-            bool eof = false;
-            auto give = [&](Text *t) {
-                std::lock_guard<std::mutex> lk(mu);
-                work_q.push_back({cut_n++, t});
-                cv.notify_all();
-            };
-            while (!eof) {
-                Text *t = nullptr;
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return stop || cut_n - next_n < max_inflight; });
-                    if (stop) return;
-                    if (!text_pool.empty()) { t = text_pool.front(); text_pool.pop_front(); }
+        th = std::thread([this] { try { cutter_loop(); } catch (const std::exception &e) { broke(e.what()); } });
+    }
+    // cuts the text into pieces that end on record boundaries and hands them to the workers
+    void cutter_loop() {
+        const size_t PIECE = std::max<size_t>(tune.parse_piece, 64);
+        std::vector<char> carry;
+        bool eof = false;
+        auto give = [&](Text *t) {
+            std::lock_guard<std::mutex> lk(mu);
+            work_q.push_back({cut_n++, t});
+            cv.notify_all();
+        };
+        while (!eof) {
+            Text *t = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || cut_n - next_n < max_inflight; });
+                if (stop) return;
+                if (!text_pool.empty()) { t = text_pool.front(); text_pool.pop_front(); }
+            }
+            if (!t) t = new Text();
+            if (t->d.size() < PIECE + (1u << 20)) t->d.resize(PIECE + (1u << 20));
+            t->n = carry.size();
+            if (t->n > t->d.size()) t->d.resize(t->n + PIECE);
+            if (t->n) memcpy(t->d.data(), carry.data(), t->n);
+            carry.clear();
+            size_t want = PIECE;
+            size_t cut = 0;
+            for (;;) {
+                while (t->n < want) {                             // fill up to the piece size
+                    if (t->d.size() < want + 1) t->d.resize(want + 1);
+                    const int got = r.read_text(t->d.data() + t->n, want - t->n);
+                    if (got < 0) fail("read error in %s: %s", path.c_str(), r.error());
+                    if (got == 0) { eof = true; break; }
+                    t->n += (size_t)got;
                 }
-                if (!t) t = new Text();
-                if (t->d.size() < PIECE + (1u << 20)) t->d.resize(PIECE + (1u << 20));
-                t->n = carry.size();
-                if (t->n > t->d.size()) t->d.resize(t->n + PIECE);
-                if (t->n) memcpy(t->d.data(), carry.data(), t->n);
-                carry.clear();
-                size_t want = PIECE;
-                size_t cut = 0;
-                for (;;) {
-                    while (t->n < want) {                             // fill up to the piece size
-                        if (t->d.size() < want + 1) t->d.resize(want + 1);
-                        const int got = r.read_text(t->d.data() + t->n, want - t->n);
-                        if (got < 0) fail("read error in %s: %s", path.c_str(), r.error());
-                        if (got == 0) { eof = true; break; }
-                        t->n += (size_t)got;
-                    }
-                    if (eof) {                                        // the rest of the file is the last piece
-                        if (t->n && t->d[t->n - 1] != '\n') t->d[t->n++] = '\n';
-                        cut = t->n;
-                        break;
-                    }
-                    cut = cut_point(t->d.data(), t->n);
-                    if (cut) break;
-                    if (want >= PIECE_MAX) { cut = 0; break; }        // no record boundary in 256 MB of text
-                    want *= 2;                                        // very long records: look at more text
-                }
-                if (!eof && !cut) { t->n = 0; give(t); break; }      // an empty piece tells the consumer to fall back
-                if (eof && !t->n) {
-                    std::lock_guard<std::mutex> lk(mu);
-                    text_pool.push_back(t);
+                if (eof) {                                        // the rest of the file is the last piece
+                    if (t->n && t->d[t->n - 1] != '\n') t->d[t->n++] = '\n';
+                    cut = t->n;
                     break;
                 }
-                carry.assign(t->d.data() + cut, t->d.data() + t->n);
-                t->n = cut;
-                give(t);
+                cut = cut_point(t->d.data(), t->n);
+                if (cut) break;
+                if (want >= PIECE_MAX) { cut = 0; break; }        // no record boundary in 256 MB of text
+                want *= 2;                                        // very long records: look at more text
             }
-            std::lock_guard<std::mutex> lk(mu);
-            done = true;
-            cv.notify_all();
-          } catch (const std::exception &e) { broke(e.what()); }
-        });
+            if (!eof && !cut) { t->n = 0; give(t); break; }      // an empty piece tells the consumer to fall back
+            if (eof && !t->n) {
+                std::lock_guard<std::mutex> lk(mu);
+                text_pool.push_back(t);
+                break;
+            }
+            carry.assign(t->d.data() + cut, t->d.data() + t->n);
+            t->n = cut;
+            give(t);
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        done = true;
+        cv.notify_all();
     }
     void stop_threads() {
         { std::lock_guard<std::mutex> lk(mu); stop = true; }
