@@ -36,6 +36,7 @@
 #endif
 
 extern "C" void kmcpg_internal_reader_stats(uint64_t *pieces, uint64_t *fallbacks);      // test hook of reader.cpp
+extern "C" int kmcpg_internal_unmatched_results(const uint64_t *off, uint32_t n_seqs, int paired, int k, kmcpg_results *out);   // test hook of engine.cpp
 
 namespace {
 
@@ -94,6 +95,7 @@ struct Opts {
     bool all_devices = false;
     std::string gpu_mode = "auto";   // --gpu-mode: shard (index split over the devices), replicate (reads split), auto (replicate when the index fits)
     double qcov = 0.55, tcov = 0, max_fpr = 0.01;
+    bool dry_run = false;            // --dry-run: no device, no database: every query comes out unmatched (host-only tests of the plumbing)
     bool try_se = false, whole_file = false, use_filename = false, default_name_map = false, keep_unmatched = false, no_header = false,
          do_not_sort = false;
     size_t batch_reads = 1u << 18, batch_bytes = 256u << 20;
@@ -568,6 +570,8 @@ int run(int argc, char **argv) {
         else if (a == "--log") o.log_file = sval();
         else if (a == "--gpu") o.devices.assign(1, atoi(sval().c_str()));
         else if (a == "--gpu-mode") o.gpu_mode = sval();
+        else if (a == "--dry-run") o.dry_run = true;
+        else if (a == "--batch-reads") o.batch_reads = (size_t)std::max(1L, atol(sval().c_str()));     // queries per engine call (default 262144)
         else if (a == "--compression-level") { g_compression_level = atoi(sval().c_str()); if (g_compression_level < 1 || g_compression_level > 9) die("--compression-level should be in range [1, 9]"); }
         else if (a == "--inflate-threads") g_tune.inflate_threads = atoi(sval().c_str());
         else if (a == "--parse-threads") g_tune.parse_threads = atoi(sval().c_str());
@@ -595,7 +599,8 @@ int run(int argc, char **argv) {
     auto t_start = std::chrono::steady_clock::now();
 
     // ---- flag checks (S:157-205) ----
-    if (o.db_dirs.empty()) die("flag -d/--db-dir needed");
+    if (o.db_dirs.empty() && !o.dry_run) die("flag -d/--db-dir needed");
+    if (o.dry_run) { o.db_dirs.clear(); o.ref_counts_file.clear(); }
     if (o.min_qlen < 0) die("value of flag --min-query-len should be greater than or equal to 0");
     if (o.min_kmers <= 0) die("value of flag --min-kmers should be greater than 0");
     if (!(o.max_fpr > 0)) die("value of flag --max-fpr should be greater than 0");
@@ -651,7 +656,13 @@ int run(int argc, char **argv) {
         dbs.emplace_back();
         dbs.back().dir = subs[0];
     }
-    if (o.all_devices) {                  // every visible device: probe the ordinals until one is refused
+    if (o.dry_run) {                      // a database of nothing: k = 21, no targets, no device
+        dbs.emplace_back();
+        memset(&dbs[0].info, 0, sizeof(dbs[0].info));
+        dbs[0].info.n_ks = 1; dbs[0].info.ks[0] = 21;
+        logf("WARN", "--dry-run: no device and no database are used, every query is reported unmatched");
+    }
+    if (o.all_devices && !o.dry_run) {    // every visible device: probe the ordinals until one is refused
         for (int d = 0; d < 64; d++) {
             kmcpg_ctx *probe = nullptr;
             if (kmcpg_create(d, &probe)) break;
@@ -661,6 +672,7 @@ int run(int argc, char **argv) {
         if (o.devices.empty()) die("%s", kmcpg_last_error(nullptr));
     }
     for (auto &db : dbs) {
+        if (o.dry_run) break;
         const int world = (int)o.devices.size();
         auto t_db = std::chrono::steady_clock::now();
         std::vector<kmcpg_ctx *> shard((size_t)world, nullptr);
@@ -889,7 +901,8 @@ int run(int argc, char **argv) {
         for (size_t d = 0; d < dbs.size(); d++) {
             const uint32_t ns = bt->b.n_seqs;
             const int nc = (int)dbs[d].ctxs.size();
-            const int rc = nc == 1           ? kmcpg_engine_search(dbs[d].ctxs[0], &eo, bt->b.seq, bt->b.off, ns, &job->res[d])
+            const int rc = o.dry_run         ? kmcpg_internal_unmatched_results(bt->b.off, ns, paired, dbs[d].info.ks[0], &job->res[d])
+                           : nc == 1         ? kmcpg_engine_search(dbs[d].ctxs[0], &eo, bt->b.seq, bt->b.off, ns, &job->res[d])
                            : dbs[d].replicas ? kmcpg_engine_search_replicas(dbs[d].ctxs.data(), nc, &eo, bt->b.seq, bt->b.off, ns, &job->res[d])
                                              : kmcpg_engine_search_sharded(dbs[d].ctxs.data(), nc, &eo, bt->b.seq, bt->b.off, ns, &job->res[d]);
             if (rc) {

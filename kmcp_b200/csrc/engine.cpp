@@ -864,6 +864,20 @@ int kmcpg_internal_engine_standin(const kmcpg_engine_opts *o, uint32_t n_queries
     return rc;
 }
 
+// test hook (kmcp-gpu search --dry-run, host only): the result of a batch in which nothing matched, so that the command's
+// reader → engine → writer plumbing can run without a device
+int kmcpg_internal_unmatched_results(const uint64_t *off, uint32_t n_seqs, int paired, int k, kmcpg_results *out) {
+    if (!out || (n_seqs && !off) || (paired && (n_seqs & 1))) return KMCPG_EINVAL;
+    const uint32_t step = paired ? 2 : 1, nq = n_seqs / step;
+    *out = alloc_results(nq, 0);
+    for (uint32_t q = 0; q < nq; q++) {
+        out->query_len[q] = (int32_t)(off[(size_t)q * step + step] - off[(size_t)q * step]);
+        out->n_kmers[q] = 0; out->k_used[q] = k;
+        out->match_off[q + 1] = 0;
+    }
+    return KMCPG_OK;
+}
+
 // test hook (tests/test_abi.py, no GPU needed): the k-way merge the sharded engine applies to the per-shard hit lists
 void kmcpg_internal_merge_hits(const kmcpg_hit *const *lists, const uint64_t *n, int k, kmcpg_hit *out, uint32_t first_query, uint32_t n_queries, int threads) {
     if (n_queries == 0) {                 // range not given: take it from the lists

@@ -326,3 +326,42 @@ def test_reader_xz_bzip2_zstd_inputs(files, tmp_path):
     open(z, "wb").write(b"\x28\xb5\x2f\xfd" + b"not really zstd" * 10)
     q = subprocess.run([EXE, "parse", z], capture_output=True, timeout=60)
     assert q.returncode != 0 and (b"zstd is not installed" in q.stderr or b"could not decompress" in q.stderr)
+
+
+def test_search_command_plumbing_without_a_device(files, tmp_path):
+    """kmcp-gpu search --dry-run: the command's reader → engine thread → writer pipeline with no device and no database (every
+    query comes out unmatched): IDs, lengths and running query numbers in input order over many batches, plain and .gz output
+    (asynchronous gzip members), paired input, the trailer lines (S:1023-1025)"""
+    recs = files["recs"]
+    hdr = "#query\tqLen\tqKmers\tFPR\thits\ttarget\tchunkIdx\tchunks\ttLen\tkSize\tmKmers\tqCov\ttCov\tjacc\tqueryIdx\n"
+    tail = "# input queries: %d\n# matched queries: 0\n# matched percentage: 0.0000%%\n"
+
+    def row(i, ln, idx):
+        return "%s\t%d\t0\t0\t0\t\t-1\t0\t0\t21\t0\t0\t0\t0\t%d\n" % (i.decode(), ln, idx)
+
+    def run(args, out):
+        p = subprocess.run([EXE, "search", "--dry-run", "-q", "-K", "-o", out] + args, capture_output=True, timeout=300)
+        assert p.returncode == 0, p.stderr.decode()
+        return gzip.open(out, "rb").read().decode() if out.endswith(".gz") else open(out).read()
+
+    exp = hdr + "".join(row(i, len(s), n) for n, (i, s) in enumerate(recs)) + tail % len(recs)
+    assert run([files["fq_gz"]], str(tmp_path / "a.tsv")) == exp
+    assert run(["--batch-reads", "500", files["fq_gz"]], str(tmp_path / "b.tsv")) == exp
+    assert run(["--batch-reads", "333", "--inflate-threads", "3", "--parse-threads", "2", files["fq_gz"]], str(tmp_path / "c.tsv.gz")) == exp
+    # several files: query numbers run on
+    many = recs[:1500] + recs[:500] + recs
+    assert run(["--batch-reads", "1000", files["fa"], files["fq_plain"], files["fq_gz"]], str(tmp_path / "d.tsv.gz")) == \
+        hdr + "".join(row(i, len(s), n) for n, (i, s) in enumerate(many)) + tail % len(many)
+    # paired: the query length is the sum of the mates, the pairs end with the shorter file
+    exp_pe = hdr + "".join(row(i, 2 * len(s), n) for n, (i, s) in enumerate(recs[:4000])) + tail % 4000
+    assert run(["--batch-reads", "700", "-1", files["fq_gz"], "-2", files["fq2_gz"]], str(tmp_path / "e.tsv")) == exp_pe
+    # without -K nothing but the header and the trailer; -H drops the header
+    p = subprocess.run([EXE, "search", "--dry-run", "-q", "-H", "-o", str(tmp_path / "f.tsv"), files["fq_plain"]], capture_output=True, timeout=300)
+    assert p.returncode == 0 and open(str(tmp_path / "f.tsv")).read() == tail % 500
+    # stdin
+    with open(files["fq_plain"], "rb") as f:
+        p = subprocess.run([EXE, "search", "--dry-run", "-q", "-K", "-o", "-"], stdin=f, capture_output=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.decode() == hdr + "".join(row(i, len(s), n) for n, (i, s) in enumerate(recs[:500])) + tail % 500
+    # a missing input file ends the command with the reference's kind of message and a non-zero code
+    p = subprocess.run([EXE, "search", "--dry-run", "-q", "-o", str(tmp_path / "g.tsv"), str(tmp_path / "nothing.fq")], capture_output=True, timeout=300)
+    assert p.returncode != 0 and b"no such file" in p.stderr
