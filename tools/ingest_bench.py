@@ -93,6 +93,16 @@ def main():
     t0 = time.perf_counter()
     zlib.compress(open(tsv, "rb").read(50_000_000), 6)
     out["writer"]["zlib level 6, one thread (python)"] = {"MB_per_s": round(50.0 / (time.perf_counter() - t0), 1)}
+    # the whole command without a device (--dry-run: every query unmatched): reader stage + engine thread + writer, -K prints a row per query
+    out["search --dry-run"] = {}
+    for name, args in (("fastq, no rows", [fq, "-o", os.path.join(tmp, "d.tsv")]), ("fastq -> tsv (-K)", ["-K", fq, "-o", os.path.join(tmp, "d.tsv")]),
+                       ("fastq.gz -> tsv.gz (-K)", ["-K", gz, "-o", os.path.join(tmp, "d.tsv.gz")]),
+                       ("paired fastq.gz -> tsv.gz (-K)", ["-K", "-1", gz, "-2", gz, "-o", os.path.join(tmp, "d.tsv.gz")])):
+        best_v = 0.0
+        for _ in range(3):
+            s = run(["search", "--dry-run"] + args).stderr.decode()
+            best_v = max(best_v, float(re.search(r"speed: ([\d.]+) million queries per minute", s).group(1)))
+        out["search --dry-run"][name] = {"M_queries_per_s": round(best_v / 60, 2)}
     print(json.dumps(out, indent=1))
     subprocess.run(["rm", "-rf", tmp])
 
