@@ -868,12 +868,7 @@ int run(int argc, char **argv) {
             for (int t = 1; t < FT; t++) fs.push_back(std::async(std::launch::async, fmt, t));
             fmt(0);
             for (auto &f : fs) f.get();
-            std::string all;
-            size_t sz = 0;
-            for (auto &t : text) sz += t.size();
-            all.reserve(sz);
-            for (auto &t : text) all += t;
-            w.write(std::move(all));
+            for (auto &t : text) w.write(std::move(t));               // in range order: no copy into one string first
             for (auto v : nmatched) matched += v;
             total += nq;
             if (refcounts && kmcpg_refcounts_add(refcounts, &job->res[0])) die("--ref-counts: inconsistent chunk numbering in the database");
