@@ -5,14 +5,17 @@
 //   * the file is cut into chunks of CHUNK compressed bytes; a worker looks for the first block header at or behind its
 //     chunk's first bit (dynamic-Huffman headers are self-validating: complete code-length code, complete literal/length
 //     code with an end-of-block symbol, code lengths that add up exactly), and decodes from there up to the first block
-//     boundary at or behind the next chunk's first bit;
+//     boundary at or behind the next chunk's first bit; a gzip MEMBER that starts there (bgzip / pgzip files, `cat a.gz b.gz`)
+//     is a place to start as well, and a better one: nothing in front of it can be copied from;
 //   * bytes copied from in front of the chunk are not known yet: the worker writes 16-bit symbols, 0..255 for a known byte
 //     and 0x8000+j for "byte j of the 32 KB window in front of this chunk"; markers are copied like any other symbol.  Once
 //     the newest 32 KB hold no marker the worker carries on with plain bytes;
 //   * the consumer takes the chunks in file order, checks that each one starts at the very bit the data before it ended at
 //     (otherwise the chunk is discarded and the stretch is decoded again in order — a false block start, or a boundary the
 //     search cannot see such as stored and fixed-Huffman blocks), replaces the markers from the real window, and verifies
-//     CRC-32 and ISIZE of every member over the final bytes.
+//     CRC-32 and ISIZE of every member over the final bytes.  Streams where the workers keep missing (stored blocks: incompressible
+//     data) are decoded in order after a few misses; a chunk that decodes to more than a cap ends the parallel mode (memory stays
+//     bounded for any compression ratio) and the caller falls back to the sequential decoder.
 // The bytes delivered are exactly those of fastgz::Inflater / gzread(); tests/test_fastgz.py compares the two on every stream.
 //
 // Host-only code.  Needs a seekable file (pread); pipes use fastgz::Inflater.
