@@ -365,3 +365,27 @@ def test_search_command_plumbing_without_a_device(files, tmp_path):
     # a missing input file ends the command with the reference's kind of message and a non-zero code
     p = subprocess.run([EXE, "search", "--dry-run", "-q", "-o", str(tmp_path / "g.tsv"), str(tmp_path / "nothing.fq")], capture_output=True, timeout=300)
     assert p.returncode != 0 and b"no such file" in p.stderr
+
+
+@pytest.mark.reference_data
+def test_search_command_has_every_flag_of_the_reference():
+    """every flag `kmcp search` declares (search.go init(): name, shorthand, default) is offered by `kmcp-gpu search` with the same
+    name, shorthand and default — read from the reference's source, so it only runs where /root/reference exists"""
+    import re
+    src = "/root/reference/kmcp/cmd/search.go"
+    if not os.path.exists(src):
+        pytest.skip("no reference checkout here")
+    go = open(src).read()
+    live = "\n".join(l for l in go.splitlines() if not l.strip().startswith("//"))          # two flags are commented out in the reference
+    flags = re.findall(r'searchCmd\.Flags\(\)\.(\w+)P\("([\w-]+)",\s*"(\w?)",\s*([^,]+),', live)
+    assert len(flags) >= 20
+    p = subprocess.run([EXE, "search", "--help"], capture_output=True, timeout=60)
+    helptext = (p.stdout + p.stderr).decode()
+    for kind, name, short, default in flags:
+        assert "--" + name in helptext, name
+        if short:
+            assert re.search(r"-%s, --%s\b|--%s\b.*-%s\b|-%s, --\S+ / --%s" % (short, name, name, short, short, name), helptext) or ("-" + short + ",") in helptext, (name, short)
+        default = default.strip().strip('"')
+        if kind in ("Int", "Float64") and default not in ("0", "0.0"):
+            m = re.search(r"--%s\b[^\n]*\(default ([^)]+)\)" % re.escape(name), helptext)
+            assert m and float(m.group(1)) == float(default), (name, default, m and m.group(1))
