@@ -129,6 +129,7 @@ void usage() {
         "  -w, --load-whole-db / --low-mem  accepted for compatibility (the index always lives in HBM)\n"
         "  -j, --threads int                host threads for the post-filter (default all)\n"
         "  -q, --quiet / --log string       logging\n"
+        "  -i, --infile-list string         file of input files list (one file per line)\n"
         "      --gpu int                    CUDA device ordinal (default 0)\n"
         "      --gpus list|all              several devices, e.g. 0,1,2,3: every database is sharded over them by index block\n"
         "                                   (by column range when it has fewer blocks than devices); every device sees every read\n"

@@ -381,6 +381,10 @@ def test_search_command_has_every_flag_of_the_reference():
     assert len(flags) >= 20
     p = subprocess.run([EXE, "search", "--help"], capture_output=True, timeout=60)
     helptext = (p.stdout + p.stderr).decode()
+    root = open("/root/reference/kmcp/cmd/root.go").read()
+    live_root = "\n".join(l for l in root.splitlines() if not l.strip().startswith("//"))
+    for name, short in re.findall(r'RootCmd\.PersistentFlags\(\)\.\w+P\("([\w-]+)",\s*"(\w?)"', live_root):     # -j, -q, -i, --log
+        assert "--" + name in helptext and (not short or "-" + short + "," in helptext), name
     for kind, name, short, default in flags:
         assert "--" + name in helptext, name
         if short:
