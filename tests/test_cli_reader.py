@@ -362,6 +362,12 @@ def test_search_command_plumbing_without_a_device(files, tmp_path):
     with open(files["fq_plain"], "rb") as f:
         p = subprocess.run([EXE, "search", "--dry-run", "-q", "-K", "-o", "-"], stdin=f, capture_output=True, timeout=300)
     assert p.returncode == 0 and p.stdout.decode() == hdr + "".join(row(i, len(s), n) for n, (i, s) in enumerate(recs[:500])) + tail % 500
+    # -i/--infile-list: one file per line
+    lst = str(tmp_path / "files.txt")
+    open(lst, "w").write(files["fq_plain"] + "\n\n" + files["fa"] + "\n")
+    got = run(["-i", lst], str(tmp_path / "h.tsv"))
+    both = recs[:500] + recs[:1500]
+    assert got == hdr + "".join(row(i, len(s), n) for n, (i, s) in enumerate(both)) + tail % len(both)
     # a missing input file ends the command with the reference's kind of message and a non-zero code
     p = subprocess.run([EXE, "search", "--dry-run", "-q", "-o", str(tmp_path / "g.tsv"), str(tmp_path / "nothing.fq")], capture_output=True, timeout=300)
     assert p.returncode != 0 and b"no such file" in p.stderr
