@@ -70,7 +70,9 @@ void logf(const char *level, const char *fmt, ...) {
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     logf("ERRO", "%s", buf);
-    exit(255);
+    fflush(stderr);
+    if (g_log) fflush(g_log);
+    _exit(255);          // like os.Exit: at once, without unwinding under the reader / writer / engine threads that are still running
 }
 
 bool is_dir(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
@@ -629,6 +631,38 @@ int run(int argc, char **argv) {
         for (auto &f : files) if (f != "-" && f == o.out_file) die("out file should not be one of the input file");
     }
 
+    // ---- three-stage pipeline: reader thread (inflate + parse + pack) → this thread (GPU engine, every database) →
+    //      writer thread (merge across databases, TSV formatting on several threads, parallel gzip), all in input order ----
+    struct Job { Batch *batch = nullptr; std::vector<kmcpg_results> res; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Batch *> in_q;
+    std::deque<Job *> out_q;
+    bool in_done = false, out_done = false;
+    uint64_t total = 0, matched = 0;
+    std::thread reader;
+    auto start_reader = [&](int kmax) {
+        ReaderSetup rc;
+        rc.paired = paired; rc.read1 = o.read1; rc.read2 = o.read2; rc.files = files;
+        rc.whole_file = o.whole_file; rc.use_filename = o.use_filename; rc.query_id = o.query_id;
+        rc.batch_reads = o.batch_reads; rc.batch_bytes = o.batch_bytes; rc.kmax = kmax;
+        reader = std::thread([&, rc] {
+            read_batches(rc, [&](Batch *bt) {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return in_q.size() < 2; });
+                in_q.push_back(bt);
+                cv.notify_all();
+            });
+            std::lock_guard<std::mutex> lk(mu);
+            in_done = true;
+            cv.notify_all();
+        });
+    };
+    // the first batches are read while the index travels to the GPU — unless the reader needs something of the database first
+    // (-g joins records with k-1 'N'; with several devices the batch size depends on how the index is laid out)
+    const bool early_reader = !o.whole_file && o.devices.size() == 1 && !o.all_devices;
+    if (early_reader) start_reader(21);
+
     // ---- databases (S:299-324): every child directory of a -d holding __db.yml; several -d = several databases ----
     struct Db {
         std::string dir;
@@ -775,32 +809,7 @@ int run(int argc, char **argv) {
     eo.max_fpr = o.max_fpr; eo.sort_by = sort_by; eo.do_not_sort = o.do_not_sort; eo.top_n_scores = o.top_scores; eo.try_se = o.try_se;
     eo.paired = paired; eo.threads = o.threads;
 
-    // ---- three-stage pipeline: reader thread (inflate + parse + pack) → this thread (GPU engine, every database) →
-    //      writer thread (merge across databases, TSV formatting on several threads, parallel gzip), all in input order ----
-    struct Job { Batch *batch = nullptr; std::vector<kmcpg_results> res; };
-    std::mutex mu;
-    std::condition_variable cv;
-    std::deque<Batch *> in_q;
-    std::deque<Job *> out_q;
-    bool in_done = false, out_done = false;
-    uint64_t total = 0, matched = 0;
-    const int kmax = dbs[0].info.ks[0];
-
-    std::thread reader([&] {
-        ReaderSetup rc;
-        rc.paired = paired; rc.read1 = o.read1; rc.read2 = o.read2; rc.files = files;
-        rc.whole_file = o.whole_file; rc.use_filename = o.use_filename; rc.query_id = o.query_id;
-        rc.batch_reads = o.batch_reads; rc.batch_bytes = o.batch_bytes; rc.kmax = kmax;
-        read_batches(rc, [&](Batch *bt) {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return in_q.size() < 2; });
-            in_q.push_back(bt);
-            cv.notify_all();
-        });
-        std::lock_guard<std::mutex> lk(mu);
-        in_done = true;
-        cv.notify_all();
-    });
+    if (!early_reader) start_reader(dbs[0].info.ks[0]);
 
     const Less less{sort_by};
     std::thread writer([&] {
