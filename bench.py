@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py — reads/s of the `kmcp search` hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-Workload (N=1) = BASELINE.json configs[1]: synthetic 10k-chunk COBS index (1,000 seeded random genomes x
-4 Mb, 10 chunks, k=21, h=1, fpr 0.3, ONE block of 10,000 targets ≈ 1.4 GB ≫ L2) resident in HBM, 150 bp
-synthetic reads (80 % sampled from the genomes with 1 % substitutions, 20 % random).  A step = one batch of
-READS_PER_STEP reads through the whole hot path (hash → locs → probe → hit sort → D2H).  Every step uses
-different reads; the index is far larger than L2, so no explicit L2 flush is needed (stated in `config`).
+Workload = BASELINE.json configs[1]: synthetic 10k-chunk COBS index (1,000 seeded random genomes x 4 Mb, 10 chunks, k=21,
+h=1, fpr 0.3, ONE block of 10,000 targets ≈ 1.4 GB ≫ L2) per GPU, resident in HBM, 150 bp synthetic reads (80 % sampled from
+the genomes with 1 % substitutions, 20 % random).  A step = one batch of READS_PER_STEP reads through the whole hot path
+(hash → probe → hit sort → D2H).  Every step uses different reads; the index is far larger than L2, so no explicit L2 flush
+is needed (stated in `config`).  Two batches are kept submitted (kmcpg_search_submit), so step s+1 starts on the GPU the
+moment step s ends.
 
-  value   : reads/s, inputs resident in HBM when the timed region starts (kmcpg_search_batch_device).
-  e2e     : reads/s through the host-facing engine call with PINNED HOST buffers: H2D of the reads,
-            kernels, D2H of hits, host post-filter (tCov/FPR/sort) — the number to compare with the CPU arm.
-  roofline: probe kernel only; achieved = algorithmic row bytes (n_kmers·h·Σ numRowBytes per read) of a
-            launch ÷ its CUDA-event duration on the launching stream; peak = MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline: the oracle's restatement of the reference algorithm (64-row buffer, byte transpose,
-            positional popcount) on all host threads, bounded sample — kind "port" (the Go reference cannot
-            be built here: no Go toolchain).
+  value   : reads/s, inputs resident in HBM when the timed region starts.
+  e2e     : reads/s from PINNED HOST buffers to matches in host memory: H2D of the reads, kernels, D2H of hits, host post-filter
+            (tCov/FPR/sort) — the number to compare with the CPU arm.
+  roofline: probe kernel only; achieved = algorithmic row bytes (n_kmers·h·Σ numRowBytes per read) of a launch ÷ its
+            CUDA-event duration on the launching stream; peak = MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline: the oracle's restatement of the reference algorithm (64-row buffer, byte transpose, positional popcount) on all
+            host threads, bounded sample — kind "port" (the Go reference cannot be built here: no Go toolchain).
+  gtdb_scale: BASELINE.json configs[3] shape — ONE fixed index of 852,050 targets (85,205 genomes x 10 chunks), h=3, 32 blocks
+            of 26,632 targets (3,329-byte rows), block-sharded over the N ranks exactly as kmcpg_open_db(shard_rank, shard_world)
+            shards a database, the SAME reads at every N (strong scaling): job reads/s, per-rank probe GB/s, and a digest of the
+            merged (query, target, count) list that must be equal at N = 1, 2, 4, 8.
 
-N>1 (torchrun, one rank per GPU): index blocks shard across ranks (rank r holds block r, 10,000 targets;
-the DB grows with N = weak scaling), the read batch is broadcast with NCCL, per-rank hit lists are
-concatenated on the host of rank 0.  No data-path collective besides the broadcast.
+N>1 (torchrun, one rank per GPU; kmcp_b200/multigpu.py): ONE database of N blocks of 10,000 targets, rank r holds the block the
+shard plan gives it (the index grows with N = weak scaling).  Inside the timed region of `value`: the NCCL broadcast of every
+batch from rank 0's HBM (NVLink; prefetched one step ahead), the search on every rank, and the return of every rank's hit list to
+rank 0's host (device→host into per-rank shared-memory segments that rank 0 reads in place).  `e2e` adds rank 0's H2D of every batch
+from pinned host memory, the merge of the per-rank lists and the host post-filter on rank 0.
 
 `--impl reference` times the CPU port alone (rank 0), same metric/config/unit.
 """
@@ -39,11 +45,15 @@ sys.path.insert(0, ROOT)
 SCALE = os.environ.get("KMCP_BENCH_SCALE", "full")
 if SCALE == "full":
     N_GENOMES, GENOME_LEN, READS_PER_STEP, CPU_SAMPLE0 = 1000, 4_000_000, 1_000_000, 20_000
+    # GTDB-scale shape: genome length scaled ("scale down genome length, not target count — row width is what matters")
+    GTDB_GENOMES, GTDB_GL, GTDB_BLOCK, GTDB_READS = 85_205, int(os.environ.get("KMCP_GTDB_GL", 875_000)), 26_632, int(os.environ.get("KMCP_GTDB_READS", 100_000))
 else:  # quick functional check of the harness
     N_GENOMES, GENOME_LEN, READS_PER_STEP, CPU_SAMPLE0 = 100, 200_000, 100_000, 5_000
+    GTDB_GENOMES, GTDB_GL, GTDB_BLOCK, GTDB_READS = 2_000, 60_000, 632, 20_000
 N_CHUNKS, OVERLAP, K, H, FPR, READ_LEN = 10, 150, 21, 1, 0.3, 150
 BLOCK_SIZE = N_GENOMES * N_CHUNKS
 GENOME_SEED, READ_SEED = 1, 2
+GTDB_SEED, GTDB_READ_SEED, GTDB_H, GTDB_STEPS, GTDB_WARMUP = 3, 4, 3, 3, 1
 METRIC = "reads/sec (kmcp search, 150bp)"
 
 
@@ -115,6 +125,13 @@ def ncu_traffic():
     return None
 
 
+def db_yml(alias, n_targets, files, hashes=H, block_size=BLOCK_SIZE):
+    return {"version": 4, "unikiVersion": 4, "alias": alias, "k": K, "ks": [K], "hashed": True, "canonical": True, "scaled": False,
+            "scale": 0, "minimizer": False, "minimizer-w": 0, "syncmer": False, "syncmer-s": 0, "split-seq": True, "split-size": 0,
+            "split-num": N_CHUNKS, "split-overlap": OVERLAP, "compact-size": False, "hashes": hashes, "fpr": FPR,
+            "numNameGroups": int(n_targets), "blocksize": block_size, "totalKmers": 0, "files": files}
+
+
 def dump_db_for_cpu(ctx, tmpdir):
     """HBM-resident synthetic DB → .uniki files + __db.yml that the CPU port can open"""
     from oracle import oracle as O
@@ -126,11 +143,7 @@ def dump_db_for_cpu(ctx, tmpdir):
         fn = "_block%03d.uniki" % (b + 1)
         ctx.write_block(b, os.path.join(r001, fn))
         files.append(fn)
-    O.write_db_yml(os.path.join(r001, "__db.yml"), {
-        "version": 4, "unikiVersion": 4, "alias": "bench", "k": K, "ks": [K], "hashed": True, "canonical": True, "scaled": False,
-        "scale": 0, "minimizer": False, "minimizer-w": 0, "syncmer": False, "syncmer-s": 0, "split-seq": True, "split-size": 0,
-        "split-num": N_CHUNKS, "split-overlap": OVERLAP, "compact-size": False, "hashes": H, "fpr": FPR,
-        "numNameGroups": int(info.n_targets), "blocksize": BLOCK_SIZE, "totalKmers": 0, "files": files})
+    O.write_db_yml(os.path.join(r001, "__db.yml"), db_yml("bench", info.n_targets, files))
     return r001
 
 
@@ -152,30 +165,44 @@ def time_cpu_port(r001, reads_u8, n_reads, target_seconds=12.0):
     return n1 / dt, cores, n1
 
 
-def stage_reference_dbs(tmp, world, n_reads_total):
-    """the index of every shard of this arm's config (world blocks of 10,000 targets, seeds GENOME_SEED + r) as .uniki files the
-    CPU port can open, plus the seeded reads: built by the GPU index builder (byte-identical to the oracle's builder,
-    tests/test_gpu_parity.py) because the 1.4 GB blocks take minutes on the CPU.  Returns ([R001 dirs], reads u8)."""
+def stage_main(tmp, world, n_reads_total):
+    """helper process of the reference arm (`bench.py --stage-reference`): the index of this arm's config — ONE database of `world`
+    blocks of 10,000 targets, as the b200 arm shards it — as .uniki files the CPU port can open, plus the seeded reads, written under
+    `tmp`.  Built by the GPU index builder (byte-identical to the oracle's builder, tests/test_gpu_parity.py) because the 1.4 GB
+    blocks take minutes on the CPU; the timing process itself never maps libkmcp_gpu.so."""
     from kmcp_b200 import api
+    from oracle import oracle as O
     ctx = api.Context(0)
     try:
-        dirs = []
-        for r in range(world):
-            ctx.build_synth_db(GENOME_SEED + r, N_GENOMES, GENOME_LEN, k=K, n_chunks=N_CHUNKS, overlap=OVERLAP, num_hashes=H, fpr=FPR, block_size=BLOCK_SIZE)
-            dirs.append(dump_db_for_cpu(ctx, os.path.join(tmp, "shard%d" % r)))
+        ctx.build_synth_db(GENOME_SEED, N_GENOMES * world, GENOME_LEN, k=K, n_chunks=N_CHUNKS, overlap=OVERLAP, num_hashes=H, fpr=FPR, block_size=BLOCK_SIZE)
+        r001 = os.path.join(tmp, "R001")
+        os.makedirs(r001, exist_ok=True)
+        info = ctx.db_info()
+        files = []
+        for b in range(info.n_resident_blocks):
+            fn = "_block%03d.uniki" % (b + 1)
+            ctx.write_block(b, os.path.join(r001, fn))
+            files.append(fn)
+        O.write_db_yml(os.path.join(r001, "__db.yml"), db_yml("bench", info.n_targets, files))
         d = ctx.device_alloc(n_reads_total * READ_LEN)
         ctx.synth_reads(READ_SEED, 0, n_reads_total, READ_LEN, GENOME_SEED, N_GENOMES, GENOME_LEN, d)
-        reads = ctx.d2h(d, n_reads_total * READ_LEN)
+        ctx.d2h(d, n_reads_total * READ_LEN).tofile(os.path.join(tmp, "reads.u8"))
         ctx.device_free(d)
     finally:
         ctx.close()
-    return dirs, reads
 
 
-def run_reference(args, rank, world, stage=stage_reference_dbs):
-    """--impl reference: the CPU port of the reference algorithm, rank 0 only, on this arm's config: at N ranks the index is
-    N blocks of 10,000 targets (one per GPU in the b200 arm), every read is searched against all of them, and `value`
-    counts read x shard probes exactly as the b200 arm does."""
+def stage_in_helper_process(tmp, world, n_total):
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), "--stage-reference", tmp, str(world), str(n_total)], env=env, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError((p.stderr.strip().splitlines() or ["helper process failed"])[-1][:160])
+
+
+def run_reference(args, rank, world, stage=stage_in_helper_process):
+    """--impl reference: the CPU port of the reference algorithm, rank 0 only, on this arm's config: at N ranks the index is N blocks
+    of 10,000 targets (one per GPU in the b200 arm), every read is searched against all of them, and `value` counts read x shard
+    probes exactly as the b200 arm does."""
     if rank != 0:
         return
     from oracle import oracle as O
@@ -183,24 +210,26 @@ def run_reference(args, rank, world, stage=stage_reference_dbs):
     tmp = "/dev/shm/kmcp_bench_ref" if os.path.isdir("/dev/shm") else "/tmp/kmcp_bench_ref"
     shutil.rmtree(tmp, ignore_errors=True)
     os.makedirs(tmp)
-    built_by = "gpu index builder (byte-identical to the oracle builder, tests/test_gpu_parity.py)"
+    built_by = "gpu index builder in a helper process (byte-identical to the oracle builder, tests/test_gpu_parity.py)"
     step_reads = max(1000, (50_000 if SCALE == "full" else 5_000) // world)      # the CPU work per step stays the same at every N
     n_total = step_reads * (args.steps + args.warmup)
     try:
-        dirs, reads = stage(tmp, world, n_total)
+        stage(tmp, world, n_total)       # leaves tmp/R001 (the database) and tmp/reads.u8
     except Exception as e:  # no usable GPU: nothing to build the 1.4 GB index with in reasonable time
         shutil.rmtree(tmp, ignore_errors=True)
-        print(json.dumps({"impl": "reference", "unavailable": "cannot stage the synthetic index without the GPU builder: %s" % str(e)[:120]}))
+        print(json.dumps({"impl": "reference", "unavailable": "cannot stage the synthetic index without the GPU builder: %s" % str(e)[:160]}))
         return
-    odbs = [O.DB(d) for d in dirs]
+    reads = np.fromfile(os.path.join(tmp, "reads.u8"), dtype=np.uint8)
+    odb = O.DB(os.path.join(tmp, "R001"))
+    if stage is stage_in_helper_process:
+        assert "kmcp_b200" not in sys.modules, "the reference arm must not load the product library"
     cores = os.cpu_count() or 1
     off = np.arange(step_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN)
     n_hits = [0]
 
-    def step(i):
+    def step(i):      # explicit thread count: torchrun sets OMP_NUM_THREADS=1
         batch = reads[i * step_reads * READ_LEN:(i + 1) * step_reads * READ_LEN]
-        for odb in odbs:          # explicit thread count: torchrun sets OMP_NUM_THREADS=1
-            n_hits[0] += len(odb.search(packed=(batch, off), threads=cores, algo=1).hits)
+        n_hits[0] += len(odb.search(packed=(batch, off), threads=cores, algo=1).hits)
 
     for i in range(args.warmup):
         step(i)
@@ -209,8 +238,7 @@ def run_reference(args, rank, world, stage=stage_reference_dbs):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
     v = world * step_reads * args.steps / dt
-    for odb in odbs:
-        odb.close()
+    odb.close()
     shutil.rmtree(tmp, ignore_errors=True)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -220,17 +248,35 @@ def run_reference(args, rank, world, stage=stage_reference_dbs):
                                         "multi_gpu_units": "value counts read×shard probes (every read against each of the %d 10k-target blocks)" % world if world > 1 else "reads"},
         "job_reads_per_s": step_reads * args.steps / dt,
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port",
-                         "sample": "%d reads per step against %d block(s), restated reference algorithm (oracle algo=1), OpenMP all threads" % (step_reads, world)},
+                         "sample": "%d reads per step against %d block(s), restated reference algorithm (oracle algo=1: 64-row buffer, byte transpose, "
+                                   "positional popcount), OpenMP all threads" % (step_reads, world)},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
+def pack_batches(torch, ctx, seed, first_read, n_steps, n_reads, gseed, n_genomes, genome_len, off_np):
+    """device tensor of n_steps packed batches: per batch the (n_reads + 1) u64 offsets, then the read bytes"""
+    off_bytes, seq_bytes = off_np.nbytes, n_reads * READ_LEN
+    bb = off_bytes + seq_bytes
+    t = torch.empty(n_steps * bb, dtype=torch.uint8, device="cuda")
+    d_off = torch.from_numpy(off_np.view(np.uint8)).cuda()
+    for s in range(n_steps):
+        t[s * bb:s * bb + off_bytes].copy_(d_off)
+        ctx.synth_reads(seed, first_read + s * n_reads, n_reads, READ_LEN, gseed, n_genomes, genome_len, t.data_ptr() + s * bb + off_bytes)
+    torch.cuda.synchronize()
+    return t, bb, off_bytes
+
+
 def main():
+    if len(sys.argv) >= 5 and sys.argv[1] == "--stage-reference":
+        stage_main(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]))
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gtdb", action="store_true", help="skip the GTDB-scale block (development runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -246,29 +292,17 @@ def main():
     from kmcp_b200 import api, multigpu
 
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]             # keeps NCCL's version banner out of stdout: one JSON line only
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            del os.environ["NCCL_DEBUG"]             # keeps NCCL's version banner out of stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream()
     ctx = api.Context(local_rank)
     ctx.set_stream(stream.cuda_stream)
-
-    t_build = time.perf_counter()
-    ctx.build_synth_db(GENOME_SEED + rank, N_GENOMES, GENOME_LEN, k=K, n_chunks=N_CHUNKS, overlap=OVERLAP, num_hashes=H, fpr=FPR, block_size=BLOCK_SIZE)
-    t_build = time.perf_counter() - t_build
-    info = ctx.db_info()
-
-    n_steps_total = args.warmup + args.steps
-    step_bytes = READS_PER_STEP * READ_LEN
-    # reads of every step resident in HBM before any timing; same seeds on every rank = the broadcast batch
-    d_reads = torch.empty(n_steps_total * step_bytes, dtype=torch.uint8, device="cuda")
-    for s in range(n_steps_total):
-        ctx.synth_reads(READ_SEED, s * READS_PER_STEP, READS_PER_STEP, READ_LEN, GENOME_SEED, N_GENOMES, GENOME_LEN, d_reads.data_ptr() + s * step_bytes)
-    off_np = np.arange(READS_PER_STEP + 1, dtype=np.uint64) * np.uint64(READ_LEN)
-    d_off = torch.from_numpy(off_np.view(np.int64)).cuda()
-    params = ctx.default_params()
+    run_id = "kmcpb_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid() if world > 1 else os.getpid())
 
     def barrier():
         torch.cuda.synchronize()
@@ -276,95 +310,153 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    def max_over_ranks(v):
         if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- value: device-resident inputs ----------------
-    def dev_step(s):
-        return ctx.search_batch_ptr(d_reads.data_ptr() + s * step_bytes, d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes, copy=False)
+    def gather_objects(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
 
-    with torch.cuda.stream(stream):
-        for s in range(args.warmup):
-            dev_step(s)
-        barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
+    # ONE database of `world` blocks of 10,000 targets; this rank keeps the block(s) the shard plan gives it
+    t_build = time.perf_counter()
+    ctx.build_synth_db(GENOME_SEED, N_GENOMES * world, GENOME_LEN, k=K, n_chunks=N_CHUNKS, overlap=OVERLAP, num_hashes=H, fpr=FPR, block_size=BLOCK_SIZE,
+                       shard_rank=rank, shard_world=world)
+    t_build = time.perf_counter() - t_build
+    info = ctx.db_info()
+
+    n_steps_total = args.warmup + args.steps
+    off_np = np.arange(READS_PER_STEP + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    h_off, h_off_ptr = api.pinned_array(off_np.nbytes)
+    h_off[:] = off_np.view(np.uint8)
+    step_bytes = READS_PER_STEP * READ_LEN
+    params = ctx.default_params()
+    # batches of every step resident in rank 0's HBM before any timing (reads sampled from the first N_GENOMES genomes)
+    d_batches = bb = off_bytes = None
+    if rank == 0:
+        d_batches, bb, off_bytes = pack_batches(torch, ctx, READ_SEED, 0, n_steps_total, READS_PER_STEP, GENOME_SEED, N_GENOMES, GENOME_LEN, off_np)
+    else:
+        bb, off_bytes = off_np.nbytes + step_bytes, off_np.nbytes
+
+    sampler = ClockSampler(local_rank)
+    digests = []
+    if world == 1:
+        # ---------------- value (N = 1): device-resident inputs, two jobs in flight ----------------
+        def submit(s):
+            return ctx.submit(d_batches.data_ptr() + s * bb + off_bytes, d_batches.data_ptr() + s * bb, READS_PER_STEP, params, device=True, host_off_ptr=h_off_ptr)
+
+        def run_steps(first, n):
+            outs, jobs = [], []
+            for s in range(first, first + n):
+                jobs.append(submit(s))
+                if len(jobs) == 2:
+                    outs.append(ctx.wait(jobs.pop(0), copy=False))
+            while jobs:
+                outs.append(ctx.wait(jobs.pop(0), copy=False))
+            return outs
+
+        with torch.cuda.stream(stream):
+            run_steps(0, args.warmup)
+            barrier()
             sampler.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        outs = [dev_step(args.warmup + s) for s in range(args.steps)]
-        ev1.record(stream)
-        barrier()
-        clocks = sampler.stop() if rank == 0 else None
-        ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            outs = run_steps(args.warmup, args.steps)
+            ev1.record(stream)
+            barrier()
+            clocks = sampler.stop()
+            ms_total = ev0.elapsed_time(ev1)
+        sh = None
+    else:
+        # ---------------- value (N > 1): broadcast + search + hit return inside the timed region ----------------
+        sh = multigpu.ShardedSearch(ctx, rank, world, READS_PER_STEP, bb, hit_cap=4 * READS_PER_STEP, name=run_id, device=dev, dist=dist, params=params)
+
+        def feed_dev(first):
+            return lambda s: (d_batches[(first + s) * bb:(first + s + 1) * bb], False)
+
+        def consume_digest(s, lists, meta):
+            merged = multigpu.merge_lists(lists, 0, READS_PER_STEP)
+            digests.append((len(merged), multigpu.hits_digest(merged)))
+
+        with torch.cuda.stream(stream):
+            sh.run(args.warmup, feed_dev(0), consume_digest, host_off=off_np)
+            digests.clear()
+            barrier()
+            if rank == 0:
+                sampler.start()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            outs = sh.run(args.steps, feed_dev(args.warmup), consume_digest, host_off=off_np)      # returns when rank 0 holds every hit list
+            ev1.record(stream)
+            barrier()
+            clocks = sampler.stop() if rank == 0 else None
+            ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     probe_ms = sum(o.ms_probe for o in outs)
     probe_launches = sum(o.probe_launches for o in outs)
     probe_bytes = sum(o.probe_row_bytes for o in outs)
     launches = sum(o.kernel_launches for o in outs)
     n_hits = sum(o.n_hits for o in outs)
     value = world * READS_PER_STEP * args.steps / (ms_total / 1e3)       # units all ranks processed ÷ time (§5: read×shard probes)
+    value_hits = sum(n for n, _d in digests) if world > 1 else n_hits
 
-    # ---------------- e2e: pinned host buffers through the engine ----------------
-    h_reads, h_ptr = api.pinned_array(args.steps * step_bytes)
-    h_reads[:] = d_reads[args.warmup * step_bytes:].cpu().numpy()
-    h_off, h_off_ptr = api.pinned_array(off_np.nbytes)
-    h_off[:] = off_np.view(np.uint8)
+    # ---------------- e2e: pinned host buffers → matches in host memory ----------------
+    h_batches = h_ptr = None
+    if rank == 0:
+        h_batches, h_ptr = api.pinned_array(args.steps * bb)
+        h_batches[:] = d_batches[args.warmup * bb:].cpu().numpy()
     eopts = ctx.default_engine_opts()
-    d2h_bytes = 0
-    e2e_matches = 0
+    e2e_matches = [0]
     e2e_break = {"search_call_ms": 0.0, "post_filter_ms": 0.0, "engine_call_ms": 0.0}
     with torch.cuda.stream(stream):
         if world == 1:
-            ctx.engine_search_ptr(h_ptr, h_off_ptr, READS_PER_STEP, eopts)          # warm the host-side caches once
+            # kmcpg_engine_search from two host threads (a Go host calls it from goroutines): the executor runs their batches back to back
+            ctx.engine_search_ptr(h_ptr + off_bytes, h_off_ptr, READS_PER_STEP, eopts)          # warm the host-side caches once
+            res = [None] * args.steps
+
+            def worker(t):
+                for s in range(t, args.steps, 2):
+                    res[s] = ctx.engine_search_ptr(h_ptr + s * bb + off_bytes, h_off_ptr, READS_PER_STEP, eopts, copy=False)
+
             barrier()
             t0 = time.perf_counter()
-            for s in range(args.steps):
-                r = ctx.engine_search_ptr(h_ptr + s * step_bytes, h_off_ptr, READS_PER_STEP, eopts, copy=False)
-                e2e_matches += r.n_matches
-                e2e_break["search_call_ms"] += r.ms_gpu_total / args.steps; e2e_break["post_filter_ms"] += r.ms_post / args.steps
-                e2e_break["engine_call_ms"] += r.ms_total / args.steps
+            th = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
             torch.cuda.synchronize()
             e2e_s = time.perf_counter() - t0
-            d2h_bytes = int(12 * n_hits / args.steps + 8 * READS_PER_STEP)
+            for r in res:
+                e2e_matches[0] += r.n_matches
+                e2e_break["search_call_ms"] += r.ms_gpu_total / args.steps; e2e_break["post_filter_ms"] += r.ms_post / args.steps
+                e2e_break["engine_call_ms"] += r.ms_total / args.steps
+            e2e_path = "kmcpg_engine_search from two host threads (pinned host reads → H2D → kernels → D2H hits → host tCov/FPR/sort)"
         else:
-            # two staging buffers: step s+1 is copied to rank 0's GPU and broadcast (side stream) while step s is searched
-            stage = [torch.empty(step_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
-            side = torch.cuda.Stream()
-            staged = [torch.cuda.Event(), torch.cuda.Event()]
-            dev = torch.device("cuda", local_rank)
+            tsizes = ctx.target_sizes()
 
-            def prefetch(s):
-                with torch.cuda.stream(side):
-                    if rank == 0:
-                        stage[s & 1].copy_(torch.from_numpy(h_reads[s * step_bytes:(s + 1) * step_bytes]), non_blocking=True)
-                    dist.broadcast(stage[s & 1], src=0)                                # NCCL over NVLink: the only data-path collective
-                    staged[s & 1].record(side)
+            def feed_host(s):
+                return torch.from_numpy(h_batches[s * bb:(s + 1) * bb]), True
 
-            # untimed: the first gather builds NCCL's point-to-point channels
-            multigpu.gather_hits_padded(np.zeros(1024, dtype=api.HIT_DTYPE), rank, world, dev)
-            multigpu.gather_hits_padded(np.zeros(900_000, dtype=api.HIT_DTYPE), rank, world, dev)
+            def consume_full(s, lists, meta):
+                merged = multigpu.merge_lists(lists, 0, READS_PER_STEP)
+                r = multigpu.postfilter(eopts, meta.n_kmers, meta.query_len, merged, tsizes, FPR, K, copy=False)
+                e2e_matches[0] += r.n_matches
+                e2e_break["post_filter_ms"] += r.ms_post / args.steps
+
             barrier()
             t0 = time.perf_counter()
-            prefetch(0)
-            for s in range(args.steps):
-                staged[s & 1].synchronize()
-                if s + 1 < args.steps:
-                    prefetch(s + 1)
-                o = ctx.search_batch_ptr(stage[s & 1].data_ptr(), d_off.data_ptr(), READS_PER_STEP, params, device=True, seq_bytes=step_bytes)
-                # hit lists (disjoint by target) → rank 0: one padded NCCL gather, global target numbering added on the way
-                merged = multigpu.gather_hits_padded(o.hits, rank, world, dev, target_base=rank * BLOCK_SIZE)
-                if rank == 0:
-                    e2e_matches += len(merged)
+            sh.run(args.steps, feed_host, consume_full, host_off=off_np)
             barrier()
-            e2e_s = time.perf_counter() - t0
-            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-            d2h_bytes = int(12 * n_hits / args.steps + 8 * READS_PER_STEP)
+            e2e_s = max_over_ranks(time.perf_counter() - t0)
+            e2e_path = ("rank 0 pinned reads → H2D → ncclBroadcast (prefetched one step ahead) → kmcpg_search_submit on every rank → hit lists D2H into per-rank "
+                        "shared-memory segments → rank 0 merges them in place (kmcpg_merge_hits) → host tCov/FPR/sort (kmcpg_engine_postfilter)")
+    d2h_bytes = int(12 * n_hits / args.steps + 8 * READS_PER_STEP)
     e2e_value = world * READS_PER_STEP * args.steps / e2e_s
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
@@ -374,14 +466,26 @@ def main():
         shutil.rmtree(tmp, ignore_errors=True)
         try:
             r001 = dump_db_for_cpu(ctx, tmp)
-            v, cores, n1 = time_cpu_port(r001, h_reads, args.steps * READS_PER_STEP)
+            reads_only = np.concatenate([h_batches[s * bb + off_bytes:(s + 1) * bb] for s in range(args.steps)])
+            v, cores, n1 = time_cpu_port(r001, reads_only, args.steps * READS_PER_STEP)
+            del reads_only
             cpu = {"value": v, "unit": "reads/s", "cores": cores, "kind": "port",
                    "sample": "%d reads of the timed set, restated reference algorithm (oracle algo=1: 64-row buffer, byte transpose, "
                              "positional popcount), OpenMP on all %d host threads, same index in RAM" % (n1, cores)}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
+    if rank == 0:
+        api.host_free(h_ptr)
+    del d_batches
+    if sh is not None:
+        sh.close()
 
-    api.host_free(h_ptr); api.host_free(h_off_ptr)
+    # ---------------- GTDB-scale block: fixed index sharded over the ranks, fixed reads, digest of the merged hit list ----------------
+    gtdb = None
+    if not args.no_gtdb:
+        gtdb = gtdb_block(torch, dist, api, multigpu, ctx, stream, dev, rank, world, run_id, barrier, max_over_ranks, gather_objects)
+
+    api.host_free(h_off_ptr)
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = (probe_bytes / 1e9) / (probe_ms / 1e3) if probe_ms > 0 else 0.0
@@ -391,32 +495,100 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 hash / u32 bit-sliced counters", "data": "synthetic",
             "config": {"workload": workload_name(), "reads_per_step": READS_PER_STEP, "index_bytes_per_gpu": int(info.resident_bytes),
-                       "index_disk_bytes_per_gpu": int(info.disk_bytes), "targets_per_gpu": int(info.n_targets),
+                       "index_disk_bytes_per_gpu": int(info.disk_bytes), "targets_per_gpu": int(info.n_targets // world), "targets_total": int(info.n_targets),
                        "algorithmic_bytes_per_read": int(probe_bytes / max(1, READS_PER_STEP * args.steps)),
                        "l2": "index (%.2f GB) ≫ 126 MB L2 and every step probes different random rows: no explicit flush" % (info.resident_bytes / 1e9),
-                       "parallelism": "blocks sharded over %d GPU(s), read batch broadcast" % world, "db_build_s": round(t_build, 2),
-                       "hits_per_step": int(n_hits / args.steps),
+                       "parallelism": "one database of %d block(s) sharded over %d GPU(s), read batch broadcast, hit lists returned to rank 0" % (info.n_blocks, world),
+                       "db_build_s": round(t_build, 2), "hits_per_step": int(value_hits / args.steps), "pipeline": "two batches submitted at a time (kmcpg_search_submit)",
+                       "timed_region": "device-resident batches → search → hits in host memory" if world == 1 else
+                                       "batches resident on rank 0 → ncclBroadcast → search on every rank → every rank's hits in rank 0's host memory (merged + digested there)",
                        "multi_gpu_units": "value counts read×shard probes (each rank probes every read against its own 10k-target block)" if world > 1 else "reads"},
             "job_reads_per_s": READS_PER_STEP * args.steps / (ms_total / 1e3),
-            "roofline": {"bound": "hbm", "kernel": "probe_kernel<1,8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "probe_kernel<1,0,2,2,4,u32>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "launches": probe_launches, "avg_launch_ms": probe_ms / max(1, probe_launches),
                          "algorithmic_bytes_per_launch": probe_bytes / max(1, probe_launches),
+                         "whole_step_frac": (probe_bytes / 1e9) / (ms_total / 1e3) / peak,
                          "traffic": (traffic["dram_over_algorithmic"] * probe_bytes / max(1, probe_launches)) if traffic else None,
                          "traffic_note": ("average launch of this run x the DRAM/algorithmic ratio of the committed ncu --set full capture: " + traffic["source"])
-                         if traffic else "no ncu --set full capture committed yet"},
+                         if traffic else "no ncu --set full capture committed yet",
+                         "note": "launch durations are CUDA-event brackets on the probe stream; the query preparation of the next part runs beside the probe on its own stream"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": step_bytes + off_np.nbytes, "d2h_bytes_per_step": d2h_bytes,
-                    "matches_per_step": int(e2e_matches / args.steps), "ms_per_step": e2e_s / args.steps * 1e3, "breakdown_ms_per_step": e2e_break,
-                    "path": "kmcpg_engine_search (pinned host reads → H2D → kernels → D2H hits → host tCov/FPR/sort)" if world == 1 else
-                            "rank0 pinned reads → H2D → ncclBroadcast (prefetched one step ahead) → kmcpg_search_batch_device on every rank → padded NCCL gather of the hit lists → rank 0 host"},
+                    "matches_per_step": int(e2e_matches[0] / args.steps), "ms_per_step": e2e_s / args.steps * 1e3, "breakdown_ms_per_step": e2e_break,
+                    "path": e2e_path},
             "gpu_launches": int(launches), "clocks": clocks,
-            "stage_ms_per_step": {"hash": sum(o.ms_hash for o in outs) / args.steps, "locs": sum(o.ms_locs for o in outs) / args.steps,
+            "stage_ms_per_step": {"hash (own stream, beside the probes)": sum(o.ms_hash for o in outs) / args.steps,
                                   "probe": probe_ms / args.steps, "call_wall": sum(o.ms_total for o in outs) / args.steps},
+            "hit_list_digest": ("%016x" % (sum(d for _n, d in digests) & (2**64 - 1))) if digests else None,
+            "gtdb_scale": gtdb,
         }
         print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def gtdb_block(torch, dist, api, multigpu, ctx, stream, dev, rank, world, run_id, barrier, max_over_ranks, gather_objects):
+    """BASELINE.json configs[3] shape: a fixed index block-sharded over the ranks, fixed reads, strong scaling"""
+    t0 = time.perf_counter()
+    ctx.build_synth_db(GTDB_SEED, GTDB_GENOMES, GTDB_GL, k=K, n_chunks=N_CHUNKS, overlap=OVERLAP, num_hashes=GTDB_H, fpr=FPR, block_size=GTDB_BLOCK,
+                       shard_rank=rank, shard_world=world)
+    build_s = time.perf_counter() - t0
+    info = ctx.db_info()
+    n = GTDB_READS
+    off_np = np.arange(n + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    steps = GTDB_WARMUP + GTDB_STEPS
+    d_batches = None
+    bb = off_np.nbytes + n * READ_LEN
+    if rank == 0:
+        d_batches, bb, _ob = pack_batches(torch, ctx, GTDB_READ_SEED, 0, steps, n, GTDB_SEED, GTDB_GENOMES, GTDB_GL, off_np)
+    sh = multigpu.ShardedSearch(ctx, rank, world, n, bb, hit_cap=max(1 << 20, 8 * n), name=run_id + "g", device=dev, dist=dist, params=ctx.default_params())
+    digests = []
+
+    def feed(first):
+        return lambda s: (d_batches[(first + s) * bb:(first + s + 1) * bb], False)
+
+    def consume(s, lists, meta):
+        merged = multigpu.merge_lists(lists, 0, n)
+        digests.append((len(merged), multigpu.hits_digest(merged)))
+
+    with torch.cuda.stream(stream):
+        sh.run(GTDB_WARMUP, feed(0), consume, host_off=off_np)
+        digests.clear()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        outs = sh.run(GTDB_STEPS, feed(GTDB_WARMUP), consume, host_off=off_np)
+        ev1.record(stream)
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+    sh.close()
+    mine = {"rank": rank, "resident_blocks": int(info.n_resident_blocks), "index_bytes": int(info.resident_bytes), "sum_row_bytes": int(info.sum_row_bytes),
+            "probe_ms": sum(o.ms_probe for o in outs), "probe_bytes": sum(o.probe_row_bytes for o in outs), "probe_launches": sum(o.probe_launches for o in outs),
+            "launches": sum(o.kernel_launches for o in outs), "build_s": round(build_s, 1)}
+    per_rank = gather_objects(mine)
+    if rank != 0:
+        return None
+    peak, _src = measured_peak()
+    for r in per_rank:
+        r["probe_GBps"] = (r["probe_bytes"] / 1e9) / (r["probe_ms"] / 1e3) if r["probe_ms"] > 0 else 0.0
+        r["probe_frac"] = r["probe_GBps"] / peak
+    total_bytes = sum(r["probe_bytes"] for r in per_rank)
+    job = n * GTDB_STEPS / (ms / 1e3)
+    return {
+        "workload": "GTDB-scale shape: %d genomes x %d chunks = %d targets, k=%d, h=%d, fpr %.1f, %d blocks of %d targets (%d-byte rows), genome length %d (index %.1f GB; "
+                    "full GTDB would be 3.5 Mb / ~96 GB: SURVEY §8d C4 scales genome length, not target count), %d x %d bp reads per step, %d timed steps"
+                    % (GTDB_GENOMES, N_CHUNKS, int(info.n_targets), K, GTDB_H, FPR, info.n_blocks, GTDB_BLOCK, (GTDB_BLOCK + 7) // 8, GTDB_GL,
+                       sum(r["index_bytes"] for r in per_rank) / 1e9, n, READ_LEN, GTDB_STEPS),
+        "scaling": "strong", "n_gpus": world, "job_reads_per_s": job, "ms_per_step": ms / GTDB_STEPS,
+        "algorithmic_bytes_per_read": int(total_bytes / max(1, n * GTDB_STEPS)),
+        "aggregate_probe_GBps_over_wall": (total_bytes / 1e9) / (ms / 1e3), "roofline_reads_per_s_at_peak": peak * 1e9 * world / max(1.0, total_bytes / max(1, n * GTDB_STEPS)),
+        "frac_of_roofline": job / (peak * 1e9 * world / max(1.0, total_bytes / max(1, n * GTDB_STEPS))),
+        "hits_per_step": int(sum(c for c, _d in digests) / max(1, len(digests))),
+        "hit_list_digest": "%016x" % (sum(d for _c, d in digests) & (2**64 - 1)),
+        "digest_note": "sum over the timed steps of kmcpg_hits_digest of the merged (query, target, count) list in (query, target) order: must be equal at every N",
+        "per_rank": per_rank,
+    }
 
 
 if __name__ == "__main__":

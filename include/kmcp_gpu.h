@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define KMCPG_ABI_VERSION 1
+#define KMCPG_ABI_VERSION 2
 
 enum {
     KMCPG_OK = 0,
@@ -40,8 +40,10 @@ int kmcpg_create(int device, kmcpg_ctx **out);
 int kmcpg_close(kmcpg_ctx *ctx);
 const char *kmcpg_last_error(const kmcpg_ctx *ctx); /* ctx may be NULL: error of the failed kmcpg_create */
 int kmcpg_abi_version(void);
-/* run all work of this context on the caller's CUDA stream (e.g. torch's current stream) so the caller's
- * events bracket it; NULL restores the context's own stream */
+/* run the probe launches of this context on the caller's CUDA stream (e.g. torch's current stream) so the caller's
+ * events bracket them; NULL restores the context's own stream.  Query preparation, staging and result return always run
+ * on the library's own streams, so inputs handed over in device memory must be complete when they are submitted (or
+ * carry a ready_event, see kmcpg_batch). */
 int kmcpg_set_stream(kmcpg_ctx *ctx, void *cuda_stream);
 
 /* ---- database: replaces NewUnikIndexDB + NewUnikIndex + index.NewReader (U:648-760, U:1196-1280, X:372-593) */
@@ -94,6 +96,8 @@ int kmcpg_shard_pieces(const char *dir, int shard_world, kmcpg_shard_piece *out,
 int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts);
 int kmcpg_db_info(const kmcpg_ctx *ctx, kmcpg_db_info_t *out);
 int kmcpg_target(const kmcpg_ctx *ctx, int64_t global_target, kmcpg_target_t *out);
+/* Sizes[t] (k-mers of target t) of all n_targets targets as float64 (U:1393-1396 sizesFloat), n >= n_targets */
+int kmcpg_target_sizes(const kmcpg_ctx *ctx, double *out, int64_t n);
 
 /* ---- the hot path: replaces UnikIndexDB.handleQuery k-mer generation + every UnikIndex worker `fn`
  *      (U:763-941 and U:6613-7741) for a whole batch of queries ------------------------------------------- */
@@ -139,10 +143,11 @@ int kmcpg_search_batch_device(kmcpg_ctx *ctx, const kmcpg_search_params *p, cons
                               const uint64_t *d_off, uint32_t n_seqs, uint64_t seq_bytes, kmcpg_hits *out);
 void kmcpg_free_hits(kmcpg_hits *h);
 
-/* streaming form: the batch is processed in parts (≈ 250 k reads); `cb` is called on the calling thread, in query
- * order, as soon as a part's hits are in host memory — while the GPU is already probing the next parts — so a host
- * can post-process (tCov/FPR/sort, TSV formatting) in the shadow of the device work.  The pointers are valid until
- * the call returns; `hits[i].query` is the index inside the batch.  The callback must not call back into this ctx. */
+/* streaming form: the batch is processed in parts (≈ 250 k reads); `cb` is called on the context's executor thread (one
+ * call at a time, in query order) as soon as a part's hits are in host memory — while the GPU is already probing the
+ * next parts — so a host can post-process (tCov/FPR/sort, TSV formatting) in the shadow of the device work.  The
+ * pointers are valid until the call returns; `hits[i].query` is the index inside the batch.  The callback must not
+ * call back into this ctx. */
 typedef struct {
     uint32_t first_query, n_queries;
     const int32_t *n_kmers;      /* [n_queries], of first_query.. */
@@ -153,6 +158,29 @@ typedef struct {
 typedef void (*kmcpg_part_cb)(void *user, const kmcpg_part *part);
 int kmcpg_search_batch_cb(kmcpg_ctx *ctx, const kmcpg_search_params *p, const uint8_t *seq, const uint64_t *off,
                           uint32_t n_seqs, kmcpg_part_cb cb, void *user, kmcpg_hits *summary /* timings and totals; arrays stay valid until freed */);
+
+/* asynchronous form (what the three calls above are made of): kmcpg_search_submit queues a batch and returns; the context's
+ * executor thread feeds the GPU with the parts of all queued batches back to back, so with a second batch submitted before
+ * the first is waited for, the boundary between batches costs no GPU time (the Go engine keeps two batches in flight:
+ * one being filled from InCh while the other is searched, U:209-243).  Inputs must stay valid until kmcpg_search_wait
+ * returns; jobs of one context complete in submission order; submit may be called from any thread. */
+typedef struct kmcpg_job kmcpg_job;
+typedef struct {
+    const uint8_t *seq;          /* concatenated ASCII: host memory (pinned or not), or this context's device memory */
+    const uint64_t *off;         /* n_seqs + 1 offsets into seq, in the same memory space as seq */
+    uint32_t n_seqs;
+    int32_t on_device;           /* 1: seq / off are device pointers (e.g. a batch that arrived by ncclBroadcast) */
+    const uint64_t *host_off;    /* on_device: optional host copy of off (saves fetching it back to cut the batch into parts) */
+    void *ready_event;           /* on_device: optional cudaEvent_t after which seq / off are complete; NULL: complete now */
+    kmcpg_hit *hits_dst;         /* optional caller-owned destination of the hit list (pinned or cudaHostRegister-ed host memory, */
+    uint64_t hits_cap;           /*   e.g. a shared-memory segment another process reads); more than hits_cap hits: KMCPG_ENOMEM */
+    kmcpg_part_cb cb;            /* optional: parts are handed over as they land (see kmcpg_search_batch_cb) */
+    void *user;
+} kmcpg_batch;
+int kmcpg_search_submit(kmcpg_ctx *ctx, const kmcpg_search_params *p, const kmcpg_batch *b, kmcpg_job **job);
+/* blocks until the job is done and releases it; out as for kmcpg_search_batch (out->hits == hits_dst when one was given);
+ * out may be NULL to drop the results */
+int kmcpg_search_wait(kmcpg_job *job, kmcpg_hits *out);
 
 /* ---- the reader stage (host only, no device needed): replaces the reader loop of search.go (S:793-1000, fastx.Reader over
  *      xopen/pgzip on one goroutine).  FASTA/Q files, plain or gzip → packed batches of queries in input order, ready for
@@ -192,6 +220,14 @@ int kmcpg_reader_next(kmcpg_reader *r, kmcpg_read_batch *out);
 void kmcpg_reader_free_batch(kmcpg_read_batch *b);
 const char *kmcpg_reader_error(const kmcpg_reader *r);
 int kmcpg_reader_close(kmcpg_reader *r);
+
+/* host memory shared between the processes of a one-process-per-GPU run (the read batch is broadcast, every rank probes
+ * its blocks, "per-GPU hit lists concatenated on the host"): a named segment (a file under /dev/shm, or /tmp where that is missing),
+ * mapped by every process that opens the name; with cuda_register it is page-locked for this process's device, so a rank's hit
+ * list can be copied device→host straight into it (kmcpg_batch.hits_dst) and the gathering rank reads it in place.  bytes must be
+ * the same in every process; create = 1 in the process that owns the segment (the others open it afterwards). */
+int kmcpg_shm_open(const char *name, size_t bytes, int create, int cuda_register, void **ptr);
+int kmcpg_shm_close(const char *name, void *ptr, size_t bytes, int cuda_registered, int unlink_it);
 
 /* pinned host memory for batch buffers (so the H2D copy of kmcpg_search_batch runs at full PCIe speed) */
 int kmcpg_host_alloc(void **p, size_t bytes);
@@ -267,6 +303,18 @@ int kmcpg_engine_search_sharded(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_e
  * refused with KMCPG_EINVAL. */
 int kmcpg_engine_search_replicas(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opts *o, const uint8_t *seq,
                                  const uint64_t *off, uint32_t n_seqs, kmcpg_results *out);
+/* the engine's result handling alone (host only, no device): hit lists that were produced by other processes — the per-rank lists of
+ * a one-process-per-GPU run after kmcpg_merge_hits — go through the same filter / sort / top-N code as behind kmcpg_engine_search.
+ * hits sorted by (query, target); target_sizes = kmcpg_target_sizes of the whole database; fpr, k = the database's; one k, no
+ * --try-se (retries need the device); part_queries 0 = default. */
+int kmcpg_engine_postfilter(const kmcpg_engine_opts *o, uint32_t n_queries, const int32_t *n_kmers, const int32_t *query_len, const kmcpg_hit *hits,
+                            uint64_t n_hits, const double *target_sizes, int64_t n_targets, double fpr, int k, uint32_t part_queries, kmcpg_results *out);
+/* union of per-shard hit lists (each sorted by (query, target), disjoint by target) in (query, target) order — the gather of
+ * U:939-964 across processes; queries within [first_query, first_query + n_queries); out holds the sum of n[] records */
+int kmcpg_merge_hits(const kmcpg_hit *const *lists, const uint64_t *n, int n_lists, uint32_t first_query, uint32_t n_queries, int threads, kmcpg_hit *out);
+/* order-sensitive 64-bit digest of a hit list (sum over i of a mix of (first_index + i, query, target, count)): equal for runs that
+ * return the same hits in the same order, e.g. one search on 1, 2, 4 and 8 GPUs */
+uint64_t kmcpg_hits_digest(const kmcpg_hit *hits, uint64_t n, uint64_t first_index);
 void kmcpg_free_results(kmcpg_results *r);
 /* QueryFPRWithCacheWithConstantFPR's underlying function (F:32-50, F:140-193), bit-exact with Go */
 double kmcpg_query_fpr(int n, int c, double p);
@@ -338,6 +386,7 @@ typedef struct {
     int32_t k; int32_t n_chunks; int32_t overlap;
     int32_t num_hashes; double fpr; int32_t block_size; /* targets per block */
     uint32_t scale;                                      /* > 1: FracMinHash sketch database (compute -D) */
+    int32_t shard_rank, shard_world;                     /* > 1 shards: only the blocks kmcpg_open_db(shard_rank, shard_world) would keep are built */
 } kmcpg_synth_db;
 int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec);
 /* d_out[i*genome_len ..) = seeded genome (first+i), ASCII */

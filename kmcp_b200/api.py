@@ -73,6 +73,11 @@ class Part(C.Structure):
 PART_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Part))
 
 
+class Batch(C.Structure):
+    _fields_ = [("seq", C.c_void_p), ("off", C.c_void_p), ("n_seqs", C.c_uint32), ("on_device", C.c_int32), ("host_off", C.c_void_p),
+                ("ready_event", C.c_void_p), ("hits_dst", C.c_void_p), ("hits_cap", C.c_uint64), ("cb", C.c_void_p), ("user", C.c_void_p)]
+
+
 class SketchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("canonical", C.c_int32), ("scaled", C.c_int32), ("scale", C.c_uint32),
                 ("minimizer", C.c_int32), ("minimizer_w", C.c_uint32), ("syncmer", C.c_int32), ("syncmer_s", C.c_uint32)]
@@ -110,7 +115,7 @@ class IndexParams(C.Structure):
 class SynthDb(C.Structure):
     _fields_ = [("genome_seed", C.c_uint64), ("n_genomes", C.c_uint32), ("genome_len", C.c_uint32), ("k", C.c_int32),
                 ("n_chunks", C.c_int32), ("overlap", C.c_int32), ("num_hashes", C.c_int32), ("fpr", C.c_double),
-                ("block_size", C.c_int32), ("scale", C.c_uint32)]
+                ("block_size", C.c_int32), ("scale", C.c_uint32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
 
 
 # every symbol include/kmcp_gpu.h declares (checked by tests/test_abi.py without a GPU)
@@ -145,7 +150,9 @@ class ReadBatch(C.Structure):
 
 ABI_SYMBOLS = [
     "kmcpg_abi_version", "kmcpg_set_stream", "kmcpg_create", "kmcpg_close", "kmcpg_last_error", "kmcpg_shard_plan", "kmcpg_shard_pieces", "kmcpg_open_db", "kmcpg_db_info", "kmcpg_target",
-    "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_free_hits", "kmcpg_host_alloc",
+    "kmcpg_target_sizes", "kmcpg_shm_open", "kmcpg_shm_close", "kmcpg_engine_postfilter", "kmcpg_merge_hits", "kmcpg_hits_digest",
+    "kmcpg_default_params", "kmcpg_search_batch", "kmcpg_search_batch_device", "kmcpg_search_batch_cb", "kmcpg_search_submit", "kmcpg_search_wait",
+    "kmcpg_free_hits", "kmcpg_host_alloc",
     "kmcpg_host_free", "kmcpg_device_memory", "kmcpg_device_alloc", "kmcpg_device_free", "kmcpg_memcpy_h2d", "kmcpg_memcpy_d2h",
     "kmcpg_generate_kmers", "kmcpg_count_codes", "kmcpg_free", "kmcpg_default_engine_opts", "kmcpg_engine_search", "kmcpg_engine_search_sharded", "kmcpg_engine_search_replicas",
     "kmcpg_free_results", "kmcpg_query_fpr", "kmcpg_default_index_params", "kmcpg_index_fasta", "kmcpg_synth_reads", "kmcpg_synth_genomes", "kmcpg_build_synth_db", "kmcpg_write_block",
@@ -177,11 +184,20 @@ def load() -> C.CDLL:
     L.kmcpg_shard_pieces.argtypes = [C.c_char_p, C.c_int, C.POINTER(ShardPiece), C.c_int32]
     L.kmcpg_db_info.argtypes = [vp, C.POINTER(DbInfo)]
     L.kmcpg_target.argtypes = [vp, C.c_int64, C.POINTER(TargetInfo)]
+    L.kmcpg_target_sizes.argtypes = [vp, vp, C.c_int64]
+    L.kmcpg_shm_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kmcpg_shm_close.argtypes = [C.c_char_p, vp, C.c_size_t, C.c_int, C.c_int]
+    L.kmcpg_engine_postfilter.argtypes = [C.POINTER(EngineOpts), C.c_uint32, vp, vp, vp, C.c_uint64, vp, C.c_int64, C.c_double, C.c_int, C.c_uint32, C.POINTER(Results)]
+    L.kmcpg_merge_hits.argtypes = [C.POINTER(vp), C.POINTER(C.c_uint64), C.c_int, C.c_uint32, C.c_uint32, C.c_int, vp]
+    L.kmcpg_hits_digest.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.kmcpg_hits_digest.restype = C.c_uint64
     L.kmcpg_default_params.argtypes = [C.POINTER(SearchParams)]
     L.kmcpg_default_params.restype = None
     L.kmcpg_search_batch.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, C.POINTER(Hits)]
     L.kmcpg_search_batch_device.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, C.c_uint64, C.POINTER(Hits)]
     L.kmcpg_search_batch_cb.argtypes = [vp, C.POINTER(SearchParams), vp, vp, C.c_uint32, PART_CB, vp, C.POINTER(Hits)]
+    L.kmcpg_search_submit.argtypes = [vp, C.POINTER(SearchParams), C.POINTER(Batch), C.POINTER(vp)]
+    L.kmcpg_search_wait.argtypes = [vp, C.POINTER(Hits)]
     L.kmcpg_free_hits.argtypes = [C.POINTER(Hits)]
     L.kmcpg_free_hits.restype = None
     L.kmcpg_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -323,8 +339,9 @@ class Context:
         self._check(self._L.kmcpg_open_db(self._h, r001_dir.encode(), C.byref(o)))
 
     def build_synth_db(self, genome_seed: int, n_genomes: int, genome_len: int, k: int = 21, n_chunks: int = 10,
-                       overlap: int = 150, num_hashes: int = 1, fpr: float = 0.3, block_size: int = 0, scale: int = 1):
-        s = SynthDb(genome_seed, n_genomes, genome_len, k, n_chunks, overlap, num_hashes, fpr, block_size, scale)
+                       overlap: int = 150, num_hashes: int = 1, fpr: float = 0.3, block_size: int = 0, scale: int = 1,
+                       shard_rank: int = 0, shard_world: int = 1):
+        s = SynthDb(genome_seed, n_genomes, genome_len, k, n_chunks, overlap, num_hashes, fpr, block_size, scale, shard_rank, shard_world)
         self._check(self._L.kmcpg_build_synth_db(self._h, C.byref(s)))
 
     def index_fasta(self, files, out_dir: str, k: int = 21, num_hashes: int = 1, fpr: float = 0.3, split_number: int = 1, split_overlap: int = -1,
@@ -348,6 +365,11 @@ class Context:
         i = DbInfo()
         self._check(self._L.kmcpg_db_info(self._h, C.byref(i)))
         return i
+
+    def target_sizes(self) -> np.ndarray:
+        out = np.zeros(int(self.db_info().n_targets), dtype=np.float64)
+        self._check(self._L.kmcpg_target_sizes(self._h, out.ctypes.data, out.size))
+        return out
 
     def target(self, g: int) -> TargetInfo:
         t = TargetInfo()
@@ -392,6 +414,27 @@ class Context:
             self._check(self._L.kmcpg_search_batch_device(self._h, C.byref(params), seq_ptr, off_ptr, n_seqs, seq_bytes, C.byref(h)))
         else:
             self._check(self._L.kmcpg_search_batch(self._h, C.byref(params), seq_ptr, off_ptr, n_seqs, C.byref(h)))
+        return self._take_hits(h, copy)
+
+    def submit(self, seq_ptr: int, off_ptr: int, n_seqs: int, params: SearchParams, device: bool = False, host_off_ptr: int = 0,
+               hits_dst: int = 0, hits_cap: int = 0, ready_event: int = 0) -> int:
+        """kmcpg_search_submit with raw pointers (the caller keeps the buffers alive until wait()); returns the job handle"""
+        b = Batch(seq_ptr, off_ptr, n_seqs, 1 if device else 0, host_off_ptr or None, ready_event or None, hits_dst or None, hits_cap, None, None)
+        job = C.c_void_p()
+        self._check(self._L.kmcpg_search_submit(self._h, C.byref(params), C.byref(b), C.byref(job)))
+        return job.value
+
+    def wait(self, job: int, copy=True) -> BatchHits:
+        """kmcpg_search_wait: blocks until the job is done; copy=False returns only the summary (hits stay in hits_dst, if one was given),
+        copy="meta" the summary plus n_kmers / query_len"""
+        h = Hits()
+        self._check(self._L.kmcpg_search_wait(job, C.byref(h)))
+        if copy == "meta":
+            out = BatchHits(_np_from(h.n_kmers, h.n_queries, 4, np.int32), _np_from(h.query_len, h.n_queries, 4, np.int32), np.zeros(0, HIT_DTYPE),
+                            h.ms_hash, h.ms_locs, h.ms_probe, h.ms_total, int(h.probe_launches), int(h.probe_row_bytes), int(h.kernel_launches))
+            out.n_hits = int(h.n_hits)
+            self._L.kmcpg_free_hits(C.byref(h))
+            return out
         return self._take_hits(h, copy)
 
     def search_batch_streaming(self, buf: np.ndarray, off: np.ndarray, params: Optional[SearchParams] = None):

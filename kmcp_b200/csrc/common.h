@@ -63,7 +63,9 @@ double go_pow(double x, double y);
 
 // 128-bit reciprocal for exact x % d (replaces bmkessler/fastdiv Uint64.Mod; U:6611, U:6811)
 struct FastMod {
-    uint64_t d = 1, m_hi = 0, m_lo = 0;
+    uint64_t d = 1, m_hi = 0, m_lo = 0;   // m = ceil(2^128 / d): Lemire's exact remainder (host side, fastmod_host)
+    uint64_t b64 = ~0ull;                 // floor((2^64-1) / d): Barrett quotient estimate for 64-bit x, off by at most one (device side)
+    uint32_t b32 = ~0u, _pad = 0;         // floor((2^32-1) / d) for 32-bit x when d < 2^32 (the h > 1 hash values are 32-bit, H:137-139)
 };
 FastMod make_fastmod(uint64_t d);
 uint64_t fastmod_host(uint64_t a, const FastMod &f);

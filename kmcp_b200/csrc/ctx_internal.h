@@ -69,9 +69,12 @@ struct PinBuf {
 struct HitsPriv {
     kmcpg_ctx *ctx = nullptr;
     PinBuf nk, ql, hits;
+    bool ext_hits = false;      // hits.p is the caller's buffer (kmcpg_batch.hits_dst): never grown, never returned to the pool
     uint32_t nq = 0;
     uint64_t nh = 0;
 };
+
+struct Executor;
 
 // one sub-batch, inputs already on the device
 struct SubBatch {
@@ -92,7 +95,7 @@ struct WorkSet {
     DevBuf tile_n, tile_off, tile_cnt, tile_pre;   // long sequences: tiles per sequence, their scan, codes per tile, their scan
     HostBuf h_off, h_cnt;
     cudaEvent_t ev_in = nullptr, ev_a0 = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_cnt = nullptr, ev_sorted = nullptr, ev_b = nullptr;
-    std::vector<cudaEvent_t> probe_ev;   // 3 per resident block: before locs, before probe, after probe
+    std::vector<cudaEvent_t> probe_ev;   // 3 slots per resident block: [1] before, [2] after its probe launch
     // state of the part currently in flight
     bool busy = false;
     SubBatch sb{};
@@ -115,6 +118,8 @@ struct kmcpg_ctx {
                                       // sit in front of part i-1's result copies (streams are FIFO)
     cudaStream_t post_st = nullptr;   // hit-list sort + pack of a finished part (tiny kernels, concurrent with the next probe)
     cudaStream_t in_st = nullptr;     // host→device input staging (its own queue, so it never waits behind result copies)
+    cudaStream_t hash_st = nullptr;   // query preparation (slot scan, hash, dedup, verdict) of the NEXT part, beside the probes of the current one
+    kmcpg::Executor *exec = nullptr;  // the thread that feeds the GPU (executor.cu); started by the first kmcpg_search_submit
     bool has_db = false;
     kmcpg::DbMeta meta;
     std::vector<kmcpg::DeviceBlock> blocks;
@@ -138,7 +143,10 @@ uint32_t pitch_for(uint32_t row_bytes);
 void layout_block(DeviceBlock &b, const BlockMeta &m, uint32_t col0 = 0, uint32_t n_cols = 0);
 void plan_pieces(const DbMeta &m, int world, std::vector<ShardPiece> &pieces, std::vector<uint64_t> &load);
 void free_db(kmcpg_ctx *ctx);
-int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out);
+void executor_drain(kmcpg_ctx *ctx);   // waits until no search job is in flight (call with ctx->mu held)
+void executor_stop(kmcpg_ctx *ctx);
+int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb, uint32_t nq, uint64_t **codes_out, cudaStream_t st = nullptr);
+int planes_for(uint64_t max_n);
 int pin_acquire(kmcpg_ctx *ctx, size_t bytes, PinBuf &out);
 void pin_release(kmcpg_ctx *ctx, PinBuf &b);
 

@@ -229,6 +229,8 @@ int write_block_file(const std::string &path, const BlockMeta &m, const uint8_t 
 FastMod make_fastmod(uint64_t d) {
     FastMod f;
     f.d = d ? d : 1;
+    f.b64 = ~0ull / f.d;
+    f.b32 = f.d <= 0xFFFFFFFFull ? (uint32_t)(0xFFFFFFFFull / f.d) : 0;
     if (f.d == 1) { f.m_hi = 0; f.m_lo = 0; return f; }       // x % 1 == 0: lowbits = 0 → result 0
     unsigned __int128 M = ~(unsigned __int128)0;
     M /= f.d;

@@ -7,6 +7,7 @@
 // A "round" = one device search of the still-undecided queries with one k and one mate selection; its hit
 // list (sorted by query) is filtered and sorted per query by a few host threads into one flat array.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -27,21 +28,27 @@ namespace {
 
 using namespace kmcpg;
 
-// QueryFPRWithCacheWithConstantFPR (F:140-193) without its slot-sharing quirk: plain memo of the pure function
+// QueryFPRWithCacheWithConstantFPR (F:140-193) without its slot-sharing quirk: plain memo of the pure function.  One table per
+// database FPR, shared by every thread that filters hits of such a database (worker pool, replica threads, several -d databases
+// in turn): slots are relaxed atomics holding the double's bits, a racing duplicate store writes the same value.
 struct FprCache {
     static constexpr int N = 1024;
-    double p = -1;
-    std::vector<double> tab;
-    void reset(double fpr) {
-        if (fpr == p && !tab.empty()) return;
-        p = fpr;
-        tab.assign((size_t)(N + 1) * (N + 1), -1.0);
+    const double p;
+    std::unique_ptr<std::atomic<uint64_t>[]> tab;
+    static constexpr uint64_t EMPTY = ~0ull;             // a NaN pattern query_fpr never returns
+    explicit FprCache(double fpr) : p(fpr), tab(new std::atomic<uint64_t>[(size_t)(N + 1) * (N + 1)]) {
+        for (size_t i = 0; i < (size_t)(N + 1) * (N + 1); i++) tab[i].store(EMPTY, std::memory_order_relaxed);
     }
     double get(int n, int c) {
-        if (n > N || c > n) return query_fpr(n, c, p);
-        double &slot = tab[(size_t)n * (N + 1) + c];
-        double v = slot;
-        if (v < 0) { v = query_fpr(n, c, p); slot = v; }   // idempotent value: a racing duplicate store is harmless
+        if (n > N || c > n || n < 0 || c < 0) return query_fpr(n, c, p);
+        std::atomic<uint64_t> &slot = tab[(size_t)n * (N + 1) + c];
+        uint64_t bits = slot.load(std::memory_order_relaxed);
+        double v;
+        if (bits == EMPTY) {
+            v = query_fpr(n, c, p);
+            memcpy(&bits, &v, 8);
+            slot.store(bits, std::memory_order_relaxed);
+        } else memcpy(&v, &bits, 8);
         return v;
     }
 };
@@ -409,11 +416,15 @@ struct StandIn {
 };
 thread_local const StandIn *tl_standin = nullptr;
 
-// the calling thread's FPR memo for this database's p (F:140-193); handed to helper threads so they all fill ONE table
+// the memo of this database's p (F:140-193): tables live as long as the process, one per distinct FPR (databases built with
+// the same -f share one)
 FprCache *thread_fpr_cache(double fpr) {
-    static thread_local FprCache tl_cache;
-    tl_cache.reset(fpr);
-    return &tl_cache;
+    static std::mutex mu;
+    static std::vector<std::unique_ptr<FprCache>> all;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &c : all) if (c->p == fpr) return c.get();
+    all.emplace_back(new FprCache(fpr));
+    return all.back().get();
 }
 
 }  // namespace
@@ -827,12 +838,14 @@ int kmcpg_internal_replicas_selftest(int n_rep, uint32_t nq, int paired, int fai
     return same ? KMCPG_OK : KMCPG_EINVAL;
 }
 
-// test hook (tests/test_engine_host.py, no GPU needed): kmcpg_engine_search's result handling over a given hit list.  The "device"
-// delivers the hits [(query, target, count), sorted by query then target] in parts of part_queries queries, with the n_kmers /
-// query_len arrays, exactly as kmcpg_search_batch_cb would; only single-round configurations (one k, no --try-se).
-int kmcpg_internal_engine_standin(const kmcpg_engine_opts *o, uint32_t n_queries, const int32_t *n_kmers, const int32_t *query_len, const kmcpg_hit *hits,
-                                  uint64_t n_hits, const double *target_sizes, int64_t n_targets, double fpr, int k, uint32_t part_queries, kmcpg_results *out) {
-    if (!o || !out || o->try_se || (n_queries && (!n_kmers || !query_len)) || (n_hits && !hits) || !target_sizes || part_queries == 0) return KMCPG_EINVAL;
+// The engine's result handling over hit lists that were produced elsewhere — by the other processes of a one-process-per-GPU run
+// (each rank probes its blocks, the gathering rank holds the concatenated lists) or by a test.  Host only.  `hits` is sorted by
+// (query, target); the lists are handed to the same code that kmcpg_engine_search runs behind the device call, in parts of
+// part_queries queries.  Single-round configurations only (one k, no --try-se): retries need the device.
+int kmcpg_engine_postfilter(const kmcpg_engine_opts *o, uint32_t n_queries, const int32_t *n_kmers, const int32_t *query_len, const kmcpg_hit *hits,
+                            uint64_t n_hits, const double *target_sizes, int64_t n_targets, double fpr, int k, uint32_t part_queries, kmcpg_results *out) {
+    if (!o || !out || o->try_se || (n_queries && (!n_kmers || !query_len)) || (n_hits && !hits) || !target_sizes) return KMCPG_EINVAL;
+    if (part_queries == 0) part_queries = 262144;
     StandIn si;
     memset(&si.info, 0, sizeof(si.info));
     si.info.n_ks = 1; si.info.ks[0] = k; si.info.fpr = fpr; si.info.n_targets = n_targets; si.info.num_hashes = 1; si.info.n_blocks = 1;
@@ -843,8 +856,8 @@ int kmcpg_internal_engine_standin(const kmcpg_engine_opts *o, uint32_t n_queries
         uint64_t h0 = 0;
         for (uint32_t q0 = 0; q0 < n_queries; q0 += part_queries) {
             const uint32_t nq = std::min(part_queries, n_queries - q0);
-            uint64_t h1 = h0;
-            while (h1 < n_hits && hits[h1].query < q0 + nq) h1++;
+            const kmcpg_hit *e = std::lower_bound(hits + h0, hits + n_hits, (uint64_t)q0 + nq, [](const kmcpg_hit &h, uint64_t qq) { return (uint64_t)h.query < qq; });
+            const uint64_t h1 = (uint64_t)(e - hits);
             kmcpg_part pt;
             pt.first_query = q0; pt.n_queries = nq;
             pt.n_kmers = n_kmers + q0; pt.query_len = query_len + q0;
@@ -862,6 +875,47 @@ int kmcpg_internal_engine_standin(const kmcpg_engine_opts *o, uint32_t n_queries
     const int rc = engine_search_impl(&none, 1, o, &dummy, off.data(), n_queries * step, out);
     tl_standin = nullptr;
     return rc;
+}
+
+// test hook (tests/test_engine_host.py): the former name of kmcpg_engine_postfilter
+int kmcpg_internal_engine_standin(const kmcpg_engine_opts *o, uint32_t n_queries, const int32_t *n_kmers, const int32_t *query_len, const kmcpg_hit *hits,
+                                  uint64_t n_hits, const double *target_sizes, int64_t n_targets, double fpr, int k, uint32_t part_queries, kmcpg_results *out) {
+    if (part_queries == 0) return KMCPG_EINVAL;
+    return kmcpg_engine_postfilter(o, n_queries, n_kmers, query_len, hits, n_hits, target_sizes, n_targets, fpr, k, part_queries, out);
+}
+
+// Union of per-shard hit lists (each sorted by (query, target), disjoint by target) in (query, target) order: the host side of the
+// block fan-out + gather of U:939-964 when the shards live in other processes.  out holds Σ n[i] records.
+int kmcpg_merge_hits(const kmcpg_hit *const *lists, const uint64_t *n, int n_lists, uint32_t first_query, uint32_t n_queries, int threads, kmcpg_hit *out) {
+    if (n_lists < 0 || (n_lists && (!lists || !n)) || !out) return KMCPG_EINVAL;
+    for (int s = 0; s < n_lists; s++) {
+        if (n[s] && !lists[s]) return KMCPG_EINVAL;
+        if (n[s] && (lists[s][0].query < first_query || (uint64_t)lists[s][n[s] - 1].query >= (uint64_t)first_query + n_queries)) return KMCPG_EINVAL;
+    }
+    if (n_queries == 0 || n_lists == 0) return KMCPG_OK;
+    merge_shard_hits_mt(lists, n, n_lists, out, first_query, n_queries, threads > 0 ? threads : (int)std::thread::hardware_concurrency());
+    return KMCPG_OK;
+}
+
+// 64-bit digest of a hit list that depends on every field AND on the order: Σ_i mix(i, query, target, count) mod 2^64.  Two runs that
+// return the same hit set in the same (query, target) order — e.g. the same search on 1, 2, 4 and 8 GPUs — have the same digest.
+uint64_t kmcpg_hits_digest(const kmcpg_hit *hits, uint64_t n, uint64_t first_index) {
+    auto mix = [](uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; };
+    const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)pool().size() + 1, n / 65536 + 1));
+    std::vector<uint64_t> part((size_t)T, 0);
+    std::function<void(int)> work = [&](int t) {
+        const uint64_t a = n * (uint64_t)t / (uint64_t)T, b = n * (uint64_t)(t + 1) / (uint64_t)T;
+        uint64_t acc = 0;
+        for (uint64_t i = a; i < b; i++) {
+            const kmcpg_hit &h = hits[i];
+            acc += mix((first_index + i) * 0x9E3779B97F4A7C15ull ^ ((uint64_t)h.query << 32 | h.target)) ^ mix(((uint64_t)h.count << 32 | h.target) + 0x632BE59BD9B4E019ull * (first_index + i + 1));
+        }
+        part[t] = acc;
+    };
+    pool().parallel(T, work);
+    uint64_t d = 0;
+    for (uint64_t v : part) d += v;
+    return d;
 }
 
 // test hook (kmcp-gpu search --dry-run, host only): the result of a batch in which nothing matched, so that the command's

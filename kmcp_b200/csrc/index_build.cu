@@ -281,6 +281,7 @@ int kmcpg_index_fasta(kmcpg_ctx *ctx, const kmcpg_index_params *pin, const char 
     if (p.syncmer_s > 0 && p.minimizer_w > 0) return fail(ctx, KMCPG_EINVAL, "flag -W/--minimizer-w and -S/--syncmer-s are incompatible");
     if (p.syncmer_s > 0 && (int)p.syncmer_s >= p.k) return fail(ctx, KMCPG_EINVAL, "syncmer-s must be smaller than k");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    executor_drain(ctx);
     CU(cudaSetDevice(ctx->device));
     free_db(ctx);
     cudaStream_t st = ctx->st;
@@ -345,7 +346,7 @@ int kmcpg_index_fasta(kmcpg_ctx *ctx, const kmcpg_index_params *pin, const char 
                     mx = std::max(mx, tg.size);
                 }
                 bm.num_sigs = calc_signature_size(mx, p.num_hashes, p.fpr);
-                if (bm.num_sigs == 0 || bm.num_sigs >= (1ull << 32) - 1) return fail(ctx, KMCPG_EUNSUPPORTED, "block has an unsupported number of signatures");
+                if (bm.num_sigs == 0) return fail(ctx, KMCPG_EUNSUPPORTED, "block has an unsupported number of signatures");
                 DeviceBlock db;
                 db.meta_idx = (int)bi;
                 layout_block(db, bm);

@@ -601,76 +601,52 @@ cudaError_t launch_finalize(const FinalizeArgs &a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// locs: hashValues + exact modulo
+// row indices: hashValues (H:125-141) + exact modulo (fastdiv.Mod, U:6811), computed inside the probe kernel
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t fastmod_dev(uint64_t a, uint64_t m_hi, uint64_t m_lo, uint64_t d) {
-    // lowbits = M*a mod 2^128 ; result = (lowbits*d) >> 128
-    uint64_t lo = m_lo * a;
-    uint64_t hi = __umul64hi(m_lo, a) + m_hi * a;
-    uint64_t bottom = __umul64hi(lo, d);
-    uint64_t top_lo = hi * d;
-    uint64_t top_hi = __umul64hi(hi, d);
-    uint64_t sum = bottom + top_lo;
-    return top_hi + (sum < bottom ? 1 : 0);
+// x % d by Barrett reduction: q = floor(x * floor((2^W-1)/d) / 2^W) is floor(x/d) or one less (the estimate is short by
+// x(1+s)/(d 2^W) < 1, s = (2^W-1) mod d), so one conditional subtraction makes the remainder exact for every x and every d >= 1.
+__device__ __forceinline__ uint64_t mod64_dev(uint64_t x, const FastMod &fm) {
+    const uint64_t r = x - __umul64hi(x, fm.b64) * fm.d;
+    return r >= fm.d ? r - fm.d : r;
+}
+__device__ __forceinline__ uint32_t mod32_dev(uint32_t x, const FastMod &fm) {      // d < 2^32
+    const uint32_t d = (uint32_t)fm.d;
+    const uint32_t r = x - __umulhi(x, fm.b32) * d;
+    return r >= d ? r - d : r;
 }
 
+// row index of hash number h of a k-mer code.  LocT = uint32_t for blocks with numSigs < 2^32-1, uint64_t beyond.
+template <int H, typename LocT>
+__device__ __forceinline__ LocT loc_of(uint64_t code, uint32_t h, const FastMod &fm) {
+    if (H == 1) return (LocT)mod64_dev(code, fm);
+    const uint32_t v = (uint32_t)(code >> 32) + (uint32_t)code * h;            // baseHashes (H:61-63), uint32 wrap-around (H:137-139)
+    if (sizeof(LocT) == 8) return (LocT)((uint64_t)v >= fm.d ? (uint64_t)v - fm.d : (uint64_t)v);   // numSigs >= 2^32-1 >= v: at most one subtraction
+    return (LocT)mod32_dev(v, fm);
+}
+
+// the row indices as a kernel of its own (u32, numSigs < 2^32-1): locs[slot*H + h].  Development alternative to the in-kernel
+// derivation (KMCPG_DEV builds, KMCPG_PROBE_LOCS=buffer), and the device side of the arithmetic test hook.
 template <int H>
 __global__ void __launch_bounds__(256) locs_kernel(const uint64_t *__restrict__ codes, uint64_t n, FastMod fm, uint32_t *__restrict__ locs) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        uint64_t code = codes[i];
-        if (H == 1) {
-            locs[i] = (uint32_t)fastmod_dev(code, fm.m_hi, fm.m_lo, fm.d);
-        } else {
-            uint32_t x = (uint32_t)(code >> 32), y = (uint32_t)code;      // baseHashes (H:61-63)
+        const uint64_t code = codes[i];
 #pragma unroll
-            for (uint32_t j = 0; j < (uint32_t)H; j++) {
-                uint64_t v = (uint64_t)(uint32_t)(x + y * j);             // uint32 wrap-around (H:137-139)
-                locs[i * H + j] = (uint32_t)fastmod_dev(v, fm.m_hi, fm.m_lo, fm.d);
-            }
-        }
+        for (uint32_t j = 0; j < (uint32_t)H; j++) locs[i * H + j] = loc_of<H, uint32_t>(code, j, fm);
     }
 }
-
-// sketch databases: the code regions are mostly empty (FracMinHash keeps ~2/scale of the positions), so walk the
-// queries instead of the slots: one warp per query, only its n_eff codes
 template <int H>
-__global__ void __launch_bounds__(256) locs_query_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ n_eff,
-                                                         uint32_t nq, int paired, FastMod fm, uint32_t *__restrict__ locs) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t q = warp; q < nq; q += n_warps) {
-        const uint32_t n = n_eff[q];
-        const uint64_t base = slot_off[paired ? 2 * q : q];
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint64_t code = codes[base + i];
-            if (H == 1) {
-                locs[base + i] = (uint32_t)fastmod_dev(code, fm.m_hi, fm.m_lo, fm.d);
-            } else {
-                const uint32_t x = (uint32_t)(code >> 32), y = (uint32_t)code;
+__global__ void __launch_bounds__(256) locs64_kernel(const uint64_t *__restrict__ codes, uint64_t n, FastMod fm, uint64_t *__restrict__ locs) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const uint64_t code = codes[i];
 #pragma unroll
-                for (uint32_t j = 0; j < (uint32_t)H; j++)
-                    locs[(base + i) * H + j] = (uint32_t)fastmod_dev((uint64_t)(uint32_t)(x + y * j), fm.m_hi, fm.m_lo, fm.d);
-            }
+        for (uint32_t j = 0; j < (uint32_t)H; j++) {
+            locs[i * H + j] = loc_of<H, uint64_t>(code, j, fm);
         }
     }
-}
-
-cudaError_t launch_locs_by_query(const uint64_t *codes, const uint64_t *slot_off, const uint32_t *n_eff, uint32_t nq, int paired, int h, FastMod fm,
-                                 uint32_t *locs, cudaStream_t st) {
-    if (!nq) return cudaSuccess;
-    uint32_t blocks = (nq + 7) / 8;
-    if (blocks > 148u * 32u) blocks = 148u * 32u;
-    switch (h) {
-        case 1: locs_query_kernel<1><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
-        case 2: locs_query_kernel<2><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
-        case 3: locs_query_kernel<3><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
-        case 4: locs_query_kernel<4><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
-        default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_locs(const uint64_t *codes, uint64_t n, int h, FastMod fm, uint32_t *locs, cudaStream_t st) {
@@ -682,6 +658,19 @@ cudaError_t launch_locs(const uint64_t *codes, uint64_t n, int h, FastMod fm, ui
         case 2: locs_kernel<2><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
         case 3: locs_kernel<3><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
         case 4: locs_kernel<4><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_locs64(const uint64_t *codes, uint64_t n, int h, FastMod fm, uint64_t *locs, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    uint64_t blocks64 = (n + 255) / 256;
+    uint32_t blocks = blocks64 > 148u * 64u ? 148u * 64u : (uint32_t)blocks64;
+    switch (h) {
+        case 1: locs64_kernel<1><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        case 2: locs64_kernel<2><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        case 3: locs64_kernel<3><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
+        case 4: locs64_kernel<4><<<blocks, 256, 0, st>>>(codes, n, fm, locs); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -717,23 +706,53 @@ __device__ __forceinline__ Slab<W> ld_slab(const uint8_t *p) {
 
 constexpr int PROBE_THREADS = 256;
 constexpr int PROBE_ROWS = 8;   // rows per carry-save tree
-constexpr uint32_t LOC_NONE = 0xFFFFFFFFu;
 
-// row indices of 8 consecutive k-mers (H each); LOC_NONE past the end of the query
-template <int H>
-__device__ __forceinline__ void load_locs(uint32_t (&L)[PROBE_ROWS * H], const uint32_t *__restrict__ lp, uint32_t i, uint32_t n) {
+// Row indices of 8 consecutive k-mers (H each) of one task, from its k-mer codes; NONE past the end of the query.
+// A FULL lane group (G == GF = 128 / slab bytes lanes, i.e. rows of at least 64 + 1 slab bytes) shares the arithmetic: lane j computes
+// entry j (k-mer j / H, hash j % H) — and j + GF, ... when 8·H > GF — and the group exchanges the results by shuffle, so every
+// lane pays one or two reciprocals per 8 rows.  Narrower groups (rows of a few bytes) compute every entry themselves.
+template <typename LocT> struct LocNone { static constexpr LocT v = (LocT)~(LocT)0; };
+
+template <int H, int GF, typename LocT, int SRC>
+__device__ __forceinline__ void load_locs(LocT (&L)[PROBE_ROWS * H], const uint64_t *__restrict__ cp, const uint32_t *__restrict__ lp32, uint32_t i, uint32_t n,
+                                          const FastMod &fm, bool full, uint32_t gl, uint32_t gmask, int gbase) {
+    constexpr int NL = PROBE_ROWS * H;
+    constexpr LocT NONE = LocNone<LocT>::v;
+    if (SRC == 0) {                                                   // development alternative: indices precomputed by locs_kernel
 #pragma unroll
-    for (int u = 0; u < PROBE_ROWS; u++)
+        for (int u = 0; u < PROBE_ROWS; u++)
 #pragma unroll
-        for (int h = 0; h < H; h++) L[u * H + h] = (i + u < n) ? __ldg(lp + (uint64_t)(i + u) * H + h) : LOC_NONE;
+            for (int h = 0; h < H; h++) L[u * H + h] = (i + u < n) ? (LocT)__ldg(lp32 + (uint64_t)(i + u) * H + h) : NONE;
+        return;
+    }
+    if (full) {
+        constexpr int R = (NL + GF - 1) / GF;
+        LocT mine[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t e = (uint32_t)r * GF + gl, u = e / H, h = e - u * H;
+            mine[r] = NONE;
+            if (e < (uint32_t)NL && i + u < n) mine[r] = loc_of<H, LocT>(__ldg(cp + i + u), h, fm);
+        }
+#pragma unroll
+        for (int e = 0; e < NL; e++) L[e] = __shfl_sync(gmask, mine[e / GF], gbase + (e % GF));
+    } else {
+#pragma unroll
+        for (int u = 0; u < PROBE_ROWS; u++) {
+            const bool ok = i + u < n;
+            const uint64_t code = ok ? __ldg(cp + i + u) : 0;
+#pragma unroll
+            for (int h = 0; h < H; h++) L[u * H + h] = ok ? loc_of<H, LocT>(code, (uint32_t)h, fm) : NONE;
+        }
+    }
 }
 
-// slabs of the 8 rows (h rows AND-ed: pand, U:6639-6645); zero for LOC_NONE
-template <int H, int W>
-__device__ __forceinline__ void load_rows(Slab<W> (&r)[PROBE_ROWS], const uint32_t (&L)[PROBE_ROWS * H], const uint8_t *__restrict__ colbase, uint32_t pitch) {
+// slabs of the 8 rows (h rows AND-ed: pand, U:6639-6645); zero for NONE and for lanes past the end of the row
+template <int H, int W, typename LocT>
+__device__ __forceinline__ void load_rows(Slab<W> (&r)[PROBE_ROWS], const LocT (&L)[PROBE_ROWS * H], const uint8_t *__restrict__ colbase, uint32_t pitch, bool lane_ok) {
 #pragma unroll
     for (int u = 0; u < PROBE_ROWS; u++) {
-        if (L[u * H] != LOC_NONE) {
+        if (lane_ok && L[u * H] != LocNone<LocT>::v) {
             r[u] = ld_slab<W>(colbase + (uint64_t)L[u * H] * pitch);
 #pragma unroll
             for (int h = 1; h < H; h++) {
@@ -805,10 +824,11 @@ __device__ __forceinline__ void fold_planes(uint32_t (&c)[8][W], uint32_t *T) {
 // lane are always in flight while the carry-save tree of the previous 8 runs.
 // W = words per lane: 4 (16-byte slabs, 8 lanes per 128-byte task) or 2 (8-byte slabs, 16 lanes per task — half the
 // registers per row in flight, which is what the h>1 AND of several rows per k-mer needs).
-template <int H, int PH, int VAR, int MINB, int W>
+template <int H, int PH, int VAR, int MINB, int W, typename LocT, int SRC>
 __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a) {
     constexpr int P = 8 + PH;
     constexpr uint32_t SLAB = 4 * W;                                    // bytes per lane
+    constexpr int GF = 128 / SLAB;                                      // lanes of a full task group
     extern __shared__ uint32_t smem_planes[];                          // PH > 0: P*W*PROBE_THREADS words
     uint32_t *T = smem_planes + threadIdx.x;
     // task geometry for this slab width: a task covers up to 128 bytes of a row
@@ -833,21 +853,27 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
             n = a.n_eff[q];
         }
         const uint32_t colu = chunk * G + gl;                           // this lane's slab of the row
-        const bool active = n > 0 && colu < row_units;
+        const bool lane_ok = colu < row_units;                          // the last chunk of a row may not fill its group
+        const bool active = n > 0 && lane_ok;
         uint32_t c[8][W];
 #pragma unroll
         for (int p = 0; p < 8; p++)
 #pragma unroll
             for (int w = 0; w < W; w++) c[p][w] = 0;
 
-        if (active) {
+        if (n > 0) {                                                    // the WHOLE lane group runs the loop (it shares the row-index arithmetic)
             if (PH > 0) {
 #pragma unroll
                 for (int i = 0; i < P * W; i++) T[i * PROBE_THREADS] = 0;
             }
-            const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
-            const uint8_t *colbase = a.rows + (uint64_t)colu * SLAB;
-            uint32_t L[PROBE_ROWS * H];
+            const uint64_t slot0 = a.slot_off[a.paired ? 2 * q : q];
+            const uint64_t *lp = a.codes + slot0;
+            const uint32_t *lp32 = SRC == 0 ? a.locs + slot0 * (uint64_t)H : nullptr;
+            const uint8_t *colbase = a.rows + (uint64_t)(lane_ok ? colu : 0) * SLAB;
+            const bool full = G == (uint32_t)GF;
+            const int gbase = lane & ~(int)(G - 1);
+            const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << gbase;
+            LocT L[PROBE_ROWS * H];
             uint32_t acc = 0;                                           // rows added to the register planes since the last fold
             auto add8 = [&](const Slab<W> (&r)[PROBE_ROWS]) {
                 if (PH > 0) {
@@ -856,35 +882,39 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
                 }
                 csa8<W>(c, r);
             };
+#define KMCPG_LOCS(i_) load_locs<H, GF, LocT, SRC>(L, lp, lp32, (i_), n, a.fm, full, gl, gmask, gbase)
+#define KMCPG_ROWS(r_) load_rows<H, W, LocT>(r_, L, colbase, a.pitch, lane_ok)
             if (VAR == 0) {
                 for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
                     Slab<W> r[PROBE_ROWS];
-                    load_locs<H>(L, lp, i, n);
-                    load_rows<H, W>(r, L, colbase, a.pitch);
+                    KMCPG_LOCS(i);
+                    KMCPG_ROWS(r);
                     add8(r);
                 }
             } else if (VAR == 1) {
-                load_locs<H>(L, lp, 0, n);
+                KMCPG_LOCS(0);
                 for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
                     Slab<W> r[PROBE_ROWS];
-                    load_rows<H, W>(r, L, colbase, a.pitch);
-                    load_locs<H>(L, lp, i + PROBE_ROWS, n);
+                    KMCPG_ROWS(r);
+                    KMCPG_LOCS(i + PROBE_ROWS);
                     add8(r);
                 }
             } else {
                 Slab<W> r0[PROBE_ROWS], r1[PROBE_ROWS];
-                load_locs<H>(L, lp, 0, n);
-                load_rows<H, W>(r0, L, colbase, a.pitch);
-                load_locs<H>(L, lp, PROBE_ROWS, n);
+                KMCPG_LOCS(0);
+                KMCPG_ROWS(r0);
+                KMCPG_LOCS(PROBE_ROWS);
                 for (uint32_t i = 0; i < n; i += 2 * PROBE_ROWS) {
-                    load_rows<H, W>(r1, L, colbase, a.pitch);
-                    load_locs<H>(L, lp, i + 2 * PROBE_ROWS, n);
+                    KMCPG_ROWS(r1);
+                    KMCPG_LOCS(i + 2 * PROBE_ROWS);
                     add8(r0);
-                    load_rows<H, W>(r0, L, colbase, a.pitch);
-                    load_locs<H>(L, lp, i + 3 * PROBE_ROWS, n);
+                    KMCPG_ROWS(r0);
+                    KMCPG_LOCS(i + 3 * PROBE_ROWS);
                     if (i + PROBE_ROWS < n) add8(r1);
                 }
             }
+#undef KMCPG_LOCS
+#undef KMCPG_ROWS
             if (PH > 0) fold_planes<PH, W>(c, T);
         }
         // plane p, word w of this thread's final counters
@@ -968,11 +998,12 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
 // to a WHOLE CTA.  Its 256/G lane groups each take every (256/G)-th group of 8 k-mers, count them exactly like the kernel
 // above (8 register planes folded into P-plane totals in shared memory), then the per-group totals are added pairwise in
 // shared memory (bit-sliced ripple adders, log2(256/G) levels) and group 0 applies the threshold and emits the hits.
-template <int H, int PH, int W>
+template <int H, int PH, int W, typename LocT>
 __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_long_kernel(ProbeArgs a) {
     static_assert(PH > 0, "long queries always carry full-width totals in shared memory");
     constexpr int P = 8 + PH;
     constexpr uint32_t SLAB = 4 * W;
+    constexpr int GF = 128 / SLAB;
     extern __shared__ uint32_t smem_planes[];                          // P*W*PROBE_THREADS words
     uint32_t *T = smem_planes + threadIdx.x;
     const uint32_t row_units = (a.row_bytes + SLAB - 1) / SLAB;
@@ -989,7 +1020,8 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_long_kernel(ProbeArgs 
         const uint32_t chunk = (uint32_t)(g - (uint64_t)q * chunks);
         const uint32_t n = a.n_eff[q];
         const uint32_t colu = chunk * G + gl;
-        const bool active = n > 0 && colu < row_units;
+        const bool lane_ok = colu < row_units;
+        const bool active = n > 0 && lane_ok;
         uint32_t c[8][W];
 #pragma unroll
         for (int p = 0; p < 8; p++)
@@ -997,18 +1029,21 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_long_kernel(ProbeArgs 
             for (int w = 0; w < W; w++) c[p][w] = 0;
 #pragma unroll
         for (int i = 0; i < P * W; i++) T[i * PROBE_THREADS] = 0;
-        if (active) {
-            const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
-            const uint8_t *colbase = a.rows + (uint64_t)colu * SLAB;
-            uint32_t L[PROBE_ROWS * H];
+        if (n > 0) {                                                     // whole lane groups: they share the row-index arithmetic
+            const uint64_t *lp = a.codes + a.slot_off[a.paired ? 2 * q : q];
+            const uint8_t *colbase = a.rows + (uint64_t)(lane_ok ? colu : 0) * SLAB;
+            const bool full = G == (uint32_t)GF;
+            const int gbase = lane & ~(int)(G - 1);
+            const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << gbase;
+            LocT L[PROBE_ROWS * H];
             uint32_t acc = 0;
             const uint32_t stride = nseg * PROBE_ROWS;
             uint32_t i = seg * PROBE_ROWS;
-            if (i < n) load_locs<H>(L, lp, i, n);
+            if (i < n) load_locs<H, GF, LocT, 1>(L, lp, nullptr, i, n, a.fm, full, gl, gmask, gbase);
             for (; i < n; i += stride) {
                 Slab<W> r[PROBE_ROWS];
-                load_rows<H, W>(r, L, colbase, a.pitch);
-                if (i + stride < n) load_locs<H>(L, lp, i + stride, n);
+                load_rows<H, W, LocT>(r, L, colbase, a.pitch, lane_ok);
+                if (i + stride < n) load_locs<H, GF, LocT, 1>(L, lp, nullptr, i + stride, n, a.fm, full, gl, gmask, gbase);
                 if (acc + PROBE_ROWS > 255) { fold_planes<PH, W>(c, T); acc = 0; }
                 acc += PROBE_ROWS;
                 csa8<W>(c, r);
@@ -1108,24 +1143,26 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_long_kernel(ProbeArgs 
     }
 }
 
-template <int H, int PH, int W>
+template <int H, int PH, int W, typename LocT>
 static cudaError_t launch_probe_long_k(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     const size_t smem = (size_t)(8 + PH) * W * PROBE_THREADS * sizeof(uint32_t);
     if (smem > 48 * 1024) {
         static bool done = false;
         if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(probe_long_kernel<H, PH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(probe_long_kernel<H, PH, W, LocT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             done = true;
         }
     }
-    probe_long_kernel<H, PH, W><<<blocks, PROBE_THREADS, smem, st>>>(a);
+    probe_long_kernel<H, PH, W, LocT><<<blocks, PROBE_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
+// Development knobs (tools/*.sh, builds with -DKMCPG_DEV only): KMCPG_PROBE_VAR / _MINB (h=1), KMCPG_PROBE_VARH / _MINBH / _WH (h>1),
+// KMCPG_PROBE_CAP, KMCPG_PROBE_G.  The product library compiles the shipped variants only and reads no environment.
 struct ProbeTune { int var = 2, minb = 2, cap = 16, var_h = 1, minb_h = 2, w_h = 2, g = 0; };
 static ProbeTune probe_tune() {
-    // development knobs (tools/*.sh): KMCPG_PROBE_VAR / _MINB (h=1), KMCPG_PROBE_VARH / _MINBH / _WH (h>1), KMCPG_PROBE_CAP, KMCPG_PROBE_G
+#ifdef KMCPG_DEV
     static ProbeTune t = [] {
         ProbeTune x;
         if (const char *e = getenv("KMCPG_PROBE_VAR")) x.var = atoi(e);
@@ -1138,48 +1175,69 @@ static ProbeTune probe_tune() {
         return x;
     }();
     return t;
+#else
+    return ProbeTune();
+#endif
 }
 
-template <int H, int PH, int VAR, int MINB, int W>
+template <int H, int PH, int VAR, int MINB, int W, typename LocT, int SRC = 1>
 static cudaError_t launch_probe_k(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
     const size_t smem = PH > 0 ? (size_t)(8 + PH) * W * PROBE_THREADS * sizeof(uint32_t) : 0;
     if (smem > 48 * 1024) {
         static bool done = false;       // per instantiation
         if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(probe_kernel<H, PH, VAR, MINB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(probe_kernel<H, PH, VAR, MINB, W, LocT, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             done = true;
         }
     }
-    probe_kernel<H, PH, VAR, MINB, W><<<blocks, PROBE_THREADS, smem, st>>>(a);
+    probe_kernel<H, PH, VAR, MINB, W, LocT, SRC><<<blocks, PROBE_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int H, int PH>
 static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStream_t st) {
-    const ProbeTune t = probe_tune();
+    // blocks with numSigs >= 2^32-1 (the format's NumSigs is a uint64, X:173): 64-bit row indices, one CTA per SM (more registers)
+    if (a.fm.d >= 0xFFFFFFFFull) {
+        if constexpr (PH > 0) {
+            if (a.long_mode) {
+                if constexpr (H == 1) return launch_probe_long_k<H, PH, 4, uint64_t>(a, blocks, st);
+                else return launch_probe_long_k<H, PH, 2, uint64_t>(a, blocks, st);
+            }
+        }
+        if constexpr (H == 1) return launch_probe_k<H, PH, 2, 1, 4, uint64_t>(a, blocks, st);
+        else return launch_probe_k<H, PH, 1, 1, 2, uint64_t>(a, blocks, st);
+    }
     if constexpr (PH > 0) {
         if (a.long_mode) {                                   // few long queries: one CTA per (query, chunk)
-            if constexpr (H == 1) return launch_probe_long_k<H, PH, 4>(a, blocks, st);
-            else return launch_probe_long_k<H, PH, 2>(a, blocks, st);
+            if constexpr (H == 1) return launch_probe_long_k<H, PH, 4, uint32_t>(a, blocks, st);
+            else return launch_probe_long_k<H, PH, 2, uint32_t>(a, blocks, st);
         }
     }
+#ifdef KMCPG_DEV
     // the development variants (documented in profiles/config_sweeps_r01.md) exist only for the 8-plane kernels
+    const ProbeTune t = probe_tune();
     if constexpr (PH == 0) {
-        if (H == 1) {
-            if (t.var == 0) return launch_probe_k<H, PH, 0, 2, 4>(a, blocks, st);
-            if (t.var == 1) return t.minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st);
+        if (a.locs) {                                       // KMCPG_PROBE_LOCS=buffer: row indices precomputed by locs_kernel
+            if constexpr (H == 1) return launch_probe_k<H, PH, 2, 2, 4, uint32_t, 0>(a, blocks, st);
+            else return launch_probe_k<H, PH, 1, 2, 2, uint32_t, 0>(a, blocks, st);
+        }
+        if constexpr (H == 1) {
+            if (t.var == 0) return launch_probe_k<H, PH, 0, 2, 4, uint32_t>(a, blocks, st);
+            if (t.var == 1) return t.minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t>(a, blocks, st);
         } else {
-            if (t.w_h == 4) return t.minb_h >= 3 ? launch_probe_k<H, PH, 1, 3, 4>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4>(a, blocks, st);
-            if (t.var_h == 2) return launch_probe_k<H, PH, 2, 2, 2>(a, blocks, st);
-            if (t.minb_h >= 3) return launch_probe_k<H, PH, 1, 3, 2>(a, blocks, st);
+            if (t.w_h == 4) return t.minb_h >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t>(a, blocks, st);
+            if (t.var_h == 2) return launch_probe_k<H, PH, 2, 2, 2, uint32_t>(a, blocks, st);
+            if (t.minb_h >= 3) return launch_probe_k<H, PH, 1, 3, 2, uint32_t>(a, blocks, st);
         }
     }
-    if (H == 1) {
-        if (PH >= 24) return launch_probe_k<H, PH, 2, 1, 4>(a, blocks, st);      // 128 KB of counter planes per CTA
-        return launch_probe_k<H, PH, 2, 2, 4>(a, blocks, st);                    // shipped: double-buffered 16-byte slabs, 2 CTAs/SM
+#endif
+    if constexpr (H == 1) {
+        if constexpr (PH >= 24) return launch_probe_k<H, PH, 2, 1, 4, uint32_t>(a, blocks, st);      // 128 KB of counter planes per CTA
+        else return launch_probe_k<H, PH, 2, 2, 4, uint32_t>(a, blocks, st);               // shipped: double-buffered 16-byte slabs, 2 CTAs/SM
+    } else {
+        return launch_probe_k<H, PH, 1, 2, 2, uint32_t>(a, blocks, st);                    // shipped for h>1: 8-byte slabs, index prefetch, 2 CTAs/SM
     }
-    return launch_probe_k<H, PH, 1, 2, 2>(a, blocks, st);                        // shipped for h>1: 8-byte slabs, index prefetch, 2 CTAs/SM
 }
 
 template <int H>
@@ -1204,7 +1262,7 @@ cudaError_t launch_probe(const ProbeArgs &a_in, int sm_count, cudaStream_t st) {
         uint32_t G = 1;
         while (G < row_units && G < 128 / slab) G <<= 1;
         const uint64_t tasks = (uint64_t)a.n_queries * ((row_units + G - 1) / G);
-        a.long_mode = a.planes > 8 && tasks * G < (uint64_t)sm_count * 512 && !getenv("KMCPG_PROBE_NOLONG");
+        a.long_mode = a.planes > 8 && tasks * G < (uint64_t)sm_count * 512;
         if (a.long_mode) {
             const uint64_t cap2 = (uint64_t)sm_count * (a.planes >= 32 ? 1 : 2);
             uint32_t blocks = (uint32_t)(tasks < cap2 ? tasks : cap2);

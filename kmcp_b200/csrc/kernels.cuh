@@ -85,14 +85,7 @@ constexpr int SMALL_DEDUP_MAX = 2048;
 cudaError_t launch_small_dedup(uint64_t *codes, const uint64_t *slot_off, uint32_t *n_codes, uint32_t n_queries, int paired,
                                int dedup_threshold, int min_matched, uint64_t max_query_slots, cudaStream_t st);
 
-// ---- kernel 2a: code → row index of one block (hashValues + fastdiv.Mod; H:125-141, U:6811) ------------
-cudaError_t launch_locs(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint32_t *locs,
-                        cudaStream_t st);
-// same, walking the queries (sketch databases leave most slots empty)
-cudaError_t launch_locs_by_query(const uint64_t *codes, const uint64_t *slot_off, const uint32_t *n_eff, uint32_t n_queries, int paired,
-                                 int num_hashes, FastMod fm, uint32_t *locs, cudaStream_t st);
-
-// ---- kernel 2b: the COBS probe of one block (U:6613-7741) ----------------------------------------------
+// ---- kernel 2: the COBS probe of one block (hashValues + fastdiv.Mod + U:6613-7741) ----------------------------------------------
 struct ProbeArgs {
     const uint8_t *rows;        // re-pitched bit matrix of the block in HBM
     uint32_t pitch;             // bytes between rows
@@ -101,7 +94,9 @@ struct ProbeArgs {
     uint32_t n_names;
     uint32_t target_base;
     int num_hashes;
-    const uint32_t *locs;       // [slot][h]
+    const uint64_t *codes;      // k-mer codes of every query at slot_off[its first sequence]; the kernel derives the row indices itself:
+    FastMod fm;                 // hashValues (H:125-141) + code % numSigs (fastdiv.Mod, U:6811), numSigs up to 2^64-1
+    const uint32_t *locs;       // KMCPG_DEV builds only: [slot][h] precomputed by launch_locs (NULL: derived in the kernel)
     const uint64_t *slot_off;   // per sequence
     const uint32_t *n_eff;      // per query
     const uint32_t *thresh;     // per query
@@ -116,6 +111,9 @@ struct ProbeArgs {
     int long_mode;              // set by launch_probe: one CTA per (query, chunk) for few long queries
 };
 cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st);
+// the row indices alone, locs[slot*H + h] (arithmetic test hook; 32-bit form also the KMCPG_DEV alternative to the in-kernel derivation)
+cudaError_t launch_locs(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint32_t *locs, cudaStream_t st);
+cudaError_t launch_locs64(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint64_t *locs, cudaStream_t st);
 
 // ---- small utilities ------------------------------------------------------------------------------------
 // rows (unpadded, row_bytes each) → dst with `pitch` bytes per row, zero padded

@@ -169,6 +169,7 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
         spec->n_chunks < 1 || spec->overlap < 0 || !(spec->fpr > 0 && spec->fpr < 1))
         return fail(ctx, KMCPG_EINVAL, "bad synthetic DB spec");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    executor_drain(ctx);
     CU(cudaSetDevice(ctx->device));
     free_db(ctx);
     cudaStream_t st = ctx->st;
@@ -194,15 +195,21 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
     kmcpg_default_params(&hp);
     hp.min_query_len = 0; hp.min_matched = 1; hp.dedup_threshold = 0; hp.min_query_cov = 0;   // sort+unique every window (C:815-823)
 
-    std::vector<uint64_t> sizes(n_targets, 0);
-    std::vector<uint64_t> h_off((size_t)gpp * nw + 1);
-    std::vector<uint32_t> h_nc((size_t)gpp * nw);
-    WorkSet &w = ctx->ws[0];
-    CU(w.off.ensure(((uint64_t)gpp * nw + 1) * 8));
+    const int world = spec->shard_world > 1 ? spec->shard_world : 1;
+    const int rank = world > 1 ? spec->shard_rank : 0;
+    if (rank < 0 || rank >= world) return fail(ctx, KMCPG_EINVAL, "shard_rank out of range");
 
-    // target order / block composition are known only after pass 1
+    std::vector<uint64_t> sizes(n_targets, 0);
+    std::vector<uint64_t> h_off;
+    std::vector<uint32_t> h_nc;
+    std::vector<uint64_t> h_slot;
+    std::vector<uint32_t> sel;            // windows of the running pass: target ids (genome*nw + window)
+    WorkSet &w = ctx->ws[0];
+
+    // target order / block composition are known only after pass 0
     std::vector<uint32_t> order;          // sorted position → target id (genome*nw + window)
     std::vector<uint32_t> pos_of;         // target id → sorted position
+    std::vector<int> owner;               // block → shard (kmcpg_open_db's plan)
     int block_size = 0;
 
     for (int pass = 0; pass < 2; pass++) {
@@ -233,7 +240,23 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
                     mx = std::max(mx, sizes[id]);
                 }
                 bm.num_sigs = calc_signature_size(mx, spec->num_hashes, spec->fpr);     // I:936-948, I:1023
-                if (bm.num_sigs == 0 || bm.num_sigs >= (1ull << 32)) return fail(ctx, KMCPG_EUNSUPPORTED, "synthetic block has an unsupported number of signatures");
+                if (bm.num_sigs == 0) return fail(ctx, KMCPG_EUNSUPPORTED, "synthetic block has an unsupported number of signatures");
+            }
+            m.n_targets = (int64_t)n_targets;
+            // the shard's blocks: exactly what kmcpg_open_db(shard_rank, shard_world) keeps of this database
+            std::vector<ShardPiece> pieces;
+            std::vector<uint64_t> load;
+            plan_pieces(m, world, pieces, load);
+            owner.assign(nb, -1);
+            for (const ShardPiece &pc : pieces) {
+                if (pc.col0 != 0 || pc.n_cols != (uint32_t)m.blocks[pc.block].n_names)
+                    return fail(ctx, KMCPG_EUNSUPPORTED, "the synthetic builder shards by whole blocks only (fewer blocks than shards)");
+                owner[pc.block] = pc.shard;
+            }
+            ctx->resident_of.assign(nb, -1);
+            for (uint64_t bi = 0; bi < nb; bi++) {
+                if (owner[bi] != rank) continue;
+                const BlockMeta &bm = m.blocks[bi];
                 DeviceBlock db;
                 db.meta_idx = (int)bi;
                 layout_block(db, bm);
@@ -241,46 +264,59 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
                 CU(cudaMalloc((void **)&db.d_rows, std::max<size_t>(db.bytes, 16)));
                 CU(cudaMemsetAsync(db.d_rows, 0, db.bytes, st));
                 ctx->blocks.push_back(db);
+                ctx->resident_of[bi] = (int)ctx->blocks.size() - 1;
                 ctx->sum_row_bytes += bm.row_bytes;
                 ctx->resident_bytes += (int64_t)db.bytes;
                 ctx->disk_bytes += (int64_t)(bm.num_sigs * (uint64_t)bm.row_bytes);
             }
-            m.n_targets = (int64_t)n_targets;
             ctx->target_sizes.resize(n_targets);
             for (auto &bm : m.blocks)
                 for (int c = 0; c < bm.n_names; c++) ctx->target_sizes[(size_t)bm.target_base + c] = (double)bm.sizes[c];
-            ctx->resident_of.resize(nb);
-            std::iota(ctx->resident_of.begin(), ctx->resident_of.end(), 0);
+            // bits are set idempotently: the second pass needs no sort + unique, and only this shard's windows
+            hp.dedup_threshold = 0x7fffffff;
         }
-        for (uint32_t g0 = 0; g0 < spec->n_genomes; g0 += gpp) {
-            const uint32_t ng = std::min<uint32_t>(gpp, spec->n_genomes - g0);
-            // windows of the pass as independent sequences: every genome is generated once, windows alias into it
-            // (overlapping windows need their own byte ranges, so each window is generated separately)
-            uint64_t bytes = 0;
-            const uint32_t ns = ng * nw;
-            for (uint32_t s = 0; s < ns; s++) { h_off[s] = bytes; bytes += wins[s % nw].len; }
+        const uint32_t gstep = pass == 0 ? gpp : (uint32_t)std::min<uint64_t>(spec->n_genomes, (uint64_t)gpp * (uint64_t)world);
+        for (uint32_t g0 = 0; g0 < spec->n_genomes; g0 += gstep) {
+            const uint32_t ng = std::min<uint32_t>(gstep, spec->n_genomes - g0);
+            // windows of this round as independent sequences (overlapping windows need their own byte ranges, so each window is
+            // generated separately); the second pass takes only the windows whose block lives in this shard
+            sel.clear();
+            for (uint32_t g = g0; g < g0 + ng; g++)
+                for (uint32_t wi = 0; wi < nw; wi++) {
+                    const uint32_t id = g * nw + wi;
+                    if (pass == 1 && owner[pos_of[id] / (uint32_t)block_size] != rank) continue;
+                    sel.push_back(id);
+                }
+            const uint32_t ns = (uint32_t)sel.size();
+            if (!ns) continue;
+            h_off.resize((size_t)ns + 1); h_nc.resize(ns); h_slot.resize((size_t)ns + 1);
+            uint64_t bytes = 0, total = 0, mx = 0;
+            for (uint32_t s = 0; s < ns; s++) {
+                const Window &wn = wins[sel[s] % nw];
+                h_off[s] = bytes; bytes += wn.len;
+                const uint64_t c = wn.len - spec->k + 1;
+                total += c; mx = std::max(mx, c);
+            }
             h_off[ns] = bytes;
+            CU(w.off.ensure(((uint64_t)ns + 1) * 8));
             CU(w.seq.ensure(bytes + 64));
             for (uint32_t s = 0; s < ns; s++)
-                CU(launch_synth_genome(spec->genome_seed, g0 + s / nw, wins[s % nw].start, wins[s % nw].len, w.seq.as<uint8_t>() + h_off[s], st));
+                CU(launch_synth_genome(spec->genome_seed, sel[s] / nw, wins[sel[s] % nw].start, wins[sel[s] % nw].len, w.seq.as<uint8_t>() + h_off[s], st));
             CU(cudaMemcpyAsync(w.off.p, h_off.data(), (ns + 1) * 8ull, cudaMemcpyHostToDevice, st));
-            uint64_t total = 0, mx = 0;
-            for (uint32_t s = 0; s < ns; s++) { uint64_t c = wins[s % nw].len - spec->k + 1; total += c; mx = std::max(mx, c); }
             SubBatch sb{w.seq.as<uint8_t>(), w.off.as<uint64_t>(), ns, total, mx, 0};
             uint64_t *codes = nullptr;
             int rc = run_hash_stage(ctx, w, hp, spec->k, sb, ns, &codes);
             if (rc) return rc;
             CU(cudaMemcpyAsync(h_nc.data(), w.ncodes.p, ns * 4ull, cudaMemcpyDeviceToHost, st));
-            std::vector<uint64_t> h_slot(ns + 1);
             CU(cudaMemcpyAsync(h_slot.data(), w.slot_off.p, (ns + 1) * 8ull, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             for (uint32_t s = 0; s < ns; s++) {
-                const uint64_t id = (uint64_t)(g0 + s / nw) * nw + (s % nw);
+                const uint32_t id = sel[s];
                 const uint32_t nc = h_nc[s] == 0xFFFFFFFFu ? 0 : h_nc[s];
                 if (pass == 0) { sizes[id] = nc; continue; }
                 const uint32_t pos = pos_of[id];
                 const uint32_t bi = pos / block_size, col = pos % block_size;
-                DeviceBlock &db = ctx->blocks[bi];
+                DeviceBlock &db = ctx->blocks[ctx->resident_of[bi]];
                 CU(launch_set_bits(codes + h_slot[s], nc, spec->num_hashes, db.fm, db.d_rows, db.pitch, col, st));
             }
             CU(cudaStreamSynchronize(st));

@@ -437,6 +437,21 @@ int ko_db_block(const ko_db *db, int bi, uint64_t *num_sigs, int32_t *row_bytes,
  * ---------------------------------------------------------------------------------------------- */
 #define POSPOP_BUF 64   /* U:1164 */
 
+#ifdef __AVX2__
+#include <immintrin.h>
+/* positional popcount of one 64-byte column buffer, the AVX2 form pospop.Count8 takes for short inputs: the most significant bit of
+ * every byte is collected by vpmovmskb and counted, then the bytes are shifted left by one (vpaddb) for the next position */
+static inline void count8(uint32_t *cnt /* 8 targets of this column, cnt[j] ↔ bit 7-j */, const uint8_t *buf /* 64 bytes */, int n) {
+    uint8_t pad[POSPOP_BUF];
+    if (n < POSPOP_BUF) { memset(pad, 0, sizeof(pad)); memcpy(pad, buf, (size_t)n); buf = pad; }
+    __m256i a = _mm256_loadu_si256((const __m256i *)buf), b = _mm256_loadu_si256((const __m256i *)(buf + 32));
+    for (int j = 0; j < 8; j++) {                 /* j = 0 ↔ bit 7 */
+        cnt[j] += (uint32_t)(__builtin_popcount((unsigned)_mm256_movemask_epi8(a)) + __builtin_popcount((unsigned)_mm256_movemask_epi8(b)));
+        a = _mm256_add_epi8(a, a);
+        b = _mm256_add_epi8(b, b);
+    }
+}
+#else
 static inline void count8(uint32_t *cnt /* 8 targets of this column, cnt[j] ↔ bit 7-j */, const uint8_t *buf, int n) {
     /* positional popcount over n<=64 bytes, SWAR on 64-bit words */
     uint64_t w[8];
@@ -449,6 +464,7 @@ static inline void count8(uint32_t *cnt /* 8 targets of this column, cnt[j] ↔ 
         cnt[7 - b] += (uint32_t)c;
     }
 }
+#endif
 
 static void probe_block(const ko_block *b, const uint64_t *codes, int64_t n, int algo, uint32_t *counts /* row_bytes*8 */, uint8_t *scratch /* 64*row_bytes + row_bytes */) {
     int rb = b->row_bytes, h = b->num_hashes;

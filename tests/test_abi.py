@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), "libkmcp_gpu.so does not export " + s
     assert set(syms) == set(api.ABI_SYMBOLS)
-    assert L.kmcpg_abi_version() == 1
+    assert L.kmcpg_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

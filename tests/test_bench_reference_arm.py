@@ -20,14 +20,14 @@ def test_reference_arm_contract_and_multi_rank_workload(oracle, monkeypatch, cap
     staged = {}
 
     def stage(tmp, world, n_total):
+        # what bench.py's helper process leaves behind: ONE database of `world` blocks under tmp/R001, the reads in tmp/reads.u8
         sp = O.sketch_params(bench.K)
-        dirs = []
-        for r in range(world):
-            targets = helpers.make_synth_targets(O, sp, bench.GENOME_SEED + r, 20, 20000, bench.N_CHUNKS, bench.OVERLAP)
-            dirs.append(O.build_db(targets, "%s/shard%d" % (tmp, r), sp, num_hashes=bench.H, fpr=bench.FPR, block_size=200))
+        targets = helpers.make_synth_targets(O, sp, bench.GENOME_SEED, 20 * world, 20000, bench.N_CHUNKS, bench.OVERLAP)
+        r001 = O.build_db(targets, tmp, sp, num_hashes=bench.H, fpr=bench.FPR, block_size=200)
+        assert len(O.DB(r001).info.__class__._fields_) and O.DB(r001).info.n_blocks == world
         reads = helpers.make_reads(O, bench.READ_SEED, n_total, 20, 20000, bench.GENOME_SEED, bench.READ_LEN)
+        np.frombuffer(b"".join(reads), dtype=np.uint8).tofile(tmp + "/reads.u8")
         staged["world"], staged["n"] = world, n_total
-        return dirs, np.frombuffer(b"".join(reads), dtype=np.uint8)
 
     for world in (1, 2):
         args = argparse.Namespace(gpus=world, steps=2, warmup=1)

@@ -1,5 +1,7 @@
-"""N>1 host logic on CPU: world_size-2 gloo processes shard the hit space by block owner (the plan the library
-uses), gather on rank 0, and the union must equal the single-process result."""
+"""N>1 host logic on CPU: world_size-2 gloo processes play the ranks of a one-process-per-GPU run.  Each rank holds the hits whose
+targets live in the blocks the library's shard plan gives it (what its GPU context would return), hands them to rank 0 through the
+shared-memory hit exchange (kmcp_b200.multigpu.HitExchange over kmcpg_shm_open, here without CUDA registration), and rank 0's merge +
+host post-filter (kmcpg_merge_hits, kmcpg_engine_postfilter) must reproduce the single-process oracle result bit for bit."""
 import os
 import socket
 import sys
@@ -23,6 +25,7 @@ def _free_port():
 def _worker(rank, world, port, r001, out_path):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
     import torch.distributed as dist
     from kmcp_b200 import api, multigpu
     from oracle import oracle as O
@@ -31,33 +34,57 @@ def _worker(rank, world, port, r001, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     owner = api.shard_plan(r001, world)
     odb = O.DB(r001)
-    reads = helpers.make_reads(O, 31, 1200, 20, 20000, 9)
-    o = O.default_opts(); o.max_fpr = 1.0
-    res = odb.search(reads, opts=o)
-    # this rank's shard = hits whose target lives in a block it owns (what its GPU context would return)
+    n_steps, per_step = 5, 400
+    o = O.default_opts()
+    hx = multigpu.HitExchange("kmcp_gloo_test_%d" % port, rank, world, cap_hits=1 << 16, barrier=lambda: dist.barrier(), cuda_register=False)
     blk = np.array([odb.target(int(t)).block for t in range(odb.info.n_targets)])
-    mine = np.array([owner[b] == rank for b in blk[res.hits["target"]]], dtype=bool) if len(res.hits) else np.zeros(0, bool)
-    dt = np.dtype([("query", "<u4"), ("target", "<u4"), ("count", "<u4")])
-    local = np.zeros(int(mine.sum()), dtype=dt)
-    for f in ("query", "target", "count"):
-        local[f] = res.hits[f][mine]
-    merged = multigpu.gather_hits(local, rank, world)
-    padded = multigpu.gather_hits_padded(local, rank, world, "cpu")           # the NCCL-shaped gather, here on gloo
-    shifted = multigpu.gather_hits_padded(local, rank, world, "cpu", target_base=1000 * rank)
-    if rank == 0:
-        full = np.zeros(len(res.hits), dtype=dt)
+    tsizes = np.array([odb.target(int(t)).n_kmers for t in range(odb.info.n_targets)], dtype=np.float64)
+    ok, why = True, ""
+    digest_parts = 0
+    for s in range(n_steps):           # more steps than slots: the slot hand-back is exercised too
+        reads = helpers.make_reads(O, 31 + s, per_step, 20, 20000, 9)
+        oo = O.default_opts(); oo.max_fpr = 1.0; oo.min_target_cov = 0.0
+        raw = odb.search(reads, opts=oo)          # every (query, target, count) above the query-coverage threshold = what the probe kernel emits
+        mine = np.array([owner[b] == rank for b in blk[raw.hits["target"]]], dtype=bool) if len(raw.hits) else np.zeros(0, bool)
+        local = np.zeros(int(mine.sum()), dtype=api.HIT_DTYPE)
         for f in ("query", "target", "count"):
-            full[f] = res.hits[f]
-        full = full[np.lexsort((full["target"], full["query"]))]
-        ok = np.array_equal(merged, full) and len(full) > 500 and 0 < len(local) < len(full)
-        ok = ok and np.array_equal(padded[np.lexsort((padded["target"], padded["query"]))], full)
-        ok = ok and np.array_equal(shifted[:len(local)], local) and int(shifted["target"].astype(np.int64).sum() - padded["target"].astype(np.int64).sum()) == 1000 * (len(full) - len(local))
-        open(out_path, "w").write("ok" if ok else "mismatch %d %d %d" % (len(merged), len(full), len(local)))
+            local[f] = raw.hits[f][mine]
+        local = local[np.lexsort((local["target"], local["query"]))]
+        # the rank's library would copy device→host into its slot; here the bytes are written directly
+        hx.wait_free(s)
+        dst = np.frombuffer((C.c_uint8 * (len(local) * 12)).from_address(hx.hits_ptr(s)), dtype=np.uint8)
+        dst[:] = local.view(np.uint8)
+        hx.publish(s, len(local))
+        if rank == 0:
+            lists = hx.collect(s)
+            ok = ok and len(lists) == world and 0 < len(lists[0]) and sum(len(x) for x in lists) == len(raw.hits)
+            merged = multigpu.merge_lists(lists, 0, per_step, threads=3)
+            full = np.zeros(len(raw.hits), dtype=api.HIT_DTYPE)
+            for f in ("query", "target", "count"):
+                full[f] = raw.hits[f]
+            full = full[np.lexsort((full["target"], full["query"]))]
+            if not np.array_equal(merged, full):
+                ok, why = False, "merge step %d" % s
+            if multigpu.hits_digest(merged) != multigpu.hits_digest(full) or multigpu.hits_digest(merged) == multigpu.hits_digest(merged[::-1].copy()):
+                ok, why = False, "digest step %d" % s
+            digest_parts += multigpu.hits_digest(merged)
+            # host post-filter over the merged lists == the oracle's full engine answer (defaults: FPR <= 0.01 filter, sort by qcov)
+            exp = odb.search(reads, opts=o)
+            eo = api.EngineOpts()
+            api.load().kmcpg_default_engine_opts(C.byref(eo))
+            got = multigpu.postfilter(eo, raw.n_kmers, raw.query_len, merged, tsizes, odb.info.fpr, odb.info.ks[0])
+            same = np.array_equal(got.match_off, exp.hit_off) and all(np.array_equal(got.matches[f], exp.hits[f]) for f in ("query", "target", "count", "fpr", "qcov", "tcov", "jacc"))
+            if not same or len(exp.hits) < 100:
+                ok, why = False, "postfilter step %d" % s
+            hx.release(s)
     dist.barrier()
+    hx.close()
+    if rank == 0:
+        open(out_path, "w").write("ok" if ok and digest_parts else "mismatch: " + why)
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_equals_single_process(oracle, tmp_path):
+def test_two_rank_hit_exchange_equals_single_process(oracle, tmp_path):
     import torch.multiprocessing as mp
     O = oracle
     sp = O.sketch_params(21)
@@ -70,3 +97,24 @@ def test_two_rank_gather_equals_single_process(oracle, tmp_path):
     out = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(2, _free_port(), r001, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_shared_segment_roundtrip_and_errors(tmp_path):
+    """kmcpg_shm_open / kmcpg_shm_close without CUDA registration: two mappings of one name see each other's bytes"""
+    import ctypes as C
+    from kmcp_b200 import api
+    L = api.load()
+    name = ("kmcp_shm_test_%d" % os.getpid()).encode()
+    a, b = C.c_void_p(), C.c_void_p()
+    assert L.kmcpg_shm_open(name, 4096, 1, 0, C.byref(a)) == 0
+    assert L.kmcpg_shm_open(name, 4096, 0, 0, C.byref(b)) == 0 and a.value != b.value
+    va = np.frombuffer((C.c_uint8 * 4096).from_address(a.value), dtype=np.uint8)
+    vb = np.frombuffer((C.c_uint8 * 4096).from_address(b.value), dtype=np.uint8)
+    va[:] = np.arange(4096, dtype=np.uint64).astype(np.uint8)
+    assert np.array_equal(va, vb)
+    c = C.c_void_p()
+    assert L.kmcpg_shm_open(name, 8192, 0, 0, C.byref(c)) == api.KMCPG_EIO          # smaller than asked for
+    assert L.kmcpg_shm_open(b"kmcp_shm_test_missing", 4096, 0, 0, C.byref(c)) == api.KMCPG_EIO
+    del va, vb
+    assert L.kmcpg_shm_close(name, b, 4096, 0, 0) == 0 and L.kmcpg_shm_close(name, a, 4096, 0, 1) == 0
+    assert L.kmcpg_shm_open(name, 4096, 0, 0, C.byref(c)) == api.KMCPG_EIO          # unlinked
