@@ -176,6 +176,8 @@ typedef struct {
     uint64_t hits_cap;           /*   e.g. a shared-memory segment another process reads); more than hits_cap hits: KMCPG_ENOMEM */
     kmcpg_part_cb cb;            /* optional: parts are handed over as they land (see kmcpg_search_batch_cb) */
     void *user;
+    uint32_t first_query;        /* added to the query index of every hit and part reported (a batch submitted as several jobs); */
+    uint32_t _pad;               /*   n_kmers / query_len of kmcpg_search_wait stay indexed from 0 */
 } kmcpg_batch;
 int kmcpg_search_submit(kmcpg_ctx *ctx, const kmcpg_search_params *p, const kmcpg_batch *b, kmcpg_job **job);
 /* blocks until the job is done and releases it; out as for kmcpg_search_batch (out->hits == hits_dst when one was given);

@@ -75,7 +75,8 @@ PART_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Part))
 
 class Batch(C.Structure):
     _fields_ = [("seq", C.c_void_p), ("off", C.c_void_p), ("n_seqs", C.c_uint32), ("on_device", C.c_int32), ("host_off", C.c_void_p),
-                ("ready_event", C.c_void_p), ("hits_dst", C.c_void_p), ("hits_cap", C.c_uint64), ("cb", C.c_void_p), ("user", C.c_void_p)]
+                ("ready_event", C.c_void_p), ("hits_dst", C.c_void_p), ("hits_cap", C.c_uint64), ("cb", C.c_void_p), ("user", C.c_void_p),
+                ("first_query", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class SketchParams(C.Structure):
@@ -417,9 +418,9 @@ class Context:
         return self._take_hits(h, copy)
 
     def submit(self, seq_ptr: int, off_ptr: int, n_seqs: int, params: SearchParams, device: bool = False, host_off_ptr: int = 0,
-               hits_dst: int = 0, hits_cap: int = 0, ready_event: int = 0) -> int:
+               hits_dst: int = 0, hits_cap: int = 0, ready_event: int = 0, first_query: int = 0) -> int:
         """kmcpg_search_submit with raw pointers (the caller keeps the buffers alive until wait()); returns the job handle"""
-        b = Batch(seq_ptr, off_ptr, n_seqs, 1 if device else 0, host_off_ptr or None, ready_event or None, hits_dst or None, hits_cap, None, None)
+        b = Batch(seq_ptr, off_ptr, n_seqs, 1 if device else 0, host_off_ptr or None, ready_event or None, hits_dst or None, hits_cap, None, None, first_query, 0)
         job = C.c_void_p()
         self._check(self._L.kmcpg_search_submit(self._h, C.byref(params), C.byref(b), C.byref(job)))
         return job.value

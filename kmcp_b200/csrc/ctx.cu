@@ -71,7 +71,7 @@ void free_db(kmcpg_ctx *ctx) {
 }
 
 void WorkSet::release() {
-    for (DevBuf *b : {&seq, &off, &slot_cnt, &slot_off, &codes, &codes2, &locs, &ncodes, &qlen, &nk, &neff, &thresh, &hkeys, &hvals, &hkeys2, &hvals2,
+    for (DevBuf *b : {&seq, &off, &slot_cnt, &slot_off, &codes, &codes2, &locs[0], &locs[1], &ncodes, &qlen, &nk, &neff, &thresh, &hkeys, &hvals, &hkeys2, &hvals2,
                       &hits, &counters, &tmp, &tmp2, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off, &tile_n, &tile_off, &tile_cnt, &tile_pre})
         b->release();
     h_off.release(); h_cnt.release();
@@ -208,10 +208,12 @@ int kmcpg_create(int device, kmcpg_ctx **out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->cnt_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->in_st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-    {   // query preparation of the next part runs beside the probes of the current one: ahead of the queued probe CTAs
+    {   // query preparation of the next part runs beside the probes of the current one, at the probe stream's own (lowest) priority:
+        // its CTAs take the SM slots the probe's last wave leaves idle; ahead of the queued probe CTAs they only displace them (measured:
+        // 27.1 ms per C2 step at the same priority, 28.0 ms at a higher one, 27.6 ms on one stream; profiles/README.md round 2)
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        int prio = hi;
+        int prio = lo;
 #ifdef KMCPG_DEV
         if (const char *v = getenv("KMCPG_HASH_PRIO")) prio = !strcmp(v, "low") ? lo : (!strcmp(v, "high") ? hi : (lo + hi) / 2);
 #endif
@@ -254,6 +256,8 @@ int kmcpg_close(kmcpg_ctx *ctx) {
     ctx->h_stage.release(); ctx->h_small.release();
     for (auto &b : ctx->pin_pool) cudaFreeHost(b.p);
     ctx->pin_pool.clear();
+    for (auto &b : ctx->stage_pool) b.release();
+    ctx->stage_pool.clear();
     if (ctx->own_st) cudaStreamDestroy(ctx->own_st);
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     if (ctx->cnt_st) cudaStreamDestroy(ctx->cnt_st);
@@ -447,6 +451,109 @@ int kmcpg_shm_close(const char *name, void *ptr, size_t bytes, int cuda_register
     return KMCPG_OK;
 }
 
+// ---- one batch staged for several contexts of this process (kmcpg_engine_search_sharded) ----------------------------------
+// The batch crosses PCIe ONCE, into the first context's device; the other contexts get it by peer-to-peer copies (NVLink), piece by
+// piece, so every context can start on piece j while piece j+1 is still travelling.  ready(i, j) is the event after which piece j
+// is complete on context i (kmcpg_batch.ready_event of the job that searches it).
+struct kmcpg_stage {
+    std::vector<kmcpg_ctx *> ctxs;
+    std::vector<DevBuf> seq, off;
+    std::vector<std::vector<cudaEvent_t>> ready;      // [ctx][piece]
+    std::vector<uint64_t> rebased;                    // offsets made relative to the first byte staged
+};
+
+static void stage_release(kmcpg_stage *st) {
+    for (size_t i = 0; i < st->ctxs.size(); i++) {
+        cudaSetDevice(st->ctxs[i]->device);
+        for (cudaEvent_t e : st->ready[i]) cudaEventDestroy(e);
+        std::lock_guard<std::mutex> lk(st->ctxs[i]->pin_mu);
+        if (st->seq[i].p) st->ctxs[i]->stage_pool.push_back(st->seq[i]);
+        if (st->off[i].p) st->ctxs[i]->stage_pool.push_back(st->off[i]);
+        while (st->ctxs[i]->stage_pool.size() > 8) { st->ctxs[i]->stage_pool.front().release(); st->ctxs[i]->stage_pool.erase(st->ctxs[i]->stage_pool.begin()); }
+    }
+    delete st;
+}
+
+static cudaError_t stage_buffer(kmcpg_ctx *c, size_t bytes, DevBuf &out) {
+    {
+        std::lock_guard<std::mutex> lk(c->pin_mu);
+        int best = -1;
+        for (size_t i = 0; i < c->stage_pool.size(); i++)
+            if (c->stage_pool[i].cap >= bytes && (best < 0 || c->stage_pool[i].cap < c->stage_pool[best].cap)) best = (int)i;
+        if (best >= 0) { out = c->stage_pool[best]; c->stage_pool.erase(c->stage_pool.begin() + best); return cudaSuccess; }
+    }
+    return out.ensure(bytes);
+}
+
+int kmcpg_internal_stage_begin(kmcpg_ctx *const *ctxs, int n_ctx, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs, const uint32_t *cuts, int n_pieces,
+                               kmcpg_stage **out) {
+    if (!ctxs || n_ctx < 1 || !seq || !off || !cuts || n_pieces < 1 || !out || cuts[0] != 0 || cuts[n_pieces] != n_seqs) return KMCPG_EINVAL;
+    kmcpg_ctx *ctx = ctxs[0];                         // errors are reported on the first context
+    kmcpg_stage *st = new kmcpg_stage();
+    st->ctxs.assign(ctxs, ctxs + n_ctx);
+    st->seq.resize(n_ctx); st->off.resize(n_ctx); st->ready.resize(n_ctx);
+    const uint64_t base = off[0], bytes = off[n_seqs] - base;
+    const uint64_t *hoff = off;
+    if (base) {
+        st->rebased.resize((size_t)n_seqs + 1);
+        for (uint32_t i = 0; i <= n_seqs; i++) st->rebased[i] = off[i] - base;
+        hoff = st->rebased.data();
+    }
+    auto body = [&]() -> int {
+        for (int i = 0; i < n_ctx; i++) {
+            kmcpg_ctx *c = ctxs[i];
+            CU(cudaSetDevice(c->device));
+            CU(stage_buffer(c, bytes + 64, st->seq[i]));
+            CU(stage_buffer(c, ((size_t)n_seqs + 1) * 8, st->off[i]));
+            st->ready[i].resize(n_pieces);
+            for (int j = 0; j < n_pieces; j++) CU(cudaEventCreateWithFlags(&st->ready[i][j], cudaEventDisableTiming));
+            if (i > 0 && c->device != ctxs[0]->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, c->device, ctxs[0]->device);
+                if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[0]->device, 0); if (e != cudaSuccess) (void)cudaGetLastError(); }   // "already enabled" is fine
+            }
+        }
+        kmcpg_ctx *r = ctxs[0];
+        for (int j = 0; j < n_pieces; j++) {
+            const uint64_t o0 = hoff[cuts[j]], o1 = hoff[cuts[j + 1]];
+            CU(cudaSetDevice(r->device));
+            if (j == 0) CU(cudaMemcpyAsync(st->off[0].p, hoff, ((size_t)n_seqs + 1) * 8, cudaMemcpyHostToDevice, r->in_st));
+            if (o1 > o0) CU(cudaMemcpyAsync((uint8_t *)st->seq[0].p + o0, seq + base + o0, o1 - o0, cudaMemcpyHostToDevice, r->in_st));
+            CU(cudaEventRecord(st->ready[0][j], r->in_st));
+            for (int i = 1; i < n_ctx; i++) {
+                kmcpg_ctx *c = ctxs[i];
+                CU(cudaSetDevice(c->device));
+                CU(cudaStreamWaitEvent(c->in_st, st->ready[0][j], 0));
+                if (j == 0) CU(cudaMemcpyPeerAsync(st->off[i].p, c->device, st->off[0].p, r->device, ((size_t)n_seqs + 1) * 8, c->in_st));
+                if (o1 > o0) CU(cudaMemcpyPeerAsync((uint8_t *)st->seq[i].p + o0, c->device, (uint8_t *)st->seq[0].p + o0, r->device, o1 - o0, c->in_st));
+                CU(cudaEventRecord(st->ready[i][j], c->in_st));
+            }
+        }
+        return KMCPG_OK;
+    };
+    const int rc = body();
+    if (rc) {
+        for (int i = 0; i < n_ctx; i++) { cudaSetDevice(ctxs[i]->device); cudaStreamSynchronize(ctxs[i]->in_st); }
+        stage_release(st);
+        return rc;
+    }
+    *out = st;
+    return KMCPG_OK;
+}
+
+int kmcpg_internal_stage_get(kmcpg_stage *st, int i, int piece, const uint8_t **d_seq, const uint64_t **d_off, void **ready) {
+    if (!st || i < 0 || i >= (int)st->ctxs.size() || piece < 0 || piece >= (int)st->ready[i].size()) return KMCPG_EINVAL;
+    *d_seq = (const uint8_t *)st->seq[i].p; *d_off = (const uint64_t *)st->off[i].p; *ready = (void *)st->ready[i][piece];
+    return KMCPG_OK;
+}
+
+// after every job that reads the staged batch has been waited for
+void kmcpg_internal_stage_end(kmcpg_stage *st) {
+    if (!st) return;
+    for (kmcpg_ctx *c : st->ctxs) { cudaSetDevice(c->device); cudaStreamSynchronize(c->in_st); }
+    stage_release(st);
+}
+
 int kmcpg_target_sizes(const kmcpg_ctx *ctx, double *out, int64_t n) {
     if (!ctx || !out || !ctx->has_db || n < (int64_t)ctx->target_sizes.size()) return KMCPG_EINVAL;
     memcpy(out, ctx->target_sizes.data(), ctx->target_sizes.size() * sizeof(double));
@@ -597,7 +704,7 @@ int kmcpg_count_codes(kmcpg_ctx *ctx, const uint64_t *codes, uint64_t n, uint32_
     CU(cudaMemsetAsync(ctx->d_dense.p, 0, std::max<uint64_t>(nt, 1) * 4, st));
     if (n > 0) {
         if (n >= (1ull << 32) - 1) return fail(ctx, KMCPG_EUNSUPPORTED, "too many codes");
-        CU(w.codes.ensure(n * 8)); CU(w.slot_off.ensure(16));
+        CU(w.codes.ensure(n * 8)); CU(w.locs[0].ensure(n * 4 * H)); CU(w.slot_off.ensure(16));
         CU(w.neff.ensure(4)); CU(w.thresh.ensure(4)); CU(w.counters.ensure(64));
         CU(w.hkeys.ensure(8)); CU(w.hvals.ensure(4));
         uint64_t so[2] = {0, n};
@@ -615,6 +722,10 @@ int kmcpg_count_codes(kmcpg_ctx *ctx, const uint64_t *codes, uint64_t n, uint32_
             pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = b.row_bytes;
             pa.n_names = b.n_cols; pa.target_base = (uint32_t)(bm.target_base + b.col0); pa.num_hashes = H;
             pa.codes = w.codes.as<uint64_t>(); pa.fm = b.fm; pa.slot_off = w.slot_off.as<uint64_t>();
+            if (bm.num_sigs < 0xFFFFFFFFull) {
+                CU(launch_locs(w.codes.as<uint64_t>(), n, H, b.fm, w.locs[0].as<uint32_t>(), st));
+                pa.locs = w.locs[0].as<uint32_t>();
+            }
             pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = 1; pa.paired = 0;
             pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
             pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = 0; pa.dense_counts = ctx->d_dense.as<uint32_t>();

@@ -71,6 +71,7 @@ struct HitsPriv {
     PinBuf nk, ql, hits;
     bool ext_hits = false;      // hits.p is the caller's buffer (kmcpg_batch.hits_dst): never grown, never returned to the pool
     uint32_t nq = 0;
+    uint32_t first_query = 0;   // kmcpg_batch.first_query: added to the query index of every hit and part the job reports
     uint64_t nh = 0;
 };
 
@@ -89,13 +90,13 @@ struct SubBatch {
 // device + pinned buffers of one in-flight sub-batch; two sets let the host-side work of part i
 // (hit count round trip, result copies) hide behind the kernels of part i+1
 struct WorkSet {
-    DevBuf seq, off, slot_cnt, slot_off, codes, codes2, locs, ncodes, qlen, nk, neff, thresh;
+    DevBuf seq, off, slot_cnt, slot_off, codes, codes2, locs[2], ncodes, qlen, nk, neff, thresh;
     DevBuf hkeys, hvals, hkeys2, hvals2, hits, counters, tmp, tmp2, segb, sege;
     DevBuf ck, cs, cs_cnt, cs_off;      // sketch selection: per-position k-mer / s-mer hashes
     DevBuf tile_n, tile_off, tile_cnt, tile_pre;   // long sequences: tiles per sequence, their scan, codes per tile, their scan
     HostBuf h_off, h_cnt;
     cudaEvent_t ev_in = nullptr, ev_a0 = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_cnt = nullptr, ev_sorted = nullptr, ev_b = nullptr;
-    std::vector<cudaEvent_t> probe_ev;   // 3 slots per resident block: [1] before, [2] after its probe launch
+    std::vector<cudaEvent_t> probe_ev;   // 3 slots per resident block: [0] its row indices are ready, [1] before, [2] after its probe launch
     // state of the part currently in flight
     bool busy = false;
     SubBatch sb{};
@@ -130,6 +131,7 @@ struct kmcpg_ctx {
     kmcpg::DevBuf d_tmp, d_dense, d_scal, d_genome;
     kmcpg::HostBuf h_stage, h_small;
     std::vector<kmcpg::PinBuf> pin_pool;
+    std::vector<kmcpg::DevBuf> stage_pool;   // device buffers of batches staged for several contexts (kmcpg_engine_search_sharded)
     std::mutex pin_mu;
     std::string err;
     std::mutex mu;

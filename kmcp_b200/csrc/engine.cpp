@@ -23,6 +23,11 @@
 #include "common.h"
 
 extern "C" const double *kmcpg_internal_target_sizes(const kmcpg_ctx *ctx);
+struct kmcpg_stage;
+extern "C" int kmcpg_internal_stage_begin(kmcpg_ctx *const *ctxs, int n_ctx, const uint8_t *seq, const uint64_t *off, uint32_t n_seqs, const uint32_t *cuts, int n_pieces,
+                                          kmcpg_stage **out);
+extern "C" int kmcpg_internal_stage_get(kmcpg_stage *st, int i, int piece, const uint8_t **d_seq, const uint64_t **d_off, void **ready);
+extern "C" void kmcpg_internal_stage_end(kmcpg_stage *st);
 
 namespace {
 
@@ -608,10 +613,56 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
             if (n_ctx > 1) {
                 std::function<void(const kmcpg_part &)> fn = [&](const kmcpg_part &pt) { absorb(pt, pt.first_query); };
                 const uint32_t round_seqs = ln_total * step;
+                // The batch crosses PCIe once (into the first context's device) and reaches the others by peer copies, in a few pieces;
+                // every shard searches piece j as a job of its own, so piece j+1 travels while piece j is probed.
+                std::vector<uint32_t> cuts{0};
+                {
+                    const uint64_t bytes = round_seqs ? bo[round_seqs] - bo[0] : 0;
+                    const int n_pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, bytes / (24ull << 20)));
+                    for (int j = 1; j < n_pieces; j++) {
+                        const uint64_t want = bo[0] + bytes * (uint64_t)j / (uint64_t)n_pieces;
+                        uint32_t lo = cuts.back() / step, hi = ln_total;       // first query whose first byte is at or after `want`
+                        while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (bo[(size_t)mid * step] < want) lo = mid + 1; else hi = mid; }
+                        if (lo * step > cuts.back() && lo < ln_total) cuts.push_back(lo * step);
+                    }
+                    cuts.push_back(round_seqs);
+                }
+                const int n_pieces = (int)cuts.size() - 1;
+                kmcpg_stage *stage = nullptr;
+                if (round_seqs) {
+                    rc = kmcpg_internal_stage_begin(ctxs, n_ctx, bs, bo, round_seqs, cuts.data(), n_pieces, &stage);
+                    if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
+                }
                 ShardSearch dev = [&](int s, kmcpg_part_cb cb, void *user, kmcpg_hits *summary) {
-                    return kmcpg_search_batch_cb(ctxs[s], &p, bs, bo, round_seqs, cb, user, summary);
+                    if (!stage) return kmcpg_search_batch_cb(ctxs[s], &p, bs, bo, round_seqs, cb, user, summary);
+                    const auto t0 = std::chrono::steady_clock::now();
+                    std::vector<kmcpg_job *> jobs((size_t)n_pieces, nullptr);
+                    int r = KMCPG_OK;
+                    for (int j = 0; j < n_pieces && !r; j++) {
+                        kmcpg_batch b;
+                        memset(&b, 0, sizeof(b));
+                        void *ready = nullptr;
+                        r = kmcpg_internal_stage_get(stage, s, j, &b.seq, &b.off, &ready);
+                        if (r) break;
+                        b.off += cuts[j]; b.host_off = bo + cuts[j]; b.n_seqs = cuts[j + 1] - cuts[j]; b.on_device = 1; b.ready_event = ready;
+                        b.cb = cb; b.user = user; b.first_query = cuts[j] / step;
+                        r = kmcpg_search_submit(ctxs[s], &p, &b, &jobs[j]);
+                    }
+                    memset(summary, 0, sizeof(*summary));
+                    for (int j = 0; j < n_pieces; j++) {
+                        if (!jobs[j]) continue;
+                        kmcpg_hits h;
+                        const int rw = kmcpg_search_wait(jobs[j], &h);
+                        if (rw) { if (!r) r = rw; continue; }
+                        summary->probe_row_bytes += h.probe_row_bytes; summary->kernel_launches += h.kernel_launches; summary->probe_launches += h.probe_launches;
+                        summary->ms_probe += h.ms_probe; summary->ms_hash += h.ms_hash; summary->n_hits += h.n_hits; summary->n_queries += h.n_queries;
+                        kmcpg_free_hits(&h);
+                    }
+                    summary->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                    return r;
                 };
                 rc = sharded_round(n_ctx, dev, fn, out, threads);
+                kmcpg_internal_stage_end(stage);
                 if (rc) { for (auto &r : rounds) big_release(r.buf); delete priv; return rc; }
             } else {
                 std::function<void(const kmcpg_part &)> fn = [&](const kmcpg_part &pt) { absorb(pt, pt.first_query); };

@@ -184,29 +184,48 @@ int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int
     return KMCPG_OK;
 }
 
-// one probe launch per resident block on the compute stream (the kernel derives the row indices from the codes itself),
-// then the counters travel to the host on their own stream
-static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p) {
+// Per resident block: the row indices (locs kernel, on the query-preparation stream: the indices of block b+1 are computed while
+// block b is probed; two buffers alternate) and ONE probe launch on the compute stream; then the counters travel to the host on
+// their own stream.  Blocks with numSigs >= 2^32-1 need no locs kernel: their probe derives 64-bit indices itself.
+static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, cudaStream_t hs) {
     cudaStream_t st = ctx->st;
     const int H = ctx->meta.num_hashes;
     CU(w.hkeys.ensure(w.cap * 8)); CU(w.hvals.ensure(w.cap * 4));
+    bool in_kernel = false;
 #ifdef KMCPG_DEV
-    static const bool locs_buffer = getenv("KMCPG_PROBE_LOCS") && !strcmp(getenv("KMCPG_PROBE_LOCS"), "buffer");
-    if (locs_buffer) CU(w.locs.ensure(std::max<uint64_t>(w.sb.total_slots, 1) * 4ull * H));
+    static const bool dev_in_kernel = getenv("KMCPG_PROBE_LOCS") && !strcmp(getenv("KMCPG_PROBE_LOCS"), "kernel");
+    in_kernel = dev_in_kernel;
 #endif
+    const bool by_query = ctx->meta.scaled || ctx->meta.minimizer || ctx->meta.syncmer;
+    bool any_locs = false;
+    for (auto &b : ctx->blocks) any_locs = any_locs || (!in_kernel && ctx->meta.blocks[b.meta_idx].num_sigs < 0xFFFFFFFFull);
+    const size_t locs_bytes = std::max<uint64_t>(w.sb.total_slots, 1) * 4ull * H;
+    if (any_locs) {
+        CU(w.locs[0].ensure(locs_bytes));
+        if (ctx->blocks.size() > 1) CU(w.locs[1].ensure(locs_bytes));
+    }
     CU(cudaMemsetAsync(w.counters.p, 0, 8, st));
     size_t bi = 0;
     for (auto &b : ctx->blocks) {
         const BlockMeta &bm = ctx->meta.blocks[b.meta_idx];
-#ifdef KMCPG_DEV
-        if (locs_buffer && bm.num_sigs < 0xFFFFFFFFull) CU(launch_locs(w.codes_ptr, w.sb.total_slots, H, b.fm, w.locs.as<uint32_t>(), st));
-#endif
+        const bool use_locs = !in_kernel && bm.num_sigs < 0xFFFFFFFFull;
+        uint32_t *locs = use_locs ? w.locs[bi & 1].as<uint32_t>() : nullptr;
+        if (use_locs) {
+            if (bi >= 2 && hs != st) CU(cudaStreamWaitEvent(hs, w.probe_ev[(bi - 2) * 3 + 2], 0));   // the probe that read this buffer last
+            if (by_query) CU(launch_locs_by_query(w.codes_ptr, w.slot_off.as<uint64_t>(), w.neff.as<uint32_t>(), w.nq, p.paired, H, b.fm, locs, hs));
+            else CU(launch_locs(w.codes_ptr, w.sb.total_slots, H, b.fm, locs, hs));
+            ctx->launches++;
+            if (hs != st) {
+                CU(cudaEventRecord(w.probe_ev[bi * 3], hs));
+                CU(cudaStreamWaitEvent(st, w.probe_ev[bi * 3], 0));
+            }
+        }
         CU(cudaEventRecord(w.probe_ev[bi * 3 + 1], st));
         ProbeArgs pa;
         memset(&pa, 0, sizeof(pa));
         pa.rows = b.d_rows; pa.pitch = b.pitch; pa.row_bytes = b.row_bytes;
         pa.n_names = b.n_cols; pa.target_base = (uint32_t)(bm.target_base + b.col0); pa.num_hashes = H;
-        pa.codes = w.codes_ptr; pa.fm = b.fm; pa.slot_off = w.slot_off.as<uint64_t>();
+        pa.codes = w.codes_ptr; pa.fm = b.fm; pa.locs = locs; pa.slot_off = w.slot_off.as<uint64_t>();
         pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = w.nq; pa.paired = p.paired;
         pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
         pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = w.cap; pa.dense_counts = nullptr; pa.planes = w.planes;
@@ -265,7 +284,7 @@ static int enqueue_part(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p
     w.planes = planes_for(w.sb.max_query_slots);
     w.cap = std::max<uint64_t>(1u << 20, 4ull * w.nq);
     if (w.hkeys.cap / 8 > w.cap) w.cap = w.hkeys.cap / 8;
-    rc = enqueue_probes(ctx, w, p);
+    rc = enqueue_probes(ctx, w, p, hs);
     if (rc) return rc;
     w.busy = true;
     return KMCPG_OK;
@@ -302,7 +321,7 @@ static int finish_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &
         CU(cudaStreamSynchronize(st));
         CU(cudaStreamSynchronize(ctx->copy_st));
         w.cap = w.n_hits + w.n_hits / 4 + 1024;
-        int rc = enqueue_probes(ctx, w, p);
+        int rc = enqueue_probes(ctx, w, p, st);
         if (rc) return rc;
     }
     float a = 0;
@@ -327,7 +346,7 @@ static int finish_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &
         CU(w.tmp2.ensure(t3));
         CU(cub::DeviceRadixSort::SortPairs(w.tmp2.p, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
                                            (int64_t)n_hits, 0, 32 + qbits, ps));
-        CU(launch_pack_hits(w.hkeys2.as<uint64_t>(), w.hvals2.as<uint32_t>(), n_hits, w.sb.query_base, w.hits.as<kmcpg_hit>(), ps));
+        CU(launch_pack_hits(w.hkeys2.as<uint64_t>(), w.hvals2.as<uint32_t>(), n_hits, w.sb.query_base + res.first_query, w.hits.as<kmcpg_hit>(), ps));
         ctx->launches += 4;
     }
     CU(cudaEventRecord(w.ev_sorted, ps));
@@ -486,7 +505,7 @@ static int deliver_job(kmcpg_ctx *ctx, kmcpg_job *job) {
         if (job->cb) {
             HitsPriv &res = *job->priv;
             kmcpg_part pt;
-            pt.first_query = d.first_query; pt.n_queries = d.nq;
+            pt.first_query = d.first_query + res.first_query; pt.n_queries = d.nq;
             pt.n_kmers = (const int32_t *)res.nk.p + d.first_query; pt.query_len = (const int32_t *)res.ql.p + d.first_query;
             pt.hits = (const kmcpg_hit *)res.hits.p + d.hit_dst; pt.n_hits = d.n_hits;
             job->cb(job->user, &pt);
@@ -642,6 +661,7 @@ int kmcpg_search_submit(kmcpg_ctx *ctx, const kmcpg_search_params *p, const kmcp
     kmcpg_job *job = new kmcpg_job();
     auto bail = [&](int code) { if (job->priv) drop_priv(job->priv); pin_release(ctx, job->hoff_own); delete job; return code; };
     job->ctx = ctx; job->p = *p; job->k = k; job->n_seqs = b->n_seqs; job->cb = b->cb; job->user = b->user;
+    const uint32_t first_query = b->first_query;
     job->t0 = std::chrono::steady_clock::now();
     const uint64_t *cut_off = b->off;
     static const uint64_t zero_off[1] = {0};
@@ -669,7 +689,7 @@ int kmcpg_search_submit(kmcpg_ctx *ctx, const kmcpg_search_params *p, const kmcp
     if (rc) return bail(rc);
     HitsPriv *priv = new HitsPriv();
     job->priv = priv;
-    priv->ctx = ctx; priv->nq = b->n_seqs / step;
+    priv->ctx = ctx; priv->nq = b->n_seqs / step; priv->first_query = first_query;
     rc = pin_acquire(ctx, std::max<uint32_t>(priv->nq, 1) * 4ull, priv->nk);
     if (!rc) rc = pin_acquire(ctx, std::max<uint32_t>(priv->nq, 1) * 4ull, priv->ql);
     if (!rc) {

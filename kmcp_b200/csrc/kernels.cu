@@ -624,8 +624,9 @@ __device__ __forceinline__ LocT loc_of(uint64_t code, uint32_t h, const FastMod 
     return (LocT)mod32_dev(v, fm);
 }
 
-// the row indices as a kernel of its own (u32, numSigs < 2^32-1): locs[slot*H + h].  Development alternative to the in-kernel
-// derivation (KMCPG_DEV builds, KMCPG_PROBE_LOCS=buffer), and the device side of the arithmetic test hook.
+// the row indices as a kernel of its own (u32, numSigs < 2^32-1): locs[slot*H + h].  It runs on the query-preparation stream beside
+// the probe of the block before, so the probe kernel itself stays a pure load + count loop (deriving the indices inside the probe
+// costs it 6 % of its bandwidth, profiles/README.md round 2); blocks with numSigs >= 2^32-1 derive them in the kernel.
 template <int H>
 __global__ void __launch_bounds__(256) locs_kernel(const uint64_t *__restrict__ codes, uint64_t n, FastMod fm, uint32_t *__restrict__ locs) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -662,6 +663,40 @@ cudaError_t launch_locs(const uint64_t *codes, uint64_t n, int h, FastMod fm, ui
     }
     return cudaGetLastError();
 }
+// sketch databases: the code regions are mostly empty (FracMinHash keeps ~2/scale of the positions), so walk the
+// queries instead of the slots: one warp per query, only its n_eff codes
+template <int H>
+__global__ void __launch_bounds__(256) locs_query_kernel(const uint64_t *__restrict__ codes, const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ n_eff,
+                                                         uint32_t nq, int paired, FastMod fm, uint32_t *__restrict__ locs) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = warp; q < nq; q += n_warps) {
+        const uint32_t n = n_eff[q];
+        const uint64_t base = slot_off[paired ? 2 * q : q];
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint64_t code = codes[base + i];
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)H; j++) locs[(base + i) * H + j] = loc_of<H, uint32_t>(code, j, fm);
+        }
+    }
+}
+
+cudaError_t launch_locs_by_query(const uint64_t *codes, const uint64_t *slot_off, const uint32_t *n_eff, uint32_t nq, int paired, int h, FastMod fm,
+                                 uint32_t *locs, cudaStream_t st) {
+    if (!nq) return cudaSuccess;
+    uint32_t blocks = (nq + 7) / 8;
+    if (blocks > 148u * 32u) blocks = 148u * 32u;
+    switch (h) {
+        case 1: locs_query_kernel<1><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        case 2: locs_query_kernel<2><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        case 3: locs_query_kernel<3><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        case 4: locs_query_kernel<4><<<blocks, 256, 0, st>>>(codes, slot_off, n_eff, nq, paired, fm, locs); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_locs64(const uint64_t *codes, uint64_t n, int h, FastMod fm, uint64_t *locs, cudaStream_t st) {
     if (!n) return cudaSuccess;
     uint64_t blocks64 = (n + 255) / 256;
@@ -1218,25 +1253,26 @@ static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStre
     // the development variants (documented in profiles/config_sweeps_r01.md) exist only for the 8-plane kernels
     const ProbeTune t = probe_tune();
     if constexpr (PH == 0) {
-        if (a.locs) {                                       // KMCPG_PROBE_LOCS=buffer: row indices precomputed by locs_kernel
-            if constexpr (H == 1) return launch_probe_k<H, PH, 2, 2, 4, uint32_t, 0>(a, blocks, st);
-            else return launch_probe_k<H, PH, 1, 2, 2, uint32_t, 0>(a, blocks, st);
+        if (!a.locs) {                                      // KMCPG_PROBE_LOCS=kernel: row indices derived in the probe kernel
+            if constexpr (H == 1) return launch_probe_k<H, PH, 2, 2, 4, uint32_t, 1>(a, blocks, st);
+            else return launch_probe_k<H, PH, 1, 2, 2, uint32_t, 1>(a, blocks, st);
         }
         if constexpr (H == 1) {
-            if (t.var == 0) return launch_probe_k<H, PH, 0, 2, 4, uint32_t>(a, blocks, st);
-            if (t.var == 1) return t.minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t>(a, blocks, st);
+            if (t.var == 0) return launch_probe_k<H, PH, 0, 2, 4, uint32_t, 0>(a, blocks, st);
+            if (t.var == 1) return t.minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t, 0>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t, 0>(a, blocks, st);
         } else {
-            if (t.w_h == 4) return t.minb_h >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t>(a, blocks, st);
-            if (t.var_h == 2) return launch_probe_k<H, PH, 2, 2, 2, uint32_t>(a, blocks, st);
-            if (t.minb_h >= 3) return launch_probe_k<H, PH, 1, 3, 2, uint32_t>(a, blocks, st);
+            if (t.w_h == 4) return t.minb_h >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t, 0>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t, 0>(a, blocks, st);
+            if (t.var_h == 2) return launch_probe_k<H, PH, 2, 2, 2, uint32_t, 0>(a, blocks, st);
+            if (t.minb_h >= 3) return launch_probe_k<H, PH, 1, 3, 2, uint32_t, 0>(a, blocks, st);
         }
     }
 #endif
+    if (!a.locs) return cudaErrorInvalidValue;              // 32-bit row indices come from launch_locs (the in-kernel form is a KMCPG_DEV variant)
     if constexpr (H == 1) {
-        if constexpr (PH >= 24) return launch_probe_k<H, PH, 2, 1, 4, uint32_t>(a, blocks, st);      // 128 KB of counter planes per CTA
-        else return launch_probe_k<H, PH, 2, 2, 4, uint32_t>(a, blocks, st);               // shipped: double-buffered 16-byte slabs, 2 CTAs/SM
+        if constexpr (PH >= 24) return launch_probe_k<H, PH, 2, 1, 4, uint32_t, 0>(a, blocks, st);      // 128 KB of counter planes per CTA
+        else return launch_probe_k<H, PH, 2, 2, 4, uint32_t, 0>(a, blocks, st);               // shipped: double-buffered 16-byte slabs, 2 CTAs/SM
     } else {
-        return launch_probe_k<H, PH, 1, 2, 2, uint32_t>(a, blocks, st);                    // shipped for h>1: 8-byte slabs, index prefetch, 2 CTAs/SM
+        return launch_probe_k<H, PH, 1, 2, 2, uint32_t, 0>(a, blocks, st);                    // shipped for h>1: 8-byte slabs, index prefetch, 2 CTAs/SM
     }
 }
 

@@ -96,7 +96,7 @@ struct ProbeArgs {
     int num_hashes;
     const uint64_t *codes;      // k-mer codes of every query at slot_off[its first sequence]; the kernel derives the row indices itself:
     FastMod fm;                 // hashValues (H:125-141) + code % numSigs (fastdiv.Mod, U:6811), numSigs up to 2^64-1
-    const uint32_t *locs;       // KMCPG_DEV builds only: [slot][h] precomputed by launch_locs (NULL: derived in the kernel)
+    const uint32_t *locs;       // [slot][h] row indices from launch_locs (blocks with numSigs < 2^32-1; wider blocks derive them in the kernel)
     const uint64_t *slot_off;   // per sequence
     const uint32_t *n_eff;      // per query
     const uint32_t *thresh;     // per query
@@ -111,8 +111,11 @@ struct ProbeArgs {
     int long_mode;              // set by launch_probe: one CTA per (query, chunk) for few long queries
 };
 cudaError_t launch_probe(const ProbeArgs &a, int sm_count, cudaStream_t st);
-// the row indices alone, locs[slot*H + h] (arithmetic test hook; 32-bit form also the KMCPG_DEV alternative to the in-kernel derivation)
+// the row indices of one block, locs[slot*H + h] (hashValues H:125-141 + fastdiv.Mod U:6811); the 64-bit form is the arithmetic test hook
 cudaError_t launch_locs(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint32_t *locs, cudaStream_t st);
+// same, walking the queries (sketch databases leave most slots empty)
+cudaError_t launch_locs_by_query(const uint64_t *codes, const uint64_t *slot_off, const uint32_t *n_eff, uint32_t n_queries, int paired,
+                                 int num_hashes, FastMod fm, uint32_t *locs, cudaStream_t st);
 cudaError_t launch_locs64(const uint64_t *codes, uint64_t n_slots, int num_hashes, FastMod fm, uint64_t *locs, cudaStream_t st);
 
 // ---- small utilities ------------------------------------------------------------------------------------

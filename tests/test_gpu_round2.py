@@ -265,3 +265,49 @@ def test_two_host_threads_share_one_context(gpu_ctx, oracle, mid_db):
         assert np.array_equal(got.match_off, exp.hit_off)
         for f in ("query", "target", "count", "fpr", "qcov", "tcov", "jacc"):
             assert np.array_equal(got.matches[f], exp.hits[f]), f
+
+
+# ---------------------------------------------------------------------------------------------------- reference-held golden
+G2_ROWS = """NC_003197.2-64416/1	150	130	7.4626e-15	1	GCF_000006945.2	9	10	4857450	21	90	0.6923	0.0002	0.0002	1
+NC_003197.2-64414/1	150	130	7.4626e-15	1	GCF_000006945.2	6	10	4857450	21	130	1.0000	0.0003	0.0003	2
+NC_003197.2-64412/1	150	130	7.4626e-15	1	GCF_000006945.2	6	10	4857450	21	121	0.9308	0.0002	0.0002	3
+NC_003197.2-64410/1	150	130	7.4626e-15	1	GCF_000006945.2	1	10	4857450	21	101	0.7769	0.0002	0.0002	4
+NC_003197.2-64408/1	150	130	7.8754e-15	1	GCF_000006945.2	9	10	4857450	21	83	0.6385	0.0002	0.0002	5
+NC_003197.2-64406/1	150	130	7.4626e-15	1	GCF_000006945.2	2	10	4857450	21	103	0.7923	0.0002	0.0002	6
+NC_003197.2-64404/1	150	130	7.4671e-15	1	GCF_000006945.2	5	10	4857450	21	86	0.6615	0.0002	0.0002	7
+NC_003197.2-64402/1	150	130	7.5574e-15	1	GCF_000006945.2	3	10	4857450	21	84	0.6462	0.0002	0.0002	8
+NC_003197.2-64400/1	150	130	7.4626e-15	1	GCF_000006945.2	1	10	4857450	21	89	0.6846	0.0002	0.0002	9"""
+
+
+def test_demo_profiling_golden_through_the_cuda_path(tmp_path):
+    """The reference's own demo: `kmcp compute -k 21 -n 10 -l 150 -B plasmid -N ...` + `kmcp index -f 0.3 -n 1` (block
+    size 16) over the 15 genomes of demo-profiling/refs, then `kmcp search` of the mock reads — here through kmcp-gpu index +
+    kmcp-gpu search, i.e. the device builder and the device search path.  The first nine matched rows must be the rows the
+    reference publishes (docs/tutorial/profiling/index.md:203-211), all 15 columns; the whole TSV of the 40,000-read subset must
+    be the file the pinned oracle produced (tests/golden/make_demo_fixture.py; the oracle reproduces 308,839 / 349,084 matched
+    on the full read set, which is too large to ship)."""
+    import glob
+    import gzip
+    import json
+    import subprocess
+    demo = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demo")
+    refs = sorted(glob.glob(os.path.join(demo, "refs", "*.fa.gz")))
+    assert len(refs) == 15
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmcp_b200", "kmcp-gpu")
+    db = str(tmp_path / "refs-k21-n10.kmcp")
+    p = subprocess.run([exe, "index", "-q", "-O", db, "-k", "21", "-n", "10", "-l", "150", "-B", "plasmid", "-N", r"^([\w\.\_]+\.\d+)", "-f", "0.3", "-b", "16"] + refs,
+                       capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    assert len(glob.glob(db + "/R001/*.uniki")) == 10                      # 150 targets in blocks of 16
+    tsv = str(tmp_path / "mock.tsv")
+    p = subprocess.run([exe, "search", "-d", db, os.path.join(demo, "mock_1.20k.fastq.gz"), os.path.join(demo, "mock_2.20k.fastq.gz"), "-o", tsv], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    got = open(tsv).read()
+    rows = [ln for ln in got.splitlines() if not ln.startswith("#")]
+    assert rows[:9] == G2_ROWS.splitlines()                               # G2, byte for byte
+    exp = gzip.open(os.path.join(demo, "expected.20k.tsv.gz"), "rt").read()
+    assert got == exp
+    summary = json.load(open(os.path.join(demo, "summary.json")))
+    assert len({ln.split("\t")[14] for ln in rows}) == summary["subset"]["matched"] == 36448 and len(rows) == summary["subset"]["rows"]
+    log = p.stderr.decode()
+    assert "(36448/40000) queries matched" in log, log[-400:]
