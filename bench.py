@@ -54,6 +54,10 @@ N_CHUNKS, OVERLAP, K, H, FPR, READ_LEN = 10, 150, 21, 1, 0.3, 150
 BLOCK_SIZE = N_GENOMES * N_CHUNKS
 GENOME_SEED, READ_SEED = 1, 2
 GTDB_SEED, GTDB_READ_SEED, GTDB_H, GTDB_STEPS, GTDB_WARMUP = 3, 4, 3, 3, 1
+# BASELINE configs[4]: HiFi reads (benchmarks/mock-hifi-zymo/README.md:27-31: min 45, median 8.3 kb, mean 9.3 kb, max 45.8 kb), 0.5 % errors
+C5_SEED, C5_READS, C5_STEPS, C5_WARMUP = 5, (2_000 if SCALE == "full" else 300), 2, 1
+# BASELINE configs[2]: FracMinHash (scale 1000, k=21, h=3, fpr 0.001) genome-vs-genome search, 1,000 assemblies, one GPU
+C3_GENOMES, C3_GL, C3_QUERIES = (1000, 4_000_000, 250) if SCALE == "full" else (60, 400_000, 30)
 METRIC = "reads/sec (kmcp search, 150bp)"
 
 
@@ -251,6 +255,38 @@ def run_reference(args, rank, world, stage=stage_in_helper_process):
                          "sample": "%d reads per step against %d block(s), restated reference algorithm (oracle algo=1: 64-row buffer, byte transpose, "
                                    "positional popcount), OpenMP all threads" % (step_reads, world)},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def _splitmix64(x):
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def hifi_batch(seed, step, n_reads, gseed, n_genomes, genome_len):
+    """one packed batch [offsets | bases] of HiFi-shaped reads sampled from the seeded genomes (the generator of synth.cu, in numpy):
+    log-normal lengths (median 8.3 kb, sigma 0.5, clipped to 45 .. 45,000 and to the genome), 0.5 % substitutions, random strand"""
+    rng = np.random.default_rng(seed * 1_000_003 + step)
+    lens = np.clip(rng.lognormal(np.log(8348.0), 0.5, n_reads), 45, min(45_000, genome_len)).astype(np.int64)
+    off = np.zeros(n_reads + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens).astype(np.uint64)
+    seq = np.empty(int(off[-1]), dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for i in range(n_reads):
+        g, ln = int(rng.integers(0, n_genomes)), int(lens[i])
+        pos = int(rng.integers(0, genome_len - ln + 1))
+        with np.errstate(over="ignore"):
+            gkey = _splitmix64(np.array([(gseed * 0x100000001B3 + g) & 0xFFFFFFFFFFFFFFFF], dtype=np.uint64))[0]
+            p = np.arange(pos, pos + ln, dtype=np.uint64)
+            b = ((_splitmix64(gkey + (p >> np.uint64(5))) >> (np.uint64(2) * (p & np.uint64(31)))) & np.uint64(3)).astype(np.uint8)
+        sub = rng.random(ln) < 0.005
+        b[sub] = (b[sub] + rng.integers(1, 4, int(sub.sum())).astype(np.uint8)) & 3
+        if rng.integers(0, 2):
+            b = (3 - b)[::-1]
+        seq[int(off[i]):int(off[i + 1])] = acgt[b]
+    return off, seq
 
 
 def pack_batches(torch, ctx, seed, first_read, n_steps, n_reads, gseed, n_genomes, genome_len, off_np):
@@ -481,9 +517,12 @@ def main():
         sh.close()
 
     # ---------------- GTDB-scale block: fixed index sharded over the ranks, fixed reads, digest of the merged hit list ----------------
-    gtdb = None
+    gtdb = c5 = c3 = None
     if not args.no_gtdb:
         gtdb = gtdb_block(torch, dist, api, multigpu, ctx, stream, dev, rank, world, run_id, barrier, max_over_ranks, gather_objects)
+        c5 = c5_block(torch, dist, api, multigpu, ctx, stream, dev, rank, world, run_id, barrier, max_over_ranks, gather_objects)      # against the same sharded index
+        if world == 1:
+            c3 = c3_block(torch, api, ctx)
 
     api.host_free(h_off_ptr)
     if rank == 0:
@@ -520,7 +559,7 @@ def main():
             "stage_ms_per_step": {"hash (own stream, beside the probes)": sum(o.ms_hash for o in outs) / args.steps,
                                   "probe": probe_ms / args.steps, "call_wall": sum(o.ms_total for o in outs) / args.steps},
             "hit_list_digest": ("%016x" % (sum(d for _n, d in digests) & (2**64 - 1))) if digests else None,
-            "gtdb_scale": gtdb,
+            "gtdb_scale": gtdb, "c5_hifi": c5, "c3_fracminhash": c3,
         }
         print(json.dumps(line))
     ctx.close()
@@ -588,6 +627,111 @@ def gtdb_block(torch, dist, api, multigpu, ctx, stream, dev, rank, world, run_id
         "hit_list_digest": "%016x" % (sum(d for _c, d in digests) & (2**64 - 1)),
         "digest_note": "sum over the timed steps of kmcpg_hits_digest of the merged (query, target, count) list in (query, target) order: must be equal at every N",
         "per_rank": per_rank,
+    }
+
+
+def c5_block(torch, dist, api, multigpu, ctx, stream, dev, rank, world, run_id, barrier, max_over_ranks, gather_objects):
+    """BASELINE.json configs[4]: HiFi-shaped reads (≈ 9,300 k-mers each → sort + unique, U:874-908) against the GTDB-scale index that
+    gtdb_block left sharded over the ranks; the same reads at every N (strong scaling)"""
+    info = ctx.db_info()
+    steps = C5_WARMUP + C5_STEPS
+    batches, offs = [], []
+    if rank == 0:
+        for s in range(steps):
+            off, seq = hifi_batch(C5_SEED, s, C5_READS, GTDB_SEED, GTDB_GENOMES, GTDB_GL)
+            offs.append(off)
+            batches.append(np.concatenate([off.view(np.uint8), seq]))
+        sizes = [int(b.size) for b in batches]
+    else:
+        sizes = None
+    if world > 1:
+        box = [sizes]
+        dist.broadcast_object_list(box, src=0)
+        sizes = box[0]
+    bb = max(sizes)
+    d_batches = None
+    if rank == 0:
+        d_batches = torch.zeros(steps * bb, dtype=torch.uint8, device="cuda")
+        for s, b in enumerate(batches):
+            d_batches[s * bb:s * bb + b.size].copy_(torch.from_numpy(b))
+        torch.cuda.synchronize()
+    sh = multigpu.ShardedSearch(ctx, rank, world, C5_READS, bb, hit_cap=max(1 << 20, 64 * C5_READS), name=run_id + "h", device=dev, dist=dist, params=ctx.default_params())
+    digests = []
+
+    def feed(first):
+        return lambda s: (d_batches[(first + s) * bb:(first + s + 1) * bb], False)
+
+    def consume(s, lists, meta):
+        merged = multigpu.merge_lists(lists, 0, C5_READS)
+        digests.append((len(merged), multigpu.hits_digest(merged)))
+
+    with torch.cuda.stream(stream):
+        sh.run(C5_WARMUP, feed(0), consume)              # offsets differ from step to step: the library fetches them from the device
+        digests.clear()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        outs = sh.run(C5_STEPS, feed(C5_WARMUP), consume)
+        ev1.record(stream)
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+    sh.close()
+    mine = {"rank": rank, "probe_ms": sum(o.ms_probe for o in outs), "probe_bytes": sum(o.probe_row_bytes for o in outs), "prep_ms": sum(o.ms_hash for o in outs),
+            "probe_launches": sum(o.probe_launches for o in outs), "sum_row_bytes": int(info.sum_row_bytes)}
+    per_rank = gather_objects(mine)
+    if rank != 0:
+        return None
+    peak, _src = measured_peak()
+    for r in per_rank:
+        r["probe_GBps"] = (r["probe_bytes"] / 1e9) / (r["probe_ms"] / 1e3) if r["probe_ms"] > 0 else 0.0
+        r["probe_frac"] = r["probe_GBps"] / peak
+    n_total = C5_READS * C5_STEPS
+    bases = int(sum(int(o[-1]) for o in offs[C5_WARMUP:]))
+    total_bytes = sum(r["probe_bytes"] for r in per_rank)
+    return {
+        "workload": "HiFi-shaped reads (log-normal, median 8.3 kb, 45 .. 45,000 bp, 0.5 %% substitutions; mean %.0f bp here) against the GTDB-scale index above, "
+                    "%d reads per step, %d timed steps" % (bases / n_total, C5_READS, C5_STEPS),
+        "scaling": "strong", "n_gpus": world, "job_reads_per_s": n_total / (ms / 1e3), "job_Mbases_per_s": bases / (ms / 1e3) / 1e6, "ms_per_step": ms / C5_STEPS,
+        "algorithmic_bytes_per_read": int(total_bytes / n_total), "aggregate_probe_GBps_over_wall": (total_bytes / 1e9) / (ms / 1e3),
+        "frac_of_roofline": (total_bytes / 1e9) / (ms / 1e3) / (peak * world),
+        "hits_per_step": int(sum(c for c, _d in digests) / max(1, len(digests))), "hit_list_digest": "%016x" % (sum(d for _c, d in digests) & (2**64 - 1)),
+        "per_rank": per_rank,
+    }
+
+
+def c3_block(torch, api, ctx):
+    """BASELINE.json configs[2]: FracMinHash genome-vs-genome sketch search on one GPU — 1,000 seeded 4 Mb assemblies (scale 1000, k=21, h=3,
+    fpr 0.001: the tutorial's setting), whole genomes as -g queries.  The index (tens of MB) lives in L2: the path is bound by kernel 1
+    (hash every base once), so the figure is bases/s against "genome bytes read once"."""
+    t0 = time.perf_counter()
+    ctx.build_synth_db(GENOME_SEED, C3_GENOMES, C3_GL, k=K, n_chunks=1, overlap=0, num_hashes=3, fpr=0.001, block_size=0, scale=1000)
+    build_s = time.perf_counter() - t0
+    info = ctx.db_info()
+    nq = C3_QUERIES
+    d = torch.empty(nq * C3_GL, dtype=torch.uint8, device="cuda")
+    ctx.synth_genomes(GENOME_SEED, 0, nq, C3_GL, d.data_ptr())
+    off = np.arange(nq + 1, dtype=np.uint64) * np.uint64(C3_GL)
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    p = ctx.default_params(min_query_cov=0.5)
+    outs = []
+    for rep in range(4):
+        t0 = time.perf_counter()
+        o = ctx.wait(ctx.submit(d.data_ptr(), d_off.data_ptr(), nq, p, device=True, host_off_ptr=off.ctypes.data))
+        if rep:
+            outs.append((time.perf_counter() - t0, o))
+    dt = min(t for t, _o in outs)
+    o = outs[-1][1]
+    # every query genome is in the database: it must find itself with all of its k-mers
+    self_hits = int(np.sum(o.hits["count"] == o.n_kmers[o.hits["query"]]))
+    peak, _src = measured_peak()
+    return {
+        "workload": "FracMinHash sketch search: %d seeded %.1f Mb assemblies (scale 1000, k=%d, h=3, fpr 0.001, %d blocks, index %.1f MB), %d whole genomes as queries, device resident"
+                    % (C3_GENOMES, C3_GL / 1e6, K, info.n_blocks, info.resident_bytes / 1e6, nq),
+        "genomes_per_s": nq / dt, "Gbases_per_s": nq * C3_GL / dt / 1e9, "call_ms": dt * 1e3, "db_build_s": round(build_s, 2),
+        "sketch_kmers_per_query": int(np.mean(o.n_kmers)), "prep_ms": o.ms_hash, "probe_ms": o.ms_probe, "hits": int(len(o.hits)), "queries_matching_themselves_fully": self_hits,
+        "roofline": {"bound": "hbm (genome bytes read once; the probe works out of L2)", "achieved_GBps": nq * C3_GL / dt / 1e9, "peak_GBps": peak,
+                     "frac": nq * C3_GL / dt / 1e9 / peak, "note": "kernel 1 is ALU / shared-memory bound, not bandwidth bound: one base per k-mer position and ~40 integer operations for it"},
     }
 
 

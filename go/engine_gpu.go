@@ -59,35 +59,70 @@ func newGPUEngine(opt SearchOptions, device int, dbPath string) (*gpuEngine, err
 	return e, nil
 }
 
-// loop batches queries from InCh (≈1 M reads or 256 MB), calls the device once per batch and emits
-// QueryResults; Query/Seq objects go back to poolQuery/poolSeq exactly as U:337-341 does.
+// One batch under construction or in flight.  seq and off live in PINNED C memory (kmcpg_host_alloc): kmcpg_search_submit keeps
+// reading them until kmcpg_search_wait returns, and cgo forbids C code to hold on to Go memory after a call has returned.
+type gpuBatch struct {
+	queries []*Query
+	seq     unsafe.Pointer // maxB bytes
+	off     unsafe.Pointer // (2*maxQ+1) uint64
+	nSeq    int
+	nBytes  int
+	job     *C.kmcpg_job
+}
+
+const maxQ, maxB = 1 << 20, 256 << 20
+
+func newGpuBatch() *gpuBatch {
+	b := &gpuBatch{queries: make([]*Query, 0, maxQ)}
+	C.kmcpg_host_alloc(&b.seq, C.size_t(maxB+1<<16))
+	C.kmcpg_host_alloc(&b.off, C.size_t(8*(2*maxQ+1)))
+	return b
+}
+
+func (b *gpuBatch) add(s []byte) {
+	copy(unsafe.Slice((*byte)(unsafe.Add(b.seq, b.nBytes)), len(s)), s)
+	b.nBytes += len(s)
+	b.nSeq++
+	unsafe.Slice((*C.uint64_t)(b.off), 2*maxQ+1)[b.nSeq] = C.uint64_t(b.nBytes)
+}
+
+// loop batches queries from InCh (≈1 M reads or 256 MB) and keeps TWO batches submitted (kmcpg_search_submit): while the device
+// works on batch i, batch i+1 is already queued behind it — the executor starts its first part the moment the last part of batch i
+// leaves the compute stream — and this goroutine turns the hits of batch i-1 into QueryResults.  Query/Seq objects go back to
+// poolQuery/poolSeq exactly as U:337-341 does.
 func (e *gpuEngine) loop() {
 	defer e.wg.Done()
-	const maxQ, maxB = 1 << 20, 256 << 20
-	batch := make([]*Query, 0, maxQ)
-	var seq []byte        // Go memory is fine: the library does not retain it after the call returns
-	off := make([]C.uint64_t, 1, maxQ*2+1)
-	flush := func() {
-		if len(batch) == 0 {
-			return
-		}
+	free := []*gpuBatch{newGpuBatch(), newGpuBatch(), newGpuBatch()}
+	var inflight []*gpuBatch
+	cur := free[0]
+	free = free[1:]
+	submit := func(b *gpuBatch) {
 		var p C.kmcpg_search_params
 		C.kmcpg_default_params(&p)
 		p.min_query_len, p.min_matched = C.int32_t(e.Options.MinQLen), C.int32_t(e.Options.MinMatched)
 		p.dedup_threshold, p.min_query_cov = C.int32_t(e.Options.DeduplicateThreshold), C.double(e.Options.MinQueryCov)
-		if batch[0].Seq2 != nil {
+		if b.queries[0].Seq2 != nil {
 			p.paired = 1
 		}
-		var hits C.kmcpg_hits
-		rc := C.kmcpg_search_batch(e.ctx, &p, (*C.uint8_t)(unsafe.Pointer(&seq[0])), &off[0], C.uint32_t(len(off)-1), &hits)
-		if rc != 0 {
+		var bt C.kmcpg_batch
+		bt.seq, bt.off, bt.n_seqs = (*C.uint8_t)(b.seq), (*C.uint64_t)(b.off), C.uint32_t(b.nSeq)
+		if rc := C.kmcpg_search_submit(e.ctx, &p, &bt, &b.job); rc != 0 {
 			checkError(fmt.Errorf("kmcp-gpu: %s", C.GoString(C.kmcpg_last_error(e.ctx)))) // log + os.Exit(-1), util-cli.go:35-40
 		}
-		nk := unsafe.Slice((*int32)(unsafe.Pointer(hits.n_kmers)), len(batch))
-		ql := unsafe.Slice((*int32)(unsafe.Pointer(hits.query_len)), len(batch))
+		inflight = append(inflight, b)
+	}
+	finish := func() { // the oldest batch in flight
+		b := inflight[0]
+		inflight = inflight[1:]
+		var hits C.kmcpg_hits
+		if rc := C.kmcpg_search_wait(b.job, &hits); rc != 0 {
+			checkError(fmt.Errorf("kmcp-gpu: %s", C.GoString(C.kmcpg_last_error(e.ctx))))
+		}
+		nk := unsafe.Slice((*int32)(unsafe.Pointer(hits.n_kmers)), len(b.queries))
+		ql := unsafe.Slice((*int32)(unsafe.Pointer(hits.query_len)), len(b.queries))
 		hs := unsafe.Slice((*C.kmcpg_hit)(unsafe.Pointer(hits.hits)), int(hits.n_hits))
 		j := 0
-		for q, query := range batch {
+		for q, query := range b.queries {
 			r := poolQueryResult.Get().(*QueryResult)
 			r.QueryIdx, r.QueryID, r.QueryLen = query.Idx, query.ID, int(ql[q])
 			r.K, r.NumKmers, r.Matches = int(e.info.ks[0]), int(nk[q]), nil
@@ -110,21 +145,34 @@ func (e *gpuEngine) loop() {
 			poolQuery.Put(query)
 		}
 		C.kmcpg_free_hits(&hits)
-		batch, seq, off = batch[:0], seq[:0], off[:1]
+		b.queries, b.nSeq, b.nBytes = b.queries[:0], 0, 0
+		free = append(free, b)
+	}
+	flush := func() {
+		if len(cur.queries) == 0 {
+			return
+		}
+		submit(cur)
+		if len(inflight) == 2 { // two on the device: digest the older one while the newer one runs
+			finish()
+		}
+		cur = free[0]
+		free = free[1:]
 	}
 	for query := range e.InCh {
-		batch = append(batch, query)
-		seq = append(seq, query.Seq.Seq...)
-		off = append(off, C.uint64_t(len(seq)))
+		cur.queries = append(cur.queries, query)
+		cur.add(query.Seq.Seq)
 		if query.Seq2 != nil {
-			seq = append(seq, query.Seq2.Seq...)
-			off = append(off, C.uint64_t(len(seq)))
+			cur.add(query.Seq2.Seq)
 		}
-		if len(batch) == maxQ || len(seq) >= maxB {
+		if len(cur.queries) == maxQ || cur.nBytes >= maxB {
 			flush()
 		}
 	}
 	flush()
+	for len(inflight) > 0 {
+		finish()
+	}
 	close(e.OutCh)
 }
 

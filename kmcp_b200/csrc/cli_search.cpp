@@ -29,6 +29,7 @@
 #include <thread>
 #include <vector>
 
+#include "nvtx_ranges.h"
 #include "../../include/kmcp_gpu.h"
 #include "fastx_reader.h"
 #if defined(__x86_64__)
@@ -648,6 +649,7 @@ int run(int argc, char **argv) {
         rc.batch_reads = o.batch_reads; rc.batch_bytes = o.batch_bytes; rc.kmax = kmax;
         reader = std::thread([&, rc] {
             read_batches(rc, [&](Batch *bt) {
+                kmcpg::NvtxRange nvtx("kmcp-gpu:reader hands over a batch");
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return in_q.size() < 2; });
                 in_q.push_back(bt);
@@ -823,6 +825,7 @@ int run(int argc, char **argv) {
                 job = out_q.front(); out_q.pop_front();
                 cv.notify_all();
             }
+            kmcpg::NvtxRange nvtx("kmcp-gpu:writer (TSV formatting, gzip)");
             const Batch &bt = *job->batch;
             const uint32_t nq = (uint32_t)bt.n_ids();
             std::vector<std::string> text(FT);

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "ctx_internal.h"
+#include "nvtx_ranges.h"
 
 using namespace kmcpg;
 
@@ -61,13 +62,19 @@ void layout_block(DeviceBlock &b, const BlockMeta &m, uint32_t col0, uint32_t n_
     b.fm = make_fastmod(m.num_sigs);
 }
 
+int64_t widest_shard_row_bytes(const std::vector<ShardPiece> &pieces, int world) {
+    std::vector<int64_t> rb((size_t)std::max(1, world), 0);
+    for (const ShardPiece &pc : pieces) if (pc.shard >= 0 && pc.shard < (int)rb.size()) rb[pc.shard] += (pc.n_cols + 7) / 8;
+    return *std::max_element(rb.begin(), rb.end());
+}
+
 void free_db(kmcpg_ctx *ctx) {
     for (auto &b : ctx->blocks) if (b.d_rows) cudaFree(b.d_rows);
     ctx->blocks.clear();
     ctx->resident_of.clear();
     ctx->target_sizes.clear();
     ctx->has_db = false;
-    ctx->sum_row_bytes = ctx->resident_bytes = ctx->disk_bytes = 0;
+    ctx->sum_row_bytes = ctx->resident_bytes = ctx->disk_bytes = ctx->part_row_bytes = 0;
 }
 
 void WorkSet::release() {
@@ -270,6 +277,7 @@ int kmcpg_close(kmcpg_ctx *ctx) {
 
 int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
     if (!ctx || !dir) return KMCPG_EINVAL;
+    NvtxRange nvtx("kmcpg:open_db (pread, H2D, re-pitch)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     executor_drain(ctx);
     CU(cudaSetDevice(ctx->device));
@@ -285,6 +293,7 @@ int kmcpg_open_db(kmcpg_ctx *ctx, const char *dir, const kmcpg_db_opts *opts) {
     std::vector<ShardPiece> pieces;
     std::vector<uint64_t> load;
     plan_pieces(m, world, pieces, load);
+    ctx->part_row_bytes = widest_shard_row_bytes(pieces, world);
     if (opts && opts->max_resident_bytes > 0 && (int64_t)load[rank] > opts->max_resident_bytes)
         return fail(ctx, KMCPG_ENOMEM, "resident blocks exceed max_resident_bytes");
     ctx->resident_of.assign(m.blocks.size(), -1);

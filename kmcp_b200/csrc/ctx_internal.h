@@ -127,6 +127,7 @@ struct kmcpg_ctx {
     std::vector<int> resident_of;     // meta block index -> index in `blocks` or -1
     std::vector<double> target_sizes; // Sizes[t] of every target as float64 (U:1393-1396 sizesFloat)
     int64_t sum_row_bytes = 0, resident_bytes = 0, disk_bytes = 0;
+    int64_t part_row_bytes = 0;       // Σ row bytes of the WIDEST shard of the plan this context belongs to (part sizing, executor.cu)
     kmcpg::WorkSet ws[2];
     kmcpg::DevBuf d_tmp, d_dense, d_scal, d_genome;
     kmcpg::HostBuf h_stage, h_small;
@@ -144,6 +145,7 @@ int fail(kmcpg_ctx *c, int code, const std::string &msg);
 uint32_t pitch_for(uint32_t row_bytes);
 void layout_block(DeviceBlock &b, const BlockMeta &m, uint32_t col0 = 0, uint32_t n_cols = 0);
 void plan_pieces(const DbMeta &m, int world, std::vector<ShardPiece> &pieces, std::vector<uint64_t> &load);
+int64_t widest_shard_row_bytes(const std::vector<ShardPiece> &pieces, int world);
 void free_db(kmcpg_ctx *ctx);
 void executor_drain(kmcpg_ctx *ctx);   // waits until no search job is in flight (call with ctx->mu held)
 void executor_stop(kmcpg_ctx *ctx);

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.h"
+#include "nvtx_ranges.h"
 
 extern "C" const double *kmcpg_internal_target_sizes(const kmcpg_ctx *ctx);
 struct kmcpg_stage;
@@ -196,6 +197,7 @@ struct Round {
 // the caller) receives the number of matches of every query that has any.
 size_t post_filter(const kmcpg_engine_opts *o, const kmcpg_part &hits, uint64_t h0, uint64_t h1, const uint32_t *cur, uint32_t round_q0,
                    const double *tsize, FprCache *cache, kmcpg_match *dst, uint32_t *count) {
+    NvtxRange nvtx("kmcpg:post-filter (tCov, FPR, sort, top-N)");
     const Less less{o->sort_by};
     const uint32_t q0 = hits.first_query;                              // base of hits[].query inside this device call
     size_t w = 0;
@@ -618,7 +620,7 @@ int engine_search_impl(kmcpg_ctx *const *ctxs, int n_ctx, const kmcpg_engine_opt
                 std::vector<uint32_t> cuts{0};
                 {
                     const uint64_t bytes = round_seqs ? bo[round_seqs] - bo[0] : 0;
-                    const int n_pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, bytes / (24ull << 20)));
+                    const int n_pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(4, bytes / (64ull << 20)));
                     for (int j = 1; j < n_pieces; j++) {
                         const uint64_t want = bo[0] + bytes * (uint64_t)j / (uint64_t)n_pieces;
                         uint32_t lo = cuts.back() / step, hi = ln_total;       // first query whose first byte is at or after `want`
@@ -791,11 +793,20 @@ int replicas_impl(int n_rep, const ReplicaSearch &search, bool paired, const uin
         memcpy(out->n_kmers + a, x.n_kmers, (size_t)n * 4);
         memcpy(out->k_used + a, x.k_used, (size_t)n * 4);
         for (uint32_t i = 0; i < n; i++) out->match_off[(size_t)a + i + 1] = mbase[r] + x.match_off[i + 1];
-        kmcpg_match *dst = out->matches + mbase[r];
-        for (uint64_t i = 0; i < x.n_matches; i++) { dst[i] = x.matches[i]; dst[i].query += a; }
     };
-    const int T = std::min(n_rep, pool().size() + 1);               // the pool runs at most size()+1 tasks of a job
-    std::function<void(int)> lane = [&](int t) { for (int r = t; r < n_rep; r += T) copy(r); };
+    // the match arrays are the bulk (48 B per match): every replica's array is moved by several threads
+    const int T = pool().size() + 1;                                // the pool runs at most size()+1 tasks of a job
+    std::function<void(int)> lane = [&](int t) {
+        for (int r = t; r < n_rep; r += T) copy(r);
+        for (int r = 0; r < n_rep; r++) {
+            if (cut[r + 1] == cut[r]) continue;
+            const kmcpg_results &x = res[r];
+            const uint64_t a = x.n_matches * (uint64_t)t / (uint64_t)T, b = x.n_matches * (uint64_t)(t + 1) / (uint64_t)T;
+            kmcpg_match *dst = out->matches + mbase[r];
+            const uint32_t qa = cut[r];
+            for (uint64_t i = a; i < b; i++) { dst[i] = x.matches[i]; dst[i].query += qa; }
+        }
+    };
     pool().parallel(T, lane);
     for (int r = 0; r < n_rep; r++) {
         if (!res[r]._priv) continue;

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ctx_internal.h"
+#include "nvtx_ranges.h"
 
 using namespace kmcpg;
 
@@ -244,6 +245,7 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
 // before it) and the probe launches (compute stream).  host_seq != nullptr → the inputs are staged through the input stream.
 static int enqueue_part(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int k, const SubBatch &sb_in, const uint8_t *host_seq,
                         const uint64_t *host_off, uint64_t host_bytes, cudaEvent_t ready) {
+    NvtxRange nvtx("kmcpg:part enqueue (H2D, query preparation, locs, probe)");
     cudaStream_t st = ctx->st, hs = ctx->hash_st;
 #ifdef KMCPG_DEV
     static const bool one_stream = getenv("KMCPG_HASH_STREAM") && atoi(getenv("KMCPG_HASH_STREAM")) == 0;
@@ -306,6 +308,7 @@ static int grow_hits(kmcpg_ctx *ctx, HitsPriv &res, uint64_t need) {
 
 // stage B: hit count known → sort, pack, results to the host (asynchronously, on the copy stream)
 static int finish_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, HitsPriv &res, Timing &tm) {
+    NvtxRange nvtx("kmcpg:part finish (hit count, hit sort, D2H)");
     cudaStream_t st = ctx->st;
     for (int attempt = 0;; attempt++) {
         CU(cudaEventSynchronize(w.ev_cnt));
@@ -404,6 +407,15 @@ static const uint32_t PART_SEQS = 2u << 20;
 static int cut_parts(kmcpg_ctx *ctx, const uint64_t *off, uint32_t n_seqs, uint32_t step, int k, std::vector<Part> &parts) {
     const uint64_t kk = (uint64_t)k;
     const uint32_t BLK = 4096;
+    // A part should keep the GPU busy for a few milliseconds, or the per-part host round trips (hit count, sort launch, delivery) show:
+    // a context that holds only a narrow share of the rows (a column-range shard of one block, a small sketch database) takes
+    // proportionally more k-mers per part — up to 4x, the work-set buffers grow with it.
+    uint64_t PART_SLOTS = kmcpg::PART_SLOTS;
+    {
+        // (the widest shard of the plan decides, so that all shards of one database cut a batch into the same parts)
+        const uint64_t row_work = (uint64_t)std::max<int64_t>(1, ctx->part_row_bytes > 0 ? ctx->part_row_bytes : ctx->sum_row_bytes) * (uint64_t)std::max(1, ctx->meta.num_hashes);
+        if (row_work < 1250) PART_SLOTS = std::min<uint64_t>(4 * PART_SLOTS, PART_SLOTS * 1250 / row_work);
+    }
     uint32_t a = 0, b = 0;
     uint64_t slots = 0, maxq = 0;
     auto limit = [&]() { return a == 0 ? PART_SLOTS / 4 : PART_SLOTS; };   // a short first part fills the pipeline quickly
@@ -499,7 +511,10 @@ static int deliver_job(kmcpg_ctx *ctx, kmcpg_job *job) {
     for (; job->delivered < job->done.size(); job->delivered++) {
         const PartDone &d = job->done[job->delivered];
         const float ta = now_ms();
-        CU(cudaEventSynchronize(d.ev));
+        {
+            NvtxRange nvtx("kmcpg:part wait for D2H");
+            CU(cudaEventSynchronize(d.ev));
+        }
         ctx->ws[d.ws].busy = false;                  // the newest user of that work set is this part: everything it queued is done
         const float tb = now_ms();
         if (job->cb) {
@@ -508,6 +523,7 @@ static int deliver_job(kmcpg_ctx *ctx, kmcpg_job *job) {
             pt.first_query = d.first_query + res.first_query; pt.n_queries = d.nq;
             pt.n_kmers = (const int32_t *)res.nk.p + d.first_query; pt.query_len = (const int32_t *)res.ql.p + d.first_query;
             pt.hits = (const kmcpg_hit *)res.hits.p + d.hit_dst; pt.n_hits = d.n_hits;
+            NvtxRange nvtx("kmcpg:part callback (host post-filter)");
             job->cb(job->user, &pt);
         }
         if (g_trace) fprintf(stderr, "[trace] job %p part %zu: d2h wait %.2f..%.2f cb ..%.2f (%u q, %llu hits)\n", (void *)job, job->delivered, ta, tb, now_ms(), d.nq, (unsigned long long)d.n_hits);

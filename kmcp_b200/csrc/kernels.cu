@@ -1287,11 +1287,221 @@ static cudaError_t launch_probe_h(const ProbeArgs &a, uint32_t blocks, cudaStrea
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// probe, TMA form (wide rows): the rows travel global → shared memory by cp.async.bulk (the TMA unit's 1-D bulk copy), completion
+// is signalled on mbarriers, the threads read them back with LDS.  A task = (query, slice of up to 1 KB of the row); thread t owns
+// 4 bytes of the slice and 8 bit-sliced counter words.  Sixteen k-mers (x h rows) are in flight per CTA in a shared-memory ring —
+// the memory-level parallelism that the register kernel above buys with 128 registers per thread.  One elected thread issues the
+// copies of k-mer group g+2 while everybody adds up group g.  Short queries only (<= 255 k-mers: 8 counter planes), 32-bit row indices.
+// ------------------------------------------------------------------------------------------------------
+constexpr int BULK_THREADS = 256;
+constexpr int BULK_STAGES = 16;          // k-mers in flight per CTA (two groups of PROBE_ROWS)
+constexpr uint32_t BULK_SLICE = 1024;    // bytes of a row per task, at most
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int H>
+__global__ void __launch_bounds__(BULK_THREADS) probe_bulk_kernel(ProbeArgs a, uint32_t slice, uint32_t n_slices) {
+    extern __shared__ __align__(128) uint8_t bulk_smem[];
+    uint8_t *ring = bulk_smem;                                                     // [BULK_STAGES][H][BULK_SLICE]
+    uint64_t *full = (uint64_t *)(bulk_smem + (size_t)BULK_STAGES * H * BULK_SLICE);   // [BULK_STAGES]
+    uint32_t *sloc = (uint32_t *)(full + BULK_STAGES);                             // [2][PROBE_ROWS * H]: row indices of the two groups ahead
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < BULK_STAGES; s++) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr int NL = PROBE_ROWS * H;
+    const uint64_t total = (uint64_t)a.n_queries * n_slices;
+    uint32_t kglobal = 0;                                                          // k-mers this CTA has pushed through the ring so far (stage = kglobal % STAGES)
+    for (uint64_t task = blockIdx.x; task < total; task += gridDim.x) {
+        const uint32_t q = (uint32_t)(task / n_slices), sl = (uint32_t)(task - (uint64_t)q * n_slices);
+        const uint32_t n = a.n_eff[q];
+        const uint32_t byte0 = sl * slice;
+        const uint32_t bytes = a.pitch - byte0 < slice ? a.pitch - byte0 : slice;  // the pitch is a multiple of 128 and zero padded behind row_bytes
+        const bool lane_ok = (uint32_t)tid * 4 < bytes;
+        uint32_t c[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) c[p] = 0;
+        if (n > 0) {
+            const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
+            const uint8_t *col = a.rows + byte0;
+            const uint32_t groups = (n + PROBE_ROWS - 1) / PROBE_ROWS;
+            // issue the copies of one group of 8 k-mers (indices in sloc[buf]); k0 = ring position of its first k-mer
+            auto issue = [&](uint32_t g, int buf, uint32_t k0) {
+                const uint32_t cnt = n - g * PROBE_ROWS < (uint32_t)PROBE_ROWS ? n - g * PROBE_ROWS : (uint32_t)PROBE_ROWS;
+                for (uint32_t u = 0; u < cnt; u++) {
+                    const uint32_t s = (k0 + u) % BULK_STAGES;
+                    mbar_expect_tx(full + s, (uint32_t)H * bytes);
+#pragma unroll
+                    for (int h = 0; h < H; h++)
+                        bulk_g2s(ring + ((size_t)s * H + h) * BULK_SLICE, col + (uint64_t)sloc[buf * NL + u * H + h] * a.pitch, bytes, full + s);
+                }
+            };
+            auto fetch_locs = [&](uint32_t g, int buf) {                           // by the first 8*H threads
+                if (tid < NL) {
+                    const uint32_t i = g * PROBE_ROWS + (uint32_t)tid / H;
+                    sloc[buf * NL + tid] = i < n ? __ldg(lp + (uint64_t)g * NL + tid) : 0;
+                }
+            };
+            fetch_locs(0, 0);
+            if (groups > 1) fetch_locs(1, 1);
+            __syncthreads();
+            if (tid == 0) {
+                issue(0, 0, kglobal);
+                if (groups > 1) issue(1, 1, kglobal + PROBE_ROWS);
+            }
+            for (uint32_t g = 0; g < groups; g++) {
+                uint32_t r[PROBE_ROWS];
+#pragma unroll
+                for (int u = 0; u < PROBE_ROWS; u++) {
+                    const uint32_t i = g * PROBE_ROWS + u;
+                    r[u] = 0;
+                    if (i < n) {
+                        const uint32_t kk = kglobal + i, s = kk % BULK_STAGES;
+                        mbar_wait(full + s, (kk / BULK_STAGES) & 1u);
+                        if (lane_ok) {
+                            uint32_t v = *(const uint32_t *)(ring + (size_t)s * H * BULK_SLICE + (size_t)tid * 4);
+#pragma unroll
+                            for (int h = 1; h < H; h++) v &= *(const uint32_t *)(ring + ((size_t)s * H + h) * BULK_SLICE + (size_t)tid * 4);      // pand, U:6639-6645
+                            r[u] = v;
+                        }
+                    }
+                }
+                if (g + 2 < groups) fetch_locs(g + 2, (int)(g & 1));               // group g's indices are not needed any more
+                __syncthreads();                                                   // every thread has taken group g out of the ring
+                if (tid == 0 && g + 2 < groups) issue(g + 2, (int)(g & 1), kglobal + (g + 2) * PROBE_ROWS);
+                // Harley–Seal over the 8 rows (one word per thread)
+                {
+                    uint32_t ones = c[0], twos = c[1], fours = c[2];
+                    uint32_t t1a = maj3(ones, r[0], r[1]); ones = xor3(ones, r[0], r[1]);
+                    uint32_t t1b = maj3(ones, r[2], r[3]); ones = xor3(ones, r[2], r[3]);
+                    uint32_t t2a = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
+                    t1a = maj3(ones, r[4], r[5]); ones = xor3(ones, r[4], r[5]);
+                    t1b = maj3(ones, r[6], r[7]); ones = xor3(ones, r[6], r[7]);
+                    uint32_t t2b = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
+                    uint32_t carry = maj3(fours, t2a, t2b); fours = xor3(fours, t2a, t2b);
+                    c[0] = ones; c[1] = twos; c[2] = fours;
+#pragma unroll
+                    for (int p = 3; p < 8; p++) { const uint32_t t = c[p] & carry; c[p] ^= carry; carry = t; }
+                }
+            }
+            kglobal += n;
+            __syncthreads();                                                       // sloc is rewritten by the next task
+        }
+        // ---- threshold on the bit-sliced counters + hit append (as in probe_kernel, one word per thread) ----
+        uint32_t ge = 0;
+        int nhit = 0;
+        if (n > 0 && lane_ok) {
+            const uint32_t Tq = a.thresh[q];
+            if (!(Tq >> 8)) {
+                uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+                for (int p = 7; p >= 0; p--) {
+                    if ((Tq >> p) & 1) eq &= c[p];
+                    else { gt |= eq & c[p]; eq &= ~c[p]; }
+                }
+                ge = gt | eq;
+                // bits of the zero padding behind the last target never count: their rows are zero
+                nhit = __popc(ge);
+            }
+        }
+        int incl = nhit;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot > 0) {
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(a.hit_count, (unsigned long long)tot);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            unsigned long long slot = base + (unsigned long long)(incl - nhit);
+            uint32_t m = ge;
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t t = (byte0 + (uint32_t)tid * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int p = 0; p < 8; p++) cnt |= ((c[p] >> bit) & 1u) << p;
+                if (slot < a.hit_cap) {
+                    a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
+                    a.hit_vals[slot] = cnt;
+                }
+                slot++;
+            }
+        }
+    }
+}
+
+template <int H>
+static cudaError_t launch_probe_bulk_h(const ProbeArgs &a, int sm_count, cudaStream_t st) {
+    const uint32_t n_slices = (a.pitch + BULK_SLICE - 1) / BULK_SLICE;
+    const uint32_t slice = ((a.pitch + n_slices - 1) / n_slices + 127) / 128 * 128;          // equal slices, multiples of 128 bytes
+    const size_t smem = (size_t)BULK_STAGES * H * BULK_SLICE + BULK_STAGES * sizeof(uint64_t) + 2 * PROBE_ROWS * H * sizeof(uint32_t);
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(probe_bulk_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        done = true;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const uint64_t tasks = (uint64_t)a.n_queries * n_slices;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(tasks, (uint64_t)sm_count * per_sm);
+    probe_bulk_kernel<H><<<blocks, BULK_THREADS, smem, st>>>(a, slice, n_slices);
+    return cudaGetLastError();
+}
+
+// true when the TMA form applies: short queries, precomputed 32-bit row indices, rows of at least 512 bytes, no dense-count dump
+static bool probe_bulk_applies(const ProbeArgs &a) {
+    return a.planes == 8 && a.locs && !a.dense_counts && a.row_bytes >= 512 && a.fm.d < 0xFFFFFFFFull && a.pitch % 128 == 0;
+}
+
 cudaError_t launch_probe(const ProbeArgs &a_in, int sm_count, cudaStream_t st) {
     if (!a_in.n_queries) return cudaSuccess;
     ProbeArgs a = a_in;
     const ProbeTune t = probe_tune();
     a.lanes_per_task_override = (uint32_t)t.g;
+#ifdef KMCPG_DEV
+    // KMCPG_PROBE_BULK=1: wide rows through the cp.async.bulk + mbarrier form (A/B against the register kernel, profiles/README.md round 2)
+    static const bool bulk = getenv("KMCPG_PROBE_BULK") && atoi(getenv("KMCPG_PROBE_BULK")) != 0;
+    if (bulk && probe_bulk_applies(a)) {
+        switch (a.num_hashes) {
+            case 1: return launch_probe_bulk_h<1>(a, sm_count, st);
+            case 2: return launch_probe_bulk_h<2>(a, sm_count, st);
+            case 3: return launch_probe_bulk_h<3>(a, sm_count, st);
+            case 4: return launch_probe_bulk_h<4>(a, sm_count, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+#endif
     {   // few long queries leave the lane-per-slab mapping without parallelism: give every (query, chunk) a whole CTA
         const uint32_t slab = a.num_hashes == 1 ? 16 : 8;
         const uint32_t row_units = (a.row_bytes + slab - 1) / slab;

@@ -247,6 +247,7 @@ int kmcpg_build_synth_db(kmcpg_ctx *ctx, const kmcpg_synth_db *spec) {
             std::vector<ShardPiece> pieces;
             std::vector<uint64_t> load;
             plan_pieces(m, world, pieces, load);
+            ctx->part_row_bytes = widest_shard_row_bytes(pieces, world);
             owner.assign(nb, -1);
             for (const ShardPiece &pc : pieces) {
                 if (pc.col0 != 0 || pc.n_cols != (uint32_t)m.blocks[pc.block].n_names)
