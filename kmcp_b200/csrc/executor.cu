@@ -40,7 +40,7 @@ static int ensure_events(kmcpg_ctx *ctx, WorkSet &w) {
         w.probe_ev.push_back(e);
     }
     CU(w.h_cnt.ensure(64));
-    CU(w.counters.ensure(64));
+    CU(w.counters.ensure(64 + ctx->blocks.size() * 8));       // [0] hit count, [1] Σ n_kmers, [2 + b] task counter of block b
     return KMCPG_OK;
 }
 
@@ -206,6 +206,7 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
         if (ctx->blocks.size() > 1) CU(w.locs[1].ensure(locs_bytes));
     }
     CU(cudaMemsetAsync(w.counters.p, 0, 8, st));
+    if (w.planes > 8) CU(cudaMemsetAsync(w.counters.as<unsigned long long>() + 2, 0, ctx->blocks.size() * 8, st));
     size_t bi = 0;
     for (auto &b : ctx->blocks) {
         const BlockMeta &bm = ctx->meta.blocks[b.meta_idx];
@@ -230,6 +231,7 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
         pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = w.nq; pa.paired = p.paired;
         pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
         pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = w.cap; pa.dense_counts = nullptr; pa.planes = w.planes;
+        pa.task_counter = w.counters.as<unsigned long long>() + 2 + bi;        // one counter per block of this part, zeroed below
         CU(launch_probe(pa, ctx->sm_count, st)); ctx->launches++;
         CU(cudaEventRecord(w.probe_ev[bi * 3 + 2], st));
         bi++;

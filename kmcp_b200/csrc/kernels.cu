@@ -879,8 +879,27 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
     const uint64_t iters = (total + groups_per_grid - 1) / groups_per_grid;
     const int lane = threadIdx.x & 31;
 
-    for (uint64_t it = 0; it < iters; it++) {
-        const uint64_t g = first + it * groups_per_grid;
+    // Long queries (more than 255 k-mers: PH > 0) differ a lot in length and are few per launch, so a fixed share of the tasks per lane group
+    // leaves much of the grid idle at the end; their lane groups draw the next task from a counter instead.  Short reads keep the fixed
+    // assignment (ten million atomics on one address per batch would cost more than they save).
+    constexpr bool DYNAMIC = PH > 0;
+    const int gbase0 = lane & ~(int)(G - 1);
+    const uint32_t gmask0 = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << gbase0;
+    for (uint64_t it = 0;; it++) {
+        uint64_t g;
+        if (DYNAMIC) {
+            // one draw per WARP: its 32/G lane groups take consecutive tasks — with the chunk index running fastest these are
+            // slices of the same query, so the groups of a warp finish together (queries of very different lengths in one warp
+            // left the shorter one's lanes idle: 0.79 of the short-read bandwidth on HiFi reads)
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(a.task_counter, (unsigned long long)(32 / G));
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= total) break;                                      // warp-uniform: the hit append below is warp-wide
+            g = t + (uint64_t)(lane / G);
+        } else {
+            if (it >= iters) break;
+            g = first + it * groups_per_grid;
+        }
         uint32_t q = 0, chunk = 0, n = 0;
         if (g < total) {
             q = (uint32_t)(g / chunks);
@@ -906,8 +925,8 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
             const uint32_t *lp32 = SRC == 0 ? a.locs + slot0 * (uint64_t)H : nullptr;
             const uint8_t *colbase = a.rows + (uint64_t)(lane_ok ? colu : 0) * SLAB;
             const bool full = G == (uint32_t)GF;
-            const int gbase = lane & ~(int)(G - 1);
-            const uint32_t gmask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << gbase;
+            const int gbase = gbase0;
+            const uint32_t gmask = gmask0;
             LocT L[PROBE_ROWS * H];
             uint32_t acc = 0;                                           // rows added to the register planes since the last fold
             auto add8 = [&](const Slab<W> (&r)[PROBE_ROWS]) {
@@ -1296,7 +1315,8 @@ static cudaError_t launch_probe_h(const ProbeArgs &a, uint32_t blocks, cudaStrea
 // ------------------------------------------------------------------------------------------------------
 constexpr int BULK_THREADS = 256;
 constexpr int BULK_STAGES = 16;          // k-mers in flight per CTA (two groups of PROBE_ROWS)
-constexpr uint32_t BULK_SLICE = 1024;    // bytes of a row per task, at most
+constexpr uint32_t BULK_SLICE = 4096;    // bytes of a row per task, at most (whole rows up to 4 KB: one bulk copy per row — the TMA unit
+                                         // takes 60-100 cycles per copy, so slices of 640-900 bytes cap it at 2-4 TB/s, profiles/README.md)
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -1324,11 +1344,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
-template <int H>
+// WPT = 32-bit words of the slice per thread (thread t owns words t, t + 256, ...: conflict-free LDS)
+template <int H, int WPT>
 __global__ void __launch_bounds__(BULK_THREADS) probe_bulk_kernel(ProbeArgs a, uint32_t slice, uint32_t n_slices) {
     extern __shared__ __align__(128) uint8_t bulk_smem[];
-    uint8_t *ring = bulk_smem;                                                     // [BULK_STAGES][H][BULK_SLICE]
-    uint64_t *full = (uint64_t *)(bulk_smem + (size_t)BULK_STAGES * H * BULK_SLICE);   // [BULK_STAGES]
+    uint8_t *ring = bulk_smem;                                                     // [BULK_STAGES][H][slice]
+    uint64_t *full = (uint64_t *)(bulk_smem + (size_t)BULK_STAGES * H * slice);    // [BULK_STAGES]
     uint32_t *sloc = (uint32_t *)(full + BULK_STAGES);                             // [2][PROBE_ROWS * H]: row indices of the two groups ahead
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
@@ -1344,10 +1365,11 @@ __global__ void __launch_bounds__(BULK_THREADS) probe_bulk_kernel(ProbeArgs a, u
         const uint32_t n = a.n_eff[q];
         const uint32_t byte0 = sl * slice;
         const uint32_t bytes = a.pitch - byte0 < slice ? a.pitch - byte0 : slice;  // the pitch is a multiple of 128 and zero padded behind row_bytes
-        const bool lane_ok = (uint32_t)tid * 4 < bytes;
-        uint32_t c[8];
+        uint32_t c[8][WPT];
 #pragma unroll
-        for (int p = 0; p < 8; p++) c[p] = 0;
+        for (int p = 0; p < 8; p++)
+#pragma unroll
+            for (int w = 0; w < WPT; w++) c[p][w] = 0;
         if (n > 0) {
             const uint32_t *lp = a.locs + a.slot_off[a.paired ? 2 * q : q] * (uint64_t)H;
             const uint8_t *col = a.rows + byte0;
@@ -1360,7 +1382,7 @@ __global__ void __launch_bounds__(BULK_THREADS) probe_bulk_kernel(ProbeArgs a, u
                     mbar_expect_tx(full + s, (uint32_t)H * bytes);
 #pragma unroll
                     for (int h = 0; h < H; h++)
-                        bulk_g2s(ring + ((size_t)s * H + h) * BULK_SLICE, col + (uint64_t)sloc[buf * NL + u * H + h] * a.pitch, bytes, full + s);
+                        bulk_g2s(ring + ((size_t)s * H + h) * slice, col + (uint64_t)sloc[buf * NL + u * H + h] * a.pitch, bytes, full + s);
                 }
             };
             auto fetch_locs = [&](uint32_t g, int buf) {                           // by the first 8*H threads
@@ -1377,58 +1399,68 @@ __global__ void __launch_bounds__(BULK_THREADS) probe_bulk_kernel(ProbeArgs a, u
                 if (groups > 1) issue(1, 1, kglobal + PROBE_ROWS);
             }
             for (uint32_t g = 0; g < groups; g++) {
-                uint32_t r[PROBE_ROWS];
+                uint32_t r[PROBE_ROWS][WPT];
 #pragma unroll
                 for (int u = 0; u < PROBE_ROWS; u++) {
                     const uint32_t i = g * PROBE_ROWS + u;
-                    r[u] = 0;
+#pragma unroll
+                    for (int w = 0; w < WPT; w++) r[u][w] = 0;
                     if (i < n) {
                         const uint32_t kk = kglobal + i, s = kk % BULK_STAGES;
                         mbar_wait(full + s, (kk / BULK_STAGES) & 1u);
-                        if (lane_ok) {
-                            uint32_t v = *(const uint32_t *)(ring + (size_t)s * H * BULK_SLICE + (size_t)tid * 4);
 #pragma unroll
-                            for (int h = 1; h < H; h++) v &= *(const uint32_t *)(ring + ((size_t)s * H + h) * BULK_SLICE + (size_t)tid * 4);      // pand, U:6639-6645
-                            r[u] = v;
+                        for (int w = 0; w < WPT; w++) {
+                            const uint32_t o = ((uint32_t)w * BULK_THREADS + (uint32_t)tid) * 4;
+                            if (o < bytes) {
+                                uint32_t v = *(const uint32_t *)(ring + (size_t)s * H * slice + o);
+#pragma unroll
+                                for (int h = 1; h < H; h++) v &= *(const uint32_t *)(ring + ((size_t)s * H + h) * slice + o);      // pand, U:6639-6645
+                                r[u][w] = v;
+                            }
                         }
                     }
                 }
                 if (g + 2 < groups) fetch_locs(g + 2, (int)(g & 1));               // group g's indices are not needed any more
                 __syncthreads();                                                   // every thread has taken group g out of the ring
                 if (tid == 0 && g + 2 < groups) issue(g + 2, (int)(g & 1), kglobal + (g + 2) * PROBE_ROWS);
-                // Harley–Seal over the 8 rows (one word per thread)
-                {
-                    uint32_t ones = c[0], twos = c[1], fours = c[2];
-                    uint32_t t1a = maj3(ones, r[0], r[1]); ones = xor3(ones, r[0], r[1]);
-                    uint32_t t1b = maj3(ones, r[2], r[3]); ones = xor3(ones, r[2], r[3]);
+                // Harley–Seal over the 8 rows
+#pragma unroll
+                for (int w = 0; w < WPT; w++) {
+                    uint32_t ones = c[0][w], twos = c[1][w], fours = c[2][w];
+                    uint32_t t1a = maj3(ones, r[0][w], r[1][w]); ones = xor3(ones, r[0][w], r[1][w]);
+                    uint32_t t1b = maj3(ones, r[2][w], r[3][w]); ones = xor3(ones, r[2][w], r[3][w]);
                     uint32_t t2a = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
-                    t1a = maj3(ones, r[4], r[5]); ones = xor3(ones, r[4], r[5]);
-                    t1b = maj3(ones, r[6], r[7]); ones = xor3(ones, r[6], r[7]);
+                    t1a = maj3(ones, r[4][w], r[5][w]); ones = xor3(ones, r[4][w], r[5][w]);
+                    t1b = maj3(ones, r[6][w], r[7][w]); ones = xor3(ones, r[6][w], r[7][w]);
                     uint32_t t2b = maj3(twos, t1a, t1b); twos = xor3(twos, t1a, t1b);
                     uint32_t carry = maj3(fours, t2a, t2b); fours = xor3(fours, t2a, t2b);
-                    c[0] = ones; c[1] = twos; c[2] = fours;
+                    c[0][w] = ones; c[1][w] = twos; c[2][w] = fours;
 #pragma unroll
-                    for (int p = 3; p < 8; p++) { const uint32_t t = c[p] & carry; c[p] ^= carry; carry = t; }
+                    for (int p = 3; p < 8; p++) { const uint32_t t = c[p][w] & carry; c[p][w] ^= carry; carry = t; }
                 }
             }
             kglobal += n;
             __syncthreads();                                                       // sloc is rewritten by the next task
         }
-        // ---- threshold on the bit-sliced counters + hit append (as in probe_kernel, one word per thread) ----
-        uint32_t ge = 0;
+        // ---- threshold on the bit-sliced counters + hit append (as in probe_kernel) ----
+        uint32_t ge[WPT];
         int nhit = 0;
-        if (n > 0 && lane_ok) {
+#pragma unroll
+        for (int w = 0; w < WPT; w++) ge[w] = 0;
+        if (n > 0) {
             const uint32_t Tq = a.thresh[q];
             if (!(Tq >> 8)) {
-                uint32_t gt = 0, eq = 0xFFFFFFFFu;
 #pragma unroll
-                for (int p = 7; p >= 0; p--) {
-                    if ((Tq >> p) & 1) eq &= c[p];
-                    else { gt |= eq & c[p]; eq &= ~c[p]; }
+                for (int w = 0; w < WPT; w++) {
+                    uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int p = 7; p >= 0; p--) {
+                        if ((Tq >> p) & 1) eq &= c[p][w];
+                        else { gt |= eq & c[p][w]; eq &= ~c[p][w]; }
+                    }
+                    ge[w] = gt | eq;                                               // words behind the row stayed zero: they never pass (threshold >= 1)
+                    nhit += __popc(ge[w]);
                 }
-                ge = gt | eq;
-                // bits of the zero padding behind the last target never count: their rows are zero
-                nhit = __popc(ge);
             }
         }
         int incl = nhit;
@@ -1443,40 +1475,61 @@ __global__ void __launch_bounds__(BULK_THREADS) probe_bulk_kernel(ProbeArgs a, u
             if (lane == 31) base = atomicAdd(a.hit_count, (unsigned long long)tot);
             base = __shfl_sync(0xffffffffu, base, 31);
             unsigned long long slot = base + (unsigned long long)(incl - nhit);
-            uint32_t m = ge;
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t t = (byte0 + (uint32_t)tid * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
-                uint32_t cnt = 0;
 #pragma unroll
-                for (int p = 0; p < 8; p++) cnt |= ((c[p] >> bit) & 1u) << p;
-                if (slot < a.hit_cap) {
-                    a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
-                    a.hit_vals[slot] = cnt;
+            for (int w = 0; w < WPT; w++) {
+                uint32_t m = ge[w];
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t t = (byte0 + ((uint32_t)w * BULK_THREADS + (uint32_t)tid) * 4 + (bit >> 3)) * 8 + (7 - (bit & 7));
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int p = 0; p < 8; p++) cnt |= ((c[p][w] >> bit) & 1u) << p;
+                    if (slot < a.hit_cap) {
+                        a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
+                        a.hit_vals[slot] = cnt;
+                    }
+                    slot++;
                 }
-                slot++;
             }
         }
     }
 }
 
-template <int H>
-static cudaError_t launch_probe_bulk_h(const ProbeArgs &a, int sm_count, cudaStream_t st) {
-    const uint32_t n_slices = (a.pitch + BULK_SLICE - 1) / BULK_SLICE;
-    const uint32_t slice = ((a.pitch + n_slices - 1) / n_slices + 127) / 128 * 128;          // equal slices, multiples of 128 bytes
-    const size_t smem = (size_t)BULK_STAGES * H * BULK_SLICE + BULK_STAGES * sizeof(uint64_t) + 2 * PROBE_ROWS * H * sizeof(uint32_t);
-    static bool done = false;
-    if (!done) {
-        cudaError_t e = cudaFuncSetAttribute(probe_bulk_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static size_t bulk_smem_bytes(int H, uint32_t slice) { return (size_t)BULK_STAGES * H * slice + BULK_STAGES * sizeof(uint64_t) + 2 * PROBE_ROWS * H * sizeof(uint32_t); }
+static void bulk_geometry(const ProbeArgs &a, uint32_t &slice, uint32_t &n_slices) {
+    n_slices = (a.pitch + BULK_SLICE - 1) / BULK_SLICE;
+    slice = ((a.pitch + n_slices - 1) / n_slices + 127) / 128 * 128;               // equal slices, multiples of 128 bytes
+    // the ring must fit the SM's shared memory: narrower slices when h rows of 16 k-mers do not
+    while (bulk_smem_bytes(a.num_hashes, slice) > 200 * 1024) { n_slices++; slice = ((a.pitch + n_slices - 1) / n_slices + 127) / 128 * 128; }
+}
+
+template <int H, int WPT>
+static cudaError_t launch_probe_bulk_hw(const ProbeArgs &a, int sm_count, uint32_t slice, uint32_t n_slices, cudaStream_t st) {
+    const size_t smem = bulk_smem_bytes(H, slice);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(probe_bulk_kernel<H, WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        done = true;
+        attr = smem;
     }
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
     const uint64_t tasks = (uint64_t)a.n_queries * n_slices;
     const uint32_t blocks = (uint32_t)std::min<uint64_t>(tasks, (uint64_t)sm_count * per_sm);
-    probe_bulk_kernel<H><<<blocks, BULK_THREADS, smem, st>>>(a, slice, n_slices);
+    probe_bulk_kernel<H, WPT><<<blocks, BULK_THREADS, smem, st>>>(a, slice, n_slices);
     return cudaGetLastError();
+}
+
+template <int H>
+static cudaError_t launch_probe_bulk_h(const ProbeArgs &a, int sm_count, cudaStream_t st) {
+    uint32_t slice = 0, n_slices = 0;
+    bulk_geometry(a, slice, n_slices);
+    switch ((slice + 1023) / 1024) {
+        case 1: return launch_probe_bulk_hw<H, 1>(a, sm_count, slice, n_slices, st);
+        case 2: return launch_probe_bulk_hw<H, 2>(a, sm_count, slice, n_slices, st);
+        case 3: return launch_probe_bulk_hw<H, 3>(a, sm_count, slice, n_slices, st);
+        default: return launch_probe_bulk_hw<H, 4>(a, sm_count, slice, n_slices, st);
+    }
 }
 
 // true when the TMA form applies: short queries, precomputed 32-bit row indices, rows of at least 512 bytes, no dense-count dump

@@ -105,6 +105,7 @@ struct ProbeArgs {
     uint64_t *hit_keys;         // query<<32 | global target
     uint32_t *hit_vals;         // matched k-mers
     unsigned long long *hit_count;
+    unsigned long long *task_counter;   // zeroed before the launch: next task of the long-query kernels (planes > 8)
     uint64_t hit_cap;
     uint32_t *dense_counts;     // optional [n_queries=1][n_targets] dump of all counts (kmcpg_count_codes)
     int planes;                 // counter bits: 8, 16, 24, 32
