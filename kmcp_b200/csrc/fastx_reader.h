@@ -116,7 +116,7 @@ struct InflateAhead {
 struct Tuning {
     int inflate_threads = 0;                   // 0 = decide per file, 1 = always the sequential decoder, N = N workers on one .gz stream
     size_t inflate_chunk = 2u << 20;           // compressed bytes per task of the chunk-parallel decoder
-    size_t inflate_cap = (size_t)256 << 20;    // most bytes a chunk may decode to before the sequential decoder takes over
+    size_t inflate_cap = (size_t)64 << 20;     // most bytes a chunk may decode to before the sequential decoder takes over
     int parse_threads = 0;                     // 0/1 = one parser thread per input, N = N workers on one FASTQ text
     size_t parse_piece = 8u << 20;             // bytes of text per task of the parallel parser
 };
