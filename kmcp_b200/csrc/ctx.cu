@@ -79,7 +79,7 @@ void free_db(kmcpg_ctx *ctx) {
 
 void WorkSet::release() {
     for (DevBuf *b : {&seq, &off, &slot_cnt, &slot_off, &codes, &codes2, &locs[0], &locs[1], &ncodes, &qlen, &nk, &neff, &thresh, &hkeys, &hvals, &hkeys2, &hvals2,
-                      &hits, &counters, &tmp, &tmp2, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off, &tile_n, &tile_off, &tile_cnt, &tile_pre})
+                      &hits, &counters, &tmp, &tmp2, &segb, &sege, &ck, &cs, &cs_cnt, &cs_off, &tile_n, &tile_off, &tile_cnt, &tile_pre, &order, &order_in, &neff_sorted})
         b->release();
     h_off.release(); h_cnt.release();
     for (cudaEvent_t *e : {&ev_in, &ev_a0, &ev_hash, &ev_a, &ev_cnt, &ev_sorted, &ev_b}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }

@@ -94,6 +94,8 @@ struct WorkSet {
     DevBuf hkeys, hvals, hkeys2, hvals2, hits, counters, tmp, tmp2, segb, sege;
     DevBuf ck, cs, cs_cnt, cs_off;      // sketch selection: per-position k-mer / s-mer hashes
     DevBuf tile_n, tile_off, tile_cnt, tile_pre;   // long sequences: tiles per sequence, their scan, codes per tile, their scan
+    DevBuf order, order_in, neff_sorted;           // long queries: query indices by descending number of k-mers (task order of the probe)
+    bool order_valid = false;
     HostBuf h_off, h_cnt;
     cudaEvent_t ev_in = nullptr, ev_a0 = nullptr, ev_hash = nullptr, ev_a = nullptr, ev_cnt = nullptr, ev_sorted = nullptr, ev_b = nullptr;
     std::vector<cudaEvent_t> probe_ev;   // 3 slots per resident block: [0] its row indices are ready, [1] before, [2] after its probe launch

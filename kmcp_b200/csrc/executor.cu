@@ -182,6 +182,19 @@ int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int
     fa.min_matched = p.min_matched; fa.min_query_cov = p.min_query_cov;
     CU(launch_finalize(fa, st)); ctx->launches++;
     *codes_out = codes;
+    w.order_valid = false;
+    if (sb.max_query_slots > 255 && nq > 1) {
+        // long queries differ a lot in length (HiFi reads: 45 bp .. 45 kb): the probe's warps draw their tasks from a counter, longest
+        // queries first, so that the draws left for the end of a launch are short ones
+        CU(w.order.ensure(nq * 4ull)); CU(w.order_in.ensure(nq * 4ull)); CU(w.neff_sorted.ensure(nq * 4ull));
+        CU(launch_iota(w.order_in.as<uint32_t>(), nq, st));
+        size_t t4 = 0;
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, t4, w.neff.as<uint32_t>(), w.neff_sorted.as<uint32_t>(), w.order_in.as<uint32_t>(), w.order.as<uint32_t>(), (int)nq, 0, 32, st);
+        CU(w.tmp.ensure(t4));
+        CU(cub::DeviceRadixSort::SortPairsDescending(w.tmp.p, t4, w.neff.as<uint32_t>(), w.neff_sorted.as<uint32_t>(), w.order_in.as<uint32_t>(), w.order.as<uint32_t>(), (int)nq, 0, 32, st));
+        ctx->launches += 3;
+        w.order_valid = true;
+    }
     return KMCPG_OK;
 }
 
@@ -231,7 +244,8 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
         pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = w.nq; pa.paired = p.paired;
         pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
         pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = w.cap; pa.dense_counts = nullptr; pa.planes = w.planes;
-        pa.task_counter = w.counters.as<unsigned long long>() + 2 + bi;        // one counter per block of this part, zeroed below
+        pa.task_counter = w.counters.as<unsigned long long>() + 2 + bi;        // one counter per block of this part, zeroed above
+        pa.order = w.order_valid ? w.order.as<uint32_t>() : nullptr;
         CU(launch_probe(pa, ctx->sm_count, st)); ctx->launches++;
         CU(cudaEventRecord(w.probe_ev[bi * 3 + 2], st));
         bi++;

@@ -197,6 +197,9 @@ class Inflater {
     }
     const char *error() const { return err_.c_str(); }
     bool is_gzip() const { return saw_gzip_; }
+    // bytes that are not a gzip member followed the last member (ignored here; Go's gzip reader — the reference's xopen — fails with
+    // "gzip: invalid header" on such a file)
+    bool trailing_garbage() const { return garbage_; }
     uint64_t members() const { return members_; }
 
     // ---- table construction (also used by the chunk-parallel decoder in pargz.h) ------------------------------------------
@@ -366,11 +369,11 @@ class Inflater {
                 if (!ensure(2)) {
                     if (io_error_) return fail("read error");
                     if (in_end_ == in_next_) { state_ = ST_END; return true; }                  // clean end (or an empty file)
-                    if (members_) { state_ = ST_END; return true; }                             // one stray byte after the last member
+                    if (members_) { garbage_ = true; state_ = ST_END; return true; }            // one stray byte after the last member
                     state_ = ST_PLAIN; break;
                 }
                 if (in_next_[0] != 0x1f || in_next_[1] != 0x8b) {
-                    if (members_) { state_ = ST_END; return true; }                             // trailing garbage is ignored, as gzread does
+                    if (members_) { garbage_ = true; state_ = ST_END; return true; }            // trailing garbage is ignored, as gzread does (callers may ask)
                     state_ = ST_PLAIN; break;
                 }
                 saw_gzip_ = true;
@@ -661,7 +664,7 @@ class Inflater {
     bool verify_;
     std::vector<uint8_t> ibuf_, obuf_;
     const uint8_t *in_next_, *in_end_;
-    bool in_eof_ = false, io_error_ = false, failed_ = false, saw_gzip_ = false, final_ = false;
+    bool in_eof_ = false, io_error_ = false, failed_ = false, saw_gzip_ = false, final_ = false, garbage_ = false;
     uint64_t bitbuf_ = 0;
     unsigned bitcnt_ = 0;
     uint8_t *out_base_, *out_limit_, *out_next_, *drain_, *crc_from_;

@@ -230,6 +230,8 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
     ssize_t raw_read(void *dst, size_t n) {
         if (pf) {
             const ssize_t r = pf->read(dst, n);
+            // a damaged or overwritten multi-member file is an error, as for the reference's reader (Go's gzip: "gzip: invalid header"), not a shorter input
+            if (r == 0 && pf->trailing_garbage()) { ext_err = "gzip: invalid header (bytes that are not a gzip member follow the last member)"; return -1; }
             if (r >= 0 || !pf->too_big()) { if (r > 0) raw_total += (uint64_t)r; return r; }
             // a stretch that expands beyond what the chunk-parallel decoder keeps in memory (compression ratios in the hundreds):
             // the sequential decoder streams; it starts over and drops what was handed out already
@@ -245,6 +247,7 @@ struct Reader {          // FASTA/Q, plain or gzip (bio/seqio/fastx default read
         }
         const ssize_t r = f->read(dst, n);
         if (r > 0) raw_total += (uint64_t)r;
+        if (r == 0 && f->trailing_garbage()) { ext_err = "gzip: invalid header (bytes that are not a gzip member follow the last member)"; return -1; }
         if (r == 0 && child > 0) {              // the decompressor's verdict on the file
             int st = 0;
             waitpid(child, &st, 0);

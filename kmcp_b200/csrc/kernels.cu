@@ -904,6 +904,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
         if (g < total) {
             q = (uint32_t)(g / chunks);
             chunk = (uint32_t)(g - (uint64_t)q * chunks);               // chunk fastest: neighbouring groups share rows
+            if (DYNAMIC && a.order) q = a.order[q];                     // longest queries first: the last draws are the short ones
             n = a.n_eff[q];
         }
         const uint32_t colu = chunk * G + gl;                           // this lane's slab of the row
@@ -1623,6 +1624,16 @@ __global__ void unpitch_kernel(const uint8_t *__restrict__ src, uint8_t *__restr
         uint32_t x = (uint32_t)(i - r * row_bytes);
         dst[i] = src[r * pitch + x];
     }
+}
+
+__global__ void iota_kernel(uint32_t *__restrict__ v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+cudaError_t launch_iota(uint32_t *v, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(v, n);
+    return cudaGetLastError();
 }
 
 __global__ void pack_hits_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t qbase, kmcpg_hit *__restrict__ out) {

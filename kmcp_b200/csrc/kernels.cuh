@@ -106,6 +106,7 @@ struct ProbeArgs {
     uint32_t *hit_vals;         // matched k-mers
     unsigned long long *hit_count;
     unsigned long long *task_counter;   // zeroed before the launch: next task of the long-query kernels (planes > 8)
+    const uint32_t *order;              // optional, long-query kernels: queries by descending number of k-mers (draw i works on query order[i / chunks])
     uint64_t hit_cap;
     uint32_t *dense_counts;     // optional [n_queries=1][n_targets] dump of all counts (kmcpg_count_codes)
     int planes;                 // counter bits: 8, 16, 24, 32
@@ -128,6 +129,7 @@ cudaError_t launch_repitch_cols(const uint8_t *src, uint8_t *dst, uint64_t n_row
                                 uint32_t pitch, cudaStream_t st);
 cudaError_t launch_unpitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, uint32_t row_bytes, uint32_t pitch,
                            cudaStream_t st);
+cudaError_t launch_iota(uint32_t *v, uint32_t n, cudaStream_t st);
 // sorted (key,val) pairs → kmcpg_hit records, query index rebased by query_base
 cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint32_t query_base, kmcpg_hit *out,
                              cudaStream_t st);

@@ -61,6 +61,7 @@ struct ChunkResult {
     bool found = false;               // a place to start was found (chunk 0: the gzip header was read)
     bool not_gzip = false;            // chunk 0 only
     bool at_eof = false;              // the last member ended and nothing (or only garbage) follows
+    bool garbage = false;             // ... and what follows is not a gzip member
     bool failed = false;
     bool too_big = false;             // failed because the chunk decodes to more than the cap (a stream for the sequential decoder)
     std::string err;
@@ -596,7 +597,7 @@ class ChunkDecoder {
                 const size_t off = (size_t)(in_ - src_.z.data());
                 if (src_.z_len - off < 2) more_input();
                 const size_t left = src_.z_len - (size_t)(in_ - src_.z.data());
-                if (left < 2 || in_[0] != 0x1f || in_[1] != 0x8b) { R.at_eof = true; R.end_bit = bitpos(); return; }   // end, or garbage that gzread ignores too
+                if (left < 2 || in_[0] != 0x1f || in_[1] != 0x8b) { R.at_eof = true; R.garbage = left > 0; R.end_bit = bitpos(); return; }   // end, or garbage that gzread ignores too
                 if (!member_header(R)) return;
                 // a new member starts with an empty window: plain bytes from here on, whatever came before
                 if (markers_) start_bytes(R, nullptr, 0);
@@ -697,6 +698,7 @@ class ParallelInflater {
     }
     const char *error() const { return err_.c_str(); }
     bool too_big() const { return too_big_; }
+    bool trailing_garbage() const { return garbage_; }     // see fastgz::Inflater::trailing_garbage
     // how the stream was put together (tests and logs)
     uint64_t chunks_used() const { return used_; }
     uint64_t chunks_redone() const { return redone_; }
@@ -951,6 +953,7 @@ class ParallelInflater {
         else s_member_out_ = total - r->members.back().out_off;
         if (!r->failed) cur_bit_ = r->end_bit;
         if (r->at_eof || r->failed) at_eof_ = true;                    // nothing can follow a broken stretch
+        if (r->garbage) garbage_ = true;
         resolved_ += ns;
         it->r = std::move(r);
         std::lock_guard<std::mutex> lk(mu_);
@@ -982,7 +985,7 @@ class ParallelInflater {
     std::deque<std::shared_ptr<Item>> queue_;  // settled, not handed out yet
     std::vector<uint8_t> tail_;                // the 32 KB in front of cur_bit_, right-aligned
     uint64_t cur_bit_ = 0, s_member_out_ = 0;  // end of the settled data; bytes of the current member in front of it
-    bool at_eof_ = false, settled_all_ = false;
+    bool at_eof_ = false, settled_all_ = false, garbage_ = false;
     std::shared_ptr<Item> cur_;                // being handed out
     size_t cur_len_ = 0, pos_ = 0;
     uint64_t member_out_ = 0;                  // delivery side: bytes and CRC of the current member so far

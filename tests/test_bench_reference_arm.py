@@ -53,3 +53,34 @@ def test_reference_arm_contract_and_multi_rank_workload(oracle, monkeypatch, cap
         bench.run_reference(argparse.Namespace(gpus=1, steps=1, warmup=1), 0, 1)
         line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
         assert line["impl"] == "reference" and "unavailable" in line
+
+
+def test_hifi_batch_is_seeded_and_follows_the_genome_generator(oracle, monkeypatch):
+    """bench.py's HiFi read generator (C5): deterministic in (seed, step), lengths in the stated range, and every read a
+    lightly mutated window of the seeded genome the device generator produces (oracle.synth_genome)"""
+    O = oracle
+    monkeypatch.setenv("KMCP_BENCH_SCALE", "quick")
+    import bench
+    importlib.reload(bench)
+    off, seq = bench.hifi_batch(5, 0, 40, 3, 7, 60000)
+    off2, seq2 = bench.hifi_batch(5, 0, 40, 3, 7, 60000)
+    assert np.array_equal(off, off2) and np.array_equal(seq, seq2)
+    assert not np.array_equal(seq[:200], bench.hifi_batch(5, 1, 40, 3, 7, 60000)[1][:200])
+    lens = np.diff(off.astype(np.int64))
+    assert lens.min() >= 45 and lens.max() <= 45000 and 4000 < lens.mean() < 16000
+    genomes = [O.synth_genome(3, g, 60000) for g in range(7)]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for i in range(10):
+        r = seq[int(off[i]):int(off[i + 1])].tobytes()
+        best = 1.0
+        for cand in (r, r.translate(comp)[::-1]):
+            probe = cand[:24] if len(cand) >= 24 else cand
+            for g in genomes:
+                # a 24-mer free of substitutions somewhere in the read locates it; compare the whole window then
+                for start in range(0, max(1, len(cand) - 24), 24):
+                    pos = g.find(cand[start:start + 24])
+                    if pos >= 0 and pos - start >= 0 and pos - start + len(cand) <= len(g):
+                        w = g[pos - start:pos - start + len(cand)]
+                        best = min(best, sum(a != b for a, b in zip(w, cand)) / len(cand))
+                        break
+        assert best < 0.02, (i, best)

@@ -399,3 +399,25 @@ def test_search_command_has_every_flag_of_the_reference():
         if kind in ("Int", "Float64") and default not in ("0", "0.0"):
             m = re.search(r"--%s\b[^\n]*\(default ([^)]+)\)" % re.escape(name), helptext)
             assert m and float(m.group(1)) == float(default), (name, default, m and m.group(1))
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_bytes_behind_the_last_gzip_member_are_a_read_error(tmp_path, threads):
+    """a multi-member .gz that was damaged or overwritten behind a member boundary: the reference reads through Go's multistream gzip
+    reader (xopen), which fails with "gzip: invalid header"; the reader stage reports a read error too instead of searching a silently
+    shorter input (the stand-alone `kmcp-gpu gunzip` stays as lenient as gzread, tests/test_fastgz.py)"""
+    import gzip
+    from kmcp_b200 import api
+    rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"ACGT" * 30, b"I" * 120) for i in range(30000))
+    good = gzip.compress(rec[:len(rec) // 2], 6) + gzip.compress(rec[len(rec) // 2:], 6)
+    ok, bad, pad = str(tmp_path / "ok.fq.gz"), str(tmp_path / "bad.fq.gz"), str(tmp_path / "pad.fq.gz")
+    open(ok, "wb").write(good)
+    open(bad, "wb").write(good + b"overwritten tail that is not a gzip member")
+    open(pad, "wb").write(good + b"\0" * 512)
+    kw = dict(inflate_threads=threads, inflate_chunk=65536)
+    assert sum(len(ids) for _f, ids, _s, _o in api.read_batches([ok], **kw)) == 30000
+    for p in (bad, pad):
+        with pytest.raises(api.KmcpGpuError) as e:
+            for _ in api.read_batches([p], **kw):
+                pass
+        assert "gzip: invalid header" in str(e.value)

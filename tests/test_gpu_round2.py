@@ -311,3 +311,44 @@ def test_demo_profiling_golden_through_the_cuda_path(tmp_path):
     assert len({ln.split("\t")[14] for ln in rows}) == summary["subset"]["matched"] == 36448 and len(rows) == summary["subset"]["rows"]
     log = p.stderr.decode()
     assert "(36448/40000) queries matched" in log, log[-400:]
+
+
+def test_sharded_search_pipeline_single_rank(gpu_ctx, oracle, mid_db):
+    """kmcp_b200.multigpu.ShardedSearch with one rank: the step pipeline bench.py runs under torchrun — staged batch + ready event, two jobs in
+    flight, the library's device→host copy straight into the CUDA-registered shared-memory slot, consumer thread, slot hand-back over more steps
+    than slots — must hand the consumer exactly the hits of the blocking call, step by step"""
+    import torch
+    from kmcp_b200 import api, multigpu
+    O = oracle
+    gpu_ctx.open_db(mid_db)
+    n, steps = 2000, 5
+    p = gpu_ctx.default_params()
+    batches, refs = [], []
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(150)
+    for s in range(steps):
+        reads = helpers.make_reads(O, RSEED + 50 + s, n, 30, 25000, GSEED + 4)
+        buf, off2 = api.pack_seqs(reads)
+        assert np.array_equal(off, off2)
+        refs.append(gpu_ctx.search_batch(buf, off, p))
+        batches.append(np.concatenate([off.view(np.uint8), buf]))
+    bb = batches[0].size
+    dev = torch.device("cuda", 0)
+    d = torch.from_numpy(np.concatenate(batches)).to(dev)
+    sh = multigpu.ShardedSearch(gpu_ctx, 0, 1, n, bb, hit_cap=1 << 16, name="kmcp_test_%d" % os.getpid(), device=dev, dist=None, params=p)
+    got = {}
+
+    def consume(s, lists, meta):
+        assert len(lists) == 1
+        got[s] = (lists[0].copy(), meta.n_kmers.copy(), multigpu.hits_digest(multigpu.merge_lists(lists, 0, n)))
+
+    try:
+        for rep in range(2):          # the step counter of the exchange carries on across run() calls
+            got.clear()
+            outs = sh.run(steps, lambda s: (d[s * bb:(s + 1) * bb], False), consume, host_off=off if rep == 0 else None)
+            assert len(outs) == steps and sorted(got) == list(range(steps))
+            for s in range(steps):
+                hits, nk, dig = got[s]
+                assert np.array_equal(hits, refs[s].hits) and np.array_equal(nk, refs[s].n_kmers)
+                assert dig == multigpu.hits_digest(refs[s].hits) and outs[s].n_hits == len(refs[s].hits)
+    finally:
+        sh.close()
