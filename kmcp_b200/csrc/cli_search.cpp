@@ -109,7 +109,10 @@ void usage() {
         "Search sequences against a kmcp database on a B200 GPU (drop-in for `kmcp search`)\n\n"
         "Usage:\n  kmcp-gpu search [flags] [-w] -d <kmcp db> [-t <min-query-cov>] [read1.fq.gz] [read2.fq.gz] [unpaired.fq.gz] [-o read.tsv.gz]\n\n"
         "Flags (same names, shorthands and defaults as kmcp search):\n"
-        "  -d, --db-dir string              database directory created by \"kmcp index\"\n"
+        "  -d, --db-dir string              database directory created by \"kmcp index\"; may be given several times: the hits of a\n"
+        "                                   query in all of them are united and re-sorted, as \"kmcp merge\" does with the outputs of\n"
+        "                                   separate searches (-n/--keep-top-scores applies per database, as it would there;\n"
+        "                                   databases with several sub-databases R001, R002, ... are not supported)\n"
         "  -1, --read1 string / -2, --read2 string   paired-end read files\n"
         "      --try-se                     if paired-end reads have no hits, re-search with read1, then read2\n"
         "  -u, --kmer-dedup-threshold int   remove duplicated kmers for a query with >= X k-mers (default 256)\n"
@@ -351,6 +354,17 @@ int index_main(int argc, char **argv) {
     if (kmcpg_index_fasta(ctx, &p, fp.data(), (int)fp.size(), out_dir.c_str())) die("%s", kmcpg_last_error(ctx));
     kmcpg_db_info_t info;
     kmcpg_db_info(ctx, &info);
+    {   // `kmcp index` moves references with more than -x 10M / -8 20M / -1 200M k-mers into blocks of -X 256 / 8 / 1 (I:213-259, 787-880) so that one
+        // huge genome does not set the Bloom-filter size of a whole -b wide block; this builder keeps one block width
+        uint64_t big = 0, mx = 0;
+        for (int64_t t = 0; t < info.n_targets; t++) {
+            kmcpg_target_t tg;
+            if (kmcpg_target(ctx, t, &tg) == 0) { big += tg.n_kmers > 10000000ull; mx = std::max<uint64_t>(mx, tg.n_kmers); }
+        }
+        if (big)
+            logf("WARN", "%llu target(s) hold more than 10M k-mers (largest: %llu): `kmcp index` would give them narrower blocks (-x/-8/-1); "
+                         "this build keeps -b wide blocks, so the index is larger than the reference's", (unsigned long long)big, (unsigned long long)mx);
+    }
     logf("INFO", "kmcp database with %lld targets in %d block(s) saved to: %s (%.1f s)", (long long)info.n_targets, info.n_blocks, out_dir.c_str(),
          std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     kmcpg_close(ctx);
