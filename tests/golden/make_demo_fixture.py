@@ -73,3 +73,8 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# tests/golden/demo_searching/refs/: the nine genomes of /root/reference/demo-searching/refs, byte for byte (input data of the reference's
+# genome-similarity demo; the expected qCov / tCov / jacc tables are the ones printed in demo-searching/README.md:61-68 and :102-109, G3 / G4):
+#   mkdir -p tests/golden/demo_searching/refs && cp /root/reference/demo-searching/refs/*.fasta.gz tests/golden/demo_searching/refs/

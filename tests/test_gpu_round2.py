@@ -352,3 +352,37 @@ def test_sharded_search_pipeline_single_rank(gpu_ctx, oracle, mid_db):
                 assert dig == multigpu.hits_digest(refs[s].hits) and outs[s].n_hits == len(refs[s].hits)
     finally:
         sh.close()
+
+
+G34_ORDER = ["NC_018658.1", "NZ_CP028116.1", "NC_000913.3", "NC_012971.2", "NZ_CP007592.1", "NC_002695.2"]    # the README's rows (name.map resolved)
+
+
+@pytest.mark.parametrize("label,flags,expected", [
+    ("G3 FracMinHash", ["-D", "1000"],                                     # demo-searching/README.md:102-109
+     [("1.0000", "1.0000", "1.0000"), ("0.7499", "0.7234", "0.5828"), ("0.6064", "0.6833", "0.4734"), ("0.5965", "0.6893", "0.4701"),
+      ("0.5852", "0.5958", "0.4189"), ("0.5527", "0.5383", "0.3750")]),
+    ("G4 closed syncmer", ["-S", "15", "-D", "62"],                        # demo-searching/README.md:61-68
+     [("1.0000", "1.0000", "1.0000"), ("0.7439", "0.7189", "0.5763"), ("0.6041", "0.6768", "0.4688"), ("0.5972", "0.6807", "0.4665"),
+      ("0.5782", "0.5868", "0.4109"), ("0.5482", "0.5322", "0.3699")]),
+])
+def test_demo_searching_golden_tables_through_the_cuda_path(tmp_path, label, flags, expected):
+    """The reference's genome-similarity demo: `kmcp compute -k 31 -B plasmid [-D 1000 | -S 15 -D 62]`, `kmcp index -n 3 -f 0.01`,
+    `kmcp search -g -t 0.5 -n 0 -s jacc refs/NC_018658.1.fasta.gz` — through kmcp-gpu index + kmcp-gpu search (device sketching with the FracMinHash
+    cut / closed-syncmer selection, device builder, -g whole-file query through the tile hashing and the CTA-per-task probe).  The qCov, tCov and jacc
+    columns and the order of the six targets must be the table the reference prints in demo-searching/README.md."""
+    import glob
+    import subprocess
+    demo = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demo_searching", "refs")
+    refs = sorted(glob.glob(os.path.join(demo, "*.fasta.gz")))
+    assert len(refs) == 9
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmcp_b200", "kmcp-gpu")
+    db = str(tmp_path / "refs.kmcp")
+    p = subprocess.run([exe, "index", "-q", "-O", db, "-k", "31", "-B", "plasmid", "--num-hash", "3", "-f", "0.01", "-j", "16"] + flags + refs, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    assert len(glob.glob(db + "/R001/*.uniki")) == 2                       # 9 references, -j 16: blocks of 8 + 1 (I:670-682)
+    tsv = str(tmp_path / "out.tsv")
+    p = subprocess.run([exe, "search", "-q", "-d", db, "-g", "-t", "0.5", "-n", "0", "-s", "jacc", os.path.join(demo, "NC_018658.1.fasta.gz"), "-o", tsv], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    rows = [ln.split("\t") for ln in open(tsv).read().splitlines() if not ln.startswith("#")]
+    assert [r[5] for r in rows] == G34_ORDER, label
+    assert [(r[11], r[12], r[13]) for r in rows] == expected, label
