@@ -736,7 +736,7 @@ int kmcpg_count_codes(kmcpg_ctx *ctx, const uint64_t *codes, uint64_t n, uint32_
                 pa.locs = w.locs[0].as<uint32_t>();
             }
             pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = 1; pa.paired = 0;
-            pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
+            pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>(); pa.target_bits = 32;
             pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = 0; pa.dense_counts = ctx->d_dense.as<uint32_t>();
             pa.task_counter = w.counters.as<unsigned long long>() + 2;
             CU(cudaMemsetAsync(w.counters.as<unsigned long long>() + 2, 0, 8, st));

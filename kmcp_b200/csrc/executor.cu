@@ -49,6 +49,10 @@ struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { re
 
 // hashing of one HashArgs job: warp per query for short sequences, warp per 4096-position tile (+ gather) when a query is long
 static int hash_any(kmcpg_ctx *ctx, WorkSet &w, const HashArgs &ha, uint32_t n_seqs, uint64_t total_slots, uint64_t max_query_slots, cudaStream_t st) {
+    if (!ha.raw && !ha.scaled && max_query_slots <= HASH_GROUP_MAX_KMERS) {        // short reads, every k-mer kept: eight lanes per query
+        CU(launch_hash_groups(ha, st)); ctx->launches++;
+        return KMCPG_OK;
+    }
     if (max_query_slots <= 2ull * HASH_TILE_POS) {
         CU(launch_hash(ha, st)); ctx->launches++;
         return KMCPG_OK;
@@ -198,6 +202,13 @@ int run_hash_stage(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &p, int
     return KMCPG_OK;
 }
 
+// bits of the largest global target index (hit keys are query << bits | target)
+static int target_bits_of(const kmcpg_ctx *ctx) {
+    int b = 1;
+    while (b < 32 && (1ll << b) < std::max<int64_t>(ctx->meta.n_targets, 1)) b++;
+    return b;
+}
+
 // Per resident block: the row indices (locs kernel, on the query-preparation stream: the indices of block b+1 are computed while
 // block b is probed; two buffers alternate) and ONE probe launch on the compute stream; then the counters travel to the host on
 // their own stream.  Blocks with numSigs >= 2^32-1 need no locs kernel: their probe derives 64-bit indices itself.
@@ -242,7 +253,7 @@ static int enqueue_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params 
         pa.n_names = b.n_cols; pa.target_base = (uint32_t)(bm.target_base + b.col0); pa.num_hashes = H;
         pa.codes = w.codes_ptr; pa.fm = b.fm; pa.locs = locs; pa.slot_off = w.slot_off.as<uint64_t>();
         pa.n_eff = w.neff.as<uint32_t>(); pa.thresh = w.thresh.as<uint32_t>(); pa.n_queries = w.nq; pa.paired = p.paired;
-        pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>();
+        pa.hit_keys = w.hkeys.as<uint64_t>(); pa.hit_vals = w.hvals.as<uint32_t>(); pa.target_bits = target_bits_of(ctx);
         pa.hit_count = w.counters.as<unsigned long long>(); pa.hit_cap = w.cap; pa.dense_counts = nullptr; pa.planes = w.planes;
         pa.task_counter = w.counters.as<unsigned long long>() + 2 + bi;        // one counter per block of this part, zeroed above
         pa.order = w.order_valid ? w.order.as<uint32_t>() : nullptr;
@@ -359,13 +370,14 @@ static int finish_probes(kmcpg_ctx *ctx, WorkSet &w, const kmcpg_search_params &
         if (rc) return rc;
         CU(w.hkeys2.ensure(n_hits * 8)); CU(w.hvals2.ensure(n_hits * 4)); CU(w.hits.ensure(n_hits * sizeof(kmcpg_hit)));
         int qbits = 1; while ((1ull << qbits) < w.nq) qbits++;
+        const int tbits = target_bits_of(ctx);                   // keys are query << tbits | target: the sort looks at tbits + qbits bits only
         size_t t3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
-                                        (int64_t)n_hits, 0, 32 + qbits, ps);
+                                        (int64_t)n_hits, 0, tbits + qbits, ps);
         CU(w.tmp2.ensure(t3));
         CU(cub::DeviceRadixSort::SortPairs(w.tmp2.p, t3, w.hkeys.as<uint64_t>(), w.hkeys2.as<uint64_t>(), w.hvals.as<uint32_t>(), w.hvals2.as<uint32_t>(),
-                                           (int64_t)n_hits, 0, 32 + qbits, ps));
-        CU(launch_pack_hits(w.hkeys2.as<uint64_t>(), w.hvals2.as<uint32_t>(), n_hits, w.sb.query_base + res.first_query, w.hits.as<kmcpg_hit>(), ps));
+                                           (int64_t)n_hits, 0, tbits + qbits, ps));
+        CU(launch_pack_hits(w.hkeys2.as<uint64_t>(), w.hvals2.as<uint32_t>(), n_hits, w.sb.query_base + res.first_query, tbits, w.hits.as<kmcpg_hit>(), ps));
         ctx->launches += 4;
     }
     CU(cudaEventRecord(w.ev_sorted, ps));
@@ -463,6 +475,24 @@ static int cut_parts(kmcpg_ctx *ctx, const uint64_t *off, uint32_t n_seqs, uint3
         }
     }
     if (b > a) close();
+    // A short LAST part drains the pipeline quickly: what follows it — hit sort, result copy, the caller's post-filter of that part — is not
+    // hidden behind another probe unless a second batch is queued.  The tail of a big last part becomes a part of its own (~ 1/8 of a part).
+    if (!parts.empty() && parts.back().slots > PART_SLOTS / 4) {
+        Part &last = parts.back();
+        uint64_t tail = 0, tmax = 0;
+        uint32_t c = last.b;
+        while (c > last.a + step && tail < PART_SLOTS / 8) {
+            uint64_t qs = 0;
+            for (uint32_t m = 0; m < step; m++) { const uint64_t len = off[c - step + m + 1] - off[c - step + m]; qs += len >= kk ? len - kk + 1 : 0; }
+            if (tail + qs > PART_SLOTS / 4) break;
+            tail += qs; tmax = std::max(tmax, qs); c -= step;
+        }
+        if (c > last.a && c < last.b && tail > 0) {
+            const Part t{c, last.b, tail, tmax};
+            last.b = c; last.slots -= tail;                     // its maxq stays as an upper bound
+            parts.push_back(t);
+        }
+    }
     return KMCPG_OK;
 }
 

@@ -176,6 +176,98 @@ __global__ void __launch_bounds__(HASH_WARPS * 32) hash_kernel(HashArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// short reads, plain k-mers (no FracMinHash cut, no sketch selection): EIGHT lanes per query, four queries per warp.  With a whole
+// warp on a 150 bp read every lane pays the k-step Horner initialisation for a run of only 5 k-mers (21 of 26 steps are set-up);
+// eight lanes roll runs of 17, so a warp spends 2.3x fewer instructions per read.  Every k-mer code is kept unless it is 0
+// (U:1097-1102), which a 64-bit hash practically never is: codes go straight to their position, and a mate that did produce a
+// zero code is compacted afterwards by its first lane.  Same codes in the same order as hash_kernel.
+// ------------------------------------------------------------------------------------------------------
+constexpr int HG_LANES = 8;
+constexpr uint32_t HG_MAX_KMERS = 512;      // per mate: runs of at most 64 k-mers per lane
+
+__global__ void __launch_bounds__(HASH_WARPS * 32) hash_group_kernel(HashArgs a) {
+    __shared__ SeedTables T;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint64_t f = seed_fwd((uint8_t)i);
+        if (i < 8) {
+            const uint64_t r8[8] = {0, SEED_T, 0, SEED_G, SEED_A, SEED_A, 0, SEED_C};
+            f = r8[i];
+            T.R[i] = f; T.R1[i] = ror1(f); T.Rk1[i] = rolv(f, (unsigned)(a.k - 1));
+        }
+        T.F[i] = f;
+        T.Fk[i] = rolv(f, (unsigned)a.k);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, gl = lane & (HG_LANES - 1), gbase = lane & ~(HG_LANES - 1);
+    const uint32_t gmask = ((1u << HG_LANES) - 1u) << gbase;
+    const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / HG_LANES;
+    const uint32_t n_groups = (gridDim.x * blockDim.x) / HG_LANES;
+    const int k = a.k;
+    for (uint32_t q = group; q < a.n_queries; q += n_groups) {
+        const uint32_t s0 = a.paired ? 2 * q : q;
+        const int n_mates = a.paired ? 2 : 1;
+        const uint64_t len0 = a.seq_off[s0 + 1] - a.seq_off[s0];
+        const uint64_t len1 = a.paired ? a.seq_off[s0 + 2] - a.seq_off[s0 + 1] : 0;
+        uint64_t *out = a.codes + a.slot_off[s0];
+        uint32_t written = 0;
+        const bool skip = (int64_t)len0 < a.min_query_len && !(a.paired && (int64_t)len1 >= a.min_query_len);      // U:778-786
+        int32_t qlen = (int32_t)(len0 + len1);
+        if (a.mate_select == 1) qlen = (int32_t)len0;
+        if (a.mate_select == 2) qlen = (int32_t)len1;
+        if (!skip) {
+            for (int m = 0; m < n_mates; m++) {
+                if (a.mate_select == 1 && m == 1) continue;
+                if (a.mate_select == 2 && m == 0) continue;
+                const uint8_t *s = a.seq + a.seq_off[s0 + m];
+                const uint64_t len = m == 0 ? len0 : len1;
+                if (len < (uint64_t)k) continue;                       // sketches.ErrShortSeq (U:1059-1062)
+                const uint32_t nk = (uint32_t)(len - k + 1);
+                const uint32_t run = (nk + HG_LANES - 1) / HG_LANES;
+                const uint32_t p0 = (uint32_t)gl * run;
+                const uint32_t cnt = p0 < nk ? (nk - p0 < run ? nk - p0 : run) : 0;
+                bool zero = false;
+                if (cnt > 0) {
+                    uint64_t fh = 0, rh = 0;
+#pragma unroll 4
+                    for (int j = 0; j < k; j++) {
+                        const uint8_t b = s[p0 + j];
+                        fh = rol1(fh) ^ T.F[b];
+                        rh = ror1(rh) ^ T.Rk1[b & 7];
+                    }
+                    uint64_t *o = out + written + p0;
+#pragma unroll 4
+                    for (uint32_t r = 0; r < cnt; r++) {
+                        const uint64_t code = a.canonical ? (fh < rh ? fh : rh) : fh;
+                        o[r] = code;
+                        zero |= code == 0;
+                        if (r + 1 < cnt) {
+                            const uint8_t bo = s[p0 + r], bi = s[p0 + r + k];
+                            fh = rol1(fh) ^ T.Fk[bo] ^ T.F[bi];
+                            rh = ror1(rh) ^ T.R1[bo & 7] ^ T.Rk1[bi & 7];
+                        }
+                    }
+                }
+                uint32_t kept = nk;
+                if (__any_sync(gmask, zero)) {                          // practically never: drop the zero codes, in order
+                    __syncwarp(gmask);
+                    uint32_t w = 0;
+                    if (gl == 0) {
+                        uint64_t *o = out + written;
+                        for (uint32_t i = 0; i < nk; i++) { const uint64_t c = o[i]; if (c) o[w++] = c; }
+                    }
+                    kept = __shfl_sync(gmask, w, gbase);
+                }
+                written += kept;
+            }
+        }
+        if (gl == 0) {
+            a.n_codes[q] = skip ? 0xFFFFFFFFu : written;                // 0xFFFFFFFF marks "skipped by length" (NumKmers = 0)
+            a.query_len[q] = qlen;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // minimizer / closed syncmer selection: one warp per query, 32 windows per round, every lane scans its window
 // for the LEFTMOST minimum (bio/sketches keeps a sorted buffer whose ties stay in arrival order)
 // ------------------------------------------------------------------------------------------------------
@@ -426,6 +518,15 @@ cudaError_t launch_gather_tiles(const HashArgs &a, uint32_t n_seqs, const uint64
     uint64_t blocks64 = (std::max<uint64_t>(max_tiles, a.n_queries / 8 + 1) + 7) / 8;
     uint32_t blocks = blocks64 > 148u * 32u ? 148u * 32u : (uint32_t)blocks64;
     gather_tiles_kernel<<<blocks, 256, 0, st>>>(a, n_seqs, tile_off, tile_pre, tile_cnt, tmp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hash_groups(const HashArgs &a, cudaStream_t st) {
+    if (a.n_queries == 0) return cudaSuccess;
+    const uint32_t per_block = HASH_WARPS * 32 / HG_LANES;
+    uint32_t blocks = (a.n_queries + per_block - 1) / per_block;
+    if (blocks > 148u * 64u) blocks = 148u * 64u;
+    hash_group_kernel<<<blocks, HASH_WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1038,7 +1139,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
 #pragma unroll
                         for (int p = 0; p < P; p++) cnt |= ((plane(p, w) >> bit) & 1u) << p;
                         if (slot < a.hit_cap) {
-                            a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
+                            a.hit_keys[slot] = ((uint64_t)q << a.target_bits) | (uint64_t)(a.target_base + t);
                             a.hit_vals[slot] = cnt;
                         }
                         slot++;
@@ -1185,7 +1286,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, 1) probe_long_kernel(ProbeArgs 
 #pragma unroll
                             for (int p = 0; p < P; p++) cnt |= ((T[(p * W + w) * PROBE_THREADS] >> bit) & 1u) << p;
                             if (slot < a.hit_cap) {
-                                a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
+                                a.hit_keys[slot] = ((uint64_t)q << a.target_bits) | (uint64_t)(a.target_base + t);
                                 a.hit_vals[slot] = cnt;
                             }
                             slot++;
@@ -1487,7 +1588,7 @@ __global__ void __launch_bounds__(BULK_THREADS) probe_bulk_kernel(ProbeArgs a, u
 #pragma unroll
                     for (int p = 0; p < 8; p++) cnt |= ((c[p][w] >> bit) & 1u) << p;
                     if (slot < a.hit_cap) {
-                        a.hit_keys[slot] = ((uint64_t)q << 32) | (uint64_t)(a.target_base + t);
+                        a.hit_keys[slot] = ((uint64_t)q << a.target_bits) | (uint64_t)(a.target_base + t);
                         a.hit_vals[slot] = cnt;
                     }
                     slot++;
@@ -1636,17 +1737,18 @@ cudaError_t launch_iota(uint32_t *v, uint32_t n, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-__global__ void pack_hits_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t qbase, kmcpg_hit *__restrict__ out) {
+__global__ void pack_hits_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, uint32_t qbase, int target_bits,
+                                 kmcpg_hit *__restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t k = keys[i];
     kmcpg_hit h;
-    h.query = (uint32_t)(k >> 32) + qbase; h.target = (uint32_t)k; h.count = vals[i];
+    h.query = (uint32_t)(k >> target_bits) + qbase; h.target = (uint32_t)(k & ((1ull << target_bits) - 1)); h.count = vals[i];
     out[i] = h;
 }
-cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint32_t qbase, kmcpg_hit *out, cudaStream_t st) {
+cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint32_t qbase, int target_bits, kmcpg_hit *out, cudaStream_t st) {
     if (!n) return cudaSuccess;
-    pack_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, vals, n, qbase, out);
+    pack_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, vals, n, qbase, target_bits, out);
     return cudaGetLastError();
 }
 

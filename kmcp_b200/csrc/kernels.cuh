@@ -51,6 +51,9 @@ struct SelectArgs {
 cudaError_t launch_select(const SelectArgs &a, cudaStream_t st);
 cudaError_t launch_slot_bounds(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *slot_cnt, cudaStream_t st);
 cudaError_t launch_hash(const HashArgs &a, cudaStream_t st);
+// plain k-mers of short reads (every mate at most HASH_GROUP_MAX_KMERS k-mers, no FracMinHash cut, not raw): eight lanes per query
+constexpr uint32_t HASH_GROUP_MAX_KMERS = 512;
+cudaError_t launch_hash_groups(const HashArgs &a, cudaStream_t st);
 // long sequences (genomes, long reads): warp per 4096-position tile + gather, same results in the same order
 constexpr uint32_t HASH_TILE_POS = 4096;
 cudaError_t launch_tiles_per_seq(const uint64_t *seq_off, uint32_t n_seqs, int k, uint64_t *cnt, cudaStream_t st);
@@ -102,7 +105,8 @@ struct ProbeArgs {
     const uint32_t *thresh;     // per query
     uint32_t n_queries;
     int paired;
-    uint64_t *hit_keys;         // query<<32 | global target
+    uint64_t *hit_keys;         // query << target_bits | global target: only as many key bits as the hit sort has to look at
+    int target_bits;            // bits of the largest global target index of the database (<= 32)
     uint32_t *hit_vals;         // matched k-mers
     unsigned long long *hit_count;
     unsigned long long *task_counter;   // zeroed before the launch: next task of the long-query kernels (planes > 8)
@@ -131,7 +135,7 @@ cudaError_t launch_unpitch(const uint8_t *src, uint8_t *dst, uint64_t n_rows, ui
                            cudaStream_t st);
 cudaError_t launch_iota(uint32_t *v, uint32_t n, cudaStream_t st);
 // sorted (key,val) pairs → kmcpg_hit records, query index rebased by query_base
-cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint32_t query_base, kmcpg_hit *out,
+cudaError_t launch_pack_hits(const uint64_t *keys, const uint32_t *vals, uint64_t n, uint32_t query_base, int target_bits, kmcpg_hit *out,
                              cudaStream_t st);
 
 // ---- synthetic data + device index builder (synth.cu) ---------------------------------------------------
