@@ -903,6 +903,46 @@ __device__ __forceinline__ void load_rows(Slab<W> (&r)[PROBE_ROWS], const LocT (
     }
 }
 
+// ---- h > 1, raw double buffering (VAR 3): the h rows of a k-mer must be AND-ed before they are counted, so keeping only the AND-ed rows of
+// the next group in registers (VAR 2) makes every group wait for its own loads.  Here the RAW rows of the next group (8·h slabs) stay in
+// flight while the current group's raw rows are AND-ed and counted.  The registers for that come from the row indices: a lane keeps only
+// its share of them (entry e of the 8·h lives in lane e % GF, coalesced u32 loads) and the group hands them round by shuffle when the
+// loads are issued — never a private copy of all 8·h.  Full lane groups only (GF lanes = rows of at least GF slabs).
+template <int H, int GF>
+__device__ __forceinline__ void load_shared_locs(uint32_t (&mine)[(PROBE_ROWS * H + GF - 1) / GF], const uint32_t *__restrict__ lp32, uint32_t i, uint32_t n, uint32_t gl) {
+    constexpr int NL = PROBE_ROWS * H, R = (NL + GF - 1) / GF;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const uint32_t e = (uint32_t)r * GF + gl;
+        mine[r] = (e < (uint32_t)NL && i + e / H < n) ? __ldg(lp32 + (uint64_t)i * H + e) : 0xFFFFFFFFu;
+    }
+}
+template <int H, int W, int GF>
+__device__ __forceinline__ void issue_raw_rows(Slab<W> (&t)[PROBE_ROWS * H], const uint32_t (&mine)[(PROBE_ROWS * H + GF - 1) / GF], const uint8_t *__restrict__ colbase,
+                                               uint32_t pitch, bool lane_ok, uint32_t gmask, int gbase) {
+#pragma unroll
+    for (int e = 0; e < PROBE_ROWS * H; e++) {
+        const uint32_t loc = __shfl_sync(gmask, mine[e / GF], gbase + (e % GF));
+        if (lane_ok && loc != 0xFFFFFFFFu) t[e] = ld_slab<W>(colbase + (uint64_t)loc * pitch);
+        else {
+#pragma unroll
+            for (int w = 0; w < W; w++) t[e].v[w] = 0;
+        }
+    }
+}
+template <int H, int W>
+__device__ __forceinline__ void and_raw_rows(Slab<W> (&r)[PROBE_ROWS], const Slab<W> (&t)[PROBE_ROWS * H]) {
+#pragma unroll
+    for (int u = 0; u < PROBE_ROWS; u++)
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            uint32_t v = t[u * H].v[w];
+#pragma unroll
+            for (int h = 1; h < H; h++) v &= t[u * H + h].v[w];             // pand, U:6639-6645
+            r[u].v[w] = v;
+        }
+}
+
 // Harley–Seal: 8 one-bit inputs + planes 0..2 → planes 0..2 and one weight-8 carry rippled into planes 3..7
 template <int W>
 __device__ __forceinline__ void csa8(uint32_t (&c)[8][W], const Slab<W> (&r)[PROBE_ROWS]) {
@@ -1054,6 +1094,38 @@ __global__ void __launch_bounds__(PROBE_THREADS, MINB) probe_kernel(ProbeArgs a)
                     KMCPG_ROWS(r);
                     KMCPG_LOCS(i + PROBE_ROWS);
                     add8(r);
+                }
+            } else if (VAR == 4) {
+                // VAR 1 with shared row indices: the 8·h indices never sit in every lane's registers, which leaves room for a third CTA per SM
+                if constexpr (SRC == 0 && sizeof(LocT) == 4) {
+                    constexpr int RS = (PROBE_ROWS * H + GF - 1) / GF;
+                    uint32_t mine[RS];
+                    Slab<W> t[PROBE_ROWS * H], r[PROBE_ROWS];
+                    load_shared_locs<H, GF>(mine, lp32, 0, n, gl);
+                    for (uint32_t i = 0; i < n; i += PROBE_ROWS) {
+                        issue_raw_rows<H, W, GF>(t, mine, colbase, a.pitch, lane_ok, gmask, gbase);
+                        load_shared_locs<H, GF>(mine, lp32, i + PROBE_ROWS, n, gl);
+                        and_raw_rows<H, W>(r, t);
+                        add8(r);
+                    }
+                }
+            } else if (VAR == 3) {
+                if constexpr (SRC == 0 && sizeof(LocT) == 4) {           // (instantiated for u32 indices from the locs kernel only)
+                    constexpr int RS = (PROBE_ROWS * H + GF - 1) / GF;
+                    uint32_t mine[RS];
+                    Slab<W> ta[PROBE_ROWS * H], tb[PROBE_ROWS * H], r[PROBE_ROWS];
+                    load_shared_locs<H, GF>(mine, lp32, 0, n, gl);
+                    issue_raw_rows<H, W, GF>(ta, mine, colbase, a.pitch, lane_ok, gmask, gbase);
+                    load_shared_locs<H, GF>(mine, lp32, PROBE_ROWS, n, gl);
+                    for (uint32_t i = 0; i < n; i += 2 * PROBE_ROWS) {
+                        issue_raw_rows<H, W, GF>(tb, mine, colbase, a.pitch, lane_ok, gmask, gbase);
+                        load_shared_locs<H, GF>(mine, lp32, i + 2 * PROBE_ROWS, n, gl);
+                        and_raw_rows<H, W>(r, ta);
+                        add8(r);
+                        issue_raw_rows<H, W, GF>(ta, mine, colbase, a.pitch, lane_ok, gmask, gbase);
+                        load_shared_locs<H, GF>(mine, lp32, i + 3 * PROBE_ROWS, n, gl);
+                        if (i + PROBE_ROWS < n) { and_raw_rows<H, W>(r, tb); add8(r); }
+                    }
                 }
             } else {
                 Slab<W> r0[PROBE_ROWS], r1[PROBE_ROWS];
@@ -1383,6 +1455,8 @@ static cudaError_t launch_probe_hp(const ProbeArgs &a, uint32_t blocks, cudaStre
             if (t.var == 1) return t.minb >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t, 0>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t, 0>(a, blocks, st);
         } else {
             if (t.w_h == 4) return t.minb_h >= 3 ? launch_probe_k<H, PH, 1, 3, 4, uint32_t, 0>(a, blocks, st) : launch_probe_k<H, PH, 1, 2, 4, uint32_t, 0>(a, blocks, st);
+            if (t.var_h == 3 && H < 4 && a.row_bytes > 8 * 8) return launch_probe_k<H, PH, 3, 2, 2, uint32_t, 0>(a, blocks, st);   // raw double buffering (full groups)
+            if (t.var_h == 4 && a.row_bytes > 8 * 8) return t.minb_h >= 3 ? launch_probe_k<H, PH, 4, 3, 2, uint32_t, 0>(a, blocks, st) : launch_probe_k<H, PH, 4, 2, 2, uint32_t, 0>(a, blocks, st);
             if (t.var_h == 2) return launch_probe_k<H, PH, 2, 2, 2, uint32_t, 0>(a, blocks, st);
             if (t.minb_h >= 3) return launch_probe_k<H, PH, 1, 3, 2, uint32_t, 0>(a, blocks, st);
         }
