@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: the KMCPG_PROBE_* knobs exist only in development builds of the library: make -C kmcp_b200/csrc clean all DEV=1
 # other BASELINE.json shapes through the same path (dev tool): h=3, many narrow blocks, long reads
 cd "$(dirname "$0")/.."
 echo "# C4-like: h=3, 8 blocks x 10k targets (fpr 0.3), 150 bp";  H=3 NG=8000 GL=400000 BS=10000 NR=200000 python tools/probe_one.py 2>&1 | tail -1
