@@ -32,6 +32,7 @@
 #include "nvtx_ranges.h"
 #include "../../include/kmcp_gpu.h"
 #include "fastx_reader.h"
+#include "tsv_format.h"
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -546,6 +547,12 @@ int run(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "index")) return index_main(argc, argv);
     if (argc > 1 && !strcmp(argv[1], "gzip-write")) return gzip_write_main(argc, argv);
     if (argc > 1 && !strcmp(argv[1], "gunzip")) return gunzip_main(argc, argv);
+    if (argc > 1 && !strcmp(argv[1], "fmt-selftest")) {        // kmcp-gpu fmt-selftest [n [seed]]: tsv_format.h against printf (host-only test)
+        const uint64_t n = argc > 2 ? strtoull(argv[2], nullptr, 10) : 2000000, seed = argc > 3 ? strtoull(argv[3], nullptr, 10) : 1;
+        const uint64_t bad = tsvfmt::selftest(n, seed);
+        printf("%llu mismatches in %llu values\n", (unsigned long long)bad, (unsigned long long)n);
+        return bad ? 1 : 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "parse")) return parse_main(argc, argv);
     Opts o;
     int ai = 1;
@@ -846,6 +853,7 @@ int run(int argc, char **argv) {
             std::vector<uint64_t> nmatched(FT, 0);
             auto fmt = [&](int t) {
                 char line[512];
+                static thread_local tsvfmt::E4Cache e4;                // the %.4e strings of the FPR values seen lately
                 std::string &out = text[t];
                 const uint32_t lo = (uint32_t)((uint64_t)nq * t / FT), hi = (uint32_t)((uint64_t)nq * (t + 1) / FT);
                 out.reserve((size_t)(hi - lo) * 96);
@@ -858,21 +866,43 @@ int run(int argc, char **argv) {
                     for (auto &r : job->res) hits += r.match_off[q + 1] - r.match_off[q];
                     if (hits == 0) {
                         if (!o.keep_unmatched) continue;
-                        int n = snprintf(line, sizeof(line), "\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%llu\n", r0.query_len[q], r0.n_kmers[q], r0.k_used[q],     // S:460-511
-                                         (unsigned long long)(bt.b.first_query + q));
+                        char *p = line;                                   // S:460-511: "\t%d\t%d\t0\t0\t\t-1\t0\t0\t%d\t0\t0\t0\t0\t%d\n"
+                        *p++ = '\t'; p = tsvfmt::put_int(p, r0.query_len[q]);
+                        *p++ = '\t'; p = tsvfmt::put_int(p, r0.n_kmers[q]);
+                        memcpy(p, "\t0\t0\t\t-1\t0\t0\t", 13); p += 13;
+                        p = tsvfmt::put_int(p, r0.k_used[q]);
+                        memcpy(p, "\t0\t0\t0\t0\t", 9); p += 9;
+                        p = tsvfmt::put_uint(p, bt.b.first_query + q);
+                        *p++ = '\n';
+                        const int n = (int)(p - line);
                         out.append(idp, idn); out.append(line, (size_t)n);
                         continue;
                     }
                     nmatched[t]++;
                     auto put = [&](const kmcpg_results &r, const Db &db, const kmcpg_match &m) {
+                        // S:517-575: "%s\t%d\t%d\t%.4e\t%d\t%s\t%d\t%d\t%d\t%d\t%d\t%.4f\t%.4f\t%.4f\t%d\n", by hand (tsv_format.h: byte for byte what printf prints)
                         const kmcpg_target_t &tg = db.targets[m.target];
                         const std::string *mp = db.mapped[m.target];
-                        int n1 = snprintf(line, sizeof(line), "\t%d\t%d\t%.4e\t%llu\t", r.query_len[q], r.n_kmers[q], m.fpr, (unsigned long long)hits);
-                        out.append(idp, idn); out.append(line, (size_t)n1);
+                        char *p = line;
+                        *p++ = '\t'; p = tsvfmt::put_int(p, r.query_len[q]);
+                        *p++ = '\t'; p = tsvfmt::put_int(p, r.n_kmers[q]);
+                        *p++ = '\t'; p = e4.put(p, m.fpr);
+                        *p++ = '\t'; p = tsvfmt::put_uint(p, hits);
+                        *p++ = '\t';
+                        out.append(idp, idn); out.append(line, (size_t)(p - line));
                         if (mp) out.append(*mp); else out.append(tg.name);
-                        int n2 = snprintf(line, sizeof(line), "\t%u\t%u\t%llu\t%d\t%u\t%.4f\t%.4f\t%.4f\t%llu\n", tg.index & 0xFFFFu, tg.index >> 16,          // S:532-539
-                                          (unsigned long long)tg.genome_size, r.k_used[q], m.count, m.qcov, m.tcov, m.jacc, (unsigned long long)(bt.b.first_query + q));
-                        out.append(line, (size_t)n2);
+                        p = line;
+                        *p++ = '\t'; p = tsvfmt::put_uint(p, tg.index & 0xFFFFu);                               // S:532-539
+                        *p++ = '\t'; p = tsvfmt::put_uint(p, tg.index >> 16);
+                        *p++ = '\t'; p = tsvfmt::put_uint(p, tg.genome_size);
+                        *p++ = '\t'; p = tsvfmt::put_int(p, r.k_used[q]);
+                        *p++ = '\t'; p = tsvfmt::put_uint(p, m.count);
+                        *p++ = '\t'; p = tsvfmt::put_f4(p, m.qcov);
+                        *p++ = '\t'; p = tsvfmt::put_f4(p, m.tcov);
+                        *p++ = '\t'; p = tsvfmt::put_f4(p, m.jacc);
+                        *p++ = '\t'; p = tsvfmt::put_uint(p, bt.b.first_query + q);
+                        *p++ = '\n';
+                        out.append(line, (size_t)(p - line));
                     };
                     if (job->res.size() == 1) {
                         for (uint64_t i = r0.match_off[q]; i < r0.match_off[q + 1]; i++) put(r0, dbs[0], r0.matches[i]);

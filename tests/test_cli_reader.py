@@ -421,3 +421,12 @@ def test_bytes_behind_the_last_gzip_member_are_a_read_error(tmp_path, threads):
             for _ in api.read_batches([p], **kw):
                 pass
         assert "gzip: invalid header" in str(e.value)
+
+
+def test_tsv_number_formatting_is_what_printf_prints():
+    """kmcp_b200/csrc/tsv_format.h (the hand-written %.4f / %.4e / %d of the result table) against snprintf: uniform values, ratios of
+    small integers, every kind of rounding tie of the fourth decimal and its neighbours, tiny and large values"""
+    for seed in (1, 2, 3):
+        p = subprocess.run([EXE, "fmt-selftest", "1500000", str(seed)], capture_output=True, timeout=300)
+        assert p.returncode == 0, p.stdout.decode() + p.stderr.decode()
+        assert p.stdout.decode().startswith("0 mismatches")
