@@ -247,8 +247,8 @@ def run_reference(args, rank, world, stage=stage_in_helper_process):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u8 bitset",
-        "data": "synthetic", "config": {"workload": workload_name(), "reads_per_step_cpu_sample": step_reads, "db_built_by": built_by,
-                                        "blocks_searched": world,
+        "data": "synthetic", "config": {"workload": workload_name(), "reads_per_step": READS_PER_STEP, "targets_total": BLOCK_SIZE * world,
+                                        "reads_per_step_cpu_sample": step_reads, "db_built_by": built_by, "blocks_searched": world,
                                         "multi_gpu_units": "value counts read×shard probes (every read against each of the %d 10k-target blocks)" % world if world > 1 else "reads"},
         "job_reads_per_s": step_reads * args.steps / dt,
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port",
