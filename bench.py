@@ -338,7 +338,11 @@ def main():
     stream = torch.cuda.Stream()
     ctx = api.Context(local_rank)
     ctx.set_stream(stream.cuda_stream)
-    run_id = "kmcpb_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid() if world > 1 else os.getpid())
+    run_id = "kmcpb_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getpid())        # names the shared-memory segments of this run
+    if world > 1:
+        box = [run_id]
+        dist.broadcast_object_list(box, src=0)          # every rank uses rank 0's id, however the ranks were launched
+        run_id = box[0]
 
     def barrier():
         torch.cuda.synchronize()
