@@ -125,7 +125,7 @@ typedef struct {
     kmcpg_hit *hits;       /* every (query,target) with count >= min_matched and count > n*min_query_cov, sorted by (query,target) */
     /* device-side timing of this call (CUDA events on the library's streams), milliseconds */
     float ms_hash;    /* slot scan + hash (+ sort/unique) + per-query verdict */
-    float ms_locs;    /* code → row index kernels */
+    float ms_locs;    /* always 0 since ABI 2: the row-index kernels run on the query-preparation stream and are part of ms_hash's stage */
     float ms_probe;   /* Σ durations of the probe kernel launches ONLY (events bracketing each launch) */
     float ms_total;   /* host wall clock of the call */
     uint32_t probe_launches;
